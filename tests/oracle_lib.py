@@ -1,0 +1,247 @@
+"""ctypes loader for the CPU oracle (oracle/liblmono_oracle.so).  TEST INFRASTRUCTURE ONLY:
+imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs; never by lmono_b200/."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SO = os.path.join(_ROOT, "oracle", "liblmono_oracle.so")
+
+
+class Pose(C.Structure):
+    _fields_ = [("q", C.c_double * 4), ("t", C.c_double * 3)]
+
+    @staticmethod
+    def make(q=(0, 0, 0, 1), t=(0, 0, 0)):
+        p = Pose()
+        p.q[:] = [float(v) for v in q]
+        p.t[:] = [float(v) for v in t]
+        return p
+
+    def as_np(self):
+        return np.array(self.q[:]), np.array(self.t[:])
+
+
+class Factor(C.Structure):
+    _fields_ = [("type", C.c_int32), ("pad", C.c_int32), ("p", C.c_double * 3),
+                ("a", C.c_double * 3), ("b", C.c_double * 3)]
+
+
+FACTOR_DTYPE = np.dtype([("type", "<i4"), ("pad", "<i4"), ("p", "<f8", 3), ("a", "<f8", 3), ("b", "<f8", 3)])
+
+
+class SolveSummary(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("num_successful", C.c_int32), ("termination", C.c_int32),
+                ("num_factors", C.c_int32), ("initial_cost", C.c_double), ("final_cost", C.c_double)]
+
+
+class MapReport(C.Structure):
+    _fields_ = [("corner_from_map", C.c_int32), ("surf_from_map", C.c_int32),
+                ("corner_stack", C.c_int32), ("surf_stack", C.c_int32),
+                ("corner_num", C.c_int32 * 2), ("surf_num", C.c_int32 * 2),
+                ("optimized", C.c_int32), ("center_cube", C.c_int32 * 3), ("cen", C.c_int32 * 3),
+                ("solve", SolveSummary * 2),
+                ("ms_shift", C.c_double), ("ms_tree", C.c_double), ("ms_assoc", C.c_double),
+                ("ms_solver", C.c_double), ("ms_add", C.c_double), ("ms_filter", C.c_double),
+                ("ms_whole", C.c_double)]
+
+
+class ScanReport(C.Structure):
+    _fields_ = [("n_in", C.c_int32), ("n_kept", C.c_int32), ("n_sharp", C.c_int32),
+                ("n_less_sharp", C.c_int32), ("n_flat", C.c_int32), ("n_less_flat", C.c_int32),
+                ("ring_start", C.c_int32 * 64), ("ring_end", C.c_int32 * 64),
+                ("start_ori", C.c_float), ("end_ori", C.c_float), ("min_margin_ok", C.c_int32)]
+
+
+class OdomReport(C.Structure):
+    _fields_ = [("inited", C.c_int32), ("corner_corr", C.c_int32 * 2), ("plane_corr", C.c_int32 * 2),
+                ("solve", SolveSummary * 2),
+                ("ms_assoc", C.c_double), ("ms_solver", C.c_double), ("ms_whole", C.c_double)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("k1", C.c_double), ("k2", C.c_double), ("p1", C.c_double), ("p2", C.c_double),
+                ("width", C.c_int32), ("height", C.c_int32), ("kernel_type", C.c_int32),
+                ("kernel_size", C.c_int32), ("blur_type", C.c_int32)]
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with gcc/g++ (seconds)."""
+    d = os.path.join(_ROOT, "oracle")
+    srcs = [os.path.join(d, f) for f in os.listdir(d) if f.endswith((".c", ".cpp", ".h", "Makefile"))]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+        subprocess.run(["make", "-s", "-C", d], check=True)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.lmono_cpu_mapper_create.restype = C.c_void_p
+        _lib.lmono_cpu_kdtree_build.restype = C.c_void_p
+        if hasattr(_lib, "lmono_cpu_odom_create"):
+            _lib.lmono_cpu_odom_create.restype = C.c_void_p
+    return _lib
+
+
+def _f32(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def voxel_grid(pts, leaf, order_mode=0):
+    pts = _f32(pts).reshape(-1, 4)
+    out = np.zeros_like(pts)
+    n = C.c_int(0)
+    lib().lmono_cpu_voxel_grid(_p(pts), len(pts), C.c_float(leaf), order_mode, _p(out), C.byref(n))
+    return out[: n.value].copy()
+
+
+def knn_brute(pts, queries, k=5):
+    pts = _f32(pts).reshape(-1, 4)
+    queries = _f32(queries).reshape(-1, 4)
+    idx = np.zeros((len(queries), k), np.int32)
+    d2 = np.zeros((len(queries), k), np.float32)
+    lib().lmono_cpu_knn_brute(_p(pts), len(pts), _p(queries), len(queries), k, _p(idx), _p(d2))
+    return idx, d2
+
+
+def knn_kdtree(pts, queries, k=5):
+    pts = _f32(pts).reshape(-1, 4)
+    queries = _f32(queries).reshape(-1, 4)
+    idx = np.zeros((len(queries), k), np.int32)
+    d2 = np.zeros((len(queries), k), np.float32)
+    L = lib()
+    t = C.c_void_p(L.lmono_cpu_kdtree_build(_p(pts), len(pts)))
+    L.lmono_cpu_kdtree_knn(t, _p(queries), len(queries), k, _p(idx), _p(d2))
+    L.lmono_cpu_kdtree_free(t)
+    return idx, d2
+
+
+def eigh3(A):
+    A = np.ascontiguousarray(A, np.float64).reshape(9)
+    w = np.zeros(3)
+    V = np.zeros(9)
+    rc = lib().lmono_cpu_eigh3(_p(A), _p(w), _p(V))
+    return w, V.reshape(3, 3), rc
+
+
+def colpiv_solve_5x3(A, b):
+    A = np.ascontiguousarray(A, np.float64).reshape(15)
+    b = np.ascontiguousarray(b, np.float64).reshape(5)
+    x = np.zeros(3)
+    lib().lmono_cpu_colpiv_qr_solve_5x3(_p(A), _p(b), _p(x))
+    return x
+
+
+def normal_eq(factors, q, t):
+    f = np.ascontiguousarray(factors, FACTOR_DTYPE)
+    H = np.zeros(36)
+    g = np.zeros(6)
+    cost = C.c_double(0)
+    pose = Pose.make(q, t)
+    lib().lmono_cpu_normal_eq(_p(f), len(f), C.byref(pose), _p(H), _p(g), C.byref(cost))
+    return H.reshape(6, 6), g, cost.value
+
+
+def lm_solve(factors, q, t, max_iter=4):
+    f = np.ascontiguousarray(factors, FACTOR_DTYPE)
+    pose = Pose.make(q, t)
+    s = SolveSummary()
+    lib().lmono_cpu_lm_solve(_p(f), len(f), C.byref(pose), max_iter, C.byref(s))
+    qo, to = pose.as_np()
+    return qo, to, s
+
+
+class Mapper:
+    """Oracle laserMapping state (Aloam/src/laserMapping.cpp globals)."""
+
+    def __init__(self, line_res=0.4, plane_res=0.8, order_mode=0, use_kdtree=1):
+        self.L = lib()
+        self.h = C.c_void_p(self.L.lmono_cpu_mapper_create(C.c_float(line_res), C.c_float(plane_res), order_mode, use_kdtree))
+
+    def close(self):
+        if self.h:
+            self.L.lmono_cpu_mapper_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def import_points(self, which, pts):
+        pts = _f32(pts).reshape(-1, 4)
+        self.L.lmono_cpu_mapper_import(self.h, which, _p(pts), len(pts))
+
+    def export(self, which, scope=1):
+        n = self.L.lmono_cpu_mapper_export(self.h, which, scope, None, 0)
+        out = np.zeros((max(n, 1), 4), np.float32)
+        self.L.lmono_cpu_mapper_export(self.h, which, scope, _p(out), n)
+        return out[:n]
+
+    def get_state(self):
+        p = Pose()
+        cen = (C.c_int32 * 3)()
+        self.L.lmono_cpu_mapper_get_state(self.h, C.byref(p), cen)
+        q, t = p.as_np()
+        return q, t, list(cen)
+
+    def set_state(self, q, t):
+        p = Pose.make(q, t)
+        self.L.lmono_cpu_mapper_set_state(self.h, C.byref(p))
+
+    def prepare_window(self, t_w_curr):
+        t = (C.c_double * 3)(*[float(v) for v in t_w_curr])
+        return self.L.lmono_cpu_mapper_prepare_window(self.h, t)
+
+    def knn5(self, which, queries_world):
+        qw = _f32(queries_world).reshape(-1, 4)
+        idx = np.zeros((len(qw), 5), np.int32)
+        d2 = np.zeros((len(qw), 5), np.float32)
+        self.L.lmono_cpu_mapper_knn5(self.h, which, _p(qw), len(qw), _p(idx), _p(d2))
+        return idx, d2
+
+    def associate(self, corner_stack, surf_stack, q, t):
+        cs = _f32(corner_stack).reshape(-1, 4)
+        ss = _f32(surf_stack).reshape(-1, 4)
+        cap = len(cs) + len(ss)
+        out = np.zeros(max(cap, 1), FACTOR_DTYPE)
+        nc = C.c_int32(0)
+        ns = C.c_int32(0)
+        pose = Pose.make(q, t)
+        nf = self.L.lmono_cpu_mapper_associate(self.h, _p(cs), len(cs), _p(ss), len(ss), C.byref(pose),
+                                               _p(out), cap, C.byref(nc), C.byref(ns))
+        return out[:nf], nc.value, ns.value
+
+    def step(self, corner_last, surf_last, q_odom, t_odom, full_res=None):
+        cl = _f32(corner_last).reshape(-1, 4)
+        sl = _f32(surf_last).reshape(-1, 4)
+        odom = Pose.make(q_odom, t_odom)
+        w = Pose()
+        rep = MapReport()
+        fr = None
+        nfull = 0
+        if full_res is not None:
+            fr = _f32(full_res).reshape(-1, 4).copy()
+            nfull = len(fr)
+        self.L.lmono_cpu_map_step(self.h, _p(cl), len(cl), _p(sl), len(sl), C.byref(odom), C.byref(w),
+                                  C.byref(rep), _p(fr) if fr is not None else None, nfull)
+        q, t = w.as_np()
+        return q, t, rep, fr
