@@ -1,0 +1,213 @@
+/*
+ * lmono.h -- C ABI of liblmono_b200.so: the B200-native (sm_100a CUDA) implementation of
+ * LMONO-Fusion's LiDAR registration hot path (A-LOAM scanRegistration -> laserOdometry ->
+ * laserMapping, plus the mono_lidar_mapping LiDAR->camera colour projection).
+ *
+ * The reference (bobocode/lmono) exposes NO plugin/FFI interface for this path: the hot
+ * loops are inlined in the ROS node mains.  Each entry point below
+ * therefore replaces a block of a reference node's callback, cited as file:line relative
+ * to the reference tree; nodes/ holds the patched node sources that call them and
+ * INTEGRATION.md shows the binding.  Plain C: opaque handle, POD structs, caller-owned
+ * host buffers, no exceptions, no torch types.
+ *
+ * Conventions: return 0 = OK, negative = error (lmono_strerror).  "Not enough map points"
+ * and "<10 correspondences" are statuses in the report, not errors (they mirror
+ * Aloam/src/laserMapping.cpp:730-733 and Aloam/src/laserOdometry.cpp:488-491).  One ctx is
+ * single-caller (one process() thread per node, laserMapping.cpp:934); several ctxs (one
+ * per sequence / GPU) are independent.  There is no CPU fallback: every entry point fails
+ * with LMONO_E_CUDA if the device is unusable.
+ */
+#ifndef LMONO_H
+#define LMONO_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LMONO_ABI_VERSION 1
+
+enum {
+  LMONO_OK = 0,
+  LMONO_E_ARG = -1,          /* bad argument */
+  LMONO_E_CAPACITY = -2,     /* an output buffer or internal capacity is too small */
+  LMONO_E_CUDA = -3,         /* CUDA runtime error (latched in the ctx) */
+  LMONO_E_STATE = -4,        /* call not valid in the current state */
+  LMONO_E_DEVICE = -5        /* device-side fault flag raised by a kernel (see lmono_last_fault) */
+};
+
+typedef struct lmono_ctx lmono_ctx;
+
+/* Host point cloud, array of structs.  x,y,z are floats at byte offsets 0,4,8 of each
+ * record; intensity is a float at intensity_offset (or absent if < 0).  pcl::PointXYZI is
+ * {stride 32, intensity_offset 16} (Aloam/include/aloam_velodyne/common.h:43);
+ * pcl::PointXYZ is {16, -1}; KITTI .bin (Aloam/src/kittiHelper.cpp:25-35) is {16, 12}. */
+typedef struct {
+  const void* base;
+  int32_t n;
+  int32_t stride_bytes;
+  int32_t intensity_offset;
+} lmono_cloud_view;
+
+/* Caller-allocated output cloud in the same layout; callee fills n_out.  If capacity is
+ * too small the call returns LMONO_E_CAPACITY and n_out holds the required size. */
+typedef struct {
+  void* base;
+  int32_t capacity;
+  int32_t stride_bytes;
+  int32_t intensity_offset;
+  int32_t n_out;
+} lmono_cloud_out;
+
+typedef struct { double q[4]; /* x,y,z,w */ double t[3]; } lmono_pose;
+
+/* Parameters = the reference's ROS params / compile-time constants, same names. */
+typedef struct {
+  int32_t scan_line;                 /* scanRegistration.cpp:466  (16/32/64) */
+  float   minimum_range;             /* scanRegistration.cpp:468 */
+  float   mapping_line_resolution;   /* laserMapping.cpp:902 */
+  float   mapping_plane_resolution;  /* laserMapping.cpp:903 */
+  int32_t mapping_skip_frame;        /* laserOdometry.cpp:191 */
+  /* capacities (0 = default) */
+  int32_t max_sweep_points;          /* raw points per sweep            (default 262144) */
+  int32_t max_feature_points;        /* points per feature cloud        (default 131072) */
+  int32_t cube_capacity_corner;      /* points per 50 m cube, corner map (default 16384) */
+  int32_t cube_capacity_surf;        /* points per 50 m cube, surf map   (default 49152) */
+  int32_t max_cubes_corner;          /* non-empty cubes held at once     (default 768) */
+  int32_t max_cubes_surf;            /*                                  (default 768) */
+  int32_t image_width, image_height; /* colour projection raster (default 1241 x 376) */
+  int32_t reserved[8];
+} lmono_params;
+
+void lmono_default_params(lmono_params* p);
+
+typedef struct {
+  int32_t iterations, num_successful, termination, num_factors;
+  double initial_cost, final_cost;
+} lmono_solve_summary;     /* termination: 0 max-iter 1 gradient 2 parameter 3 function 4 radius 5 failure 6 none */
+
+/* laserMapping report: the numbers the reference prints (laserMapping.cpp:552-553,707-708). */
+typedef struct {
+  int32_t corner_from_map, surf_from_map;   /* :538-539 */
+  int32_t corner_stack, surf_stack;         /* :545,550 */
+  int32_t corner_num[2], surf_num[2];       /* :620,685 per outer iteration */
+  int32_t optimized;                        /* :554 gate (0 => "Map corner and surf num are not enough") */
+  int32_t center_cube[3];
+  int32_t cen[3];                           /* laserCloudCenWidth/Height/Depth after the shift */
+  lmono_solve_summary solve[2];
+  float ms_gpu;                             /* device time of the step (CUDA events) */
+} lmono_map_report;
+
+typedef struct {
+  int32_t inited;                           /* 0 on the first frame (laserOdometry.cpp:267-271) */
+  int32_t corner_corr[2], plane_corr[2];    /* :382,480 */
+  lmono_solve_summary solve[2];
+  float ms_gpu;
+} lmono_odom_report;
+
+typedef struct {
+  int32_t n_in, n_kept;
+  int32_t n_sharp, n_less_sharp, n_flat, n_less_flat;
+  int32_t ring_start[64], ring_end[64];     /* scanStartInd / scanEndInd (scanRegistration.cpp:249-251) */
+  float start_ori, end_ori;
+  float ms_gpu;
+} lmono_scan_report;
+
+typedef struct {
+  double fx, fy, cx, cy, k1, k2, p1, p2;    /* camera_models PinholeCamera parameters */
+  int32_t width, height;
+  int32_t kernel_type;                       /* 0 FULL 1 CROSS 2 ELLIPSE (map_build_node.cc:278) */
+  int32_t kernel_size;
+  int32_t blur_type;                         /* 0 bilateral 1 gaussian */
+} lmono_pinhole;
+
+/* ------------------------------------------------------------------ lifecycle */
+/* stream: a cudaStream_t (as void*) the ctx should enqueue on, or NULL to create its own. */
+int  lmono_create(int device, const lmono_params* params, void* stream, lmono_ctx** out);
+void lmono_destroy(lmono_ctx* ctx);
+const char* lmono_strerror(int code);
+/* device-side fault bits raised since the last call (0 = none); clears them. */
+int  lmono_last_fault(lmono_ctx* ctx, uint32_t* bits);
+int  lmono_sync(lmono_ctx* ctx);
+/* number of kernels this ctx has launched so far (bench.py reports it as gpu_launches). */
+int64_t lmono_launch_count(const lmono_ctx* ctx);
+
+/* ------------------------------------------------------------------ L3: laserMapping */
+/* Replaces Aloam/src/laserMapping.cpp:307-801 (+ :838-842 when full_res is given):
+ * transformAssociateToMap, cube-window shift, local-map gather, VoxelGrid of the incoming
+ * features, 2 x (5-NN + line/plane fit + LM solve), transformUpdate, map insertion and
+ * per-cube VoxelGrid refilter.  corner_last / surf_last are the odometry node's
+ * /laser_cloud_corner_last and /laser_cloud_surf_last clouds (sensor frame). */
+int lmono_map_step(lmono_ctx* ctx, lmono_cloud_view corner_last, lmono_cloud_view surf_last,
+                   const lmono_pose* wodom_curr, lmono_pose* w_curr /*out*/,
+                   lmono_pose* wmap_wodom /*out, may be NULL*/, lmono_map_report* report /*may be NULL*/,
+                   lmono_cloud_view full_res /*n=0 to skip*/, lmono_cloud_out* registered /*may be NULL*/);
+
+/* Device-resident variant: inputs are packed XYZI float4 arrays already in HBM; the call
+ * only enqueues work on the ctx stream.  lmono_map_collect() synchronises and returns the
+ * results of the most recent step. */
+int lmono_map_step_device(lmono_ctx* ctx, const void* d_corner_xyzi, int32_t n_corner,
+                          const void* d_surf_xyzi, int32_t n_surf, const lmono_pose* wodom_curr);
+int lmono_map_collect(lmono_ctx* ctx, lmono_pose* w_curr, lmono_pose* wmap_wodom, lmono_map_report* report);
+
+/* q_wmap_wodom / t_wmap_wodom (laserMapping.cpp:116-117) */
+int lmono_map_get_state(lmono_ctx* ctx, lmono_pose* wmap_wodom, int32_t cen[3]);
+int lmono_map_set_state(lmono_ctx* ctx, const lmono_pose* wmap_wodom);
+
+/* Map exchange (the publishers at laserMapping.cpp:806-836 and checkpoint/restore).
+ * which: 0 corner, 1 surf.  scope: 0 = the <=75 cubes of the current window in the order of
+ * :512-537, 1 = all 4851 cubes in the order of :826-830. */
+int lmono_map_export(lmono_ctx* ctx, int which, int scope, lmono_cloud_out* out);
+/* Load world-frame points into an EMPTY map: every point goes to its cube
+ * (laserMapping.cpp:741-758 arithmetic) and every cube is VoxelGrid-filtered (:788-801). */
+int lmono_map_import(lmono_ctx* ctx, int which, lmono_cloud_view pts_world);
+int lmono_map_clear(lmono_ctx* ctx);
+
+/* ------------------------------------------------------------------ test / bench hooks */
+/* Positions the cube window for a pose translation (laserMapping.cpp:312-539). */
+int lmono_map_prepare_window(lmono_ctx* ctx, const double t_w_curr[3]);
+/* 5-NN of world-frame queries against the current window (replaces the
+ * kdtree*FromMap->nearestKSearch calls at laserMapping.cpp:582,648).  idx are positions in
+ * the :533-537 concatenation; a query whose 5th neighbour is not within d2 < 1.0 gets
+ * idx = -1 / d2 = +inf in the slots that could not be proven. */
+int lmono_knn5(lmono_ctx* ctx, int which, lmono_cloud_view queries_world, int32_t* idx, float* d2);
+int lmono_knn5_device(lmono_ctx* ctx, int which, const void* d_queries_xyzi, int32_t n, void* d_idx, void* d_d2);
+/* One association pass (laserMapping.cpp:577-687) at pose w_curr followed by one
+ * evaluation of the 6x6 normal equations (H = J^T J, g = J^T r, cost) of the resulting
+ * factors, Huber(0.1) corrected, in the tangent space (rotation, translation). */
+int lmono_map_normal_eq(lmono_ctx* ctx, lmono_cloud_view corner_stack, lmono_cloud_view surf_stack,
+                        const lmono_pose* w_curr, double H[36], double g[6], double* cost,
+                        int32_t* n_corner, int32_t* n_surf);
+/* pcl::VoxelGrid<PointXYZI> as configured by the reference (canonical index-order sums). */
+int lmono_voxel_grid(lmono_ctx* ctx, lmono_cloud_view in, float leaf, lmono_cloud_out* out);
+
+/* ------------------------------------------------------------------ L1: scanRegistration */
+/* Replaces Aloam/src/scanRegistration.cpp:132-408. */
+int lmono_scan_register(lmono_ctx* ctx, lmono_cloud_view raw, lmono_cloud_out* full,
+                        lmono_cloud_out* sharp, lmono_cloud_out* less_sharp,
+                        lmono_cloud_out* flat, lmono_cloud_out* less_flat,
+                        int32_t* labels /*may be NULL; one per point of `full`*/,
+                        lmono_scan_report* report);
+
+/* ------------------------------------------------------------------ L2: laserOdometry */
+/* Replaces Aloam/src/laserOdometry.cpp:265-568. */
+int lmono_odom_step(lmono_ctx* ctx, lmono_cloud_view sharp, lmono_cloud_view less_sharp,
+                    lmono_cloud_view flat, lmono_cloud_view less_flat,
+                    lmono_pose* last_curr /*out*/, lmono_pose* w_curr /*out*/, lmono_odom_report* report);
+int lmono_odom_reset(lmono_ctx* ctx);
+
+/* ------------------------------------------------------------------ L6: colour projection */
+/* Replaces mono_lidar_mapping/src/map_builder/Map_Builder.cc:224-245 (raster), :336-403
+ * (depthFill) and :275-322 (lift + world transform). */
+int lmono_project_color(lmono_ctx* ctx, lmono_cloud_view pts_cam, const uint8_t* bgr, int32_t step_bytes,
+                        const lmono_pinhole* cam, const lmono_pose* Q_T,
+                        uint8_t* depth_raw /*may be NULL*/, uint8_t* depth_filled /*may be NULL*/,
+                        float* cloud_cam_xyz /*may be NULL*/, float* cloud_world_xyz, uint8_t* cloud_rgb,
+                        int32_t capacity, int32_t* n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

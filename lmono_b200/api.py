@@ -1,0 +1,304 @@
+"""Host-side binding of liblmono_b200.so (include/lmono.h) over ctypes.
+
+The reference's host code is C++ inside ROS nodes (nodes/ holds the patched node sources
+that call the same C ABI); this module is the Python face used by tests/, bench.py and
+__graft_entry__.py.  Method names follow the reference stages:
+``scan_register`` (Aloam/src/scanRegistration.cpp laserCloudHandler), ``odom_step``
+(Aloam/src/laserOdometry.cpp main loop body), ``map_step`` (Aloam/src/laserMapping.cpp
+process()) and ``project_color`` (mono_lidar_mapping Map_Builder::associateToMap).
+
+There is no CPU fallback: loading fails loudly when the CUDA library has not been built,
+and every call raises LmonoError when the device is unusable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+_SO = os.path.join(_CSRC, "liblmono_b200.so")
+
+
+class LmonoError(RuntimeError):
+    def __init__(self, code, what=""):
+        self.code = code
+        msg = ""
+        try:
+            msg = lib().lmono_strerror(code).decode()
+        except Exception:
+            pass
+        super().__init__(f"lmono error {code} ({msg}) {what}")
+
+
+class CloudView(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("n", C.c_int32), ("stride_bytes", C.c_int32), ("intensity_offset", C.c_int32)]
+
+
+class CloudOut(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("capacity", C.c_int32), ("stride_bytes", C.c_int32),
+                ("intensity_offset", C.c_int32), ("n_out", C.c_int32)]
+
+
+class Pose(C.Structure):
+    _fields_ = [("q", C.c_double * 4), ("t", C.c_double * 3)]
+
+    @staticmethod
+    def make(q=(0, 0, 0, 1), t=(0, 0, 0)):
+        p = Pose()
+        p.q[:] = [float(v) for v in q]
+        p.t[:] = [float(v) for v in t]
+        return p
+
+    def as_np(self):
+        return np.array(self.q[:]), np.array(self.t[:])
+
+
+class Params(C.Structure):
+    _fields_ = [("scan_line", C.c_int32), ("minimum_range", C.c_float),
+                ("mapping_line_resolution", C.c_float), ("mapping_plane_resolution", C.c_float),
+                ("mapping_skip_frame", C.c_int32),
+                ("max_sweep_points", C.c_int32), ("max_feature_points", C.c_int32),
+                ("cube_capacity_corner", C.c_int32), ("cube_capacity_surf", C.c_int32),
+                ("max_cubes_corner", C.c_int32), ("max_cubes_surf", C.c_int32),
+                ("image_width", C.c_int32), ("image_height", C.c_int32),
+                ("reserved", C.c_int32 * 8)]
+
+
+class SolveSummary(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("num_successful", C.c_int32), ("termination", C.c_int32),
+                ("num_factors", C.c_int32), ("initial_cost", C.c_double), ("final_cost", C.c_double)]
+
+
+class MapReport(C.Structure):
+    _fields_ = [("corner_from_map", C.c_int32), ("surf_from_map", C.c_int32),
+                ("corner_stack", C.c_int32), ("surf_stack", C.c_int32),
+                ("corner_num", C.c_int32 * 2), ("surf_num", C.c_int32 * 2),
+                ("optimized", C.c_int32), ("center_cube", C.c_int32 * 3), ("cen", C.c_int32 * 3),
+                ("solve", SolveSummary * 2), ("ms_gpu", C.c_float)]
+
+
+class OdomReport(C.Structure):
+    _fields_ = [("inited", C.c_int32), ("corner_corr", C.c_int32 * 2), ("plane_corr", C.c_int32 * 2),
+                ("solve", SolveSummary * 2), ("ms_gpu", C.c_float)]
+
+
+class ScanReport(C.Structure):
+    _fields_ = [("n_in", C.c_int32), ("n_kept", C.c_int32), ("n_sharp", C.c_int32), ("n_less_sharp", C.c_int32),
+                ("n_flat", C.c_int32), ("n_less_flat", C.c_int32),
+                ("ring_start", C.c_int32 * 64), ("ring_end", C.c_int32 * 64),
+                ("start_ori", C.c_float), ("end_ori", C.c_float), ("ms_gpu", C.c_float)]
+
+
+class Pinhole(C.Structure):
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("k1", C.c_double), ("k2", C.c_double), ("p1", C.c_double), ("p2", C.c_double),
+                ("width", C.c_int32), ("height", C.c_int32), ("kernel_type", C.c_int32),
+                ("kernel_size", C.c_int32), ("blur_type", C.c_int32)]
+
+
+def build(force: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into csrc/liblmono_b200.so (nvcc cross-compiles
+    without a GPU)."""
+    srcs = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cu", ".cuh", "Makefile"))]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "lmono.h"))
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+        subprocess.run(["make", "-s", "-j8", "-C", _CSRC], check=True)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise ImportError(f"{_SO} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)")
+        L = C.CDLL(_SO)
+        L.lmono_strerror.restype = C.c_char_p
+        L.lmono_launch_count.restype = C.c_int64
+        L.lmono_launch_count.argtypes = [C.c_void_p]
+        L.lmono_create.argtypes = [C.c_int, C.POINTER(Params), C.c_void_p, C.POINTER(C.c_void_p)]
+        _lib = L
+    return _lib
+
+
+def _xyzi(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] != 4:
+        raise ValueError("expected float32 [n,4] x,y,z,intensity")
+    return a
+
+
+def view_of(a: np.ndarray) -> CloudView:
+    """CloudView over a float32 [n,4] (KITTI layout) or [n,8] (pcl::PointXYZI 32-byte) array."""
+    if a.dtype != np.float32 or a.ndim != 2 or not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("expected a C-contiguous float32 2-D array")
+    if a.shape[1] == 4:
+        return CloudView(a.ctypes.data, a.shape[0], 16, 12)
+    if a.shape[1] == 8:
+        return CloudView(a.ctypes.data, a.shape[0], 32, 16)
+    if a.shape[1] == 3:
+        return CloudView(a.ctypes.data, a.shape[0], 12, -1)
+    raise ValueError("unsupported point width")
+
+
+def _out(cap):
+    buf = np.zeros((max(cap, 1), 4), np.float32)
+    return buf, CloudOut(buf.ctypes.data, cap, 16, 12, 0)
+
+
+class Context:
+    """One lmono_ctx: owns the device-resident map and per-stage state of one sequence."""
+
+    def __init__(self, device: int = 0, stream=None, **params):
+        L = lib()
+        p = Params()
+        L.lmono_default_params(C.byref(p))
+        for k, v in params.items():
+            if not hasattr(p, k):
+                raise TypeError(f"unknown parameter {k}")
+            setattr(p, k, v)
+        self.params = p
+        self._h = C.c_void_p()
+        rc = L.lmono_create(device, C.byref(p), C.c_void_p(stream) if stream else None, C.byref(self._h))
+        if rc:
+            raise LmonoError(rc, "lmono_create")
+        self.L = L
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.L.lmono_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _chk(self, rc, what):
+        if rc:
+            raise LmonoError(rc, what)
+
+    # -- plumbing
+    def sync(self):
+        self._chk(self.L.lmono_sync(self._h), "sync")
+
+    def launch_count(self) -> int:
+        return int(self.L.lmono_launch_count(self._h))
+
+    def last_fault(self) -> int:
+        bits = C.c_uint32(0)
+        self._chk(self.L.lmono_last_fault(self._h, C.byref(bits)), "last_fault")
+        return bits.value
+
+    # -- laserMapping
+    def map_step(self, corner_last, surf_last, q_odom, t_odom, full_res=None):
+        cl = corner_last if corner_last.dtype == np.float32 and corner_last.flags["C_CONTIGUOUS"] else _xyzi(corner_last)
+        sl = surf_last if surf_last.dtype == np.float32 and surf_last.flags["C_CONTIGUOUS"] else _xyzi(surf_last)
+        odom = Pose.make(q_odom, t_odom)
+        w = Pose()
+        wm = Pose()
+        rep = MapReport()
+        reg = None
+        if full_res is not None:
+            fr = _xyzi(full_res)
+            buf, reg = _out(len(fr))
+            fv = view_of(fr)
+        else:
+            fv = CloudView(None, 0, 16, 12)
+        rc = self.L.lmono_map_step(self._h, view_of(cl), view_of(sl), C.byref(odom), C.byref(w), C.byref(wm),
+                                   C.byref(rep), fv, C.byref(reg) if reg is not None else None)
+        self._chk(rc, "map_step")
+        q, t = w.as_np()
+        return q, t, rep, (buf[: reg.n_out] if reg is not None else None)
+
+    def map_step_device(self, d_corner_ptr, n_corner, d_surf_ptr, n_surf, q_odom, t_odom):
+        odom = Pose.make(q_odom, t_odom)
+        self._chk(self.L.lmono_map_step_device(self._h, C.c_void_p(d_corner_ptr), n_corner, C.c_void_p(d_surf_ptr), n_surf,
+                                               C.byref(odom)), "map_step_device")
+
+    def map_collect(self):
+        w = Pose()
+        wm = Pose()
+        rep = MapReport()
+        self._chk(self.L.lmono_map_collect(self._h, C.byref(w), C.byref(wm), C.byref(rep)), "map_collect")
+        q, t = w.as_np()
+        return q, t, rep
+
+    def map_get_state(self):
+        p = Pose()
+        cen = (C.c_int32 * 3)()
+        self._chk(self.L.lmono_map_get_state(self._h, C.byref(p), cen), "map_get_state")
+        q, t = p.as_np()
+        return q, t, list(cen)
+
+    def map_set_state(self, q, t):
+        p = Pose.make(q, t)
+        self._chk(self.L.lmono_map_set_state(self._h, C.byref(p)), "map_set_state")
+
+    def map_import(self, which, pts):
+        pts = _xyzi(pts)
+        step = (1 << 21) - 1
+        if len(pts) > step:
+            raise ValueError("import at most 2^21-1 points per call")
+        self._chk(self.L.lmono_map_import(self._h, which, view_of(pts)), "map_import")
+
+    def map_export(self, which, scope=1):
+        cap = 1 << 16
+        while True:
+            buf, out = _out(cap)
+            rc = self.L.lmono_map_export(self._h, which, scope, C.byref(out))
+            if rc == -2:
+                cap = out.n_out
+                continue
+            self._chk(rc, "map_export")
+            return buf[: out.n_out].copy()
+
+    def map_clear(self):
+        self._chk(self.L.lmono_map_clear(self._h), "map_clear")
+
+    def map_prepare_window(self, t_w_curr):
+        t = (C.c_double * 3)(*[float(v) for v in t_w_curr])
+        self._chk(self.L.lmono_map_prepare_window(self._h, t), "map_prepare_window")
+
+    def knn5(self, which, queries_world):
+        q = _xyzi(queries_world)
+        idx = np.zeros((len(q), 5), np.int32)
+        d2 = np.zeros((len(q), 5), np.float32)
+        self._chk(self.L.lmono_knn5(self._h, which, view_of(q), idx.ctypes.data_as(C.c_void_p), d2.ctypes.data_as(C.c_void_p)), "knn5")
+        return idx, d2
+
+    def knn5_device(self, which, d_q_ptr, n, d_idx_ptr, d_d2_ptr):
+        self._chk(self.L.lmono_knn5_device(self._h, which, C.c_void_p(d_q_ptr), n, C.c_void_p(d_idx_ptr), C.c_void_p(d_d2_ptr)), "knn5_device")
+
+    def map_normal_eq(self, corner_stack, surf_stack, q, t):
+        cs = _xyzi(corner_stack)
+        ss = _xyzi(surf_stack)
+        H = np.zeros(36)
+        g = np.zeros(6)
+        cost = C.c_double(0)
+        nc = C.c_int32(0)
+        ns = C.c_int32(0)
+        pose = Pose.make(q, t)
+        self._chk(self.L.lmono_map_normal_eq(self._h, view_of(cs), view_of(ss), C.byref(pose), H.ctypes.data_as(C.c_void_p),
+                                             g.ctypes.data_as(C.c_void_p), C.byref(cost), C.byref(nc), C.byref(ns)), "map_normal_eq")
+        return H.reshape(6, 6), g, cost.value, nc.value, ns.value
+
+    def voxel_grid(self, pts, leaf):
+        p = _xyzi(pts)
+        buf, out = _out(len(p))
+        self._chk(self.L.lmono_voxel_grid(self._h, view_of(p), C.c_float(leaf), C.byref(out)), "voxel_grid")
+        return buf[: out.n_out].copy()

@@ -1,0 +1,415 @@
+// Scan-to-map data association (Aloam/src/laserMapping.cpp:577-687) on device:
+//   pointAssociateToMap -> exact 5-NN (replaces kdtree*FromMap->nearestKSearch, :582,648)
+//   -> d2[4] < 1.0 gate -> 3x3 covariance + symmetric eigen-decomposition, lambda2 > 3 lambda1
+//   (corner, :586-616) or 5x3 least-squares plane + 0.2 m validity (surf, :650-679)
+//   -> one LmFactor per query.
+//
+// Exactness of the search: a correspondence is only used if its 5th neighbour has fp32
+// d2 < 1.0, hence every neighbour that matters satisfies |dx|,|dy|,|dz| < 1 and its integer
+// floor differs from the query's by at most 1 per axis.  With 2 m cells keyed on
+// floor(x) >> 1 those floors fall in exactly 2 cells per axis: 8 cells per query, one per
+// lane of an 8-lane group (cells that straddle a 50 m cube border are looked up in both
+// cubes, <= 27 (cube, cell) pairs).  d2 is accumulated like FLANN's L2_Simple:
+// ((dx*dx) + dy*dy) + dz*dz in fp32 without FMA.  Ties are broken on the index in the
+// reference's concatenation order (:533-537), so results are order-independent.
+#include "common.cuh"
+#include <float.h>
+
+constexpr int KNN_K = 5;
+constexpr int GROUP = 8;      // lanes per query
+
+struct Cand { float d; int idx; int ref; };   // ref: element index into the map type's cellpts pool
+
+__device__ __forceinline__ bool cand_less(float d1, int i1, float d2, int i2) { return d1 < d2 || (d1 == d2 && i1 < i2); }
+
+// ---- Eigen 3.3 SelfAdjointEigenSolver<Matrix3d> (same operation order as oracle/linalg.c)
+__device__ __forceinline__ void d_make_givens(double p, double q, double* c, double* s) {
+  if (q == 0.0) { *c = p < 0.0 ? -1.0 : 1.0; *s = 0.0; }
+  else if (p == 0.0) { *c = 0.0; *s = q < 0.0 ? 1.0 : -1.0; }
+  else if (fabs(p) > fabs(q)) {
+    double t = q / p; double u = sqrt(1.0 + t * t); if (p < 0.0) u = -u;
+    *c = 1.0 / u; *s = -t * (*c);
+  } else {
+    double t = p / q; double u = sqrt(1.0 + t * t); if (q < 0.0) u = -u;
+    *s = -1.0 / u; *c = -t * (*s);
+  }
+}
+
+// hypot without relying on libm specifics: both sides use the same scaled formula? No --
+// the oracle calls C hypot(); CUDA's hypot() is also correctly rounded to < 1 ulp but not
+// guaranteed identical, and the value only steers the Wilkinson shift (any shift converges
+// to the same eigen-pairs up to rounding).  Gate margins are reported by the tests.
+__device__ void d_tridiagonal_qr_step(double* diag, double* subdiag, int start, int end, double* Q) {
+  double td = (diag[end - 1] - diag[end]) * 0.5;
+  double e = subdiag[end - 1];
+  double mu = diag[end];
+  if (td == 0.0) {
+    mu -= fabs(e);
+  } else {
+    double e2 = e * e;
+    double h = hypot(td, e);
+    if (e2 == 0.0) mu -= (e / (td + (td > 0.0 ? 1.0 : -1.0))) * (e / h);
+    else mu -= e2 / (td + (td > 0.0 ? h : -h));
+  }
+  double x = diag[start] - mu;
+  double z = subdiag[start];
+  for (int k = start; k < end; ++k) {
+    double c, s;
+    d_make_givens(x, z, &c, &s);
+    double sdk = s * diag[k] + c * subdiag[k];
+    double dkp1 = s * subdiag[k] + c * diag[k + 1];
+    diag[k] = c * (c * diag[k] - s * subdiag[k]) - s * (c * subdiag[k] - s * diag[k + 1]);
+    diag[k + 1] = s * sdk + c * dkp1;
+    subdiag[k] = c * sdk - s * dkp1;
+    if (k > start) subdiag[k - 1] = c * subdiag[k - 1] - s * z;
+    x = subdiag[k];
+    if (k < end - 1) {
+      z = -s * subdiag[k + 1];
+      subdiag[k + 1] = c * subdiag[k + 1];
+    }
+    for (int i = 0; i < 3; ++i) {
+      double xi = Q[k * 3 + i], yi = Q[(k + 1) * 3 + i];
+      Q[k * 3 + i] = c * xi - s * yi;
+      Q[(k + 1) * 3 + i] = s * xi + c * yi;
+    }
+  }
+}
+
+// A: row-major 3x3 (lower triangle used). w ascending; Q column-major (column c = eigenvector c)
+__device__ void d_eigh3(const double* A, double* w, double* Q) {
+  double m00 = A[0], m10 = A[3], m11 = A[4], m20 = A[6], m21 = A[7], m22 = A[8];
+  double scale = fabs(m00);
+  if (fabs(m10) > scale) scale = fabs(m10);
+  if (fabs(m11) > scale) scale = fabs(m11);
+  if (fabs(m20) > scale) scale = fabs(m20);
+  if (fabs(m21) > scale) scale = fabs(m21);
+  if (fabs(m22) > scale) scale = fabs(m22);
+  if (scale == 0.0) scale = 1.0;
+  m00 /= scale; m10 /= scale; m11 /= scale; m20 /= scale; m21 /= scale; m22 /= scale;
+  double diag[3], subdiag[2];
+  const double tol = DBL_MIN;
+  diag[0] = m00;
+  double v1norm2 = m20 * m20;
+  if (v1norm2 <= tol) {
+    diag[1] = m11; diag[2] = m22; subdiag[0] = m10; subdiag[1] = m21;
+    Q[0] = 1; Q[1] = 0; Q[2] = 0; Q[3] = 0; Q[4] = 1; Q[5] = 0; Q[6] = 0; Q[7] = 0; Q[8] = 1;
+  } else {
+    double beta = sqrt(m10 * m10 + v1norm2);
+    double invBeta = 1.0 / beta;
+    double m01 = m10 * invBeta;
+    double m02 = m20 * invBeta;
+    double q = 2.0 * m01 * m21 + m02 * (m22 - m11);
+    diag[1] = m11 + m02 * q;
+    diag[2] = m22 - m02 * q;
+    subdiag[0] = beta;
+    subdiag[1] = m21 - m01 * q;
+    Q[0] = 1; Q[1] = 0;   Q[2] = 0;
+    Q[3] = 0; Q[4] = m01; Q[5] = m02;
+    Q[6] = 0; Q[7] = m02; Q[8] = -m01;
+  }
+  const int n = 3;
+  int end = n - 1, start = 0, iter = 0;
+  const int maxIterations = 30;
+  const double precision = 2.0 * DBL_EPSILON;
+  while (end > 0) {
+    for (int i = start; i < end; ++i)
+      if (fabs(subdiag[i]) <= (fabs(diag[i]) + fabs(diag[i + 1])) * precision || fabs(subdiag[i]) <= DBL_MIN) subdiag[i] = 0.0;
+    while (end > 0 && subdiag[end - 1] == 0.0) end--;
+    if (end <= 0) break;
+    iter++;
+    if (iter > maxIterations * n) break;
+    start = end - 1;
+    while (start > 0 && subdiag[start - 1] != 0.0) start--;
+    d_tridiagonal_qr_step(diag, subdiag, start, end, Q);
+  }
+  for (int i = 0; i < n - 1; ++i) {
+    int k = 0; double mn = diag[i];
+    for (int j = 1; j < n - i; ++j) if (diag[i + j] < mn) { mn = diag[i + j]; k = j; }
+    if (k > 0) {
+      double tmp = diag[i]; diag[i] = diag[k + i]; diag[k + i] = tmp;
+      for (int r = 0; r < 3; ++r) { double t2 = Q[i * 3 + r]; Q[i * 3 + r] = Q[(k + i) * 3 + r]; Q[(k + i) * 3 + r] = t2; }
+    }
+  }
+  for (int i = 0; i < 3; ++i) w[i] = diag[i] * scale;
+}
+
+// ---- Eigen 3.3 ColPivHouseholderQR<Matrix<double,5,3>>::solve (same order as oracle/linalg.c)
+__device__ __forceinline__ void d_make_householder(double* v, int len, int stride, double* tau, double* beta) {
+  double tailSqNorm = 0.0;
+  for (int i = 1; i < len; ++i) tailSqNorm += v[i * stride] * v[i * stride];
+  double c0 = v[0];
+  if (tailSqNorm <= DBL_MIN) {
+    *tau = 0.0; *beta = c0;
+    for (int i = 1; i < len; ++i) v[i * stride] = 0.0;
+  } else {
+    double b = sqrt(c0 * c0 + tailSqNorm);
+    if (c0 >= 0.0) b = -b;
+    for (int i = 1; i < len; ++i) v[i * stride] = v[i * stride] / (c0 - b);
+    *tau = (b - c0) / b;
+    *beta = b;
+  }
+}
+
+__device__ void d_colpiv_qr_solve_5x3(const double* Ain, const double* bin, double* x) {
+  constexpr int R = 5, C = 3;
+  double qr[R * C];
+  for (int i = 0; i < R * C; ++i) qr[i] = Ain[i];
+  double hC[C]; int transp[C];
+  double nU[C], nD[C];
+  for (int k = 0; k < C; ++k) {
+    double s = 0.0; for (int r = 0; r < R; ++r) s += qr[r * C + k] * qr[r * C + k];
+    nD[k] = sqrt(s); nU[k] = nD[k];
+  }
+  double maxn = nU[0]; for (int k = 1; k < C; ++k) if (nU[k] > maxn) maxn = nU[k];
+  double th = maxn * DBL_EPSILON; double threshold_helper = (th * th) / (double)R;
+  double norm_downdate_threshold = sqrt(DBL_EPSILON);
+  int nonzero_pivots = C;
+  for (int k = 0; k < C; ++k) {
+    int big = k; double bn = nU[k];
+    for (int j = k + 1; j < C; ++j) if (nU[j] > bn) { bn = nU[j]; big = j; }
+    double biggest_sq = bn * bn;
+    if (nonzero_pivots == C && biggest_sq < threshold_helper * (double)(R - k)) nonzero_pivots = k;
+    transp[k] = big;
+    if (k != big) {
+      for (int r = 0; r < R; ++r) { double t = qr[r * C + k]; qr[r * C + k] = qr[r * C + big]; qr[r * C + big] = t; }
+      double t = nU[k]; nU[k] = nU[big]; nU[big] = t;
+      t = nD[k]; nD[k] = nD[big]; nD[big] = t;
+    }
+    double beta;
+    d_make_householder(&qr[k * C + k], R - k, C, &hC[k], &beta);
+    qr[k * C + k] = beta;
+    if (hC[k] != 0.0) {
+      for (int j = k + 1; j < C; ++j) {
+        double tmp = 0.0;
+        for (int r = k + 1; r < R; ++r) tmp += qr[r * C + k] * qr[r * C + j];
+        tmp += qr[k * C + j];
+        qr[k * C + j] -= hC[k] * tmp;
+        for (int r = k + 1; r < R; ++r) qr[r * C + j] -= hC[k] * qr[r * C + k] * tmp;
+      }
+    }
+    for (int j = k + 1; j < C; ++j) {
+      if (nU[j] != 0.0) {
+        double temp = fabs(qr[k * C + j]) / nU[j];
+        temp = (1.0 + temp) * (1.0 - temp);
+        temp = temp < 0.0 ? 0.0 : temp;
+        double ratio = nU[j] / nD[j];
+        double temp2 = temp * (ratio * ratio);
+        if (temp2 <= norm_downdate_threshold) {
+          double s = 0.0; for (int r = k + 1; r < R; ++r) s += qr[r * C + j] * qr[r * C + j];
+          nD[j] = sqrt(s); nU[j] = nD[j];
+        } else {
+          nU[j] *= sqrt(temp);
+        }
+      }
+    }
+  }
+  int perm[C]; for (int i = 0; i < C; ++i) perm[i] = i;
+  for (int k = 0; k < C; ++k) { int t = perm[k]; perm[k] = perm[transp[k]]; perm[transp[k]] = t; }
+  if (nonzero_pivots == 0) { x[0] = x[1] = x[2] = 0.0; return; }
+  double c[R]; for (int r = 0; r < R; ++r) c[r] = bin[r];
+  for (int k = 0; k < nonzero_pivots; ++k) {
+    if (hC[k] != 0.0) {
+      double tmp = 0.0;
+      for (int r = k + 1; r < R; ++r) tmp += qr[r * C + k] * c[r];
+      tmp += c[k];
+      c[k] -= hC[k] * tmp;
+      for (int r = k + 1; r < R; ++r) c[r] -= hC[k] * qr[r * C + k] * tmp;
+    }
+  }
+  for (int i = nonzero_pivots - 1; i >= 0; --i) {
+    double s = c[i];
+    for (int j = i + 1; j < nonzero_pivots; ++j) s -= qr[i * C + j] * c[j];
+    c[i] = s / qr[i * C + i];
+  }
+  for (int i = 0; i < nonzero_pivots; ++i) x[perm[i]] = c[i];
+  for (int i = nonzero_pivots; i < C; ++i) x[perm[i]] = 0.0;
+}
+
+// ---- fits
+__device__ void d_fit_corner(const float4* nb, float4 ori, LmFactor* f) {
+  double near[5][3], center[3] = { 0, 0, 0 };
+  for (int j = 0; j < 5; ++j) {
+    near[j][0] = nb[j].x; near[j][1] = nb[j].y; near[j][2] = nb[j].z;
+    for (int k = 0; k < 3; ++k) center[k] = center[k] + near[j][k];
+  }
+  for (int k = 0; k < 3; ++k) center[k] = center[k] / 5.0;
+  double cov[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+  for (int j = 0; j < 5; ++j) {
+    double z[3] = { near[j][0] - center[0], near[j][1] - center[1], near[j][2] - center[2] };
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) cov[a * 3 + b] = cov[a * 3 + b] + z[a] * z[b];
+  }
+  double w[3], Q[9];
+  d_eigh3(cov, w, Q);
+  if (!(w[2] > 3 * w[1])) { f->kind = -1; return; }
+  // unit_direction = eigenvectors().col(2): Q column-major, column 2 = Q[6..8]
+  for (int k = 0; k < 3; ++k) { f->a[k] = 0.1 * Q[6 + k] + center[k]; f->b[k] = -0.1 * Q[6 + k] + center[k]; }
+  f->p[0] = ori.x; f->p[1] = ori.y; f->p[2] = ori.z;
+  f->kind = 0;
+}
+
+__device__ void d_fit_surf(const float4* nb, float4 ori, LmFactor* f) {
+  double A[15], B[5] = { -1, -1, -1, -1, -1 };
+  for (int j = 0; j < 5; ++j) { A[j * 3 + 0] = nb[j].x; A[j * 3 + 1] = nb[j].y; A[j * 3 + 2] = nb[j].z; }
+  double n[3];
+  d_colpiv_qr_solve_5x3(A, B, n);
+  double z2 = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+  double nn = sqrt(z2);
+  double negative_OA_dot_norm = 1 / nn;
+  if (z2 > 0.0) { n[0] /= nn; n[1] /= nn; n[2] /= nn; }
+  for (int j = 0; j < 5; ++j) {
+    if (fabs(n[0] * A[j * 3 + 0] + n[1] * A[j * 3 + 1] + n[2] * A[j * 3 + 2] + negative_OA_dot_norm) > 0.2) { f->kind = -1; return; }
+  }
+  f->a[0] = n[0]; f->a[1] = n[1]; f->a[2] = n[2];
+  f->b[0] = negative_OA_dot_norm; f->b[1] = 0.0; f->b[2] = 0.0;
+  f->p[0] = ori.x; f->p[1] = ori.y; f->p[2] = ori.z;
+  f->kind = 2;
+}
+
+// ---- 8-lane exact 5-NN of one world-frame query against the window of one map type.
+// All 8 lanes of the group call this with the same query; returns on every lane the merged
+// top-5 (d2, canonical idx, ref).  n_found < 5 leaves +inf / -1 entries.
+__device__ __forceinline__ void d_knn5_group(const LmMapType& M, const LmMapState* __restrict__ st,
+                                             const int32_t* __restrict__ slot_valid_rank, int ty, float qx, float qy, float qz,
+                                             int sub, unsigned gmask, float* od, int* oi, int* oref) {
+  float bd[KNN_K]; int bi[KNN_K]; int br[KNN_K];
+#pragma unroll
+  for (int k = 0; k < KNN_K; ++k) { bd[k] = FLT_MAX; bi[k] = 0x7fffffff; br[k] = -1; }
+
+  // per axis: up to 3 (cube, local cell) pairs
+  int f[3] = { (int)floorf(qx), (int)floorf(qy), (int)floorf(qz) };
+  int pg[3][3], pc[3][3], np[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    np[a] = 0;
+    const int c0 = (f[a] - 1) >> 1, c1 = (f[a] + 1) >> 1;
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const int c = w == 0 ? c0 : c1;
+      const int g_lo = d_floordiv(c + 12, 25), g_hi = d_floordiv(c + 13, 25);
+      for (int g = g_lo; g <= g_hi; ++g) { if (np[a] < 3) { pg[a][np[a]] = g; pc[a][np[a]] = c - (25 * g - 13); np[a]++; } }
+    }
+  }
+  const int ncomb = np[0] * np[1] * np[2];
+  const int cen0 = st->cen[0], cen1 = st->cen[1], cen2 = st->cen[2];
+  for (int cmb = sub; cmb < ncomb; cmb += GROUP) {
+    const int ix = cmb % np[0], iy = (cmb / np[0]) % np[1], iz = cmb / (np[0] * np[1]);
+    const int gi = pg[0][ix], gj = pg[1][iy], gk = pg[2][iz];
+    const int li = gi + cen0, lj = gj + cen1, lk = gk + cen2;
+    if (li < 0 || li >= LM_GW || lj < 0 || lj >= LM_GH || lk < 0 || lk >= LM_GD) continue;
+    const int ps = d_phys_slot(gi, gj, gk);
+    const int rank = slot_valid_rank[ps];
+    if (rank < 0) continue;
+    const int sid = M.slot_slab[ps];
+    if (sid < 0) continue;
+    const int cell = pc[0][ix] + LM_CELLS_AXIS * (pc[1][iy] + LM_CELLS_AXIS * pc[2][iz]);
+    const uint32_t* cs = M.cellstart + (size_t)sid * (LM_NCELL + 1);
+    const uint32_t b = cs[cell], e = cs[cell + 1];
+    const int base_idx = st->valid_off[ty][rank];
+    const float4* cp = M.cellpts + (size_t)sid * M.cap;
+    for (uint32_t t = b; t < e; ++t) {
+      const float4 p = cp[t];
+      const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
+      float d = __fmul_rn(dx, dx);
+      d = __fadd_rn(d, __fmul_rn(dy, dy));
+      d = __fadd_rn(d, __fmul_rn(dz, dz));
+      const int idx = base_idx + __float_as_int(p.w);
+      if (cand_less(d, idx, bd[KNN_K - 1], bi[KNN_K - 1])) {
+        bd[KNN_K - 1] = d; bi[KNN_K - 1] = idx; br[KNN_K - 1] = sid * M.cap + (int)t;
+#pragma unroll
+        for (int k = KNN_K - 1; k > 0; --k) {
+          if (cand_less(bd[k], bi[k], bd[k - 1], bi[k - 1])) {
+            float td = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td;
+            int ti = bi[k]; bi[k] = bi[k - 1]; bi[k - 1] = ti;
+            int tr = br[k]; br[k] = br[k - 1]; br[k - 1] = tr;
+          }
+        }
+      }
+    }
+  }
+  // merge the 8 sorted lists: 5 rounds of (min over lane heads, owner pops)
+  int head = 0;
+#pragma unroll
+  for (int k = 0; k < KNN_K; ++k) {
+    float hd = FLT_MAX; int hi = 0x7fffffff, hr = -1;
+#pragma unroll
+    for (int j = 0; j < KNN_K; ++j) if (head == j) { hd = bd[j]; hi = bi[j]; hr = br[j]; }
+    float md = hd; int mi = hi, mr = hr;
+#pragma unroll
+    for (int o = GROUP / 2; o > 0; o >>= 1) {
+      float od2 = __shfl_xor_sync(gmask, md, o);
+      int oi2 = __shfl_xor_sync(gmask, mi, o);
+      int or2 = __shfl_xor_sync(gmask, mr, o);
+      if (cand_less(od2, oi2, md, mi)) { md = od2; mi = oi2; mr = or2; }
+    }
+    if (head < KNN_K && hi == mi && hr == mr && hr >= 0) head++;   // canonical indices are unique
+    od[k] = md; oi[k] = (mr >= 0) ? mi : -1; oref[k] = mr;
+  }
+}
+
+// one 8-lane group per query; queries of both map types in one launch
+__global__ void __launch_bounds__(256) k_associate(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1,
+                                                   const int32_t* __restrict__ slot_valid_rank,
+                                                   const float4* __restrict__ stack0, const float4* __restrict__ stack1,
+                                                   LmFactor* __restrict__ fac0, LmFactor* __restrict__ fac1) {
+  if (!st->optimize) return;
+  const int n0 = st->stack_n[0], n1 = st->stack_n[1];
+  const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / GROUP;
+  const int sub = threadIdx.x & (GROUP - 1);
+  const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~(GROUP - 1));
+  if (gid >= n0 + n1) return;
+  const int ty = gid < n0 ? 0 : 1;
+  const int qi = ty == 0 ? gid : gid - n0;
+  const LmMapType& M = ty == 0 ? M0 : M1;
+  const float4 ori = ty == 0 ? stack0[qi] : stack1[qi];
+  const float4 sel = d_associate(st->q_w_curr, st->t_w_curr, ori);
+  float d[KNN_K]; int idx[KNN_K], ref[KNN_K];
+  d_knn5_group(M, st, slot_valid_rank, ty, sel.x, sel.y, sel.z, sub, gmask, d, idx, ref);
+  if (sub != 0) return;
+  LmFactor* f = (ty == 0 ? fac0 : fac1) + qi;
+  if (!(ref[KNN_K - 1] >= 0 && d[KNN_K - 1] < 1.0f)) { f->kind = -1; return; }
+  float4 nb[KNN_K];
+#pragma unroll
+  for (int k = 0; k < KNN_K; ++k) nb[k] = M.cellpts[ref[k]];
+  LmFactor out;
+  if (ty == 0) d_fit_corner(nb, ori, &out); else d_fit_surf(nb, ori, &out);
+  if (out.kind < 0) { f->kind = -1; return; }
+  *f = out;
+}
+
+int lm_map_associate(lmono_ctx* ctx, int n_max_corner, int n_max_surf) {
+  const int nq = n_max_corner + n_max_surf;
+  if (nq <= 0) return LMONO_OK;
+  const int blocks = lm_div_up(nq * GROUP, 256);
+  k_associate<<<blocks, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_slot_valid_rank,
+                                               ctx->d_stack[0], ctx->d_stack[1], ctx->d_fac[0], ctx->d_fac[1]);
+  LM_LAUNCH_CHECK();
+  return LMONO_OK;
+}
+
+// test hook: world-frame queries, raw 5-NN output
+__global__ void __launch_bounds__(256) k_knn5_hook(const LmMapState* __restrict__ st, LmMapType M, int ty,
+                                                   const int32_t* __restrict__ slot_valid_rank,
+                                                   const float4* __restrict__ q, int n, int32_t* __restrict__ oidx, float* __restrict__ od2) {
+  const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / GROUP;
+  const int sub = threadIdx.x & (GROUP - 1);
+  const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~(GROUP - 1));
+  if (gid >= n) return;
+  const float4 p = q[gid];
+  float d[KNN_K]; int idx[KNN_K], ref[KNN_K];
+  d_knn5_group(M, st, slot_valid_rank, ty, p.x, p.y, p.z, sub, gmask, d, idx, ref);
+  if (sub != 0) return;
+#pragma unroll
+  for (int k = 0; k < KNN_K; ++k) {
+    const bool ok = ref[k] >= 0;
+    oidx[gid * KNN_K + k] = ok ? idx[k] : -1;
+    od2[gid * KNN_K + k] = ok ? d[k] : INFINITY;
+  }
+}
+
+int lm_knn5_device(lmono_ctx* ctx, int which, const float4* d_q, int n, int32_t* d_idx, float* d_d2) {
+  if (n <= 0) return LMONO_OK;
+  const int blocks = lm_div_up(n * GROUP, 256);
+  k_knn5_hook<<<blocks, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[which], which, ctx->d_slot_valid_rank, d_q, n, d_idx, d_d2);
+  LM_LAUNCH_CHECK();
+  return LMONO_OK;
+}

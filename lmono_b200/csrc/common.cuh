@@ -1,0 +1,292 @@
+// lmono_b200 internal header: device data layout, shared device helpers, host ctx.
+// Target: sm_100a (B200).  Compiled with -fmad=false so that every fp32/fp64 product-sum
+// is rounded exactly like the reference's x86-64 (no FMA) arithmetic -- feature labels,
+// voxel keys, kNN distances and fit gates are bit-exact against the oracle.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+#include "../../include/lmono.h"
+
+// ---------------------------------------------------------------- constants
+// rolling cube grid of the reference (Aloam/src/laserMapping.cpp:74-82)
+constexpr int LM_GW = 21, LM_GH = 21, LM_GD = 11;
+constexpr int LM_NSLOT = LM_GW * LM_GH * LM_GD;   // 4851
+constexpr int LM_MAX_VALID = 125;                 // :85 (<=75 used)
+// per-cube search grid: 2 m cells keyed on floor(x)>>1; a 50 m cube (+1 floor of slack on
+// each side) spans 26 cells per axis.
+constexpr int LM_CELLS_AXIS = 26;
+constexpr int LM_NCELL = LM_CELLS_AXIS * LM_CELLS_AXIS * LM_CELLS_AXIS;   // 17576
+constexpr int LM_SORT_TILE = 4096;                // elements per CTA in the global tile sort
+constexpr int LM_TAIL_TILE = 16384;               // max unsorted tail per cube refilter (smem sort)
+
+// device fault bits (LmMapState::fault)
+enum : unsigned {
+  LM_FAULT_CUBE_OVERFLOW = 1u << 0,   // a cube slab exceeded its capacity
+  LM_FAULT_POOL_EXHAUSTED = 1u << 1,  // no free cube slab
+  LM_FAULT_TAIL_OVERFLOW = 1u << 2,   // unsorted tail larger than LM_TAIL_TILE
+  LM_FAULT_CELL_RANGE = 1u << 3,      // point outside its cube's cell table (internal error)
+  LM_FAULT_FEATURE_OVERFLOW = 1u << 4,
+  LM_FAULT_IMPORT_NONEMPTY = 1u << 5,
+};
+
+// ---------------------------------------------------------------- device structs
+struct LmFactor {           // 64 B, one per query (kind < 0: no factor)
+  double a[3];              // EDGE: point_a | PLANE: point_j | PLANE_NORM: unit normal
+  double b[3];              // EDGE: point_b | PLANE: unit normal ljm | PLANE_NORM: b[0] = negative_OA_dot_norm
+  float p[3];               // curr_point (sensor frame), stored as the float it is
+  int32_t kind;             // -1 none, 0 edge, 1 plane, 2 plane_norm
+};
+static_assert(sizeof(LmFactor) == 64, "LmFactor must be 64 bytes");
+
+struct LmSolveSummary { int32_t iterations, num_successful, termination, num_factors; double initial_cost, final_cost; };
+
+struct LmLmState {          // Levenberg-Marquardt controller state (one solve at a time)
+  double x[7];              // accepted parameters q(xyzw), t
+  double cand[7];           // candidate being evaluated
+  double x_norm, cost;
+  double H[21], g[6];       // upper-triangular J^T J and J^T r at x (unscaled tangent space)
+  double scaling[6], diagonal[6];
+  double radius, decrease_factor, model_cost_change;
+  int32_t reuse_diagonal, num_invalid;
+  int32_t iteration, num_successful, termination, done, phase, max_iter;
+  int32_t nfactors, pad;
+  double initial_cost;
+  // scratch for the grid reduction
+  unsigned int ticket;
+  unsigned int pad2;
+};
+
+struct LmMapState {
+  int32_t cen[3];                        // laserCloudCenWidth/Height/Depth
+  int32_t center[3];                     // centerCubeI/J/K after the shift
+  int32_t valid_num;
+  int32_t valid_slot[LM_MAX_VALID + 3];  // physical slot of each window cube, reference order
+  int32_t valid_off[2][LM_MAX_VALID + 3];// exclusive prefix of cube sizes per map type
+  int32_t from_map_n[2];
+  int32_t optimize;
+  int32_t stack_n[2];                    // voxel-filtered feature counts (corner, surf)
+  int32_t raw_n[2];
+  int32_t frame_count;
+  uint32_t fault;
+  int32_t corner_num[2], surf_num[2];
+  LmSolveSummary solve[2];
+  double q_wmap_wodom[4], t_wmap_wodom[3];
+  double q_wodom_curr[4], t_wodom_curr[3];
+  double q_w_curr[4], t_w_curr[3];
+};
+
+struct LmMapType {           // one per map (0 corner, 1 surf); device pointers, passed by value
+  float leaf, inv_leaf;
+  int32_t cap;               // points per cube slab
+  int32_t n_slabs;
+  float4* pts;               // [n_slabs][2][cap]  canonical (VoxelGrid) order, ping-pong
+  float4* cellpts;           // [n_slabs][cap]     cell-sorted copy, .w = bits of slab position
+  uint32_t* cellstart;       // [n_slabs][LM_NCELL+1]
+  uint32_t* pkey;            // [n_slabs][cap]     voxel keys of the sorted prefix (scratch)
+  int32_t* slot_slab;        // [LM_NSLOT] slab id or -1
+  int32_t* slab_n;           // [n_slabs] points in slab (sorted prefix + tail)
+  int32_t* slab_nsorted;     // [n_slabs] length of the sorted, voxel-unique prefix
+  int32_t* slab_cur;         // [n_slabs] current ping-pong buffer
+  int32_t* slab_dirty;       // [n_slabs] 1 = cell index stale
+  int32_t* slab_g;           // [n_slabs][4] absolute cube coordinate (gi,gj,gk) of the slab
+  int32_t* free_stack;       // [n_slabs]
+  int32_t* free_top;         // [1]
+};
+
+struct VgParams {            // scan-level VoxelGrid parameters computed on device
+  int32_t min_b[3], div_b[3], mul[3];
+  int32_t guard;             // 1: PCL's "leaf size too small" path -> output = input
+  int32_t n;
+};
+
+// ---------------------------------------------------------------- host ctx
+struct lmono_ctx {
+  int device;
+  lmono_params prm;
+  cudaStream_t stream;
+  bool own_stream;
+  int last_cuda_error;
+  int64_t launches;
+  cudaEvent_t ev0, ev1;
+
+  LmMapType map[2];
+  LmMapState* d_state;
+  LmMapState* h_state;          // pinned mirror
+  LmLmState* d_lm;
+  int32_t* d_slot_valid_rank;   // [LM_NSLOT]
+  double* d_partials;           // reduction partials [max_blocks][32]
+
+  // feature staging
+  uint8_t* d_raw[3]; size_t raw_bytes;     // raw AoS uploads (corner, surf, full)
+  float4* d_in[2];                          // unpacked XYZI inputs
+  float4* d_stack[2];                       // voxel-filtered features
+  float4* d_world[2];                       // features in the world frame (insertion)
+  LmFactor* d_fac[2];
+  unsigned long long* d_sort_a; unsigned long long* d_sort_b; unsigned long long* d_sort_c;
+  int32_t* d_blockcnt;                      // block counts for 2-kernel scans
+  int32_t* d_tmp_i32;                       // misc int scratch [max_feature_points*2]
+  VgParams* d_vg;
+  float4* d_full;                           // full-res sweep
+  int32_t* d_slot_first; int32_t* d_slot_base; // insertion run tables [LM_NSLOT]
+  float4* d_export; size_t export_cap;      // export / import staging
+  int32_t* d_export_off;                    // [LM_NSLOT+1]
+  int max_feat, max_sweep;
+  int sm_count;
+  bool step_pending;
+  // later stages (scan registration / odometry / colour) attach their own state
+  void* scan_state; void* odom_state; void* color_state;
+};
+
+#define LM_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { ctx->last_cuda_error = (int)_e; \
+  fprintf(stderr, "[lmono_b200] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); \
+  return LMONO_E_CUDA; } } while (0)
+#define LM_LAUNCH_CHECK() do { ctx->launches++; cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { ctx->last_cuda_error = (int)_e; \
+  fprintf(stderr, "[lmono_b200] launch error %s at %s:%d\n", cudaGetErrorName(_e), __FILE__, __LINE__); return LMONO_E_CUDA; } } while (0)
+
+static inline int lm_div_up(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+__device__ __forceinline__ int d_pmod(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
+__device__ __forceinline__ int d_floordiv(int a, int b) { int q = a / b; if ((a % b != 0) && ((a < 0) != (b < 0))) --q; return q; }
+
+// cube coordinate of a world value: (int)((v + 25.0) / 50.0) + cen, minus one if v + 25.0 < 0
+// (Aloam/src/laserMapping.cpp:312-321, 741-750)
+__device__ __forceinline__ int d_cube_coord(double v, int cen) {
+  int c = (int)((v + 25.0) / 50.0) + cen;
+  if (v + 25.0 < 0) c--;
+  return c;
+}
+__device__ __forceinline__ int d_phys_slot(int gi, int gj, int gk) {
+  return d_pmod(gi, LM_GW) + LM_GW * d_pmod(gj, LM_GH) + LM_GW * LM_GH * d_pmod(gk, LM_GD);
+}
+
+// Eigen quaternion algebra, q = (x,y,z,w), double, evaluated in Eigen's operation order
+__device__ __forceinline__ void d_qmul(const double* a, const double* b, double* o) {
+  double w = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+  double x = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+  double y = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
+  double z = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+  o[0] = x; o[1] = y; o[2] = z; o[3] = w;
+}
+__device__ __forceinline__ void d_qrot(const double* q, const double* v, double* o) {
+  double uv0 = q[1] * v[2] - q[2] * v[1], uv1 = q[2] * v[0] - q[0] * v[2], uv2 = q[0] * v[1] - q[1] * v[0];
+  uv0 += uv0; uv1 += uv1; uv2 += uv2;
+  double c0 = q[1] * uv2 - q[2] * uv1, c1 = q[2] * uv0 - q[0] * uv2, c2 = q[0] * uv1 - q[1] * uv0;
+  o[0] = (v[0] + q[3] * uv0) + c0; o[1] = (v[1] + q[3] * uv1) + c1; o[2] = (v[2] + q[3] * uv2) + c2;
+}
+__device__ __forceinline__ void d_qinv(const double* q, double* o) {
+  double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  if (n2 > 0.0) { o[0] = -q[0] / n2; o[1] = -q[1] / n2; o[2] = -q[2] / n2; o[3] = q[3] / n2; }
+  else { o[0] = o[1] = o[2] = o[3] = 0.0; }
+}
+// pointAssociateToMap (laserMapping.cpp:154-163): double rotate + translate, stored as float
+__device__ __forceinline__ float4 d_associate(const double* q, const double* t, float4 pi) {
+  double v[3] = { (double)pi.x, (double)pi.y, (double)pi.z }, o[3];
+  d_qrot(q, v, o);
+  float4 r;
+  r.x = (float)(o[0] + t[0]); r.y = (float)(o[1] + t[1]); r.z = (float)(o[2] + t[2]); r.w = pi.w;
+  return r;
+}
+
+// voxel coordinate of PCL VoxelGrid: floor(x * inverse_leaf) in fp32
+__device__ __forceinline__ int d_voxel_coord(float x, float inv_leaf) { return (int)floorf(__fmul_rn(x, inv_leaf)); }
+
+// cube-local voxel key (z-major, then y, then x -- the order PCL's linear index induces).
+// 10 bits per axis; origin = voxel of the cube's lower corner minus 2 (slack).
+__device__ __forceinline__ uint32_t d_cube_voxel_key(float4 p, float inv_leaf, const int* g) {
+  int ox = (int)floorf((float)(50 * g[0] - 25) * inv_leaf) - 2;
+  int oy = (int)floorf((float)(50 * g[1] - 25) * inv_leaf) - 2;
+  int oz = (int)floorf((float)(50 * g[2] - 25) * inv_leaf) - 2;
+  int lx = d_voxel_coord(p.x, inv_leaf) - ox, ly = d_voxel_coord(p.y, inv_leaf) - oy, lz = d_voxel_coord(p.z, inv_leaf) - oz;
+  lx = min(max(lx, 0), 1023); ly = min(max(ly, 0), 1023); lz = min(max(lz, 0), 1023);
+  return ((uint32_t)lz << 20) | ((uint32_t)ly << 10) | (uint32_t)lx;
+}
+
+// cube-local 2 m cell index of a point; returns -1 if outside the table (never for points
+// stored in the cube)
+__device__ __forceinline__ int d_cube_cell(float4 p, const int* g) {
+  int cx = ((int)floorf(p.x) >> 1) - (25 * g[0] - 13);
+  int cy = ((int)floorf(p.y) >> 1) - (25 * g[1] - 13);
+  int cz = ((int)floorf(p.z) >> 1) - (25 * g[2] - 13);
+  if ((unsigned)cx >= (unsigned)LM_CELLS_AXIS || (unsigned)cy >= (unsigned)LM_CELLS_AXIS || (unsigned)cz >= (unsigned)LM_CELLS_AXIS) return -1;
+  return cx + LM_CELLS_AXIS * (cy + LM_CELLS_AXIS * cz);
+}
+
+// block-wide exclusive scan of one int per thread (blockDim.x <= 1024, multiple of 32).
+// warp_sums: shared int[33]. Returns the exclusive prefix; *total = block sum.
+__device__ __forceinline__ int d_block_exscan(int v, int* warp_sums, int* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) warp_sums[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int s = lane < nw ? warp_sums[lane] : 0;
+    int si = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, si, o); if (lane >= o) si += t; }
+    if (lane < nw) warp_sums[lane] = si - s;      // exclusive warp offsets
+    if (lane == 31) warp_sums[32] = si;            // total
+  }
+  __syncthreads();
+  int res = warp_sums[wid] + incl - v;
+  *total = warp_sums[32];
+  __syncthreads();
+  return res;
+}
+
+// in-place ascending bitonic sort of n_pow2 64-bit keys in shared memory by the whole block
+__device__ __forceinline__ void d_bitonic_sort(unsigned long long* s, int n_pow2) {
+  for (int k = 2; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < (n_pow2 >> 1); i += blockDim.x) {
+        int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));   // index with bit j cleared
+        int hi = lo | j;
+        bool up = ((lo & k) == 0);
+        unsigned long long a = s[lo], b = s[hi];
+        if ((a > b) == up) { s[lo] = b; s[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// first index in sorted[0..n) with sorted[i] >= key
+__device__ __forceinline__ int d_lower_bound_u64(const unsigned long long* sorted, int n, unsigned long long key) {
+  int lo = 0, hi = n;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (sorted[mid] < key) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+__device__ __forceinline__ int d_lower_bound_u32(const uint32_t* sorted, int n, uint32_t key) {
+  int lo = 0, hi = n;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (sorted[mid] < key) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+#endif  // __CUDACC__
+
+// ---------------------------------------------------------------- cross-TU host functions
+// sort.cu: sorts n (device int *n_dev, <= n_max) unique 64-bit keys ascending: in -> out (tmp is scratch)
+int lm_sort_u64(lmono_ctx* ctx, const unsigned long long* in, unsigned long long* tmp, unsigned long long* out,
+                const int32_t* n_dev, int n_max);
+// voxel.cu: VoxelGrid of `in` (n_dev points, <= n_max) -> out, *out_n_dev
+int lm_voxel_grid_device(lmono_ctx* ctx, const float4* in, const int32_t* n_dev, int n_max, float leaf,
+                         float4* out, int32_t* out_n_dev);
+// mapstore.cu
+int lm_map_alloc(lmono_ctx* ctx);
+void lm_map_free(lmono_ctx* ctx);
+int lm_map_begin_step(lmono_ctx* ctx, const lmono_pose* wodom_curr, const double* t_override);
+int lm_map_index_build(lmono_ctx* ctx);
+int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf);
+// assoc.cu
+int lm_map_associate(lmono_ctx* ctx, int n_max_corner, int n_max_surf);
+int lm_knn5_device(lmono_ctx* ctx, int which, const float4* d_q, int n, int32_t* d_idx, float* d_d2);
+// lm.cu
+int lm_solve_enqueue(lmono_ctx* ctx, int solve_index, int n_max_corner, int n_max_surf, int max_iter);
+int lm_normal_eq_enqueue(lmono_ctx* ctx, int n_max_corner, int n_max_surf);
+// ctx.cu helpers
+int lm_upload_cloud(lmono_ctx* ctx, lmono_cloud_view v, uint8_t* d_raw, float4* d_out, int32_t* d_n /*may be null*/);
+int lm_download_cloud(lmono_ctx* ctx, const float4* d_src, int n, lmono_cloud_out* out);

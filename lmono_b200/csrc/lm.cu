@@ -1,0 +1,336 @@
+// On-device Levenberg-Marquardt replacing ceres::Solve at Aloam/src/laserMapping.cpp:713-720
+// and Aloam/src/laserOdometry.cpp:494-499 (HuberLoss(0.1), EigenQuaternionParameterization,
+// DENSE_QR, max_num_iterations = 4, Ceres 1.14 defaults otherwise).
+//
+// One launch = one evaluation of all factors at the pose under test: per factor the residual
+// (Aloam/src/lidarFactor.hpp:19-43, 69-90, 114-125), its analytic 3x6 / 1x6 Jacobian in the
+// tangent space of q+ = [sin|d| d/|d|, cos|d|] (x) q  (d lp / d delta = -2 [R p]x,
+// d lp / d t = I), the Huber corrector sqrt(rho'), and the 28 unique doubles
+// {J^T J (21), J^T r (6), cost} reduced warp-shuffle -> shared -> per-block partials; the
+// last block to finish sums the partials in fixed order (run-to-run deterministic, no float
+// atomics) and one thread advances the trust-region state machine: Jacobi scaling, LM
+// diagonal, damped 6x6 Cholesky solve in double, step-quality test, radius update and the
+// function / parameter / gradient tolerances -- no host round trip inside a solve.
+#include "common.cuh"
+#include <float.h>
+
+constexpr int NRED = 28;          // 21 + 6 + 1
+constexpr int EVAL_THREADS = 256;
+
+__device__ __forceinline__ void d_cross(const double* a, const double* b, double* o) {
+  o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+// accumulate one residual row: J (6), r, into the 27 sums
+__device__ __forceinline__ void d_acc_row(const double* J, double r, double* acc) {
+  int k = 0;
+#pragma unroll
+  for (int a = 0; a < 6; ++a)
+#pragma unroll
+    for (int b = a; b < 6; ++b) acc[k++] += J[a] * J[b];
+#pragma unroll
+  for (int a = 0; a < 6; ++a) acc[21 + a] += J[a] * r;
+}
+
+__device__ __forceinline__ void d_eval_factor(const LmFactor& f, const double* q, const double* t, double* acc) {
+  if (f.kind < 0) return;
+  const double p[3] = { (double)f.p[0], (double)f.p[1], (double)f.p[2] };
+  double rp[3]; d_qrot(q, p, rp);                       // R p
+  const double lp[3] = { rp[0] + t[0], rp[1] + t[1], rp[2] + t[2] };
+  // d lp / d delta = -2 [R p]x  (columns), d lp / d t = I
+  // row k of a 1x3 covector c maps to: J_rot = c^T * (-2 [rp]x) = -2 (c x rp)^T ... computed per case
+  if (f.kind == 0) {
+    double da[3] = { lp[0] - f.a[0], lp[1] - f.a[1], lp[2] - f.a[2] };
+    double db[3] = { lp[0] - f.b[0], lp[1] - f.b[1], lp[2] - f.b[2] };
+    double nu[3]; d_cross(da, db, nu);
+    double de[3] = { f.a[0] - f.b[0], f.a[1] - f.b[1], f.a[2] - f.b[2] };
+    double den = sqrt(de[0] * de[0] + de[1] * de[1] + de[2] * de[2]);
+    double r[3] = { nu[0] / den, nu[1] / den, nu[2] / den };
+    double s = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    double rho0, rho1;
+    if (s > 0.01) { double rs = sqrt(s); rho0 = 2.0 * 0.1 * rs - 0.01; rho1 = fmax(DBL_MIN, 0.1 / rs); } else { rho0 = s; rho1 = 1.0; }
+    acc[27] += 0.5 * rho0;
+    const double sr = sqrt(rho1);
+    // dr/dlp = [b - a]x / den = -[de]x / den.  Row k of [v]x: e_k^T [v]x.
+    // M = -[de]x / den  (3x3); J_t = M ; J_rot = M * (-2 [rp]x)
+    double Mx[3][3] = { { 0.0, de[2], -de[1] }, { -de[2], 0.0, de[0] }, { de[1], -de[0], 0.0 } };   // -[de]x
+    for (int k = 0; k < 3; ++k) {
+      double m[3] = { Mx[k][0] / den, Mx[k][1] / den, Mx[k][2] / den };
+      // m^T (-2 [rp]x) = -2 (m^T [rp]x) ; m^T [v]x = (v x m)^T ... use: m^T [v]x w = m . (v x w) = (m x v) . w
+      double mxv[3]; d_cross(m, rp, mxv);
+      double J[6] = { -2.0 * mxv[0] * sr, -2.0 * mxv[1] * sr, -2.0 * mxv[2] * sr, m[0] * sr, m[1] * sr, m[2] * sr };
+      d_acc_row(J, r[k] * sr, acc);
+    }
+  } else {
+    double r, n[3];
+    if (f.kind == 1) { n[0] = f.b[0]; n[1] = f.b[1]; n[2] = f.b[2]; r = (lp[0] - f.a[0]) * n[0] + (lp[1] - f.a[1]) * n[1] + (lp[2] - f.a[2]) * n[2]; }
+    else { n[0] = f.a[0]; n[1] = f.a[1]; n[2] = f.a[2]; r = (n[0] * lp[0] + n[1] * lp[1] + n[2] * lp[2]) + f.b[0]; }
+    double s = r * r;
+    double rho0, rho1;
+    if (s > 0.01) { double rs = sqrt(s); rho0 = 2.0 * 0.1 * rs - 0.01; rho1 = fmax(DBL_MIN, 0.1 / rs); } else { rho0 = s; rho1 = 1.0; }
+    acc[27] += 0.5 * rho0;
+    const double sr = sqrt(rho1);
+    double nxv[3]; d_cross(n, rp, nxv);
+    double J[6] = { -2.0 * nxv[0] * sr, -2.0 * nxv[1] * sr, -2.0 * nxv[2] * sr, n[0] * sr, n[1] * sr, n[2] * sr };
+    d_acc_row(J, r * sr, acc);
+  }
+}
+
+// ---- trust-region controller (single thread) -------------------------------------------
+__device__ void d_plus(const double* x, const double* d, double* out) {
+  const double nd = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  if (nd > 0.0) {
+    const double sbd = sin(nd) / nd;
+    const double a[4] = { sbd * d[0], sbd * d[1], sbd * d[2], cos(nd) };
+    d_qmul(a, x, out);
+  } else { out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; out[3] = x[3]; }
+  out[4] = x[4] + d[3]; out[5] = x[5] + d[4]; out[6] = x[6] + d[5];
+}
+__device__ __forceinline__ double d_norm7(const double* v) { double s = 0; for (int i = 0; i < 7; ++i) s += v[i] * v[i]; return sqrt(s); }
+__device__ __forceinline__ double d_Hat(const double* H, int a, int b) {   // upper-triangular packed access
+  if (a > b) { int t = a; a = b; b = t; }
+  return H[a * 6 - (a * (a - 1)) / 2 + (b - a)];
+}
+__device__ double d_gradient_max_norm(const double* x, const double* g) {
+  double ng[6], xp[7];
+  for (int i = 0; i < 6; ++i) ng[i] = -g[i];
+  d_plus(x, ng, xp);
+  double m = 0.0;
+  for (int i = 0; i < 7; ++i) { double a = fabs(x[i] - xp[i]); if (a > m) m = a; }
+  return m;
+}
+
+// solve (A) y = b for SPD 6x6 A via Cholesky; returns 0 on success
+__device__ int d_chol6(double A[6][6], const double* b, double* y) {
+  double L[6][6];
+  for (int i = 0; i < 6; ++i) {
+    for (int j = 0; j <= i; ++j) {
+      double s = A[i][j];
+      for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
+      if (i == j) { if (!(s > 0.0)) return 1; L[i][i] = sqrt(s); }
+      else L[i][j] = s / L[j][j];
+    }
+  }
+  double z[6];
+  for (int i = 0; i < 6; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= L[i][k] * z[k]; z[i] = s / L[i][i]; }
+  for (int i = 5; i >= 0; --i) { double s = z[i]; for (int k = i + 1; k < 6; ++k) s -= L[k][i] * y[k]; y[i] = s / L[i][i]; }
+  return 0;
+}
+
+// Computes the next trust-region step from (H, g) at x; on success sets lm->cand and returns 1.
+// Returns 0 if the solve terminated (lm->done set).
+__device__ int d_compute_step(LmLmState* lm) {
+  for (;;) {
+    if (lm->iteration >= lm->max_iter) { lm->termination = 0; lm->done = 1; return 0; }
+    if (!(lm->radius > 1e-32)) { lm->termination = 4; lm->done = 1; return 0; }
+    lm->iteration++;
+    double Hs[6][6], gs[6];
+    for (int a = 0; a < 6; ++a) { gs[a] = lm->g[a] * lm->scaling[a]; for (int b = 0; b < 6; ++b) Hs[a][b] = d_Hat(lm->H, a, b) * lm->scaling[a] * lm->scaling[b]; }
+    if (!lm->reuse_diagonal)
+      for (int j = 0; j < 6; ++j) { double s = Hs[j][j]; lm->diagonal[j] = s < 1e-6 ? 1e-6 : (s > 1e32 ? 1e32 : s); }
+    double A[6][6];
+    for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) A[a][b] = Hs[a][b];
+    for (int j = 0; j < 6; ++j) A[j][j] += lm->diagonal[j] / lm->radius;     // D^2 = diagonal / radius
+    double y[6];
+    int fail = d_chol6(A, gs, y);
+    for (int j = 0; j < 6; ++j) if (!isfinite(y[j])) fail = 1;
+    lm->reuse_diagonal = 1;
+    int valid = 0;
+    double step[6];
+    if (!fail) {
+      for (int j = 0; j < 6; ++j) step[j] = -y[j];
+      // model_cost_change = -(J s)^T (r + J s / 2) = -(s^T g + s^T H s / 2)
+      double sg = 0.0, sHs = 0.0;
+      for (int a = 0; a < 6; ++a) { sg += step[a] * gs[a]; double row = 0.0; for (int b = 0; b < 6; ++b) row += Hs[a][b] * step[b]; sHs += step[a] * row; }
+      lm->model_cost_change = -(sg + 0.5 * sHs);
+      valid = lm->model_cost_change > 0.0;
+    }
+    if (!valid) {
+      if (++lm->num_invalid >= 5) { lm->termination = 5; lm->done = 1; return 0; }
+      lm->radius *= 0.5; lm->reuse_diagonal = 1;
+      continue;
+    }
+    lm->num_invalid = 0;
+    double delta[6];
+    for (int j = 0; j < 6; ++j) delta[j] = step[j] * lm->scaling[j];
+    d_plus(lm->x, delta, lm->cand);
+    return 1;
+  }
+}
+
+__device__ void d_lm_control(LmLmState* lm, const double* red /*28*/, LmMapState* st, int solve_index, int write_back) {
+  const double cost_e = red[27];
+  if (lm->phase == 0) {
+    // IterationZero
+    lm->cost = cost_e; lm->initial_cost = cost_e;
+    for (int k = 0; k < 21; ++k) lm->H[k] = red[k];
+    for (int k = 0; k < 6; ++k) lm->g[k] = red[21 + k];
+    for (int j = 0; j < 6; ++j) lm->scaling[j] = 1.0 / (1.0 + sqrt(d_Hat(lm->H, j, j)));
+    lm->x_norm = d_norm7(lm->x);
+    lm->phase = 1;
+    if (d_gradient_max_norm(lm->x, lm->g) <= 1e-10) { lm->termination = 1; lm->done = 1; }
+    else d_compute_step(lm);
+  } else {
+    // candidate evaluated
+    const double* x = lm->x; const double* c = lm->cand;
+    double dn = 0.0; for (int i = 0; i < 7; ++i) dn += (x[i] - c[i]) * (x[i] - c[i]);
+    const double step_norm = sqrt(dn);
+    if (step_norm <= 1e-8 * (lm->x_norm + 1e-8)) { lm->termination = 2; lm->done = 1; }
+    else {
+      const double cost_change = lm->cost - cost_e;
+      if (fabs(cost_change) <= 1e-6 * lm->cost) { lm->termination = 3; lm->done = 1; }
+      else {
+        const double rd = cost_change / lm->model_cost_change;
+        if (rd > 1e-3) {
+          for (int i = 0; i < 7; ++i) lm->x[i] = lm->cand[i];
+          lm->x_norm = d_norm7(lm->x);
+          lm->cost = cost_e;
+          for (int k = 0; k < 21; ++k) lm->H[k] = red[k];
+          for (int k = 0; k < 6; ++k) lm->g[k] = red[21 + k];
+          const double tq = 2.0 * rd - 1.0;
+          double den = 1.0 - tq * tq * tq; if (den < 1.0 / 3.0) den = 1.0 / 3.0;
+          lm->radius = lm->radius / den; if (lm->radius > 1e16) lm->radius = 1e16;
+          lm->decrease_factor = 2.0; lm->reuse_diagonal = 0;
+          lm->num_successful++;
+          if (lm->iteration < lm->max_iter && d_gradient_max_norm(lm->x, lm->g) <= 1e-10) { lm->termination = 1; lm->done = 1; }
+        } else {
+          lm->radius = lm->radius / lm->decrease_factor; lm->decrease_factor *= 2.0; lm->reuse_diagonal = 1;
+        }
+        if (!lm->done) d_compute_step(lm);
+      }
+    }
+  }
+  if (lm->done && write_back) {
+    for (int k = 0; k < 4; ++k) st->q_w_curr[k] = lm->x[k];
+    for (int k = 0; k < 3; ++k) st->t_w_curr[k] = lm->x[4 + k];
+    LmSolveSummary* S = &st->solve[solve_index];
+    S->iterations = lm->iteration; S->num_successful = lm->num_successful; S->termination = lm->termination;
+    S->num_factors = lm->nfactors; S->initial_cost = lm->initial_cost; S->final_cost = lm->cost;
+  }
+}
+
+// ---- kernels -----------------------------------------------------------------------------
+__global__ void k_lm_begin(LmLmState* __restrict__ lm, LmMapState* __restrict__ st, const LmFactor* __restrict__ fac0,
+                           const LmFactor* __restrict__ fac1, int solve_index, int max_iter) {
+  // counts the factors of this association pass (corner_num / surf_num, :620,685) and arms the controller
+  __shared__ int ws[33];
+  const int n0 = st->stack_n[0], n1 = st->stack_n[1];
+  int c0 = 0, c1 = 0;
+  if (st->optimize) {
+    for (int i = threadIdx.x; i < n0; i += blockDim.x) c0 += fac0[i].kind >= 0;
+    for (int i = threadIdx.x; i < n1; i += blockDim.x) c1 += fac1[i].kind >= 0;
+  }
+  int t0, t1;
+  d_block_exscan(c0, ws, &t0);
+  d_block_exscan(c1, ws, &t1);
+  if (threadIdx.x == 0) {
+    st->corner_num[solve_index] = t0; st->surf_num[solve_index] = t1;
+    for (int k = 0; k < 4; ++k) lm->x[k] = st->q_w_curr[k];
+    for (int k = 0; k < 3; ++k) lm->x[4 + k] = st->t_w_curr[k];
+    for (int k = 0; k < 7; ++k) lm->cand[k] = lm->x[k];
+    lm->radius = 1e4; lm->decrease_factor = 2.0; lm->reuse_diagonal = 0; lm->num_invalid = 0;
+    lm->iteration = 0; lm->num_successful = 0; lm->termination = 0; lm->phase = 0; lm->max_iter = max_iter;
+    lm->nfactors = t0 + t1; lm->ticket = 0; lm->initial_cost = 0.0; lm->cost = 0.0;
+    lm->done = (!st->optimize || (t0 + t1) == 0) ? 1 : 0;
+    if (lm->done && st->optimize) {   // Ceres: no residual blocks -> parameters untouched
+      LmSolveSummary* S = &st->solve[solve_index];
+      S->iterations = 0; S->num_successful = 0; S->termination = 6; S->num_factors = 0; S->initial_cost = 0.0; S->final_cost = 0.0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(EVAL_THREADS) k_lm_eval(LmLmState* __restrict__ lm, LmMapState* __restrict__ st,
+                                                          const LmFactor* __restrict__ fac0, const LmFactor* __restrict__ fac1,
+                                                          double* __restrict__ partials, int solve_index, int write_back) {
+  if (lm->done) return;
+  __shared__ double sred[EVAL_THREADS / 32][NRED];
+  __shared__ bool s_last;
+  const int n0 = st->stack_n[0], n1 = st->stack_n[1];
+  const double* xe = lm->phase == 0 ? lm->x : lm->cand;
+  const double q[4] = { xe[0], xe[1], xe[2], xe[3] };
+  const double t[3] = { xe[4], xe[5], xe[6] };
+  double acc[NRED];
+#pragma unroll
+  for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1; i += gridDim.x * blockDim.x) {
+    const LmFactor f = i < n0 ? fac0[i] : fac1[i - n0];
+    d_eval_factor(f, q, t, acc);
+  }
+#pragma unroll
+  for (int k = 0; k < NRED; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    acc[k] = v;
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NRED; ++k) sred[wid][k] = acc[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < NRED) {
+    double v = 0.0;
+    for (int w = 0; w < EVAL_THREADS / 32; ++w) v += sred[w][threadIdx.x];
+    partials[(size_t)blockIdx.x * 32 + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int tk = atomicAdd(&lm->ticket, 1u);
+    s_last = (tk == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  __shared__ double fin[NRED];
+  if (threadIdx.x < NRED) {
+    double v = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) v += partials[(size_t)b * 32 + threadIdx.x];   // fixed order
+    fin[threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    lm->ticket = 0;
+    d_lm_control(lm, fin, st, solve_index, write_back);
+  }
+}
+
+// test hook output: H (36), g (6), cost of the factors at q_w_curr/t_w_curr
+__global__ void k_lm_export_normal_eq(const LmLmState* __restrict__ lm, double* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) out[a * 6 + b] = d_Hat(lm->H, a, b);
+  for (int a = 0; a < 6; ++a) out[36 + a] = lm->g[a];
+  out[42] = lm->cost;
+  out[43] = (double)lm->nfactors;
+}
+
+static int eval_blocks(lmono_ctx* ctx, int n) {
+  int b = lm_div_up(n, EVAL_THREADS);
+  if (b < 1) b = 1;
+  if (b > 2 * ctx->sm_count) b = 2 * ctx->sm_count;
+  return b;
+}
+
+int lm_solve_enqueue(lmono_ctx* ctx, int solve_index, int n_max_corner, int n_max_surf, int max_iter) {
+  k_lm_begin<<<1, 1024, 0, ctx->stream>>>(ctx->d_lm, ctx->d_state, ctx->d_fac[0], ctx->d_fac[1], solve_index, max_iter);
+  LM_LAUNCH_CHECK();
+  const int blocks = eval_blocks(ctx, n_max_corner + n_max_surf);
+  for (int it = 0; it <= max_iter; ++it) {
+    k_lm_eval<<<blocks, EVAL_THREADS, 0, ctx->stream>>>(ctx->d_lm, ctx->d_state, ctx->d_fac[0], ctx->d_fac[1], ctx->d_partials, solve_index, 1);
+    LM_LAUNCH_CHECK();
+  }
+  return LMONO_OK;
+}
+
+int lm_normal_eq_enqueue(lmono_ctx* ctx, int n_max_corner, int n_max_surf) {
+  // max_iter = 0: IterationZero fills H, g, cost and the controller stops immediately
+  k_lm_begin<<<1, 1024, 0, ctx->stream>>>(ctx->d_lm, ctx->d_state, ctx->d_fac[0], ctx->d_fac[1], 0, 0);
+  LM_LAUNCH_CHECK();
+  const int blocks = eval_blocks(ctx, n_max_corner + n_max_surf);
+  k_lm_eval<<<blocks, EVAL_THREADS, 0, ctx->stream>>>(ctx->d_lm, ctx->d_state, ctx->d_fac[0], ctx->d_fac[1], ctx->d_partials, 0, 0);
+  LM_LAUNCH_CHECK();
+  k_lm_export_normal_eq<<<1, 32, 0, ctx->stream>>>(ctx->d_lm, ctx->d_partials + 32 * 1024);
+  LM_LAUNCH_CHECK();
+  return LMONO_OK;
+}

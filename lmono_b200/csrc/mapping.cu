@@ -1,0 +1,250 @@
+// C-ABI entry points of the laserMapping stage (Aloam/src/laserMapping.cpp:307-801, 838-842)
+// and its test hooks.  A step is a fixed sequence of kernel launches on the ctx stream with
+// no host synchronisation until the results are collected.
+#include "common.cuh"
+#include <string.h>
+#include <stdlib.h>
+
+int lm_map_clear_device(lmono_ctx* ctx);
+int lm_map_export_device(lmono_ctx* ctx, int which, int scope, int* n_total);
+int lm_map_import_device(lmono_ctx* ctx, int which, const float4* d_pts, int n,
+                         unsigned long long* d_a, unsigned long long* d_b, unsigned long long* d_c,
+                         int32_t* d_n, int32_t* d_blockcnt, int32_t* d_head_rank);
+
+// transformUpdate (:148-152) + frame counter
+__global__ void k_transform_update(LmMapState* st) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double qi[4]; d_qinv(st->q_wodom_curr, qi);
+  double qn[4]; d_qmul(st->q_w_curr, qi, qn);
+  for (int k = 0; k < 4; ++k) st->q_wmap_wodom[k] = qn[k];
+  double tmp[3]; d_qrot(st->q_wmap_wodom, st->t_wodom_curr, tmp);
+  for (int k = 0; k < 3; ++k) st->t_wmap_wodom[k] = st->t_w_curr[k] - tmp[k];
+  st->frame_count++;
+}
+
+// :838-842 full-resolution sweep to the world frame
+__global__ void __launch_bounds__(256) k_transform_cloud(const LmMapState* __restrict__ st, const float4* __restrict__ in, int n, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = d_associate(st->q_w_curr, st->t_w_curr, in[i]);
+}
+
+__global__ void k_set_counts(LmMapState* st, int n0, int n1) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { st->raw_n[0] = n0; st->raw_n[1] = n1; }
+}
+
+// enqueue the whole step on inputs that are already float4 XYZI in device memory
+static int enqueue_step(lmono_ctx* ctx, const float4* d_corner, int nc, const float4* d_surf, int ns, const lmono_pose* wodom_curr) {
+  if (nc < 0 || ns < 0 || nc > ctx->max_feat || ns > ctx->max_feat) return LMONO_E_CAPACITY;
+  int rc;
+  LM_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  k_set_counts<<<1, 32, 0, ctx->stream>>>(ctx->d_state, nc, ns);
+  LM_LAUNCH_CHECK();
+  if ((rc = lm_map_begin_step(ctx, wodom_curr, nullptr))) return rc;        // :309-539
+  if ((rc = lm_map_index_build(ctx))) return rc;                            // replaces kdtree setInputCloud :558-559
+  // :542-550 VoxelGrid of the incoming features
+  if ((rc = lm_voxel_grid_device(ctx, d_corner, &ctx->d_state->raw_n[0], nc, ctx->map[0].leaf, ctx->d_stack[0], &ctx->d_state->stack_n[0]))) return rc;
+  if ((rc = lm_voxel_grid_device(ctx, d_surf, &ctx->d_state->raw_n[1], ns, ctx->map[1].leaf, ctx->d_stack[1], &ctx->d_state->stack_n[1]))) return rc;
+  for (int iter = 0; iter < 2; ++iter) {                                    // :562
+    if ((rc = lm_map_associate(ctx, nc, ns))) return rc;                    // :577-687
+    if ((rc = lm_solve_enqueue(ctx, iter, nc, ns, 4))) return rc;           // :713-720
+  }
+  k_transform_update<<<1, 32, 0, ctx->stream>>>(ctx->d_state);              // :734
+  LM_LAUNCH_CHECK();
+  if ((rc = lm_map_insert_and_refilter(ctx, nc, ns))) return rc;            // :737-801
+  LM_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->step_pending = true;
+  return LMONO_OK;
+}
+
+static void fill_report(const LmMapState* h, lmono_map_report* r, float ms) {
+  memset(r, 0, sizeof(*r));
+  r->corner_from_map = h->from_map_n[0]; r->surf_from_map = h->from_map_n[1];
+  r->corner_stack = h->stack_n[0]; r->surf_stack = h->stack_n[1];
+  for (int k = 0; k < 2; ++k) {
+    r->corner_num[k] = h->corner_num[k]; r->surf_num[k] = h->surf_num[k];
+    r->solve[k].iterations = h->solve[k].iterations; r->solve[k].num_successful = h->solve[k].num_successful;
+    r->solve[k].termination = h->solve[k].termination; r->solve[k].num_factors = h->solve[k].num_factors;
+    r->solve[k].initial_cost = h->solve[k].initial_cost; r->solve[k].final_cost = h->solve[k].final_cost;
+  }
+  r->optimized = h->optimize;
+  for (int k = 0; k < 3; ++k) { r->center_cube[k] = h->center[k]; r->cen[k] = h->cen[k]; }
+  r->ms_gpu = ms;
+}
+
+static int collect(lmono_ctx* ctx, lmono_pose* w_curr, lmono_pose* wmap_wodom, lmono_map_report* report) {
+  LM_CUDA(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(LmMapState), cudaMemcpyDeviceToHost, ctx->stream));
+  LM_CUDA(cudaStreamSynchronize(ctx->stream));
+  const LmMapState* h = ctx->h_state;
+  if (w_curr) { memcpy(w_curr->q, h->q_w_curr, sizeof(w_curr->q)); memcpy(w_curr->t, h->t_w_curr, sizeof(w_curr->t)); }
+  if (wmap_wodom) { memcpy(wmap_wodom->q, h->q_wmap_wodom, sizeof(wmap_wodom->q)); memcpy(wmap_wodom->t, h->t_wmap_wodom, sizeof(wmap_wodom->t)); }
+  float ms = 0.f;
+  if (ctx->step_pending) { cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->step_pending = false; }
+  if (report) fill_report(h, report, ms);
+  if (h->fault) {
+    fprintf(stderr, "[lmono_b200] device fault bits 0x%x\n", h->fault);
+    cudaMemsetAsync(&ctx->d_state->fault, 0, sizeof(uint32_t), ctx->stream);
+    return LMONO_E_DEVICE;
+  }
+  return LMONO_OK;
+}
+
+extern "C" int lmono_map_step_device(lmono_ctx* ctx, const void* d_corner, int32_t nc, const void* d_surf, int32_t ns,
+                                     const lmono_pose* wodom_curr) {
+  if (!ctx || !wodom_curr) return LMONO_E_ARG;
+  return enqueue_step(ctx, (const float4*)d_corner, nc, (const float4*)d_surf, ns, wodom_curr);
+}
+
+extern "C" int lmono_map_collect(lmono_ctx* ctx, lmono_pose* w_curr, lmono_pose* wmap_wodom, lmono_map_report* report) {
+  if (!ctx) return LMONO_E_ARG;
+  return collect(ctx, w_curr, wmap_wodom, report);
+}
+
+extern "C" int lmono_map_step(lmono_ctx* ctx, lmono_cloud_view corner_last, lmono_cloud_view surf_last,
+                              const lmono_pose* wodom_curr, lmono_pose* w_curr, lmono_pose* wmap_wodom,
+                              lmono_map_report* report, lmono_cloud_view full_res, lmono_cloud_out* registered) {
+  if (!ctx || !wodom_curr) return LMONO_E_ARG;
+  if (corner_last.n > ctx->max_feat || surf_last.n > ctx->max_feat || full_res.n > ctx->max_sweep) return LMONO_E_CAPACITY;
+  int rc;
+  if ((rc = lm_upload_cloud(ctx, corner_last, ctx->d_raw[0], ctx->d_in[0], nullptr))) return rc;
+  if ((rc = lm_upload_cloud(ctx, surf_last, ctx->d_raw[1], ctx->d_in[1], nullptr))) return rc;
+  if ((rc = enqueue_step(ctx, ctx->d_in[0], corner_last.n, ctx->d_in[1], surf_last.n, wodom_curr))) return rc;
+  const bool want_full = registered && full_res.n > 0;
+  if (want_full) {
+    float4* d_full_in = (float4*)ctx->d_raw[0];   // raw staging is free again once the step is enqueued
+    if ((rc = lm_upload_cloud(ctx, full_res, ctx->d_raw[2], d_full_in, nullptr))) return rc;
+    k_transform_cloud<<<lm_div_up(full_res.n, 256), 256, 0, ctx->stream>>>(ctx->d_state, d_full_in, full_res.n, ctx->d_full);
+    LM_LAUNCH_CHECK();
+  }
+  rc = collect(ctx, w_curr, wmap_wodom, report);
+  if (want_full) { int rc2 = lm_download_cloud(ctx, ctx->d_full, full_res.n, registered); if (!rc) rc = rc2; }
+  else if (registered) registered->n_out = 0;
+  return rc;
+}
+
+extern "C" int lmono_map_get_state(lmono_ctx* ctx, lmono_pose* wmap_wodom, int32_t cen[3]) {
+  if (!ctx) return LMONO_E_ARG;
+  LM_CUDA(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(LmMapState), cudaMemcpyDeviceToHost, ctx->stream));
+  LM_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (wmap_wodom) { memcpy(wmap_wodom->q, ctx->h_state->q_wmap_wodom, 32); memcpy(wmap_wodom->t, ctx->h_state->t_wmap_wodom, 24); }
+  if (cen) for (int k = 0; k < 3; ++k) cen[k] = ctx->h_state->cen[k];
+  return LMONO_OK;
+}
+
+extern "C" int lmono_map_set_state(lmono_ctx* ctx, const lmono_pose* p) {
+  if (!ctx || !p) return LMONO_E_ARG;
+  LM_CUDA(cudaMemcpyAsync(ctx->d_state->q_wmap_wodom, p->q, 32, cudaMemcpyHostToDevice, ctx->stream));
+  LM_CUDA(cudaMemcpyAsync(ctx->d_state->t_wmap_wodom, p->t, 24, cudaMemcpyHostToDevice, ctx->stream));
+  LM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return LMONO_OK;
+}
+
+extern "C" int lmono_map_clear(lmono_ctx* ctx) {
+  if (!ctx) return LMONO_E_ARG;
+  return lm_map_clear_device(ctx);
+}
+
+extern "C" int lmono_map_export(lmono_ctx* ctx, int which, int scope, lmono_cloud_out* out) {
+  if (!ctx || !out || which < 0 || which > 1 || scope < 0 || scope > 1) return LMONO_E_ARG;
+  int total = 0;
+  int rc = lm_map_export_device(ctx, which, scope, &total);
+  if (rc) return rc;
+  return lm_download_cloud(ctx, ctx->d_export, total, out);
+}
+
+extern "C" int lmono_map_import(lmono_ctx* ctx, int which, lmono_cloud_view pts) {
+  if (!ctx || which < 0 || which > 1) return LMONO_E_ARG;
+  if (pts.n <= 0) return LMONO_OK;
+  if (pts.n >= (1 << 21)) return LMONO_E_CAPACITY;
+  const size_t n = (size_t)pts.n;
+  float4* d_pts = nullptr; uint8_t* d_rawtmp = nullptr;
+  unsigned long long *a = nullptr, *b = nullptr, *c = nullptr; int32_t* ints = nullptr;
+  LM_CUDA(cudaMalloc((void**)&d_pts, n * sizeof(float4)));
+  LM_CUDA(cudaMalloc((void**)&d_rawtmp, n * (size_t)pts.stride_bytes));
+  LM_CUDA(cudaMalloc((void**)&a, n * 8)); LM_CUDA(cudaMalloc((void**)&b, n * 8)); LM_CUDA(cudaMalloc((void**)&c, n * 8));
+  LM_CUDA(cudaMalloc((void**)&ints, sizeof(int32_t) * (n + n / 256 + 64)));
+  size_t saved = ctx->raw_bytes; ctx->raw_bytes = n * (size_t)pts.stride_bytes;
+  int rc = lm_upload_cloud(ctx, pts, d_rawtmp, d_pts, nullptr);
+  ctx->raw_bytes = saved;
+  if (!rc) rc = lm_map_import_device(ctx, which, d_pts, pts.n, a, b, c, ints, ints + 16, ints + 16 + (n / 256 + 32));
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_pts); cudaFree(d_rawtmp); cudaFree(a); cudaFree(b); cudaFree(c); cudaFree(ints);
+  if (rc) return rc;
+  uint32_t bits = 0;
+  lmono_last_fault(ctx, &bits);
+  if (bits) { fprintf(stderr, "[lmono_b200] import fault bits 0x%x\n", bits); return LMONO_E_DEVICE; }
+  return LMONO_OK;
+}
+
+extern "C" int lmono_map_prepare_window(lmono_ctx* ctx, const double t_w_curr[3]) {
+  if (!ctx || !t_w_curr) return LMONO_E_ARG;
+  int rc = lm_map_begin_step(ctx, nullptr, t_w_curr);
+  if (rc) return rc;
+  if ((rc = lm_map_index_build(ctx))) return rc;
+  LM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return LMONO_OK;
+}
+
+extern "C" int lmono_knn5_device(lmono_ctx* ctx, int which, const void* d_q, int32_t n, void* d_idx, void* d_d2) {
+  if (!ctx || which < 0 || which > 1) return LMONO_E_ARG;
+  return lm_knn5_device(ctx, which, (const float4*)d_q, n, (int32_t*)d_idx, (float*)d_d2);
+}
+
+extern "C" int lmono_knn5(lmono_ctx* ctx, int which, lmono_cloud_view q, int32_t* idx, float* d2) {
+  if (!ctx || which < 0 || which > 1 || !idx || !d2) return LMONO_E_ARG;
+  if (q.n <= 0) return LMONO_OK;
+  if (q.n > ctx->max_feat) return LMONO_E_CAPACITY;
+  int rc = lm_upload_cloud(ctx, q, ctx->d_raw[0], ctx->d_in[0], nullptr);
+  if (rc) return rc;
+  int32_t* d_idx = (int32_t*)ctx->d_sort_a; float* d_d2 = (float*)ctx->d_sort_b;
+  if ((rc = lm_knn5_device(ctx, which, ctx->d_in[0], q.n, d_idx, d_d2))) return rc;
+  LM_CUDA(cudaMemcpyAsync(idx, d_idx, (size_t)q.n * 5 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  LM_CUDA(cudaMemcpyAsync(d2, d_d2, (size_t)q.n * 5 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  LM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return LMONO_OK;
+}
+
+__global__ void k_set_pose_and_counts(LmMapState* st, double qx, double qy, double qz, double qw, double tx, double ty, double tz, int n0, int n1) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  st->q_w_curr[0] = qx; st->q_w_curr[1] = qy; st->q_w_curr[2] = qz; st->q_w_curr[3] = qw;
+  st->t_w_curr[0] = tx; st->t_w_curr[1] = ty; st->t_w_curr[2] = tz;
+  st->stack_n[0] = n0; st->stack_n[1] = n1;
+  st->optimize = 1;
+}
+
+extern "C" int lmono_map_normal_eq(lmono_ctx* ctx, lmono_cloud_view corner_stack, lmono_cloud_view surf_stack,
+                                   const lmono_pose* w, double H[36], double g[6], double* cost,
+                                   int32_t* n_corner, int32_t* n_surf) {
+  if (!ctx || !w || !H || !g || !cost) return LMONO_E_ARG;
+  if (corner_stack.n > ctx->max_feat || surf_stack.n > ctx->max_feat) return LMONO_E_CAPACITY;
+  int rc;
+  if ((rc = lm_map_begin_step(ctx, nullptr, w->t))) return rc;
+  if ((rc = lm_map_index_build(ctx))) return rc;
+  if ((rc = lm_upload_cloud(ctx, corner_stack, ctx->d_raw[0], ctx->d_stack[0], nullptr))) return rc;
+  if ((rc = lm_upload_cloud(ctx, surf_stack, ctx->d_raw[1], ctx->d_stack[1], nullptr))) return rc;
+  k_set_pose_and_counts<<<1, 32, 0, ctx->stream>>>(ctx->d_state, w->q[0], w->q[1], w->q[2], w->q[3], w->t[0], w->t[1], w->t[2],
+                                                   corner_stack.n, surf_stack.n);
+  LM_LAUNCH_CHECK();
+  if ((rc = lm_map_associate(ctx, corner_stack.n, surf_stack.n))) return rc;
+  if ((rc = lm_normal_eq_enqueue(ctx, corner_stack.n, surf_stack.n))) return rc;
+  double out[44];
+  LM_CUDA(cudaMemcpyAsync(out, ctx->d_partials + 32 * 1024, sizeof(out), cudaMemcpyDeviceToHost, ctx->stream));
+  LM_CUDA(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(LmMapState), cudaMemcpyDeviceToHost, ctx->stream));
+  LM_CUDA(cudaStreamSynchronize(ctx->stream));
+  memcpy(H, out, 36 * sizeof(double)); memcpy(g, out + 36, 6 * sizeof(double)); *cost = out[42];
+  if (n_corner) *n_corner = ctx->h_state->corner_num[0];
+  if (n_surf) *n_surf = ctx->h_state->surf_num[0];
+  return LMONO_OK;
+}
+
+extern "C" int lmono_voxel_grid(lmono_ctx* ctx, lmono_cloud_view in, float leaf, lmono_cloud_out* out) {
+  if (!ctx || !out || !(leaf > 0)) return LMONO_E_ARG;
+  if (in.n > ctx->max_feat) return LMONO_E_CAPACITY;
+  int rc = lm_upload_cloud(ctx, in, ctx->d_raw[0], ctx->d_in[0], &ctx->d_state->raw_n[0]);
+  if (rc) return rc;
+  if ((rc = lm_voxel_grid_device(ctx, ctx->d_in[0], &ctx->d_state->raw_n[0], in.n, leaf, ctx->d_stack[0], &ctx->d_state->stack_n[0]))) return rc;
+  int n_out = 0;
+  LM_CUDA(cudaMemcpyAsync(&n_out, &ctx->d_state->stack_n[0], sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  LM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return lm_download_cloud(ctx, ctx->d_stack[0], n_out, out);
+}

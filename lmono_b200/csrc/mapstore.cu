@@ -1,0 +1,691 @@
+// Device-resident rolling cube map of laserMapping (Aloam/src/laserMapping.cpp:74-104).
+//
+// Layout in HBM (per map type: 0 corner, 1 surf):
+//   * the reference's 21x21x11 array of cube clouds becomes a ring buffer: absolute cube
+//     g = logical index - laserCloudCen{Width,Height,Depth} lives in physical slot
+//     (g mod 21, g mod 21, g mod 11); the pointer rotations of :323-507 reduce to updating
+//     the three Cen offsets and freeing the recycled plane.
+//   * each non-empty cube owns a slab from a pool: float4 XYZI points in exactly the order
+//     the reference's cube cloud would have (VoxelGrid output order = ascending voxel key,
+//     then appended points), ping-pong buffered so a refilter never works in place.
+//   * per slab a 26^3 table of 2 m cells (key floor(x)>>1) with a cell-sorted copy of the
+//     points carrying their slab position: the exact-kNN search structure (assoc.cu).
+//
+// Per-sweep upkeep is O(points touched), not O(map): only cubes that received points are
+// re-filtered (a VoxelGrid pass over an already filtered cube is the identity, SURVEY
+// App. B.3), by merging the stably sorted new points into the sorted prefix.
+#include "common.cuh"
+
+// ------------------------------------------------------------------ allocation
+template <typename T> static int dev_alloc(lmono_ctx* ctx, T** p, size_t count) {
+  LM_CUDA(cudaMalloc((void**)p, count * sizeof(T)));
+  return LMONO_OK;
+}
+
+__global__ void k_map_reset(LmMapType M) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < LM_NSLOT; i += gridDim.x * blockDim.x) M.slot_slab[i] = -1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M.n_slabs; i += gridDim.x * blockDim.x) {
+    M.free_stack[i] = M.n_slabs - 1 - i;   // pop order 0,1,2,...
+    M.slab_n[i] = 0; M.slab_nsorted[i] = 0; M.slab_cur[i] = 0; M.slab_dirty[i] = 0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *M.free_top = M.n_slabs;
+}
+
+int lm_map_alloc(lmono_ctx* ctx) {
+  for (int ty = 0; ty < 2; ++ty) {
+    LmMapType& M = ctx->map[ty];
+    M.leaf = ty == 0 ? ctx->prm.mapping_line_resolution : ctx->prm.mapping_plane_resolution;
+    M.inv_leaf = 1.0f / M.leaf;
+    M.cap = ty == 0 ? ctx->prm.cube_capacity_corner : ctx->prm.cube_capacity_surf;
+    M.n_slabs = ty == 0 ? ctx->prm.max_cubes_corner : ctx->prm.max_cubes_surf;
+    int rc;
+    if ((rc = dev_alloc(ctx, &M.pts, (size_t)M.n_slabs * 2 * M.cap))) return rc;
+    if ((rc = dev_alloc(ctx, &M.cellpts, (size_t)M.n_slabs * M.cap))) return rc;
+    if ((rc = dev_alloc(ctx, &M.cellstart, (size_t)M.n_slabs * (LM_NCELL + 1)))) return rc;
+    if ((rc = dev_alloc(ctx, &M.pkey, (size_t)M.n_slabs * M.cap))) return rc;
+    if ((rc = dev_alloc(ctx, &M.slot_slab, (size_t)LM_NSLOT))) return rc;
+    if ((rc = dev_alloc(ctx, &M.slab_n, (size_t)M.n_slabs))) return rc;
+    if ((rc = dev_alloc(ctx, &M.slab_nsorted, (size_t)M.n_slabs))) return rc;
+    if ((rc = dev_alloc(ctx, &M.slab_cur, (size_t)M.n_slabs))) return rc;
+    if ((rc = dev_alloc(ctx, &M.slab_dirty, (size_t)M.n_slabs))) return rc;
+    if ((rc = dev_alloc(ctx, &M.slab_g, (size_t)M.n_slabs * 4))) return rc;
+    if ((rc = dev_alloc(ctx, &M.free_stack, (size_t)M.n_slabs))) return rc;
+    if ((rc = dev_alloc(ctx, &M.free_top, 1))) return rc;
+    k_map_reset<<<32, 256, 0, ctx->stream>>>(M);
+    LM_LAUNCH_CHECK();
+  }
+  return LMONO_OK;
+}
+
+void lm_map_free(lmono_ctx* ctx) {
+  for (int ty = 0; ty < 2; ++ty) {
+    LmMapType& M = ctx->map[ty];
+    cudaFree(M.pts); cudaFree(M.cellpts); cudaFree(M.cellstart); cudaFree(M.pkey); cudaFree(M.slot_slab);
+    cudaFree(M.slab_n); cudaFree(M.slab_nsorted); cudaFree(M.slab_cur); cudaFree(M.slab_dirty);
+    cudaFree(M.slab_g); cudaFree(M.free_stack); cudaFree(M.free_top);
+  }
+}
+
+int lm_map_clear_device(lmono_ctx* ctx) {
+  for (int ty = 0; ty < 2; ++ty) { k_map_reset<<<32, 256, 0, ctx->stream>>>(ctx->map[ty]); LM_LAUNCH_CHECK(); }
+  return LMONO_OK;
+}
+
+// ------------------------------------------------------------------ begin step: pose, window
+struct PoseArg { double q[4]; double t[3]; };
+
+__device__ __forceinline__ void d_free_slot(const LmMapType& M, int ps) {
+  int sid = M.slot_slab[ps];
+  if (sid >= 0) {
+    M.slot_slab[ps] = -1;
+    M.slab_n[sid] = 0; M.slab_nsorted[sid] = 0; M.slab_dirty[sid] = 0;
+    int pos = atomicAdd(M.free_top, 1);
+    M.free_stack[pos] = sid;
+  }
+}
+
+// transformAssociateToMap (:142-146), centre cube (:312-321), the six shift loops
+// (:323-507), the valid list (:512-529) and the per-type offsets of the concatenation
+// (:533-539), all on device so consecutive sweeps need no host round trip.
+__global__ void __launch_bounds__(256) k_begin_step(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1,
+                                                    int32_t* __restrict__ slot_valid_rank, PoseArg odom,
+                                                    int use_override, double ox, double oy, double oz) {
+  __shared__ unsigned clear_mask[3];
+  __shared__ int s_n[2][LM_MAX_VALID + 3];
+  __shared__ int s_all;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 4; ++k) st->q_wodom_curr[k] = odom.q[k];
+    for (int k = 0; k < 3; ++k) st->t_wodom_curr[k] = odom.t[k];
+    double tw[3];
+    if (use_override) {
+      tw[0] = ox; tw[1] = oy; tw[2] = oz;
+      st->q_w_curr[0] = st->q_w_curr[1] = st->q_w_curr[2] = 0.0; st->q_w_curr[3] = 1.0;
+    } else {
+      d_qmul(st->q_wmap_wodom, odom.q, st->q_w_curr);
+      double tmp[3]; d_qrot(st->q_wmap_wodom, odom.t, tmp);
+      for (int k = 0; k < 3; ++k) tw[k] = tmp[k] + st->t_wmap_wodom[k];
+    }
+    for (int k = 0; k < 3; ++k) st->t_w_curr[k] = tw[k];
+    const int dim[3] = { LM_GW, LM_GH, LM_GD };
+    int all = 0;
+    for (int a = 0; a < 3; ++a) {
+      unsigned mask = 0;
+      int cen = st->cen[a];
+      int c = d_cube_coord(tw[a], cen);
+      int shifts = 0;
+      while (c < 3) {                    // contents move up, logical plane dim-1 is recycled
+        mask |= 1u << d_pmod(dim[a] - 1 - cen, dim[a]);
+        c++; cen++;
+        if (++shifts >= dim[a]) { int need = 3 - c; if (need > 0) { c += need; cen += need; } all = 1; break; }
+      }
+      shifts = 0;
+      while (c >= dim[a] - 3) {          // contents move down, logical plane 0 is recycled
+        mask |= 1u << d_pmod(-cen, dim[a]);
+        c--; cen--;
+        if (++shifts >= dim[a]) { int need = c - (dim[a] - 4); if (need > 0) { c -= need; cen -= need; } all = 1; break; }
+      }
+      st->cen[a] = cen; st->center[a] = c;
+      clear_mask[a] = mask;
+    }
+    s_all = all;
+    // valid cubes in the reference's loop order (i outer, j, k inner)
+    int vn = 0;
+    for (int i = st->center[0] - 2; i <= st->center[0] + 2; i++)
+      for (int j = st->center[1] - 2; j <= st->center[1] + 2; j++)
+        for (int k = st->center[2] - 1; k <= st->center[2] + 1; k++)
+          if (i >= 0 && i < LM_GW && j >= 0 && j < LM_GH && k >= 0 && k < LM_GD)
+            st->valid_slot[vn++] = d_phys_slot(i - st->cen[0], j - st->cen[1], k - st->cen[2]);
+    st->valid_num = vn;
+    st->corner_num[0] = st->corner_num[1] = st->surf_num[0] = st->surf_num[1] = 0;
+    for (int s = 0; s < 2; ++s) { st->solve[s].iterations = 0; st->solve[s].num_successful = 0; st->solve[s].termination = 6; st->solve[s].num_factors = 0; st->solve[s].initial_cost = 0.0; st->solve[s].final_cost = 0.0; }
+  }
+  __syncthreads();
+  // free recycled planes
+  const unsigned mi = clear_mask[0], mj = clear_mask[1], mk = clear_mask[2];
+  const int all = s_all;
+  if (mi | mj | mk | (unsigned)all) {
+    for (int ps = threadIdx.x; ps < LM_NSLOT; ps += blockDim.x) {
+      int pi = ps % LM_GW, pj = (ps / LM_GW) % LM_GH, pk = ps / (LM_GW * LM_GH);
+      if (all || ((mi >> pi) & 1u) || ((mj >> pj) & 1u) || ((mk >> pk) & 1u)) { d_free_slot(M0, ps); d_free_slot(M1, ps); }
+    }
+  }
+  for (int ps = threadIdx.x; ps < LM_NSLOT; ps += blockDim.x) slot_valid_rank[ps] = -1;
+  __syncthreads();
+  const int vn = st->valid_num;
+  if ((int)threadIdx.x < vn) {
+    int ps = st->valid_slot[threadIdx.x];
+    slot_valid_rank[ps] = threadIdx.x;
+    int s0 = M0.slot_slab[ps], s1 = M1.slot_slab[ps];
+    s_n[0][threadIdx.x] = s0 >= 0 ? M0.slab_n[s0] : 0;
+    s_n[1][threadIdx.x] = s1 >= 0 ? M1.slab_n[s1] : 0;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    int acc = 0;
+    for (int r = 0; r < vn; ++r) { st->valid_off[threadIdx.x][r] = acc; acc += s_n[threadIdx.x][r]; }
+    st->valid_off[threadIdx.x][vn] = acc;
+    st->from_map_n[threadIdx.x] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) st->optimize = (st->from_map_n[0] > 10 && st->from_map_n[1] > 50) ? 1 : 0;   // :554
+}
+
+int lm_map_begin_step(lmono_ctx* ctx, const lmono_pose* wodom_curr, const double* t_override) {
+  PoseArg pa;
+  if (wodom_curr) { for (int k = 0; k < 4; ++k) pa.q[k] = wodom_curr->q[k]; for (int k = 0; k < 3; ++k) pa.t[k] = wodom_curr->t[k]; }
+  else { pa.q[0] = pa.q[1] = pa.q[2] = 0; pa.q[3] = 1; pa.t[0] = pa.t[1] = pa.t[2] = 0; }
+  k_begin_step<<<1, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_slot_valid_rank, pa,
+                                           t_override ? 1 : 0, t_override ? t_override[0] : 0.0,
+                                           t_override ? t_override[1] : 0.0, t_override ? t_override[2] : 0.0);
+  LM_LAUNCH_CHECK();
+  return LMONO_OK;
+}
+
+// ------------------------------------------------------------------ cell index of one slab
+// s_cnt: shared uint32[LM_NCELL]; ws: shared int[33].  All threads of the block call this.
+__device__ void d_build_cell_index(const LmMapType& M, int sid, const float4* __restrict__ src, int n,
+                                   uint32_t* s_cnt, int* ws, LmMapState* st) {
+  const int* g = M.slab_g + sid * 4;
+  const int g3[3] = { g[0], g[1], g[2] };
+  for (int i = threadIdx.x; i < LM_NCELL; i += blockDim.x) s_cnt[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    int c = d_cube_cell(src[i], g3);
+    if (c < 0) { atomicOr(&st->fault, LM_FAULT_CELL_RANGE); c = 0; }
+    atomicAdd(&s_cnt[c], 1u);
+  }
+  __syncthreads();
+  const int per = (LM_NCELL + blockDim.x - 1) / blockDim.x;
+  const int b = min((int)threadIdx.x * per, LM_NCELL), e = min(b + per, LM_NCELL);
+  int sum = 0;
+  for (int c = b; c < e; ++c) sum += (int)s_cnt[c];
+  int total;
+  int run = d_block_exscan(sum, ws, &total);
+  for (int c = b; c < e; ++c) { int v = (int)s_cnt[c]; s_cnt[c] = (uint32_t)run; run += v; }
+  __syncthreads();
+  uint32_t* cs = M.cellstart + (size_t)sid * (LM_NCELL + 1);
+  for (int i = threadIdx.x; i < LM_NCELL; i += blockDim.x) cs[i] = s_cnt[i];
+  if (threadIdx.x == 0) cs[LM_NCELL] = (uint32_t)n;
+  __syncthreads();
+  float4* cp = M.cellpts + (size_t)sid * M.cap;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float4 p = src[i];
+    int c = d_cube_cell(p, g3);
+    if (c < 0) c = 0;
+    uint32_t pos = atomicAdd(&s_cnt[c], 1u);
+    p.w = __int_as_float(i);
+    cp[pos] = p;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024, 1) k_index_build(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1) {
+  extern __shared__ unsigned char smem_raw[];
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem_raw);
+  int* ws = reinterpret_cast<int*>(s_cnt + LM_NCELL);
+  const int r = blockIdx.x;
+  if (r >= st->valid_num) return;
+  const LmMapType& M = blockIdx.y == 0 ? M0 : M1;
+  const int ps = st->valid_slot[r];
+  const int sid = M.slot_slab[ps];
+  if (sid < 0) return;
+  if (!M.slab_dirty[sid]) return;
+  const int n = M.slab_n[sid];
+  const float4* src = M.pts + ((size_t)sid * 2 + M.slab_cur[sid]) * M.cap;
+  d_build_cell_index(M, sid, src, n, s_cnt, ws, st);
+  if (threadIdx.x == 0) M.slab_dirty[sid] = 0;
+}
+
+static const int kIndexSmem = LM_NCELL * 4 + 64 * 4;
+
+int lm_map_index_build(lmono_ctx* ctx) {
+  k_index_build<<<dim3(75, 2), 1024, kIndexSmem, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1]);
+  LM_LAUNCH_CHECK();
+  return LMONO_OK;
+}
+
+// ------------------------------------------------------------------ insertion (:737-783)
+// key = type << 13 | physical slot (8191 = rejected), composite = key << 32 | index in stack
+__global__ void __launch_bounds__(256) k_insert_prepare(LmMapState* __restrict__ st, const float4* __restrict__ stack0,
+                                                        const float4* __restrict__ stack1, float4* __restrict__ world0,
+                                                        float4* __restrict__ world1, unsigned long long* __restrict__ comp,
+                                                        int32_t* __restrict__ n_ins) {
+  const int n0 = st->stack_n[0], n1 = st->stack_n[1];
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e == 0) *n_ins = n0 + n1;
+  if (e >= n0 + n1) return;
+  const int ty = e < n0 ? 0 : 1;
+  const int i = ty == 0 ? e : e - n0;
+  float4 pw = d_associate(st->q_w_curr, st->t_w_curr, ty == 0 ? stack0[i] : stack1[i]);
+  (ty == 0 ? world0 : world1)[i] = pw;
+  int cI = d_cube_coord((double)pw.x, st->cen[0]);
+  int cJ = d_cube_coord((double)pw.y, st->cen[1]);
+  int cK = d_cube_coord((double)pw.z, st->cen[2]);
+  uint32_t ps = 8191u;
+  if (cI >= 0 && cI < LM_GW && cJ >= 0 && cJ < LM_GH && cK >= 0 && cK < LM_GD)
+    ps = (uint32_t)d_phys_slot(cI - st->cen[0], cJ - st->cen[1], cK - st->cen[2]);
+  comp[e] = ((unsigned long long)(((uint32_t)ty << 13) | ps) << 32) | (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256) k_insert_heads(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1,
+                                                      const unsigned long long* __restrict__ sorted, const int32_t* __restrict__ n_ins,
+                                                      const float4* __restrict__ world0, const float4* __restrict__ world1,
+                                                      int32_t* __restrict__ slot_first, int32_t* __restrict__ slot_base,
+                                                      int32_t* __restrict__ slot_len) {
+  const int n = *n_ins;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const unsigned long long me = sorted[p];
+  const uint32_t key = (uint32_t)(me >> 32);
+  if (p > 0 && (uint32_t)(sorted[p - 1] >> 32) == key) return;   // not a run head
+  const uint32_t ps = key & 8191u;
+  if (ps == 8191u) return;                                        // outside the 21x21x11 grid: dropped (:752-754)
+  const int ty = (int)(key >> 13);
+  const LmMapType& M = ty == 0 ? M0 : M1;
+  const int run_end = d_lower_bound_u64(sorted, n, (unsigned long long)(key + 1u) << 32);
+  int len = run_end - p;
+  int sid = M.slot_slab[ps];
+  if (sid < 0) {
+    int top = atomicSub(M.free_top, 1) - 1;
+    if (top < 0) { atomicAdd(M.free_top, 1); atomicOr(&st->fault, LM_FAULT_POOL_EXHAUSTED); slot_first[ty * LM_NSLOT + ps] = p; slot_len[ty * LM_NSLOT + ps] = 0; slot_base[ty * LM_NSLOT + ps] = 0; return; }
+    sid = M.free_stack[top];
+    M.slot_slab[ps] = sid;
+    M.slab_n[sid] = 0; M.slab_nsorted[sid] = 0; M.slab_cur[sid] = 0;
+    float4 pw = (ty == 0 ? world0 : world1)[(uint32_t)me];
+    M.slab_g[sid * 4 + 0] = d_cube_coord((double)pw.x, 0);
+    M.slab_g[sid * 4 + 1] = d_cube_coord((double)pw.y, 0);
+    M.slab_g[sid * 4 + 2] = d_cube_coord((double)pw.z, 0);
+  }
+  const int base = M.slab_n[sid];
+  if (base + len > M.cap) { atomicOr(&st->fault, LM_FAULT_CUBE_OVERFLOW); len = max(0, M.cap - base); }
+  slot_first[ty * LM_NSLOT + ps] = p;
+  slot_base[ty * LM_NSLOT + ps] = base;
+  slot_len[ty * LM_NSLOT + ps] = len;
+  M.slab_n[sid] = base + len;
+  M.slab_dirty[sid] = 1;
+}
+
+__global__ void __launch_bounds__(256) k_insert_write(LmMapType M0, LmMapType M1, const unsigned long long* __restrict__ sorted,
+                                                      const int32_t* __restrict__ n_ins, const float4* __restrict__ world0,
+                                                      const float4* __restrict__ world1, const int32_t* __restrict__ slot_first,
+                                                      const int32_t* __restrict__ slot_base, const int32_t* __restrict__ slot_len) {
+  const int n = *n_ins;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const unsigned long long me = sorted[p];
+  const uint32_t key = (uint32_t)(me >> 32);
+  const uint32_t ps = key & 8191u;
+  if (ps == 8191u) return;
+  const int ty = (int)(key >> 13);
+  const LmMapType& M = ty == 0 ? M0 : M1;
+  const int sid = M.slot_slab[ps];
+  if (sid < 0) return;
+  const int rel = p - slot_first[ty * LM_NSLOT + ps];
+  if (rel >= slot_len[ty * LM_NSLOT + ps]) return;
+  float4* dst = M.pts + ((size_t)sid * 2 + M.slab_cur[sid]) * M.cap;
+  dst[slot_base[ty * LM_NSLOT + ps] + rel] = (ty == 0 ? world0 : world1)[(uint32_t)me];
+}
+
+// ------------------------------------------------------------------ refilter (:788-801)
+// One CTA per window cube and map type.  slab = sorted voxel-unique prefix [0,ns) + tail
+// [ns,n) in arrival order.  VoxelGrid(prefix ++ tail) == merge(prefix, stable-sorted tail):
+// a voxel's members are the prefix point (if any) followed by the tail points in arrival
+// order, summed in fp32 in that order and divided by (float)count.
+__global__ void __launch_bounds__(1024, 1) k_refilter(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned long long* S = reinterpret_cast<unsigned long long*>(smem_raw);              // [LM_TAIL_TILE]
+  int* NV = reinterpret_cast<int*>(smem_raw + (size_t)LM_TAIL_TILE * 8);                // [LM_TAIL_TILE]
+  int* ws = reinterpret_cast<int*>(smem_raw + (size_t)LM_TAIL_TILE * 12);               // [64]
+  __shared__ int s_flag;
+  const int r = blockIdx.x;
+  if (r >= st->valid_num) return;
+  const LmMapType& M = blockIdx.y == 0 ? M0 : M1;
+  const int ps = st->valid_slot[r];
+  const int sid = M.slot_slab[ps];
+  if (sid < 0) return;
+  const int n = M.slab_n[sid];
+  const int ns = M.slab_nsorted[sid];
+  const int nt = n - ns;
+  if (nt == 0) return;                         // already filtered: VoxelGrid is the identity
+  if (nt > LM_TAIL_TILE) { if (threadIdx.x == 0) atomicOr(&st->fault, LM_FAULT_TAIL_OVERFLOW); return; }
+  const int cur = M.slab_cur[sid];
+  const float4* src = M.pts + ((size_t)sid * 2 + cur) * M.cap;
+  float4* dst = M.pts + ((size_t)sid * 2 + (cur ^ 1)) * M.cap;
+  uint32_t* pkey = M.pkey + (size_t)sid * M.cap;
+  const int g3[3] = { M.slab_g[sid * 4], M.slab_g[sid * 4 + 1], M.slab_g[sid * 4 + 2] };
+  const float il = M.inv_leaf;
+
+  for (int i = threadIdx.x; i < ns; i += blockDim.x) pkey[i] = d_cube_voxel_key(src[i], il, g3);
+  int np2 = 1; while (np2 < nt) np2 <<= 1;
+  for (int j = threadIdx.x; j < np2; j += blockDim.x)
+    S[j] = j < nt ? (((unsigned long long)d_cube_voxel_key(src[ns + j], il, g3) << 32) | (uint32_t)j) : ~0ULL;
+  __syncthreads();
+  d_bitonic_sort(S, np2);
+
+  // new-voxel flags and their exclusive prefix over the sorted tail
+  const int per = (nt + blockDim.x - 1) / blockDim.x;
+  const int b = min((int)threadIdx.x * per, nt), e = min(b + per, nt);
+  int local = 0;
+  for (int j = b; j < e; ++j) {
+    const uint32_t key = (uint32_t)(S[j] >> 32);
+    int nv = 0;
+    if (j == 0 || (uint32_t)(S[j - 1] >> 32) != key) {
+      int lb = d_lower_bound_u32(pkey, ns, key);
+      nv = !(lb < ns && pkey[lb] == key);
+    }
+    NV[j] = nv;
+    local += nv;
+  }
+  int total_new;
+  int run = d_block_exscan(local, ws, &total_new);
+  for (int j = b; j < e; ++j) { int nv = NV[j]; NV[j] = (run << 1) | nv; run += nv; }   // (exclusive count << 1) | flag
+  __syncthreads();
+  const int n_new = ns + total_new;
+  if (n_new > M.cap) { if (threadIdx.x == 0) atomicOr(&st->fault, LM_FAULT_CUBE_OVERFLOW); }
+
+  // prefix points: shifted by the number of new voxels sorting before them; merged if the tail hits their voxel
+  for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+    const uint32_t key = pkey[i];
+    const int lb = d_lower_bound_u64(S, nt, (unsigned long long)key << 32);
+    const int before = lb < nt ? (NV[lb] >> 1) : total_new;
+    float4 p = src[i];
+    if (lb < nt && (uint32_t)(S[lb] >> 32) == key) {
+      float sx = p.x, sy = p.y, sz = p.z, si = p.w;
+      int cnt = 1;
+      for (int m = lb; m < nt && (uint32_t)(S[m] >> 32) == key; ++m) {
+        float4 t = src[ns + (uint32_t)S[m]];
+        sx = __fadd_rn(sx, t.x); sy = __fadd_rn(sy, t.y); sz = __fadd_rn(sz, t.z); si = __fadd_rn(si, t.w);
+        ++cnt;
+      }
+      const float c = (float)cnt;
+      p = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), __fdiv_rn(si, c));
+    }
+    const int pos = i + before;
+    if (pos < M.cap) dst[pos] = p;
+  }
+  // new voxels
+  for (int j = threadIdx.x; j < nt; j += blockDim.x) {
+    const int v = NV[j];
+    if (!(v & 1)) continue;
+    const uint32_t key = (uint32_t)(S[j] >> 32);
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    int cnt = 0;
+    for (int m = j; m < nt && (uint32_t)(S[m] >> 32) == key; ++m) {
+      float4 t = src[ns + (uint32_t)S[m]];
+      sx = __fadd_rn(sx, t.x); sy = __fadd_rn(sy, t.y); sz = __fadd_rn(sz, t.z); si = __fadd_rn(si, t.w);
+      ++cnt;
+    }
+    const float c = (float)cnt;
+    const int pos = d_lower_bound_u32(pkey, ns, key) + (v >> 1);
+    if (pos < M.cap) dst[pos] = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), __fdiv_rn(si, c));
+  }
+  if (threadIdx.x == 0) s_flag = 0;
+  __syncthreads();
+  const int nn = min(n_new, M.cap);
+  // a centroid may round across a voxel border: verify the output is still strictly ascending,
+  // otherwise the whole slab is treated as unsorted tail next time (what PCL would do anyway).
+  for (int i = threadIdx.x + 1; i < nn; i += blockDim.x)
+    if (d_cube_voxel_key(dst[i], il, g3) <= d_cube_voxel_key(dst[i - 1], il, g3)) s_flag = 1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    M.slab_n[sid] = nn;
+    M.slab_nsorted[sid] = s_flag ? 0 : nn;
+    M.slab_cur[sid] = cur ^ 1;
+  }
+  __syncthreads();
+  // rebuild the search index of this cube from the new buffer (reuses the sort scratch)
+  d_build_cell_index(M, sid, dst, nn, reinterpret_cast<uint32_t*>(smem_raw), ws, st);
+  if (threadIdx.x == 0) M.slab_dirty[sid] = 0;
+}
+
+static const int kRefilterSmem = LM_TAIL_TILE * 12 + 64 * 4;
+
+int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf) {
+  const int n_max = n_max_corner + n_max_surf;
+  if (n_max > 0) {
+    int32_t* n_ins = ctx->d_tmp_i32;                 // [0]
+    int32_t* slot_len = ctx->d_tmp_i32 + 16;         // [2*LM_NSLOT]
+    const int blocks = lm_div_up(n_max, 256);
+    k_insert_prepare<<<blocks, 256, 0, ctx->stream>>>(ctx->d_state, ctx->d_stack[0], ctx->d_stack[1], ctx->d_world[0],
+                                                      ctx->d_world[1], ctx->d_sort_a, n_ins);
+    LM_LAUNCH_CHECK();
+    int rc = lm_sort_u64(ctx, ctx->d_sort_a, ctx->d_sort_b, ctx->d_sort_c, n_ins, n_max);
+    if (rc) return rc;
+    k_insert_heads<<<blocks, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_sort_c, n_ins,
+                                                    ctx->d_world[0], ctx->d_world[1], ctx->d_slot_first, ctx->d_slot_base, slot_len);
+    LM_LAUNCH_CHECK();
+    k_insert_write<<<blocks, 256, 0, ctx->stream>>>(ctx->map[0], ctx->map[1], ctx->d_sort_c, n_ins, ctx->d_world[0],
+                                                    ctx->d_world[1], ctx->d_slot_first, ctx->d_slot_base, slot_len);
+    LM_LAUNCH_CHECK();
+  }
+  k_refilter<<<dim3(75, 2), 1024, kRefilterSmem, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1]);
+  LM_LAUNCH_CHECK();
+  return LMONO_OK;
+}
+
+int lm_map_configure_kernels(lmono_ctx* ctx) {
+  LM_CUDA(cudaFuncSetAttribute(k_index_build, cudaFuncAttributeMaxDynamicSharedMemorySize, kIndexSmem));
+  LM_CUDA(cudaFuncSetAttribute(k_refilter, cudaFuncAttributeMaxDynamicSharedMemorySize, kRefilterSmem));
+  return LMONO_OK;
+}
+
+// ------------------------------------------------------------------ export
+// scope 0: window cubes in :512-537 order; scope 1: all cubes in logical linear order (:826-830)
+__global__ void __launch_bounds__(1024) k_export_offsets(const LmMapState* __restrict__ st, LmMapType M, int scope,
+                                                         int32_t* __restrict__ off /*[LM_NSLOT+1]*/, int32_t* __restrict__ order /*[LM_NSLOT]*/) {
+  __shared__ int ws[33];
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int count = scope == 0 ? st->valid_num : LM_NSLOT;
+  for (int base = 0; base < count; base += blockDim.x) {
+    const int e = base + threadIdx.x;
+    int n = 0, ps = -1;
+    if (e < count) {
+      if (scope == 0) ps = st->valid_slot[e];
+      else {
+        int i = e % LM_GW, j = (e / LM_GW) % LM_GH, k = e / (LM_GW * LM_GH);
+        ps = d_phys_slot(i - st->cen[0], j - st->cen[1], k - st->cen[2]);
+      }
+      int sid = M.slot_slab[ps];
+      n = sid >= 0 ? M.slab_n[sid] : 0;
+      order[e] = ps;
+    }
+    int total;
+    int ex = d_block_exscan(n, ws, &total);
+    if (e < count) off[e] = s_carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) off[count] = s_carry;
+}
+
+__global__ void __launch_bounds__(256) k_export_copy(LmMapType M, const int32_t* __restrict__ off, const int32_t* __restrict__ order,
+                                                     int count_slots, float4* __restrict__ out, int cap_out) {
+  const int e = blockIdx.x;
+  if (e >= count_slots) return;
+  const int ps = order[e];
+  const int sid = M.slot_slab[ps];
+  if (sid < 0) return;
+  const int n = M.slab_n[sid];
+  const float4* src = M.pts + ((size_t)sid * 2 + M.slab_cur[sid]) * M.cap;
+  const int o = off[e];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) if (o + i < cap_out) out[o + i] = src[i];
+}
+
+int lm_map_export_device(lmono_ctx* ctx, int which, int scope, int* n_total) {
+  LmMapType& M = ctx->map[which];
+  int32_t* order = ctx->d_export_off + LM_NSLOT + 8;
+  k_export_offsets<<<1, 1024, 0, ctx->stream>>>(ctx->d_state, M, scope, ctx->d_export_off, order);
+  LM_LAUNCH_CHECK();
+  int valid_num = LM_NSLOT;
+  if (scope == 0) {
+    LM_CUDA(cudaMemcpyAsync(&ctx->h_state->valid_num, &ctx->d_state->valid_num, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LM_CUDA(cudaStreamSynchronize(ctx->stream));
+    valid_num = ctx->h_state->valid_num;
+  }
+  int total = 0;
+  LM_CUDA(cudaMemcpyAsync(&total, ctx->d_export_off + valid_num, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  LM_CUDA(cudaStreamSynchronize(ctx->stream));
+  *n_total = total;
+  if (total == 0) return LMONO_OK;
+  if ((size_t)total > ctx->export_cap) {
+    cudaFree(ctx->d_export);
+    ctx->export_cap = (size_t)total + (total >> 2) + 1024;
+    LM_CUDA(cudaMalloc((void**)&ctx->d_export, ctx->export_cap * sizeof(float4)));
+  }
+  k_export_copy<<<valid_num, 256, 0, ctx->stream>>>(M, ctx->d_export_off, order, valid_num, ctx->d_export, total);
+  LM_LAUNCH_CHECK();
+  return LMONO_OK;
+}
+
+// ------------------------------------------------------------------ import into an empty map
+// composite = slot(13) | voxel key(30) | index(21)
+__global__ void __launch_bounds__(256) k_import_keys(LmMapState* __restrict__ st, LmMapType M, const float4* __restrict__ pts, int n,
+                                                     unsigned long long* __restrict__ comp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = pts[i];
+  int cI = d_cube_coord((double)p.x, st->cen[0]), cJ = d_cube_coord((double)p.y, st->cen[1]), cK = d_cube_coord((double)p.z, st->cen[2]);
+  unsigned long long ps = 8191ULL; uint32_t vkey = 0;
+  if (cI >= 0 && cI < LM_GW && cJ >= 0 && cJ < LM_GH && cK >= 0 && cK < LM_GD) {
+    int g3[3] = { cI - st->cen[0], cJ - st->cen[1], cK - st->cen[2] };
+    ps = (unsigned long long)d_phys_slot(g3[0], g3[1], g3[2]);
+    vkey = d_cube_voxel_key(p, M.inv_leaf, g3);
+  }
+  comp[i] = (ps << 51) | ((unsigned long long)vkey << 21) | (unsigned long long)i;
+}
+
+__global__ void __launch_bounds__(256) k_import_count(const unsigned long long* __restrict__ sorted, int n, int32_t* __restrict__ blockcnt) {
+  __shared__ int ws[33];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int head = 0;
+  if (i < n && (sorted[i] >> 51) != 8191ULL) head = (i == 0) || ((sorted[i] >> 21) != (sorted[i - 1] >> 21));
+  int total;
+  d_block_exscan(head, ws, &total);
+  if (threadIdx.x == 0) blockcnt[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_blocks(int32_t* __restrict__ blockcnt, int nblocks) {
+  __shared__ int ws[33];
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nblocks; base += blockDim.x) {
+    const int e = base + threadIdx.x;
+    int v = e < nblocks ? blockcnt[e] : 0;
+    int total;
+    int ex = d_block_exscan(v, ws, &total);
+    if (e < nblocks) blockcnt[e] = s_carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry += total;
+    __syncthreads();
+  }
+}
+
+// head ranks + first head rank of each slot
+__global__ void __launch_bounds__(256) k_import_ranks(const unsigned long long* __restrict__ sorted, int n, const int32_t* __restrict__ blockoff,
+                                                      int32_t* __restrict__ head_rank, int32_t* __restrict__ slot_first_rank) {
+  __shared__ int ws[33];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int head = 0; unsigned long long me = 0;
+  if (i < n) { me = sorted[i]; if ((me >> 51) != 8191ULL) head = (i == 0) || ((me >> 21) != (sorted[i - 1] >> 21)); }
+  int total;
+  int ex = d_block_exscan(head, ws, &total);
+  if (i < n) {
+    head_rank[i] = head ? blockoff[blockIdx.x] + ex : -1;
+    if (head && (i == 0 || (sorted[i - 1] >> 51) != (me >> 51))) slot_first_rank[(int)(me >> 51)] = blockoff[blockIdx.x] + ex;
+  }
+}
+
+// one thread per physical slot: allocate slabs in slot order (deterministic placement)
+__global__ void k_import_alloc(LmMapState* __restrict__ st, LmMapType M, const int32_t* __restrict__ slot_first_rank) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  for (int ps = 0; ps < LM_NSLOT; ++ps) {
+    if (slot_first_rank[ps] < 0) continue;
+    if (M.slot_slab[ps] >= 0) { st->fault |= LM_FAULT_IMPORT_NONEMPTY; continue; }
+    int top = *M.free_top - 1;
+    if (top < 0) { st->fault |= LM_FAULT_POOL_EXHAUSTED; continue; }
+    *M.free_top = top;
+    int sid = M.free_stack[top];
+    M.slot_slab[ps] = sid;
+    M.slab_n[sid] = 0; M.slab_nsorted[sid] = 0; M.slab_cur[sid] = 0; M.slab_dirty[sid] = 1;
+    // absolute cube coordinate from the physical slot and the window offsets
+    int pi = ps % LM_GW, pj = (ps / LM_GW) % LM_GH, pk = ps / (LM_GW * LM_GH);
+    // logical l in [0,dim) with (l - cen) mod dim == p  =>  l = (p + cen) mod dim
+    int li = d_pmod(pi + st->cen[0], LM_GW), lj = d_pmod(pj + st->cen[1], LM_GH), lk = d_pmod(pk + st->cen[2], LM_GD);
+    M.slab_g[sid * 4 + 0] = li - st->cen[0]; M.slab_g[sid * 4 + 1] = lj - st->cen[1]; M.slab_g[sid * 4 + 2] = lk - st->cen[2];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_import_write(LmMapState* __restrict__ st, LmMapType M, const float4* __restrict__ pts,
+                                                      const unsigned long long* __restrict__ sorted, int n,
+                                                      const int32_t* __restrict__ head_rank, const int32_t* __restrict__ slot_first_rank) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int hr = head_rank[i];
+  if (hr < 0) return;
+  const unsigned long long me = sorted[i];
+  const int ps = (int)(me >> 51);
+  const int sid = M.slot_slab[ps];
+  if (sid < 0) return;
+  const unsigned long long vk = me >> 21;
+  float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f; int cnt = 0;
+  int j = i;
+  for (; j < n && (sorted[j] >> 21) == vk; ++j) {
+    float4 t = pts[(uint32_t)(sorted[j] & 0x1FFFFFULL)];
+    sx = __fadd_rn(sx, t.x); sy = __fadd_rn(sy, t.y); sz = __fadd_rn(sz, t.z); si = __fadd_rn(si, t.w);
+    ++cnt;
+  }
+  const float c = (float)cnt;
+  const int pos = hr - slot_first_rank[ps];
+  if (pos >= M.cap) { atomicOr(&st->fault, LM_FAULT_CUBE_OVERFLOW); return; }
+  float4* dst = M.pts + ((size_t)sid * 2) * M.cap;
+  dst[pos] = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), __fdiv_rn(si, c));
+  // last voxel of this slot fixes the slab size
+  if (j >= n || (sorted[j] >> 51) != (me >> 51)) { M.slab_n[sid] = pos + 1; M.slab_nsorted[sid] = pos + 1; }
+}
+
+// after import a centroid may have crossed a voxel border: demote such slabs to "unsorted"
+__global__ void __launch_bounds__(256) k_import_verify(LmMapType M) {
+  __shared__ int s_flag;
+  const int sid = blockIdx.x;
+  if (sid >= M.n_slabs) return;
+  const int n = M.slab_n[sid];
+  if (n == 0 || M.slab_nsorted[sid] != n) return;
+  if (threadIdx.x == 0) s_flag = 0;
+  __syncthreads();
+  const float4* src = M.pts + ((size_t)sid * 2 + M.slab_cur[sid]) * M.cap;
+  const int g3[3] = { M.slab_g[sid * 4], M.slab_g[sid * 4 + 1], M.slab_g[sid * 4 + 2] };
+  for (int i = threadIdx.x + 1; i < n; i += blockDim.x)
+    if (d_cube_voxel_key(src[i], M.inv_leaf, g3) <= d_cube_voxel_key(src[i - 1], M.inv_leaf, g3)) s_flag = 1;
+  __syncthreads();
+  if (threadIdx.x == 0 && s_flag) M.slab_nsorted[sid] = 0;
+}
+
+int lm_map_import_device(lmono_ctx* ctx, int which, const float4* d_pts, int n,
+                         unsigned long long* d_a, unsigned long long* d_b, unsigned long long* d_c,
+                         int32_t* d_n, int32_t* d_blockcnt, int32_t* d_head_rank) {
+  LmMapType& M = ctx->map[which];
+  const int blocks = lm_div_up(n, 256);
+  LM_CUDA(cudaMemcpyAsync(d_n, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  k_import_keys<<<blocks, 256, 0, ctx->stream>>>(ctx->d_state, M, d_pts, n, d_a);
+  LM_LAUNCH_CHECK();
+  int rc = lm_sort_u64(ctx, d_a, d_b, d_c, d_n, n);
+  if (rc) return rc;
+  k_import_count<<<blocks, 256, 0, ctx->stream>>>(d_c, n, d_blockcnt);
+  LM_LAUNCH_CHECK();
+  k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(d_blockcnt, blocks);
+  LM_LAUNCH_CHECK();
+  LM_CUDA(cudaMemsetAsync(ctx->d_slot_first, 0xFF, sizeof(int32_t) * LM_NSLOT, ctx->stream));
+  k_import_ranks<<<blocks, 256, 0, ctx->stream>>>(d_c, n, d_blockcnt, d_head_rank, ctx->d_slot_first);
+  LM_LAUNCH_CHECK();
+  k_import_alloc<<<1, 32, 0, ctx->stream>>>(ctx->d_state, M, ctx->d_slot_first);
+  LM_LAUNCH_CHECK();
+  k_import_write<<<blocks, 256, 0, ctx->stream>>>(ctx->d_state, M, d_pts, d_c, n, d_head_rank, ctx->d_slot_first);
+  LM_LAUNCH_CHECK();
+  k_import_verify<<<M.n_slabs, 256, 0, ctx->stream>>>(M);
+  LM_LAUNCH_CHECK();
+  return LMONO_OK;
+}

@@ -1,0 +1,39 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    import oracle_lib
+    oracle_lib.lib()
+    return oracle_lib
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx_factory():
+    """Factory for lmono_b200 contexts; fails loudly (no CPU fallback) if CUDA is unusable."""
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    from lmono_b200 import api
+
+    made = []
+
+    def make(**params):
+        c = api.Context(device=0, **params)
+        made.append(c)
+        return c
+
+    yield make
+    for c in made:
+        c.close()
