@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- scan-to-map registrations/s on the C-3 workload of SURVEY.md section 8(d):
+an HDL-64-sized feature sweep (~4 k corner + ~12 k surf queries after the 0.4 / 0.8 m voxel
+filter) registered against a ~1 M-point local map in the reference's 21x21x11 cube structure,
+one full pass of laserMapping's process() per step (window upkeep, VoxelGrid of the features,
+2 x (5-NN association + line/plane fits + LM solve), map insertion and cube refilter).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Our arm: `value` = device-resident inputs, CUDA-event timed, L2 flushed between steps;
+`e2e` = the same registrations through the public host API (lmono_map_step) with pinned host
+buffers, H2D of the features and D2H of the pose inside the timed region.  The reference arm
+times the CPU oracle (a restatement of the reference's PCL/FLANN/Ceres path; the reference
+itself cannot be built here) on the host cores.  Multi-GPU: one independent sequence per rank
+(weak scaling, no data-path collective).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from lmono_b200 import synth  # noqa: E402
+
+METRIC = "scan-to-map registrations/s"
+UNIT = "registrations/s"
+WORKLOAD = "C-3 HDL-64 scan-to-map: ~4k corner + ~12k surf queries vs ~1M-pt 21x21x11 cube local map (0.4/0.8 m voxels), incl. map update"
+N_DISTINCT_SWEEPS = 24
+RAW_CORNER, RAW_SURF = 6800, 16000
+
+
+# ----------------------------------------------------------------------------- workload
+def voxel_dedupe(pts, leaf):
+    """keep the first sample of every global voxel (host-side thinning of the raw samples so
+    that a map import stays below 2^21 points; the import itself still runs the VoxelGrid)."""
+    inv = np.float32(1.0) / np.float32(leaf)
+    ijk = np.floor(pts[:, :3] * inv).astype(np.int64)
+    key = (ijk[:, 2] * 2_000_003 + ijk[:, 1]) * 2_000_003 + ijk[:, 0]
+    _, first = np.unique(key, return_index=True)
+    return pts[np.sort(first)]
+
+
+def make_workload(rank=0, n_sweeps=N_DISTINCT_SWEEPS):
+    city = synth.make_city(seed=7, pole_pitch=3.7, street_radius=18.0)   # sensor stays inside the centre cube
+    c = (0.0, 0.0, 0.0)
+    cm, sm = synth.sample_map(city, c, half_xy=125.0, n_surf=7_000_000, n_corner=2_500_000, seed=7)
+    rng = np.random.default_rng(70)
+    roofs = synth.to_xyzi(synth.sample_box_roofs(city, c, 180.0, 1_500_000, rng) + rng.normal(0, 0.01, (1_500_000, 3)))
+    roofs = roofs[(np.abs(roofs[:, 0]) < 125.0) & (np.abs(roofs[:, 1]) < 125.0)]
+    sm = np.concatenate([sm, roofs])
+    cm = voxel_dedupe(cm, 0.4)
+    sm = voxel_dedupe(sm, 0.8)
+    rng = np.random.default_rng(11 + 1000 * rank)
+    sweeps = []
+    for k in range(n_sweeps):
+        q, t = synth.city_pose(city, 1.0 * k + 7.0 * rank)
+        co, su = synth.sample_sweep_features(city, q, t, rng, RAW_CORNER, RAW_SURF, max_range=60.0)
+        qp, tp = synth.perturb_pose(q, t, rng, 0.2, 1.0)        # U(+-0.2 m, +-1 deg), SURVEY 8d C-3
+        sweeps.append((co, su, q, t, qp, tp))
+    return city, cm, sm, sweeps
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def _oracle_worker(args):
+    rank, steps, warmup = args
+    import oracle_lib as O
+    _, cm, sm, sweeps = make_workload(rank)
+    m = O.Mapper(0.4, 0.8, 0, 1)
+    m.import_points(0, cm)
+    m.import_points(1, sm)
+    phases = {"ms_tree": 0.0, "ms_assoc": 0.0, "ms_solver": 0.0, "ms_filter": 0.0, "ms_add": 0.0, "ms_shift": 0.0}
+    for i in range(warmup):
+        c, s, q, t, qp, tp = sweeps[i % len(sweeps)]
+        m.set_state([0, 0, 0, 1], [0, 0, 0])
+        m.step(c, s, qp, tp)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        c, s, q, t, qp, tp = sweeps[(warmup + i) % len(sweeps)]
+        m.set_state([0, 0, 0, 1], [0, 0, 0])
+        _, _, rep, _ = m.step(c, s, qp, tp)
+        for k in phases:
+            phases[k] += getattr(rep, k)
+    dt = time.perf_counter() - t0
+    nmap = len(m.export(0)) + len(m.export(1))
+    return dt, phases, nmap
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 16))
+    with mp.get_context("spawn").Pool(procs) as pool:
+        res = pool.map(_oracle_worker, [(r, args.steps, args.warmup) for r in range(procs)])
+    wall = max(r[0] for r in res)
+    value = procs * args.steps / wall
+    ph = {k: sum(r[1][k] for r in res) / (procs * args.steps) for k in res[0][1]}
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps / procs * procs, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "map_points": res[0][2], "parallelism": f"{procs} independent sequences on {procs} host processes"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
+                         "sample": f"{args.steps} registrations per process x {procs} processes (oracle restatement of the PCL/FLANN/Ceres path: "
+                                   "per-sweep KD-tree rebuild, 5-NN, fits, Ceres-style LM, per-cube VoxelGrid refilter)",
+                         "ms_per_registration_phases": {k: round(v, 3) for k, v in ph.items()}},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from lmono_b200 import api
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+
+    _, cm, sm, sweeps = make_workload(rank)
+    stream = torch.cuda.current_stream()
+    ctx = api.Context(device=local, stream=stream.cuda_stream)
+    ctx.map_import(0, cm)
+    ctx.map_import(1, sm)
+    ctx.sync()
+
+    # device-resident copies of the sweeps (value leg) and pinned host copies (e2e leg)
+    d_sweeps = [(torch.from_numpy(c).to(dev), torch.from_numpy(s).to(dev)) for (c, s, *_rest) in sweeps]
+    h_sweeps = [(torch.from_numpy(c).pin_memory(), torch.from_numpy(s).pin_memory()) for (c, s, *_rest) in sweeps]
+    h_np = [(a.numpy(), b.numpy()) for a, b in h_sweeps]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    ident = ([0, 0, 0, 1], [0, 0, 0])
+
+    def step_device(i):
+        c, s = d_sweeps[i % len(sweeps)]
+        _, _, _, _, qp, tp = sweeps[i % len(sweeps)]
+        ctx.map_set_state(*ident)       # every registration starts from its own U(+-0.2 m, +-1 deg) perturbation
+        ctx.map_step_device(c.data_ptr(), c.shape[0], s.data_ptr(), s.shape[0], qp, tp)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up
+    for i in range(max(args.warmup, 3)):
+        step_device(i)
+    ctx.map_collect()
+
+    # ---- value leg: device-resident inputs, CUDA events per step, L2 flushed between steps
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    n_launch0 = ctx.launch_count()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        ev0[i].record(stream)
+        step_device(args.warmup + i)
+        ev1[i].record(stream)
+    barrier()
+    n_launch = ctx.launch_count() - n_launch0
+    clocks = sampler.stop()
+    q_last, t_last, rep = ctx.map_collect()
+    step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
+    total_ms = float(sum(step_ms))
+    tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tt.item())
+    value = world * args.steps / (total_ms_max * 1e-3)
+
+    # sanity of the work done inside the timed region: the last registration converged
+    c, s, qg, tg, qp, tp = sweeps[(args.warmup + args.steps - 1) % len(sweeps)]
+    reg_err = float(np.linalg.norm(t_last - tg))
+    assert rep.optimized == 1 and reg_err < 0.1, (rep.optimized, reg_err)
+
+    # ---- e2e leg: public host API, pinned host inputs, H2D + D2H inside the timed region
+    for i in range(3):
+        c, s = h_np[i % len(sweeps)]
+        ctx.map_set_state(*ident)
+        ctx.map_step(c, s, sweeps[i % len(sweeps)][4], sweeps[i % len(sweeps)][5])
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    h2d = d2h = 0
+    e0.record(stream)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        k = (args.warmup + i) % len(sweeps)
+        c, s = h_np[k]
+        ctx.map_set_state(*ident)
+        ctx.map_step(c, s, sweeps[k][4], sweeps[k][5])
+        h2d += c.nbytes + s.nbytes
+    e1.record(stream)
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    e2e_ms = max(e0.elapsed_time(e1), e2e_wall * 1e3)
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps / (float(te.item()) * 1e-3)
+    d2h = int(ctx.L.lmono_map_result_bytes()) * args.steps      # pose + report read back per step
+
+    # ---- per-phase device times (CUDA events around each phase, same workload, L2 flushed)
+    ctx.profile_enable(True)
+    nprof = min(args.steps, 16)
+    for i in range(nprof):
+        flush.fill_(1)
+        step_device(args.warmup + i)
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    q_last, t_last, rep = ctx.map_collect()
+    phase_ms = {k: v[0] / max(nprof, 1) for k, v in prof.items()}
+    nq = rep.corner_stack + rep.surf_stack
+    nmap = rep.corner_from_map + rep.surf_from_map
+    # dominant kernel family by device time
+    assoc_launch_ms = prof["assoc"][0] / max(prof["assoc"][1], 1)
+    refilter_launch_ms = prof["refilter"][0] / max(prof["refilter"][1], 1)
+    # algorithmic bytes per launch: kNN query = 16 B query + 5 x 16 B neighbours + 5 x 4 B indices
+    assoc_bytes = 116.0 * nq
+    roofline = {
+        "bound": "hbm", "kernel": "k_associate (exact 5-NN + line/plane fit, one launch per outer iteration)",
+        "achieved": assoc_bytes / (assoc_launch_ms * 1e-3) / 1e9 if assoc_launch_ms > 0 else None,
+        "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
+        "frac": (assoc_bytes / (assoc_launch_ms * 1e-3) / 1e9 / hbm_peak) if assoc_launch_ms > 0 else None,
+        "traffic": None,
+        "algorithmic_bytes_per_launch": assoc_bytes, "avg_launch_ms": assoc_launch_ms,
+        "queries_per_launch": nq, "knn_queries_per_s": nq / (assoc_launch_ms * 1e-3) if assoc_launch_ms > 0 else None,
+        "phase_ms_per_step": {k: round(v, 4) for k, v in phase_ms.items()},
+        "note": "map (~16 MB) is L2-resident between launches of one step; see DESIGN.md for why HBM% is low on this path",
+    }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32+f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "map_points": int(nmap), "queries_per_sweep": int(nq),
+                   "raw_features_per_sweep": [RAW_CORNER, RAW_SURF], "l2": "flushed between steps (256 MiB write)",
+                   "parallelism": "one independent sequence per GPU, no collective"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps},
+        "gpu_launches": int(n_launch),
+        "clocks": clocks,
+        "roofline": roofline,
+        "registration_error_m": reg_err,
+    }
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import oracle_lib as O
+        m = O.Mapper(0.4, 0.8, 0, 1)
+        m.import_points(0, cm)
+        m.import_points(1, sm)
+        ncpu = args.cpu_steps
+        t0 = time.perf_counter()
+        for i in range(ncpu):
+            c, s, q, t, qp, tp = sweeps[i % len(sweeps)]
+            m.set_state([0, 0, 0, 1], [0, 0, 0])
+            m.step(c, s, qp, tp)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": ncpu / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"{ncpu} registrations of the same workload on 1 host thread (the reference nodes are single-threaded)"}
+    if rank == 0:
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-steps", type=int, default=12)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 40:
+            args.steps = 40          # bounded sample: ~1 s of CPU per registration
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

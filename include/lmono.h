@@ -154,7 +154,9 @@ int lmono_map_collect(lmono_ctx* ctx, lmono_pose* w_curr, lmono_pose* wmap_wodom
 
 /* q_wmap_wodom / t_wmap_wodom (laserMapping.cpp:116-117) */
 int lmono_map_get_state(lmono_ctx* ctx, lmono_pose* wmap_wodom, int32_t cen[3]);
-int lmono_map_set_state(lmono_ctx* ctx, const lmono_pose* wmap_wodom);
+int lmono_map_set_state(lmono_ctx* ctx, const lmono_pose* wmap_wodom);   /* enqueue-only */
+/* bytes lmono_map_collect / lmono_map_step read back from the device per step (pose + report) */
+int32_t lmono_map_result_bytes(void);
 
 /* Map exchange (the publishers at laserMapping.cpp:806-836 and checkpoint/restore).
  * which: 0 corner, 1 surf.  scope: 0 = the <=75 cubes of the current window in the order of
@@ -182,6 +184,13 @@ int lmono_map_normal_eq(lmono_ctx* ctx, lmono_cloud_view corner_stack, lmono_clo
                         int32_t* n_corner, int32_t* n_surf);
 /* pcl::VoxelGrid<PointXYZI> as configured by the reference (canonical index-order sums). */
 int lmono_voxel_grid(lmono_ctx* ctx, lmono_cloud_view in, float leaf, lmono_cloud_out* out);
+
+/* Per-phase device timing (CUDA events on the ctx stream) of lmono_map_step, used by bench.py
+ * for the roofline numbers.  Phases: 0 window shift, 1 cell-index build, 2 VoxelGrid of the
+ * features, 3 association (5-NN + fits), 4 LM solve, 5 insertion, 6 cube refilter, 7 misc. */
+#define LMONO_PROFILE_PHASES 8
+int lmono_profile_enable(lmono_ctx* ctx, int on);
+int lmono_profile_read(lmono_ctx* ctx, float* ms /*[8]*/, int32_t* counts /*[8]*/);
 
 /* ------------------------------------------------------------------ L1: scanRegistration */
 /* Replaces Aloam/src/scanRegistration.cpp:132-408. */

@@ -204,6 +204,17 @@ class Context:
         self._chk(self.L.lmono_last_fault(self._h, C.byref(bits)), "last_fault")
         return bits.value
 
+    PROFILE_PHASES = ("window", "index", "voxel", "assoc", "solve", "insert", "refilter", "misc")
+
+    def profile_enable(self, on=True):
+        self._chk(self.L.lmono_profile_enable(self._h, 1 if on else 0), "profile_enable")
+
+    def profile_read(self):
+        ms = (C.c_float * 8)()
+        cnt = (C.c_int32 * 8)()
+        self._chk(self.L.lmono_profile_read(self._h, ms, cnt), "profile_read")
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROFILE_PHASES)}
+
     # -- laserMapping
     def map_step(self, corner_last, surf_last, q_odom, t_odom, full_res=None):
         cl = corner_last if corner_last.dtype == np.float32 and corner_last.flags["C_CONTIGUOUS"] else _xyzi(corner_last)

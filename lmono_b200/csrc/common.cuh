@@ -101,6 +101,11 @@ struct VgParams {            // scan-level VoxelGrid parameters computed on devi
   int32_t n;
 };
 
+// profiler phases (lmono_profile_read order)
+enum { LM_PROF_WINDOW = 0, LM_PROF_INDEX, LM_PROF_VOXEL, LM_PROF_ASSOC, LM_PROF_SOLVE, LM_PROF_INSERT, LM_PROF_REFILTER,
+       LM_PROF_MISC, LM_PROF_NTAGS };
+constexpr int LM_PROF_MAX_EVENTS = 2048;
+
 // ---------------------------------------------------------------- host ctx
 struct lmono_ctx {
   int device;
@@ -137,7 +142,20 @@ struct lmono_ctx {
   bool step_pending;
   // later stages (scan registration / odometry / colour) attach their own state
   void* scan_state; void* odom_state; void* color_state;
+  // optional per-phase CUDA-event profiler (bench.py roofline numbers)
+  bool prof_on; int prof_n; int prof_tag[LM_PROF_MAX_EVENTS]; cudaEvent_t prof_ev[LM_PROF_MAX_EVENTS][2];
 };
+
+static inline void lm_prof_begin(lmono_ctx* ctx, int tag) {
+  if (!ctx->prof_on || ctx->prof_n >= LM_PROF_MAX_EVENTS) return;
+  ctx->prof_tag[ctx->prof_n] = tag;
+  cudaEventRecord(ctx->prof_ev[ctx->prof_n][0], ctx->stream);
+}
+static inline void lm_prof_end(lmono_ctx* ctx) {
+  if (!ctx->prof_on || ctx->prof_n >= LM_PROF_MAX_EVENTS) return;
+  cudaEventRecord(ctx->prof_ev[ctx->prof_n][1], ctx->stream);
+  ctx->prof_n++;
+}
 
 #define LM_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { ctx->last_cuda_error = (int)_e; \
   fprintf(stderr, "[lmono_b200] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); \

@@ -40,14 +40,24 @@ static int enqueue_step(lmono_ctx* ctx, const float4* d_corner, int nc, const fl
   LM_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
   k_set_counts<<<1, 32, 0, ctx->stream>>>(ctx->d_state, nc, ns);
   LM_LAUNCH_CHECK();
+  lm_prof_begin(ctx, LM_PROF_WINDOW);
   if ((rc = lm_map_begin_step(ctx, wodom_curr, nullptr))) return rc;        // :309-539
+  lm_prof_end(ctx);
+  lm_prof_begin(ctx, LM_PROF_INDEX);
   if ((rc = lm_map_index_build(ctx))) return rc;                            // replaces kdtree setInputCloud :558-559
+  lm_prof_end(ctx);
   // :542-550 VoxelGrid of the incoming features
+  lm_prof_begin(ctx, LM_PROF_VOXEL);
   if ((rc = lm_voxel_grid_device(ctx, d_corner, &ctx->d_state->raw_n[0], nc, ctx->map[0].leaf, ctx->d_stack[0], &ctx->d_state->stack_n[0]))) return rc;
   if ((rc = lm_voxel_grid_device(ctx, d_surf, &ctx->d_state->raw_n[1], ns, ctx->map[1].leaf, ctx->d_stack[1], &ctx->d_state->stack_n[1]))) return rc;
+  lm_prof_end(ctx);
   for (int iter = 0; iter < 2; ++iter) {                                    // :562
+    lm_prof_begin(ctx, LM_PROF_ASSOC);
     if ((rc = lm_map_associate(ctx, nc, ns))) return rc;                    // :577-687
+    lm_prof_end(ctx);
+    lm_prof_begin(ctx, LM_PROF_SOLVE);
     if ((rc = lm_solve_enqueue(ctx, iter, nc, ns, 4))) return rc;           // :713-720
+    lm_prof_end(ctx);
   }
   k_transform_update<<<1, 32, 0, ctx->stream>>>(ctx->d_state);              // :734
   LM_LAUNCH_CHECK();
@@ -131,13 +141,21 @@ extern "C" int lmono_map_get_state(lmono_ctx* ctx, lmono_pose* wmap_wodom, int32
   return LMONO_OK;
 }
 
+__global__ void k_set_wmap(LmMapState* st, double qx, double qy, double qz, double qw, double tx, double ty, double tz) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  st->q_wmap_wodom[0] = qx; st->q_wmap_wodom[1] = qy; st->q_wmap_wodom[2] = qz; st->q_wmap_wodom[3] = qw;
+  st->t_wmap_wodom[0] = tx; st->t_wmap_wodom[1] = ty; st->t_wmap_wodom[2] = tz;
+}
+
+// enqueue-only (ordered on the ctx stream, no host synchronisation)
 extern "C" int lmono_map_set_state(lmono_ctx* ctx, const lmono_pose* p) {
   if (!ctx || !p) return LMONO_E_ARG;
-  LM_CUDA(cudaMemcpyAsync(ctx->d_state->q_wmap_wodom, p->q, 32, cudaMemcpyHostToDevice, ctx->stream));
-  LM_CUDA(cudaMemcpyAsync(ctx->d_state->t_wmap_wodom, p->t, 24, cudaMemcpyHostToDevice, ctx->stream));
-  LM_CUDA(cudaStreamSynchronize(ctx->stream));
+  k_set_wmap<<<1, 32, 0, ctx->stream>>>(ctx->d_state, p->q[0], p->q[1], p->q[2], p->q[3], p->t[0], p->t[1], p->t[2]);
+  LM_LAUNCH_CHECK();
   return LMONO_OK;
 }
+
+extern "C" int32_t lmono_map_result_bytes(void) { return (int32_t)sizeof(LmMapState); }
 
 extern "C" int lmono_map_clear(lmono_ctx* ctx) {
   if (!ctx) return LMONO_E_ARG;
@@ -247,4 +265,26 @@ extern "C" int lmono_voxel_grid(lmono_ctx* ctx, lmono_cloud_view in, float leaf,
   LM_CUDA(cudaMemcpyAsync(&n_out, &ctx->d_state->stack_n[0], sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   LM_CUDA(cudaStreamSynchronize(ctx->stream));
   return lm_download_cloud(ctx, ctx->d_stack[0], n_out, out);
+}
+
+// ---- per-phase CUDA-event profiler (bench.py) --------------------------------------------
+extern "C" int lmono_profile_enable(lmono_ctx* ctx, int on) {
+  if (!ctx) return LMONO_E_ARG;
+  if (on && !ctx->prof_ev[0][0]) {
+    for (int i = 0; i < LM_PROF_MAX_EVENTS; ++i) { LM_CUDA(cudaEventCreate(&ctx->prof_ev[i][0])); LM_CUDA(cudaEventCreate(&ctx->prof_ev[i][1])); }
+  }
+  ctx->prof_on = on != 0; ctx->prof_n = 0;
+  return LMONO_OK;
+}
+
+extern "C" int lmono_profile_read(lmono_ctx* ctx, float* ms /*[LM_PROF_NTAGS]*/, int32_t* counts /*[LM_PROF_NTAGS]*/) {
+  if (!ctx || !ms || !counts) return LMONO_E_ARG;
+  LM_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int t = 0; t < LM_PROF_NTAGS; ++t) { ms[t] = 0.f; counts[t] = 0; }
+  for (int i = 0; i < ctx->prof_n; ++i) {
+    float e = 0.f;
+    if (cudaEventElapsedTime(&e, ctx->prof_ev[i][0], ctx->prof_ev[i][1]) == cudaSuccess) { ms[ctx->prof_tag[i]] += e; counts[ctx->prof_tag[i]]++; }
+  }
+  ctx->prof_n = 0;
+  return LMONO_OK;
 }

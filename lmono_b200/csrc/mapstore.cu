@@ -442,6 +442,7 @@ static const int kRefilterSmem = LM_TAIL_TILE * 12 + 64 * 4;
 
 int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf) {
   const int n_max = n_max_corner + n_max_surf;
+  lm_prof_begin(ctx, LM_PROF_INSERT);
   if (n_max > 0) {
     int32_t* n_ins = ctx->d_tmp_i32;                 // [0]
     int32_t* slot_len = ctx->d_tmp_i32 + 16;         // [2*LM_NSLOT]
@@ -458,8 +459,11 @@ int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf)
                                                     ctx->d_world[1], ctx->d_slot_first, ctx->d_slot_base, slot_len);
     LM_LAUNCH_CHECK();
   }
+  lm_prof_end(ctx);
+  lm_prof_begin(ctx, LM_PROF_REFILTER);
   k_refilter<<<dim3(75, 2), 1024, kRefilterSmem, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1]);
   LM_LAUNCH_CHECK();
+  lm_prof_end(ctx);
   return LMONO_OK;
 }
 

@@ -301,3 +301,57 @@ def raycast_sweep(world: World, q, t, n_scans=64, n_az=1875, rng=None, noise=0.0
     out[:, :3] = pts[ok]
     out[:, 3] = 0.5
     return out
+
+
+# --------------------------------------------------------------------------- bench city (C-3)
+def make_city(center=(0.0, 0.0), half=125.0, seed=7, pitch=15.0, footprint=(9.0, 12.0),
+              height=(12.0, 40.0), pole_pitch=4.2, street_radius=30.0) -> World:
+    """Dense block city filling the 250 x 250 m mapping window of SURVEY 8d C-3: a lattice of
+    buildings (planes -> ~750 k surf voxels at 0.8 m) and a lattice of poles plus the building
+    edges (lines -> ~250 k corner voxels at 0.4 m).  A ring road of radius `street_radius`
+    around the centre is kept free of buildings for the sensor to drive on."""
+    rng = np.random.default_rng(seed)
+    cx, cy = center
+    boxes, poles = [], []
+    g = np.arange(-half + pitch / 2, half, pitch)
+    for x in g:
+        for y in g:
+            r = math.hypot(x, y)
+            if abs(r - street_radius) < 9.0:
+                continue
+            sx, sy = rng.uniform(*footprint, size=2)
+            h = rng.uniform(*height)
+            boxes.append([cx + x - sx / 2, cy + y - sy / 2, 0.0, cx + x + sx / 2, cy + y + sy / 2, h])
+    gp = np.arange(-half + 1.0, half, pole_pitch)
+    for x in gp:
+        for y in gp:
+            px, py = x + rng.uniform(-0.8, 0.8), y + rng.uniform(-0.8, 0.8)
+            inside = False
+            for b in boxes:
+                if b[0] - 0.3 < cx + px < b[3] + 0.3 and b[1] - 0.3 < cy + py < b[4] + 0.3:
+                    inside = True
+                    break
+            if not inside:
+                poles.append([cx + px, cy + py, 0.1, rng.uniform(8.0, 36.0)])
+    w = World(np.asarray(boxes, np.float64), np.asarray(poles, np.float64), street_radius, seed)
+    w.extra["center"] = (cx, cy)
+    return w
+
+
+def city_pose(world: World, s: float):
+    """Pose on the ring road of a make_city() world after arc length s."""
+    cx, cy = world.extra.get("center", (0.0, 0.0))
+    R = world.loop_radius
+    ang = s / R
+    t = np.array([cx + R * math.cos(ang), cy + R * math.sin(ang), SENSOR_HEIGHT])
+    yaw = ang + math.pi / 2.0
+    return np.array([0.0, 0.0, math.sin(yaw / 2), math.cos(yaw / 2)]), t
+
+
+def sample_box_roofs(world: World, center, radius, n, rng):
+    boxes, _ = _nearby(world, center, radius)
+    if not len(boxes) or n <= 0:
+        return np.zeros((0, 3))
+    b = boxes[rng.integers(0, len(boxes), n)]
+    return np.stack([b[:, 0] + rng.uniform(0, 1, n) * (b[:, 3] - b[:, 0]),
+                     b[:, 1] + rng.uniform(0, 1, n) * (b[:, 4] - b[:, 1]), b[:, 5]], 1)
