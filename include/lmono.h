@@ -200,12 +200,19 @@ int lmono_scan_register(lmono_ctx* ctx, lmono_cloud_view raw, lmono_cloud_out* f
                         int32_t* labels /*may be NULL; one per point of `full`*/,
                         lmono_scan_report* report);
 
+/* test hook: curvature (scanRegistration.cpp:262) and index into the raw input of the first n
+ * points of the last sweep's ring-sorted cloud */
+int lmono_scan_debug(lmono_ctx* ctx, float* curvature, int32_t* src_index, int32_t n);
+
 /* ------------------------------------------------------------------ L2: laserOdometry */
 /* Replaces Aloam/src/laserOdometry.cpp:265-568. */
 int lmono_odom_step(lmono_ctx* ctx, lmono_cloud_view sharp, lmono_cloud_view less_sharp,
                     lmono_cloud_view flat, lmono_cloud_view less_flat,
                     lmono_pose* last_curr /*out*/, lmono_pose* w_curr /*out*/, lmono_odom_report* report);
 int lmono_odom_reset(lmono_ctx* ctx);
+/* test hook: correspondences of association pass 0 / 1 of the last step; corner_idx is
+ * [n_sharp x 2] (closestPointInd, minPointInd2), plane_idx [n_flat x 3] (+ minPointInd3); -1 = none */
+int lmono_odom_debug(lmono_ctx* ctx, int32_t pass, int32_t* corner_idx, int32_t n_sharp, int32_t* plane_idx, int32_t n_flat);
 
 /* ------------------------------------------------------------------ L6: colour projection */
 /* Replaces mono_lidar_mapping/src/map_builder/Map_Builder.cc:224-245 (raster), :336-403

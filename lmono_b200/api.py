@@ -308,6 +308,50 @@ class Context:
                                              g.ctypes.data_as(C.c_void_p), C.byref(cost), C.byref(nc), C.byref(ns)), "map_normal_eq")
         return H.reshape(6, 6), g, cost.value, nc.value, ns.value
 
+    # -- scanRegistration
+    def scan_register(self, raw, want_debug=False):
+        """raw: float32 [n,4] (KITTI .bin layout) or [n,3].  Returns dict of clouds, labels, report."""
+        raw = np.ascontiguousarray(raw, np.float32)
+        n = len(raw)
+        cap = max(n, 1)
+        bufs, outs = {}, {}
+        for k, c in (("full", cap), ("sharp", 64 * 12), ("less_sharp", 64 * 120), ("flat", 64 * 24), ("less_flat", cap)):
+            bufs[k], outs[k] = _out(c)
+        labels = np.zeros(cap, np.int32)
+        rep = ScanReport()
+        rc = self.L.lmono_scan_register(self._h, view_of(raw), C.byref(outs["full"]), C.byref(outs["sharp"]),
+                                        C.byref(outs["less_sharp"]), C.byref(outs["flat"]), C.byref(outs["less_flat"]),
+                                        labels.ctypes.data_as(C.c_void_p), C.byref(rep))
+        self._chk(rc, "scan_register")
+        res = {k: bufs[k][: outs[k].n_out] for k in bufs}
+        res["labels"] = labels[: rep.n_kept]
+        res["report"] = rep
+        if want_debug:
+            curv = np.zeros(max(rep.n_kept, 1), np.float32)
+            src = np.zeros(max(rep.n_kept, 1), np.int32)
+            self._chk(self.L.lmono_scan_debug(self._h, curv.ctypes.data_as(C.c_void_p), src.ctypes.data_as(C.c_void_p), rep.n_kept), "scan_debug")
+            res["curvature"] = curv[: rep.n_kept]
+            res["src_index"] = src[: rep.n_kept]
+        return res
+
+    # -- laserOdometry
+    def odom_step(self, sharp, less_sharp, flat, less_flat):
+        a, b, c, d = (_xyzi(x) for x in (sharp, less_sharp, flat, less_flat))
+        lc, wc, rep = Pose(), Pose(), OdomReport()
+        self._chk(self.L.lmono_odom_step(self._h, view_of(a), view_of(b), view_of(c), view_of(d),
+                                         C.byref(lc), C.byref(wc), C.byref(rep)), "odom_step")
+        return lc.as_np(), wc.as_np(), rep
+
+    def odom_reset(self):
+        self._chk(self.L.lmono_odom_reset(self._h), "odom_reset")
+
+    def odom_debug(self, which_pass, n_sharp, n_flat):
+        ci = np.full((max(n_sharp, 1), 2), -9, np.int32)
+        pi = np.full((max(n_flat, 1), 3), -9, np.int32)
+        self._chk(self.L.lmono_odom_debug(self._h, which_pass, ci.ctypes.data_as(C.c_void_p), n_sharp,
+                                          pi.ctypes.data_as(C.c_void_p), n_flat), "odom_debug")
+        return ci[:n_sharp], pi[:n_flat]
+
     def voxel_grid(self, pts, leaf):
         p = _xyzi(pts)
         buf, out = _out(len(p))

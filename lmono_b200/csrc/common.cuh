@@ -58,6 +58,15 @@ struct LmLmState {          // Levenberg-Marquardt controller state (one solve a
   unsigned int pad2;
 };
 
+struct LmProblem {          // one LM solve: factor arrays, pose in/out, report slots (device pointers)
+  const LmFactor* fac0; const LmFactor* fac1;
+  const int32_t* n0; const int32_t* n1;   // factor-slot counts (invalid slots have kind < 0)
+  const int32_t* gate;                    // solve only if *gate != 0 (NULL = always)
+  double* pose_q; double* pose_t;         // q (x,y,z,w), t: initial value in, result out
+  LmSolveSummary* summary;
+  int32_t* count0; int32_t* count1;       // valid factors per array
+};
+
 struct LmMapState {
   int32_t cen[3];                        // laserCloudCenWidth/Height/Depth
   int32_t center[3];                     // centerCubeI/J/K after the shift
@@ -273,6 +282,62 @@ __device__ __forceinline__ void d_bitonic_sort(unsigned long long* s, int n_pow2
   }
 }
 
+// ---- register-resident bitonic sort ---------------------------------------------------
+// Sorts N = ITEMS * nthreads 64-bit keys ascending; thread t of the group holds elements
+// [t*ITEMS, (t+1)*ITEMS).  Stages whose partner distance j is < ITEMS run in registers,
+// ITEMS <= j < 32*ITEMS through warp shuffles, larger j through shared memory (2 barriers
+// per stage, only log2(N/(32*ITEMS)) * (..+1)/2 of them).  `nthreads` threads with contiguous
+// ids starting at `tid0 = 0` must call it together; if nthreads > 32, `xch` must hold N keys
+// and the whole block must participate (uses __syncthreads).
+__device__ __forceinline__ void d_cmpx(unsigned long long& a, unsigned long long& b, bool up) {
+  // a at the lower index, b at the higher
+  if ((a > b) == up) { unsigned long long t = a; a = b; b = t; }
+}
+
+template <int ITEMS>
+__device__ __forceinline__ void d_bitonic_regs(unsigned long long (&v)[ITEMS], int t, int nthreads, unsigned long long* xch) {
+  const int N = ITEMS * nthreads;
+  for (int k = 2; k <= N; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32 * ITEMS) {
+        // cross-warp: exchange through shared memory
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) xch[t * ITEMS + r] = v[r];
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) {
+          const int i = t * ITEMS + r;
+          const unsigned long long o = xch[i ^ j];
+          const bool up = (i & k) == 0;
+          const bool lower = (i & j) == 0;
+          const unsigned long long mn = v[r] < o ? v[r] : o, mx = v[r] < o ? o : v[r];
+          v[r] = (lower == up) ? mn : mx;
+        }
+        __syncthreads();
+      } else if (j >= ITEMS) {
+        const int lane_x = j / ITEMS;
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) {
+          const int i = t * ITEMS + r;
+          const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[r], lane_x);
+          const bool up = (i & k) == 0;
+          const bool lower = (i & j) == 0;
+          const unsigned long long mn = v[r] < o ? v[r] : o, mx = v[r] < o ? o : v[r];
+          v[r] = (lower == up) ? mn : mx;
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) {
+          if ((r & j) == 0 && (r | j) < ITEMS) {
+            const int i = t * ITEMS + r;
+            d_cmpx(v[r], v[r | j], (i & k) == 0);
+          }
+        }
+      }
+    }
+  }
+}
+
 // first index in sorted[0..n) with sorted[i] >= key
 __device__ __forceinline__ int d_lower_bound_u64(const unsigned long long* sorted, int n, unsigned long long key) {
   int lo = 0, hi = n;
@@ -305,6 +370,7 @@ int lm_knn5_device(lmono_ctx* ctx, int which, const float4* d_q, int n, int32_t*
 // lm.cu
 int lm_solve_enqueue(lmono_ctx* ctx, int solve_index, int n_max_corner, int n_max_surf, int max_iter);
 int lm_normal_eq_enqueue(lmono_ctx* ctx, int n_max_corner, int n_max_surf);
+int lm_solve_problem(lmono_ctx* ctx, const LmProblem& P, int n_max, int max_iter, int write_back);
 // ctx.cu helpers
 int lm_upload_cloud(lmono_ctx* ctx, lmono_cloud_view v, uint8_t* d_raw, float4* d_out, int32_t* d_n /*may be null*/);
 int lm_download_cloud(lmono_ctx* ctx, const float4* d_src, int n, lmono_cloud_out* out);

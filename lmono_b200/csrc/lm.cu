@@ -158,7 +158,7 @@ __device__ int d_compute_step(LmLmState* lm) {
   }
 }
 
-__device__ void d_lm_control(LmLmState* lm, const double* red /*28*/, LmMapState* st, int solve_index, int write_back) {
+__device__ void d_lm_control(LmLmState* lm, const double* red /*28*/, const LmProblem& P, int write_back) {
   const double cost_e = red[27];
   if (lm->phase == 0) {
     // IterationZero
@@ -201,51 +201,53 @@ __device__ void d_lm_control(LmLmState* lm, const double* red /*28*/, LmMapState
     }
   }
   if (lm->done && write_back) {
-    for (int k = 0; k < 4; ++k) st->q_w_curr[k] = lm->x[k];
-    for (int k = 0; k < 3; ++k) st->t_w_curr[k] = lm->x[4 + k];
-    LmSolveSummary* S = &st->solve[solve_index];
+    for (int k = 0; k < 4; ++k) P.pose_q[k] = lm->x[k];
+    for (int k = 0; k < 3; ++k) P.pose_t[k] = lm->x[4 + k];
+    LmSolveSummary* S = P.summary;
     S->iterations = lm->iteration; S->num_successful = lm->num_successful; S->termination = lm->termination;
     S->num_factors = lm->nfactors; S->initial_cost = lm->initial_cost; S->final_cost = lm->cost;
   }
 }
 
 // ---- kernels -----------------------------------------------------------------------------
-__global__ void k_lm_begin(LmLmState* __restrict__ lm, LmMapState* __restrict__ st, const LmFactor* __restrict__ fac0,
-                           const LmFactor* __restrict__ fac1, int solve_index, int max_iter) {
-  // counts the factors of this association pass (corner_num / surf_num, :620,685) and arms the controller
+__global__ void k_lm_begin(LmLmState* __restrict__ lm, LmProblem P, int max_iter) {
+  // counts the factors of this association pass (corner_num / surf_num, laserMapping.cpp:620,685;
+  // corner_correspondence / plane_correspondence, laserOdometry.cpp:382,480) and arms the controller
   __shared__ int ws[33];
-  const int n0 = st->stack_n[0], n1 = st->stack_n[1];
+  const int gate = P.gate ? *P.gate : 1;
+  const int n0 = *P.n0, n1 = *P.n1;
   int c0 = 0, c1 = 0;
-  if (st->optimize) {
-    for (int i = threadIdx.x; i < n0; i += blockDim.x) c0 += fac0[i].kind >= 0;
-    for (int i = threadIdx.x; i < n1; i += blockDim.x) c1 += fac1[i].kind >= 0;
+  if (gate) {
+    for (int i = threadIdx.x; i < n0; i += blockDim.x) c0 += P.fac0[i].kind >= 0;
+    for (int i = threadIdx.x; i < n1; i += blockDim.x) c1 += P.fac1[i].kind >= 0;
   }
   int t0, t1;
   d_block_exscan(c0, ws, &t0);
   d_block_exscan(c1, ws, &t1);
   if (threadIdx.x == 0) {
-    st->corner_num[solve_index] = t0; st->surf_num[solve_index] = t1;
-    for (int k = 0; k < 4; ++k) lm->x[k] = st->q_w_curr[k];
-    for (int k = 0; k < 3; ++k) lm->x[4 + k] = st->t_w_curr[k];
+    if (P.count0) *P.count0 = t0;
+    if (P.count1) *P.count1 = t1;
+    for (int k = 0; k < 4; ++k) lm->x[k] = P.pose_q[k];
+    for (int k = 0; k < 3; ++k) lm->x[4 + k] = P.pose_t[k];
     for (int k = 0; k < 7; ++k) lm->cand[k] = lm->x[k];
     lm->radius = 1e4; lm->decrease_factor = 2.0; lm->reuse_diagonal = 0; lm->num_invalid = 0;
     lm->iteration = 0; lm->num_successful = 0; lm->termination = 0; lm->phase = 0; lm->max_iter = max_iter;
     lm->nfactors = t0 + t1; lm->ticket = 0; lm->initial_cost = 0.0; lm->cost = 0.0;
-    lm->done = (!st->optimize || (t0 + t1) == 0) ? 1 : 0;
-    if (lm->done && st->optimize) {   // Ceres: no residual blocks -> parameters untouched
-      LmSolveSummary* S = &st->solve[solve_index];
+    lm->done = (!gate || (t0 + t1) == 0) ? 1 : 0;
+    if (lm->done && P.summary) {   // Ceres: no residual blocks -> parameters untouched
+      LmSolveSummary* S = P.summary;
       S->iterations = 0; S->num_successful = 0; S->termination = 6; S->num_factors = 0; S->initial_cost = 0.0; S->final_cost = 0.0;
     }
   }
 }
 
-__global__ void __launch_bounds__(EVAL_THREADS) k_lm_eval(LmLmState* __restrict__ lm, LmMapState* __restrict__ st,
-                                                          const LmFactor* __restrict__ fac0, const LmFactor* __restrict__ fac1,
-                                                          double* __restrict__ partials, int solve_index, int write_back) {
+__global__ void __launch_bounds__(EVAL_THREADS) k_lm_eval(LmLmState* __restrict__ lm, LmProblem P,
+                                                          double* __restrict__ partials, int write_back) {
   if (lm->done) return;
   __shared__ double sred[EVAL_THREADS / 32][NRED];
   __shared__ bool s_last;
-  const int n0 = st->stack_n[0], n1 = st->stack_n[1];
+  const int n0 = *P.n0, n1 = *P.n1;
+  const LmFactor* __restrict__ fac0 = P.fac0; const LmFactor* __restrict__ fac1 = P.fac1;
   const double* xe = lm->phase == 0 ? lm->x : lm->cand;
   const double q[4] = { xe[0], xe[1], xe[2], xe[3] };
   const double t[3] = { xe[4], xe[5], xe[6] };
@@ -292,7 +294,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_lm_eval(LmLmState* __restrict_
   __syncthreads();
   if (threadIdx.x == 0) {
     lm->ticket = 0;
-    d_lm_control(lm, fin, st, solve_index, write_back);
+    d_lm_control(lm, fin, P, write_back);
   }
 }
 
@@ -312,24 +314,37 @@ static int eval_blocks(lmono_ctx* ctx, int n) {
   return b;
 }
 
-int lm_solve_enqueue(lmono_ctx* ctx, int solve_index, int n_max_corner, int n_max_surf, int max_iter) {
-  k_lm_begin<<<1, 1024, 0, ctx->stream>>>(ctx->d_lm, ctx->d_state, ctx->d_fac[0], ctx->d_fac[1], solve_index, max_iter);
+int lm_solve_problem(lmono_ctx* ctx, const LmProblem& P, int n_max, int max_iter, int write_back) {
+  k_lm_begin<<<1, 1024, 0, ctx->stream>>>(ctx->d_lm, P, max_iter);
   LM_LAUNCH_CHECK();
-  const int blocks = eval_blocks(ctx, n_max_corner + n_max_surf);
+  const int blocks = eval_blocks(ctx, n_max);
   for (int it = 0; it <= max_iter; ++it) {
-    k_lm_eval<<<blocks, EVAL_THREADS, 0, ctx->stream>>>(ctx->d_lm, ctx->d_state, ctx->d_fac[0], ctx->d_fac[1], ctx->d_partials, solve_index, 1);
+    k_lm_eval<<<blocks, EVAL_THREADS, 0, ctx->stream>>>(ctx->d_lm, P, ctx->d_partials, write_back);
     LM_LAUNCH_CHECK();
   }
   return LMONO_OK;
 }
 
+static LmProblem map_problem(lmono_ctx* ctx, int solve_index) {
+  LmMapState* st = ctx->d_state;
+  LmProblem P;
+  P.fac0 = ctx->d_fac[0]; P.fac1 = ctx->d_fac[1];
+  P.n0 = &st->stack_n[0]; P.n1 = &st->stack_n[1];
+  P.gate = &st->optimize;
+  P.pose_q = st->q_w_curr; P.pose_t = st->t_w_curr;
+  P.summary = &st->solve[solve_index];
+  P.count0 = &st->corner_num[solve_index]; P.count1 = &st->surf_num[solve_index];
+  return P;
+}
+
+int lm_solve_enqueue(lmono_ctx* ctx, int solve_index, int n_max_corner, int n_max_surf, int max_iter) {
+  return lm_solve_problem(ctx, map_problem(ctx, solve_index), n_max_corner + n_max_surf, max_iter, 1);
+}
+
 int lm_normal_eq_enqueue(lmono_ctx* ctx, int n_max_corner, int n_max_surf) {
   // max_iter = 0: IterationZero fills H, g, cost and the controller stops immediately
-  k_lm_begin<<<1, 1024, 0, ctx->stream>>>(ctx->d_lm, ctx->d_state, ctx->d_fac[0], ctx->d_fac[1], 0, 0);
-  LM_LAUNCH_CHECK();
-  const int blocks = eval_blocks(ctx, n_max_corner + n_max_surf);
-  k_lm_eval<<<blocks, EVAL_THREADS, 0, ctx->stream>>>(ctx->d_lm, ctx->d_state, ctx->d_fac[0], ctx->d_fac[1], ctx->d_partials, 0, 0);
-  LM_LAUNCH_CHECK();
+  int rc = lm_solve_problem(ctx, map_problem(ctx, 0), n_max_corner + n_max_surf, 0, 0);
+  if (rc) return rc;
   k_lm_export_normal_eq<<<1, 32, 0, ctx->stream>>>(ctx->d_lm, ctx->d_partials + 32 * 1024);
   LM_LAUNCH_CHECK();
   return LMONO_OK;

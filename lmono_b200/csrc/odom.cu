@@ -1,0 +1,350 @@
+// laserOdometry on device: replaces the main-loop body of Aloam/src/laserOdometry.cpp:265-568.
+//
+//   k_odom_nn1   :302,390   TransformToStart + exact nearest neighbour in the previous sweep's
+//                           less-sharp / less-flat cloud.  Tiled brute force: a CTA stages 256-point
+//                           tiles of the target cloud in shared memory for 64 queries x 4 lanes, target
+//                           chunks across blockIdx.y, chunk results merged with a packed 64-bit
+//                           atomicMin (d2 bits << 32 | index) => (d2, index) lexicographic minimum,
+//                           the oracle's brute-force tie rule.  d2 as FLANN L2_Simple, fp32 no FMA.
+//   k_odom_corr  :305-483   one warp per feature: the +-NEARBY_SCAN ring-window scans in the
+//                           reference's visiting order (ascending j, then descending j, strict '<'),
+//                           reproduced as arg-min over (d2, visit rank); builds the Edge / Plane factor.
+//   LM solve     :494-499   lm.cu (shared with laserMapping)
+//   k_odom_finish:504-505   t_w_curr += q_w_curr * t_last_curr ; q_w_curr *= q_last_curr
+// The "last" clouds (:554-563) stay resident on the device between sweeps.
+#include "common.cuh"
+#include <string.h>
+#include <stdlib.h>
+#include <float.h>
+
+struct OdomDev {
+  int32_t inited, do_solve;
+  int32_t n_sharp, n_flat, n_less_sharp, n_less_flat;
+  int32_t n_corner_last, n_surf_last;
+  int32_t corner_corr[2], plane_corr[2];
+  LmSolveSummary solve[2];
+  double para_q[4], para_t[3];      // q_last_curr (x,y,z,w), t_last_curr  (laserOdometry.cpp:97-98)
+  double q_w_curr[4], t_w_curr[3];  // :93-94
+};
+
+struct OdomState {
+  OdomDev* d; OdomDev* h;
+  float4* d_feat[4];                // sharp, less_sharp, flat, less_flat of the current sweep
+  float4* d_last[2];                // laserCloudCornerLast, laserCloudSurfLast
+  unsigned long long* d_best[2];    // packed 1-NN result per sharp / flat feature
+  int32_t* d_corr;                  // test hook: [n_sharp*2] + [n_flat*3]
+  int cap;
+};
+
+constexpr int NN_QB = 64, NN_SUB = 4, NN_TILE = 256, NN_CHUNK = 4096;
+
+__global__ void k_odom_begin(OdomDev* o, int n_sharp, int n_ls, int n_flat, int n_lf) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  o->n_sharp = n_sharp; o->n_less_sharp = n_ls; o->n_flat = n_flat; o->n_less_flat = n_lf;
+  o->do_solve = o->inited;                       // first frame only initialises (:267-271)
+  for (int k = 0; k < 2; ++k) {
+    o->corner_corr[k] = 0; o->plane_corr[k] = 0;
+    o->solve[k].iterations = 0; o->solve[k].num_successful = 0; o->solve[k].termination = 6; o->solve[k].num_factors = 0;
+    o->solve[k].initial_cost = 0.0; o->solve[k].final_cost = 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_odom_best_init(unsigned long long* b0, int n0, unsigned long long* b1, int n1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n0) b0[i] = ~0ULL;
+  if (i < n1) b1[i] = ~0ULL;
+}
+
+// TransformToStart (:111-129) with DISTORTION 0 (s = 1): q_last_curr * p + t_last_curr in double, stored float
+__device__ __forceinline__ float4 d_to_start(const OdomDev* o, float4 p) { return d_associate(o->para_q, o->para_t, p); }
+
+// blockIdx.z: 0 = sharp vs corner_last, 1 = flat vs surf_last
+__global__ void __launch_bounds__(NN_QB * NN_SUB) k_odom_nn1(const OdomDev* __restrict__ o, const float4* __restrict__ sharp,
+                                                             const float4* __restrict__ flat, const float4* __restrict__ corner_last,
+                                                             const float4* __restrict__ surf_last, unsigned long long* __restrict__ best0,
+                                                             unsigned long long* __restrict__ best1) {
+  __shared__ float4 tile[NN_TILE];
+  if (!o->do_solve) return;
+  const int which = blockIdx.z;
+  const int nq = which == 0 ? o->n_sharp : o->n_flat;
+  const int nt = which == 0 ? o->n_corner_last : o->n_surf_last;
+  const float4* __restrict__ qs = which == 0 ? sharp : flat;
+  const float4* __restrict__ ts = which == 0 ? corner_last : surf_last;
+  unsigned long long* __restrict__ best = which == 0 ? best0 : best1;
+  const int q0 = blockIdx.x * NN_QB;
+  const int c0 = blockIdx.y * NN_CHUNK;
+  if (q0 >= nq || c0 >= nt) return;
+  const int qi = q0 + (threadIdx.x / NN_SUB);
+  const int sub = threadIdx.x % NN_SUB;
+  float4 sel = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (qi < nq) sel = d_to_start(o, qs[qi]);
+  unsigned long long bestk = ~0ULL;
+  const int c1 = min(c0 + NN_CHUNK, nt);
+  for (int tb = c0; tb < c1; tb += NN_TILE) {
+    __syncthreads();
+    if (tb + (int)threadIdx.x < c1) tile[threadIdx.x] = ts[tb + threadIdx.x];
+    __syncthreads();
+    const int tn = min(NN_TILE, c1 - tb);
+    for (int k = sub; k < tn; k += NN_SUB) {
+      const float4 p = tile[k];
+      const float dx = __fsub_rn(sel.x, p.x), dy = __fsub_rn(sel.y, p.y), dz = __fsub_rn(sel.z, p.z);
+      float d = __fmul_rn(dx, dx);
+      d = __fadd_rn(d, __fmul_rn(dy, dy));
+      d = __fadd_rn(d, __fmul_rn(dz, dz));
+      const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)(tb + k);
+      bestk = key < bestk ? key : bestk;
+    }
+  }
+#pragma unroll
+  for (int ofs = NN_SUB / 2; ofs > 0; ofs >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, bestk, ofs);
+    bestk = other < bestk ? other : bestk;
+  }
+  if (sub == 0 && qi < nq && bestk != ~0ULL) atomicMin(&best[qi], bestk);
+}
+
+__device__ __forceinline__ float d_sqdis(float4 a, float4 sel) {
+  // (a.x - sel.x)*(a.x - sel.x) + (a.y - sel.y)*(a.y - sel.y) + (a.z - sel.z)*(a.z - sel.z), fp32 (:322-327)
+  const float dx = __fsub_rn(a.x, sel.x), dy = __fsub_rn(a.y, sel.y), dz = __fsub_rn(a.z, sel.z);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+__device__ __forceinline__ unsigned long long d_warp_min_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; }
+  return v;
+}
+
+// one warp per feature; features [0, n_sharp) are corners, [n_sharp, n_sharp + n_flat) planes
+__global__ void __launch_bounds__(256) k_odom_corr(const OdomDev* __restrict__ o, const float4* __restrict__ sharp,
+                                                   const float4* __restrict__ flat, const float4* __restrict__ corner_last,
+                                                   const float4* __restrict__ surf_last, const unsigned long long* __restrict__ best0,
+                                                   const unsigned long long* __restrict__ best1, LmFactor* __restrict__ fac0,
+                                                   LmFactor* __restrict__ fac1, int32_t* __restrict__ corr_out) {
+  if (!o->do_solve) return;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int ns = o->n_sharp, nf = o->n_flat;
+  if (warp >= ns + nf) return;
+  const bool is_corner = warp < ns;
+  const int qi = is_corner ? warp : warp - ns;
+  const float4 ori = is_corner ? sharp[qi] : flat[qi];
+  const float4* __restrict__ last = is_corner ? corner_last : surf_last;
+  const int nl = is_corner ? o->n_corner_last : o->n_surf_last;
+  LmFactor* f = (is_corner ? fac0 : fac1) + qi;
+  int32_t* co = corr_out ? (is_corner ? corr_out + qi * 2 : corr_out + ns * 2 + qi * 3) : nullptr;
+  const unsigned long long bk = (is_corner ? best0 : best1)[qi];
+  const float d_nn = __uint_as_float((uint32_t)(bk >> 32));
+  int closest = -1, ind2 = -1, ind3 = -1;
+  if (bk != ~0ULL && (double)d_nn < 25.0) {                   // DISTANCE_SQ_THRESHOLD :305,393
+    closest = (int)(uint32_t)bk;
+    const float4 sel = d_to_start(o, ori);
+    const int id = (int)last[closest].w;                       // closestPointScanID
+    unsigned long long m2 = ~0ULL, m3 = ~0ULL;
+    const unsigned long long gate = (unsigned long long)__float_as_uint(25.0f) << 32;   // candidates need d2 < 25
+    // ascending j (:312-335, 402-427)
+    bool stop = false;
+    for (int base = closest + 1; base < nl && !stop; base += 32) {
+      const int j = base + lane;
+      bool over = false; float4 p = make_float4(0.f, 0.f, 0.f, 0.f); int ring = 0;
+      if (j < nl) { p = last[j]; ring = (int)p.w; over = (double)ring > (double)id + 2.5; }
+      const unsigned om = __ballot_sync(0xffffffffu, over);
+      const int first_over = om ? (__ffs(om) - 1) : 32;
+      if (j < nl && lane < first_over) {
+        const float d = d_sqdis(p, sel);
+        const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)(j - closest);
+        if ((key >> 32) < (gate >> 32)) {
+          if (is_corner) { if (ring > id) m2 = key < m2 ? key : m2; }
+          else { if (ring <= id) m2 = key < m2 ? key : m2; else m3 = key < m3 ? key : m3; }
+        }
+      }
+      stop = om != 0;
+    }
+    // descending j (:338-361, 430-455); visit ranks continue after the ascending pass
+    const uint32_t rank0 = 1u << 30;
+    stop = false;
+    for (int base = closest - 1; base >= 0 && !stop; base -= 32) {
+      const int j = base - lane;
+      bool under = false; float4 p = make_float4(0.f, 0.f, 0.f, 0.f); int ring = 0;
+      if (j >= 0) { p = last[j]; ring = (int)p.w; under = (double)ring < (double)id - 2.5; }
+      const unsigned um = __ballot_sync(0xffffffffu, under);
+      const int first_under = um ? (__ffs(um) - 1) : 32;
+      if (j >= 0 && lane < first_under) {
+        const float d = d_sqdis(p, sel);
+        const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (rank0 + (uint32_t)(closest - j));
+        if ((key >> 32) < (gate >> 32)) {
+          if (is_corner) { if (ring < id) m2 = key < m2 ? key : m2; }
+          else { if (ring >= id) m2 = key < m2 ? key : m2; else m3 = key < m3 ? key : m3; }
+        }
+      }
+      stop = um != 0;
+    }
+    m2 = d_warp_min_u64(m2); m3 = d_warp_min_u64(m3);
+    if (m2 != ~0ULL) { const uint32_t r = (uint32_t)m2; ind2 = r >= rank0 ? closest - (int)(r - rank0) : closest + (int)r; }
+    if (m3 != ~0ULL) { const uint32_t r = (uint32_t)m3; ind3 = r >= rank0 ? closest - (int)(r - rank0) : closest + (int)r; }
+  }
+  if (lane != 0) return;
+  if (co) { co[0] = closest; co[1] = ind2; if (!is_corner) co[2] = ind3; }
+  if (is_corner) {
+    if (ind2 < 0) { f->kind = -1; return; }                    // :363
+    const float4 a = last[closest], b = last[ind2];
+    f->a[0] = a.x; f->a[1] = a.y; f->a[2] = a.z;
+    f->b[0] = b.x; f->b[1] = b.y; f->b[2] = b.z;
+    f->p[0] = ori.x; f->p[1] = ori.y; f->p[2] = ori.z;
+    f->kind = 0;
+  } else {
+    if (ind2 < 0 || ind3 < 0) { f->kind = -1; return; }        // :457
+    const float4 pj = last[closest], pl = last[ind2], pm = last[ind3];
+    const double j[3] = { pj.x, pj.y, pj.z }, l[3] = { pl.x, pl.y, pl.z }, m[3] = { pm.x, pm.y, pm.z };
+    // lidarFactor.hpp:64-65
+    const double u[3] = { j[0] - l[0], j[1] - l[1], j[2] - l[2] }, v[3] = { j[0] - m[0], j[1] - m[1], j[2] - m[2] };
+    double n[3] = { u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0] };
+    const double z2 = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+    if (z2 > 0.0) { const double nn = sqrt(z2); n[0] /= nn; n[1] /= nn; n[2] /= nn; }
+    for (int k = 0; k < 3; ++k) { f->a[k] = j[k]; f->b[k] = n[k]; }
+    f->p[0] = ori.x; f->p[1] = ori.y; f->p[2] = ori.z;
+    f->kind = 1;
+  }
+}
+
+__global__ void k_odom_finish(OdomDev* o) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (o->do_solve) {
+    double tmp[3]; d_qrot(o->q_w_curr, o->para_t, tmp);
+    for (int k = 0; k < 3; ++k) o->t_w_curr[k] = o->t_w_curr[k] + tmp[k];
+    double qn[4]; d_qmul(o->q_w_curr, o->para_q, qn);
+    for (int k = 0; k < 4; ++k) o->q_w_curr[k] = qn[k];
+  }
+  o->inited = 1;
+  o->n_corner_last = o->n_less_sharp; o->n_surf_last = o->n_less_flat;   // :554-563
+}
+
+__global__ void k_odom_reset(OdomDev* o) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  o->inited = 0; o->do_solve = 0;
+  o->n_corner_last = 0; o->n_surf_last = 0;
+  for (int k = 0; k < 4; ++k) { o->para_q[k] = k == 3; o->q_w_curr[k] = k == 3; }
+  for (int k = 0; k < 3; ++k) { o->para_t[k] = 0.0; o->t_w_curr[k] = 0.0; }
+}
+
+static int odom_state(lmono_ctx* ctx, OdomState** out) {
+  if (ctx->odom_state) { *out = (OdomState*)ctx->odom_state; return LMONO_OK; }
+  OdomState* s = (OdomState*)calloc(1, sizeof(OdomState));
+  s->cap = ctx->max_feat;
+  const size_t n = (size_t)s->cap;
+  LM_CUDA(cudaMalloc((void**)&s->d, sizeof(OdomDev)));
+  LM_CUDA(cudaMallocHost((void**)&s->h, sizeof(OdomDev)));
+  for (int k = 0; k < 4; ++k) LM_CUDA(cudaMalloc((void**)&s->d_feat[k], n * sizeof(float4)));
+  for (int k = 0; k < 2; ++k) { LM_CUDA(cudaMalloc((void**)&s->d_last[k], n * sizeof(float4))); LM_CUDA(cudaMalloc((void**)&s->d_best[k], n * sizeof(unsigned long long))); }
+  LM_CUDA(cudaMalloc((void**)&s->d_corr, n * 10 * sizeof(int32_t)));
+  k_odom_reset<<<1, 32, 0, ctx->stream>>>(s->d);
+  LM_LAUNCH_CHECK();
+  ctx->odom_state = s;
+  *out = s;
+  return LMONO_OK;
+}
+
+void lm_odom_free(lmono_ctx* ctx) {
+  OdomState* s = (OdomState*)ctx->odom_state;
+  if (!s) return;
+  cudaFree(s->d); cudaFreeHost(s->h);
+  for (int k = 0; k < 4; ++k) cudaFree(s->d_feat[k]);
+  for (int k = 0; k < 2; ++k) { cudaFree(s->d_last[k]); cudaFree(s->d_best[k]); }
+  cudaFree(s->d_corr);
+  free(s); ctx->odom_state = nullptr;
+}
+
+// one association pass on device-resident clouds of the current sweep
+static int odom_associate(lmono_ctx* ctx, OdomState* s, const float4* sharp, int n_sharp, const float4* flat, int n_flat, int nl_max0, int nl_max1, int pass) {
+  const int nq = n_sharp > n_flat ? n_sharp : n_flat;
+  if (nq <= 0) return LMONO_OK;
+  k_odom_best_init<<<lm_div_up(nq, 256), 256, 0, ctx->stream>>>(s->d_best[0], n_sharp, s->d_best[1], n_flat);
+  LM_LAUNCH_CHECK();
+  const int nlm = nl_max0 > nl_max1 ? nl_max0 : nl_max1;
+  if (nlm > 0) {
+    dim3 grid(lm_div_up(nq, NN_QB), lm_div_up(nlm, NN_CHUNK), 2);
+    k_odom_nn1<<<grid, NN_QB * NN_SUB, 0, ctx->stream>>>(s->d, sharp, flat, s->d_last[0], s->d_last[1], s->d_best[0], s->d_best[1]);
+    LM_LAUNCH_CHECK();
+  }
+  const int warps = n_sharp + n_flat;
+  k_odom_corr<<<lm_div_up(warps * 32, 256), 256, 0, ctx->stream>>>(s->d, sharp, flat, s->d_last[0], s->d_last[1], s->d_best[0], s->d_best[1],
+                                                                  ctx->d_fac[0], ctx->d_fac[1], s->d_corr + (size_t)pass * s->cap * 5);
+  LM_LAUNCH_CHECK();
+  return LMONO_OK;
+}
+
+// enqueue one odometry step on device-resident feature clouds (sizes known to the host)
+int lm_odom_enqueue(lmono_ctx* ctx, const float4* sharp, int n_sharp, const float4* less_sharp, int n_ls,
+                    const float4* flat, int n_flat, const float4* less_flat, int n_lf, int prev_ls_max, int prev_lf_max) {
+  OdomState* s; int rc = odom_state(ctx, &s); if (rc) return rc;
+  k_odom_begin<<<1, 32, 0, ctx->stream>>>(s->d, n_sharp, n_ls, n_flat, n_lf);
+  LM_LAUNCH_CHECK();
+  for (int opti = 0; opti < 2; ++opti) {                       // :278
+    if ((rc = odom_associate(ctx, s, sharp, n_sharp, flat, n_flat, prev_ls_max, prev_lf_max, opti))) return rc;
+    LmProblem P;
+    P.fac0 = ctx->d_fac[0]; P.fac1 = ctx->d_fac[1];
+    P.n0 = &s->d->n_sharp; P.n1 = &s->d->n_flat;
+    P.gate = &s->d->do_solve;
+    P.pose_q = s->d->para_q; P.pose_t = s->d->para_t;
+    P.summary = &s->d->solve[opti];
+    P.count0 = &s->d->corner_corr[opti]; P.count1 = &s->d->plane_corr[opti];
+    if ((rc = lm_solve_problem(ctx, P, n_sharp + n_flat, 4, 1))) return rc;
+  }
+  k_odom_finish<<<1, 32, 0, ctx->stream>>>(s->d);
+  LM_LAUNCH_CHECK();
+  if (n_ls > 0) LM_CUDA(cudaMemcpyAsync(s->d_last[0], less_sharp, (size_t)n_ls * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (n_lf > 0) LM_CUDA(cudaMemcpyAsync(s->d_last[1], less_flat, (size_t)n_lf * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+  return LMONO_OK;
+}
+
+extern "C" int lmono_odom_step(lmono_ctx* ctx, lmono_cloud_view sharp, lmono_cloud_view less_sharp, lmono_cloud_view flat,
+                               lmono_cloud_view less_flat, lmono_pose* last_curr, lmono_pose* w_curr, lmono_odom_report* report) {
+  if (!ctx) return LMONO_E_ARG;
+  OdomState* s; int rc = odom_state(ctx, &s); if (rc) return rc;
+  if (sharp.n > s->cap || less_sharp.n > s->cap || flat.n > s->cap || less_flat.n > s->cap) return LMONO_E_CAPACITY;
+  LM_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  lmono_cloud_view v[4] = { sharp, less_sharp, flat, less_flat };
+  for (int k = 0; k < 4; ++k) if ((rc = lm_upload_cloud(ctx, v[k], ctx->d_raw[k < 3 ? k : 0], s->d_feat[k], nullptr))) return rc;
+  // sizes of the previous sweep's clouds bound the search grids; cap is always safe
+  if ((rc = lm_odom_enqueue(ctx, s->d_feat[0], sharp.n, s->d_feat[1], less_sharp.n, s->d_feat[2], flat.n, s->d_feat[3], less_flat.n,
+                            s->h->n_corner_last > 0 ? s->h->n_corner_last : s->cap, s->h->n_surf_last > 0 ? s->h->n_surf_last : s->cap))) return rc;
+  LM_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  LM_CUDA(cudaMemcpyAsync(s->h, s->d, sizeof(OdomDev), cudaMemcpyDeviceToHost, ctx->stream));
+  LM_CUDA(cudaStreamSynchronize(ctx->stream));
+  const OdomDev* h = s->h;
+  if (last_curr) { memcpy(last_curr->q, h->para_q, 32); memcpy(last_curr->t, h->para_t, 24); }
+  if (w_curr) { memcpy(w_curr->q, h->q_w_curr, 32); memcpy(w_curr->t, h->t_w_curr, 24); }
+  if (report) {
+    memset(report, 0, sizeof(*report));
+    report->inited = h->do_solve;
+    for (int k = 0; k < 2; ++k) {
+      report->corner_corr[k] = h->corner_corr[k]; report->plane_corr[k] = h->plane_corr[k];
+      report->solve[k].iterations = h->solve[k].iterations; report->solve[k].num_successful = h->solve[k].num_successful;
+      report->solve[k].termination = h->solve[k].termination; report->solve[k].num_factors = h->solve[k].num_factors;
+      report->solve[k].initial_cost = h->solve[k].initial_cost; report->solve[k].final_cost = h->solve[k].final_cost;
+    }
+    float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); report->ms_gpu = ms;
+  }
+  return LMONO_OK;
+}
+
+extern "C" int lmono_odom_reset(lmono_ctx* ctx) {
+  if (!ctx) return LMONO_E_ARG;
+  OdomState* s; int rc = odom_state(ctx, &s); if (rc) return rc;
+  k_odom_reset<<<1, 32, 0, ctx->stream>>>(s->d);
+  LM_LAUNCH_CHECK();
+  memset(s->h, 0, sizeof(OdomDev));
+  return LMONO_OK;
+}
+
+// test hook: correspondences of association pass `pass` (0 or 1) of the last step:
+// corner_idx [n_sharp x 2] (closest, min2), plane_idx [n_flat x 3] (closest, min2, min3)
+extern "C" int lmono_odom_debug(lmono_ctx* ctx, int32_t pass, int32_t* corner_idx, int32_t n_sharp, int32_t* plane_idx, int32_t n_flat) {
+  OdomState* s = ctx ? (OdomState*)ctx->odom_state : nullptr;
+  if (!s || pass < 0 || pass > 1) return LMONO_E_STATE;
+  const int32_t* src = s->d_corr + (size_t)pass * s->cap * 5;
+  if (corner_idx && n_sharp > 0) LM_CUDA(cudaMemcpyAsync(corner_idx, src, (size_t)n_sharp * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (plane_idx && n_flat > 0) LM_CUDA(cudaMemcpyAsync(plane_idx, src + (size_t)n_sharp * 2, (size_t)n_flat * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  LM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return LMONO_OK;
+}

@@ -1,0 +1,609 @@
+// scanRegistration on device: replaces laserCloudHandler, Aloam/src/scanRegistration.cpp:132-408.
+//
+//   k_scan_classify  :136-137,166-200  NaN / range filter, elevation -> ring id, stable in-block
+//                                      rank per ring (warp match), per-block ring histogram,
+//                                      first / last surviving point (for startOri / endOri)
+//   k_scan_halfpass  :208-224          index of the first kept point with ori - startOri > pi
+//                                      (the reference's sequential halfPassed flag)
+//   k_scan_blockscan :246-252          per-ring exclusive scan of the block histograms
+//   k_scan_scatter   :208-252          relTime, intensity = ring + 0.1 relTime, stable ring-major
+//                                      reorder, scanStartInd / scanEndInd
+//   k_scan_curvature :256-266          11-tap curvature, strictly left-to-right fp32
+//   k_scan_ring      :277-405          one CTA per ring: six sector sorts (one warp each, keys in
+//                                      registers), the serial greedy pick with +-5 suppression,
+//                                      less-flat gather and the 0.2 m VoxelGrid of the ring
+//   k_scan_compact   :304-310,356,407  ring-ordered output clouds
+//
+// fp32 arithmetic uses __fmul_rn/__fadd_rn in the reference's association order; comparisons
+// against the double literals 0.1 / 0.05 widen the float first, as C++ does.
+#include "common.cuh"
+#include <string.h>
+#include <stdlib.h>
+#include <float.h>
+
+constexpr int SC_THREADS = 256;
+constexpr int SC_NRING = 65;            // 64 rings + bucket 64 = dropped
+constexpr int SC_RING_MAX = 4096;       // points per ring handled by k_scan_ring
+constexpr int SC_SECTOR_MAX = 1024;
+constexpr int SC_PICK_STRIDE = 26;      // per (ring, sector): 2 sharp + 20 less-sharp + 4 flat indices
+#define SC_PI 3.14159265358979323846
+
+struct ScanMeta {
+  int32_t first_valid, last_valid, i_star, n_kept;
+  int32_t ring_total[SC_NRING + 3];
+  int32_t ring_start[SC_NRING + 3];
+  int32_t out_n[4];                     // sharp, less_sharp, flat, less_flat
+  float start_ori, end_ori;
+  uint32_t fault;
+};
+
+struct ScanState {
+  int cap, nb_max;
+  float4* d_in; int32_t* d_key; int32_t* d_block_hist; int32_t* d_block_off;
+  ScanMeta* d_meta; ScanMeta* h_meta;
+  float4* d_full; int32_t* d_src; float* d_curv; int32_t* d_label;
+  int32_t* d_pick_idx; int32_t* d_pick_cnt;
+  float4* d_lf_tmp; int32_t* d_lf_cnt;
+  float4* d_out[4];
+};
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int d_ring_of(float x, float y, float z, int n_scans) {
+  // :166 angle = atan(z / sqrt(x*x + y*y)) * 180 / M_PI  (double libm overloads, float product-sum)
+  const float r2 = __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y));
+  const float angle = (float)(atan((double)z / sqrt((double)r2)) * 180 / SC_PI);
+  int scanID;
+  if (n_scans == 16) {
+    scanID = (int)((double)(__fdiv_rn(__fadd_rn(angle, 15.0f), 2.0f)) + 0.5);
+    if (scanID > (n_scans - 1) || scanID < 0) return -1;
+  } else if (n_scans == 32) {
+    scanID = (int)(((double)angle + 92.0 / 3.0) * 3.0 / 4.0);
+    if (scanID > (n_scans - 1) || scanID < 0) return -1;
+  } else {
+    if ((double)angle >= -8.83) scanID = (int)((2 - (double)angle) * 3.0 + 0.5);
+    else scanID = n_scans / 2 + (int)((-8.83 - (double)angle) * 2.0 + 0.5);
+    if ((double)angle > 2 || (double)angle < -24.33 || scanID > 50 || scanID < 0) return -1;
+  }
+  return scanID;
+}
+
+__device__ __forceinline__ float d_neg_atan2f(float y, float x) {
+  // std::atan2(float, float): evaluated in double and rounded once (CUDA's atan2f is 3 ulp)
+  return -(float)atan2((double)y, (double)x);
+}
+
+__global__ void __launch_bounds__(SC_THREADS) k_scan_classify(const float4* __restrict__ in, int n, int n_scans, float thres,
+                                                              int32_t* __restrict__ key, int32_t* __restrict__ block_hist, int nb,
+                                                              ScanMeta* __restrict__ meta) {
+  __shared__ int counts[SC_THREADS / 32][SC_NRING];
+  __shared__ int s_first[SC_THREADS / 32], s_last[SC_THREADS / 32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int e = threadIdx.x; e < (SC_THREADS / 32) * SC_NRING; e += blockDim.x) (&counts[0][0])[e] = 0;
+  int ring = 64;
+  bool valid0 = false;
+  if (i < n) {
+    const float4 p = in[i];
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+      const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(p.x, p.x), __fmul_rn(p.y, p.y)), __fmul_rn(p.z, p.z));
+      if (!(r2 < __fmul_rn(thres, thres))) {         // :99
+        valid0 = true;
+        int r = d_ring_of(p.x, p.y, p.z, n_scans);
+        if (r >= 0) ring = r;
+      }
+    }
+  }
+  // first / last point surviving the NaN and range filters (cloud [0] and [cloudSize-1], :141-143)
+  int fv = valid0 ? i : 0x7fffffff, lv = valid0 ? i : -1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { fv = min(fv, __shfl_xor_sync(0xffffffffu, fv, o)); lv = max(lv, __shfl_xor_sync(0xffffffffu, lv, o)); }
+  if (lane == 0) { s_first[wid] = fv; s_last[wid] = lv; }
+  __syncthreads();
+  const unsigned peers = __match_any_sync(0xffffffffu, ring);
+  const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+  if (rank_in_warp == 0) counts[wid][ring] = __popc(peers);
+  __syncthreads();
+  int base = 0;
+  for (int w = 0; w < wid; ++w) base += counts[w][ring];
+  if (i < n) key[i] = ring < 64 ? ((ring << 16) | (base + rank_in_warp)) : -1;
+  if (threadIdx.x < SC_NRING) {
+    int tot = 0;
+    for (int w = 0; w < SC_THREADS / 32; ++w) tot += counts[w][threadIdx.x];
+    block_hist[threadIdx.x * nb + blockIdx.x] = tot;
+  }
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < SC_THREADS / 32; ++w) { s_first[0] = min(s_first[0], s_first[w]); s_last[0] = max(s_last[0], s_last[w]); }
+    if (s_first[0] != 0x7fffffff) atomicMin(&meta->first_valid, s_first[0]);
+    if (s_last[0] >= 0) atomicMax(&meta->last_valid, s_last[0]);
+  }
+}
+
+__device__ __forceinline__ void d_start_end_ori(const float4* __restrict__ in, const ScanMeta* __restrict__ meta, float* so, float* eo) {
+  const float4 a = in[meta->first_valid], b = in[meta->last_valid];
+  float startOri = d_neg_atan2f(a.y, a.x);
+  float endOri = (float)((double)d_neg_atan2f(b.y, b.x) + 2 * SC_PI);
+  if ((double)__fsub_rn(endOri, startOri) > 3 * SC_PI) endOri = (float)((double)endOri - 2 * SC_PI);
+  else if ((double)__fsub_rn(endOri, startOri) < SC_PI) endOri = (float)((double)endOri + 2 * SC_PI);
+  *so = startOri; *eo = endOri;
+}
+
+__global__ void __launch_bounds__(SC_THREADS) k_scan_halfpass(const float4* __restrict__ in, int n, const int32_t* __restrict__ key,
+                                                              ScanMeta* __restrict__ meta) {
+  __shared__ float s_so, s_eo;
+  __shared__ int s_min[SC_THREADS / 32];
+  if (meta->last_valid < 0) return;
+  if (threadIdx.x == 0) d_start_end_ori(in, meta, &s_so, &s_eo);
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int cand = 0x7fffffff;
+  if (i < n && key[i] >= 0) {
+    const float4 p = in[i];
+    float ori = d_neg_atan2f(p.y, p.x);
+    const double so = (double)s_so;
+    if ((double)ori < so - SC_PI / 2) ori = (float)((double)ori + 2 * SC_PI);
+    else if ((double)ori > so + SC_PI * 3 / 2) ori = (float)((double)ori - 2 * SC_PI);
+    if ((double)__fsub_rn(ori, s_so) > SC_PI) cand = i;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+  if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = cand;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < SC_THREADS / 32; ++w) s_min[0] = min(s_min[0], s_min[w]);
+    if (s_min[0] != 0x7fffffff) atomicMin(&meta->i_star, s_min[0]);
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_blockscan(const int32_t* __restrict__ block_hist, int32_t* __restrict__ block_off, int nb,
+                                                         ScanMeta* __restrict__ meta) {
+  __shared__ int ws[33];
+  __shared__ int s_carry;
+  const int r = blockIdx.x;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += blockDim.x) {
+    const int e = base + threadIdx.x;
+    int v = e < nb ? block_hist[r * nb + e] : 0;
+    int total;
+    int ex = d_block_exscan(v, ws, &total);
+    if (e < nb) block_off[r * nb + e] = s_carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) meta->ring_total[r] = s_carry;
+}
+
+__global__ void __launch_bounds__(SC_THREADS) k_scan_scatter(const float4* __restrict__ in, int n, int n_scans, const int32_t* __restrict__ key,
+                                                             const int32_t* __restrict__ block_off, int nb, ScanMeta* __restrict__ meta,
+                                                             float4* __restrict__ full, int32_t* __restrict__ src) {
+  __shared__ int s_start[SC_NRING + 1];
+  __shared__ float s_so, s_eo;
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int r = 0; r < 64; ++r) { s_start[r] = acc; acc += (r < n_scans) ? meta->ring_total[r] : 0; }
+    s_start[64] = acc;
+    s_so = 0.f; s_eo = 1.f;
+    if (meta->last_valid >= 0) d_start_end_ori(in, meta, &s_so, &s_eo);
+    if (blockIdx.x == 0) {
+      for (int r = 0; r <= 64; ++r) meta->ring_start[r] = s_start[r];
+      meta->n_kept = acc; meta->start_ori = s_so; meta->end_ori = s_eo;
+    }
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int k = key[i];
+  if (k < 0) return;
+  const int ring = k >> 16, rank = k & 0xffff;
+  const float4 p = in[i];
+  float ori = d_neg_atan2f(p.y, p.x);
+  const double so = (double)s_so, eo = (double)s_eo;
+  if (i <= meta->i_star) {                 // halfPassed still false when this point is visited
+    if ((double)ori < so - SC_PI / 2) ori = (float)((double)ori + 2 * SC_PI);
+    else if ((double)ori > so + SC_PI * 3 / 2) ori = (float)((double)ori - 2 * SC_PI);
+  } else {
+    ori = (float)((double)ori + 2 * SC_PI);
+    if ((double)ori < eo - SC_PI * 3 / 2) ori = (float)((double)ori + 2 * SC_PI);
+    else if ((double)ori > eo + SC_PI / 2) ori = (float)((double)ori - 2 * SC_PI);
+  }
+  const float relTime = __fdiv_rn(__fsub_rn(ori, s_so), __fsub_rn(s_eo, s_so));
+  const int pos = s_start[ring] + block_off[ring * nb + blockIdx.x] + rank;
+  full[pos] = make_float4(p.x, p.y, p.z, (float)((double)ring + 0.1 * (double)relTime));
+  src[pos] = i;
+}
+
+__global__ void __launch_bounds__(SC_THREADS) k_scan_curvature(const float4* __restrict__ full, const ScanMeta* __restrict__ meta,
+                                                               float* __restrict__ curv, int32_t* __restrict__ label) {
+  const int N = meta->n_kept;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  label[i] = 0;
+  if (i < 5 || i >= N - 5) { curv[i] = 0.f; return; }
+  float dx = full[i - 5].x, dy = full[i - 5].y, dz = full[i - 5].z;
+#pragma unroll
+  for (int o = -4; o <= -1; ++o) { const float4 q = full[i + o]; dx = __fadd_rn(dx, q.x); dy = __fadd_rn(dy, q.y); dz = __fadd_rn(dz, q.z); }
+  { const float4 q = full[i]; dx = __fsub_rn(dx, __fmul_rn(10.0f, q.x)); dy = __fsub_rn(dy, __fmul_rn(10.0f, q.y)); dz = __fsub_rn(dz, __fmul_rn(10.0f, q.z)); }
+#pragma unroll
+  for (int o = 1; o <= 5; ++o) { const float4 q = full[i + o]; dx = __fadd_rn(dx, q.x); dy = __fadd_rn(dy, q.y); dz = __fadd_rn(dz, q.z); }
+  curv[i] = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int ITEMS>
+__device__ __forceinline__ void d_warp_sort_sector(unsigned long long* dst, const float* __restrict__ curv, int sp, int len, int lane) {
+  unsigned long long v[ITEMS];
+#pragma unroll
+  for (int r = 0; r < ITEMS; ++r) {
+    const int e = lane * ITEMS + r;
+    v[r] = e < len ? (((unsigned long long)__float_as_uint(curv[sp + e]) << 32) | (uint32_t)(sp + e)) : ~0ULL;
+  }
+  d_bitonic_regs<ITEMS>(v, lane, 32, nullptr);
+#pragma unroll
+  for (int r = 0; r < ITEMS; ++r) dst[lane * ITEMS + r] = v[r];
+}
+
+__device__ __forceinline__ bool d_gap_exceeds(const float* xyz, int a, int b) {
+  // (p[a] - p[b]) squared norm > 0.05 (double literal), fp32 left to right
+  const float dx = __fsub_rn(xyz[a * 3], xyz[b * 3]), dy = __fsub_rn(xyz[a * 3 + 1], xyz[b * 3 + 1]), dz = __fsub_rn(xyz[a * 3 + 2], xyz[b * 3 + 2]);
+  const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+  return (double)d > 0.05;
+}
+
+template <int ITEMS>
+__device__ __forceinline__ void d_block_sort_lf(unsigned long long* xch, int n, const float* xyz, const uint16_t* lf, const int* vgp, float inv) {
+  unsigned long long v[ITEMS];
+#pragma unroll
+  for (int r = 0; r < ITEMS; ++r) {
+    const int e = threadIdx.x * ITEMS + r;
+    unsigned long long c = ~0ULL;
+    if (e < n) {
+      const int li = lf[e];
+      int ijk0 = (int)(__fsub_rn(floorf(__fmul_rn(xyz[li * 3], inv)), (float)vgp[0]));
+      int ijk1 = (int)(__fsub_rn(floorf(__fmul_rn(xyz[li * 3 + 1], inv)), (float)vgp[1]));
+      int ijk2 = (int)(__fsub_rn(floorf(__fmul_rn(xyz[li * 3 + 2], inv)), (float)vgp[2]));
+      int idx = ijk0 + ijk1 * vgp[3] + ijk2 * vgp[4];
+      c = ((unsigned long long)(uint32_t)idx << 32) | (uint32_t)e;
+    }
+    v[r] = c;
+  }
+  d_bitonic_regs<ITEMS>(v, threadIdx.x, SC_THREADS, xch);
+#pragma unroll
+  for (int r = 0; r < ITEMS; ++r) xch[threadIdx.x * ITEMS + r] = v[r];
+  __syncthreads();
+}
+
+// dynamic shared memory layout of k_scan_ring
+constexpr int SCR_SEC_BYTES = 6 * SC_SECTOR_MAX * 8;                  // 49152: sector sort keys / voxel sort keys
+constexpr int SCR_XYZ_BYTES = SC_RING_MAX * 12;                       // 49152
+constexpr int SCR_INT_BYTES = SC_RING_MAX * 4;                        // intensity
+constexpr int SCR_PICK_BYTES = SC_RING_MAX + 32;                      // picked flags
+constexpr int SCR_LABEL_BYTES = SC_RING_MAX;                          // labels (int8)
+constexpr int SCR_LF_BYTES = SC_RING_MAX * 2;                         // less-flat local indices (uint16)
+constexpr int SCR_TOTAL = SCR_SEC_BYTES + SCR_XYZ_BYTES + SCR_INT_BYTES + SCR_PICK_BYTES + SCR_LABEL_BYTES + SCR_LF_BYTES + 256;
+
+__global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __restrict__ full, const float* __restrict__ curv,
+                                                             ScanMeta* __restrict__ meta, int32_t* __restrict__ label_out,
+                                                             int32_t* __restrict__ pick_idx, int32_t* __restrict__ pick_cnt,
+                                                             float4* __restrict__ lf_tmp, int32_t* __restrict__ lf_cnt) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned long long* sec = reinterpret_cast<unsigned long long*>(smem);
+  float* xyz = reinterpret_cast<float*>(smem + SCR_SEC_BYTES);
+  float* inten = reinterpret_cast<float*>(smem + SCR_SEC_BYTES + SCR_XYZ_BYTES);
+  unsigned char* picked = smem + SCR_SEC_BYTES + SCR_XYZ_BYTES + SCR_INT_BYTES;
+  signed char* label = reinterpret_cast<signed char*>(picked + SCR_PICK_BYTES);
+  uint16_t* lf = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(label) + SCR_LABEL_BYTES);
+  int* ws = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(lf) + SCR_LF_BYTES);     // [64]
+  __shared__ int s_vg[8];
+  __shared__ float s_mn[3][SC_THREADS / 32], s_mx[3][SC_THREADS / 32];
+
+  const int r = blockIdx.x;
+  const int rs = meta->ring_start[r], re = meta->ring_start[r + 1];
+  const int L = re - rs;
+  const int S = rs + 5, E = re - 6;
+  if (threadIdx.x < 18) pick_cnt[r * 18 + threadIdx.x] = 0;
+  if (threadIdx.x == 0) lf_cnt[r] = 0;
+  if (E - S < 6) return;                                  // :279
+  if (L > SC_RING_MAX) { if (threadIdx.x == 0) atomicOr(&meta->fault, 1u); return; }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    const float4 p = full[rs + i];
+    xyz[i * 3] = p.x; xyz[i * 3 + 1] = p.y; xyz[i * 3 + 2] = p.z; inten[i] = p.w;
+    picked[i] = 0; label[i] = 0;
+  }
+  // :284-288 six sector sorts, one warp each, (curvature, index) ascending
+  if (wid < 6) {
+    const int sp = S + (E - S) * wid / 6, ep = S + (E - S) * (wid + 1) / 6 - 1;
+    const int len = ep - sp + 1;
+    unsigned long long* dst = sec + wid * SC_SECTOR_MAX;
+    if (len > SC_SECTOR_MAX) { if (lane == 0) atomicOr(&meta->fault, 2u); }
+    else if (len <= 256) d_warp_sort_sector<8>(dst, curv, sp, len, lane);
+    else if (len <= 512) d_warp_sort_sector<16>(dst, curv, sp, len, lane);
+    else d_warp_sort_sector<32>(dst, curv, sp, len, lane);
+  }
+  __syncthreads();
+
+  // :291-390 greedy picking: sectors of a ring are order dependent (suppression crosses the
+  // sector border), so one thread walks them in sequence; all its data is in shared memory.
+  if (threadIdx.x == 0) {
+    for (int j = 0; j < 6; ++j) {
+      const int sp = S + (E - S) * j / 6, ep = S + (E - S) * (j + 1) / 6 - 1;
+      const int len = ep - sp + 1;
+      if (len > SC_SECTOR_MAX) continue;
+      const unsigned long long* sk = sec + j * SC_SECTOR_MAX;
+      int* out = pick_idx + (r * 6 + j) * SC_PICK_STRIDE;
+      int n_sharp = 0, n_ls = 0, n_flat = 0;
+      int largest = 0;
+      for (int k = len - 1; k >= 0; --k) {
+        const unsigned long long c = sk[k];
+        if (!((double)__uint_as_float((uint32_t)(c >> 32)) > 0.1)) break;     // sorted: nothing below qualifies either
+        const int ind = (int)(uint32_t)c, li = ind - rs;
+        if (picked[li]) continue;
+        largest++;
+        if (largest <= 2) { label[li] = 2; out[n_sharp++] = ind; out[2 + n_ls++] = ind; }
+        else if (largest <= 20) { label[li] = 1; out[2 + n_ls++] = ind; }
+        else break;
+        picked[li] = 1;
+        for (int l = 1; l <= 5; l++) { if (d_gap_exceeds(xyz, li + l, li + l - 1)) break; picked[li + l] = 1; }
+        for (int l = -1; l >= -5; l--) { if (d_gap_exceeds(xyz, li + l, li + l + 1)) break; picked[li + l] = 1; }
+      }
+      int smallest = 0;
+      for (int k = 0; k < len; ++k) {
+        const unsigned long long c = sk[k];
+        if (!((double)__uint_as_float((uint32_t)(c >> 32)) < 0.1)) break;
+        const int ind = (int)(uint32_t)c, li = ind - rs;
+        if (picked[li]) continue;
+        label[li] = -1; out[22 + n_flat++] = ind;
+        smallest++;
+        if (smallest >= 4) break;                                             // :359-362
+        picked[li] = 1;
+        for (int l = 1; l <= 5; l++) { if (d_gap_exceeds(xyz, li + l, li + l - 1)) break; picked[li + l] = 1; }
+        for (int l = -1; l >= -5; l--) { if (d_gap_exceeds(xyz, li + l, li + l + 1)) break; picked[li + l] = 1; }
+      }
+      pick_cnt[r * 18 + j * 3 + 0] = n_sharp; pick_cnt[r * 18 + j * 3 + 1] = n_ls; pick_cnt[r * 18 + j * 3 + 2] = n_flat;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < L; i += blockDim.x) label_out[rs + i] = (int)label[i];
+
+  // :392-398 less-flat = every k in [sp_0, ep_5] with label <= 0, in index order
+  const int k0 = S - rs, k1 = (S + (E - S) * 6 / 6 - 1) - rs;      // local, inclusive
+  int n_lf = 0;
+  for (int base = k0; base <= k1; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int flag = (i <= k1 && label[i] <= 0) ? 1 : 0;
+    int total;
+    const int ex = d_block_exscan(flag, ws, &total);
+    if (flag) lf[n_lf + ex] = (uint16_t)i;
+    n_lf += total;
+  }
+  __syncthreads();
+  if (n_lf == 0) return;
+
+  // :401-405 VoxelGrid(0.2) of the ring's less-flat points (PCL arithmetic, see voxel.cu)
+  const float inv = 1.0f / 0.2f;
+  float mn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, mx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+  for (int e = threadIdx.x; e < n_lf; e += blockDim.x) {
+    const int li = lf[e];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { mn[d] = fminf(mn[d], xyz[li * 3 + d]); mx[d] = fmaxf(mx[d], xyz[li * 3 + d]); }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o)); mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o)); }
+    if (lane == 0) { s_mn[d][wid] = mn[d]; s_mx[d][wid] = mx[d]; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long dd[3]; int minb[3], divb[3];
+    for (int d = 0; d < 3; ++d) {
+      float a = s_mn[d][0], b = s_mx[d][0];
+      for (int w = 1; w < SC_THREADS / 32; ++w) { a = fminf(a, s_mn[d][w]); b = fmaxf(b, s_mx[d][w]); }
+      dd[d] = (long long)(__fmul_rn(__fsub_rn(b, a), inv)) + 1;
+      minb[d] = (int)floorf(__fmul_rn(a, inv));
+      divb[d] = (int)floorf(__fmul_rn(b, inv)) - minb[d] + 1;
+    }
+    s_vg[0] = minb[0]; s_vg[1] = minb[1]; s_vg[2] = minb[2];
+    s_vg[3] = divb[0]; s_vg[4] = divb[0] * divb[1];
+    s_vg[5] = (dd[0] * dd[1] * dd[2] > (long long)INT32_MAX) ? 1 : 0;
+  }
+  __syncthreads();
+  float4* outp = lf_tmp + rs;
+  if (s_vg[5]) {                                   // PCL: leaf too small -> cloud returned unchanged
+    for (int e = threadIdx.x; e < n_lf; e += blockDim.x) { const int li = lf[e]; outp[e] = make_float4(xyz[li * 3], xyz[li * 3 + 1], xyz[li * 3 + 2], inten[li]); }
+    if (threadIdx.x == 0) lf_cnt[r] = n_lf;
+    return;
+  }
+  if (n_lf <= SC_THREADS * 4) d_block_sort_lf<4>(sec, n_lf, xyz, lf, s_vg, inv);
+  else if (n_lf <= SC_THREADS * 8) d_block_sort_lf<8>(sec, n_lf, xyz, lf, s_vg, inv);
+  else d_block_sort_lf<16>(sec, n_lf, xyz, lf, s_vg, inv);
+  int n_out = 0;
+  for (int base = 0; base < n_lf; base += blockDim.x) {
+    const int e = base + threadIdx.x;
+    int head = 0; unsigned long long me = 0;
+    if (e < n_lf) { me = sec[e]; head = (e == 0) || ((me >> 32) != (sec[e - 1] >> 32)); }
+    int total;
+    const int ex = d_block_exscan(head, ws, &total);
+    if (head) {
+      const uint32_t key = (uint32_t)(me >> 32);
+      float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f; int cnt = 0;
+      for (int m = e; m < n_lf; ++m) {
+        const unsigned long long c = sec[m];
+        if ((uint32_t)(c >> 32) != key) break;
+        const int li = lf[(uint32_t)c];
+        sx = __fadd_rn(sx, xyz[li * 3]); sy = __fadd_rn(sy, xyz[li * 3 + 1]); sz = __fadd_rn(sz, xyz[li * 3 + 2]); si = __fadd_rn(si, inten[li]);
+        ++cnt;
+      }
+      const float c = (float)cnt;
+      outp[n_out + ex] = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), __fdiv_rn(si, c));
+    }
+    n_out += total;
+  }
+  if (threadIdx.x == 0) lf_cnt[r] = n_out;
+}
+
+__global__ void __launch_bounds__(SC_THREADS) k_scan_compact(const float4* __restrict__ full, ScanMeta* __restrict__ meta, int n_scans,
+                                                             const int32_t* __restrict__ pick_idx, const int32_t* __restrict__ pick_cnt,
+                                                             const float4* __restrict__ lf_tmp, const int32_t* __restrict__ lf_cnt,
+                                                             float4* __restrict__ o_sharp, float4* __restrict__ o_ls,
+                                                             float4* __restrict__ o_flat, float4* __restrict__ o_lf) {
+  const int b = blockIdx.x;
+  if (b < n_scans) {
+    int off = 0;
+    for (int r = 0; r < b; ++r) off += lf_cnt[r];
+    const int cnt = lf_cnt[b];
+    const float4* src = lf_tmp + meta->ring_start[b];
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) o_lf[off + i] = src[i];
+    if (b == n_scans - 1 && threadIdx.x == 0) meta->out_n[3] = off + cnt;
+    return;
+  }
+  // picks: (ring, sector) major, pick order inside
+  __shared__ int s_off[3];
+  if (threadIdx.x == 0) { s_off[0] = s_off[1] = s_off[2] = 0; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int a0 = 0, a1 = 0, a2 = 0;
+    for (int e = 0; e < n_scans * 6; ++e) {
+      const int c0 = pick_cnt[e * 3], c1 = pick_cnt[e * 3 + 1], c2 = pick_cnt[e * 3 + 2];
+      const int* idx = pick_idx + e * SC_PICK_STRIDE;
+      for (int k = 0; k < c0; ++k) o_sharp[a0 + k] = full[idx[k]];
+      for (int k = 0; k < c1; ++k) o_ls[a1 + k] = full[idx[2 + k]];
+      for (int k = 0; k < c2; ++k) o_flat[a2 + k] = full[idx[22 + k]];
+      a0 += c0; a1 += c1; a2 += c2;
+    }
+    meta->out_n[0] = a0; meta->out_n[1] = a1; meta->out_n[2] = a2;
+  }
+}
+
+__global__ void k_scan_meta_init(ScanMeta* meta) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  meta->first_valid = 0x7fffffff; meta->last_valid = -1; meta->i_star = 0x7fffffff; meta->n_kept = 0;
+  for (int r = 0; r < SC_NRING + 3; ++r) { meta->ring_total[r] = 0; meta->ring_start[r] = 0; }
+  for (int k = 0; k < 4; ++k) meta->out_n[k] = 0;
+  meta->start_ori = 0.f; meta->end_ori = 0.f; meta->fault = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int scan_state(lmono_ctx* ctx, ScanState** out) {
+  if (ctx->scan_state) { *out = (ScanState*)ctx->scan_state; return LMONO_OK; }
+  ScanState* s = (ScanState*)calloc(1, sizeof(ScanState));
+  s->cap = ctx->max_sweep; s->nb_max = lm_div_up(s->cap, SC_THREADS);
+  const size_t n = (size_t)s->cap;
+  LM_CUDA(cudaMalloc((void**)&s->d_in, n * sizeof(float4)));
+  LM_CUDA(cudaMalloc((void**)&s->d_key, n * sizeof(int32_t)));
+  LM_CUDA(cudaMalloc((void**)&s->d_block_hist, (size_t)SC_NRING * s->nb_max * sizeof(int32_t)));
+  LM_CUDA(cudaMalloc((void**)&s->d_block_off, (size_t)SC_NRING * s->nb_max * sizeof(int32_t)));
+  LM_CUDA(cudaMalloc((void**)&s->d_meta, sizeof(ScanMeta)));
+  LM_CUDA(cudaMallocHost((void**)&s->h_meta, sizeof(ScanMeta)));
+  LM_CUDA(cudaMalloc((void**)&s->d_full, n * sizeof(float4)));
+  LM_CUDA(cudaMalloc((void**)&s->d_src, n * sizeof(int32_t)));
+  LM_CUDA(cudaMalloc((void**)&s->d_curv, n * sizeof(float)));
+  LM_CUDA(cudaMalloc((void**)&s->d_label, n * sizeof(int32_t)));
+  LM_CUDA(cudaMalloc((void**)&s->d_pick_idx, (size_t)64 * 6 * SC_PICK_STRIDE * sizeof(int32_t)));
+  LM_CUDA(cudaMalloc((void**)&s->d_pick_cnt, (size_t)64 * 18 * sizeof(int32_t)));
+  LM_CUDA(cudaMalloc((void**)&s->d_lf_tmp, n * sizeof(float4)));
+  LM_CUDA(cudaMalloc((void**)&s->d_lf_cnt, 64 * sizeof(int32_t)));
+  LM_CUDA(cudaMalloc((void**)&s->d_out[0], (size_t)64 * 6 * 2 * sizeof(float4)));
+  LM_CUDA(cudaMalloc((void**)&s->d_out[1], (size_t)64 * 6 * 20 * sizeof(float4)));
+  LM_CUDA(cudaMalloc((void**)&s->d_out[2], (size_t)64 * 6 * 4 * sizeof(float4)));
+  LM_CUDA(cudaMalloc((void**)&s->d_out[3], n * sizeof(float4)));
+  LM_CUDA(cudaFuncSetAttribute(k_scan_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, SCR_TOTAL));
+  ctx->scan_state = s;
+  *out = s;
+  return LMONO_OK;
+}
+
+void lm_scan_free(lmono_ctx* ctx) {
+  ScanState* s = (ScanState*)ctx->scan_state;
+  if (!s) return;
+  cudaFree(s->d_in); cudaFree(s->d_key); cudaFree(s->d_block_hist); cudaFree(s->d_block_off); cudaFree(s->d_meta); cudaFreeHost(s->h_meta);
+  cudaFree(s->d_full); cudaFree(s->d_src); cudaFree(s->d_curv); cudaFree(s->d_label); cudaFree(s->d_pick_idx); cudaFree(s->d_pick_cnt);
+  cudaFree(s->d_lf_tmp); cudaFree(s->d_lf_cnt);
+  for (int k = 0; k < 4; ++k) cudaFree(s->d_out[k]);
+  free(s); ctx->scan_state = nullptr;
+}
+
+// enqueue the whole stage on a device-resident float4 input; results stay on the device
+int lm_scan_enqueue(lmono_ctx* ctx, const float4* d_in, int n) {
+  ScanState* s; int rc = scan_state(ctx, &s); if (rc) return rc;
+  const int n_scans = ctx->prm.scan_line;
+  const int nb = lm_div_up(n > 0 ? n : 1, SC_THREADS);
+  k_scan_meta_init<<<1, 32, 0, ctx->stream>>>(s->d_meta); LM_LAUNCH_CHECK();
+  k_scan_classify<<<nb, SC_THREADS, 0, ctx->stream>>>(d_in, n, n_scans, ctx->prm.minimum_range, s->d_key, s->d_block_hist, nb, s->d_meta); LM_LAUNCH_CHECK();
+  k_scan_halfpass<<<nb, SC_THREADS, 0, ctx->stream>>>(d_in, n, s->d_key, s->d_meta); LM_LAUNCH_CHECK();
+  k_scan_blockscan<<<64, 1024, 0, ctx->stream>>>(s->d_block_hist, s->d_block_off, nb, s->d_meta); LM_LAUNCH_CHECK();
+  k_scan_scatter<<<nb, SC_THREADS, 0, ctx->stream>>>(d_in, n, n_scans, s->d_key, s->d_block_off, nb, s->d_meta, s->d_full, s->d_src); LM_LAUNCH_CHECK();
+  k_scan_curvature<<<nb, SC_THREADS, 0, ctx->stream>>>(s->d_full, s->d_meta, s->d_curv, s->d_label); LM_LAUNCH_CHECK();
+  k_scan_ring<<<n_scans, SC_THREADS, SCR_TOTAL, ctx->stream>>>(s->d_full, s->d_curv, s->d_meta, s->d_label, s->d_pick_idx, s->d_pick_cnt, s->d_lf_tmp, s->d_lf_cnt); LM_LAUNCH_CHECK();
+  k_scan_compact<<<n_scans + 1, SC_THREADS, 0, ctx->stream>>>(s->d_full, s->d_meta, n_scans, s->d_pick_idx, s->d_pick_cnt, s->d_lf_tmp, s->d_lf_cnt,
+                                                              s->d_out[0], s->d_out[1], s->d_out[2], s->d_out[3]); LM_LAUNCH_CHECK();
+  return LMONO_OK;
+}
+
+// device-side views of the stage outputs (for the fused pipeline and the odometry stage)
+int lm_scan_outputs(lmono_ctx* ctx, const float4** full, const float4** sharp, const float4** less_sharp, const float4** flat,
+                    const float4** less_flat, const int32_t** counts /* device: n_kept at [0], out_n[4] at [1..4] */) {
+  ScanState* s = (ScanState*)ctx->scan_state;
+  if (!s) return LMONO_E_STATE;
+  if (full) *full = s->d_full;
+  if (sharp) *sharp = s->d_out[0];
+  if (less_sharp) *less_sharp = s->d_out[1];
+  if (flat) *flat = s->d_out[2];
+  if (less_flat) *less_flat = s->d_out[3];
+  if (counts) *counts = &s->d_meta->n_kept;
+  return LMONO_OK;
+}
+
+extern "C" int lmono_scan_register(lmono_ctx* ctx, lmono_cloud_view raw, lmono_cloud_out* full, lmono_cloud_out* sharp,
+                                   lmono_cloud_out* less_sharp, lmono_cloud_out* flat, lmono_cloud_out* less_flat,
+                                   int32_t* labels, lmono_scan_report* report) {
+  if (!ctx) return LMONO_E_ARG;
+  if (raw.n > ctx->max_sweep) return LMONO_E_CAPACITY;
+  ScanState* s; int rc = scan_state(ctx, &s); if (rc) return rc;
+  LM_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  if ((rc = lm_upload_cloud(ctx, raw, ctx->d_raw[2], s->d_in, nullptr))) return rc;
+  if ((rc = lm_scan_enqueue(ctx, s->d_in, raw.n))) return rc;
+  LM_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  LM_CUDA(cudaMemcpyAsync(s->h_meta, s->d_meta, sizeof(ScanMeta), cudaMemcpyDeviceToHost, ctx->stream));
+  LM_CUDA(cudaStreamSynchronize(ctx->stream));
+  const ScanMeta* m = s->h_meta;
+  if (report) {
+    memset(report, 0, sizeof(*report));
+    report->n_in = raw.n; report->n_kept = m->n_kept;
+    report->n_sharp = m->out_n[0]; report->n_less_sharp = m->out_n[1]; report->n_flat = m->out_n[2]; report->n_less_flat = m->out_n[3];
+    for (int r = 0; r < 64; ++r) {
+      report->ring_start[r] = r < ctx->prm.scan_line ? m->ring_start[r] + 5 : 0;
+      report->ring_end[r] = r < ctx->prm.scan_line ? m->ring_start[r + 1] - 6 : 0;
+    }
+    report->start_ori = m->start_ori; report->end_ori = m->end_ori;
+    float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); report->ms_gpu = ms;
+  }
+  if (m->fault) { fprintf(stderr, "[lmono_b200] scan_register fault bits 0x%x (ring or sector larger than the kernel limit)\n", m->fault); return LMONO_E_DEVICE; }
+  int worst = LMONO_OK;
+  lmono_cloud_out* outs[5] = { full, sharp, less_sharp, flat, less_flat };
+  const float4* srcs[5] = { s->d_full, s->d_out[0], s->d_out[1], s->d_out[2], s->d_out[3] };
+  const int counts[5] = { m->n_kept, m->out_n[0], m->out_n[1], m->out_n[2], m->out_n[3] };
+  for (int k = 0; k < 5; ++k) {
+    if (!outs[k]) continue;
+    int r2 = lm_download_cloud(ctx, srcs[k], counts[k], outs[k]);
+    if (r2 && !worst) worst = r2;
+  }
+  if (labels && m->n_kept > 0) {
+    LM_CUDA(cudaMemcpyAsync(labels, s->d_label, (size_t)m->n_kept * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    LM_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return worst;
+}
+
+// test hook: curvature and source indices of the last sweep
+extern "C" int lmono_scan_debug(lmono_ctx* ctx, float* curvature, int32_t* src_index, int32_t n) {
+  ScanState* s = ctx ? (ScanState*)ctx->scan_state : nullptr;
+  if (!s) return LMONO_E_STATE;
+  if (n <= 0) return LMONO_OK;
+  if (curvature) LM_CUDA(cudaMemcpyAsync(curvature, s->d_curv, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  if (src_index) LM_CUDA(cudaMemcpyAsync(src_index, s->d_src, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  LM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return LMONO_OK;
+}

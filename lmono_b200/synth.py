@@ -296,7 +296,7 @@ def raycast_sweep(world: World, q, t, n_scans=64, n_az=1875, rng=None, noise=0.0
         best = np.where(hit & (th < best), th, best)
     ok = np.isfinite(best) & (best < max_range) & (best > min_range)
     rr = best + rng.normal(0, noise, best.shape)
-    pts = d_s * rr[:, None]
+    pts = d_s * np.where(ok, rr, 0.0)[:, None]
     out = np.zeros((int(ok.sum()), 4), np.float32)
     out[:, :3] = pts[ok]
     out[:, 3] = 0.5

@@ -144,6 +144,9 @@ int lmono_cpu_scan_register(const float* xyz_in, int n_in, int stride_floats,
                             int32_t* labels, float* curvature, int32_t* src_index,
                             o_scan_report* rep);
 
+/* 0: double atan/sqrt (GCC 5.4-era headers, default), 1: float overloads (scanRegistration.cpp:166) */
+void lmono_cpu_scan_set_trig_mode(int mode);
+
 /* ---- laserOdometry (Aloam/src/laserOdometry.cpp) ------------------------- */
 typedef struct o_odom o_odom;
 typedef struct {

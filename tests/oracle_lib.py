@@ -245,3 +245,64 @@ class Mapper:
                                   C.byref(rep), _p(fr) if fr is not None else None, nfull)
         q, t = w.as_np()
         return q, t, rep, fr
+
+
+def scan_register(raw, n_scans=64, minimum_range=5.0, voxel_order_mode=0, sort_mode=0, trig_mode=0):
+    """raw: float32 [n, >=3].  Returns dict with full/sharp/less_sharp/flat/less_flat clouds,
+    labels, curvature, src_index, report."""
+    raw = np.ascontiguousarray(raw, np.float32)
+    n = len(raw)
+    L = lib()
+    L.lmono_cpu_scan_set_trig_mode(trig_mode)
+    cap = max(n, 1)
+    bufs = {k: np.zeros((cap, 4), np.float32) for k in ("full", "sharp", "less_sharp", "flat", "less_flat")}
+    labels = np.zeros(cap, np.int32)
+    curv = np.zeros(cap, np.float32)
+    src = np.zeros(cap, np.int32)
+    rep = ScanReport()
+    rc = L.lmono_cpu_scan_register(_p(raw), n, raw.shape[1], n_scans, C.c_float(minimum_range), voxel_order_mode, sort_mode,
+                                   _p(bufs["full"]), _p(bufs["sharp"]), _p(bufs["less_sharp"]), _p(bufs["flat"]),
+                                   _p(bufs["less_flat"]), _p(labels), _p(curv), _p(src), C.byref(rep))
+    assert rc == 0
+    out = {"full": bufs["full"][: rep.n_kept], "sharp": bufs["sharp"][: rep.n_sharp],
+           "less_sharp": bufs["less_sharp"][: rep.n_less_sharp], "flat": bufs["flat"][: rep.n_flat],
+           "less_flat": bufs["less_flat"][: rep.n_less_flat], "labels": labels[: rep.n_kept],
+           "curvature": curv[: rep.n_kept], "src_index": src[: rep.n_kept], "report": rep}
+    return out
+
+
+class Odometry:
+    """Oracle laserOdometry state (Aloam/src/laserOdometry.cpp globals)."""
+
+    def __init__(self):
+        self.L = lib()
+        self.h = C.c_void_p(self.L.lmono_cpu_odom_create())
+
+    def close(self):
+        if self.h:
+            self.L.lmono_cpu_odom_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def step(self, sharp, less_sharp, flat, less_flat):
+        a, b, c, d = (_f32(x).reshape(-1, 4) for x in (sharp, less_sharp, flat, less_flat))
+        lc = Pose()
+        wc = Pose()
+        rep = OdomReport()
+        self.L.lmono_cpu_odom_step(self.h, _p(a), len(a), _p(b), len(b), _p(c), len(c), _p(d), len(d),
+                                   C.byref(lc), C.byref(wc), C.byref(rep))
+        return lc.as_np(), wc.as_np(), rep
+
+
+def odom_associate(sharp, flat, corner_last, surf_last, q, t):
+    a, c, cl, sl = (_f32(x).reshape(-1, 4) for x in (sharp, flat, corner_last, surf_last))
+    ci = np.zeros((len(a), 2), np.int32)
+    pi = np.zeros((len(c), 3), np.int32)
+    pose = Pose.make(q, t)
+    lib().lmono_cpu_odom_associate(_p(a), len(a), _p(c), len(c), _p(cl), len(cl), _p(sl), len(sl), C.byref(pose), _p(ci), _p(pi))
+    return ci, pi
