@@ -215,9 +215,14 @@ int lmono_odom_reset(lmono_ctx* ctx);
 int lmono_odom_debug(lmono_ctx* ctx, int32_t pass, int32_t* corner_idx, int32_t n_sharp, int32_t* plane_idx, int32_t n_flat);
 
 /* ------------------------------------------------------------------ L6: colour projection */
-/* Replaces mono_lidar_mapping/src/map_builder/Map_Builder.cc:224-245 (raster), :336-403
- * (depthFill) and :275-322 (lift + world transform). */
-int lmono_project_color(lmono_ctx* ctx, lmono_cloud_view pts_cam, const uint8_t* bgr, int32_t step_bytes,
+/* Replaces mono_lidar_mapping/src/map_build_node.cc:216-225 (LiDAR -> camera extrinsic transform,
+ * when T_cam_lidar is given: the node's 3x4 row-major `transformation` = [rlc^T | -rlc^T tlc]),
+ * src/map_builder/Map_Builder.cc:224-245 (8-bit inverse-depth raster, last point wins), :336-403
+ * (depthFill) and :275-322 (per-pixel lift, colour fetch, world transform by Q_T).
+ * Outputs: depth_raw / depth_filled are width*height bytes; the clouds are packed xyz floats and
+ * rgb bytes in row-major pixel order (the order of rgb_cloud / w_cloud in the reference). */
+int lmono_project_color(lmono_ctx* ctx, lmono_cloud_view pts, const double* T_cam_lidar /*[12] or NULL*/,
+                        const uint8_t* bgr, int32_t step_bytes,
                         const lmono_pinhole* cam, const lmono_pose* Q_T,
                         uint8_t* depth_raw /*may be NULL*/, uint8_t* depth_filled /*may be NULL*/,
                         float* cloud_cam_xyz /*may be NULL*/, float* cloud_world_xyz, uint8_t* cloud_rgb,

@@ -352,6 +352,31 @@ class Context:
                                           pi.ctypes.data_as(C.c_void_p), n_flat), "odom_debug")
         return ci[:n_sharp], pi[:n_flat]
 
+    # -- colour projection (mono_lidar_mapping map builder)
+    def project_color(self, pts, bgr, cam: "Pinhole", q, t, T_cam_lidar=None, want_cam=True):
+        """pts: float32 [n,3|4] (camera frame, or LiDAR frame with T_cam_lidar = 3x4); bgr: uint8 [H,W,3]."""
+        p = np.ascontiguousarray(pts, np.float32)
+        img = np.ascontiguousarray(bgr, np.uint8)
+        H, W = img.shape[:2]
+        assert (W, H) == (cam.width, cam.height)
+        npix = W * H
+        raw = np.zeros((H, W), np.uint8)
+        fill = np.zeros((H, W), np.uint8)
+        cc = np.zeros((npix, 3), np.float32)
+        cw = np.zeros((npix, 3), np.float32)
+        rgb = np.zeros((npix, 3), np.uint8)
+        n = C.c_int32(0)
+        pose = Pose.make(q, t)
+        T = None
+        if T_cam_lidar is not None:
+            T = np.ascontiguousarray(T_cam_lidar, np.float64).reshape(12)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = self.L.lmono_project_color(self._h, view_of(p), vp(T) if T is not None else None, vp(img), C.c_int32(img.strides[0]),
+                                        C.byref(cam), C.byref(pose), vp(raw), vp(fill), vp(cc) if want_cam else None,
+                                        vp(cw), vp(rgb), npix, C.byref(n))
+        self._chk(rc, "project_color")
+        return {"depth_raw": raw, "depth": fill, "cloud_cam": cc[: n.value], "cloud_world": cw[: n.value], "rgb": rgb[: n.value]}
+
     def voxel_grid(self, pts, leaf):
         p = _xyzi(pts)
         buf, out = _out(len(p))

@@ -22,7 +22,7 @@ struct Cand { float d; int idx; int ref; };   // ref: element index into the map
 
 __device__ __forceinline__ bool cand_less(float d1, int i1, float d2, int i2) { return d1 < d2 || (d1 == d2 && i1 < i2); }
 
-// ---- Eigen 3.3 SelfAdjointEigenSolver<Matrix3d> (same operation order as oracle/linalg.c)
+// ---- Eigen 3.3 SelfAdjointEigenSolver<Matrix3d> (same operation order as the test oracle, so the fit gates are reproducible)
 __device__ __forceinline__ void d_make_givens(double p, double q, double* c, double* s) {
   if (q == 0.0) { *c = p < 0.0 ? -1.0 : 1.0; *s = 0.0; }
   else if (p == 0.0) { *c = 0.0; *s = q < 0.0 ? 1.0 : -1.0; }
@@ -133,7 +133,7 @@ __device__ void d_eigh3(const double* A, double* w, double* Q) {
   for (int i = 0; i < 3; ++i) w[i] = diag[i] * scale;
 }
 
-// ---- Eigen 3.3 ColPivHouseholderQR<Matrix<double,5,3>>::solve (same order as oracle/linalg.c)
+// ---- Eigen 3.3 ColPivHouseholderQR<Matrix<double,5,3>>::solve (same operation order as the test oracle)
 __device__ __forceinline__ void d_make_householder(double* v, int len, int stride, double* tau, double* beta) {
   double tailSqNorm = 0.0;
   for (int i = 1; i < len; ++i) tailSqNorm += v[i * stride] * v[i * stride];

@@ -6,6 +6,7 @@
 int lm_map_configure_kernels(lmono_ctx* ctx);
 void lm_scan_free(lmono_ctx* ctx);
 void lm_odom_free(lmono_ctx* ctx);
+void lm_color_free(lmono_ctx* ctx);
 
 extern "C" void lmono_default_params(lmono_params* p) {
   memset(p, 0, sizeof(*p));
@@ -122,6 +123,7 @@ extern "C" void lmono_destroy(lmono_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   lm_scan_free(ctx);
   lm_odom_free(ctx);
+  lm_color_free(ctx);
   lm_map_free(ctx);
   cudaFree(ctx->d_state); cudaFreeHost(ctx->h_state); cudaFree(ctx->d_lm); cudaFree(ctx->d_slot_valid_rank); cudaFree(ctx->d_partials);
   for (int i = 0; i < 3; ++i) cudaFree(ctx->d_raw[i]);

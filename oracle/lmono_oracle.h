@@ -177,6 +177,8 @@ typedef struct {
 /* pts_cam: camera-frame XYZ (after map_build_node.cc:216-225), bgr: h x w x 3.
  * depth_raw: raster before depthFill, depth_u8: after. rgb_cloud: 8 floats per point
  * (x,y,z,pad,r,g,b,pad as floats) in camera frame and world frame. */
+/* D1: pcl::transformPointCloud with a double 3x4 (row-major) matrix, float store */
+int lmono_cpu_transform_cloud(const float* in, int n, int stride_floats, const double T[12], float* out_xyz);
 int lmono_cpu_project_raster(const float* pts_cam, int n, int stride_floats, const o_camera* cam,
                              uint8_t* depth_raw);
 int lmono_cpu_depth_fill(const uint8_t* depth_raw, const o_camera* cam, uint8_t* depth_out);

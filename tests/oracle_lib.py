@@ -306,3 +306,44 @@ def odom_associate(sharp, flat, corner_last, surf_last, q, t):
     pose = Pose.make(q, t)
     lib().lmono_cpu_odom_associate(_p(a), len(a), _p(c), len(c), _p(cl), len(cl), _p(sl), len(sl), C.byref(pose), _p(ci), _p(pi))
     return ci, pi
+
+
+def make_camera(fx=718.856, fy=718.856, cx=607.1928, cy=185.2157, k1=0.0, k2=0.0, p1=0.0, p2=0.0,
+                width=1241, height=376, kernel_type=0, kernel_size=5, blur_type=0):
+    """mono_lidar_mapping/config/kitti00_cam.yaml + kitti_map_config_00.yaml defaults."""
+    return Camera(fx, fy, cx, cy, k1, k2, p1, p2, width, height, kernel_type, kernel_size, blur_type)
+
+
+def transform_cloud(pts, T):
+    pts = _f32(pts)
+    T = np.ascontiguousarray(T, np.float64).reshape(12)
+    out = np.zeros((len(pts), 3), np.float32)
+    lib().lmono_cpu_transform_cloud(_p(pts), len(pts), pts.shape[1], _p(T), _p(out))
+    return out
+
+
+def project_raster(pts_cam, cam):
+    pts = _f32(pts_cam)
+    out = np.zeros((cam.height, cam.width), np.uint8)
+    lib().lmono_cpu_project_raster(_p(pts), len(pts), pts.shape[1], C.byref(cam), _p(out))
+    return out
+
+
+def depth_fill(depth_raw, cam):
+    d = np.ascontiguousarray(depth_raw, np.uint8)
+    out = np.zeros_like(d)
+    lib().lmono_cpu_depth_fill(_p(d), C.byref(cam), _p(out))
+    return out
+
+
+def lift_cloud(depth, bgr, cam, q, t):
+    d = np.ascontiguousarray(depth, np.uint8)
+    img = np.ascontiguousarray(bgr, np.uint8)
+    cap = cam.width * cam.height
+    cc = np.zeros((cap, 3), np.float32)
+    cw = np.zeros((cap, 3), np.float32)
+    rgb = np.zeros((cap, 3), np.uint8)
+    n = C.c_int(0)
+    pose = Pose.make(q, t)
+    lib().lmono_cpu_lift_cloud(_p(d), _p(img), C.byref(cam), C.byref(pose), _p(cc), _p(cw), _p(rgb), cap, C.byref(n))
+    return cc[: n.value], cw[: n.value], rgb[: n.value]
