@@ -36,7 +36,10 @@ def _check(got, ref, n_scans):
         assert got[k].shape == ref[k].shape, (k, got[k].shape, ref[k].shape)
         assert np.array_equal(got[k][:, :3].view(np.uint32), ref[k][:, :3].view(np.uint32)), k
         if len(ref[k]):
-            assert np.abs(got[k][:, 3] - ref[k][:, 3]).max() <= 4e-6, k
+            # less_flat intensities are VoxelGrid means of per-point intensities that already differ by
+            # up to dI (atan2f); the fp32 sum / n adds at most a couple of ulp of the ring id magnitude
+            tol = 4e-6 + (2.0 * np.spacing(np.abs(ref[k][:, 3])) if k == "less_flat" else 0.0)
+            assert np.all(np.abs(got[k][:, 3] - ref[k][:, 3]) <= tol), k
     return dI
 
 
