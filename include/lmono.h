@@ -167,6 +167,32 @@ int lmono_map_export(lmono_ctx* ctx, int which, int scope, lmono_cloud_out* out)
 int lmono_map_import(lmono_ctx* ctx, int which, lmono_cloud_view pts_world);
 int lmono_map_clear(lmono_ctx* ctx);
 
+/* ------------------------------------------------------------------ cube-sharded global map (multi-GPU)
+ * Extension beyond the reference (its map is one process's 21x21x11 cube array, laserMapping.cpp:74-104):
+ * the cubes are distributed over `nranks` contexts (one per GPU) by a hash of the absolute cube
+ * coordinate, each stored with a 1 m halo (accepted neighbours have d2 < 1.0, laserMapping.cpp:584,652,
+ * so every query's 5-NN is local to the rank owning the query's cube).  One registration =
+ *   lmono_shard_begin -> [all-reduce ws] -> lmono_shard_gate ->
+ *   2 x { lmono_shard_associate, lmono_shard_lm_begin, 5 x { lmono_shard_lm_eval -> [all-reduce ws] ->
+ *         lmono_shard_lm_control } } -> lmono_shard_end -> lmono_map_collect
+ * where [all-reduce ws] is a SUM all-reduce of the 35 doubles of d_workspace over the ranks, issued by
+ * the host on the ctx stream (torch.distributed / ncclAllReduce; lmono_b200/shard.py is the host side).
+ * d_workspace: caller-owned device memory, >= 35 doubles: [0..20] J^T J upper triangle, [21..26] J^T r,
+ * [27] cost, [28..29] corner / surf factor counts, [30..31] owned map points in the window, pad.
+ * lmono_map_import and the insertion at the end of every registration keep only the points this
+ * rank owns or holds as halo.  All calls are enqueue-only. */
+int lmono_shard_configure(lmono_ctx* ctx, int32_t rank, int32_t nranks, void* d_workspace);
+int lmono_shard_begin(lmono_ctx* ctx, const void* d_corner_xyzi, int32_t n_corner, const void* d_surf_xyzi, int32_t n_surf,
+                      const lmono_pose* wodom_curr);
+int lmono_shard_gate(lmono_ctx* ctx);
+int lmono_shard_associate(lmono_ctx* ctx);
+int lmono_shard_lm_begin(lmono_ctx* ctx, int32_t solve_index);
+int lmono_shard_lm_eval(lmono_ctx* ctx, int32_t solve_index);
+int lmono_shard_lm_control(lmono_ctx* ctx, int32_t solve_index);
+int lmono_shard_end(lmono_ctx* ctx);
+/* owner rank of the cube containing a world point / of an absolute cube coordinate (cube 0 is centred on the origin) */
+int32_t lmono_shard_owner_of_cube(int32_t gi, int32_t gj, int32_t gk, int32_t nranks);
+
 /* ------------------------------------------------------------------ test / bench hooks */
 /* Positions the cube window for a pose translation (laserMapping.cpp:312-539). */
 int lmono_map_prepare_window(lmono_ctx* ctx, const double t_w_curr[3]);

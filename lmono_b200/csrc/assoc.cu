@@ -362,10 +362,16 @@ __global__ void __launch_bounds__(256) k_associate(LmMapState* __restrict__ st, 
   const LmMapType& M = ty == 0 ? M0 : M1;
   const float4 ori = ty == 0 ? stack0[qi] : stack1[qi];
   const float4 sel = d_associate(st->q_w_curr, st->t_w_curr, ori);
+  LmFactor* f = (ty == 0 ? fac0 : fac1) + qi;
+  if (st->shard_n > 1) {   // cube-sharded map: a query belongs to the rank that owns the cube it falls in
+    if (lm_cube_owner(d_cube_coord((double)sel.x, 0), d_cube_coord((double)sel.y, 0), d_cube_coord((double)sel.z, 0), st->shard_n) != st->shard_rank) {
+      if (sub == 0) f->kind = -1;
+      return;
+    }
+  }
   float d[KNN_K]; int idx[KNN_K], ref[KNN_K];
   d_knn5_group(M, st, slot_valid_rank, ty, sel.x, sel.y, sel.z, sub, gmask, d, idx, ref);
   if (sub != 0) return;
-  LmFactor* f = (ty == 0 ? fac0 : fac1) + qi;
   if (!(ref[KNN_K - 1] >= 0 && d[KNN_K - 1] < 1.0f)) { f->kind = -1; return; }
   float4 nb[KNN_K];
 #pragma unroll

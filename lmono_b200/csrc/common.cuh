@@ -84,6 +84,9 @@ struct LmMapState {
   double q_wmap_wodom[4], t_wmap_wodom[3];
   double q_wodom_curr[4], t_wodom_curr[3];
   double q_w_curr[4], t_w_curr[3];
+  // cube-sharded global map (shard.cu): shard_n <= 1 means "not sharded, every cube is mine"
+  int32_t shard_rank, shard_n;
+  int32_t shard_owned_n[2];              // points of OWNED window cubes (summed over ranks for the :554 gate)
 };
 
 struct LmMapType {           // one per map (0 corner, 1 surf); device pointers, passed by value
@@ -149,6 +152,8 @@ struct lmono_ctx {
   int max_feat, max_sweep;
   int sm_count;
   bool step_pending;
+  // cube-sharded mode (shard.cu): caller-owned device workspace the host all-reduces between kernels
+  double* d_shard_ws; int shard_nc, shard_ns;
   // later stages (scan registration / odometry / colour) attach their own state
   void* scan_state; void* odom_state; void* color_state;
   // optional per-phase CUDA-event profiler (bench.py roofline numbers)
@@ -240,6 +245,46 @@ __device__ __forceinline__ int d_cube_cell(float4 p, const int* g) {
   int cz = ((int)floorf(p.z) >> 1) - (25 * g[2] - 13);
   if ((unsigned)cx >= (unsigned)LM_CELLS_AXIS || (unsigned)cy >= (unsigned)LM_CELLS_AXIS || (unsigned)cz >= (unsigned)LM_CELLS_AXIS) return -1;
   return cx + LM_CELLS_AXIS * (cy + LM_CELLS_AXIS * cz);
+}
+
+// ---- cube sharding: owner rank of an absolute cube coordinate, and the rule that decides
+// whether this rank stores a map point: it owns the point's cube, or the point's VoxelGrid voxel
+// reaches into the LM_SHARD_HALO shell around an adjacent cube it owns.  Accepted neighbours satisfy
+// fp32 d2 < 1.0 (laserMapping.cpp:584,652), so a 1 m shell (taken voxel-complete, with slack) makes
+// every owned query's 5-NN local and exact; voxel-complete halos make the per-cube VoxelGrid
+// refilter of a halo copy reproduce the owner's centroids bit for bit.
+#define LM_SHARD_HALO 1.25
+__host__ __device__ __forceinline__ int lm_cube_owner(int gi, int gj, int gk, int nranks) {
+  if (nranks <= 1) return 0;
+  uint32_t h = ((uint32_t)gi * 73856093u) ^ ((uint32_t)gj * 19349663u) ^ ((uint32_t)gk * 83492791u);
+  h ^= h >> 15; h *= 0x2c1b3c6du; h ^= h >> 12;
+  return (int)(h % (uint32_t)nranks);
+}
+__device__ __forceinline__ bool d_shard_keep(float4 p, float leaf, float inv_leaf, int rank, int nranks) {
+  if (nranks <= 1) return true;
+  const float pc[3] = { p.x, p.y, p.z };
+  int g[3]; bool lo[3], hi[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    g[a] = d_cube_coord((double)pc[a], 0);
+    const double v = (double)floorf(__fmul_rn(pc[a], inv_leaf));
+    const double vlo = v * (double)leaf, vhi = (v + 1.0) * (double)leaf;
+    lo[a] = vlo < (50.0 * g[a] - 25.0) + LM_SHARD_HALO;
+    hi[a] = vhi > (50.0 * g[a] + 25.0) - LM_SHARD_HALO;
+  }
+  if (lm_cube_owner(g[0], g[1], g[2], nranks) == rank) return true;
+  for (int dz = -1; dz <= 1; ++dz) {
+    if ((dz < 0 && !lo[2]) || (dz > 0 && !hi[2])) continue;
+    for (int dy = -1; dy <= 1; ++dy) {
+      if ((dy < 0 && !lo[1]) || (dy > 0 && !hi[1])) continue;
+      for (int dx = -1; dx <= 1; ++dx) {
+        if ((dx < 0 && !lo[0]) || (dx > 0 && !hi[0])) continue;
+        if ((dx | dy | dz) == 0) continue;
+        if (lm_cube_owner(g[0] + dx, g[1] + dy, g[2] + dz, nranks) == rank) return true;
+      }
+    }
+  }
+  return false;
 }
 
 // block-wide exclusive scan of one int per thread (blockDim.x <= 1024, multiple of 32).
@@ -371,6 +416,10 @@ int lm_knn5_device(lmono_ctx* ctx, int which, const float4* d_q, int n, int32_t*
 int lm_solve_enqueue(lmono_ctx* ctx, int solve_index, int n_max_corner, int n_max_surf, int max_iter);
 int lm_normal_eq_enqueue(lmono_ctx* ctx, int n_max_corner, int n_max_surf);
 int lm_solve_problem(lmono_ctx* ctx, const LmProblem& P, int n_max, int max_iter, int write_back);
+// sharded LM pieces: begin / partial evaluation into the workspace / controller from the reduced workspace
+int lm_shard_lm_begin(lmono_ctx* ctx, int solve_index);
+int lm_shard_lm_eval(lmono_ctx* ctx, int solve_index);
+int lm_shard_lm_control(lmono_ctx* ctx, int solve_index);
 // ctx.cu helpers
 int lm_upload_cloud(lmono_ctx* ctx, lmono_cloud_view v, uint8_t* d_raw, float4* d_out, int32_t* d_n /*may be null*/);
 int lm_download_cloud(lmono_ctx* ctx, const float4* d_src, int n, lmono_cloud_out* out);

@@ -39,6 +39,7 @@ __global__ void k_state_init(LmMapState* st) {
   st->valid_num = 0; st->from_map_n[0] = st->from_map_n[1] = 0; st->optimize = 0;
   st->stack_n[0] = st->stack_n[1] = 0; st->raw_n[0] = st->raw_n[1] = 0;
   st->frame_count = 0; st->fault = 0;
+  st->shard_rank = 0; st->shard_n = 1; st->shard_owned_n[0] = st->shard_owned_n[1] = 0;
   for (int k = 0; k < 4; ++k) { st->q_wmap_wodom[k] = k == 3; st->q_wodom_curr[k] = k == 3; st->q_w_curr[k] = k == 3; }
   for (int k = 0; k < 3; ++k) { st->t_wmap_wodom[k] = 0; st->t_wodom_curr[k] = 0; st->t_w_curr[k] = 0; }
 }

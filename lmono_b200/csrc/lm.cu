@@ -210,7 +210,7 @@ __device__ void d_lm_control(LmLmState* lm, const double* red /*28*/, const LmPr
 }
 
 // ---- kernels -----------------------------------------------------------------------------
-__global__ void k_lm_begin(LmLmState* __restrict__ lm, LmProblem P, int max_iter) {
+__global__ void k_lm_begin(LmLmState* __restrict__ lm, LmProblem P, int max_iter, int sharded) {
   // counts the factors of this association pass (corner_num / surf_num, laserMapping.cpp:620,685;
   // corner_correspondence / plane_correspondence, laserOdometry.cpp:382,480) and arms the controller
   __shared__ int ws[33];
@@ -233,7 +233,7 @@ __global__ void k_lm_begin(LmLmState* __restrict__ lm, LmProblem P, int max_iter
     lm->radius = 1e4; lm->decrease_factor = 2.0; lm->reuse_diagonal = 0; lm->num_invalid = 0;
     lm->iteration = 0; lm->num_successful = 0; lm->termination = 0; lm->phase = 0; lm->max_iter = max_iter;
     lm->nfactors = t0 + t1; lm->ticket = 0; lm->initial_cost = 0.0; lm->cost = 0.0;
-    lm->done = (!gate || (t0 + t1) == 0) ? 1 : 0;
+    lm->done = (!gate || (!sharded && (t0 + t1) == 0)) ? 1 : 0;   // sharded: the global count decides (k_lm_control)
     if (lm->done && P.summary) {   // Ceres: no residual blocks -> parameters untouched
       LmSolveSummary* S = P.summary;
       S->iterations = 0; S->num_successful = 0; S->termination = 6; S->num_factors = 0; S->initial_cost = 0.0; S->final_cost = 0.0;
@@ -241,8 +241,12 @@ __global__ void k_lm_begin(LmLmState* __restrict__ lm, LmProblem P, int max_iter
   }
 }
 
+// shard_ws != NULL: cube-sharded map -- the last block publishes this rank's 28 partial sums (and its factor
+// counts) to the workspace instead of running the controller; the host all-reduces the workspace over the
+// ranks (NCCL) and k_lm_control advances the (replicated, deterministic) controller from the reduced sums.
 __global__ void __launch_bounds__(EVAL_THREADS) k_lm_eval(LmLmState* __restrict__ lm, LmProblem P,
-                                                          double* __restrict__ partials, int write_back) {
+                                                          double* __restrict__ partials, int write_back,
+                                                          double* __restrict__ shard_ws) {
   if (lm->done) return;
   __shared__ double sred[EVAL_THREADS / 32][NRED];
   __shared__ bool s_last;
@@ -292,10 +296,39 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_lm_eval(LmLmState* __restrict_
     fin[threadIdx.x] = v;
   }
   __syncthreads();
+  if (shard_ws) {
+    if (threadIdx.x < NRED) shard_ws[threadIdx.x] = fin[threadIdx.x];
+    if (threadIdx.x == 0) {
+      lm->ticket = 0;
+      shard_ws[28] = P.count0 ? (double)*P.count0 : 0.0;
+      shard_ws[29] = P.count1 ? (double)*P.count1 : 0.0;
+    }
+    return;
+  }
   if (threadIdx.x == 0) {
     lm->ticket = 0;
     d_lm_control(lm, fin, P, write_back);
   }
+}
+
+// controller step from the all-reduced workspace (sharded map): identical on every rank
+__global__ void k_lm_control(LmLmState* __restrict__ lm, LmProblem P, const double* __restrict__ ws, int write_back) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (lm->done) return;
+  if (lm->phase == 0) {          // global factor counts replace the local ones of k_lm_begin
+    const int c0 = (int)ws[28], c1 = (int)ws[29];
+    if (P.count0) *P.count0 = c0;
+    if (P.count1) *P.count1 = c1;
+    lm->nfactors = c0 + c1;
+    if (c0 + c1 == 0) {
+      lm->done = 1;
+      if (P.summary) { LmSolveSummary* S = P.summary; S->iterations = 0; S->num_successful = 0; S->termination = 6; S->num_factors = 0; S->initial_cost = 0.0; S->final_cost = 0.0; }
+      return;
+    }
+  }
+  double red[NRED];
+  for (int k = 0; k < NRED; ++k) red[k] = ws[k];
+  d_lm_control(lm, red, P, write_back);
 }
 
 // test hook output: H (36), g (6), cost of the factors at q_w_curr/t_w_curr
@@ -315,11 +348,11 @@ static int eval_blocks(lmono_ctx* ctx, int n) {
 }
 
 int lm_solve_problem(lmono_ctx* ctx, const LmProblem& P, int n_max, int max_iter, int write_back) {
-  k_lm_begin<<<1, 1024, 0, ctx->stream>>>(ctx->d_lm, P, max_iter);
+  k_lm_begin<<<1, 1024, 0, ctx->stream>>>(ctx->d_lm, P, max_iter, 0);
   LM_LAUNCH_CHECK();
   const int blocks = eval_blocks(ctx, n_max);
   for (int it = 0; it <= max_iter; ++it) {
-    k_lm_eval<<<blocks, EVAL_THREADS, 0, ctx->stream>>>(ctx->d_lm, P, ctx->d_partials, write_back);
+    k_lm_eval<<<blocks, EVAL_THREADS, 0, ctx->stream>>>(ctx->d_lm, P, ctx->d_partials, write_back, nullptr);
     LM_LAUNCH_CHECK();
   }
   return LMONO_OK;
@@ -346,6 +379,24 @@ int lm_normal_eq_enqueue(lmono_ctx* ctx, int n_max_corner, int n_max_surf) {
   int rc = lm_solve_problem(ctx, map_problem(ctx, 0), n_max_corner + n_max_surf, 0, 0);
   if (rc) return rc;
   k_lm_export_normal_eq<<<1, 32, 0, ctx->stream>>>(ctx->d_lm, ctx->d_partials + 32 * 1024);
+  LM_LAUNCH_CHECK();
+  return LMONO_OK;
+}
+
+// ---- cube-sharded map: one LM evaluation = eval (local partials) -> all-reduce on the host side -> control
+int lm_shard_lm_begin(lmono_ctx* ctx, int solve_index) {
+  k_lm_begin<<<1, 1024, 0, ctx->stream>>>(ctx->d_lm, map_problem(ctx, solve_index), 4, 1);
+  LM_LAUNCH_CHECK();
+  return LMONO_OK;
+}
+int lm_shard_lm_eval(lmono_ctx* ctx, int solve_index) {
+  const int blocks = eval_blocks(ctx, ctx->shard_nc + ctx->shard_ns);
+  k_lm_eval<<<blocks, EVAL_THREADS, 0, ctx->stream>>>(ctx->d_lm, map_problem(ctx, solve_index), ctx->d_partials, 1, ctx->d_shard_ws);
+  LM_LAUNCH_CHECK();
+  return LMONO_OK;
+}
+int lm_shard_lm_control(lmono_ctx* ctx, int solve_index) {
+  k_lm_control<<<1, 32, 0, ctx->stream>>>(ctx->d_lm, map_problem(ctx, solve_index), ctx->d_shard_ws, 1);
   LM_LAUNCH_CHECK();
   return LMONO_OK;
 }

@@ -67,6 +67,92 @@ static int enqueue_step(lmono_ctx* ctx, const float4* d_corner, int nc, const fl
   return LMONO_OK;
 }
 
+// ------------------------------------------------------------------ cube-sharded global map
+// The map's 50 m cubes are distributed over the ranks by lm_cube_owner (each stored with a voxel-complete
+// 1 m halo, d_shard_keep); queries and the pose are replicated; a query is associated on the rank that
+// owns the cube it falls in, so the 5-NN is local and exact.  One registration is the same kernel
+// sequence as enqueue_step, cut at the points where the ranks must exchange data: the host all-reduces
+// the 35-double workspace (caller-owned device memory, e.g. a torch tensor -> torch.distributed / NCCL
+// over NVLink) after lmono_shard_begin and after every lmono_shard_lm_eval.
+// workspace layout: [0..20] J^T J upper triangle, [21..26] J^T r, [27] cost, [28] corner factors,
+// [29] surf factors, [30] owned corner map points in the window, [31] owned surf map points, [32..34] pad.
+__global__ void k_shard_config(LmMapState* st, int rank, int n) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { st->shard_rank = rank; st->shard_n = n; }
+}
+__global__ void k_shard_publish_counts(const LmMapState* __restrict__ st, double* __restrict__ ws) {
+  if (threadIdx.x < 35) ws[threadIdx.x] = 0.0;
+  __syncwarp();
+  if (threadIdx.x == 0) { ws[30] = (double)st->shard_owned_n[0]; ws[31] = (double)st->shard_owned_n[1]; }
+}
+__global__ void k_shard_gate(LmMapState* __restrict__ st, const double* __restrict__ ws) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // laserMapping.cpp:554 on the GLOBAL window content (halo copies are not counted twice)
+  st->from_map_n[0] = (int)ws[30]; st->from_map_n[1] = (int)ws[31];
+  st->optimize = (ws[30] > 10.0 && ws[31] > 50.0) ? 1 : 0;
+}
+
+extern "C" int lmono_shard_configure(lmono_ctx* ctx, int32_t rank, int32_t nranks, void* d_workspace) {
+  if (!ctx || nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !d_workspace)) return LMONO_E_ARG;
+  ctx->d_shard_ws = (double*)d_workspace;
+  k_shard_config<<<1, 32, 0, ctx->stream>>>(ctx->d_state, rank, nranks);
+  LM_LAUNCH_CHECK();
+  return LMONO_OK;
+}
+
+extern "C" int32_t lmono_shard_owner_of_cube(int32_t gi, int32_t gj, int32_t gk, int32_t nranks) { return lm_cube_owner(gi, gj, gk, nranks); }
+
+extern "C" int lmono_shard_begin(lmono_ctx* ctx, const void* d_corner, int32_t nc, const void* d_surf, int32_t ns,
+                                 const lmono_pose* wodom_curr) {
+  if (!ctx || !wodom_curr || !ctx->d_shard_ws) return LMONO_E_ARG;
+  if (nc < 0 || ns < 0 || nc > ctx->max_feat || ns > ctx->max_feat) return LMONO_E_CAPACITY;
+  int rc;
+  ctx->shard_nc = nc; ctx->shard_ns = ns;
+  LM_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  k_set_counts<<<1, 32, 0, ctx->stream>>>(ctx->d_state, nc, ns);
+  LM_LAUNCH_CHECK();
+  if ((rc = lm_map_begin_step(ctx, wodom_curr, nullptr))) return rc;
+  if ((rc = lm_map_index_build(ctx))) return rc;
+  if ((rc = lm_voxel_grid_device(ctx, (const float4*)d_corner, &ctx->d_state->raw_n[0], nc, ctx->map[0].leaf, ctx->d_stack[0], &ctx->d_state->stack_n[0]))) return rc;
+  if ((rc = lm_voxel_grid_device(ctx, (const float4*)d_surf, &ctx->d_state->raw_n[1], ns, ctx->map[1].leaf, ctx->d_stack[1], &ctx->d_state->stack_n[1]))) return rc;
+  k_shard_publish_counts<<<1, 64, 0, ctx->stream>>>(ctx->d_state, ctx->d_shard_ws);
+  LM_LAUNCH_CHECK();
+  return LMONO_OK;
+}
+
+extern "C" int lmono_shard_gate(lmono_ctx* ctx) {
+  if (!ctx || !ctx->d_shard_ws) return LMONO_E_ARG;
+  k_shard_gate<<<1, 32, 0, ctx->stream>>>(ctx->d_state, ctx->d_shard_ws);
+  LM_LAUNCH_CHECK();
+  return LMONO_OK;
+}
+
+extern "C" int lmono_shard_associate(lmono_ctx* ctx) {
+  if (!ctx || !ctx->d_shard_ws) return LMONO_E_ARG;
+  return lm_map_associate(ctx, ctx->shard_nc, ctx->shard_ns);
+}
+extern "C" int lmono_shard_lm_begin(lmono_ctx* ctx, int32_t solve_index) {
+  if (!ctx || !ctx->d_shard_ws || solve_index < 0 || solve_index > 1) return LMONO_E_ARG;
+  return lm_shard_lm_begin(ctx, solve_index);
+}
+extern "C" int lmono_shard_lm_eval(lmono_ctx* ctx, int32_t solve_index) {
+  if (!ctx || !ctx->d_shard_ws || solve_index < 0 || solve_index > 1) return LMONO_E_ARG;
+  return lm_shard_lm_eval(ctx, solve_index);
+}
+extern "C" int lmono_shard_lm_control(lmono_ctx* ctx, int32_t solve_index) {
+  if (!ctx || !ctx->d_shard_ws || solve_index < 0 || solve_index > 1) return LMONO_E_ARG;
+  return lm_shard_lm_control(ctx, solve_index);
+}
+extern "C" int lmono_shard_end(lmono_ctx* ctx) {
+  if (!ctx || !ctx->d_shard_ws) return LMONO_E_ARG;
+  k_transform_update<<<1, 32, 0, ctx->stream>>>(ctx->d_state);
+  LM_LAUNCH_CHECK();
+  int rc = lm_map_insert_and_refilter(ctx, ctx->shard_nc, ctx->shard_ns);
+  if (rc) return rc;
+  LM_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->step_pending = true;
+  return LMONO_OK;
+}
+
 static void fill_report(const LmMapState* h, lmono_map_report* r, float ms) {
   memset(r, 0, sizeof(*r));
   r->corner_from_map = h->from_map_n[0]; r->surf_from_map = h->from_map_n[1];

@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(256) k_begin_step(LmMapState* __restrict__ st,
                                                     int use_override, double ox, double oy, double oz) {
   __shared__ unsigned clear_mask[3];
   __shared__ int s_n[2][LM_MAX_VALID + 3];
+  __shared__ int s_own[LM_MAX_VALID + 3];
   __shared__ int s_all;
   if (threadIdx.x == 0) {
     for (int k = 0; k < 4; ++k) st->q_wodom_curr[k] = odom.q[k];
@@ -133,8 +134,10 @@ __global__ void __launch_bounds__(256) k_begin_step(LmMapState* __restrict__ st,
     for (int i = st->center[0] - 2; i <= st->center[0] + 2; i++)
       for (int j = st->center[1] - 2; j <= st->center[1] + 2; j++)
         for (int k = st->center[2] - 1; k <= st->center[2] + 1; k++)
-          if (i >= 0 && i < LM_GW && j >= 0 && j < LM_GH && k >= 0 && k < LM_GD)
+          if (i >= 0 && i < LM_GW && j >= 0 && j < LM_GH && k >= 0 && k < LM_GD) {
+            s_own[vn] = lm_cube_owner(i - st->cen[0], j - st->cen[1], k - st->cen[2], st->shard_n) == st->shard_rank;
             st->valid_slot[vn++] = d_phys_slot(i - st->cen[0], j - st->cen[1], k - st->cen[2]);
+          }
     st->valid_num = vn;
     st->corner_num[0] = st->corner_num[1] = st->surf_num[0] = st->surf_num[1] = 0;
     for (int s = 0; s < 2; ++s) { st->solve[s].iterations = 0; st->solve[s].num_successful = 0; st->solve[s].termination = 6; st->solve[s].num_factors = 0; st->solve[s].initial_cost = 0.0; st->solve[s].final_cost = 0.0; }
@@ -165,6 +168,9 @@ __global__ void __launch_bounds__(256) k_begin_step(LmMapState* __restrict__ st,
     for (int r = 0; r < vn; ++r) { st->valid_off[threadIdx.x][r] = acc; acc += s_n[threadIdx.x][r]; }
     st->valid_off[threadIdx.x][vn] = acc;
     st->from_map_n[threadIdx.x] = acc;
+    int own = 0;
+    for (int r = 0; r < vn; ++r) if (s_own[r]) own += s_n[threadIdx.x][r];
+    st->shard_owned_n[threadIdx.x] = own;
   }
   __syncthreads();
   if (threadIdx.x == 0) st->optimize = (st->from_map_n[0] > 10 && st->from_map_n[1] > 50) ? 1 : 0;   // :554
@@ -249,7 +255,7 @@ int lm_map_index_build(lmono_ctx* ctx) {
 __global__ void __launch_bounds__(256) k_insert_prepare(LmMapState* __restrict__ st, const float4* __restrict__ stack0,
                                                         const float4* __restrict__ stack1, float4* __restrict__ world0,
                                                         float4* __restrict__ world1, unsigned long long* __restrict__ comp,
-                                                        int32_t* __restrict__ n_ins) {
+                                                        int32_t* __restrict__ n_ins, float leaf0, float inv_leaf0, float leaf1, float inv_leaf1) {
   const int n0 = st->stack_n[0], n1 = st->stack_n[1];
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e == 0) *n_ins = n0 + n1;
@@ -262,7 +268,8 @@ __global__ void __launch_bounds__(256) k_insert_prepare(LmMapState* __restrict__
   int cJ = d_cube_coord((double)pw.y, st->cen[1]);
   int cK = d_cube_coord((double)pw.z, st->cen[2]);
   uint32_t ps = 8191u;
-  if (cI >= 0 && cI < LM_GW && cJ >= 0 && cJ < LM_GH && cK >= 0 && cK < LM_GD)
+  if (cI >= 0 && cI < LM_GW && cJ >= 0 && cJ < LM_GH && cK >= 0 && cK < LM_GD &&
+      d_shard_keep(pw, ty == 0 ? leaf0 : leaf1, ty == 0 ? inv_leaf0 : inv_leaf1, st->shard_rank, st->shard_n))
     ps = (uint32_t)d_phys_slot(cI - st->cen[0], cJ - st->cen[1], cK - st->cen[2]);
   comp[e] = ((unsigned long long)(((uint32_t)ty << 13) | ps) << 32) | (uint32_t)i;
 }
@@ -448,7 +455,8 @@ int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf)
     int32_t* slot_len = ctx->d_tmp_i32 + 16;         // [2*LM_NSLOT]
     const int blocks = lm_div_up(n_max, 256);
     k_insert_prepare<<<blocks, 256, 0, ctx->stream>>>(ctx->d_state, ctx->d_stack[0], ctx->d_stack[1], ctx->d_world[0],
-                                                      ctx->d_world[1], ctx->d_sort_a, n_ins);
+                                                      ctx->d_world[1], ctx->d_sort_a, n_ins, ctx->map[0].leaf, ctx->map[0].inv_leaf,
+                                                      ctx->map[1].leaf, ctx->map[1].inv_leaf);
     LM_LAUNCH_CHECK();
     int rc = lm_sort_u64(ctx, ctx->d_sort_a, ctx->d_sort_b, ctx->d_sort_c, n_ins, n_max);
     if (rc) return rc;
@@ -553,7 +561,7 @@ __global__ void __launch_bounds__(256) k_import_keys(LmMapState* __restrict__ st
   float4 p = pts[i];
   int cI = d_cube_coord((double)p.x, st->cen[0]), cJ = d_cube_coord((double)p.y, st->cen[1]), cK = d_cube_coord((double)p.z, st->cen[2]);
   unsigned long long ps = 8191ULL; uint32_t vkey = 0;
-  if (cI >= 0 && cI < LM_GW && cJ >= 0 && cJ < LM_GH && cK >= 0 && cK < LM_GD) {
+  if (cI >= 0 && cI < LM_GW && cJ >= 0 && cJ < LM_GH && cK >= 0 && cK < LM_GD && d_shard_keep(p, M.leaf, M.inv_leaf, st->shard_rank, st->shard_n)) {
     int g3[3] = { cI - st->cen[0], cJ - st->cen[1], cK - st->cen[2] };
     ps = (unsigned long long)d_phys_slot(g3[0], g3[1], g3[2]);
     vkey = d_cube_voxel_key(p, M.inv_leaf, g3);
