@@ -196,7 +196,11 @@ def run_ours(args):
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
 
     _, cm, sm, sweeps = make_workload(rank)
-    stream = torch.cuda.current_stream()
+    # one real (non-default) stream for torch, NCCL, the CUDA events and the ctx: a NULL handle would make the
+    # ctx create its own stream, and events recorded on torch's stream would not bracket its kernels
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = api.Context(device=local, stream=stream.cuda_stream)
     ctx.map_import(0, cm)
     ctx.map_import(1, sm)

@@ -211,6 +211,11 @@ int lmono_map_normal_eq(lmono_ctx* ctx, lmono_cloud_view corner_stack, lmono_clo
 /* pcl::VoxelGrid<PointXYZI> as configured by the reference (canonical index-order sums). */
 int lmono_voxel_grid(lmono_ctx* ctx, lmono_cloud_view in, float leaf, lmono_cloud_out* out);
 
+/* Latency study hook: %globaltimer stamps (ns) written by instrumented kernels (slot map in DESIGN.md):
+ * [0..63] the LM solve kernel of the most recent solve: 0 start, 1 armed, then per evaluation e (8 slots from
+ * 8 + 8 e): factors evaluated, warp+block reduced, cluster exchanged, controller done. */
+int lmono_debug_stamps(lmono_ctx* ctx, uint64_t* out /*[n]*/, int32_t n /*<= 256*/);
+
 /* Per-phase device timing (CUDA events on the ctx stream) of lmono_map_step, used by bench.py
  * for the roofline numbers.  Phases: 0 window shift, 1 cell-index build, 2 VoxelGrid of the
  * features, 3 association (5-NN + fits), 4 LM solve, 5 insertion, 6 cube refilter, 7 misc. */

@@ -119,6 +119,11 @@ enum { LM_PROF_WINDOW = 0, LM_PROF_INDEX, LM_PROF_VOXEL, LM_PROF_ASSOC, LM_PROF_
 constexpr int LM_PROF_MAX_EVENTS = 2048;
 
 // ---------------------------------------------------------------- host ctx
+// One captured CUDA graph per (input pointers, launch-grid capacity bucket) of a laserMapping step.
+struct LmGraphEntry { const void* dc; const void* ds; int nc_cap, ns_cap; cudaGraphExec_t exec; int n_launch; };
+constexpr int LM_MAX_GRAPHS = 64;
+constexpr int LM_GRAPH_BUCKET = 2048;     // launch grids are sized for counts rounded up to this
+
 struct lmono_ctx {
   int device;
   lmono_params prm;
@@ -154,6 +159,10 @@ struct lmono_ctx {
   bool step_pending;
   // cube-sharded mode (shard.cu): caller-owned device workspace the host all-reduces between kernels
   double* d_shard_ws; int shard_nc, shard_ns;
+  // CUDA-graph replay of the laserMapping step (mapping.cu); LMONO_NO_GRAPH=1 disables it
+  bool graphs_on; int n_graphs; LmGraphEntry graphs[LM_MAX_GRAPHS];
+  // in-kernel %globaltimer stamps (ns) for latency studies (lmono_debug_stamps); 256 slots, written by thread 0 of CTA 0
+  unsigned long long* d_stamps;
   // later stages (scan registration / odometry / colour) attach their own state
   void* scan_state; void* odom_state; void* color_state;
   // optional per-phase CUDA-event profiler (bench.py roofline numbers)
@@ -181,6 +190,8 @@ static inline int lm_div_up(int a, int b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long d_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define LM_STAMP(buf, slot) do { if ((buf) != nullptr && threadIdx.x == 0 && blockIdx.x == 0) (buf)[(slot)] = d_globaltimer(); } while (0)
 __device__ __forceinline__ int d_pmod(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
 __device__ __forceinline__ int d_floordiv(int a, int b) { int q = a / b; if ((a % b != 0) && ((a < 0) != (b < 0))) --q; return q; }
 
@@ -406,6 +417,7 @@ int lm_voxel_grid_device(lmono_ctx* ctx, const float4* in, const int32_t* n_dev,
 // mapstore.cu
 int lm_map_alloc(lmono_ctx* ctx);
 void lm_map_free(lmono_ctx* ctx);
+// pose source: wodom_curr (by value), else t_override (test hooks), else the q/t_wodom_curr already in the state
 int lm_map_begin_step(lmono_ctx* ctx, const lmono_pose* wodom_curr, const double* t_override);
 int lm_map_index_build(lmono_ctx* ctx);
 int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf);

@@ -67,6 +67,7 @@ extern "C" int lmono_create(int device, const lmono_params* params, void* stream
   if (P.mapping_line_resolution < 0.06f || P.mapping_plane_resolution < 0.06f) { free(ctx); return LMONO_E_ARG; }
   if (P.scan_line != 16 && P.scan_line != 32 && P.scan_line != 64) { free(ctx); return LMONO_E_ARG; }
   ctx->device = device;
+  { const char* ng = getenv("LMONO_NO_GRAPH"); ctx->graphs_on = !(ng && ng[0] == '1'); }
   ctx->max_feat = P.max_feature_points; ctx->max_sweep = P.max_sweep_points;
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) { fprintf(stderr, "[lmono_b200] cudaSetDevice(%d): %s\n", device, cudaGetErrorString(e)); free(ctx); return LMONO_E_CUDA; }
@@ -85,6 +86,8 @@ extern "C" int lmono_create(int device, const lmono_params* params, void* stream
   LM_CUDA(cudaMalloc((void**)&ctx->d_slot_valid_rank, sizeof(int32_t) * LM_NSLOT));
   LM_CUDA(cudaMemsetAsync(ctx->d_slot_valid_rank, 0xFF, sizeof(int32_t) * LM_NSLOT, ctx->stream));
   LM_CUDA(cudaMalloc((void**)&ctx->d_partials, sizeof(double) * 32 * (1024 + 8)));
+  LM_CUDA(cudaMalloc((void**)&ctx->d_stamps, sizeof(unsigned long long) * 256));
+  LM_CUDA(cudaMemsetAsync(ctx->d_stamps, 0, sizeof(unsigned long long) * 256, ctx->stream));
   const size_t nf = (size_t)ctx->max_feat;
   ctx->raw_bytes = (size_t)ctx->max_sweep * 32;
   for (int i = 0; i < 3; ++i) LM_CUDA(cudaMalloc((void**)&ctx->d_raw[i], ctx->raw_bytes));
@@ -122,11 +125,12 @@ extern "C" void lmono_destroy(lmono_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < ctx->n_graphs; ++i) cudaGraphExecDestroy(ctx->graphs[i].exec);
   lm_scan_free(ctx);
   lm_odom_free(ctx);
   lm_color_free(ctx);
   lm_map_free(ctx);
-  cudaFree(ctx->d_state); cudaFreeHost(ctx->h_state); cudaFree(ctx->d_lm); cudaFree(ctx->d_slot_valid_rank); cudaFree(ctx->d_partials);
+  cudaFree(ctx->d_state); cudaFreeHost(ctx->h_state); cudaFree(ctx->d_lm); cudaFree(ctx->d_slot_valid_rank); cudaFree(ctx->d_partials); cudaFree(ctx->d_stamps);
   for (int i = 0; i < 3; ++i) cudaFree(ctx->d_raw[i]);
   for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_in[i]); cudaFree(ctx->d_stack[i]); cudaFree(ctx->d_world[i]); cudaFree(ctx->d_fac[i]); }
   cudaFree(ctx->d_sort_a); cudaFree(ctx->d_sort_b); cudaFree(ctx->d_sort_c); cudaFree(ctx->d_blockcnt); cudaFree(ctx->d_tmp_i32);
@@ -138,6 +142,13 @@ extern "C" void lmono_destroy(lmono_ctx* ctx) {
 
 extern "C" int lmono_sync(lmono_ctx* ctx) {
   if (!ctx) return LMONO_E_ARG;
+  LM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return LMONO_OK;
+}
+
+extern "C" int lmono_debug_stamps(lmono_ctx* ctx, uint64_t* out, int32_t n) {
+  if (!ctx || !out || n < 0 || n > 256) return LMONO_E_ARG;
+  LM_CUDA(cudaMemcpyAsync(out, ctx->d_stamps, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   LM_CUDA(cudaStreamSynchronize(ctx->stream));
   return LMONO_OK;
 }

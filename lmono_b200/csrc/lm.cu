@@ -13,6 +13,9 @@
 // function / parameter / gradient tolerances -- no host round trip inside a solve.
 #include "common.cuh"
 #include <float.h>
+#include <stdlib.h>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 constexpr int NRED = 28;          // 21 + 6 + 1
 constexpr int EVAL_THREADS = 256;
@@ -21,15 +24,17 @@ __device__ __forceinline__ void d_cross(const double* a, const double* b, double
   o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
 }
 
-// accumulate one residual row: J (6), r, into the 27 sums
+// accumulate one residual row: J (6), r, into the 27 sums.  Explicit fp64 FMAs (the TU is built with
+// -fmad=false for the fp32 parity paths): the sums are only compared at 1e-5 relative (north_star), and
+// the fused form halves the fp64 issue slots of the hottest loop.
 __device__ __forceinline__ void d_acc_row(const double* J, double r, double* acc) {
   int k = 0;
 #pragma unroll
   for (int a = 0; a < 6; ++a)
 #pragma unroll
-    for (int b = a; b < 6; ++b) acc[k++] += J[a] * J[b];
+    for (int b = a; b < 6; ++b) { acc[k] = fma(J[a], J[b], acc[k]); ++k; }
 #pragma unroll
-  for (int a = 0; a < 6; ++a) acc[21 + a] += J[a] * r;
+  for (int a = 0; a < 6; ++a) acc[21 + a] = fma(J[a], r, acc[21 + a]);
 }
 
 __device__ __forceinline__ void d_eval_factor(const LmFactor& f, const double* q, const double* t, double* acc) {
@@ -86,62 +91,107 @@ __device__ void d_plus(const double* x, const double* d, double* out) {
   } else { out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; out[3] = x[3]; }
   out[4] = x[4] + d[3]; out[5] = x[5] + d[4]; out[6] = x[6] + d[5];
 }
-__device__ __forceinline__ double d_norm7(const double* v) { double s = 0; for (int i = 0; i < 7; ++i) s += v[i] * v[i]; return sqrt(s); }
-__device__ __forceinline__ double d_Hat(const double* H, int a, int b) {   // upper-triangular packed access
-  if (a > b) { int t = a; a = b; b = t; }
-  return H[a * 6 - (a * (a - 1)) / 2 + (b - a)];
+__device__ __forceinline__ double d_norm7(const double* v) {
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) s += v[i] * v[i];
+  return sqrt(s);
 }
+// upper-triangular packed index of (a, b), a <= b; constant-folds when a, b are unrolled loop indices
+__device__ __forceinline__ constexpr int d_tri(int a, int b) { return a <= b ? a * 6 - (a * (a - 1)) / 2 + (b - a) : b * 6 - (b * (b - 1)) / 2 + (a - b); }
+__device__ __forceinline__ double d_Hat(const double* H, int a, int b) { return H[d_tri(a, b)]; }
 __device__ double d_gradient_max_norm(const double* x, const double* g) {
   double ng[6], xp[7];
+#pragma unroll
   for (int i = 0; i < 6; ++i) ng[i] = -g[i];
   d_plus(x, ng, xp);
   double m = 0.0;
+#pragma unroll
   for (int i = 0; i < 7; ++i) { double a = fabs(x[i] - xp[i]); if (a > m) m = a; }
   return m;
 }
 
-// solve (A) y = b for SPD 6x6 A via Cholesky; returns 0 on success
-__device__ int d_chol6(double A[6][6], const double* b, double* y) {
-  double L[6][6];
+// solve (A) y = b for SPD 6x6 A (upper-triangular packed) via Cholesky; returns 0 on success.
+// Fully unrolled: every index is a compile-time constant, so the factor lives in registers.
+__device__ __forceinline__ int d_chol6(const double* A /*21*/, const double* b, double* y) {
+  double L[21];       // lower factor, packed like the upper triangle of its transpose: L(i,j), j <= i, at d_tri(j, i)
+  int bad = 0;
+#pragma unroll
   for (int i = 0; i < 6; ++i) {
+#pragma unroll
     for (int j = 0; j <= i; ++j) {
-      double s = A[i][j];
-      for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
-      if (i == j) { if (!(s > 0.0)) return 1; L[i][i] = sqrt(s); }
-      else L[i][j] = s / L[j][j];
+      double s = A[d_tri(j, i)];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s -= L[d_tri(k, i)] * L[d_tri(k, j)];
+      if (i == j) { if (!(s > 0.0)) bad = 1; L[d_tri(i, i)] = sqrt(s); }
+      else L[d_tri(j, i)] = s / L[d_tri(j, j)];
     }
   }
+  if (bad) return 1;
   double z[6];
-  for (int i = 0; i < 6; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= L[i][k] * z[k]; z[i] = s / L[i][i]; }
-  for (int i = 5; i >= 0; --i) { double s = z[i]; for (int k = i + 1; k < 6; ++k) s -= L[k][i] * y[k]; y[i] = s / L[i][i]; }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double s = b[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) s -= L[d_tri(k, i)] * z[k];
+    z[i] = s / L[d_tri(i, i)];
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    double s = z[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) s -= L[d_tri(i, k)] * y[k];
+    y[i] = s / L[d_tri(i, i)];
+  }
   return 0;
 }
 
 // Computes the next trust-region step from (H, g) at x; on success sets lm->cand and returns 1.
 // Returns 0 if the solve terminated (lm->done set).
 __device__ int d_compute_step(LmLmState* lm) {
+  double Hs[21], gs[6], sc[6];
+#pragma unroll
+  for (int a = 0; a < 6; ++a) sc[a] = lm->scaling[a];
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+    gs[a] = lm->g[a] * sc[a];
+#pragma unroll
+    for (int b = a; b < 6; ++b) Hs[d_tri(a, b)] = lm->H[d_tri(a, b)] * sc[a] * sc[b];
+  }
   for (;;) {
     if (lm->iteration >= lm->max_iter) { lm->termination = 0; lm->done = 1; return 0; }
     if (!(lm->radius > 1e-32)) { lm->termination = 4; lm->done = 1; return 0; }
     lm->iteration++;
-    double Hs[6][6], gs[6];
-    for (int a = 0; a < 6; ++a) { gs[a] = lm->g[a] * lm->scaling[a]; for (int b = 0; b < 6; ++b) Hs[a][b] = d_Hat(lm->H, a, b) * lm->scaling[a] * lm->scaling[b]; }
-    if (!lm->reuse_diagonal)
-      for (int j = 0; j < 6; ++j) { double s = Hs[j][j]; lm->diagonal[j] = s < 1e-6 ? 1e-6 : (s > 1e32 ? 1e32 : s); }
-    double A[6][6];
-    for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) A[a][b] = Hs[a][b];
-    for (int j = 0; j < 6; ++j) A[j][j] += lm->diagonal[j] / lm->radius;     // D^2 = diagonal / radius
+    if (!lm->reuse_diagonal) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) { double s = Hs[d_tri(j, j)]; lm->diagonal[j] = s < 1e-6 ? 1e-6 : (s > 1e32 ? 1e32 : s); }
+    }
+    double A[21];
+#pragma unroll
+    for (int k = 0; k < 21; ++k) A[k] = Hs[k];
+    const double radius = lm->radius;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) A[d_tri(j, j)] += lm->diagonal[j] / radius;     // D^2 = diagonal / radius
     double y[6];
     int fail = d_chol6(A, gs, y);
+#pragma unroll
     for (int j = 0; j < 6; ++j) if (!isfinite(y[j])) fail = 1;
     lm->reuse_diagonal = 1;
     int valid = 0;
     double step[6];
     if (!fail) {
+#pragma unroll
       for (int j = 0; j < 6; ++j) step[j] = -y[j];
       // model_cost_change = -(J s)^T (r + J s / 2) = -(s^T g + s^T H s / 2)
       double sg = 0.0, sHs = 0.0;
-      for (int a = 0; a < 6; ++a) { sg += step[a] * gs[a]; double row = 0.0; for (int b = 0; b < 6; ++b) row += Hs[a][b] * step[b]; sHs += step[a] * row; }
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        sg += step[a] * gs[a];
+        double row = 0.0;
+#pragma unroll
+        for (int b = 0; b < 6; ++b) row += Hs[d_tri(a, b)] * step[b];
+        sHs += step[a] * row;
+      }
       lm->model_cost_change = -(sg + 0.5 * sHs);
       valid = lm->model_cost_change > 0.0;
     }
@@ -152,7 +202,8 @@ __device__ int d_compute_step(LmLmState* lm) {
     }
     lm->num_invalid = 0;
     double delta[6];
-    for (int j = 0; j < 6; ++j) delta[j] = step[j] * lm->scaling[j];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) delta[j] = step[j] * sc[j];
     d_plus(lm->x, delta, lm->cand);
     return 1;
   }
@@ -163,9 +214,9 @@ __device__ void d_lm_control(LmLmState* lm, const double* red /*28*/, const LmPr
   if (lm->phase == 0) {
     // IterationZero
     lm->cost = cost_e; lm->initial_cost = cost_e;
-    for (int k = 0; k < 21; ++k) lm->H[k] = red[k];
-    for (int k = 0; k < 6; ++k) lm->g[k] = red[21 + k];
-    for (int j = 0; j < 6; ++j) lm->scaling[j] = 1.0 / (1.0 + sqrt(d_Hat(lm->H, j, j)));
+    _Pragma("unroll") for (int k = 0; k < 21; ++k) lm->H[k] = red[k];
+    _Pragma("unroll") for (int k = 0; k < 6; ++k) lm->g[k] = red[21 + k];
+    _Pragma("unroll") for (int j = 0; j < 6; ++j) lm->scaling[j] = 1.0 / (1.0 + sqrt(d_Hat(lm->H, j, j)));
     lm->x_norm = d_norm7(lm->x);
     lm->phase = 1;
     if (d_gradient_max_norm(lm->x, lm->g) <= 1e-10) { lm->termination = 1; lm->done = 1; }
@@ -182,11 +233,11 @@ __device__ void d_lm_control(LmLmState* lm, const double* red /*28*/, const LmPr
       else {
         const double rd = cost_change / lm->model_cost_change;
         if (rd > 1e-3) {
-          for (int i = 0; i < 7; ++i) lm->x[i] = lm->cand[i];
+          _Pragma("unroll") for (int i = 0; i < 7; ++i) lm->x[i] = lm->cand[i];
           lm->x_norm = d_norm7(lm->x);
           lm->cost = cost_e;
-          for (int k = 0; k < 21; ++k) lm->H[k] = red[k];
-          for (int k = 0; k < 6; ++k) lm->g[k] = red[21 + k];
+          _Pragma("unroll") for (int k = 0; k < 21; ++k) lm->H[k] = red[k];
+          _Pragma("unroll") for (int k = 0; k < 6; ++k) lm->g[k] = red[21 + k];
           const double tq = 2.0 * rd - 1.0;
           double den = 1.0 - tq * tq * tq; if (den < 1.0 / 3.0) den = 1.0 / 3.0;
           lm->radius = lm->radius / den; if (lm->radius > 1e16) lm->radius = 1e16;
@@ -201,8 +252,8 @@ __device__ void d_lm_control(LmLmState* lm, const double* red /*28*/, const LmPr
     }
   }
   if (lm->done && write_back) {
-    for (int k = 0; k < 4; ++k) P.pose_q[k] = lm->x[k];
-    for (int k = 0; k < 3; ++k) P.pose_t[k] = lm->x[4 + k];
+    _Pragma("unroll") for (int k = 0; k < 4; ++k) P.pose_q[k] = lm->x[k];
+    _Pragma("unroll") for (int k = 0; k < 3; ++k) P.pose_t[k] = lm->x[4 + k];
     LmSolveSummary* S = P.summary;
     S->iterations = lm->iteration; S->num_successful = lm->num_successful; S->termination = lm->termination;
     S->num_factors = lm->nfactors; S->initial_cost = lm->initial_cost; S->final_cost = lm->cost;
@@ -331,6 +382,131 @@ __global__ void k_lm_control(LmLmState* __restrict__ lm, LmProblem P, const doub
   d_lm_control(lm, red, P, write_back);
 }
 
+// ---- whole solve in ONE launch: a thread-block cluster replaces the launch-per-evaluation loop --------
+// The factors of one registration (~16 k x 64 B) are a few microseconds of fp64 work; what the
+// launch-per-evaluation version paid for was 6 launches per solve, each with a grid-wide "last block"
+// tail and a single-thread controller behind it.  Here LMC_CLUSTER CTAs of one cluster (co-scheduled on
+// one GPC) keep everything on chip: every thread evaluates its factors (grid-stride over the cluster),
+// warps reduce the 30-vector {J^T J (21), J^T r (6), cost, corner count, surf count} with a halving
+// butterfly (31 double shuffles instead of 150), each CTA pushes its block sums into EVERY CTA's shared
+// memory through distributed shared memory, one cluster barrier, and every CTA advances its own copy
+// of the deterministic trust-region controller (identical inputs -> identical state), so the next
+// evaluation starts without another exchange.  Sums are taken in a fixed order: run-to-run bit-stable.
+constexpr int LMC_THREADS = 256;
+constexpr int LMC_CLUSTER = 16;   // max cluster size (non-portable, opt-in); 8 is used where 16 cannot be scheduled
+
+// after the call lane L holds the warp-wide sum of element L (L < 32) in v[0]
+__device__ __forceinline__ void d_warp_transpose_reduce32(double (&v)[32], int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const double send = upper ? v[i] : v[i + half];
+      const double keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(LMC_THREADS, 1)
+k_lm_solve_cluster(LmLmState* __restrict__ lm_g, LmProblem P, int max_iter, int write_back, unsigned long long* __restrict__ stamps) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank();
+  const int csize = (int)cluster.num_blocks();
+  __shared__ double s_part[LMC_THREADS / 32][32];
+  __shared__ double s_all[2][LMC_CLUSTER][32];      // [parity][source CTA][element], written remotely
+  __shared__ double s_fin[32];
+  __shared__ LmLmState s_lm;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  LM_STAMP(stamps, 0);
+  const int n0 = *P.n0, n1 = *P.n1;
+  const LmFactor* __restrict__ fac0 = P.fac0; const LmFactor* __restrict__ fac1 = P.fac1;
+  if (threadIdx.x == 0) {
+    LmLmState* lm = &s_lm;
+    const int gate = P.gate ? *P.gate : 1;
+    for (int k = 0; k < 4; ++k) lm->x[k] = P.pose_q[k];
+    for (int k = 0; k < 3; ++k) lm->x[4 + k] = P.pose_t[k];
+    for (int k = 0; k < 7; ++k) lm->cand[k] = lm->x[k];
+    for (int k = 0; k < 21; ++k) lm->H[k] = 0.0;
+    for (int k = 0; k < 6; ++k) { lm->g[k] = 0.0; lm->scaling[k] = 1.0; lm->diagonal[k] = 0.0; }
+    lm->x_norm = 0.0; lm->model_cost_change = 0.0;
+    lm->radius = 1e4; lm->decrease_factor = 2.0; lm->reuse_diagonal = 0; lm->num_invalid = 0;
+    lm->iteration = 0; lm->num_successful = 0; lm->termination = 0; lm->phase = 0; lm->max_iter = max_iter;
+    lm->nfactors = 0; lm->ticket = 0; lm->initial_cost = 0.0; lm->cost = 0.0; lm->pad = 0; lm->pad2 = 0;
+    lm->done = gate ? 0 : 1;
+    if (!gate && crank == 0) {
+      if (P.count0) *P.count0 = 0;
+      if (P.count1) *P.count1 = 0;
+      if (P.summary) { LmSolveSummary* S = P.summary; S->iterations = 0; S->num_successful = 0; S->termination = 6; S->num_factors = 0; S->initial_cost = 0.0; S->final_cost = 0.0; }
+    }
+  }
+  __syncthreads();
+  const int wb = (write_back && crank == 0) ? 1 : 0;
+  LM_STAMP(stamps, 1);
+  for (int it = 0; it <= max_iter; ++it) {
+    if (s_lm.done) break;                       // replicated state: uniform over the whole cluster
+    const double* xe = s_lm.phase == 0 ? s_lm.x : s_lm.cand;
+    const double q[4] = { xe[0], xe[1], xe[2], xe[3] };
+    const double t[3] = { xe[4], xe[5], xe[6] };
+    double acc[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc[k] = 0.0;
+    {   // grid-stride over the cluster, next factor's 64 B in flight while the current one is evaluated
+      const int stride = csize * LMC_THREADS, nf = n0 + n1;
+      int i = crank * LMC_THREADS + threadIdx.x;
+      LmFactor f;
+      if (i < nf) f = i < n0 ? fac0[i] : fac1[i - n0];
+      while (i < nf) {
+        const int inext = i + stride;
+        LmFactor fn;
+        if (inext < nf) fn = inext < n0 ? fac0[inext] : fac1[inext - n0];
+        if (f.kind >= 0) { if (i < n0) acc[28] += 1.0; else acc[29] += 1.0; }
+        d_eval_factor(f, q, t, acc);
+        f = fn; i = inext;
+      }
+    }
+    LM_STAMP(stamps, 8 + 8 * it);
+    d_warp_transpose_reduce32(acc, lane);
+    s_part[wid][lane] = acc[0];
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < LMC_THREADS / 32; ++w) v += s_part[w][threadIdx.x];
+      double* mine = &s_all[it & 1][crank][threadIdx.x];
+      for (int r = 0; r < csize; ++r) *cluster.map_shared_rank(mine, r) = v;
+    }
+    LM_STAMP(stamps, 9 + 8 * it);
+    cluster.sync();
+    LM_STAMP(stamps, 10 + 8 * it);
+    if (threadIdx.x < 32) {
+      double v = 0.0;
+      for (int r = 0; r < csize; ++r) v += s_all[it & 1][r][threadIdx.x];     // fixed order
+      s_fin[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      LmLmState* lm = &s_lm;
+      if (lm->phase == 0) {
+        const int c0 = (int)s_fin[28], c1 = (int)s_fin[29];
+        lm->nfactors = c0 + c1;
+        if (crank == 0) { if (P.count0) *P.count0 = c0; if (P.count1) *P.count1 = c1; }
+        if (c0 + c1 == 0) {                     // Ceres: no residual blocks -> parameters untouched
+          lm->done = 1;
+          if (wb && P.summary) { LmSolveSummary* S = P.summary; S->iterations = 0; S->num_successful = 0; S->termination = 6; S->num_factors = 0; S->initial_cost = 0.0; S->final_cost = 0.0; }
+        }
+      }
+      if (!lm->done) d_lm_control(lm, s_fin, P, wb);
+    }
+    LM_STAMP(stamps, 11 + 8 * it);
+    __syncthreads();
+  }
+  LM_STAMP(stamps, 2);
+  if (crank == 0 && threadIdx.x == 0) *lm_g = s_lm;     // test hooks read H, g, cost from here
+  cluster.sync();                                        // nobody leaves while its shared memory may still be written
+}
+
 // test hook output: H (36), g (6), cost of the factors at q_w_curr/t_w_curr
 __global__ void k_lm_export_normal_eq(const LmLmState* __restrict__ lm, double* __restrict__ out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -338,6 +514,35 @@ __global__ void k_lm_export_normal_eq(const LmLmState* __restrict__ lm, double* 
   for (int a = 0; a < 6; ++a) out[36 + a] = lm->g[a];
   out[42] = lm->cost;
   out[43] = (double)lm->nfactors;
+}
+
+// LMONO_LM_MULTILAUNCH=1 keeps the launch-per-evaluation path (the one the sharded mode builds on) for A/B runs
+static bool lm_use_launch_per_eval() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LMONO_LM_MULTILAUNCH"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
+// largest cluster the device schedules for the solve kernel: 16 (opt-in, non-portable) if possible, else 8
+static int lm_cluster_size(lmono_ctx* ctx) {
+  static int cached[64] = { 0 };
+  const int d = ctx->device & 63;
+  if (cached[d]) return cached[d];
+  int best = 8;
+  if (cudaFuncSetAttribute(k_lm_solve_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(LMC_CLUSTER); cfg.blockDim = dim3(LMC_THREADS);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = LMC_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k_lm_solve_cluster, &cfg) == cudaSuccess && n >= 1) best = LMC_CLUSTER;
+  }
+  cudaGetLastError();
+  const char* e = getenv("LMONO_LM_CLUSTER");
+  if (e && atoi(e) >= 1 && atoi(e) <= best) best = atoi(e);
+  cached[d] = best;
+  return best;
 }
 
 static int eval_blocks(lmono_ctx* ctx, int n) {
@@ -348,6 +553,18 @@ static int eval_blocks(lmono_ctx* ctx, int n) {
 }
 
 int lm_solve_problem(lmono_ctx* ctx, const LmProblem& P, int n_max, int max_iter, int write_back) {
+  if (!lm_use_launch_per_eval()) {
+    const int cs = lm_cluster_size(ctx);
+    if (cs < 0) return LMONO_E_CUDA;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cs); cfg.blockDim = dim3(LMC_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    LM_CUDA(cudaLaunchKernelEx(&cfg, k_lm_solve_cluster, ctx->d_lm, P, max_iter, write_back, ctx->d_stamps));
+    LM_LAUNCH_CHECK();
+    return LMONO_OK;
+  }
   k_lm_begin<<<1, 1024, 0, ctx->stream>>>(ctx->d_lm, P, max_iter, 0);
   LM_LAUNCH_CHECK();
   const int blocks = eval_blocks(ctx, n_max);

@@ -33,15 +33,21 @@ __global__ void k_set_counts(LmMapState* st, int n0, int n1) {
   if (threadIdx.x == 0 && blockIdx.x == 0) { st->raw_n[0] = n0; st->raw_n[1] = n1; }
 }
 
-// enqueue the whole step on inputs that are already float4 XYZI in device memory
-static int enqueue_step(lmono_ctx* ctx, const float4* d_corner, int nc, const float4* d_surf, int ns, const lmono_pose* wodom_curr) {
-  if (nc < 0 || ns < 0 || nc > ctx->max_feat || ns > ctx->max_feat) return LMONO_E_CAPACITY;
+// every per-step scalar (feature counts, odometry pose) enters through this one launch, so the rest of
+// the step is a parameter-free kernel sequence that can be replayed as a CUDA graph
+struct StepArgs { double q[4]; double t[3]; int n0, n1; };
+__global__ void k_step_args(LmMapState* st, StepArgs a) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  st->raw_n[0] = a.n0; st->raw_n[1] = a.n1;
+  for (int k = 0; k < 4; ++k) st->q_wodom_curr[k] = a.q[k];
+  for (int k = 0; k < 3; ++k) st->t_wodom_curr[k] = a.t[k];
+}
+
+// the step body: nc / ns only size the launch grids (every kernel reads the real counts from the state)
+static int enqueue_body(lmono_ctx* ctx, const float4* d_corner, int nc, const float4* d_surf, int ns) {
   int rc;
-  LM_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-  k_set_counts<<<1, 32, 0, ctx->stream>>>(ctx->d_state, nc, ns);
-  LM_LAUNCH_CHECK();
   lm_prof_begin(ctx, LM_PROF_WINDOW);
-  if ((rc = lm_map_begin_step(ctx, wodom_curr, nullptr))) return rc;        // :309-539
+  if ((rc = lm_map_begin_step(ctx, nullptr, nullptr))) return rc;           // :309-539
   lm_prof_end(ctx);
   lm_prof_begin(ctx, LM_PROF_INDEX);
   if ((rc = lm_map_index_build(ctx))) return rc;                            // replaces kdtree setInputCloud :558-559
@@ -62,6 +68,59 @@ static int enqueue_step(lmono_ctx* ctx, const float4* d_corner, int nc, const fl
   k_transform_update<<<1, 32, 0, ctx->stream>>>(ctx->d_state);              // :734
   LM_LAUNCH_CHECK();
   if ((rc = lm_map_insert_and_refilter(ctx, nc, ns))) return rc;            // :737-801
+  return LMONO_OK;
+}
+
+static int bucket_up(int n, int cap) {
+  if (n <= 0) return 0;
+  long long b = ((long long)n + LM_GRAPH_BUCKET - 1) / LM_GRAPH_BUCKET * LM_GRAPH_BUCKET;
+  return (int)(b > cap ? cap : b);
+}
+
+// enqueue the whole step on inputs that are already float4 XYZI in device memory
+static int enqueue_step(lmono_ctx* ctx, const float4* d_corner, int nc, const float4* d_surf, int ns, const lmono_pose* wodom_curr) {
+  if (nc < 0 || ns < 0 || nc > ctx->max_feat || ns > ctx->max_feat) return LMONO_E_CAPACITY;
+  int rc;
+  LM_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  StepArgs a;
+  for (int k = 0; k < 4; ++k) a.q[k] = wodom_curr->q[k];
+  for (int k = 0; k < 3; ++k) a.t[k] = wodom_curr->t[k];
+  a.n0 = nc; a.n1 = ns;
+  k_step_args<<<1, 32, 0, ctx->stream>>>(ctx->d_state, a);
+  LM_LAUNCH_CHECK();
+  const int nc_cap = bucket_up(nc, ctx->max_feat), ns_cap = bucket_up(ns, ctx->max_feat);
+  if (!ctx->graphs_on || ctx->prof_on) {
+    if ((rc = enqueue_body(ctx, d_corner, nc_cap, d_surf, ns_cap))) return rc;
+  } else {
+    LmGraphEntry* g = nullptr;
+    for (int i = 0; i < ctx->n_graphs; ++i) {
+      LmGraphEntry& e = ctx->graphs[i];
+      if (e.dc == d_corner && e.ds == d_surf && e.nc_cap == nc_cap && e.ns_cap == ns_cap) { g = &e; break; }
+    }
+    if (!g) {
+      if (ctx->n_graphs == LM_MAX_GRAPHS) {      // cache full: drop everything (callers normally cycle through few buffers)
+        for (int i = 0; i < ctx->n_graphs; ++i) cudaGraphExecDestroy(ctx->graphs[i].exec);
+        ctx->n_graphs = 0;
+      }
+      const int64_t l0 = ctx->launches;
+      cudaGraph_t graph = nullptr;
+      LM_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+      rc = enqueue_body(ctx, d_corner, nc_cap, d_surf, ns_cap);
+      cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      LM_CUDA(ce);
+      g = &ctx->graphs[ctx->n_graphs];
+      g->dc = d_corner; g->ds = d_surf; g->nc_cap = nc_cap; g->ns_cap = ns_cap;
+      g->n_launch = (int)(ctx->launches - l0);
+      ctx->launches = l0;
+      ce = cudaGraphInstantiate(&g->exec, graph, 0);
+      cudaGraphDestroy(graph);
+      LM_CUDA(ce);
+      ctx->n_graphs++;
+    }
+    LM_CUDA(cudaGraphLaunch(g->exec, ctx->stream));
+    ctx->launches += g->n_launch;
+  }
   LM_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->step_pending = true;
   return LMONO_OK;

@@ -95,6 +95,11 @@ __global__ void __launch_bounds__(256) k_begin_step(LmMapState* __restrict__ st,
   __shared__ int s_own[LM_MAX_VALID + 3];
   __shared__ int s_all;
   if (threadIdx.x == 0) {
+    if (use_override == 2) {               // pose already stored by k_step_args (CUDA-graph replay: no per-step kernel arguments)
+      for (int k = 0; k < 4; ++k) odom.q[k] = st->q_wodom_curr[k];
+      for (int k = 0; k < 3; ++k) odom.t[k] = st->t_wodom_curr[k];
+      use_override = 0;
+    }
     for (int k = 0; k < 4; ++k) st->q_wodom_curr[k] = odom.q[k];
     for (int k = 0; k < 3; ++k) st->t_wodom_curr[k] = odom.t[k];
     double tw[3];
@@ -181,7 +186,7 @@ int lm_map_begin_step(lmono_ctx* ctx, const lmono_pose* wodom_curr, const double
   if (wodom_curr) { for (int k = 0; k < 4; ++k) pa.q[k] = wodom_curr->q[k]; for (int k = 0; k < 3; ++k) pa.t[k] = wodom_curr->t[k]; }
   else { pa.q[0] = pa.q[1] = pa.q[2] = 0; pa.q[3] = 1; pa.t[0] = pa.t[1] = pa.t[2] = 0; }
   k_begin_step<<<1, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_slot_valid_rank, pa,
-                                           t_override ? 1 : 0, t_override ? t_override[0] : 0.0,
+                                           t_override ? 1 : (wodom_curr ? 0 : 2), t_override ? t_override[0] : 0.0,
                                            t_override ? t_override[1] : 0.0, t_override ? t_override[2] : 0.0);
   LM_LAUNCH_CHECK();
   return LMONO_OK;

@@ -71,7 +71,10 @@ def gen_primitives():
 def gen_scan():
     w = synth.make_world()
     out = {}
-    for n_scans, min_range, n_az in ((64, 5.0, 300), (32, 0.3, 300), (16, 0.3, 300)):
+    # n_az is deliberately NOT a multiple of 4: on a regular azimuth grid a point exactly 90 deg from the last
+    # point sits on the `ori > endOri + pi/2` branch of the unwrap (scanRegistration.cpp:226-233), where the last
+    # ulp of atan2f (libm build vs device) decides a 2*pi jump of relTime -- the hazard DESIGN.md documents
+    for n_scans, min_range, n_az in ((64, 5.0, 301), (32, 0.3, 301), (16, 0.3, 301)):
         q, t = synth.loop_pose(w, 5.0)
         raw = synth.raycast_sweep(w, q, t, n_scans, n_az, np.random.default_rng(40 + n_scans)).astype(np.float32)
         r = O.scan_register(raw, n_scans, min_range)
@@ -97,7 +100,7 @@ def gen_odometry():
     feats = []
     for k in range(3):
         q, t = synth.loop_pose(w, 0.8 * k)
-        raw = synth.raycast_sweep(w, q, t, 64, 450, rng).astype(np.float32)
+        raw = synth.raycast_sweep(w, q, t, 64, 451, rng).astype(np.float32)
         r = O.scan_register(raw, 64, 5.0)
         feats.append(r)
         (lq, lt), (wq, wt), rep = od.step(r["sharp"], r["less_sharp"], r["flat"], r["less_flat"])

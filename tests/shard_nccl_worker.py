@@ -25,7 +25,11 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    # one real (non-default) stream shared by torch / NCCL and both contexts: a 0 handle would make each ctx
+    # create its own stream and the all-reduces would not be ordered with the kernels
+    ts = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(ts)
+    stream = ts.cuda_stream
     cm, sm = scenario.small_map(half_xy=80.0, n_surf=250_000, n_corner=60_000)
     ref = api.Context(device=local, stream=stream)
     ref.map_import(0, cm); ref.map_import(1, sm)

@@ -57,7 +57,8 @@ def _check_scan(r, g, k, gpu=False):
     # relTime goes through atan2f: the integer ring part is exact, the fraction is compared at 4e-6 (+ ulps after averaging)
     assert np.array_equal(np.floor(r["full"][:, 3]), np.floor(g[k + "full_intensity"]))
     tol = 4e-6 if gpu else 0.0
-    assert np.all(np.abs(r["full"][:, 3] - g[k + "full_intensity"]) <= tol)
+    dI = np.abs(r["full"][:, 3] - g[k + "full_intensity"])
+    assert dI.max() <= tol, (dI.max(), int(dI.argmax()), r["full"][dI.argmax()], g[k + "full_intensity"][dI.argmax()], rep.start_ori, rep.end_ori)
     assert np.all(np.abs(r["less_flat"][:, 3] - g[k + "less_flat"][:, 3]) <= tol + (2.0 * np.spacing(np.abs(g[k + "less_flat"][:, 3])) if gpu else 0.0))
 
 

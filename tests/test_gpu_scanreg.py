@@ -78,8 +78,12 @@ def test_scan_register_edge_cases(gpu_ctx_factory, oracle):
 
 def test_ring_assignment_margin(oracle):
     """The generator puts beams at ring-bin centres; double- and float-overload evaluations of
-    scanRegistration.cpp:166 must then agree on every ring id (hard part 2)."""
+    scanRegistration.cpp:166 must then agree on every ring id (hard part 2).  The topmost
+    HDL-64 beam sits at exactly +2 deg = the `angle > 2` drop threshold of :195, where the last ulp of
+    atan decides (and differs between libm builds / CPUs): that beam is excluded from the claim."""
     raw = _sweep(64, 1875, 4)
+    elev = np.degrees(np.arctan2(raw[:, 2].astype(np.float64), np.hypot(raw[:, 0].astype(np.float64), raw[:, 1].astype(np.float64))))
+    raw = np.ascontiguousarray(raw[elev < 1.99])
     a = oracle.scan_register(raw, 64, 5.0, trig_mode=0)
     b = oracle.scan_register(raw, 64, 5.0, trig_mode=1)
     assert a["report"].n_kept == b["report"].n_kept

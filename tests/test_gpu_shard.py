@@ -40,7 +40,9 @@ def test_sharded_registration_matches_unsharded_on_one_gpu(gpu_ctx_factory, nran
     import torch
     dev = torch.device("cuda", 0)
     cm, sm = scenario.small_map(half_xy=80.0, n_surf=250_000, n_corner=60_000)
-    stream = torch.cuda.current_stream().cuda_stream
+    ts = torch.cuda.Stream(device=dev)       # real stream shared by torch and all contexts (handle 0 = "create your own")
+    torch.cuda.set_stream(ts)
+    stream = ts.cuda_stream
     from lmono_b200 import api
     ref = api.Context(device=0, stream=stream)
     ref.map_import(0, cm); ref.map_import(1, sm)
@@ -76,6 +78,8 @@ def test_sharded_registration_matches_unsharded_on_one_gpu(gpu_ctx_factory, nran
                 n_union += len(a)
             assert n_union == len(full)
     finally:
+        torch.cuda.synchronize()
+        torch.cuda.set_stream(torch.cuda.default_stream(dev))
         ref.close()
         for c in ctxs:
             c.close()
