@@ -214,7 +214,7 @@ int lmono_voxel_grid(lmono_ctx* ctx, lmono_cloud_view in, float leaf, lmono_clou
 /* Latency study hook: %globaltimer stamps (ns) written by instrumented kernels (slot map in DESIGN.md):
  * [0..63] the LM solve kernel of the most recent solve: 0 start, 1 armed, then per evaluation e (8 slots from
  * 8 + 8 e): factors evaluated, warp+block reduced, cluster exchanged, controller done. */
-int lmono_debug_stamps(lmono_ctx* ctx, uint64_t* out /*[n]*/, int32_t n /*<= 256*/);
+int lmono_debug_stamps(lmono_ctx* ctx, uint64_t* out /*[n]*/, int32_t n /*<= 4096*/);
 
 /* Per-phase device timing (CUDA events on the ctx stream) of lmono_map_step, used by bench.py
  * for the roofline numbers.  Phases: 0 window shift, 1 cell-index build, 2 VoxelGrid of the

@@ -18,7 +18,8 @@ constexpr int LM_MAX_VALID = 125;                 // :85 (<=75 used)
 // each side) spans 26 cells per axis.
 constexpr int LM_CELLS_AXIS = 26;
 constexpr int LM_NCELL = LM_CELLS_AXIS * LM_CELLS_AXIS * LM_CELLS_AXIS;   // 17576
-constexpr int LM_SORT_TILE = 4096;                // elements per CTA in the global tile sort
+constexpr int LM_SORT_TILE = 2048;                // elements per CTA in the global tile sort
+constexpr int LM_SORT_MAXSEG = 2;                 // independent segments sorted by one pair of launches
 constexpr int LM_TAIL_TILE = 16384;               // max unsorted tail per cube refilter (smem sort)
 
 // device fault bits (LmMapState::fault)
@@ -107,9 +108,9 @@ struct LmMapType {           // one per map (0 corner, 1 surf); device pointers,
   int32_t* free_top;         // [1]
 };
 
-struct VgParams {            // scan-level VoxelGrid parameters computed on device
-  int32_t min_b[3], div_b[3], mul[3];
-  int32_t guard;             // 1: PCL's "leaf size too small" path -> output = input
+struct VgParams {            // per-cloud VoxelGrid side state (voxel.cu): bounding box for PCL's overflow guard
+  uint32_t mn[3], mx[3];     // order-preserving encodings of the float min / max (atomicMin / atomicMax)
+  uint32_t ticket;           // blocks of k_vg_write that finished (the last one re-arms mn / mx)
   int32_t n;
 };
 
@@ -408,10 +409,16 @@ __device__ __forceinline__ int d_lower_bound_u32(const uint32_t* sorted, int n, 
 #endif  // __CUDACC__
 
 // ---------------------------------------------------------------- cross-TU host functions
-// sort.cu: sorts n (device int *n_dev, <= n_max) unique 64-bit keys ascending: in -> out (tmp is scratch)
+// sort.cu: segment s sorts *n[s] keys in[off[s] ...] -> out[off[s] ...] (tmp[off[s] ...] is scratch)
+struct LmSortSegs { const unsigned long long* in; unsigned long long* tmp; unsigned long long* out; int off[LM_SORT_MAXSEG]; const int32_t* n[LM_SORT_MAXSEG]; };
+int lm_sort_u64_segs(lmono_ctx* ctx, const LmSortSegs& sg, int nseg, const int* n_max);
+// sorts n (device int *n_dev, <= n_max) unique 64-bit keys ascending: in -> out (tmp is scratch)
 int lm_sort_u64(lmono_ctx* ctx, const unsigned long long* in, unsigned long long* tmp, unsigned long long* out,
                 const int32_t* n_dev, int n_max);
-// voxel.cu: VoxelGrid of `in` (n_dev points, <= n_max) -> out, *out_n_dev
+// voxel.cu: VoxelGrid of `in` (n_dev points, <= n_max) -> out, *out_n_dev; _multi runs up to LM_SORT_MAXSEG clouds through shared launches
+int lm_voxel_init(lmono_ctx* ctx);
+int lm_voxel_grid_multi(lmono_ctx* ctx, int nseg, const float4* const* in, const int32_t* const* n_dev, const int* n_max,
+                        const float* leaf, float4* const* out, int32_t* const* out_n_dev);
 int lm_voxel_grid_device(lmono_ctx* ctx, const float4* in, const int32_t* n_dev, int n_max, float leaf,
                          float4* out, int32_t* out_n_dev);
 // mapstore.cu

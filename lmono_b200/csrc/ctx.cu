@@ -86,8 +86,8 @@ extern "C" int lmono_create(int device, const lmono_params* params, void* stream
   LM_CUDA(cudaMalloc((void**)&ctx->d_slot_valid_rank, sizeof(int32_t) * LM_NSLOT));
   LM_CUDA(cudaMemsetAsync(ctx->d_slot_valid_rank, 0xFF, sizeof(int32_t) * LM_NSLOT, ctx->stream));
   LM_CUDA(cudaMalloc((void**)&ctx->d_partials, sizeof(double) * 32 * (1024 + 8)));
-  LM_CUDA(cudaMalloc((void**)&ctx->d_stamps, sizeof(unsigned long long) * 256));
-  LM_CUDA(cudaMemsetAsync(ctx->d_stamps, 0, sizeof(unsigned long long) * 256, ctx->stream));
+  LM_CUDA(cudaMalloc((void**)&ctx->d_stamps, sizeof(unsigned long long) * 4096));
+  LM_CUDA(cudaMemsetAsync(ctx->d_stamps, 0, sizeof(unsigned long long) * 4096, ctx->stream));
   const size_t nf = (size_t)ctx->max_feat;
   ctx->raw_bytes = (size_t)ctx->max_sweep * 32;
   for (int i = 0; i < 3; ++i) LM_CUDA(cudaMalloc((void**)&ctx->d_raw[i], ctx->raw_bytes));
@@ -104,6 +104,8 @@ extern "C" int lmono_create(int device, const lmono_params* params, void* stream
   LM_CUDA(cudaMalloc((void**)&ctx->d_blockcnt, sizeof(int32_t) * (nsort / 256 + 64)));
   LM_CUDA(cudaMalloc((void**)&ctx->d_tmp_i32, sizeof(int32_t) * (2 * LM_NSLOT + 64 + nsort)));
   LM_CUDA(cudaMalloc((void**)&ctx->d_vg, sizeof(VgParams) * 4));
+  { int rcv = lm_voxel_init(ctx); if (rcv) return rcv; }
+  if (ctx->max_feat > (1 << 19)) { fprintf(stderr, "[lmono_b200] max_feature_points must be <= 524288\n"); return LMONO_E_ARG; }
   LM_CUDA(cudaMalloc((void**)&ctx->d_full, (size_t)ctx->max_sweep * sizeof(float4)));
   LM_CUDA(cudaMalloc((void**)&ctx->d_slot_first, sizeof(int32_t) * 2 * LM_NSLOT));
   LM_CUDA(cudaMalloc((void**)&ctx->d_slot_base, sizeof(int32_t) * 2 * LM_NSLOT));
@@ -147,7 +149,7 @@ extern "C" int lmono_sync(lmono_ctx* ctx) {
 }
 
 extern "C" int lmono_debug_stamps(lmono_ctx* ctx, uint64_t* out, int32_t n) {
-  if (!ctx || !out || n < 0 || n > 256) return LMONO_E_ARG;
+  if (!ctx || !out || n < 0 || n > 4096) return LMONO_E_ARG;
   LM_CUDA(cudaMemcpyAsync(out, ctx->d_stamps, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   LM_CUDA(cudaStreamSynchronize(ctx->stream));
   return LMONO_OK;

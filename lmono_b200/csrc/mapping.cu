@@ -43,6 +43,17 @@ __global__ void k_step_args(LmMapState* st, StepArgs a) {
   for (int k = 0; k < 3; ++k) st->t_wodom_curr[k] = a.t[k];
 }
 
+// :542-550 VoxelGrid of the incoming corner and surf features, both clouds through the same four launches
+static int voxel_both(lmono_ctx* ctx, const float4* d_corner, int nc, const float4* d_surf, int ns) {
+  const float4* in[2] = { d_corner, d_surf };
+  const int32_t* n_dev[2] = { &ctx->d_state->raw_n[0], &ctx->d_state->raw_n[1] };
+  const int n_max[2] = { nc, ns };
+  const float leaf[2] = { ctx->map[0].leaf, ctx->map[1].leaf };
+  float4* out[2] = { ctx->d_stack[0], ctx->d_stack[1] };
+  int32_t* out_n[2] = { &ctx->d_state->stack_n[0], &ctx->d_state->stack_n[1] };
+  return lm_voxel_grid_multi(ctx, 2, in, n_dev, n_max, leaf, out, out_n);
+}
+
 // the step body: nc / ns only size the launch grids (every kernel reads the real counts from the state)
 static int enqueue_body(lmono_ctx* ctx, const float4* d_corner, int nc, const float4* d_surf, int ns) {
   int rc;
@@ -54,8 +65,7 @@ static int enqueue_body(lmono_ctx* ctx, const float4* d_corner, int nc, const fl
   lm_prof_end(ctx);
   // :542-550 VoxelGrid of the incoming features
   lm_prof_begin(ctx, LM_PROF_VOXEL);
-  if ((rc = lm_voxel_grid_device(ctx, d_corner, &ctx->d_state->raw_n[0], nc, ctx->map[0].leaf, ctx->d_stack[0], &ctx->d_state->stack_n[0]))) return rc;
-  if ((rc = lm_voxel_grid_device(ctx, d_surf, &ctx->d_state->raw_n[1], ns, ctx->map[1].leaf, ctx->d_stack[1], &ctx->d_state->stack_n[1]))) return rc;
+  if ((rc = voxel_both(ctx, d_corner, nc, d_surf, ns))) return rc;
   lm_prof_end(ctx);
   for (int iter = 0; iter < 2; ++iter) {                                    // :562
     lm_prof_begin(ctx, LM_PROF_ASSOC);
@@ -171,8 +181,7 @@ extern "C" int lmono_shard_begin(lmono_ctx* ctx, const void* d_corner, int32_t n
   LM_LAUNCH_CHECK();
   if ((rc = lm_map_begin_step(ctx, wodom_curr, nullptr))) return rc;
   if ((rc = lm_map_index_build(ctx))) return rc;
-  if ((rc = lm_voxel_grid_device(ctx, (const float4*)d_corner, &ctx->d_state->raw_n[0], nc, ctx->map[0].leaf, ctx->d_stack[0], &ctx->d_state->stack_n[0]))) return rc;
-  if ((rc = lm_voxel_grid_device(ctx, (const float4*)d_surf, &ctx->d_state->raw_n[1], ns, ctx->map[1].leaf, ctx->d_stack[1], &ctx->d_state->stack_n[1]))) return rc;
+  if ((rc = voxel_both(ctx, (const float4*)d_corner, nc, (const float4*)d_surf, ns))) return rc;
   k_shard_publish_counts<<<1, 64, 0, ctx->stream>>>(ctx->d_state, ctx->d_shard_ws);
   LM_LAUNCH_CHECK();
   return LMONO_OK;

@@ -343,13 +343,16 @@ __global__ void __launch_bounds__(256) k_insert_write(LmMapType M0, LmMapType M1
 // [ns,n) in arrival order.  VoxelGrid(prefix ++ tail) == merge(prefix, stable-sorted tail):
 // a voxel's members are the prefix point (if any) followed by the tail points in arrival
 // order, summed in fp32 in that order and divided by (float)count.
-__global__ void __launch_bounds__(1024, 1) k_refilter(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1) {
+#define RF_STAMP(k) do { if (stamps && threadIdx.x == 0) stamps[256 + (blockIdx.y * 75 + blockIdx.x) * 8 + (k)] = d_globaltimer(); } while (0)
+__global__ void __launch_bounds__(1024, 1) k_refilter(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, unsigned long long* __restrict__ stamps) {
   extern __shared__ unsigned char smem_raw[];
   unsigned long long* S = reinterpret_cast<unsigned long long*>(smem_raw);              // [LM_TAIL_TILE]
   int* NV = reinterpret_cast<int*>(smem_raw + (size_t)LM_TAIL_TILE * 8);                // [LM_TAIL_TILE]
   int* ws = reinterpret_cast<int*>(smem_raw + (size_t)LM_TAIL_TILE * 12);               // [64]
   __shared__ int s_flag;
   const int r = blockIdx.x;
+  RF_STAMP(0);
+  if (stamps && threadIdx.x == 0) { stamps[256 + (blockIdx.y * 75 + blockIdx.x) * 8 + 5] = 0; stamps[256 + (blockIdx.y * 75 + blockIdx.x) * 8 + 6] = 0; }
   if (r >= st->valid_num) return;
   const LmMapType& M = blockIdx.y == 0 ? M0 : M1;
   const int ps = st->valid_slot[r];
@@ -359,6 +362,7 @@ __global__ void __launch_bounds__(1024, 1) k_refilter(LmMapState* __restrict__ s
   const int ns = M.slab_nsorted[sid];
   const int nt = n - ns;
   if (nt == 0) return;                         // already filtered: VoxelGrid is the identity
+  if (stamps && threadIdx.x == 0) { stamps[256 + (blockIdx.y * 75 + blockIdx.x) * 8 + 5] = ns; stamps[256 + (blockIdx.y * 75 + blockIdx.x) * 8 + 6] = nt; }
   if (nt > LM_TAIL_TILE) { if (threadIdx.x == 0) atomicOr(&st->fault, LM_FAULT_TAIL_OVERFLOW); return; }
   const int cur = M.slab_cur[sid];
   const float4* src = M.pts + ((size_t)sid * 2 + cur) * M.cap;
@@ -372,7 +376,9 @@ __global__ void __launch_bounds__(1024, 1) k_refilter(LmMapState* __restrict__ s
   for (int j = threadIdx.x; j < np2; j += blockDim.x)
     S[j] = j < nt ? (((unsigned long long)d_cube_voxel_key(src[ns + j], il, g3) << 32) | (uint32_t)j) : ~0ULL;
   __syncthreads();
+  RF_STAMP(1);
   d_bitonic_sort(S, np2);
+  RF_STAMP(2);
 
   // new-voxel flags and their exclusive prefix over the sorted tail
   const int per = (nt + blockDim.x - 1) / blockDim.x;
@@ -433,6 +439,7 @@ __global__ void __launch_bounds__(1024, 1) k_refilter(LmMapState* __restrict__ s
   }
   if (threadIdx.x == 0) s_flag = 0;
   __syncthreads();
+  RF_STAMP(3);
   const int nn = min(n_new, M.cap);
   // a centroid may round across a voxel border: verify the output is still strictly ascending,
   // otherwise the whole slab is treated as unsorted tail next time (what PCL would do anyway).
@@ -445,9 +452,11 @@ __global__ void __launch_bounds__(1024, 1) k_refilter(LmMapState* __restrict__ s
     M.slab_cur[sid] = cur ^ 1;
   }
   __syncthreads();
+  RF_STAMP(4);
   // rebuild the search index of this cube from the new buffer (reuses the sort scratch)
   d_build_cell_index(M, sid, dst, nn, reinterpret_cast<uint32_t*>(smem_raw), ws, st);
   if (threadIdx.x == 0) M.slab_dirty[sid] = 0;
+  RF_STAMP(7);
 }
 
 static const int kRefilterSmem = LM_TAIL_TILE * 12 + 64 * 4;
@@ -474,7 +483,7 @@ int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf)
   }
   lm_prof_end(ctx);
   lm_prof_begin(ctx, LM_PROF_REFILTER);
-  k_refilter<<<dim3(75, 2), 1024, kRefilterSmem, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1]);
+  k_refilter<<<dim3(75, 2), 1024, kRefilterSmem, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_stamps);
   LM_LAUNCH_CHECK();
   lm_prof_end(ctx);
   return LMONO_OK;

@@ -1,69 +1,116 @@
-// Device sort of unique 64-bit keys whose count lives in device memory.
+// Device sort of unique 64-bit keys whose counts live in device memory; up to LM_SORT_MAXSEG
+// independent segments per call (e.g. the corner and the surf VoxelGrid of one sweep share launches).
 // Two launches, no host synchronisation:
-//   k_sort_tiles : each CTA bitonic-sorts one 4096-key tile held in registers (8 keys/thread;
-//                  in-thread, warp-shuffle and only 10 shared-memory stages of 78)
-//   k_merge_ranks: every key finds its global rank = own position + sum over the other
-//                  tiles of lower_bound(tile, key)  (keys are unique), and scatters.
-// Used for VoxelGrid keys (PCL sorts cloud_point_index_idx, voxel_grid.hpp), cube
-// insertion order and map import.  Keys are (sort key << 32 | original index) composites,
-// so the result equals a STABLE sort by key -- the canonical order DESIGN.md defines in
-// place of libstdc++'s unstable std::sort.
+//   k_sort_tiles : each CTA bitonic-sorts one 2048-key tile held in registers (8 keys/thread x 256
+//                  threads: 3 in-thread + 5 warp-shuffle partner distances, only 6 of the 66 stages go
+//                  through shared memory).  Small tiles on many SMs: the network is issue-bound, so
+//                  16 k keys on 8 SMs finish in a fraction of the time of 4 SMs x 4096.
+//   k_merge_ranks: one pass merges groups of 8 sorted runs: every key finds its rank = own position +
+//                  sum over the other runs of its group of lower_bound(run, key) (keys are unique) and
+//                  scatters.  The searches over different runs are independent: four run interleaved
+//                  per thread so their (L1/L2-resident) loads overlap instead of forming one long
+//                  dependent chain.  <= 16 k keys need one pass, 2 M keys (map import) four.
+// Used for VoxelGrid keys (PCL sorts cloud_point_index_idx, voxel_grid.hpp), cube insertion
+// order and map import.  Keys are (sort key << k | original index) composites, so the result
+// equals a STABLE sort by key -- the canonical order DESIGN.md defines in place of libstdc++'s
+// unstable std::sort.
 #include "common.cuh"
 
-__global__ void __launch_bounds__(512) k_sort_tiles(const unsigned long long* __restrict__ in,
-                                                    unsigned long long* __restrict__ tmp,
-                                                    unsigned long long* __restrict__ out,
-                                                    const int32_t* __restrict__ n_dev) {
+constexpr int ST_THREADS = 256;
+constexpr int ST_ITEMS = LM_SORT_TILE / ST_THREADS;
+static_assert(LM_SORT_TILE == 2048 && ST_ITEMS == 8, "tile geometry");
+
+__global__ void __launch_bounds__(ST_THREADS) k_sort_tiles(LmSortSegs sg, int dst_is_tmp) {
   __shared__ unsigned long long s[LM_SORT_TILE];
-  const int n = *n_dev;
+  const int seg = blockIdx.y;
+  const int n = *sg.n[seg];
   const int base = blockIdx.x * LM_SORT_TILE;
   if (base >= n) return;
-  constexpr int ITEMS = LM_SORT_TILE / 512;
+  const unsigned long long* __restrict__ in = sg.in + sg.off[seg];
   // coalesced load through shared memory into the blocked register arrangement
-  for (int i = threadIdx.x; i < LM_SORT_TILE; i += blockDim.x) s[i] = (base + i < n) ? in[base + i] : ~0ULL;
+  for (int i = threadIdx.x; i < LM_SORT_TILE; i += ST_THREADS) s[i] = (base + i < n) ? in[base + i] : ~0ULL;
   __syncthreads();
-  unsigned long long v[ITEMS];
+  unsigned long long v[ST_ITEMS];
 #pragma unroll
-  for (int r = 0; r < ITEMS; ++r) v[r] = s[threadIdx.x * ITEMS + r];
+  for (int r = 0; r < ST_ITEMS; ++r) v[r] = s[threadIdx.x * ST_ITEMS + r];
   __syncthreads();
-  d_bitonic_regs<ITEMS>(v, threadIdx.x, 512, s);
+  d_bitonic_regs<ST_ITEMS>(v, threadIdx.x, ST_THREADS, s);
 #pragma unroll
-  for (int r = 0; r < ITEMS; ++r) s[threadIdx.x * ITEMS + r] = v[r];
+  for (int r = 0; r < ST_ITEMS; ++r) s[threadIdx.x * ST_ITEMS + r] = v[r];
   __syncthreads();
-  unsigned long long* dst = (n <= LM_SORT_TILE) ? out : tmp;
-  for (int i = threadIdx.x; i < LM_SORT_TILE; i += blockDim.x) if (base + i < n) dst[base + i] = s[i];
+  unsigned long long* dst = (dst_is_tmp ? sg.tmp : sg.out) + sg.off[seg];
+  for (int i = threadIdx.x; i < LM_SORT_TILE; i += ST_THREADS) if (base + i < n) dst[base + i] = s[i];
 }
 
-__global__ void __launch_bounds__(256) k_merge_ranks(const unsigned long long* __restrict__ tmp,
-                                                     unsigned long long* __restrict__ out,
-                                                     const int32_t* __restrict__ n_dev) {
-  const int n = *n_dev;
-  if (n <= LM_SORT_TILE) return;   // single tile already written to out
-  const int ntiles = (n + LM_SORT_TILE - 1) / LM_SORT_TILE;
+// One merge pass: sorted runs of `run` keys (a power of two) are merged in groups of LM_MERGE_GROUP into
+// runs of LM_MERGE_GROUP * run keys.  Every key ranks itself inside the other runs of its group with
+// branch-free binary searches, four of them interleaved so their loads overlap.
+constexpr int LM_MERGE_GROUP = 8;
+
+__global__ void __launch_bounds__(256) k_merge_ranks(LmSortSegs sg, int run, int src_is_tmp) {
+  const int seg = blockIdx.y;
+  const int n = *sg.n[seg];
+  const unsigned long long* __restrict__ src = (src_is_tmp ? sg.tmp : sg.out) + sg.off[seg];
+  unsigned long long* __restrict__ dst = (src_is_tmp ? sg.out : sg.tmp) + sg.off[seg];
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-    const unsigned long long key = tmp[e];
-    const int my_tile = e / LM_SORT_TILE;
-    int rank = e - my_tile * LM_SORT_TILE;
-    for (int t = 0; t < ntiles; ++t) {
-      if (t == my_tile) continue;
-      const int tb = t * LM_SORT_TILE;
-      const int tn = min(LM_SORT_TILE, n - tb);
-      rank += d_lower_bound_u64(tmp + tb, tn, key);
+    const unsigned long long key = src[e];
+    const int my_run = e / run;
+    const int g0 = (my_run / LM_MERGE_GROUP) * LM_MERGE_GROUP;        // first run of my group
+    int rank = g0 * run + (e - my_run * run);
+#pragma unroll
+    for (int b = 0; b < LM_MERGE_GROUP; b += 4) {
+      int pos[4] = { 0, 0, 0, 0 }, tn[4];
+      const unsigned long long* a[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = g0 + b + u;
+        const long long start = (long long)t * run;
+        const bool on = t != my_run && start < n;
+        a[u] = src + (on ? start : 0);
+        tn[u] = on ? (int)min((long long)run, (long long)n - start) : 0;
+      }
+      for (int s = run; s > 0; s >>= 1) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int probe = pos[u] + s;
+          if (probe <= tn[u] && a[u][probe - 1] < key) pos[u] = probe;
+        }
+      }
+      rank += pos[0] + pos[1] + pos[2] + pos[3];
     }
-    out[rank] = key;
+    dst[rank] = key;
   }
+}
+
+static int merge_passes(int n_max) {
+  int p = 0;
+  for (long long run = LM_SORT_TILE; run < n_max; run *= LM_MERGE_GROUP) ++p;
+  return p;
+}
+
+int lm_sort_u64_segs(lmono_ctx* ctx, const LmSortSegs& sg, int nseg, const int* n_max) {
+  int mx = 0;
+  for (int s = 0; s < nseg; ++s) mx = n_max[s] > mx ? n_max[s] : mx;
+  if (mx <= 0 || nseg <= 0) return LMONO_OK;
+  const int ntiles = lm_div_up(mx, LM_SORT_TILE);
+  const int passes = merge_passes(mx);
+  // buffers alternate tmp <-> out per pass and the last pass must land in `out`
+  int cur_is_tmp = (passes & 1) ? 1 : 0;
+  k_sort_tiles<<<dim3(ntiles, nseg), ST_THREADS, 0, ctx->stream>>>(sg, cur_is_tmp);
+  LM_LAUNCH_CHECK();
+  long long run = LM_SORT_TILE;
+  for (int p = 0; p < passes; ++p, run *= LM_MERGE_GROUP) {
+    k_merge_ranks<<<dim3(lm_div_up(mx, 256), nseg), 256, 0, ctx->stream>>>(sg, (int)run, cur_is_tmp);
+    LM_LAUNCH_CHECK();
+    cur_is_tmp ^= 1;
+  }
+  return LMONO_OK;
 }
 
 int lm_sort_u64(lmono_ctx* ctx, const unsigned long long* in, unsigned long long* tmp, unsigned long long* out,
                 const int32_t* n_dev, int n_max) {
-  if (n_max <= 0) return LMONO_OK;
-  const int ntiles = lm_div_up(n_max, LM_SORT_TILE);
-  k_sort_tiles<<<ntiles, 512, 0, ctx->stream>>>(in, tmp, out, n_dev);
-  LM_LAUNCH_CHECK();
-  if (ntiles > 1) {
-    int blocks = lm_div_up(n_max, 256);
-    k_merge_ranks<<<blocks, 256, 0, ctx->stream>>>(tmp, out, n_dev);
-    LM_LAUNCH_CHECK();
-  }
-  return LMONO_OK;
+  LmSortSegs sg;
+  sg.in = in; sg.tmp = tmp; sg.out = out;
+  for (int s = 0; s < LM_SORT_MAXSEG; ++s) { sg.off[s] = 0; sg.n[s] = n_dev; }
+  return lm_sort_u64_segs(ctx, sg, 1, &n_max);
 }

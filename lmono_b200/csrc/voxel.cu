@@ -2,138 +2,200 @@
 // fields, output ascending in PCL's linear voxel index).  Call sites replaced:
 // Aloam/src/laserMapping.cpp:542-550 (incoming corner/surf features) and
 // Aloam/src/scanRegistration.cpp:401-405 (per-ring less-flat downsample, see scanreg.cu).
-// Arithmetic follows PCL 1.8 voxel_grid.hpp: bbox -> min_b/div_b, per-point
-// ijk = (int)(floor(p * inv_leaf) - (float)min_b), idx = ijk . divb_mul; members summed in
-// fp32 in (idx, input index) order and divided by (float)count.
+// Arithmetic follows PCL 1.8 voxel_grid.hpp: per-point voxel coordinate floor(p * inv_leaf) in fp32;
+// members of a voxel summed in fp32 in (voxel, input index) order and divided by (float)count.
+//
+// PCL sorts on idx = ijk . (1, dx, dx*dy) with ijk = floor(p * inv_leaf) - min_b: that order is the
+// lexicographic (z, y, x) order of the ABSOLUTE voxel coordinates, independent of the bounding box.
+// The sort key here is therefore the absolute coordinate triple (3 x 15 bits, biased) | input index
+// (19 bits), which needs no bounding-box pass in front of the sort; the box is only needed for PCL's
+// overflow guard ("leaf size too small": output = input) and is reduced on the side with atomics.
+// Both clouds of a sweep (corner, surf) go through the same four launches:
+//   k_vg_keys -> k_sort_tiles -> k_merge_ranks -> k_vg_write
 #include "common.cuh"
 #include <float.h>
 
-__global__ void __launch_bounds__(1024) k_vg_bbox(const float4* __restrict__ pts, const int32_t* __restrict__ n_dev,
-                                                  float inv_leaf, VgParams* __restrict__ vg) {
-  __shared__ float smn[3][32], smx[3][32];
-  const int n = *n_dev;
-  float mn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, mx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    float4 p = pts[i];
-    mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
-    mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
-    mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+constexpr int VG_BIAS = 16384;           // voxel coordinates in [-16384, 16383]
+constexpr int VG_IDX_BITS = 19;          // input index < 524288
+constexpr int VW_THREADS = 256, VW_ITEMS = 4, VW_BLOCK = VW_THREADS * VW_ITEMS;
+
+struct VgSegs {
+  const float4* in[LM_SORT_MAXSEG]; float4* out[LM_SORT_MAXSEG];
+  const int32_t* n[LM_SORT_MAXSEG]; int32_t* out_n[LM_SORT_MAXSEG];
+  float inv_leaf[LM_SORT_MAXSEG];
+  int off[LM_SORT_MAXSEG];
+};
+
+__device__ __forceinline__ uint32_t d_f2ord(float f) { uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float d_ord2f(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+__global__ void k_vg_reset(VgParams* vg) {
+  if (threadIdx.x < LM_SORT_MAXSEG) {
+    VgParams& v = vg[threadIdx.x];
+    for (int d = 0; d < 3; ++d) { v.mn[d] = 0xFFFFFFFFu; v.mx[d] = 0u; }
+    v.ticket = 0; v.n = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_vg_keys(VgSegs sg, VgParams* __restrict__ vgs, unsigned long long* __restrict__ comp,
+                                                 LmMapState* __restrict__ st) {
+  __shared__ uint32_t smn[3][8], smx[3][8];
+  const int seg = blockIdx.y;
+  const int n = *sg.n[seg];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.x * blockDim.x >= n) return;
+  uint32_t mn[3] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu }, mx[3] = { 0u, 0u, 0u };
+  if (i < n) {
+    const float4 p = sg.in[seg][i];
+    const float il = sg.inv_leaf[seg];
+    int v[3] = { (int)floorf(__fmul_rn(p.x, il)), (int)floorf(__fmul_rn(p.y, il)), (int)floorf(__fmul_rn(p.z, il)) };
+    bool bad = false;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { v[d] += VG_BIAS; if (v[d] < 0 || v[d] >= 2 * VG_BIAS) { bad = true; v[d] = min(max(v[d], 0), 2 * VG_BIAS - 1); } }
+    if (bad || i >= (1 << VG_IDX_BITS)) atomicOr(&st->fault, LM_FAULT_FEATURE_OVERFLOW);
+    const unsigned long long key = ((unsigned long long)v[2] << 30) | ((unsigned long long)v[1] << 15) | (unsigned long long)v[0];
+    comp[sg.off[seg] + i] = (key << VG_IDX_BITS) | (unsigned long long)i;
+    mn[0] = mx[0] = d_f2ord(p.x); mn[1] = mx[1] = d_f2ord(p.y); mn[2] = mx[2] = d_f2ord(p.z);
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
-      mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+      mn[d] = min(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+      mx[d] = max(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
     }
     if (lane == 0) { smn[d][wid] = mn[d]; smx[d][wid] = mx[d]; }
   }
   __syncthreads();
+  if (threadIdx.x < 3) {
+    const int d = threadIdx.x;
+    uint32_t a = smn[d][0], b = smx[d][0];
+    for (int w = 1; w < 8; ++w) { a = min(a, smn[d][w]); b = max(b, smx[d][w]); }
+    atomicMin(&vgs[seg].mn[d], a);
+    atomicMax(&vgs[seg].mx[d], b);
+  }
+}
+
+// sorted composites -> one centroid per voxel run, in run order.  Each block owns VW_BLOCK consecutive
+// sorted positions; its output offset = number of run heads before it, recounted from the (L2-resident,
+// <= 128 KB) sorted array instead of a separate scan launch.
+__global__ void __launch_bounds__(VW_THREADS) k_vg_write(VgSegs sg, VgParams* __restrict__ vgs, const unsigned long long* __restrict__ sorted_all) {
+  __shared__ int ws[33];
+  __shared__ int s_guard;
+  const int seg = blockIdx.y;
+  const int n = *sg.n[seg];
+  VgParams& vg = vgs[seg];
+  const float4* __restrict__ pts = sg.in[seg];
+  float4* __restrict__ out = sg.out[seg];
+  const unsigned long long* __restrict__ sorted = sorted_all + sg.off[seg];
+  const int base = blockIdx.x * VW_BLOCK;
+  const int nblocks_active = max(1, (n + VW_BLOCK - 1) / VW_BLOCK);
+  if ((int)blockIdx.x >= nblocks_active) return;
   if (threadIdx.x == 0) {
-    const int nw = blockDim.x >> 5;
-    for (int d = 0; d < 3; ++d) for (int w = 1; w < nw; ++w) { smn[d][0] = fminf(smn[d][0], smn[d][w]); smx[d][0] = fmaxf(smx[d][0], smx[d][w]); }
-    vg->n = n;
-    if (n <= 0) { vg->guard = 0; for (int d = 0; d < 3; ++d) { vg->min_b[d] = 0; vg->div_b[d] = 1; vg->mul[d] = 0; } return; }
-    long long dd[3];
-    for (int d = 0; d < 3; ++d) dd[d] = (long long)(__fmul_rn(__fsub_rn(smx[d][0], smn[d][0]), inv_leaf)) + 1;
-    vg->guard = (dd[0] * dd[1] * dd[2] > (long long)INT32_MAX) ? 1 : 0;
-    int maxb[3];
-    for (int d = 0; d < 3; ++d) {
-      vg->min_b[d] = (int)floorf(__fmul_rn(smn[d][0], inv_leaf));
-      maxb[d] = (int)floorf(__fmul_rn(smx[d][0], inv_leaf));
-      vg->div_b[d] = maxb[d] - vg->min_b[d] + 1;
+    int guard = 0;
+    if (n > 0) {
+      const float il = sg.inv_leaf[seg];
+      long long dd[3];
+      for (int d = 0; d < 3; ++d) dd[d] = (long long)(__fmul_rn(__fsub_rn(d_ord2f(vg.mx[d]), d_ord2f(vg.mn[d])), il)) + 1;
+      guard = (dd[0] * dd[1] * dd[2] > (long long)INT32_MAX) ? 1 : 0;     // PCL: "Leaf size is too small"
     }
-    vg->mul[0] = 1; vg->mul[1] = vg->div_b[0]; vg->mul[2] = vg->div_b[0] * vg->div_b[1];
-  }
-}
-
-__global__ void __launch_bounds__(256) k_vg_keys(const float4* __restrict__ pts, float inv_leaf,
-                                                 const VgParams* __restrict__ vg, unsigned long long* __restrict__ comp) {
-  const int n = vg->n;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float4 p = pts[i];
-  int ijk0 = (int)(__fsub_rn(floorf(__fmul_rn(p.x, inv_leaf)), (float)vg->min_b[0]));
-  int ijk1 = (int)(__fsub_rn(floorf(__fmul_rn(p.y, inv_leaf)), (float)vg->min_b[1]));
-  int ijk2 = (int)(__fsub_rn(floorf(__fmul_rn(p.z, inv_leaf)), (float)vg->min_b[2]));
-  int idx = ijk0 * vg->mul[0] + ijk1 * vg->mul[1] + ijk2 * vg->mul[2];
-  comp[i] = ((unsigned long long)(uint32_t)idx << 32) | (uint32_t)i;
-}
-
-// heads of voxel runs in the sorted composite array, counted per block
-__global__ void __launch_bounds__(256) k_vg_count(const unsigned long long* __restrict__ sorted,
-                                                  const VgParams* __restrict__ vg, int32_t* __restrict__ blockcnt) {
-  __shared__ int ws[33];
-  const int n = vg->n;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int head = 0;
-  if (i < n) head = (i == 0) || ((sorted[i] >> 32) != (sorted[i - 1] >> 32));
-  int total;
-  d_block_exscan(head, ws, &total);
-  if (threadIdx.x == 0) blockcnt[blockIdx.x] = total;
-}
-
-__global__ void __launch_bounds__(256) k_vg_write(const float4* __restrict__ pts, const unsigned long long* __restrict__ sorted,
-                                                  const VgParams* __restrict__ vg, const int32_t* __restrict__ blockcnt,
-                                                  float4* __restrict__ out, int32_t* __restrict__ out_n) {
-  __shared__ int ws[33];
-  __shared__ int s_base;
-  const int n = vg->n;
-  if (vg->guard) {   // PCL returns the input cloud unchanged
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = pts[i];
-    if (blockIdx.x == 0 && threadIdx.x == 0) *out_n = n;
-    return;
-  }
-  // offset of this block = sum of the head counts of the blocks before it (few hundred at most)
-  if (threadIdx.x < 32) {
-    int acc = 0;
-    for (int b = threadIdx.x; b < (int)blockIdx.x; b += 32) acc += blockcnt[b];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (threadIdx.x == 0) s_base = acc;
+    s_guard = guard;
   }
   __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int head = 0;
-  unsigned long long me = 0;
-  if (i < n) { me = sorted[i]; head = (i == 0) || ((me >> 32) != (sorted[i - 1] >> 32)); }
-  int total;
-  int off = d_block_exscan(head, ws, &total);
-  if (head) {
-    const uint32_t key = (uint32_t)(me >> 32);
-    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-    int cnt = 0;
-    for (int j = i; j < n; ++j) {
-      unsigned long long c = sorted[j];
-      if ((uint32_t)(c >> 32) != key) break;
-      float4 p = pts[(uint32_t)c];
-      sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
-      ++cnt;
+  if (n == 0) {
+    if (threadIdx.x == 0) *sg.out_n[seg] = 0;
+  } else if (s_guard) {      // PCL returns the input cloud unchanged
+    for (int i = base + threadIdx.x; i < min(n, base + VW_BLOCK); i += VW_THREADS) out[i] = pts[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *sg.out_n[seg] = n;
+  } else {
+    // heads before this block
+    int before = 0;
+    for (int i = threadIdx.x; i < base; i += VW_THREADS)
+      before += (i == 0) || ((sorted[i] >> VG_IDX_BITS) != (sorted[i - 1] >> VG_IDX_BITS));
+    int total_before;
+    d_block_exscan(before, ws, &total_before);
+    // my VW_ITEMS consecutive positions
+    const int p0 = base + threadIdx.x * VW_ITEMS;
+    unsigned long long me[VW_ITEMS];
+    int head[VW_ITEMS], cnt = 0;
+    unsigned long long prev = (p0 > 0 && p0 < n) ? (sorted[p0 - 1] >> VG_IDX_BITS) : ~0ULL;
+#pragma unroll
+    for (int r = 0; r < VW_ITEMS; ++r) {
+      const int p = p0 + r;
+      head[r] = 0; me[r] = 0;
+      if (p < n) {
+        me[r] = sorted[p];
+        const unsigned long long k = me[r] >> VG_IDX_BITS;
+        head[r] = (p == 0) || (k != prev);
+        prev = k;
+      }
+      cnt += head[r];
     }
-    const float c = (float)cnt;
-    out[s_base + off] = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), __fdiv_rn(si, c));
+    int total;
+    int off = total_before + d_block_exscan(cnt, ws, &total);
+#pragma unroll
+    for (int r = 0; r < VW_ITEMS; ++r) {
+      if (!head[r]) continue;
+      const unsigned long long key = me[r] >> VG_IDX_BITS;
+      float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+      int c = 0;
+      for (int j = p0 + r; j < n; ++j) {
+        const unsigned long long cj = sorted[j];
+        if ((cj >> VG_IDX_BITS) != key) break;
+        const float4 p = pts[(uint32_t)(cj & ((1u << VG_IDX_BITS) - 1u))];
+        sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
+        ++c;
+      }
+      const float cf = (float)c;
+      out[off++] = make_float4(__fdiv_rn(sx, cf), __fdiv_rn(sy, cf), __fdiv_rn(sz, cf), __fdiv_rn(si, cf));
+    }
+    if (p0 <= n - 1 && n - 1 < p0 + VW_ITEMS) *sg.out_n[seg] = off;     // the thread that owns the last position
   }
-  if (i == n - 1 || (n == 0 && i == 0)) *out_n = (n == 0) ? 0 : (s_base + off + head);
+  // the last block to finish re-arms the bounding box for the next call
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned t = atomicAdd(&vg.ticket, 1u);
+    if (t == (unsigned)nblocks_active - 1) {
+      for (int d = 0; d < 3; ++d) { vg.mn[d] = 0xFFFFFFFFu; vg.mx[d] = 0u; }
+      vg.ticket = 0;
+    }
+  }
+}
+
+// VoxelGrid of up to LM_SORT_MAXSEG clouds with shared launches.  Scratch: ctx->d_sort_a/b/c (segment s at
+// offset sum of n_max of the segments before it), ctx->d_vg.
+int lm_voxel_grid_multi(lmono_ctx* ctx, int nseg, const float4* const* in, const int32_t* const* n_dev, const int* n_max,
+                        const float* leaf, float4* const* out, int32_t* const* out_n_dev) {
+  if (nseg < 1 || nseg > LM_SORT_MAXSEG) return LMONO_E_ARG;
+  VgSegs sg; LmSortSegs ss;
+  ss.in = ctx->d_sort_a; ss.tmp = ctx->d_sort_b; ss.out = ctx->d_sort_c;
+  int off = 0, mx = 0;
+  for (int s = 0; s < LM_SORT_MAXSEG; ++s) {
+    const int k = s < nseg ? s : 0;
+    sg.in[s] = in[k]; sg.out[s] = out[k]; sg.n[s] = n_dev[k]; sg.out_n[s] = out_n_dev[k]; sg.inv_leaf[s] = 1.0f / leaf[k];
+    sg.off[s] = s < nseg ? off : 0; ss.off[s] = sg.off[s]; ss.n[s] = n_dev[k];
+    if (s < nseg) { off += n_max[s]; mx = n_max[s] > mx ? n_max[s] : mx; }
+  }
+  if (mx > 0) {
+    k_vg_keys<<<dim3(lm_div_up(mx, 256), nseg), 256, 0, ctx->stream>>>(sg, ctx->d_vg, ctx->d_sort_a, ctx->d_state);
+    LM_LAUNCH_CHECK();
+    int rc = lm_sort_u64_segs(ctx, ss, nseg, n_max);
+    if (rc) return rc;
+  }
+  k_vg_write<<<dim3(max(1, lm_div_up(mx, VW_BLOCK)), nseg), VW_THREADS, 0, ctx->stream>>>(sg, ctx->d_vg, ctx->d_sort_c);
+  LM_LAUNCH_CHECK();
+  return LMONO_OK;
 }
 
 int lm_voxel_grid_device(lmono_ctx* ctx, const float4* in, const int32_t* n_dev, int n_max, float leaf,
                          float4* out, int32_t* out_n_dev) {
-  const float inv_leaf = 1.0f / leaf;
-  k_vg_bbox<<<1, 1024, 0, ctx->stream>>>(in, n_dev, inv_leaf, ctx->d_vg);
-  LM_LAUNCH_CHECK();
-  if (n_max <= 0) {   // still define out_n
-    LM_CUDA(cudaMemsetAsync(out_n_dev, 0, sizeof(int32_t), ctx->stream));
-    return LMONO_OK;
-  }
-  const int blocks = lm_div_up(n_max, 256);
-  k_vg_keys<<<blocks, 256, 0, ctx->stream>>>(in, inv_leaf, ctx->d_vg, ctx->d_sort_a);
-  LM_LAUNCH_CHECK();
-  int rc = lm_sort_u64(ctx, ctx->d_sort_a, ctx->d_sort_b, ctx->d_sort_c, &ctx->d_vg->n, n_max);
-  if (rc) return rc;
-  k_vg_count<<<blocks, 256, 0, ctx->stream>>>(ctx->d_sort_c, ctx->d_vg, ctx->d_blockcnt);
-  LM_LAUNCH_CHECK();
-  k_vg_write<<<blocks, 256, 0, ctx->stream>>>(in, ctx->d_sort_c, ctx->d_vg, ctx->d_blockcnt, out, out_n_dev);
+  return lm_voxel_grid_multi(ctx, 1, &in, &n_dev, &n_max, &leaf, &out, &out_n_dev);
+}
+
+int lm_voxel_init(lmono_ctx* ctx) {
+  k_vg_reset<<<1, 32, 0, ctx->stream>>>(ctx->d_vg);
   LM_LAUNCH_CHECK();
   return LMONO_OK;
 }
