@@ -20,7 +20,9 @@ constexpr int LM_CELLS_AXIS = 26;
 constexpr int LM_NCELL = LM_CELLS_AXIS * LM_CELLS_AXIS * LM_CELLS_AXIS;   // 17576
 constexpr int LM_SORT_TILE = 2048;                // elements per CTA in the global tile sort
 constexpr int LM_SORT_MAXSEG = 2;                 // independent segments sorted by one pair of launches
-constexpr int LM_TAIL_TILE = 16384;               // max unsorted tail per cube refilter (smem sort)
+constexpr int LM_TAIL_TILE = 16384;               // max points of a slab the whole-slab fallback refilter can re-voxelise (smem sort)
+constexpr int LM_RF_CHUNK = 2048;                 // points per CTA in the chunked refilter kernels
+constexpr int LM_WIN_MAX = 75;                    // cubes of the 5x5x3 window
 
 // device fault bits (LmMapState::fault)
 enum : unsigned {
@@ -97,7 +99,9 @@ struct LmMapType {           // one per map (0 corner, 1 surf); device pointers,
   float4* pts;               // [n_slabs][2][cap]  canonical (VoxelGrid) order, ping-pong
   float4* cellpts;           // [n_slabs][cap]     cell-sorted copy, .w = bits of slab position
   uint32_t* cellstart;       // [n_slabs][LM_NCELL+1]
-  uint32_t* pkey;            // [n_slabs][cap]     voxel keys of the sorted prefix (scratch)
+  uint32_t* pkey;            // [n_slabs][2][cap]  cube-local voxel key of every point of pts (same ping-pong buffer)
+  int32_t* cellcount;        // [n_slabs][LM_NCELL] refilter scratch: cell histogram, then scatter cursors
+  int32_t* slab_unsorted;    // [n_slabs] 1 = a centroid crossed a voxel border: the slab must be re-voxelised as a whole
   int32_t* slot_slab;        // [LM_NSLOT] slab id or -1
   int32_t* slab_n;           // [n_slabs] points in slab (sorted prefix + tail)
   int32_t* slab_nsorted;     // [n_slabs] length of the sorted, voxel-unique prefix
@@ -153,6 +157,8 @@ struct lmono_ctx {
   VgParams* d_vg;
   float4* d_full;                           // full-res sweep
   int32_t* d_slot_first; int32_t* d_slot_base; // insertion run tables [LM_NSLOT]
+  int32_t* d_rf_nvx;                        // refilter scratch [2][75][max cap]: (new voxels before j) << 1 | (j starts a new voxel)
+  int32_t* d_rf_meta;                       // [2][75][8]: active, total_new, ns, nt, unsorted flag, cur
   float4* d_export; size_t export_cap;      // export / import staging
   int32_t* d_export_off;                    // [LM_NSLOT+1]
   int max_feat, max_sweep;
@@ -351,11 +357,19 @@ __device__ __forceinline__ void d_cmpx(unsigned long long& a, unsigned long long
   if ((a > b) == up) { unsigned long long t = a; a = b; b = t; }
 }
 
-template <int ITEMS>
-__device__ __forceinline__ void d_bitonic_regs(unsigned long long (&v)[ITEMS], int t, int nthreads, unsigned long long* xch) {
-  const int N = ITEMS * nthreads;
-  for (int k = 2; k <= N; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
+template <int ITEMS, int NTHREADS>
+__device__ __forceinline__ void d_bitonic_regs(unsigned long long (&v)[ITEMS], int t, unsigned long long* xch) {
+  // every loop has a compile-time trip count and is fully unrolled: v[] must be indexed with constants
+  // only, otherwise it is demoted to local memory and the network runs ~5x slower
+  constexpr int N = ITEMS * NTHREADS;
+  constexpr int LOGN = (N <= 1) ? 0 : (31 - __builtin_clz((unsigned)N));
+  static_assert((1 << LOGN) == N, "ITEMS * NTHREADS must be a power of two");
+#pragma unroll
+  for (int lk = 1; lk <= LOGN; ++lk) {
+    const int k = 1 << lk;
+#pragma unroll
+    for (int lj = lk - 1; lj >= 0; --lj) {
+      const int j = 1 << lj;
       if (j >= 32 * ITEMS) {
         // cross-warp: exchange through shared memory
 #pragma unroll

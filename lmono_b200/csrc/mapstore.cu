@@ -26,7 +26,7 @@ __global__ void k_map_reset(LmMapType M) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < LM_NSLOT; i += gridDim.x * blockDim.x) M.slot_slab[i] = -1;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M.n_slabs; i += gridDim.x * blockDim.x) {
     M.free_stack[i] = M.n_slabs - 1 - i;   // pop order 0,1,2,...
-    M.slab_n[i] = 0; M.slab_nsorted[i] = 0; M.slab_cur[i] = 0; M.slab_dirty[i] = 0;
+    M.slab_n[i] = 0; M.slab_nsorted[i] = 0; M.slab_cur[i] = 0; M.slab_dirty[i] = 0; M.slab_unsorted[i] = 0;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) *M.free_top = M.n_slabs;
 }
@@ -42,7 +42,9 @@ int lm_map_alloc(lmono_ctx* ctx) {
     if ((rc = dev_alloc(ctx, &M.pts, (size_t)M.n_slabs * 2 * M.cap))) return rc;
     if ((rc = dev_alloc(ctx, &M.cellpts, (size_t)M.n_slabs * M.cap))) return rc;
     if ((rc = dev_alloc(ctx, &M.cellstart, (size_t)M.n_slabs * (LM_NCELL + 1)))) return rc;
-    if ((rc = dev_alloc(ctx, &M.pkey, (size_t)M.n_slabs * M.cap))) return rc;
+    if ((rc = dev_alloc(ctx, &M.pkey, (size_t)M.n_slabs * 2 * M.cap))) return rc;
+    if ((rc = dev_alloc(ctx, &M.cellcount, (size_t)M.n_slabs * LM_NCELL))) return rc;
+    if ((rc = dev_alloc(ctx, &M.slab_unsorted, (size_t)M.n_slabs))) return rc;
     if ((rc = dev_alloc(ctx, &M.slot_slab, (size_t)LM_NSLOT))) return rc;
     if ((rc = dev_alloc(ctx, &M.slab_n, (size_t)M.n_slabs))) return rc;
     if ((rc = dev_alloc(ctx, &M.slab_nsorted, (size_t)M.n_slabs))) return rc;
@@ -60,7 +62,7 @@ int lm_map_alloc(lmono_ctx* ctx) {
 void lm_map_free(lmono_ctx* ctx) {
   for (int ty = 0; ty < 2; ++ty) {
     LmMapType& M = ctx->map[ty];
-    cudaFree(M.pts); cudaFree(M.cellpts); cudaFree(M.cellstart); cudaFree(M.pkey); cudaFree(M.slot_slab);
+    cudaFree(M.pts); cudaFree(M.cellpts); cudaFree(M.cellstart); cudaFree(M.pkey); cudaFree(M.cellcount); cudaFree(M.slab_unsorted); cudaFree(M.slot_slab);
     cudaFree(M.slab_n); cudaFree(M.slab_nsorted); cudaFree(M.slab_cur); cudaFree(M.slab_dirty);
     cudaFree(M.slab_g); cudaFree(M.free_stack); cudaFree(M.free_top);
   }
@@ -78,7 +80,7 @@ __device__ __forceinline__ void d_free_slot(const LmMapType& M, int ps) {
   int sid = M.slot_slab[ps];
   if (sid >= 0) {
     M.slot_slab[ps] = -1;
-    M.slab_n[sid] = 0; M.slab_nsorted[sid] = 0; M.slab_dirty[sid] = 0;
+    M.slab_n[sid] = 0; M.slab_nsorted[sid] = 0; M.slab_dirty[sid] = 0; M.slab_unsorted[sid] = 0;
     int pos = atomicAdd(M.free_top, 1);
     M.free_stack[pos] = sid;
   }
@@ -256,7 +258,13 @@ int lm_map_index_build(lmono_ctx* ctx) {
 }
 
 // ------------------------------------------------------------------ insertion (:737-783)
-// key = type << 13 | physical slot (8191 = rejected), composite = key << 32 | index in stack
+// composite = type (1) | physical slot (13, 8191 = rejected) | cube-local voxel key (30) | index in stack (20):
+// after the sort every cube's new points are contiguous AND already in (voxel key, arrival) order, i.e.
+// the order the cube's VoxelGrid refilter needs -- no per-cube sort later
+constexpr int INS_IDX_BITS = 20;
+__device__ __forceinline__ uint32_t d_ins_group(unsigned long long c) { return (uint32_t)(c >> (30 + INS_IDX_BITS)); }   // type << 13 | slot
+__device__ __forceinline__ uint32_t d_ins_vkey(unsigned long long c) { return (uint32_t)(c >> INS_IDX_BITS) & 0x3FFFFFFFu; }
+__device__ __forceinline__ uint32_t d_ins_index(unsigned long long c) { return (uint32_t)c & ((1u << INS_IDX_BITS) - 1u); }
 __global__ void __launch_bounds__(256) k_insert_prepare(LmMapState* __restrict__ st, const float4* __restrict__ stack0,
                                                         const float4* __restrict__ stack1, float4* __restrict__ world0,
                                                         float4* __restrict__ world1, unsigned long long* __restrict__ comp,
@@ -272,11 +280,14 @@ __global__ void __launch_bounds__(256) k_insert_prepare(LmMapState* __restrict__
   int cI = d_cube_coord((double)pw.x, st->cen[0]);
   int cJ = d_cube_coord((double)pw.y, st->cen[1]);
   int cK = d_cube_coord((double)pw.z, st->cen[2]);
-  uint32_t ps = 8191u;
+  uint32_t ps = 8191u, vkey = 0u;
   if (cI >= 0 && cI < LM_GW && cJ >= 0 && cJ < LM_GH && cK >= 0 && cK < LM_GD &&
-      d_shard_keep(pw, ty == 0 ? leaf0 : leaf1, ty == 0 ? inv_leaf0 : inv_leaf1, st->shard_rank, st->shard_n))
-    ps = (uint32_t)d_phys_slot(cI - st->cen[0], cJ - st->cen[1], cK - st->cen[2]);
-  comp[e] = ((unsigned long long)(((uint32_t)ty << 13) | ps) << 32) | (uint32_t)i;
+      d_shard_keep(pw, ty == 0 ? leaf0 : leaf1, ty == 0 ? inv_leaf0 : inv_leaf1, st->shard_rank, st->shard_n)) {
+    const int g3[3] = { cI - st->cen[0], cJ - st->cen[1], cK - st->cen[2] };
+    ps = (uint32_t)d_phys_slot(g3[0], g3[1], g3[2]);
+    vkey = d_cube_voxel_key(pw, ty == 0 ? inv_leaf0 : inv_leaf1, g3);
+  }
+  comp[e] = ((unsigned long long)(((uint32_t)ty << 13) | ps) << (30 + INS_IDX_BITS)) | ((unsigned long long)vkey << INS_IDX_BITS) | (unsigned long long)i;
 }
 
 __global__ void __launch_bounds__(256) k_insert_heads(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1,
@@ -288,13 +299,13 @@ __global__ void __launch_bounds__(256) k_insert_heads(LmMapState* __restrict__ s
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   const unsigned long long me = sorted[p];
-  const uint32_t key = (uint32_t)(me >> 32);
-  if (p > 0 && (uint32_t)(sorted[p - 1] >> 32) == key) return;   // not a run head
+  const uint32_t key = d_ins_group(me);
+  if (p > 0 && d_ins_group(sorted[p - 1]) == key) return;        // not a run head
   const uint32_t ps = key & 8191u;
   if (ps == 8191u) return;                                        // outside the 21x21x11 grid: dropped (:752-754)
   const int ty = (int)(key >> 13);
   const LmMapType& M = ty == 0 ? M0 : M1;
-  const int run_end = d_lower_bound_u64(sorted, n, (unsigned long long)(key + 1u) << 32);
+  const int run_end = d_lower_bound_u64(sorted, n, (unsigned long long)(key + 1u) << (30 + INS_IDX_BITS));
   int len = run_end - p;
   int sid = M.slot_slab[ps];
   if (sid < 0) {
@@ -302,8 +313,8 @@ __global__ void __launch_bounds__(256) k_insert_heads(LmMapState* __restrict__ s
     if (top < 0) { atomicAdd(M.free_top, 1); atomicOr(&st->fault, LM_FAULT_POOL_EXHAUSTED); slot_first[ty * LM_NSLOT + ps] = p; slot_len[ty * LM_NSLOT + ps] = 0; slot_base[ty * LM_NSLOT + ps] = 0; return; }
     sid = M.free_stack[top];
     M.slot_slab[ps] = sid;
-    M.slab_n[sid] = 0; M.slab_nsorted[sid] = 0; M.slab_cur[sid] = 0;
-    float4 pw = (ty == 0 ? world0 : world1)[(uint32_t)me];
+    M.slab_n[sid] = 0; M.slab_nsorted[sid] = 0; M.slab_cur[sid] = 0; M.slab_unsorted[sid] = 0;
+    float4 pw = (ty == 0 ? world0 : world1)[d_ins_index(me)];
     M.slab_g[sid * 4 + 0] = d_cube_coord((double)pw.x, 0);
     M.slab_g[sid * 4 + 1] = d_cube_coord((double)pw.y, 0);
     M.slab_g[sid * 4 + 2] = d_cube_coord((double)pw.z, 0);
@@ -325,7 +336,7 @@ __global__ void __launch_bounds__(256) k_insert_write(LmMapType M0, LmMapType M1
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   const unsigned long long me = sorted[p];
-  const uint32_t key = (uint32_t)(me >> 32);
+  const uint32_t key = d_ins_group(me);
   const uint32_t ps = key & 8191u;
   if (ps == 8191u) return;
   const int ty = (int)(key >> 13);
@@ -334,94 +345,232 @@ __global__ void __launch_bounds__(256) k_insert_write(LmMapType M0, LmMapType M1
   if (sid < 0) return;
   const int rel = p - slot_first[ty * LM_NSLOT + ps];
   if (rel >= slot_len[ty * LM_NSLOT + ps]) return;
-  float4* dst = M.pts + ((size_t)sid * 2 + M.slab_cur[sid]) * M.cap;
-  dst[slot_base[ty * LM_NSLOT + ps] + rel] = (ty == 0 ? world0 : world1)[(uint32_t)me];
+  const size_t buf = ((size_t)sid * 2 + M.slab_cur[sid]) * M.cap + slot_base[ty * LM_NSLOT + ps] + rel;
+  M.pts[buf] = (ty == 0 ? world0 : world1)[d_ins_index(me)];
+  M.pkey[buf] = d_ins_vkey(me);
 }
 
 // ------------------------------------------------------------------ refilter (:788-801)
-// One CTA per window cube and map type.  slab = sorted voxel-unique prefix [0,ns) + tail
-// [ns,n) in arrival order.  VoxelGrid(prefix ++ tail) == merge(prefix, stable-sorted tail):
-// a voxel's members are the prefix point (if any) followed by the tail points in arrival
-// order, summed in fp32 in that order and divided by (float)count.
-#define RF_STAMP(k) do { if (stamps && threadIdx.x == 0) stamps[256 + (blockIdx.y * 75 + blockIdx.x) * 8 + (k)] = d_globaltimer(); } while (0)
-__global__ void __launch_bounds__(1024, 1) k_refilter(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, unsigned long long* __restrict__ stamps) {
+// slab = sorted voxel-unique prefix [0,ns) + tail [ns,n) of newly inserted points, already in
+// (voxel key, arrival) order (the insertion sort key carries the voxel key).
+// VoxelGrid(prefix ++ tail) == merge(prefix, tail): a voxel's members are the prefix point (if any)
+// followed by the tail points in arrival order, summed in fp32 in that order and divided by (float)count;
+// a VoxelGrid pass over the untouched part of a filtered cube is the identity.
+// The merge runs as four small kernels over (window cube, map type[, 2048-point chunk]) so that the
+// ~25 k points of a busy cube are spread over a dozen SMs instead of serialised on one:
+//   k_rf_flags   per cube: which tail runs open a NEW voxel (binary search in the prefix keys), exclusive
+//                scan -> output offsets; clears the cell histogram
+//   k_rf_merge   per chunk: prefix points shift by the new voxels sorting before them and absorb their tail
+//                run; new voxels are centroided; every output also counts into its 2 m search cell
+//   k_rf_scan    per cube: histogram -> cell starts, slab bookkeeping (ping-pong flip)
+//   k_rf_scatter per chunk: cell-sorted copy for the kNN search
+// A centroid that rounds across a voxel border breaks the "prefix is sorted" invariant (PCL would simply
+// re-voxelise): such a slab is flagged and re-voxelised as a whole by k_refilter_whole on the next pass.
+struct RfMeta { int32_t active, total_new, ns, nt, flag, cur, sid, pad; };
+
+__device__ __forceinline__ bool d_rf_slab(const LmMapState* st, const LmMapType& M, int r, int* sid) {
+  if (r >= st->valid_num) return false;
+  const int s = M.slot_slab[st->valid_slot[r]];
+  *sid = s;
+  return s >= 0;
+}
+
+__global__ void __launch_bounds__(1024, 1) k_rf_flags(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1,
+                                                      int32_t* __restrict__ nvx_all, RfMeta* __restrict__ meta_all, int nvx_stride) {
+  __shared__ int ws[33];
+  const int r = blockIdx.x, ty = blockIdx.y;
+  const LmMapType& M = ty == 0 ? M0 : M1;
+  RfMeta* meta = meta_all + ty * LM_WIN_MAX + r;
+  int sid;
+  const bool have = d_rf_slab(st, M, r, &sid);
+  const int n = have ? M.slab_n[sid] : 0;
+  const int ns = have ? M.slab_nsorted[sid] : 0;
+  const int nt = n - ns;
+  if (!have || nt == 0 || M.slab_unsorted[sid]) { if (threadIdx.x == 0) meta->active = 0; return; }
+  const int cur = M.slab_cur[sid];
+  const uint32_t* __restrict__ pkey = M.pkey + ((size_t)sid * 2 + cur) * M.cap;
+  const uint32_t* __restrict__ tkey = pkey + ns;
+  int32_t* __restrict__ nvx = nvx_all + (size_t)(ty * LM_WIN_MAX + r) * nvx_stride;
+  int32_t* cc = M.cellcount + (size_t)sid * LM_NCELL;
+  for (int c = threadIdx.x; c < LM_NCELL; c += blockDim.x) cc[c] = 0;
+  const int per = (nt + blockDim.x - 1) / blockDim.x;
+  const int b = min((int)threadIdx.x * per, nt), e = min(b + per, nt);
+  int local = 0;
+  for (int j = b; j < e; ++j) {
+    const uint32_t key = tkey[j];
+    int nv = 0;
+    if (j == 0 || tkey[j - 1] != key) {
+      const int lb = d_lower_bound_u32(pkey, ns, key);
+      nv = !(lb < ns && pkey[lb] == key);
+    }
+    nvx[j] = nv;
+    local += nv;
+  }
+  int total_new;
+  int run = d_block_exscan(local, ws, &total_new);
+  for (int j = b; j < e; ++j) { const int nv = nvx[j]; nvx[j] = (run << 1) | nv; run += nv; }
+  if (threadIdx.x == 0) {
+    if (ns + total_new > M.cap) atomicOr(&st->fault, LM_FAULT_CUBE_OVERFLOW);
+    meta->active = 1; meta->total_new = total_new; meta->ns = ns; meta->nt = nt; meta->flag = 0; meta->cur = cur; meta->sid = sid;
+  }
+}
+
+__device__ __forceinline__ void d_rf_emit(const LmMapType& M, int sid, int cur, int pos, float4 p, uint32_t key, const int* g3, LmMapState* st) {
+  if (pos >= M.cap) return;
+  const size_t o = ((size_t)sid * 2 + (cur ^ 1)) * M.cap + pos;
+  M.pts[o] = p;
+  M.pkey[o] = key;
+  int c = d_cube_cell(p, g3);
+  if (c < 0) { atomicOr(&st->fault, LM_FAULT_CELL_RANGE); c = 0; }
+  atomicAdd(&M.cellcount[(size_t)sid * LM_NCELL + c], 1);
+}
+
+__global__ void __launch_bounds__(256) k_rf_merge(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1,
+                                                  const int32_t* __restrict__ nvx_all, RfMeta* __restrict__ meta_all, int nvx_stride) {
+  const int r = blockIdx.x, ty = blockIdx.y;
+  RfMeta* meta = meta_all + ty * LM_WIN_MAX + r;
+  if (!meta->active) return;
+  const int ns = meta->ns, nt = meta->nt, total_new = meta->total_new, cur = meta->cur, sid = meta->sid;
+  const int e0 = blockIdx.z * LM_RF_CHUNK;
+  if (e0 >= ns + nt) return;
+  const LmMapType& M = ty == 0 ? M0 : M1;
+  const float4* __restrict__ src = M.pts + ((size_t)sid * 2 + cur) * M.cap;
+  const uint32_t* __restrict__ pkey = M.pkey + ((size_t)sid * 2 + cur) * M.cap;
+  const uint32_t* __restrict__ tkey = pkey + ns;
+  const int32_t* __restrict__ nvx = nvx_all + (size_t)(ty * LM_WIN_MAX + r) * nvx_stride;
+  const int g3[3] = { M.slab_g[sid * 4], M.slab_g[sid * 4 + 1], M.slab_g[sid * 4 + 2] };
+  const float il = M.inv_leaf;
+  int bad = 0;
+  for (int e = e0 + threadIdx.x; e < min(e0 + LM_RF_CHUNK, ns + nt); e += blockDim.x) {
+    if (e < ns) {
+      // prefix point: shifted by the number of new voxels sorting before it; merged if the tail hits its voxel
+      const uint32_t key = pkey[e];
+      const int lb = d_lower_bound_u32(tkey, nt, key);
+      const int before = lb < nt ? (nvx[lb] >> 1) : total_new;
+      float4 p = src[e];
+      if (lb < nt && tkey[lb] == key) {
+        float sx = p.x, sy = p.y, sz = p.z, si = p.w;
+        int cnt = 1;
+        for (int m = lb; m < nt && tkey[m] == key; ++m) {
+          const float4 t = src[ns + m];
+          sx = __fadd_rn(sx, t.x); sy = __fadd_rn(sy, t.y); sz = __fadd_rn(sz, t.z); si = __fadd_rn(si, t.w);
+          ++cnt;
+        }
+        const float c = (float)cnt;
+        p = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), __fdiv_rn(si, c));
+        bad |= d_cube_voxel_key(p, il, g3) != key;      // the centroid left its voxel
+      }
+      d_rf_emit(M, sid, cur, e + before, p, key, g3, st);
+    } else {
+      const int j = e - ns;
+      const int v = nvx[j];
+      if (!(v & 1)) continue;
+      const uint32_t key = tkey[j];
+      float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+      int cnt = 0;
+      for (int m = j; m < nt && tkey[m] == key; ++m) {
+        const float4 t = src[ns + m];
+        sx = __fadd_rn(sx, t.x); sy = __fadd_rn(sy, t.y); sz = __fadd_rn(sz, t.z); si = __fadd_rn(si, t.w);
+        ++cnt;
+      }
+      const float c = (float)cnt;
+      const float4 p = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), __fdiv_rn(si, c));
+      bad |= d_cube_voxel_key(p, il, g3) != key;
+      d_rf_emit(M, sid, cur, d_lower_bound_u32(pkey, ns, key) + (v >> 1), p, key, g3, st);
+    }
+  }
+  if (bad) meta->flag = 1;
+}
+
+__global__ void __launch_bounds__(1024, 1) k_rf_scan(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, RfMeta* __restrict__ meta_all) {
+  __shared__ int ws[33];
+  const int r = blockIdx.x, ty = blockIdx.y;
+  RfMeta* meta = meta_all + ty * LM_WIN_MAX + r;
+  if (!meta->active) return;
+  const LmMapType& M = ty == 0 ? M0 : M1;
+  const int sid = meta->sid;
+  int32_t* cc = M.cellcount + (size_t)sid * LM_NCELL;
+  uint32_t* cs = M.cellstart + (size_t)sid * (LM_NCELL + 1);
+  const int per = (LM_NCELL + blockDim.x - 1) / blockDim.x;
+  const int b = min((int)threadIdx.x * per, LM_NCELL), e = min(b + per, LM_NCELL);
+  int sum = 0;
+  for (int c = b; c < e; ++c) sum += cc[c];
+  int total;
+  int run = d_block_exscan(sum, ws, &total);
+  for (int c = b; c < e; ++c) { const int v = cc[c]; cs[c] = (uint32_t)run; cc[c] = run; run += v; }
+  if (threadIdx.x == 0) {
+    const int nn = min(meta->ns + meta->total_new, M.cap);
+    cs[LM_NCELL] = (uint32_t)nn;
+    M.slab_n[sid] = nn;
+    M.slab_nsorted[sid] = meta->flag ? 0 : nn;
+    M.slab_unsorted[sid] = meta->flag ? 1 : 0;
+    M.slab_cur[sid] = meta->cur ^ 1;
+    M.slab_dirty[sid] = 0;
+    meta->total_new = nn;         // k_rf_scatter reads the new size here
+  }
+}
+
+__global__ void __launch_bounds__(256) k_rf_scatter(LmMapType M0, LmMapType M1, const RfMeta* __restrict__ meta_all) {
+  const int r = blockIdx.x, ty = blockIdx.y;
+  const RfMeta* meta = meta_all + ty * LM_WIN_MAX + r;
+  if (!meta->active) return;
+  const int nn = meta->total_new, sid = meta->sid;
+  const int e0 = blockIdx.z * LM_RF_CHUNK;
+  if (e0 >= nn) return;
+  const LmMapType& M = ty == 0 ? M0 : M1;
+  const float4* __restrict__ src = M.pts + ((size_t)sid * 2 + (meta->cur ^ 1)) * M.cap;
+  float4* __restrict__ cp = M.cellpts + (size_t)sid * M.cap;
+  int32_t* cc = M.cellcount + (size_t)sid * LM_NCELL;
+  const int g3[3] = { M.slab_g[sid * 4], M.slab_g[sid * 4 + 1], M.slab_g[sid * 4 + 2] };
+  for (int i = e0 + threadIdx.x; i < min(e0 + LM_RF_CHUNK, nn); i += blockDim.x) {
+    float4 p = src[i];
+    int c = d_cube_cell(p, g3);
+    if (c < 0) c = 0;
+    const int pos = atomicAdd(&cc[c], 1);
+    p.w = __int_as_float(i);
+    cp[pos] = p;
+  }
+}
+
+// Whole-slab re-voxelisation of a flagged slab (rare): one CTA per window cube and map type sorts every
+// point of the slab by voxel key in shared memory and merges runs -- exactly pcl::VoxelGrid on the cube.
+__global__ void __launch_bounds__(1024, 1) k_refilter_whole(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1) {
   extern __shared__ unsigned char smem_raw[];
   unsigned long long* S = reinterpret_cast<unsigned long long*>(smem_raw);              // [LM_TAIL_TILE]
   int* NV = reinterpret_cast<int*>(smem_raw + (size_t)LM_TAIL_TILE * 8);                // [LM_TAIL_TILE]
   int* ws = reinterpret_cast<int*>(smem_raw + (size_t)LM_TAIL_TILE * 12);               // [64]
   __shared__ int s_flag;
   const int r = blockIdx.x;
-  RF_STAMP(0);
-  if (stamps && threadIdx.x == 0) { stamps[256 + (blockIdx.y * 75 + blockIdx.x) * 8 + 5] = 0; stamps[256 + (blockIdx.y * 75 + blockIdx.x) * 8 + 6] = 0; }
-  if (r >= st->valid_num) return;
   const LmMapType& M = blockIdx.y == 0 ? M0 : M1;
-  const int ps = st->valid_slot[r];
-  const int sid = M.slot_slab[ps];
-  if (sid < 0) return;
-  const int n = M.slab_n[sid];
-  const int ns = M.slab_nsorted[sid];
-  const int nt = n - ns;
-  if (nt == 0) return;                         // already filtered: VoxelGrid is the identity
-  if (stamps && threadIdx.x == 0) { stamps[256 + (blockIdx.y * 75 + blockIdx.x) * 8 + 5] = ns; stamps[256 + (blockIdx.y * 75 + blockIdx.x) * 8 + 6] = nt; }
+  int sid;
+  if (!d_rf_slab(st, M, r, &sid)) return;
+  if (!M.slab_unsorted[sid]) return;
+  const int nt = M.slab_n[sid];
+  if (nt == 0) return;
   if (nt > LM_TAIL_TILE) { if (threadIdx.x == 0) atomicOr(&st->fault, LM_FAULT_TAIL_OVERFLOW); return; }
   const int cur = M.slab_cur[sid];
   const float4* src = M.pts + ((size_t)sid * 2 + cur) * M.cap;
   float4* dst = M.pts + ((size_t)sid * 2 + (cur ^ 1)) * M.cap;
-  uint32_t* pkey = M.pkey + (size_t)sid * M.cap;
+  uint32_t* dkey = M.pkey + ((size_t)sid * 2 + (cur ^ 1)) * M.cap;
   const int g3[3] = { M.slab_g[sid * 4], M.slab_g[sid * 4 + 1], M.slab_g[sid * 4 + 2] };
   const float il = M.inv_leaf;
-
-  for (int i = threadIdx.x; i < ns; i += blockDim.x) pkey[i] = d_cube_voxel_key(src[i], il, g3);
   int np2 = 1; while (np2 < nt) np2 <<= 1;
   for (int j = threadIdx.x; j < np2; j += blockDim.x)
-    S[j] = j < nt ? (((unsigned long long)d_cube_voxel_key(src[ns + j], il, g3) << 32) | (uint32_t)j) : ~0ULL;
+    S[j] = j < nt ? (((unsigned long long)d_cube_voxel_key(src[j], il, g3) << 32) | (uint32_t)j) : ~0ULL;
   __syncthreads();
-  RF_STAMP(1);
   d_bitonic_sort(S, np2);
-  RF_STAMP(2);
-
-  // new-voxel flags and their exclusive prefix over the sorted tail
   const int per = (nt + blockDim.x - 1) / blockDim.x;
   const int b = min((int)threadIdx.x * per, nt), e = min(b + per, nt);
   int local = 0;
   for (int j = b; j < e; ++j) {
-    const uint32_t key = (uint32_t)(S[j] >> 32);
-    int nv = 0;
-    if (j == 0 || (uint32_t)(S[j - 1] >> 32) != key) {
-      int lb = d_lower_bound_u32(pkey, ns, key);
-      nv = !(lb < ns && pkey[lb] == key);
-    }
-    NV[j] = nv;
-    local += nv;
+    const int nv = (j == 0) || ((uint32_t)(S[j - 1] >> 32) != (uint32_t)(S[j] >> 32));
+    NV[j] = nv; local += nv;
   }
   int total_new;
   int run = d_block_exscan(local, ws, &total_new);
-  for (int j = b; j < e; ++j) { int nv = NV[j]; NV[j] = (run << 1) | nv; run += nv; }   // (exclusive count << 1) | flag
+  for (int j = b; j < e; ++j) { const int nv = NV[j]; NV[j] = (run << 1) | nv; run += nv; }
+  if (threadIdx.x == 0) s_flag = 0;
   __syncthreads();
-  const int n_new = ns + total_new;
-  if (n_new > M.cap) { if (threadIdx.x == 0) atomicOr(&st->fault, LM_FAULT_CUBE_OVERFLOW); }
-
-  // prefix points: shifted by the number of new voxels sorting before them; merged if the tail hits their voxel
-  for (int i = threadIdx.x; i < ns; i += blockDim.x) {
-    const uint32_t key = pkey[i];
-    const int lb = d_lower_bound_u64(S, nt, (unsigned long long)key << 32);
-    const int before = lb < nt ? (NV[lb] >> 1) : total_new;
-    float4 p = src[i];
-    if (lb < nt && (uint32_t)(S[lb] >> 32) == key) {
-      float sx = p.x, sy = p.y, sz = p.z, si = p.w;
-      int cnt = 1;
-      for (int m = lb; m < nt && (uint32_t)(S[m] >> 32) == key; ++m) {
-        float4 t = src[ns + (uint32_t)S[m]];
-        sx = __fadd_rn(sx, t.x); sy = __fadd_rn(sy, t.y); sz = __fadd_rn(sz, t.z); si = __fadd_rn(si, t.w);
-        ++cnt;
-      }
-      const float c = (float)cnt;
-      p = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), __fdiv_rn(si, c));
-    }
-    const int pos = i + before;
-    if (pos < M.cap) dst[pos] = p;
-  }
-  // new voxels
   for (int j = threadIdx.x; j < nt; j += blockDim.x) {
     const int v = NV[j];
     if (!(v & 1)) continue;
@@ -429,34 +578,26 @@ __global__ void __launch_bounds__(1024, 1) k_refilter(LmMapState* __restrict__ s
     float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
     int cnt = 0;
     for (int m = j; m < nt && (uint32_t)(S[m] >> 32) == key; ++m) {
-      float4 t = src[ns + (uint32_t)S[m]];
+      const float4 t = src[(uint32_t)S[m]];
       sx = __fadd_rn(sx, t.x); sy = __fadd_rn(sy, t.y); sz = __fadd_rn(sz, t.z); si = __fadd_rn(si, t.w);
       ++cnt;
     }
     const float c = (float)cnt;
-    const int pos = d_lower_bound_u32(pkey, ns, key) + (v >> 1);
-    if (pos < M.cap) dst[pos] = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), __fdiv_rn(si, c));
+    const float4 p = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), __fdiv_rn(si, c));
+    if (d_cube_voxel_key(p, il, g3) != key) s_flag = 1;
+    dst[v >> 1] = p; dkey[v >> 1] = key;
   }
-  if (threadIdx.x == 0) s_flag = 0;
-  __syncthreads();
-  RF_STAMP(3);
-  const int nn = min(n_new, M.cap);
-  // a centroid may round across a voxel border: verify the output is still strictly ascending,
-  // otherwise the whole slab is treated as unsorted tail next time (what PCL would do anyway).
-  for (int i = threadIdx.x + 1; i < nn; i += blockDim.x)
-    if (d_cube_voxel_key(dst[i], il, g3) <= d_cube_voxel_key(dst[i - 1], il, g3)) s_flag = 1;
   __syncthreads();
   if (threadIdx.x == 0) {
-    M.slab_n[sid] = nn;
-    M.slab_nsorted[sid] = s_flag ? 0 : nn;
+    M.slab_n[sid] = total_new;
+    M.slab_nsorted[sid] = s_flag ? 0 : total_new;
+    M.slab_unsorted[sid] = s_flag ? 1 : 0;
     M.slab_cur[sid] = cur ^ 1;
   }
   __syncthreads();
-  RF_STAMP(4);
   // rebuild the search index of this cube from the new buffer (reuses the sort scratch)
-  d_build_cell_index(M, sid, dst, nn, reinterpret_cast<uint32_t*>(smem_raw), ws, st);
+  d_build_cell_index(M, sid, dst, total_new, reinterpret_cast<uint32_t*>(smem_raw), ws, st);
   if (threadIdx.x == 0) M.slab_dirty[sid] = 0;
-  RF_STAMP(7);
 }
 
 static const int kRefilterSmem = LM_TAIL_TILE * 12 + 64 * 4;
@@ -483,7 +624,18 @@ int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf)
   }
   lm_prof_end(ctx);
   lm_prof_begin(ctx, LM_PROF_REFILTER);
-  k_refilter<<<dim3(75, 2), 1024, kRefilterSmem, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_stamps);
+  const int cap_max = ctx->map[0].cap > ctx->map[1].cap ? ctx->map[0].cap : ctx->map[1].cap;
+  const int chunks = lm_div_up(cap_max, LM_RF_CHUNK);
+  RfMeta* meta = (RfMeta*)ctx->d_rf_meta;
+  k_refilter_whole<<<dim3(LM_WIN_MAX, 2), 1024, kRefilterSmem, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1]);
+  LM_LAUNCH_CHECK();
+  k_rf_flags<<<dim3(LM_WIN_MAX, 2), 1024, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_nvx, meta, cap_max);
+  LM_LAUNCH_CHECK();
+  k_rf_merge<<<dim3(LM_WIN_MAX, 2, chunks), 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_nvx, meta, cap_max);
+  LM_LAUNCH_CHECK();
+  k_rf_scan<<<dim3(LM_WIN_MAX, 2), 1024, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], meta);
+  LM_LAUNCH_CHECK();
+  k_rf_scatter<<<dim3(LM_WIN_MAX, 2, chunks), 256, 0, ctx->stream>>>(ctx->map[0], ctx->map[1], meta);
   LM_LAUNCH_CHECK();
   lm_prof_end(ctx);
   return LMONO_OK;
@@ -491,7 +643,11 @@ int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf)
 
 int lm_map_configure_kernels(lmono_ctx* ctx) {
   LM_CUDA(cudaFuncSetAttribute(k_index_build, cudaFuncAttributeMaxDynamicSharedMemorySize, kIndexSmem));
-  LM_CUDA(cudaFuncSetAttribute(k_refilter, cudaFuncAttributeMaxDynamicSharedMemorySize, kRefilterSmem));
+  LM_CUDA(cudaFuncSetAttribute(k_refilter_whole, cudaFuncAttributeMaxDynamicSharedMemorySize, kRefilterSmem));
+  const int cap_max = ctx->map[0].cap > ctx->map[1].cap ? ctx->map[0].cap : ctx->map[1].cap;
+  LM_CUDA(cudaMalloc((void**)&ctx->d_rf_nvx, sizeof(int32_t) * (size_t)2 * LM_WIN_MAX * cap_max));
+  LM_CUDA(cudaMalloc((void**)&ctx->d_rf_meta, sizeof(RfMeta) * 2 * LM_WIN_MAX));
+  LM_CUDA(cudaMemsetAsync(ctx->d_rf_meta, 0, sizeof(RfMeta) * 2 * LM_WIN_MAX, ctx->stream));
   return LMONO_OK;
 }
 
@@ -669,6 +825,7 @@ __global__ void __launch_bounds__(256) k_import_write(LmMapState* __restrict__ s
   if (pos >= M.cap) { atomicOr(&st->fault, LM_FAULT_CUBE_OVERFLOW); return; }
   float4* dst = M.pts + ((size_t)sid * 2) * M.cap;
   dst[pos] = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), __fdiv_rn(si, c));
+  M.pkey[((size_t)sid * 2) * M.cap + pos] = (uint32_t)(vk & 0x3FFFFFFFULL);
   // last voxel of this slot fixes the slab size
   if (j >= n || (sorted[j] >> 51) != (me >> 51)) { M.slab_n[sid] = pos + 1; M.slab_nsorted[sid] = pos + 1; }
 }
@@ -687,7 +844,7 @@ __global__ void __launch_bounds__(256) k_import_verify(LmMapType M) {
   for (int i = threadIdx.x + 1; i < n; i += blockDim.x)
     if (d_cube_voxel_key(src[i], M.inv_leaf, g3) <= d_cube_voxel_key(src[i - 1], M.inv_leaf, g3)) s_flag = 1;
   __syncthreads();
-  if (threadIdx.x == 0 && s_flag) M.slab_nsorted[sid] = 0;
+  if (threadIdx.x == 0 && s_flag) { M.slab_nsorted[sid] = 0; M.slab_unsorted[sid] = 1; }
 }
 
 int lm_map_import_device(lmono_ctx* ctx, int which, const float4* d_pts, int n,

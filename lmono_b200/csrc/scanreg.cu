@@ -238,7 +238,7 @@ __device__ __forceinline__ void d_warp_sort_sector(unsigned long long* dst, cons
     const int e = lane * ITEMS + r;
     v[r] = e < len ? (((unsigned long long)__float_as_uint(curv[sp + e]) << 32) | (uint32_t)(sp + e)) : ~0ULL;
   }
-  d_bitonic_regs<ITEMS>(v, lane, 32, nullptr);
+  d_bitonic_regs<ITEMS, 32>(v, lane, nullptr);
 #pragma unroll
   for (int r = 0; r < ITEMS; ++r) dst[lane * ITEMS + r] = v[r];
 }
@@ -267,7 +267,7 @@ __device__ __forceinline__ void d_block_sort_lf(unsigned long long* xch, int n, 
     }
     v[r] = c;
   }
-  d_bitonic_regs<ITEMS>(v, threadIdx.x, SC_THREADS, xch);
+  d_bitonic_regs<ITEMS, SC_THREADS>(v, threadIdx.x, xch);
 #pragma unroll
   for (int r = 0; r < ITEMS; ++r) xch[threadIdx.x * ITEMS + r] = v[r];
   __syncthreads();

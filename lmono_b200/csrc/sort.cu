@@ -5,11 +5,11 @@
 //                  threads: 3 in-thread + 5 warp-shuffle partner distances, only 6 of the 66 stages go
 //                  through shared memory).  Small tiles on many SMs: the network is issue-bound, so
 //                  16 k keys on 8 SMs finish in a fraction of the time of 4 SMs x 4096.
-//   k_merge_ranks: one pass merges groups of 8 sorted runs: every key finds its rank = own position +
+//   k_merge_ranks: one pass merges groups of 16 sorted runs: every key finds its rank = own position +
 //                  sum over the other runs of its group of lower_bound(run, key) (keys are unique) and
 //                  scatters.  The searches over different runs are independent: four run interleaved
 //                  per thread so their (L1/L2-resident) loads overlap instead of forming one long
-//                  dependent chain.  <= 16 k keys need one pass, 2 M keys (map import) four.
+//                  dependent chain.  <= 32 k keys need one pass, 2 M keys (map import) three.
 // Used for VoxelGrid keys (PCL sorts cloud_point_index_idx, voxel_grid.hpp), cube insertion
 // order and map import.  Keys are (sort key << k | original index) composites, so the result
 // equals a STABLE sort by key -- the canonical order DESIGN.md defines in place of libstdc++'s
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_sort_tiles(LmSortSegs sg, int ds
 #pragma unroll
   for (int r = 0; r < ST_ITEMS; ++r) v[r] = s[threadIdx.x * ST_ITEMS + r];
   __syncthreads();
-  d_bitonic_regs<ST_ITEMS>(v, threadIdx.x, ST_THREADS, s);
+  d_bitonic_regs<ST_ITEMS, ST_THREADS>(v, threadIdx.x, s);
 #pragma unroll
   for (int r = 0; r < ST_ITEMS; ++r) s[threadIdx.x * ST_ITEMS + r] = v[r];
   __syncthreads();
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_sort_tiles(LmSortSegs sg, int ds
 // One merge pass: sorted runs of `run` keys (a power of two) are merged in groups of LM_MERGE_GROUP into
 // runs of LM_MERGE_GROUP * run keys.  Every key ranks itself inside the other runs of its group with
 // branch-free binary searches, four of them interleaved so their loads overlap.
-constexpr int LM_MERGE_GROUP = 8;
+constexpr int LM_MERGE_GROUP = 16;
 
 __global__ void __launch_bounds__(256) k_merge_ranks(LmSortSegs sg, int run, int src_is_tmp) {
   const int seg = blockIdx.y;
