@@ -211,6 +211,12 @@ int lmono_map_normal_eq(lmono_ctx* ctx, lmono_cloud_view corner_stack, lmono_clo
 /* pcl::VoxelGrid<PointXYZI> as configured by the reference (canonical index-order sums). */
 int lmono_voxel_grid(lmono_ctx* ctx, lmono_cloud_view in, float leaf, lmono_cloud_out* out);
 
+/* Per-launch device timing: with marks enabled every kernel launch of lmono_map_step* is followed by a CUDA
+ * event (the step then runs as plain launches, not as a graph replay).  lmono_kmarks_dump writes one line
+ * "source.cu:line count total_ms" per launch site; bench.py --kernels maps the sites to kernel names. */
+int lmono_kmarks_enable(lmono_ctx* ctx, int on);
+int lmono_kmarks_dump(lmono_ctx* ctx, char* buf, int32_t cap);
+
 /* Latency study hook: %globaltimer stamps (ns) written by instrumented kernels (slot map in DESIGN.md):
  * [0..63] the LM solve kernel of the most recent solve: 0 start, 1 armed, then per evaluation e (8 slots from
  * 8 + 8 e): factors evaluated, warp+block reduced, cluster exchanged, controller done. */

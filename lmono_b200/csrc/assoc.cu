@@ -346,11 +346,14 @@ __device__ __forceinline__ void d_knn5_group(const LmMapType& M, const LmMapStat
   }
 }
 
-// one 8-lane group per query; queries of both map types in one launch
-__global__ void __launch_bounds__(256) k_associate(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1,
+// Association = two launches.  k_assoc_knn: one 8-lane group per query (both map types in one launch), light on
+// registers so every query of a sweep is resident at once; it leaves the 5 neighbour references (or -1 when the
+// d2[4] < 1.0 gate of :584,652 fails).  k_assoc_fit: one thread per query for the fp64 line / plane fit -- with the
+// fits inside the search kernel 7 of every 8 lanes idled through the fp64 tail and its registers halved occupancy.
+__global__ void __launch_bounds__(256) k_assoc_knn(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1,
                                                    const int32_t* __restrict__ slot_valid_rank,
                                                    const float4* __restrict__ stack0, const float4* __restrict__ stack1,
-                                                   LmFactor* __restrict__ fac0, LmFactor* __restrict__ fac1) {
+                                                   int32_t* __restrict__ nnref) {
   if (!st->optimize) return;
   const int n0 = st->stack_n[0], n1 = st->stack_n[1];
   const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / GROUP;
@@ -362,20 +365,39 @@ __global__ void __launch_bounds__(256) k_associate(LmMapState* __restrict__ st, 
   const LmMapType& M = ty == 0 ? M0 : M1;
   const float4 ori = ty == 0 ? stack0[qi] : stack1[qi];
   const float4 sel = d_associate(st->q_w_curr, st->t_w_curr, ori);
-  LmFactor* f = (ty == 0 ? fac0 : fac1) + qi;
+  int32_t* out = nnref + (size_t)gid * KNN_K;
   if (st->shard_n > 1) {   // cube-sharded map: a query belongs to the rank that owns the cube it falls in
     if (lm_cube_owner(d_cube_coord((double)sel.x, 0), d_cube_coord((double)sel.y, 0), d_cube_coord((double)sel.z, 0), st->shard_n) != st->shard_rank) {
-      if (sub == 0) f->kind = -1;
+      if (sub == 0) out[0] = -1;
       return;
     }
   }
   float d[KNN_K]; int idx[KNN_K], ref[KNN_K];
   d_knn5_group(M, st, slot_valid_rank, ty, sel.x, sel.y, sel.z, sub, gmask, d, idx, ref);
   if (sub != 0) return;
-  if (!(ref[KNN_K - 1] >= 0 && d[KNN_K - 1] < 1.0f)) { f->kind = -1; return; }
+  const bool ok = ref[KNN_K - 1] >= 0 && d[KNN_K - 1] < 1.0f;
+#pragma unroll
+  for (int k = 0; k < KNN_K; ++k) out[k] = ok ? ref[k] : -1;
+}
+
+__global__ void __launch_bounds__(128) k_assoc_fit(const LmMapState* __restrict__ st, LmMapType M0, LmMapType M1,
+                                                   const float4* __restrict__ stack0, const float4* __restrict__ stack1,
+                                                   const int32_t* __restrict__ nnref,
+                                                   LmFactor* __restrict__ fac0, LmFactor* __restrict__ fac1) {
+  if (!st->optimize) return;
+  const int n0 = st->stack_n[0], n1 = st->stack_n[1];
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n0 + n1) return;
+  const int ty = gid < n0 ? 0 : 1;
+  const int qi = ty == 0 ? gid : gid - n0;
+  LmFactor* f = (ty == 0 ? fac0 : fac1) + qi;
+  const int32_t* r = nnref + (size_t)gid * KNN_K;
+  if (r[0] < 0) { f->kind = -1; return; }
+  const float4* __restrict__ cp = ty == 0 ? M0.cellpts : M1.cellpts;
   float4 nb[KNN_K];
 #pragma unroll
-  for (int k = 0; k < KNN_K; ++k) nb[k] = M.cellpts[ref[k]];
+  for (int k = 0; k < KNN_K; ++k) nb[k] = cp[r[k]];
+  const float4 ori = ty == 0 ? stack0[qi] : stack1[qi];
   LmFactor out;
   if (ty == 0) d_fit_corner(nb, ori, &out); else d_fit_surf(nb, ori, &out);
   if (out.kind < 0) { f->kind = -1; return; }
@@ -385,9 +407,11 @@ __global__ void __launch_bounds__(256) k_associate(LmMapState* __restrict__ st, 
 int lm_map_associate(lmono_ctx* ctx, int n_max_corner, int n_max_surf) {
   const int nq = n_max_corner + n_max_surf;
   if (nq <= 0) return LMONO_OK;
-  const int blocks = lm_div_up(nq * GROUP, 256);
-  k_associate<<<blocks, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_slot_valid_rank,
-                                               ctx->d_stack[0], ctx->d_stack[1], ctx->d_fac[0], ctx->d_fac[1]);
+  k_assoc_knn<<<lm_div_up(nq * GROUP, 256), 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_slot_valid_rank,
+                                                                  ctx->d_stack[0], ctx->d_stack[1], ctx->d_nnref);
+  LM_LAUNCH_CHECK();
+  k_assoc_fit<<<lm_div_up(nq, 128), 128, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_stack[0], ctx->d_stack[1],
+                                                          ctx->d_nnref, ctx->d_fac[0], ctx->d_fac[1]);
   LM_LAUNCH_CHECK();
   return LMONO_OK;
 }

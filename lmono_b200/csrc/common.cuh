@@ -151,6 +151,7 @@ struct lmono_ctx {
   float4* d_stack[2];                       // voxel-filtered features
   float4* d_world[2];                       // features in the world frame (insertion)
   LmFactor* d_fac[2];
+  int32_t* d_nnref;                         // [2 * max_feat][5] neighbour references of the association pass (-1 = gate failed)
   unsigned long long* d_sort_a; unsigned long long* d_sort_b; unsigned long long* d_sort_c;
   int32_t* d_blockcnt;                      // block counts for 2-kernel scans
   int32_t* d_tmp_i32;                       // misc int scratch [max_feature_points*2]
@@ -174,6 +175,8 @@ struct lmono_ctx {
   void* scan_state; void* odom_state; void* color_state;
   // optional per-phase CUDA-event profiler (bench.py roofline numbers)
   bool prof_on; int prof_n; int prof_tag[LM_PROF_MAX_EVENTS]; cudaEvent_t prof_ev[LM_PROF_MAX_EVENTS][2];
+  // per-launch marks (lmono_kmarks_*): one CUDA event after every kernel launch, keyed by the launch site
+  bool kmark_on; int kmark_n; cudaEvent_t* kmark_ev; const char** kmark_file; int* kmark_line;
 };
 
 static inline void lm_prof_begin(lmono_ctx* ctx, int tag) {
@@ -190,7 +193,14 @@ static inline void lm_prof_end(lmono_ctx* ctx) {
 #define LM_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { ctx->last_cuda_error = (int)_e; \
   fprintf(stderr, "[lmono_b200] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); \
   return LMONO_E_CUDA; } } while (0)
-#define LM_LAUNCH_CHECK() do { ctx->launches++; cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { ctx->last_cuda_error = (int)_e; \
+constexpr int LM_KMARK_MAX = 8192;
+static inline void lm_kmark(lmono_ctx* ctx, const char* file, int line) {
+  if (!ctx->kmark_on || ctx->kmark_n >= LM_KMARK_MAX) return;
+  ctx->kmark_file[ctx->kmark_n] = file; ctx->kmark_line[ctx->kmark_n] = line;
+  cudaEventRecord(ctx->kmark_ev[ctx->kmark_n], ctx->stream);
+  ctx->kmark_n++;
+}
+#define LM_LAUNCH_CHECK() do { ctx->launches++; lm_kmark(ctx, __FILE__, __LINE__); cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { ctx->last_cuda_error = (int)_e; \
   fprintf(stderr, "[lmono_b200] launch error %s at %s:%d\n", cudaGetErrorName(_e), __FILE__, __LINE__); return LMONO_E_CUDA; } } while (0)
 
 static inline int lm_div_up(int a, int b) { return (a + b - 1) / b; }

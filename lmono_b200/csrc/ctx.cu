@@ -97,6 +97,7 @@ extern "C" int lmono_create(int device, const lmono_params* params, void* stream
     LM_CUDA(cudaMalloc((void**)&ctx->d_world[i], nf * sizeof(float4)));
     LM_CUDA(cudaMalloc((void**)&ctx->d_fac[i], nf * sizeof(LmFactor)));
   }
+  LM_CUDA(cudaMalloc((void**)&ctx->d_nnref, sizeof(int32_t) * 5 * 2 * nf));
   const size_t nsort = (size_t)(2 * ctx->max_feat > ctx->max_sweep ? 2 * ctx->max_feat : ctx->max_sweep);
   LM_CUDA(cudaMalloc((void**)&ctx->d_sort_a, nsort * sizeof(unsigned long long)));
   LM_CUDA(cudaMalloc((void**)&ctx->d_sort_b, nsort * sizeof(unsigned long long)));
@@ -132,7 +133,7 @@ extern "C" void lmono_destroy(lmono_ctx* ctx) {
   lm_odom_free(ctx);
   lm_color_free(ctx);
   lm_map_free(ctx);
-  cudaFree(ctx->d_state); cudaFreeHost(ctx->h_state); cudaFree(ctx->d_lm); cudaFree(ctx->d_slot_valid_rank); cudaFree(ctx->d_partials); cudaFree(ctx->d_stamps); cudaFree(ctx->d_rf_nvx); cudaFree(ctx->d_rf_meta);
+  cudaFree(ctx->d_state); cudaFreeHost(ctx->h_state); cudaFree(ctx->d_lm); cudaFree(ctx->d_slot_valid_rank); cudaFree(ctx->d_partials); cudaFree(ctx->d_stamps); cudaFree(ctx->d_nnref); cudaFree(ctx->d_rf_nvx); cudaFree(ctx->d_rf_meta);
   for (int i = 0; i < 3; ++i) cudaFree(ctx->d_raw[i]);
   for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_in[i]); cudaFree(ctx->d_stack[i]); cudaFree(ctx->d_world[i]); cudaFree(ctx->d_fac[i]); }
   cudaFree(ctx->d_sort_a); cudaFree(ctx->d_sort_b); cudaFree(ctx->d_sort_c); cudaFree(ctx->d_blockcnt); cudaFree(ctx->d_tmp_i32);

@@ -92,6 +92,7 @@ static int enqueue_step(lmono_ctx* ctx, const float4* d_corner, int nc, const fl
   if (nc < 0 || ns < 0 || nc > ctx->max_feat || ns > ctx->max_feat) return LMONO_E_CAPACITY;
   int rc;
   LM_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  lm_kmark(ctx, "begin", 0);
   StepArgs a;
   for (int k = 0; k < 4; ++k) a.q[k] = wodom_curr->q[k];
   for (int k = 0; k < 3; ++k) a.t[k] = wodom_curr->t[k];
@@ -99,7 +100,7 @@ static int enqueue_step(lmono_ctx* ctx, const float4* d_corner, int nc, const fl
   k_step_args<<<1, 32, 0, ctx->stream>>>(ctx->d_state, a);
   LM_LAUNCH_CHECK();
   const int nc_cap = bucket_up(nc, ctx->max_feat), ns_cap = bucket_up(ns, ctx->max_feat);
-  if (!ctx->graphs_on || ctx->prof_on) {
+  if (!ctx->graphs_on || ctx->prof_on || ctx->kmark_on) {
     if ((rc = enqueue_body(ctx, d_corner, nc_cap, d_surf, ns_cap))) return rc;
   } else {
     LmGraphEntry* g = nullptr;
@@ -440,5 +441,44 @@ extern "C" int lmono_profile_read(lmono_ctx* ctx, float* ms /*[LM_PROF_NTAGS]*/,
     if (cudaEventElapsedTime(&e, ctx->prof_ev[i][0], ctx->prof_ev[i][1]) == cudaSuccess) { ms[ctx->prof_tag[i]] += e; counts[ctx->prof_tag[i]]++; }
   }
   ctx->prof_n = 0;
+  return LMONO_OK;
+}
+
+// ---- per-launch marks: a CUDA event after every kernel launch of the (non-graph) step, keyed by launch site ----
+extern "C" int lmono_kmarks_enable(lmono_ctx* ctx, int on) {
+  if (!ctx) return LMONO_E_ARG;
+  if (on && !ctx->kmark_ev) {
+    ctx->kmark_ev = (cudaEvent_t*)calloc(LM_KMARK_MAX, sizeof(cudaEvent_t));
+    ctx->kmark_file = (const char**)calloc(LM_KMARK_MAX, sizeof(char*));
+    ctx->kmark_line = (int*)calloc(LM_KMARK_MAX, sizeof(int));
+    for (int i = 0; i < LM_KMARK_MAX; ++i) LM_CUDA(cudaEventCreate(&ctx->kmark_ev[i]));
+  }
+  ctx->kmark_on = on != 0; ctx->kmark_n = 0;
+  return LMONO_OK;
+}
+
+// text dump "file:line count total_ms" per launch site (time from the previous mark to this one)
+extern "C" int lmono_kmarks_dump(lmono_ctx* ctx, char* buf, int32_t cap) {
+  if (!ctx || !buf || cap < 64) return LMONO_E_ARG;
+  LM_CUDA(cudaStreamSynchronize(ctx->stream));
+  struct Site { const char* f; int l; int n; double ms; };
+  static Site sites[512];
+  int ns = 0;
+  for (int i = 1; i < ctx->kmark_n; ++i) {
+    if (ctx->kmark_line[i] == 0) continue;      // "begin" marks only delimit steps
+    float e = 0.f;
+    if (cudaEventElapsedTime(&e, ctx->kmark_ev[i - 1], ctx->kmark_ev[i]) != cudaSuccess) continue;
+    int k = 0;
+    for (; k < ns; ++k) if (sites[k].f == ctx->kmark_file[i] && sites[k].l == ctx->kmark_line[i]) break;
+    if (k == ns) { if (ns == 512) continue; sites[ns].f = ctx->kmark_file[i]; sites[ns].l = ctx->kmark_line[i]; sites[ns].n = 0; sites[ns].ms = 0; ns++; }
+    sites[k].n++; sites[k].ms += e;
+  }
+  int off = 0;
+  for (int k = 0; k < ns && off < cap - 160; ++k) {
+    const char* f = strrchr(sites[k].f, '/'); f = f ? f + 1 : sites[k].f;
+    off += snprintf(buf + off, (size_t)(cap - off), "%s:%d %d %.6f\n", f, sites[k].l, sites[k].n, sites[k].ms);
+  }
+  buf[off] = 0;
+  ctx->kmark_n = 0;
   return LMONO_OK;
 }

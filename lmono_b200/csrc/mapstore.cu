@@ -93,32 +93,38 @@ __global__ void __launch_bounds__(256) k_begin_step(LmMapState* __restrict__ st,
                                                     int32_t* __restrict__ slot_valid_rank, PoseArg odom,
                                                     int use_override, double ox, double oy, double oz) {
   __shared__ unsigned clear_mask[3];
-  __shared__ int s_n[2][LM_MAX_VALID + 3];
-  __shared__ int s_own[LM_MAX_VALID + 3];
-  __shared__ int s_all;
+  __shared__ int s_n[2][128];
+  __shared__ int s_own[128];
+  __shared__ int s_all, s_center[3], s_cen[3], s_shard[2];
   if (threadIdx.x == 0) {
     if (use_override == 2) {               // pose already stored by k_step_args (CUDA-graph replay: no per-step kernel arguments)
       for (int k = 0; k < 4; ++k) odom.q[k] = st->q_wodom_curr[k];
       for (int k = 0; k < 3; ++k) odom.t[k] = st->t_wodom_curr[k];
       use_override = 0;
     }
+    double qm[4], tm[3];
+    for (int k = 0; k < 4; ++k) qm[k] = st->q_wmap_wodom[k];
+    for (int k = 0; k < 3; ++k) tm[k] = st->t_wmap_wodom[k];
+    int cen3[3] = { st->cen[0], st->cen[1], st->cen[2] };
+    s_shard[0] = st->shard_rank; s_shard[1] = st->shard_n;
     for (int k = 0; k < 4; ++k) st->q_wodom_curr[k] = odom.q[k];
     for (int k = 0; k < 3; ++k) st->t_wodom_curr[k] = odom.t[k];
-    double tw[3];
+    double tw[3], qw[4];
     if (use_override) {
       tw[0] = ox; tw[1] = oy; tw[2] = oz;
-      st->q_w_curr[0] = st->q_w_curr[1] = st->q_w_curr[2] = 0.0; st->q_w_curr[3] = 1.0;
+      qw[0] = qw[1] = qw[2] = 0.0; qw[3] = 1.0;
     } else {
-      d_qmul(st->q_wmap_wodom, odom.q, st->q_w_curr);
-      double tmp[3]; d_qrot(st->q_wmap_wodom, odom.t, tmp);
-      for (int k = 0; k < 3; ++k) tw[k] = tmp[k] + st->t_wmap_wodom[k];
+      d_qmul(qm, odom.q, qw);
+      double tmp[3]; d_qrot(qm, odom.t, tmp);
+      for (int k = 0; k < 3; ++k) tw[k] = tmp[k] + tm[k];
     }
+    for (int k = 0; k < 4; ++k) st->q_w_curr[k] = qw[k];
     for (int k = 0; k < 3; ++k) st->t_w_curr[k] = tw[k];
     const int dim[3] = { LM_GW, LM_GH, LM_GD };
     int all = 0;
     for (int a = 0; a < 3; ++a) {
       unsigned mask = 0;
-      int cen = st->cen[a];
+      int cen = cen3[a];
       int c = d_cube_coord(tw[a], cen);
       int shifts = 0;
       while (c < 3) {                    // contents move up, logical plane dim-1 is recycled
@@ -133,24 +139,15 @@ __global__ void __launch_bounds__(256) k_begin_step(LmMapState* __restrict__ st,
         if (++shifts >= dim[a]) { int need = c - (dim[a] - 4); if (need > 0) { c -= need; cen -= need; } all = 1; break; }
       }
       st->cen[a] = cen; st->center[a] = c;
+      s_cen[a] = cen; s_center[a] = c;
       clear_mask[a] = mask;
     }
     s_all = all;
-    // valid cubes in the reference's loop order (i outer, j, k inner)
-    int vn = 0;
-    for (int i = st->center[0] - 2; i <= st->center[0] + 2; i++)
-      for (int j = st->center[1] - 2; j <= st->center[1] + 2; j++)
-        for (int k = st->center[2] - 1; k <= st->center[2] + 1; k++)
-          if (i >= 0 && i < LM_GW && j >= 0 && j < LM_GH && k >= 0 && k < LM_GD) {
-            s_own[vn] = lm_cube_owner(i - st->cen[0], j - st->cen[1], k - st->cen[2], st->shard_n) == st->shard_rank;
-            st->valid_slot[vn++] = d_phys_slot(i - st->cen[0], j - st->cen[1], k - st->cen[2]);
-          }
-    st->valid_num = vn;
     st->corner_num[0] = st->corner_num[1] = st->surf_num[0] = st->surf_num[1] = 0;
     for (int s = 0; s < 2; ++s) { st->solve[s].iterations = 0; st->solve[s].num_successful = 0; st->solve[s].termination = 6; st->solve[s].num_factors = 0; st->solve[s].initial_cost = 0.0; st->solve[s].final_cost = 0.0; }
   }
   __syncthreads();
-  // free recycled planes
+  // free recycled planes (rare) and reset the slot -> window-rank table
   const unsigned mi = clear_mask[0], mj = clear_mask[1], mk = clear_mask[2];
   const int all = s_all;
   if (mi | mj | mk | (unsigned)all) {
@@ -161,26 +158,46 @@ __global__ void __launch_bounds__(256) k_begin_step(LmMapState* __restrict__ st,
   }
   for (int ps = threadIdx.x; ps < LM_NSLOT; ps += blockDim.x) slot_valid_rank[ps] = -1;
   __syncthreads();
-  const int vn = st->valid_num;
+  // valid cubes in the reference's loop order (i outer, j, k inner; :512-529), one thread per cube: the clipped
+  // window is a product of index ranges, so the rank of (i, j, k) in loop order is closed-form
+  const int i0 = max(s_center[0] - 2, 0), i1 = min(s_center[0] + 2, LM_GW - 1);
+  const int j0 = max(s_center[1] - 2, 0), j1 = min(s_center[1] + 2, LM_GH - 1);
+  const int k0 = max(s_center[2] - 1, 0), k1 = min(s_center[2] + 1, LM_GD - 1);
+  const int ni = max(i1 - i0 + 1, 0), nj = max(j1 - j0 + 1, 0), nk = max(k1 - k0 + 1, 0);
+  const int vn = ni * nj * nk;
+  if (threadIdx.x < 128) { s_n[0][threadIdx.x] = 0; s_n[1][threadIdx.x] = 0; s_own[threadIdx.x] = 0; }
   if ((int)threadIdx.x < vn) {
-    int ps = st->valid_slot[threadIdx.x];
-    slot_valid_rank[ps] = threadIdx.x;
-    int s0 = M0.slot_slab[ps], s1 = M1.slot_slab[ps];
-    s_n[0][threadIdx.x] = s0 >= 0 ? M0.slab_n[s0] : 0;
-    s_n[1][threadIdx.x] = s1 >= 0 ? M1.slab_n[s1] : 0;
+    const int r = threadIdx.x;
+    const int gi = i0 + r / (nj * nk) - s_cen[0], gj = j0 + (r / nk) % nj - s_cen[1], gk = k0 + r % nk - s_cen[2];
+    const int ps = d_phys_slot(gi, gj, gk);
+    st->valid_slot[r] = ps;
+    slot_valid_rank[ps] = r;
+    s_own[r] = lm_cube_owner(gi, gj, gk, s_shard[1]) == s_shard[0];
+    const int s0 = M0.slot_slab[ps], s1 = M1.slot_slab[ps];
+    s_n[0][r] = s0 >= 0 ? M0.slab_n[s0] : 0;
+    s_n[1][r] = s1 >= 0 ? M1.slab_n[s1] : 0;
+  }
+  if (threadIdx.x == 0) st->valid_num = vn;
+  __syncthreads();
+  // exclusive prefix of the cube sizes per map type (the :533-537 concatenation offsets): warp ty scans 4 entries per lane
+  const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (ty < 2) {
+    int v[4], own = 0, sum = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { v[u] = s_n[ty][lane * 4 + u]; sum += v[u]; own += s_own[lane * 4 + u] ? v[u] : 0; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    int run = incl - sum;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int r = lane * 4 + u; if (r <= vn) st->valid_off[ty][r] = run; run += v[u]; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) own += __shfl_xor_sync(0xffffffffu, own, o);
+    if (lane == 0) { st->from_map_n[ty] = total; st->shard_owned_n[ty] = own; s_n[ty][127] = total; }
   }
   __syncthreads();
-  if (threadIdx.x < 2) {
-    int acc = 0;
-    for (int r = 0; r < vn; ++r) { st->valid_off[threadIdx.x][r] = acc; acc += s_n[threadIdx.x][r]; }
-    st->valid_off[threadIdx.x][vn] = acc;
-    st->from_map_n[threadIdx.x] = acc;
-    int own = 0;
-    for (int r = 0; r < vn; ++r) if (s_own[r]) own += s_n[threadIdx.x][r];
-    st->shard_owned_n[threadIdx.x] = own;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) st->optimize = (st->from_map_n[0] > 10 && st->from_map_n[1] > 50) ? 1 : 0;   // :554
+  if (threadIdx.x == 0) st->optimize = (s_n[0][127] > 10 && s_n[1][127] > 50) ? 1 : 0;   // :554
 }
 
 int lm_map_begin_step(lmono_ctx* ctx, const lmono_pose* wodom_curr, const double* t_override) {
@@ -393,6 +410,8 @@ __global__ void __launch_bounds__(1024, 1) k_rf_flags(LmMapState* __restrict__ s
   int32_t* __restrict__ nvx = nvx_all + (size_t)(ty * LM_WIN_MAX + r) * nvx_stride;
   int32_t* cc = M.cellcount + (size_t)sid * LM_NCELL;
   for (int c = threadIdx.x; c < LM_NCELL; c += blockDim.x) cc[c] = 0;
+  // the L2 may be cold: one coalesced pass over the prefix keys turns the dependent binary searches below into L2 hits
+  { uint32_t acc = 0; for (int i = threadIdx.x; i < ns; i += blockDim.x) acc |= pkey[i]; if (acc == 0xFFFFFFFFu) nvx[0] = 0; }
   const int per = (nt + blockDim.x - 1) / blockDim.x;
   const int b = min((int)threadIdx.x * per, nt), e = min(b + per, nt);
   int local = 0;
@@ -483,7 +502,7 @@ __global__ void __launch_bounds__(256) k_rf_merge(LmMapState* __restrict__ st, L
 }
 
 __global__ void __launch_bounds__(1024, 1) k_rf_scan(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, RfMeta* __restrict__ meta_all) {
-  __shared__ int ws[33];
+  __shared__ int wtot[32], wbase[32];
   const int r = blockIdx.x, ty = blockIdx.y;
   RfMeta* meta = meta_all + ty * LM_WIN_MAX + r;
   if (!meta->active) return;
@@ -491,13 +510,40 @@ __global__ void __launch_bounds__(1024, 1) k_rf_scan(LmMapState* __restrict__ st
   const int sid = meta->sid;
   int32_t* cc = M.cellcount + (size_t)sid * LM_NCELL;
   uint32_t* cs = M.cellstart + (size_t)sid * (LM_NCELL + 1);
-  const int per = (LM_NCELL + blockDim.x - 1) / blockDim.x;
-  const int b = min((int)threadIdx.x * per, LM_NCELL), e = min(b + per, LM_NCELL);
-  int sum = 0;
-  for (int c = b; c < e; ++c) sum += cc[c];
-  int total;
-  int run = d_block_exscan(sum, ws, &total);
-  for (int c = b; c < e; ++c) { const int v = cc[c]; cs[c] = (uint32_t)run; cc[c] = run; run += v; }
+  // each warp owns a contiguous segment and walks it 32 cells at a time: coalesced loads, values kept in registers
+  constexpr int SEG = (LM_NCELL + 31) / 32;          // 550 cells per warp
+  constexpr int ITERS = (SEG + 31) / 32;             // 18
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int seg0 = wid * SEG, seg1 = min(seg0 + SEG, LM_NCELL);
+  int vals[ITERS];
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) { const int c = seg0 + it * 32 + lane; vals[it] = c < seg1 ? cc[c] : 0; }
+  int carry = 0;
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    int incl = vals[it];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const int tot = __shfl_sync(0xffffffffu, incl, 31);
+    vals[it] = carry + incl - vals[it];               // exclusive within the warp segment
+    carry += tot;
+  }
+  if (lane == 0) wtot[wid] = carry;
+  __syncthreads();
+  if (wid == 0) {
+    const int v = wtot[lane];
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    wbase[lane] = incl - v;
+  }
+  __syncthreads();
+  const int base = wbase[wid];
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int c = seg0 + it * 32 + lane;
+    if (c < seg1) { const int v = base + vals[it]; cs[c] = (uint32_t)v; cc[c] = v; }
+  }
   if (threadIdx.x == 0) {
     const int nn = min(meta->ns + meta->total_new, M.cap);
     cs[LM_NCELL] = (uint32_t)nn;
