@@ -21,7 +21,7 @@ constexpr int LM_NCELL = LM_CELLS_AXIS * LM_CELLS_AXIS * LM_CELLS_AXIS;   // 175
 constexpr int LM_SORT_TILE = 2048;                // elements per CTA in the global tile sort
 constexpr int LM_SORT_MAXSEG = 2;                 // independent segments sorted by one pair of launches
 constexpr int LM_TAIL_TILE = 16384;               // max points of a slab the whole-slab fallback refilter can re-voxelise (smem sort)
-constexpr int LM_RF_CHUNK = 2048;                 // points per CTA in the chunked refilter kernels
+constexpr int LM_RF_CHUNK = 1024;                 // points per CTA in the chunked refilter kernels
 constexpr int LM_WIN_MAX = 75;                    // cubes of the 5x5x3 window
 
 // device fault bits (LmMapState::fault)
@@ -159,6 +159,7 @@ struct lmono_ctx {
   float4* d_full;                           // full-res sweep
   int32_t* d_slot_first; int32_t* d_slot_base; // insertion run tables [LM_NSLOT]
   int32_t* d_rf_nvx;                        // refilter scratch [2][75][max cap]: (new voxels before j) << 1 | (j starts a new voxel)
+  int32_t* d_rf_work;                       // [4 + 2*75*chunks]: chunk work list of the cubes being refiltered
   int32_t* d_rf_meta;                       // [2][75][8]: active, total_new, ns, nt, unsorted flag, cur
   float4* d_export; size_t export_cap;      // export / import staging
   int32_t* d_export_off;                    // [LM_NSLOT+1]
@@ -436,6 +437,7 @@ __device__ __forceinline__ int d_lower_bound_u32(const uint32_t* sorted, int n, 
 // sort.cu: segment s sorts *n[s] keys in[off[s] ...] -> out[off[s] ...] (tmp[off[s] ...] is scratch)
 struct LmSortSegs { const unsigned long long* in; unsigned long long* tmp; unsigned long long* out; int off[LM_SORT_MAXSEG]; const int32_t* n[LM_SORT_MAXSEG]; };
 int lm_sort_u64_segs(lmono_ctx* ctx, const LmSortSegs& sg, int nseg, const int* n_max);
+int lm_sort_configure(lmono_ctx* ctx);
 // sorts n (device int *n_dev, <= n_max) unique 64-bit keys ascending: in -> out (tmp is scratch)
 int lm_sort_u64(lmono_ctx* ctx, const unsigned long long* in, unsigned long long* tmp, unsigned long long* out,
                 const int32_t* n_dev, int n_max);

@@ -395,6 +395,21 @@ __global__ void k_lm_control(LmLmState* __restrict__ lm, LmProblem P, const doub
 constexpr int LMC_THREADS = 256;
 constexpr int LMC_CLUSTER = 16;   // max cluster size (non-portable, opt-in); 8 is used where 16 cannot be scheduled
 
+// factor cache in shared memory: four 16-byte planes so that consecutive threads touch consecutive words
+constexpr int LMC_CACHE = 8 * LMC_THREADS;      // factors per CTA (128 KB): 32 k factors over a 16-CTA cluster
+__device__ __forceinline__ void d_cache_store(uint4* c, int slot, const LmFactor& f) {
+  const uint4* w = reinterpret_cast<const uint4*>(&f);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) c[k * LMC_CACHE + slot] = w[k];
+}
+__device__ __forceinline__ LmFactor d_cache_load(const uint4* c, int slot) {
+  LmFactor f;
+  uint4* w = reinterpret_cast<uint4*>(&f);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) w[k] = c[k * LMC_CACHE + slot];
+  return f;
+}
+
 // after the call lane L holds the warp-wide sum of element L (L < 32) in v[0]
 __device__ __forceinline__ void d_warp_transpose_reduce32(double (&v)[32], int lane) {
 #pragma unroll
@@ -418,6 +433,7 @@ k_lm_solve_cluster(LmLmState* __restrict__ lm_g, LmProblem P, int max_iter, int 
   __shared__ double s_all[2][LMC_CLUSTER][32];      // [parity][source CTA][element], written remotely
   __shared__ double s_fin[32];
   __shared__ LmLmState s_lm;
+  extern __shared__ uint4 s_cache[];                // [4][LMC_CACHE]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   LM_STAMP(stamps, 0);
   const int n0 = *P.n0, n1 = *P.n1;
@@ -452,18 +468,23 @@ k_lm_solve_cluster(LmLmState* __restrict__ lm_g, LmProblem P, int max_iter, int 
     double acc[32];
 #pragma unroll
     for (int k = 0; k < 32; ++k) acc[k] = 0.0;
-    {   // grid-stride over the cluster, next factor's 64 B in flight while the current one is evaluated
+    {   // grid-stride over the cluster.  The first evaluation streams the factors from global memory (next
+        // factor's 64 B in flight while the current one is evaluated) and parks them in shared memory; the
+        // other evaluations of the solve re-read them from there instead of paying L2 latency per factor.
       const int stride = csize * LMC_THREADS, nf = n0 + n1;
       int i = crank * LMC_THREADS + threadIdx.x;
+      int slot = threadIdx.x;
       LmFactor f;
-      if (i < nf) f = i < n0 ? fac0[i] : fac1[i - n0];
+      const bool first = (it == 0);
+      if (i < nf) { if (first || slot >= LMC_CACHE) f = i < n0 ? fac0[i] : fac1[i - n0]; else f = d_cache_load(s_cache, slot); }
       while (i < nf) {
-        const int inext = i + stride;
+        const int inext = i + stride, snext = slot + LMC_THREADS;
         LmFactor fn;
-        if (inext < nf) fn = inext < n0 ? fac0[inext] : fac1[inext - n0];
+        if (inext < nf) { if (first || snext >= LMC_CACHE) fn = inext < n0 ? fac0[inext] : fac1[inext - n0]; else fn = d_cache_load(s_cache, snext); }
+        if (first && slot < LMC_CACHE) d_cache_store(s_cache, slot, f);
         if (f.kind >= 0) { if (i < n0) acc[28] += 1.0; else acc[29] += 1.0; }
         d_eval_factor(f, q, t, acc);
-        f = fn; i = inext;
+        f = fn; i = inext; slot = snext;
       }
     }
     LM_STAMP(stamps, 8 + 8 * it);
@@ -523,15 +544,17 @@ static bool lm_use_launch_per_eval() {
   return v == 1;
 }
 
+constexpr int LMC_SMEM = 4 * LMC_CACHE * 16;
 // largest cluster the device schedules for the solve kernel: 16 (opt-in, non-portable) if possible, else 8
 static int lm_cluster_size(lmono_ctx* ctx) {
   static int cached[64] = { 0 };
   const int d = ctx->device & 63;
   if (cached[d]) return cached[d];
   int best = 8;
+  if (cudaFuncSetAttribute(k_lm_solve_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, LMC_SMEM) != cudaSuccess) return -1;
   if (cudaFuncSetAttribute(k_lm_solve_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(LMC_CLUSTER); cfg.blockDim = dim3(LMC_THREADS);
+    cfg.gridDim = dim3(LMC_CLUSTER); cfg.blockDim = dim3(LMC_THREADS); cfg.dynamicSmemBytes = LMC_SMEM;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = LMC_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
@@ -557,7 +580,7 @@ int lm_solve_problem(lmono_ctx* ctx, const LmProblem& P, int n_max, int max_iter
     const int cs = lm_cluster_size(ctx);
     if (cs < 0) return LMONO_E_CUDA;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(cs); cfg.blockDim = dim3(LMC_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
+    cfg.gridDim = dim3(cs); cfg.blockDim = dim3(LMC_THREADS); cfg.dynamicSmemBytes = LMC_SMEM; cfg.stream = ctx->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;

@@ -375,8 +375,8 @@ __global__ void __launch_bounds__(256) k_insert_write(LmMapType M0, LmMapType M1
 // a VoxelGrid pass over the untouched part of a filtered cube is the identity.
 // The merge runs as four small kernels over (window cube, map type[, 2048-point chunk]) so that the
 // ~25 k points of a busy cube are spread over a dozen SMs instead of serialised on one:
-//   k_rf_flags   per cube: which tail runs open a NEW voxel (binary search in the prefix keys), exclusive
-//                scan -> output offsets; clears the cell histogram
+//   k_rf_tailflags per tail point: does its key run open a NEW voxel (binary search in the prefix keys)?
+//   k_rf_flags   per cube: exclusive scan of those flags -> output offsets; clears the cell histogram
 //   k_rf_merge   per chunk: prefix points shift by the new voxels sorting before them and absorb their tail
 //                run; new voxels are centroided; every output also counts into its 2 m search cell
 //   k_rf_scan    per cube: histogram -> cell starts, slab bookkeeping (ping-pong flip)
@@ -384,6 +384,8 @@ __global__ void __launch_bounds__(256) k_insert_write(LmMapType M0, LmMapType M1
 // A centroid that rounds across a voxel border breaks the "prefix is sorted" invariant (PCL would simply
 // re-voxelise): such a slab is flagged and re-voxelised as a whole by k_refilter_whole on the next pass.
 struct RfMeta { int32_t active, total_new, ns, nt, flag, cur, sid, pad; };
+// chunk work list of the active cubes: entry = type << 24 | window rank << 16 | chunk; [0] of the counter array = length
+constexpr int RF_GRID = 592;
 
 __device__ __forceinline__ bool d_rf_slab(const LmMapState* st, const LmMapType& M, int r, int* sid) {
   if (r >= st->valid_num) return false;
@@ -392,9 +394,35 @@ __device__ __forceinline__ bool d_rf_slab(const LmMapState* st, const LmMapType&
   return s >= 0;
 }
 
+// tail element j opens a NEW voxel iff it is the first of its key run and the key is absent from the prefix:
+// one thread per tail element, so the (dependent, ~15-step) binary searches of a cube spread over many SMs
+__global__ void __launch_bounds__(256) k_rf_tailflags(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1,
+                                                      int32_t* __restrict__ nvx_all, int nvx_stride) {
+  const int r = blockIdx.x, ty = blockIdx.y;
+  const LmMapType& M = ty == 0 ? M0 : M1;
+  int sid;
+  if (!d_rf_slab(st, M, r, &sid)) return;
+  const int n = M.slab_n[sid], ns = M.slab_nsorted[sid], nt = n - ns;
+  if (nt == 0 || M.slab_unsorted[sid]) return;
+  const uint32_t* __restrict__ pkey = M.pkey + ((size_t)sid * 2 + M.slab_cur[sid]) * M.cap;
+  const uint32_t* __restrict__ tkey = pkey + ns;
+  for (int j = blockIdx.z * blockDim.x + threadIdx.x; j < nt; j += gridDim.z * blockDim.x) {
+    const uint32_t key = tkey[j];
+    int nv = 0;
+    if (j == 0 || tkey[j - 1] != key) {
+      const int lb = d_lower_bound_u32(pkey, ns, key);
+      nv = !(lb < ns && pkey[lb] == key);
+    }
+    nvx_all[(size_t)(ty * LM_WIN_MAX + r) * nvx_stride + j] = nv;
+  }
+}
+
+// per cube: exclusive scan of the new-voxel flags -> output offsets; clears the cell histogram; arms the meta record
 __global__ void __launch_bounds__(1024, 1) k_rf_flags(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1,
-                                                      int32_t* __restrict__ nvx_all, RfMeta* __restrict__ meta_all, int nvx_stride) {
+                                                      int32_t* __restrict__ nvx_all, RfMeta* __restrict__ meta_all, int nvx_stride,
+                                                      int32_t* __restrict__ work_n, int32_t* __restrict__ work) {
   __shared__ int ws[33];
+  __shared__ int s_wbase;
   const int r = blockIdx.x, ty = blockIdx.y;
   const LmMapType& M = ty == 0 ? M0 : M1;
   RfMeta* meta = meta_all + ty * LM_WIN_MAX + r;
@@ -405,33 +433,28 @@ __global__ void __launch_bounds__(1024, 1) k_rf_flags(LmMapState* __restrict__ s
   const int nt = n - ns;
   if (!have || nt == 0 || M.slab_unsorted[sid]) { if (threadIdx.x == 0) meta->active = 0; return; }
   const int cur = M.slab_cur[sid];
-  const uint32_t* __restrict__ pkey = M.pkey + ((size_t)sid * 2 + cur) * M.cap;
-  const uint32_t* __restrict__ tkey = pkey + ns;
   int32_t* __restrict__ nvx = nvx_all + (size_t)(ty * LM_WIN_MAX + r) * nvx_stride;
   int32_t* cc = M.cellcount + (size_t)sid * LM_NCELL;
   for (int c = threadIdx.x; c < LM_NCELL; c += blockDim.x) cc[c] = 0;
-  // the L2 may be cold: one coalesced pass over the prefix keys turns the dependent binary searches below into L2 hits
-  { uint32_t acc = 0; for (int i = threadIdx.x; i < ns; i += blockDim.x) acc |= pkey[i]; if (acc == 0xFFFFFFFFu) nvx[0] = 0; }
-  const int per = (nt + blockDim.x - 1) / blockDim.x;
-  const int b = min((int)threadIdx.x * per, nt), e = min(b + per, nt);
-  int local = 0;
-  for (int j = b; j < e; ++j) {
-    const uint32_t key = tkey[j];
-    int nv = 0;
-    if (j == 0 || tkey[j - 1] != key) {
-      const int lb = d_lower_bound_u32(pkey, ns, key);
-      nv = !(lb < ns && pkey[lb] == key);
-    }
-    nvx[j] = nv;
-    local += nv;
+  // chunked scan, coalesced: 1024 flags per round with a running carry
+  int carry = 0, total_new = 0;
+  for (int j0 = 0; j0 < nt; j0 += blockDim.x) {
+    const int j = j0 + threadIdx.x;
+    const int nv = j < nt ? nvx[j] : 0;
+    int tot;
+    const int ex = d_block_exscan(nv, ws, &tot);
+    if (j < nt) nvx[j] = ((carry + ex) << 1) | nv;
+    carry += tot;
   }
-  int total_new;
-  int run = d_block_exscan(local, ws, &total_new);
-  for (int j = b; j < e; ++j) { const int nv = nvx[j]; nvx[j] = (run << 1) | nv; run += nv; }
+  total_new = carry;
   if (threadIdx.x == 0) {
     if (ns + total_new > M.cap) atomicOr(&st->fault, LM_FAULT_CUBE_OVERFLOW);
     meta->active = 1; meta->total_new = total_new; meta->ns = ns; meta->nt = nt; meta->flag = 0; meta->cur = cur; meta->sid = sid;
+    s_wbase = atomicAdd(work_n, (ns + nt + LM_RF_CHUNK - 1) / LM_RF_CHUNK);
   }
+  __syncthreads();
+  const int nch = (ns + nt + LM_RF_CHUNK - 1) / LM_RF_CHUNK;
+  for (int c = threadIdx.x; c < nch; c += blockDim.x) work[s_wbase + c] = (ty << 24) | (r << 16) | c;
 }
 
 __device__ __forceinline__ void d_rf_emit(const LmMapType& M, int sid, int cur, int pos, float4 p, uint32_t key, const int* g3, LmMapState* st) {
@@ -445,13 +468,16 @@ __device__ __forceinline__ void d_rf_emit(const LmMapType& M, int sid, int cur, 
 }
 
 __global__ void __launch_bounds__(256) k_rf_merge(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1,
-                                                  const int32_t* __restrict__ nvx_all, RfMeta* __restrict__ meta_all, int nvx_stride) {
-  const int r = blockIdx.x, ty = blockIdx.y;
+                                                  const int32_t* __restrict__ nvx_all, RfMeta* __restrict__ meta_all, int nvx_stride,
+                                                  const int32_t* __restrict__ work_n, const int32_t* __restrict__ work) {
+ const int nwork = *work_n;
+ for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+  const int we = work[w];
+  const int ty = we >> 24, r = (we >> 16) & 0xFF;
   RfMeta* meta = meta_all + ty * LM_WIN_MAX + r;
-  if (!meta->active) return;
   const int ns = meta->ns, nt = meta->nt, total_new = meta->total_new, cur = meta->cur, sid = meta->sid;
-  const int e0 = blockIdx.z * LM_RF_CHUNK;
-  if (e0 >= ns + nt) return;
+  const int e0 = (we & 0xFFFF) * LM_RF_CHUNK;
+  if (e0 >= ns + nt) continue;
   const LmMapType& M = ty == 0 ? M0 : M1;
   const float4* __restrict__ src = M.pts + ((size_t)sid * 2 + cur) * M.cap;
   const uint32_t* __restrict__ pkey = M.pkey + ((size_t)sid * 2 + cur) * M.cap;
@@ -499,6 +525,7 @@ __global__ void __launch_bounds__(256) k_rf_merge(LmMapState* __restrict__ st, L
     }
   }
   if (bad) meta->flag = 1;
+ }
 }
 
 __global__ void __launch_bounds__(1024, 1) k_rf_scan(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, RfMeta* __restrict__ meta_all) {
@@ -556,13 +583,16 @@ __global__ void __launch_bounds__(1024, 1) k_rf_scan(LmMapState* __restrict__ st
   }
 }
 
-__global__ void __launch_bounds__(256) k_rf_scatter(LmMapType M0, LmMapType M1, const RfMeta* __restrict__ meta_all) {
-  const int r = blockIdx.x, ty = blockIdx.y;
+__global__ void __launch_bounds__(256) k_rf_scatter(LmMapType M0, LmMapType M1, const RfMeta* __restrict__ meta_all,
+                                                    const int32_t* __restrict__ work_n, const int32_t* __restrict__ work) {
+ const int nwork = *work_n;
+ for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+  const int we = work[w];
+  const int ty = we >> 24, r = (we >> 16) & 0xFF;
   const RfMeta* meta = meta_all + ty * LM_WIN_MAX + r;
-  if (!meta->active) return;
   const int nn = meta->total_new, sid = meta->sid;
-  const int e0 = blockIdx.z * LM_RF_CHUNK;
-  if (e0 >= nn) return;
+  const int e0 = (we & 0xFFFF) * LM_RF_CHUNK;
+  if (e0 >= nn) continue;
   const LmMapType& M = ty == 0 ? M0 : M1;
   const float4* __restrict__ src = M.pts + ((size_t)sid * 2 + (meta->cur ^ 1)) * M.cap;
   float4* __restrict__ cp = M.cellpts + (size_t)sid * M.cap;
@@ -576,17 +606,19 @@ __global__ void __launch_bounds__(256) k_rf_scatter(LmMapType M0, LmMapType M1, 
     p.w = __int_as_float(i);
     cp[pos] = p;
   }
+ }
 }
 
 // Whole-slab re-voxelisation of a flagged slab (rare): one CTA per window cube and map type sorts every
 // point of the slab by voxel key in shared memory and merges runs -- exactly pcl::VoxelGrid on the cube.
-__global__ void __launch_bounds__(1024, 1) k_refilter_whole(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1) {
+__global__ void __launch_bounds__(1024, 1) k_refilter_whole(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, int32_t* __restrict__ work_n) {
   extern __shared__ unsigned char smem_raw[];
   unsigned long long* S = reinterpret_cast<unsigned long long*>(smem_raw);              // [LM_TAIL_TILE]
   int* NV = reinterpret_cast<int*>(smem_raw + (size_t)LM_TAIL_TILE * 8);                // [LM_TAIL_TILE]
   int* ws = reinterpret_cast<int*>(smem_raw + (size_t)LM_TAIL_TILE * 12);               // [64]
   __shared__ int s_flag;
   const int r = blockIdx.x;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *work_n = 0;      // first kernel of the refilter phase
   const LmMapType& M = blockIdx.y == 0 ? M0 : M1;
   int sid;
   if (!d_rf_slab(st, M, r, &sid)) return;
@@ -671,17 +703,19 @@ int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf)
   lm_prof_end(ctx);
   lm_prof_begin(ctx, LM_PROF_REFILTER);
   const int cap_max = ctx->map[0].cap > ctx->map[1].cap ? ctx->map[0].cap : ctx->map[1].cap;
-  const int chunks = lm_div_up(cap_max, LM_RF_CHUNK);
   RfMeta* meta = (RfMeta*)ctx->d_rf_meta;
-  k_refilter_whole<<<dim3(LM_WIN_MAX, 2), 1024, kRefilterSmem, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1]);
+  int32_t* work_n = ctx->d_rf_work; int32_t* work = ctx->d_rf_work + 4;
+  k_refilter_whole<<<dim3(LM_WIN_MAX, 2), 1024, kRefilterSmem, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], work_n);
   LM_LAUNCH_CHECK();
-  k_rf_flags<<<dim3(LM_WIN_MAX, 2), 1024, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_nvx, meta, cap_max);
+  k_rf_tailflags<<<dim3(LM_WIN_MAX, 2, 8), 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_nvx, cap_max);
   LM_LAUNCH_CHECK();
-  k_rf_merge<<<dim3(LM_WIN_MAX, 2, chunks), 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_nvx, meta, cap_max);
+  k_rf_flags<<<dim3(LM_WIN_MAX, 2), 1024, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_nvx, meta, cap_max, work_n, work);
+  LM_LAUNCH_CHECK();
+  k_rf_merge<<<RF_GRID, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_nvx, meta, cap_max, work_n, work);
   LM_LAUNCH_CHECK();
   k_rf_scan<<<dim3(LM_WIN_MAX, 2), 1024, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], meta);
   LM_LAUNCH_CHECK();
-  k_rf_scatter<<<dim3(LM_WIN_MAX, 2, chunks), 256, 0, ctx->stream>>>(ctx->map[0], ctx->map[1], meta);
+  k_rf_scatter<<<RF_GRID, 256, 0, ctx->stream>>>(ctx->map[0], ctx->map[1], meta, work_n, work);
   LM_LAUNCH_CHECK();
   lm_prof_end(ctx);
   return LMONO_OK;
@@ -693,6 +727,7 @@ int lm_map_configure_kernels(lmono_ctx* ctx) {
   const int cap_max = ctx->map[0].cap > ctx->map[1].cap ? ctx->map[0].cap : ctx->map[1].cap;
   LM_CUDA(cudaMalloc((void**)&ctx->d_rf_nvx, sizeof(int32_t) * (size_t)2 * LM_WIN_MAX * cap_max));
   LM_CUDA(cudaMalloc((void**)&ctx->d_rf_meta, sizeof(RfMeta) * 2 * LM_WIN_MAX));
+  LM_CUDA(cudaMalloc((void**)&ctx->d_rf_work, sizeof(int32_t) * (4 + (size_t)2 * LM_WIN_MAX * (lm_div_up(cap_max, LM_RF_CHUNK) + 1))));
   LM_CUDA(cudaMemsetAsync(ctx->d_rf_meta, 0, sizeof(RfMeta) * 2 * LM_WIN_MAX, ctx->stream));
   return LMONO_OK;
 }

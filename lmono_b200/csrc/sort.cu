@@ -16,9 +16,9 @@
 // unstable std::sort.
 #include "common.cuh"
 
-constexpr int ST_THREADS = 256;
+constexpr int ST_THREADS = 512;
 constexpr int ST_ITEMS = LM_SORT_TILE / ST_THREADS;
-static_assert(LM_SORT_TILE == 2048 && ST_ITEMS == 8, "tile geometry");
+static_assert(LM_SORT_TILE == 2048 && ST_ITEMS == 4, "tile geometry");
 
 __global__ void __launch_bounds__(ST_THREADS) k_sort_tiles(LmSortSegs sg, int dst_is_tmp) {
   __shared__ unsigned long long s[LM_SORT_TILE];
@@ -82,6 +82,41 @@ __global__ void __launch_bounds__(256) k_merge_ranks(LmSortSegs sg, int run, int
   }
 }
 
+// Single-pass variant for n <= LM_MERGE_SMEM_RUNS runs (every per-sweep sort): a dependent chain of ~40 L2
+// accesses per key is what the global-memory searches cost (~0.15 us each on B200), so each CTA first copies
+// ALL runs of its segment into shared memory (<= 12 x 16 KB, coalesced, one L2 pass) and ranks its 1024 keys
+// against them there (~30-cycle accesses).
+constexpr int LM_MERGE_SMEM_RUNS = 12;
+constexpr int MS_THREADS = 1024;
+
+__global__ void __launch_bounds__(MS_THREADS, 1) k_merge_ranks_smem(LmSortSegs sg, int src_is_tmp) {
+  extern __shared__ unsigned long long s_runs[];        // [nruns][LM_SORT_TILE]
+  const int seg = blockIdx.y;
+  const int n = *sg.n[seg];
+  const int e0 = blockIdx.x * MS_THREADS;
+  if (e0 >= n) return;
+  const unsigned long long* __restrict__ src = (src_is_tmp ? sg.tmp : sg.out) + sg.off[seg];
+  unsigned long long* __restrict__ dst = (src_is_tmp ? sg.out : sg.tmp) + sg.off[seg];
+  const int nruns = (n + LM_SORT_TILE - 1) / LM_SORT_TILE;
+  for (int i = threadIdx.x; i < nruns * LM_SORT_TILE; i += MS_THREADS) s_runs[i] = i < n ? src[i] : ~0ULL;
+  __syncthreads();
+  const int e = e0 + threadIdx.x;
+  if (e >= n) return;
+  const unsigned long long key = s_runs[e];
+  const int my_run = e / LM_SORT_TILE;
+  int rank = e - my_run * LM_SORT_TILE;
+  for (int t = 0; t < nruns; ++t) {
+    if (t == my_run) continue;
+    const unsigned long long* a = s_runs + t * LM_SORT_TILE;     // padded with ~0ULL: no length checks needed
+    int pos = 0;
+#pragma unroll
+    for (int s = LM_SORT_TILE / 2; s > 0; s >>= 1) if (a[pos + s - 1] < key) pos += s;
+    pos += (a[pos] < key);                                        // tile of 2048: 11 halvings + the last element
+    rank += pos;
+  }
+  dst[rank] = key;
+}
+
 static int merge_passes(int n_max) {
   int p = 0;
   for (long long run = LM_SORT_TILE; run < n_max; run *= LM_MERGE_GROUP) ++p;
@@ -93,6 +128,13 @@ int lm_sort_u64_segs(lmono_ctx* ctx, const LmSortSegs& sg, int nseg, const int* 
   for (int s = 0; s < nseg; ++s) mx = n_max[s] > mx ? n_max[s] : mx;
   if (mx <= 0 || nseg <= 0) return LMONO_OK;
   const int ntiles = lm_div_up(mx, LM_SORT_TILE);
+  if (ntiles > 1 && ntiles <= LM_MERGE_SMEM_RUNS) {
+    k_sort_tiles<<<dim3(ntiles, nseg), ST_THREADS, 0, ctx->stream>>>(sg, 1);
+    LM_LAUNCH_CHECK();
+    k_merge_ranks_smem<<<dim3(lm_div_up(mx, MS_THREADS), nseg), MS_THREADS, (size_t)ntiles * LM_SORT_TILE * 8, ctx->stream>>>(sg, 1);
+    LM_LAUNCH_CHECK();
+    return LMONO_OK;
+  }
   const int passes = merge_passes(mx);
   // buffers alternate tmp <-> out per pass and the last pass must land in `out`
   int cur_is_tmp = (passes & 1) ? 1 : 0;
@@ -113,4 +155,9 @@ int lm_sort_u64(lmono_ctx* ctx, const unsigned long long* in, unsigned long long
   sg.in = in; sg.tmp = tmp; sg.out = out;
   for (int s = 0; s < LM_SORT_MAXSEG; ++s) { sg.off[s] = 0; sg.n[s] = n_dev; }
   return lm_sort_u64_segs(ctx, sg, 1, &n_max);
+}
+
+int lm_sort_configure(lmono_ctx* ctx) {
+  LM_CUDA(cudaFuncSetAttribute(k_merge_ranks_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_MERGE_SMEM_RUNS * LM_SORT_TILE * 8));
+  return LMONO_OK;
 }

@@ -111,8 +111,9 @@ __global__ void __launch_bounds__(VW_THREADS) k_vg_write(VgSegs sg, VgParams* __
   } else {
     // heads before this block
     int before = 0;
-    for (int i = threadIdx.x; i < base; i += VW_THREADS)
-      before += (i == 0) || ((sorted[i] >> VG_IDX_BITS) != (sorted[i - 1] >> VG_IDX_BITS));
+#pragma unroll 8
+    for (int i = threadIdx.x; i < base; i += VW_THREADS)          // independent loads: keep 16 in flight
+      before += (i == 0) || ((sorted[i] >> VG_IDX_BITS) != (sorted[i > 0 ? i - 1 : 0] >> VG_IDX_BITS));
     int total_before;
     d_block_exscan(before, ws, &total_before);
     // my VW_ITEMS consecutive positions
