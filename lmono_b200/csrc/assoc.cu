@@ -275,25 +275,29 @@ __device__ __forceinline__ void d_knn5_group(const LmMapType& M, const LmMapStat
 #pragma unroll
   for (int k = 0; k < KNN_K; ++k) { bd[k] = FLT_MAX; bi[k] = 0x7fffffff; br[k] = -1; }
 
-  // per axis: up to 3 (cube, local cell) pairs
-  int f[3] = { (int)floorf(qx), (int)floorf(qy), (int)floorf(qz) };
-  int pg[3][3], pc[3][3], np[3];
+  // per axis: the floors f-1..f+1 fall in the two cells c0 = (f-1)>>1 and c1 = c0 + 1; a cell belongs to one cube,
+  // or to two when it straddles a 50 m border (at most one of c0 / c1 does): 2 or 3 (cube, local cell) pairs,
+  // kept in scalar registers (no dynamically indexed arrays -> no local memory)
+  const int fq[3] = { (int)floorf(qx), (int)floorf(qy), (int)floorf(qz) };
+  int e0[3], e1[3], e2[3], np[3];       // packed (cube << 8 | local cell)
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    np[a] = 0;
-    const int c0 = (f[a] - 1) >> 1, c1 = (f[a] + 1) >> 1;
-#pragma unroll
-    for (int w = 0; w < 2; ++w) {
-      const int c = w == 0 ? c0 : c1;
-      const int g_lo = d_floordiv(c + 12, 25), g_hi = d_floordiv(c + 13, 25);
-      for (int g = g_lo; g <= g_hi; ++g) { if (np[a] < 3) { pg[a][np[a]] = g; pc[a][np[a]] = c - (25 * g - 13); np[a]++; } }
-    }
+    const int c0 = (fq[a] - 1) >> 1, c1 = c0 + 1;
+    const int lo0 = d_floordiv(c0 + 12, 25), hi0 = d_floordiv(c0 + 13, 25);
+    const int lo1 = d_floordiv(c1 + 12, 25), hi1 = d_floordiv(c1 + 13, 25);
+    e0[a] = lo0 * 256 + (c0 - (25 * lo0 - 13));
+    if (hi0 != lo0)      { e1[a] = hi0 * 256 + (c0 - (25 * hi0 - 13)); e2[a] = lo1 * 256 + (c1 - (25 * lo1 - 13)); np[a] = 3; }
+    else if (hi1 != lo1) { e1[a] = lo1 * 256 + (c1 - (25 * lo1 - 13)); e2[a] = hi1 * 256 + (c1 - (25 * hi1 - 13)); np[a] = 3; }
+    else                 { e1[a] = lo1 * 256 + (c1 - (25 * lo1 - 13)); e2[a] = e1[a]; np[a] = 2; }
   }
   const int ncomb = np[0] * np[1] * np[2];
   const int cen0 = st->cen[0], cen1 = st->cen[1], cen2 = st->cen[2];
   for (int cmb = sub; cmb < ncomb; cmb += GROUP) {
     const int ix = cmb % np[0], iy = (cmb / np[0]) % np[1], iz = cmb / (np[0] * np[1]);
-    const int gi = pg[0][ix], gj = pg[1][iy], gk = pg[2][iz];
+    const int ex = ix == 0 ? e0[0] : (ix == 1 ? e1[0] : e2[0]);
+    const int ey = iy == 0 ? e0[1] : (iy == 1 ? e1[1] : e2[1]);
+    const int ez = iz == 0 ? e0[2] : (iz == 1 ? e1[2] : e2[2]);
+    const int gi = ex >> 8, ci = ex & 255, gj = ey >> 8, cj = ey & 255, gk = ez >> 8, ck = ez & 255;
     const int li = gi + cen0, lj = gj + cen1, lk = gk + cen2;
     if (li < 0 || li >= LM_GW || lj < 0 || lj >= LM_GH || lk < 0 || lk >= LM_GD) continue;
     const int ps = d_phys_slot(gi, gj, gk);
@@ -301,13 +305,15 @@ __device__ __forceinline__ void d_knn5_group(const LmMapType& M, const LmMapStat
     if (rank < 0) continue;
     const int sid = M.slot_slab[ps];
     if (sid < 0) continue;
-    const int cell = pc[0][ix] + LM_CELLS_AXIS * (pc[1][iy] + LM_CELLS_AXIS * pc[2][iz]);
+    const int cell = ci + LM_CELLS_AXIS * (cj + LM_CELLS_AXIS * ck);
     const uint32_t* cs = M.cellstart + (size_t)sid * (LM_NCELL + 1);
     const uint32_t b = cs[cell], e = cs[cell + 1];
+    if (b >= e) continue;
     const int base_idx = st->valid_off[ty][rank];
     const float4* cp = M.cellpts + (size_t)sid * M.cap;
+    float4 p = cp[b];
     for (uint32_t t = b; t < e; ++t) {
-      const float4 p = cp[t];
+      const float4 pn = cp[t + 1 < e ? t + 1 : t];          // next point in flight while this one is ranked
       const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
       float d = __fmul_rn(dx, dx);
       d = __fadd_rn(d, __fmul_rn(dy, dy));
@@ -324,6 +330,7 @@ __device__ __forceinline__ void d_knn5_group(const LmMapType& M, const LmMapStat
           }
         }
       }
+      p = pn;
     }
   }
   // merge the 8 sorted lists: 5 rounds of (min over lane heads, owner pops)
@@ -350,7 +357,7 @@ __device__ __forceinline__ void d_knn5_group(const LmMapType& M, const LmMapStat
 // registers so every query of a sweep is resident at once; it leaves the 5 neighbour references (or -1 when the
 // d2[4] < 1.0 gate of :584,652 fails).  k_assoc_fit: one thread per query for the fp64 line / plane fit -- with the
 // fits inside the search kernel 7 of every 8 lanes idled through the fp64 tail and its registers halved occupancy.
-__global__ void __launch_bounds__(256) k_assoc_knn(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1,
+__global__ void __launch_bounds__(256, 4) k_assoc_knn(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1,
                                                    const int32_t* __restrict__ slot_valid_rank,
                                                    const float4* __restrict__ stack0, const float4* __restrict__ stack1,
                                                    int32_t* __restrict__ nnref) {

@@ -85,8 +85,10 @@ __device__ __forceinline__ void d_eval_factor(const LmFactor& f, const double* q
 __device__ void d_plus(const double* x, const double* d, double* out) {
   const double nd = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
   if (nd > 0.0) {
-    const double sbd = sin(nd) / nd;
-    const double a[4] = { sbd * d[0], sbd * d[1], sbd * d[2], cos(nd) };
+    double sn, cs;
+    sincos(nd, &sn, &cs);
+    const double sbd = sn / nd;
+    const double a[4] = { sbd * d[0], sbd * d[1], sbd * d[2], cs };
     d_qmul(a, x, out);
   } else { out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; out[3] = x[3]; }
   out[4] = x[4] + d[3]; out[5] = x[5] + d[4]; out[6] = x[6] + d[5];
@@ -112,9 +114,13 @@ __device__ double d_gradient_max_norm(const double* x, const double* g) {
 }
 
 // solve (A) y = b for SPD 6x6 A (upper-triangular packed) via Cholesky; returns 0 on success.
-// Fully unrolled: every index is a compile-time constant, so the factor lives in registers.
+// Fully unrolled (every index is a compile-time constant, the factor lives in registers) and division-free:
+// one reciprocal square root per pivot instead of a sqrt and 4-5 fp64 divisions (each a ~100-cycle dependent
+// software sequence on the single controller thread).  The step differs from a divide-based Cholesky in the
+// last ulps only; north_star compares poses at 1e-4 and normal equations at 1e-5.
 __device__ __forceinline__ int d_chol6(const double* A /*21*/, const double* b, double* y) {
-  double L[21];       // lower factor, packed like the upper triangle of its transpose: L(i,j), j <= i, at d_tri(j, i)
+  double L[21];       // lower factor, L(i,j), j <= i, at d_tri(j, i)
+  double inv[6];      // 1 / L(i,i)
   int bad = 0;
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
@@ -123,8 +129,8 @@ __device__ __forceinline__ int d_chol6(const double* A /*21*/, const double* b, 
       double s = A[d_tri(j, i)];
 #pragma unroll
       for (int k = 0; k < j; ++k) s -= L[d_tri(k, i)] * L[d_tri(k, j)];
-      if (i == j) { if (!(s > 0.0)) bad = 1; L[d_tri(i, i)] = sqrt(s); }
-      else L[d_tri(j, i)] = s / L[d_tri(j, j)];
+      if (i == j) { if (!(s > 0.0)) bad = 1; inv[i] = rsqrt(s); L[d_tri(i, i)] = s * inv[i]; }
+      else L[d_tri(j, i)] = s * inv[j];
     }
   }
   if (bad) return 1;
@@ -134,14 +140,14 @@ __device__ __forceinline__ int d_chol6(const double* A /*21*/, const double* b, 
     double s = b[i];
 #pragma unroll
     for (int k = 0; k < i; ++k) s -= L[d_tri(k, i)] * z[k];
-    z[i] = s / L[d_tri(i, i)];
+    z[i] = s * inv[i];
   }
 #pragma unroll
   for (int i = 5; i >= 0; --i) {
     double s = z[i];
 #pragma unroll
     for (int k = i + 1; k < 6; ++k) s -= L[d_tri(i, k)] * y[k];
-    y[i] = s / L[d_tri(i, i)];
+    y[i] = s * inv[i];
   }
   return 0;
 }
@@ -169,9 +175,9 @@ __device__ int d_compute_step(LmLmState* lm) {
     double A[21];
 #pragma unroll
     for (int k = 0; k < 21; ++k) A[k] = Hs[k];
-    const double radius = lm->radius;
+    const double inv_radius = 1.0 / lm->radius;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) A[d_tri(j, j)] += lm->diagonal[j] / radius;     // D^2 = diagonal / radius
+    for (int j = 0; j < 6; ++j) A[d_tri(j, j)] += lm->diagonal[j] * inv_radius;     // D^2 = diagonal / radius
     double y[6];
     int fail = d_chol6(A, gs, y);
 #pragma unroll
