@@ -35,14 +35,22 @@ __device__ __forceinline__ void d_make_givens(double p, double q, double* c, dou
   }
 }
 
-// hypot without relying on libm specifics: both sides use the same scaled formula? No --
-// the oracle calls C hypot(); CUDA's hypot() is also correctly rounded to < 1 ulp but not
-// guaranteed identical, and the value only steers the Wilkinson shift (any shift converges
-// to the same eigen-pairs up to rounding).  Gate margins are reported by the tests.
-__device__ void d_tridiagonal_qr_step(double* diag, double* subdiag, int start, int end, double* Q) {
-  double td = (diag[end - 1] - diag[end]) * 0.5;
-  double e = subdiag[end - 1];
-  double mu = diag[end];
+// The value of hypot() only steers the Wilkinson shift (any shift converges to the same eigen-pairs up to
+// rounding); CUDA's hypot() is within 1 ulp of libm's.  Gate margins are reported by the tests.
+//
+// Register-resident 3x3 specialisation: Eigen's loops run over k in [start, end) with start in {0,1}, end in
+// {1,2}; here they are unrolled over k = 0, 1 with guards, so that diag / subdiag / Q are only ever indexed
+// with compile-time constants and live in registers (dynamic indexing put them in local memory, and with
+// ~3 warps per SM nothing hid that latency).  Operation order is unchanged.
+#define D3(arr, i) ((i) == 0 ? arr##0 : ((i) == 1 ? arr##1 : arr##2))
+
+struct Eig3 { double d0, d1, d2, e0, e1; double q[9]; };    // diag, subdiag, Q (row k = eigenvector k while iterating)
+
+__device__ __forceinline__ void d_tridiagonal_qr_step(Eig3& E, int start, int end) {
+  const double dEnd = end == 2 ? E.d2 : E.d1, dEndm1 = end == 2 ? E.d1 : E.d0, eEndm1 = end == 2 ? E.e1 : E.e0;
+  double td = (dEndm1 - dEnd) * 0.5;
+  double e = eEndm1;
+  double mu = dEnd;
   if (td == 0.0) {
     mu -= fabs(e);
   } else {
@@ -51,32 +59,38 @@ __device__ void d_tridiagonal_qr_step(double* diag, double* subdiag, int start, 
     if (e2 == 0.0) mu -= (e / (td + (td > 0.0 ? 1.0 : -1.0))) * (e / h);
     else mu -= e2 / (td + (td > 0.0 ? h : -h));
   }
-  double x = diag[start] - mu;
-  double z = subdiag[start];
-  for (int k = start; k < end; ++k) {
+  double x = (start == 0 ? E.d0 : E.d1) - mu;
+  double z = start == 0 ? E.e0 : E.e1;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (k < start || k >= end) continue;
     double c, s;
     d_make_givens(x, z, &c, &s);
-    double sdk = s * diag[k] + c * subdiag[k];
-    double dkp1 = s * subdiag[k] + c * diag[k + 1];
-    diag[k] = c * (c * diag[k] - s * subdiag[k]) - s * (c * subdiag[k] - s * diag[k + 1]);
-    diag[k + 1] = s * sdk + c * dkp1;
-    subdiag[k] = c * sdk - s * dkp1;
-    if (k > start) subdiag[k - 1] = c * subdiag[k - 1] - s * z;
-    x = subdiag[k];
-    if (k < end - 1) {
-      z = -s * subdiag[k + 1];
-      subdiag[k + 1] = c * subdiag[k + 1];
+    double& dk = k == 0 ? E.d0 : E.d1;
+    double& dk1 = k == 0 ? E.d1 : E.d2;
+    double& ek = k == 0 ? E.e0 : E.e1;
+    double sdk = s * dk + c * ek;
+    double dkp1 = s * ek + c * dk1;
+    dk = c * (c * dk - s * ek) - s * (c * ek - s * dk1);
+    dk1 = s * sdk + c * dkp1;
+    ek = c * sdk - s * dkp1;
+    if (k > start) E.e0 = c * E.e0 - s * z;          // only k = 1 > start = 0: subdiag[k - 1] = subdiag[0]
+    x = ek;
+    if (k < end - 1) {                                // only k = 0, end = 2: subdiag[k + 1] = subdiag[1]
+      z = -s * E.e1;
+      E.e1 = c * E.e1;
     }
+#pragma unroll
     for (int i = 0; i < 3; ++i) {
-      double xi = Q[k * 3 + i], yi = Q[(k + 1) * 3 + i];
-      Q[k * 3 + i] = c * xi - s * yi;
-      Q[(k + 1) * 3 + i] = s * xi + c * yi;
+      double xi = E.q[k * 3 + i], yi = E.q[(k + 1) * 3 + i];
+      E.q[k * 3 + i] = c * xi - s * yi;
+      E.q[(k + 1) * 3 + i] = s * xi + c * yi;
     }
   }
 }
 
 // A: row-major 3x3 (lower triangle used). w ascending; Q column-major (column c = eigenvector c)
-__device__ void d_eigh3(const double* A, double* w, double* Q) {
+__device__ __forceinline__ void d_eigh3(const double* A, double* w, double* Q) {
   double m00 = A[0], m10 = A[3], m11 = A[4], m20 = A[6], m21 = A[7], m22 = A[8];
   double scale = fabs(m00);
   if (fabs(m10) > scale) scale = fabs(m10);
@@ -86,107 +100,141 @@ __device__ void d_eigh3(const double* A, double* w, double* Q) {
   if (fabs(m22) > scale) scale = fabs(m22);
   if (scale == 0.0) scale = 1.0;
   m00 /= scale; m10 /= scale; m11 /= scale; m20 /= scale; m21 /= scale; m22 /= scale;
-  double diag[3], subdiag[2];
+  Eig3 E;
   const double tol = DBL_MIN;
-  diag[0] = m00;
+  E.d0 = m00;
   double v1norm2 = m20 * m20;
   if (v1norm2 <= tol) {
-    diag[1] = m11; diag[2] = m22; subdiag[0] = m10; subdiag[1] = m21;
-    Q[0] = 1; Q[1] = 0; Q[2] = 0; Q[3] = 0; Q[4] = 1; Q[5] = 0; Q[6] = 0; Q[7] = 0; Q[8] = 1;
+    E.d1 = m11; E.d2 = m22; E.e0 = m10; E.e1 = m21;
+    E.q[0] = 1; E.q[1] = 0; E.q[2] = 0; E.q[3] = 0; E.q[4] = 1; E.q[5] = 0; E.q[6] = 0; E.q[7] = 0; E.q[8] = 1;
   } else {
     double beta = sqrt(m10 * m10 + v1norm2);
     double invBeta = 1.0 / beta;
     double m01 = m10 * invBeta;
     double m02 = m20 * invBeta;
     double q = 2.0 * m01 * m21 + m02 * (m22 - m11);
-    diag[1] = m11 + m02 * q;
-    diag[2] = m22 - m02 * q;
-    subdiag[0] = beta;
-    subdiag[1] = m21 - m01 * q;
-    Q[0] = 1; Q[1] = 0;   Q[2] = 0;
-    Q[3] = 0; Q[4] = m01; Q[5] = m02;
-    Q[6] = 0; Q[7] = m02; Q[8] = -m01;
+    E.d1 = m11 + m02 * q;
+    E.d2 = m22 - m02 * q;
+    E.e0 = beta;
+    E.e1 = m21 - m01 * q;
+    E.q[0] = 1; E.q[1] = 0;   E.q[2] = 0;
+    E.q[3] = 0; E.q[4] = m01; E.q[5] = m02;
+    E.q[6] = 0; E.q[7] = m02; E.q[8] = -m01;
   }
-  const int n = 3;
-  int end = n - 1, start = 0, iter = 0;
+  int end = 2, start = 0, iter = 0;
   const int maxIterations = 30;
   const double precision = 2.0 * DBL_EPSILON;
   while (end > 0) {
-    for (int i = start; i < end; ++i)
-      if (fabs(subdiag[i]) <= (fabs(diag[i]) + fabs(diag[i + 1])) * precision || fabs(subdiag[i]) <= DBL_MIN) subdiag[i] = 0.0;
-    while (end > 0 && subdiag[end - 1] == 0.0) end--;
+    // for (i = start; i < end; ++i) deflation test on subdiag[i]
+    if (0 >= start && 0 < end) if (fabs(E.e0) <= (fabs(E.d0) + fabs(E.d1)) * precision || fabs(E.e0) <= DBL_MIN) E.e0 = 0.0;
+    if (1 >= start && 1 < end) if (fabs(E.e1) <= (fabs(E.d1) + fabs(E.d2)) * precision || fabs(E.e1) <= DBL_MIN) E.e1 = 0.0;
+    while (end > 0 && (end == 2 ? E.e1 : E.e0) == 0.0) end--;
     if (end <= 0) break;
     iter++;
-    if (iter > maxIterations * n) break;
+    if (iter > maxIterations * 3) break;
     start = end - 1;
-    while (start > 0 && subdiag[start - 1] != 0.0) start--;
-    d_tridiagonal_qr_step(diag, subdiag, start, end, Q);
+    while (start > 0 && (start == 2 ? E.e1 : E.e0) != 0.0) start--;     // subdiag[start - 1], start in {1}: e0
+    d_tridiagonal_qr_step(E, start, end);
   }
-  for (int i = 0; i < n - 1; ++i) {
-    int k = 0; double mn = diag[i];
-    for (int j = 1; j < n - i; ++j) if (diag[i + j] < mn) { mn = diag[i + j]; k = j; }
-    if (k > 0) {
-      double tmp = diag[i]; diag[i] = diag[k + i]; diag[k + i] = tmp;
-      for (int r = 0; r < 3; ++r) { double t2 = Q[i * 3 + r]; Q[i * 3 + r] = Q[(k + i) * 3 + r]; Q[(k + i) * 3 + r] = t2; }
-    }
+  // eigenvalues ascending (selection sort of Eigen: first minimal index, strict <), eigenvectors follow
+  {
+    int k = 0; double mn = E.d0;
+    if (E.d1 < mn) { mn = E.d1; k = 1; }
+    if (E.d2 < mn) { k = 2; }
+    if (k == 1) { double t = E.d0; E.d0 = E.d1; E.d1 = t;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) { double t2 = E.q[r]; E.q[r] = E.q[3 + r]; E.q[3 + r] = t2; } }
+    else if (k == 2) { double t = E.d0; E.d0 = E.d2; E.d2 = t;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) { double t2 = E.q[r]; E.q[r] = E.q[6 + r]; E.q[6 + r] = t2; } }
+    if (E.d2 < E.d1) { double t = E.d1; E.d1 = E.d2; E.d2 = t;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) { double t2 = E.q[3 + r]; E.q[3 + r] = E.q[6 + r]; E.q[6 + r] = t2; } }
   }
-  for (int i = 0; i < 3; ++i) w[i] = diag[i] * scale;
+  w[0] = E.d0 * scale; w[1] = E.d1 * scale; w[2] = E.d2 * scale;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Q[i] = E.q[i];
 }
 
-// ---- Eigen 3.3 ColPivHouseholderQR<Matrix<double,5,3>>::solve (same operation order as the test oracle)
-__device__ __forceinline__ void d_make_householder(double* v, int len, int stride, double* tau, double* beta) {
-  double tailSqNorm = 0.0;
-  for (int i = 1; i < len; ++i) tailSqNorm += v[i * stride] * v[i * stride];
-  double c0 = v[0];
-  if (tailSqNorm <= DBL_MIN) {
-    *tau = 0.0; *beta = c0;
-    for (int i = 1; i < len; ++i) v[i * stride] = 0.0;
-  } else {
-    double b = sqrt(c0 * c0 + tailSqNorm);
-    if (c0 >= 0.0) b = -b;
-    for (int i = 1; i < len; ++i) v[i * stride] = v[i * stride] / (c0 - b);
-    *tau = (b - c0) / b;
-    *beta = b;
-  }
+// ---- Eigen 3.3 ColPivHouseholderQR<Matrix<double,5,3>>::solve (same operation order as the test oracle).
+// Fully unrolled over the three columns; the pivot column `big` is the only dynamic index and is handled with
+// conditional swaps on constant indices, so qr[15] and the norm / permutation vectors stay in registers.
+__device__ __forceinline__ void d_swap_cols(double* qr, int a, int b) {      // a, b compile-time after unrolling
+#pragma unroll
+  for (int r = 0; r < 5; ++r) { double t = qr[r * 3 + a]; qr[r * 3 + a] = qr[r * 3 + b]; qr[r * 3 + b] = t; }
 }
 
-__device__ void d_colpiv_qr_solve_5x3(const double* Ain, const double* bin, double* x) {
+__device__ __forceinline__ void d_colpiv_qr_solve_5x3(const double* Ain, const double* bin, double* x) {
   constexpr int R = 5, C = 3;
   double qr[R * C];
+#pragma unroll
   for (int i = 0; i < R * C; ++i) qr[i] = Ain[i];
   double hC[C]; int transp[C];
   double nU[C], nD[C];
+#pragma unroll
   for (int k = 0; k < C; ++k) {
-    double s = 0.0; for (int r = 0; r < R; ++r) s += qr[r * C + k] * qr[r * C + k];
+    double s = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) s += qr[r * C + k] * qr[r * C + k];
     nD[k] = sqrt(s); nU[k] = nD[k];
   }
-  double maxn = nU[0]; for (int k = 1; k < C; ++k) if (nU[k] > maxn) maxn = nU[k];
+  double maxn = nU[0];
+#pragma unroll
+  for (int k = 1; k < C; ++k) if (nU[k] > maxn) maxn = nU[k];
   double th = maxn * DBL_EPSILON; double threshold_helper = (th * th) / (double)R;
   double norm_downdate_threshold = sqrt(DBL_EPSILON);
   int nonzero_pivots = C;
+#pragma unroll
   for (int k = 0; k < C; ++k) {
     int big = k; double bn = nU[k];
+#pragma unroll
     for (int j = k + 1; j < C; ++j) if (nU[j] > bn) { bn = nU[j]; big = j; }
     double biggest_sq = bn * bn;
     if (nonzero_pivots == C && biggest_sq < threshold_helper * (double)(R - k)) nonzero_pivots = k;
     transp[k] = big;
-    if (k != big) {
-      for (int r = 0; r < R; ++r) { double t = qr[r * C + k]; qr[r * C + k] = qr[r * C + big]; qr[r * C + big] = t; }
-      double t = nU[k]; nU[k] = nU[big]; nU[big] = t;
-      t = nD[k]; nD[k] = nD[big]; nD[big] = t;
+#pragma unroll
+    for (int j = k + 1; j < C; ++j) {
+      if (big == j) {
+        d_swap_cols(qr, k, j);
+        double t = nU[k]; nU[k] = nU[j]; nU[j] = t;
+        t = nD[k]; nD[k] = nD[j]; nD[j] = t;
+      }
     }
-    double beta;
-    d_make_householder(&qr[k * C + k], R - k, C, &hC[k], &beta);
+    // householder on column k, rows k..R-1
+    double beta, tau;
+    {
+      double tailSqNorm = 0.0;
+#pragma unroll
+      for (int r = k + 1; r < R; ++r) tailSqNorm += qr[r * C + k] * qr[r * C + k];
+      double c0 = qr[k * C + k];
+      if (tailSqNorm <= DBL_MIN) {
+        tau = 0.0; beta = c0;
+#pragma unroll
+        for (int r = k + 1; r < R; ++r) qr[r * C + k] = 0.0;
+      } else {
+        double bb = sqrt(c0 * c0 + tailSqNorm);
+        if (c0 >= 0.0) bb = -bb;
+#pragma unroll
+        for (int r = k + 1; r < R; ++r) qr[r * C + k] = qr[r * C + k] / (c0 - bb);
+        tau = (bb - c0) / bb;
+        beta = bb;
+      }
+    }
+    hC[k] = tau;
     qr[k * C + k] = beta;
     if (hC[k] != 0.0) {
+#pragma unroll
       for (int j = k + 1; j < C; ++j) {
         double tmp = 0.0;
+#pragma unroll
         for (int r = k + 1; r < R; ++r) tmp += qr[r * C + k] * qr[r * C + j];
         tmp += qr[k * C + j];
         qr[k * C + j] -= hC[k] * tmp;
+#pragma unroll
         for (int r = k + 1; r < R; ++r) qr[r * C + j] -= hC[k] * qr[r * C + k] * tmp;
       }
     }
+#pragma unroll
     for (int j = k + 1; j < C; ++j) {
       if (nU[j] != 0.0) {
         double temp = fabs(qr[k * C + j]) / nU[j];
@@ -195,7 +243,9 @@ __device__ void d_colpiv_qr_solve_5x3(const double* Ain, const double* bin, doub
         double ratio = nU[j] / nD[j];
         double temp2 = temp * (ratio * ratio);
         if (temp2 <= norm_downdate_threshold) {
-          double s = 0.0; for (int r = k + 1; r < R; ++r) s += qr[r * C + j] * qr[r * C + j];
+          double s = 0.0;
+#pragma unroll
+          for (int r = k + 1; r < R; ++r) s += qr[r * C + j] * qr[r * C + j];
           nD[j] = sqrt(s); nU[j] = nD[j];
         } else {
           nU[j] *= sqrt(temp);
@@ -203,30 +253,43 @@ __device__ void d_colpiv_qr_solve_5x3(const double* Ain, const double* bin, doub
       }
     }
   }
-  int perm[C]; for (int i = 0; i < C; ++i) perm[i] = i;
-  for (int k = 0; k < C; ++k) { int t = perm[k]; perm[k] = perm[transp[k]]; perm[transp[k]] = t; }
+  // column permutation: perm = identity with transpositions (k, transp[k]) applied in order
+  int p0 = 0, p1 = 1, p2 = 2;
+  { const int t = transp[0]; if (t == 1) { int u = p0; p0 = p1; p1 = u; } else if (t == 2) { int u = p0; p0 = p2; p2 = u; } }
+  { const int t = transp[1]; if (t == 2) { int u = p1; p1 = p2; p2 = u; } }
   if (nonzero_pivots == 0) { x[0] = x[1] = x[2] = 0.0; return; }
-  double c[R]; for (int r = 0; r < R; ++r) c[r] = bin[r];
-  for (int k = 0; k < nonzero_pivots; ++k) {
-    if (hC[k] != 0.0) {
+  double c[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) c[r] = bin[r];
+#pragma unroll
+  for (int k = 0; k < C; ++k) {
+    if (k < nonzero_pivots && hC[k] != 0.0) {
       double tmp = 0.0;
+#pragma unroll
       for (int r = k + 1; r < R; ++r) tmp += qr[r * C + k] * c[r];
       tmp += c[k];
       c[k] -= hC[k] * tmp;
+#pragma unroll
       for (int r = k + 1; r < R; ++r) c[r] -= hC[k] * qr[r * C + k] * tmp;
     }
   }
-  for (int i = nonzero_pivots - 1; i >= 0; --i) {
-    double s = c[i];
-    for (int j = i + 1; j < nonzero_pivots; ++j) s -= qr[i * C + j] * c[j];
-    c[i] = s / qr[i * C + i];
+#pragma unroll
+  for (int i = C - 1; i >= 0; --i) {
+    if (i < nonzero_pivots) {
+      double s = c[i];
+#pragma unroll
+      for (int j = i + 1; j < C; ++j) if (j < nonzero_pivots) s -= qr[i * C + j] * c[j];
+      c[i] = s / qr[i * C + i];
+    }
   }
-  for (int i = 0; i < nonzero_pivots; ++i) x[perm[i]] = c[i];
-  for (int i = nonzero_pivots; i < C; ++i) x[perm[i]] = 0.0;
+  // x[perm[i]] = c[i] for i < nonzero_pivots, 0 otherwise
+  const double c0 = 0 < nonzero_pivots ? c[0] : 0.0, c1 = 1 < nonzero_pivots ? c[1] : 0.0, c2 = 2 < nonzero_pivots ? c[2] : 0.0;
+#pragma unroll
+  for (int t = 0; t < 3; ++t) x[t] = (p0 == t) ? c0 : ((p1 == t) ? c1 : c2);
 }
 
 // ---- fits
-__device__ void d_fit_corner(const float4* nb, float4 ori, LmFactor* f) {
+__device__ __forceinline__ void d_fit_corner(const float4* nb, float4 ori, LmFactor* f) {
   double near[5][3], center[3] = { 0, 0, 0 };
   for (int j = 0; j < 5; ++j) {
     near[j][0] = nb[j].x; near[j][1] = nb[j].y; near[j][2] = nb[j].z;
@@ -247,7 +310,7 @@ __device__ void d_fit_corner(const float4* nb, float4 ori, LmFactor* f) {
   f->kind = 0;
 }
 
-__device__ void d_fit_surf(const float4* nb, float4 ori, LmFactor* f) {
+__device__ __forceinline__ void d_fit_surf(const float4* nb, float4 ori, LmFactor* f) {
   double A[15], B[5] = { -1, -1, -1, -1, -1 };
   for (int j = 0; j < 5; ++j) { A[j * 3 + 0] = nb[j].x; A[j * 3 + 1] = nb[j].y; A[j * 3 + 2] = nb[j].z; }
   double n[3];
