@@ -7,8 +7,8 @@
 // Exactness of the search: a correspondence is only used if its 5th neighbour has fp32
 // d2 < 1.0, hence every neighbour that matters satisfies |dx|,|dy|,|dz| < 1 and its integer
 // floor differs from the query's by at most 1 per axis.  With 2 m cells keyed on
-// floor(x) >> 1 those floors fall in exactly 2 cells per axis: 8 cells per query, one per
-// lane of an 8-lane group (cells that straddle a 50 m cube border are looked up in both
+// floor(x) >> 1 those floors fall in exactly 2 cells per axis: 8 cells per query, spread over
+// the GROUP lanes that share a query (cells that straddle a 50 m cube border are looked up in both
 // cubes, <= 27 (cube, cell) pairs).  d2 is accumulated like FLANN's L2_Simple:
 // ((dx*dx) + dy*dy) + dz*dz in fp32 without FMA.  Ties are broken on the index in the
 // reference's concatenation order (:533-537), so results are order-independent.
@@ -16,7 +16,8 @@
 #include <float.h>
 
 constexpr int KNN_K = 5;
-constexpr int GROUP = 8;      // lanes per query
+constexpr int GROUP = 8;      // lanes per query, one candidate cell each (4 lanes x 2 cells issues fewer instructions per query but
+                              // measured slower on B200: 26.6 vs 23.1 us per launch -- the kernel wants the extra warps to hide latency)
 
 struct Cand { float d; int idx; int ref; };   // ref: element index into the map type's cellpts pool
 
@@ -328,8 +329,8 @@ __device__ __forceinline__ void d_fit_surf(const float4* nb, float4 ori, LmFacto
   f->kind = 2;
 }
 
-// ---- 8-lane exact 5-NN of one world-frame query against the window of one map type.
-// All 8 lanes of the group call this with the same query; returns on every lane the merged
+// ---- GROUP-lane exact 5-NN of one world-frame query against the window of one map type.
+// All lanes of the group call this with the same query; returns on every lane the merged
 // top-5 (d2, canonical idx, ref).  n_found < 5 leaves +inf / -1 entries.
 __device__ __forceinline__ void d_knn5_group(const LmMapType& M, const LmMapState* __restrict__ st,
                                              const int32_t* __restrict__ slot_valid_rank, int ty, float qx, float qy, float qz,
@@ -396,7 +397,7 @@ __device__ __forceinline__ void d_knn5_group(const LmMapType& M, const LmMapStat
       p = pn;
     }
   }
-  // merge the 8 sorted lists: 5 rounds of (min over lane heads, owner pops)
+  // merge the GROUP sorted lists: 5 rounds of (min over lane heads, owner pops)
   int head = 0;
 #pragma unroll
   for (int k = 0; k < KNN_K; ++k) {
@@ -416,10 +417,10 @@ __device__ __forceinline__ void d_knn5_group(const LmMapType& M, const LmMapStat
   }
 }
 
-// Association = two launches.  k_assoc_knn: one 8-lane group per query (both map types in one launch), light on
+// Association = two launches.  k_assoc_knn: one GROUP-lane group per query (both map types in one launch), light on
 // registers so every query of a sweep is resident at once; it leaves the 5 neighbour references (or -1 when the
 // d2[4] < 1.0 gate of :584,652 fails).  k_assoc_fit: one thread per query for the fp64 line / plane fit -- with the
-// fits inside the search kernel 7 of every 8 lanes idled through the fp64 tail and its registers halved occupancy.
+// fits inside the search kernel all but one lane of a group idled through the fp64 tail and its registers halved occupancy.
 __global__ void __launch_bounds__(256, 4) k_assoc_knn(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1,
                                                    const int32_t* __restrict__ slot_valid_rank,
                                                    const float4* __restrict__ stack0, const float4* __restrict__ stack1,
@@ -428,7 +429,7 @@ __global__ void __launch_bounds__(256, 4) k_assoc_knn(LmMapState* __restrict__ s
   const int n0 = st->stack_n[0], n1 = st->stack_n[1];
   const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / GROUP;
   const int sub = threadIdx.x & (GROUP - 1);
-  const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~(GROUP - 1));
+  const unsigned gmask = ((1u << GROUP) - 1u) << ((threadIdx.x & 31) & ~(GROUP - 1));
   if (gid >= n0 + n1) return;
   const int ty = gid < n0 ? 0 : 1;
   const int qi = ty == 0 ? gid : gid - n0;
@@ -492,7 +493,7 @@ __global__ void __launch_bounds__(256) k_knn5_hook(const LmMapState* __restrict_
                                                    const float4* __restrict__ q, int n, int32_t* __restrict__ oidx, float* __restrict__ od2) {
   const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / GROUP;
   const int sub = threadIdx.x & (GROUP - 1);
-  const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~(GROUP - 1));
+  const unsigned gmask = ((1u << GROUP) - 1u) << ((threadIdx.x & 31) & ~(GROUP - 1));
   if (gid >= n) return;
   const float4 p = q[gid];
   float d[KNN_K]; int idx[KNN_K], ref[KNN_K];
