@@ -286,33 +286,65 @@ def run_ours(args):
     e2e_value = world * args.steps / (float(te.item()) * 1e-3)
     d2h = int(ctx.L.lmono_map_result_bytes()) * args.steps      # pose + report read back per step
 
-    # ---- per-phase device times (CUDA events around each phase, same workload, L2 flushed)
-    ctx.profile_enable(True)
-    nprof = min(args.steps, 16)
+    # ---- per-kernel device times in situ: a CUDA event after every launch of the step (plain launches, same kernel
+    # order and cache state as the timed leg: L2 flushed before each step); a GPU-side sleep in front of each step lets
+    # the host enqueue the whole step before the device starts it, so the deltas are device durations, not launch latency
+    nprof = min(args.steps, 24)
+    ctx.kernel_marks_enable(True)
     for i in range(nprof):
         flush.fill_(1)
+        torch.cuda._sleep(4_000_000)
         step_device(args.warmup + i)
-    prof = ctx.profile_read()
-    ctx.profile_enable(False)
+    marks = ctx.kernel_marks()
+    ctx.kernel_marks_enable(False)
     q_last, t_last, rep = ctx.map_collect()
-    phase_ms = {k: v[0] / max(nprof, 1) for k, v in prof.items()}
+    marks.pop("k_set_wmap", None)          # first mark of a step: its delta contains the flush + sleep
+    kern_us = {k: 1e3 * v[1] / nprof for k, v in marks.items()}                    # us per step
+    kern_launch_ms = {k: v[1] / max(v[0], 1) for k, v in marks.items()}            # ms per launch
     nq = rep.corner_stack + rep.surf_stack
     nmap = rep.corner_from_map + rep.surf_from_map
-    # dominant kernel family by device time
-    assoc_launch_ms = prof["assoc"][0] / max(prof["assoc"][1], 1)
-    refilter_launch_ms = prof["refilter"][0] / max(prof["refilter"][1], 1)
-    # algorithmic bytes per launch: kNN query = 16 B query + 5 x 16 B neighbours + 5 x 4 B indices
-    assoc_bytes = 116.0 * nq
+    nfac = rep.corner_num[1] + rep.surf_num[1]
+    evals = sum(s_.iterations + 1 for s_ in rep.solve)
+    ncu = {}
+    try:
+        for l in json.load(open(os.path.join(ROOT, "profiles", "ncu_r01_full_metrics.json")))["launches"]:
+            ncu.setdefault(l["kernel"], []).append(l)
+    except Exception:
+        pass
+
+    def roof(kernel, alg_bytes, what):
+        ms = kern_launch_ms.get(kernel)
+        if not ms:
+            return None
+        gbs = alg_bytes / (ms * 1e-3) / 1e9
+        r = {"kernel": kernel, "what": what, "algorithmic_bytes_per_launch": float(alg_bytes), "avg_launch_ms": ms,
+             "achieved": gbs, "frac": gbs / hbm_peak}
+        if kernel in ncu:
+            r["traffic"] = float(np.mean([l["dram_bytes_total"] for l in ncu[kernel]]))
+            r["l2_hit_pct_ncu"] = float(np.mean([l["lts__t_sector_hit_rate.pct"] for l in ncu[kernel]]))
+        return r
+
+    nraw = RAW_CORNER + RAW_SURF
+    others = [roof("k_lm_solve_cluster", 64.0 * nfac * max(evals, 1) / 2.0, "one LM solve: E evaluations x F factors x 64 B (SURVEY 8d); fp64-latency bound, factors stay in shared memory after the first pass"),
+              roof("k_assoc_fit", 160.0 * nq, "line / plane fit: 5 neighbours + query + factor record per query"),
+              roof("k_sort_tiles", 16.0 * nraw, "register bitonic tile sort: 8 B key read + write"),
+              roof("k_merge_ranks_smem", 16.0 * nraw, "rank merge of the sorted tiles in shared memory"),
+              roof("k_vg_write", 8.0 * nraw + 16.0 * nraw + 16.0 * nq, "VoxelGrid centroids of both feature clouds")]
+    knn = roof("k_assoc_knn", 116.0 * nq, "exact 5-NN: 16 B query + 5 x 16 B neighbours + 5 x 4 B indices per query (SURVEY 8d)") or {}
     roofline = {
-        "bound": "hbm", "kernel": "k_associate (exact 5-NN + line/plane fit, one launch per outer iteration)",
-        "achieved": assoc_bytes / (assoc_launch_ms * 1e-3) / 1e9 if assoc_launch_ms > 0 else None,
-        "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
-        "frac": (assoc_bytes / (assoc_launch_ms * 1e-3) / 1e9 / hbm_peak) if assoc_launch_ms > 0 else None,
-        "traffic": None,
-        "algorithmic_bytes_per_launch": assoc_bytes, "avg_launch_ms": assoc_launch_ms,
-        "queries_per_launch": nq, "knn_queries_per_s": nq / (assoc_launch_ms * 1e-3) if assoc_launch_ms > 0 else None,
-        "phase_ms_per_step": {k: round(v, 4) for k, v in phase_ms.items()},
-        "note": "map (~16 MB) is L2-resident between launches of one step; see DESIGN.md for why HBM% is low on this path",
+        "bound": "hbm", "kernel": "k_assoc_knn (exact 5-NN of every feature against the cube map, one launch per outer iteration)",
+        "achieved": knn.get("achieved"), "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
+        "frac": knn.get("frac"), "traffic": knn.get("traffic"),
+        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture committed as profiles/ncu_r01_full_metrics.json (cold caches per ncu replay)",
+        "algorithmic_bytes_per_launch": knn.get("algorithmic_bytes_per_launch"), "avg_launch_ms": knn.get("avg_launch_ms"),
+        "queries_per_launch": int(nq), "knn_queries_per_s": nq / (knn["avg_launch_ms"] * 1e-3) if knn.get("avg_launch_ms") else None,
+        "l2_hit_pct_ncu": knn.get("l2_hit_pct_ncu"),
+        "kernel_us_per_step": {k: round(v, 2) for k, v in sorted(kern_us.items(), key=lambda kv: -kv[1])},
+        "kernel_us_note": "CUDA-event deltas between consecutive launches of the un-graphed step: each includes ~3 us of event + launch gap, "
+                          "so the sum exceeds ms_per_step (graph replay); profiles/ holds the ncu launch list of the same command",
+        "other_kernels": [r for r in others if r],
+        "note": "the map (~16 MB + 16 MB index) fits the 126 MB L2 and one registration moves ~30-60 MB algorithmically (5-10 us of HBM time): "
+                "the step is bound by dependent L2 gathers, fp64 latency and ~26 launches, not by HBM bandwidth (DESIGN.md section 4)",
     }
 
     line = {
@@ -358,7 +390,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--cpu-steps", type=int, default=12)
+    ap.add_argument("--cpu-steps", type=int, default=60)
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 40:

@@ -215,6 +215,34 @@ class Context:
         self._chk(self.L.lmono_profile_read(self._h, ms, cnt), "profile_read")
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROFILE_PHASES)}
 
+    def kernel_marks_enable(self, on=True):
+        """Per-launch CUDA events on every kernel of map_step* (the step then runs as plain launches, not a graph replay)."""
+        self._chk(self.L.lmono_kmarks_enable(self._h, 1 if on else 0), "kmarks_enable")
+
+    def kernel_marks(self):
+        """{kernel name: (launches, total_ms)} since the marks were enabled / last read."""
+        import re
+        buf = C.create_string_buffer(1 << 16)
+        self._chk(self.L.lmono_kmarks_dump(self._h, buf, len(buf)), "kmarks_dump")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            site, n, ms = line.split()
+            f, l = site.split(":")
+            name = site
+            try:
+                src = open(os.path.join(_CSRC, f)).read().splitlines()
+                for k in range(int(l) - 1, max(int(l) - 8, -1), -1):
+                    m = re.search(r"(k_\w+)\s*(?:<<<|,)", src[k]) if k < len(src) else None
+                    if m:
+                        name = m.group(1)
+                        break
+            except OSError:
+                pass
+            a = out.setdefault(name, [0, 0.0])
+            a[0] += int(n)
+            a[1] += float(ms)
+        return {k: (v[0], v[1]) for k, v in out.items()}
+
     # -- laserMapping
     def map_step(self, corner_last, surf_last, q_odom, t_odom, full_res=None):
         cl = corner_last if corner_last.dtype == np.float32 and corner_last.flags["C_CONTIGUOUS"] else _xyzi(corner_last)
