@@ -195,16 +195,24 @@ def run_ours(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
 
+    S = max(1, args.sequences)
     _, cm, sm, sweeps = make_workload(rank)
-    # one real (non-default) stream for torch, NCCL, the CUDA events and the ctx: a NULL handle would make the
-    # ctx create its own stream, and events recorded on torch's stream would not bracket its kernels
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
-    ctx = api.Context(device=local, stream=stream.cuda_stream)
-    ctx.map_import(0, cm)
-    ctx.map_import(1, sm)
-    ctx.sync()
+    nsw = len(sweeps)
+    # one real (non-default) stream for torch, NCCL and the CUDA events: the fork / join point of every batch step.
+    # Sequence 0 runs on it as well (single-sequence legs); the other sequences get their own streams.
+    main = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(main)
+    assert main.cuda_stream != 0
+    seq_streams = [main] + [torch.cuda.Stream(device=dev) for _ in range(S - 1)]
+    ctxs = []
+    for s_ in range(S):
+        c_ = api.Context(device=local, stream=seq_streams[s_].cuda_stream)
+        c_.map_import(0, cm)
+        c_.map_import(1, sm)
+        c_.sync()
+        ctxs.append(c_)
+    ctx = ctxs[0]
+    batch = api.SequenceBatch(ctxs)
 
     # device-resident copies of the sweeps (value leg) and pinned host copies (e2e leg)
     d_sweeps = [(torch.from_numpy(c).to(dev), torch.from_numpy(s).to(dev)) for (c, s, *_rest) in sweeps]
@@ -213,11 +221,20 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
     ident = ([0, 0, 0, 1], [0, 0, 0])
 
-    def step_device(i):
-        c, s = d_sweeps[i % len(sweeps)]
-        _, _, _, _, qp, tp = sweeps[i % len(sweeps)]
-        ctx.map_set_state(*ident)       # every registration starts from its own U(+-0.2 m, +-1 deg) perturbation
-        ctx.map_step_device(c.data_ptr(), c.shape[0], s.data_ptr(), s.shape[0], qp, tp)
+    # sequence s registers sweep (i + 3 s) mod 24 at batch step i; every registration starts from its own
+    # U(+-0.2 m, +-1 deg) perturbation (wmap_wodom reset to identity).  One argument set per i mod 24.
+    def sweep_of(i, s_):
+        return (i + 3 * s_) % nsw
+
+    bargs = []
+    for i in range(nsw):
+        ks = [sweep_of(i, s_) for s_ in range(S)]
+        a_ = api.BatchArgs(S)
+        a_.set_odom([(sweeps[k][4], sweeps[k][5]) for k in ks]).set_wmap_in([ident] * S)
+        a_.set_device_inputs([d_sweeps[k][0].data_ptr() for k in ks], [d_sweeps[k][0].shape[0] for k in ks],
+                             [d_sweeps[k][1].data_ptr() for k in ks], [d_sweeps[k][1].shape[0] for k in ks])
+        a_.set_host_inputs([h_np[k][0] for k in ks], [h_np[k][1] for k in ks])
+        bargs.append(a_)
 
     def barrier():
         torch.cuda.synchronize()
@@ -225,66 +242,100 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # warm-up
-    for i in range(max(args.warmup, 3)):
-        step_device(i)
-    ctx.map_collect()
+    def allmax(x):
+        t_ = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        return float(t_.item())
 
-    # ---- value leg: device-resident inputs, CUDA events per step, L2 flushed between steps
+    def check_converged(res, i_last):
+        worst = 0.0
+        for s_, (q_, t_, rep_) in enumerate(res):
+            tg = sweeps[sweep_of(i_last, s_)][3]
+            err = float(np.linalg.norm(t_ - tg))
+            assert rep_.optimized == 1 and err < 0.1, (s_, rep_.optimized, err)
+            worst = max(worst, err)
+        return worst
+
+    W = max(args.warmup, 3)
+    for i in range(W):
+        batch.step_device(join_stream=main.cuda_stream, args=bargs[i % nsw])
+    batch.collect()
+
+    # ---- value leg: S sequences per GPU, device-resident inputs.  Per batch step: L2 flush on the main stream, event,
+    # fork -> one registration per sequence, overlapping on the device -> join, event.  value = registrations / sum of the
+    # event-bracketed times (the flush is outside the brackets).
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    n_launch0 = ctx.launch_count()
+    n_launch0 = sum(c_.launch_count() for c_ in ctxs)
+    t_host0 = time.perf_counter()
     for i in range(args.steps):
         flush.fill_(i & 0xFF)
-        ev0[i].record(stream)
-        step_device(args.warmup + i)
-        ev1[i].record(stream)
+        ev0[i].record(main)
+        batch.step_device(join_stream=main.cuda_stream, args=bargs[(W + i) % nsw])
+        ev1[i].record(main)
+    host_enqueue_s = time.perf_counter() - t_host0
     barrier()
-    n_launch = ctx.launch_count() - n_launch0
+    n_launch = sum(c_.launch_count() for c_ in ctxs) - n_launch0
     clocks = sampler.stop()
-    q_last, t_last, rep = ctx.map_collect()
+    res = batch.collect()
     step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
-    total_ms = float(sum(step_ms))
-    tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    total_ms_max = float(tt.item())
-    value = world * args.steps / (total_ms_max * 1e-3)
+    total_ms_max = allmax(float(sum(step_ms)))
+    value = world * S * args.steps / (total_ms_max * 1e-3)
+    reg_err = check_converged(res, W + args.steps - 1)     # the work inside the timed region converged
 
-    # sanity of the work done inside the timed region: the last registration converged
-    c, s, qg, tg, qp, tp = sweeps[(args.warmup + args.steps - 1) % len(sweeps)]
-    reg_err = float(np.linalg.norm(t_last - tg))
-    assert rep.optimized == 1 and reg_err < 0.1, (rep.optimized, reg_err)
-
-    # ---- e2e leg: public host API, pinned host inputs, H2D + D2H inside the timed region
+    # ---- e2e leg: public host API (lmono_map_step_batch), pinned host inputs, H2D of the features and D2H of the pose
+    # + report inside the timed region, S sequences in flight
     for i in range(3):
-        c, s = h_np[i % len(sweeps)]
-        ctx.map_set_state(*ident)
-        ctx.map_step(c, s, sweeps[i % len(sweeps)][4], sweeps[i % len(sweeps)][5])
+        batch.step(args=bargs[i % nsw])
     barrier()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
-    h2d = d2h = 0
-    e0.record(stream)
+    h2d = 0
+    e0.record(main)
     t0 = time.perf_counter()
     for i in range(args.steps):
-        k = (args.warmup + i) % len(sweeps)
-        c, s = h_np[k]
-        ctx.map_set_state(*ident)
-        ctx.map_step(c, s, sweeps[k][4], sweeps[k][5])
-        h2d += c.nbytes + s.nbytes
-    e1.record(stream)
+        a_ = bargs[(W + i) % nsw]
+        res = batch.step(args=a_)
+        h2d += sum(a_.cv[s_].n + a_.sv[s_].n for s_ in range(S)) * 16
+    e1.record(main)
     barrier()
     e2e_wall = time.perf_counter() - t0
-    e2e_ms = max(e0.elapsed_time(e1), e2e_wall * 1e3)
-    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * args.steps / (float(te.item()) * 1e-3)
-    d2h = int(ctx.L.lmono_map_result_bytes()) * args.steps      # pose + report read back per step
+    check_converged(res, W + args.steps - 1)
+    e2e_ms = allmax(max(e0.elapsed_time(e1), e2e_wall * 1e3))
+    e2e_value = world * S * args.steps / (e2e_ms * 1e-3)
+    d2h = int(ctx.L.lmono_map_result_bytes()) * S * args.steps      # pose + report read back per registration
+
+    # ---- single sequence alone on the GPU (latency of one registration; the round-1 headline): device-resident inputs,
+    # CUDA events per step, L2 flushed between steps
+    def step_single(i):
+        k = i % nsw
+        ctx.map_set_state(*ident)
+        ctx.map_step_device(d_sweeps[k][0].data_ptr(), d_sweeps[k][0].shape[0], d_sweeps[k][1].data_ptr(), d_sweeps[k][1].shape[0],
+                            sweeps[k][4], sweeps[k][5])
+
+    for i in range(3):
+        step_single(i)
+    barrier()
+    sv0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    sv1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        sv0[i].record(main)
+        step_single(W + i)
+        sv1[i].record(main)
+    barrier()
+    single_ms = allmax(float(sum(a.elapsed_time(b) for a, b in zip(sv0, sv1)))) / args.steps
+    # the same through the host API (lmono_map_step: upload, step, synchronous read-back)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        k = (W + i) % nsw
+        ctx.map_set_state(*ident)
+        ctx.map_step(h_np[k][0], h_np[k][1], sweeps[k][4], sweeps[k][5])
+    single_e2e_ms = allmax((time.perf_counter() - t0) * 1e3) / args.steps
 
     # ---- per-kernel device times in situ: a CUDA event after every launch of the step (plain launches, same kernel
     # order and cache state as the timed leg: L2 flushed before each step); a GPU-side sleep in front of each step lets
@@ -294,7 +345,7 @@ def run_ours(args):
     for i in range(nprof):
         flush.fill_(1)
         torch.cuda._sleep(4_000_000)
-        step_device(args.warmup + i)
+        step_single(W + i)
     marks = ctx.kernel_marks()
     ctx.kernel_marks_enable(False)
     q_last, t_last, rep = ctx.map_collect()
@@ -306,8 +357,9 @@ def run_ours(args):
     nfac = rep.corner_num[1] + rep.surf_num[1]
     evals = sum(s_.iterations + 1 for s_ in rep.solve)
     ncu = {}
+    ncu_file = "ncu_r01_full_metrics.json"
     try:
-        for l in json.load(open(os.path.join(ROOT, "profiles", "ncu_r01_full_metrics.json")))["launches"]:
+        for l in json.load(open(os.path.join(ROOT, "profiles", ncu_file)))["launches"]:
             ncu.setdefault(l["kernel"], []).append(l)
     except Exception:
         pass
@@ -335,8 +387,9 @@ def run_ours(args):
         "bound": "hbm", "kernel": "k_assoc_knn (exact 5-NN of every feature against the cube map, one launch per outer iteration)",
         "achieved": knn.get("achieved"), "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
         "frac": knn.get("frac"), "traffic": knn.get("traffic"),
-        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture committed as profiles/ncu_r01_full_metrics.json (cold caches per ncu replay)",
+        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture committed as profiles/" + ncu_file + " (cold caches per ncu replay)",
         "algorithmic_bytes_per_launch": knn.get("algorithmic_bytes_per_launch"), "avg_launch_ms": knn.get("avg_launch_ms"),
+        "timing": "one sequence alone on the GPU, un-graphed step, CUDA event after every launch",
         "queries_per_launch": int(nq), "knn_queries_per_s": nq / (knn["avg_launch_ms"] * 1e-3) if knn.get("avg_launch_ms") else None,
         "l2_hit_pct_ncu": knn.get("l2_hit_pct_ncu"),
         "kernel_us_per_step": {k: round(v, 2) for k, v in sorted(kern_us.items(), key=lambda kv: -kv[1])},
@@ -352,9 +405,15 @@ def run_ours(args):
         "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32+f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "map_points": int(nmap), "queries_per_sweep": int(nq),
-                   "raw_features_per_sweep": [RAW_CORNER, RAW_SURF], "l2": "flushed between steps (256 MiB write)",
-                   "parallelism": "one independent sequence per GPU, no collective"},
+                   "raw_features_per_sweep": [RAW_CORNER, RAW_SURF], "sequences_per_gpu": S,
+                   "registrations_per_step": S * world,
+                   "l2": "flushed between steps (256 MiB write)",
+                   "parallelism": f"{S} independent sequences per GPU (one ctx + stream each, BASELINE config C-4), one registration of every sequence per step, no collective"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps},
+        "single_sequence": {"value": 1e3 / single_ms * world, "unit": UNIT, "ms_per_registration": single_ms,
+                            "e2e_value": 1e3 / single_e2e_ms * world, "e2e_ms_per_registration": single_e2e_ms,
+                            "note": "one sequence alone on each GPU: latency of one registration (graph replay, L2 flushed between steps)"},
+        "host_enqueue_ms_per_step": 1e3 * host_enqueue_s / args.steps,
         "gpu_launches": int(n_launch),
         "clocks": clocks,
         "roofline": roofline,
@@ -378,7 +437,7 @@ def run_ours(args):
                                 "sample": f"{ncpu} registrations of the same workload on 1 host thread (the reference nodes are single-threaded)"}
     if rank == 0:
         print(json.dumps(line))
-    ctx.close()
+    batch.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -389,6 +448,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sequences", type=int, default=8, help="independent sequences per GPU (one ctx + stream each)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-steps", type=int, default=60)
     args = ap.parse_args()

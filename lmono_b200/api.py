@@ -410,3 +410,111 @@ class Context:
         buf, out = _out(len(p))
         self._chk(self.L.lmono_voxel_grid(self._h, view_of(p), C.c_float(leaf), C.byref(out)), "voxel_grid")
         return buf[: out.n_out].copy()
+
+
+class BatchArgs:
+    """The per-step argument arrays of a SequenceBatch (ctypes, n entries each).  A caller that cycles through a
+    fixed set of inputs builds one BatchArgs per input set once and passes it to step / step_device."""
+
+    def __init__(self, n):
+        self.n = n
+        self.cv = (CloudView * n)()
+        self.sv = (CloudView * n)()
+        self.dc = (C.c_void_p * n)()
+        self.ds = (C.c_void_p * n)()
+        self.nc = (C.c_int32 * n)()
+        self.ns = (C.c_int32 * n)()
+        self.odom = (Pose * n)()
+        self.wmap_in = (Pose * n)()
+        self.use_wmap_in = False
+        self._keep = None
+
+    @staticmethod
+    def _poses(arr, poses):
+        for i, (q, t) in enumerate(poses):
+            arr[i].q[:] = [float(v) for v in q]
+            arr[i].t[:] = [float(v) for v in t]
+
+    def set_odom(self, poses):
+        """wodom_curr of the step of every sequence: [(q, t)] * n"""
+        self._poses(self.odom, poses)
+        return self
+
+    def set_wmap_in(self, poses):
+        """q/t_wmap_wodom to install before the step (None: keep what the previous step left)"""
+        self.use_wmap_in = poses is not None
+        if poses is not None:
+            self._poses(self.wmap_in, poses)
+        return self
+
+    def set_device_inputs(self, corner_ptrs, corner_ns, surf_ptrs, surf_ns):
+        for i in range(self.n):
+            self.dc[i] = corner_ptrs[i]
+            self.ds[i] = surf_ptrs[i]
+            self.nc[i] = corner_ns[i]
+            self.ns[i] = surf_ns[i]
+        return self
+
+    def set_host_inputs(self, corners, surfs):
+        """float32 [n_i, 4] arrays (page-locked memory makes the uploads asynchronous); kept alive by this object"""
+        self._keep = (list(corners), list(surfs))
+        for i in range(self.n):
+            self.cv[i] = view_of(corners[i])
+            self.sv[i] = view_of(surfs[i])
+        return self
+
+
+class SequenceBatch:
+    """n independent sequences on one GPU (BASELINE config C-4): one Context per sequence, each on its own
+    stream, driven together through lmono_map_step_batch / lmono_map_step_device_batch so that their
+    registrations overlap on the device."""
+
+    def __init__(self, contexts):
+        self.ctxs = list(contexts)
+        n = self.n = len(self.ctxs)
+        assert n > 0
+        self.L = self.ctxs[0].L
+        self._h = (C.c_void_p * n)(*[c._h for c in self.ctxs])
+        self.args = BatchArgs(n)
+        self._w = (Pose * n)()
+        self._wm = (Pose * n)()
+        self._rep = (MapReport * n)()
+
+    # convenience setters on the default argument set
+    def set_odom(self, poses):
+        self.args.set_odom(poses)
+
+    def set_wmap_in(self, poses):
+        self.args.set_wmap_in(poses)
+
+    def set_device_inputs(self, *a):
+        self.args.set_device_inputs(*a)
+
+    def set_host_inputs(self, *a):
+        self.args.set_host_inputs(*a)
+
+    def step_device(self, join_stream=0, args=None):
+        """enqueue one registration per sequence on device-resident inputs (no host synchronisation)"""
+        a = args or self.args
+        rc = self.L.lmono_map_step_device_batch(self._h, self.n, a.dc, a.nc, a.ds, a.ns, a.odom,
+                                                a.wmap_in if a.use_wmap_in else None,
+                                                C.c_void_p(join_stream) if join_stream else None)
+        if rc:
+            raise LmonoError(rc, "map_step_device_batch")
+
+    def step(self, args=None):
+        """one registration per sequence through the host API (upload, step, read-back): [(q, t, report)] * n.
+        The reports are views of a buffer the next call overwrites."""
+        a = args or self.args
+        rc = self.L.lmono_map_step_batch(self._h, self.n, a.cv, a.sv, a.odom,
+                                         a.wmap_in if a.use_wmap_in else None, self._w, self._wm, self._rep)
+        if rc:
+            raise LmonoError(rc, "map_step_batch")
+        return [(np.array(self._w[i].q[:]), np.array(self._w[i].t[:]), self._rep[i]) for i in range(self.n)]
+
+    def collect(self):
+        return [c.map_collect() for c in self.ctxs]
+
+    def close(self):
+        for c in self.ctxs:
+            c.close()

@@ -14,14 +14,11 @@
 // reference's concatenation order (:533-537), so results are order-independent.
 #include "common.cuh"
 #include <float.h>
+#include <stdlib.h>
 
 constexpr int KNN_K = 5;
-constexpr int GROUP = 8;      // lanes per query, one candidate cell each (4 lanes x 2 cells issues fewer instructions per query but
-                              // measured slower on B200: 26.6 vs 23.1 us per launch -- the kernel wants the extra warps to hide latency)
+constexpr int GROUP_DEFAULT = 8;   // lanes per query (template parameter of the search kernels)
 
-struct Cand { float d; int idx; int ref; };   // ref: element index into the map type's cellpts pool
-
-__device__ __forceinline__ bool cand_less(float d1, int i1, float d2, int i2) { return d1 < d2 || (d1 == d2 && i1 < i2); }
 
 // ---- Eigen 3.3 SelfAdjointEigenSolver<Matrix3d> (same operation order as the test oracle, so the fit gates are reproducible)
 __device__ __forceinline__ void d_make_givens(double p, double q, double* c, double* s) {
@@ -330,101 +327,150 @@ __device__ __forceinline__ void d_fit_surf(const float4* nb, float4 ori, LmFacto
 }
 
 // ---- GROUP-lane exact 5-NN of one world-frame query against the window of one map type.
-// All lanes of the group call this with the same query; returns on every lane the merged
-// top-5 (d2, canonical idx, ref).  n_found < 5 leaves +inf / -1 entries.
-__device__ __forceinline__ void d_knn5_group(const LmMapType& M, const LmMapState* __restrict__ st,
-                                             const int32_t* __restrict__ slot_valid_rank, int ty, float qx, float qy, float qz,
-                                             int sub, unsigned gmask, float* od, int* oi, int* oref) {
-  float bd[KNN_K]; int bi[KNN_K]; int br[KNN_K];
+// Phase 1: lane `sub` resolves one of the (normally 8, at cube borders up to 27) candidate cells to its
+// (first element, count, concatenation offset).  Phase 2: the group scans the CONCATENATION of its cells
+// cooperatively -- an 8-lane prefix sum of the counts maps a flat candidate number f to (cell, offset), lane
+// `sub` takes f = sub, sub + 8, ... -- so the work is balanced over the lanes whatever the cell occupancies are and
+// a lane's loads are independent of each other (the per-cell scan this replaces was a dependent chain of up to
+// ~15 L2 loads on the fullest cell while the lanes of empty cells idled).  Only candidates with fp32 d2 < 1.0 can
+// matter (the :584,652 gate is on the 5th neighbour), the others are dropped before the top-5 insertion.
+// Candidates are ranked by the 64-bit key (d2 bits << 32 | canonical index): d2 >= 0, so the float bits order like
+// the value, and ties fall back to the index in the reference's concatenation order (:533-537).
+// All lanes of the group call this with the same query; every lane returns the merged top-5 (key, ref),
+// missing entries are key = ~0, ref = -1.
+constexpr unsigned long long KNN_NOKEY = ~0ull;
+
+__device__ __forceinline__ void d_top5_insert(unsigned long long (&tk)[KNN_K], int (&tr)[KNN_K], unsigned long long key, int ref) {
+  if (key < tk[KNN_K - 1]) {
+    tk[KNN_K - 1] = key; tr[KNN_K - 1] = ref;
 #pragma unroll
-  for (int k = 0; k < KNN_K; ++k) { bd[k] = FLT_MAX; bi[k] = 0x7fffffff; br[k] = -1; }
+    for (int k = KNN_K - 1; k > 0; --k) {
+      if (tk[k] < tk[k - 1]) {
+        const unsigned long long t = tk[k]; tk[k] = tk[k - 1]; tk[k - 1] = t;
+        const int r = tr[k]; tr[k] = tr[k - 1]; tr[k - 1] = r;
+      }
+    }
+  }
+}
+
+template <int GROUP>
+__device__ __forceinline__ void d_knn5_group(const float4* __restrict__ cellpts, const uint32_t* __restrict__ cellstart, int cap,
+                                             const int2* __restrict__ slot_info, int cen0, int cen1, int cen2,
+                                             float qx, float qy, float qz, int sub, unsigned gmask,
+                                             unsigned long long (&tk)[KNN_K], int (&tr)[KNN_K]) {
+#pragma unroll
+  for (int k = 0; k < KNN_K; ++k) { tk[k] = KNN_NOKEY; tr[k] = -1; }
 
   // per axis: the floors f-1..f+1 fall in the two cells c0 = (f-1)>>1 and c1 = c0 + 1; a cell belongs to one cube,
   // or to two when it straddles a 50 m border (at most one of c0 / c1 does): 2 or 3 (cube, local cell) pairs,
   // kept in scalar registers (no dynamically indexed arrays -> no local memory)
-  const int fq[3] = { (int)floorf(qx), (int)floorf(qy), (int)floorf(qz) };
+  constexpr int FQ_MAX = 1 << 24;     // beyond +-16.7 km an fp32 coordinate has no sub-metre neighbours left to find; keeps the integer maths in range
+  const int fq[3] = { min(max((int)floorf(qx), -FQ_MAX), FQ_MAX), min(max((int)floorf(qy), -FQ_MAX), FQ_MAX), min(max((int)floorf(qz), -FQ_MAX), FQ_MAX) };
   int e0[3], e1[3], e2[3], np[3];       // packed (cube << 8 | local cell)
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     const int c0 = (fq[a] - 1) >> 1, c1 = c0 + 1;
-    const int lo0 = d_floordiv(c0 + 12, 25), hi0 = d_floordiv(c0 + 13, 25);
-    const int lo1 = d_floordiv(c1 + 12, 25), hi1 = d_floordiv(c1 + 13, 25);
+    const int lo0 = d_floordiv25(c0 + 12), hi0 = d_floordiv25(c0 + 13);
+    const int lo1 = d_floordiv25(c1 + 12), hi1 = d_floordiv25(c1 + 13);
     e0[a] = lo0 * 256 + (c0 - (25 * lo0 - 13));
     if (hi0 != lo0)      { e1[a] = hi0 * 256 + (c0 - (25 * hi0 - 13)); e2[a] = lo1 * 256 + (c1 - (25 * lo1 - 13)); np[a] = 3; }
     else if (hi1 != lo1) { e1[a] = lo1 * 256 + (c1 - (25 * lo1 - 13)); e2[a] = hi1 * 256 + (c1 - (25 * hi1 - 13)); np[a] = 3; }
     else                 { e1[a] = lo1 * 256 + (c1 - (25 * lo1 - 13)); e2[a] = e1[a]; np[a] = 2; }
   }
   const int ncomb = np[0] * np[1] * np[2];
-  const int cen0 = st->cen[0], cen1 = st->cen[1], cen2 = st->cen[2];
-  for (int cmb = sub; cmb < ncomb; cmb += GROUP) {
-    const int ix = cmb % np[0], iy = (cmb / np[0]) % np[1], iz = cmb / (np[0] * np[1]);
-    const int ex = ix == 0 ? e0[0] : (ix == 1 ? e1[0] : e2[0]);
-    const int ey = iy == 0 ? e0[1] : (iy == 1 ? e1[1] : e2[1]);
-    const int ez = iz == 0 ? e0[2] : (iz == 1 ? e1[2] : e2[2]);
-    const int gi = ex >> 8, ci = ex & 255, gj = ey >> 8, cj = ey & 255, gk = ez >> 8, ck = ez & 255;
-    const int li = gi + cen0, lj = gj + cen1, lk = gk + cen2;
-    if (li < 0 || li >= LM_GW || lj < 0 || lj >= LM_GH || lk < 0 || lk >= LM_GD) continue;
-    const int ps = d_phys_slot(gi, gj, gk);
-    const int rank = slot_valid_rank[ps];
-    if (rank < 0) continue;
-    const int sid = M.slot_slab[ps];
-    if (sid < 0) continue;
-    const int cell = ci + LM_CELLS_AXIS * (cj + LM_CELLS_AXIS * ck);
-    const uint32_t* cs = M.cellstart + (size_t)sid * (LM_NCELL + 1);
-    const uint32_t b = cs[cell], e = cs[cell + 1];
-    if (b >= e) continue;
-    const int base_idx = st->valid_off[ty][rank];
-    const float4* cp = M.cellpts + (size_t)sid * M.cap;
-    float4 p = cp[b];
-    for (uint32_t t = b; t < e; ++t) {
-      const float4 pn = cp[t + 1 < e ? t + 1 : t];          // next point in flight while this one is ranked
-      const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
-      float d = __fmul_rn(dx, dx);
-      d = __fadd_rn(d, __fmul_rn(dy, dy));
-      d = __fadd_rn(d, __fmul_rn(dz, dz));
-      const int idx = base_idx + __float_as_int(p.w);
-      if (cand_less(d, idx, bd[KNN_K - 1], bi[KNN_K - 1])) {
-        bd[KNN_K - 1] = d; bi[KNN_K - 1] = idx; br[KNN_K - 1] = sid * M.cap + (int)t;
-#pragma unroll
-        for (int k = KNN_K - 1; k > 0; --k) {
-          if (cand_less(bd[k], bi[k], bd[k - 1], bi[k - 1])) {
-            float td = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td;
-            int ti = bi[k]; bi[k] = bi[k - 1]; bi[k - 1] = ti;
-            int tr = br[k]; br[k] = br[k - 1]; br[k - 1] = tr;
-          }
+  for (int cb = 0; cb < ncomb; cb += GROUP) {        // group-uniform trip count: 1, or up to 4 next to a cube border
+    const int cmb = cb + sub;
+    int cnt = 0, start = 0, bidx = 0;
+    if (cmb < ncomb) {
+      int r = cmb;                                   // mixed radix (np[0], np[1], np[2]), every radix 2 or 3: constant divisors only
+      const int ix = np[0] == 2 ? (r & 1) : (r % 3); r = np[0] == 2 ? (r >> 1) : (r / 3);
+      const int iy = np[1] == 2 ? (r & 1) : (r % 3); r = np[1] == 2 ? (r >> 1) : (r / 3);
+      const int iz = r;
+      const int ex = ix == 0 ? e0[0] : (ix == 1 ? e1[0] : e2[0]);
+      const int ey = iy == 0 ? e0[1] : (iy == 1 ? e1[1] : e2[1]);
+      const int ez = iz == 0 ? e0[2] : (iz == 1 ? e1[2] : e2[2]);
+      const int gi = ex >> 8, ci = ex & 255, gj = ey >> 8, cj = ey & 255, gk = ez >> 8, ck = ez & 255;
+      const int li = gi + cen0, lj = gj + cen1, lk = gk + cen2;
+      if (li >= 0 && li < LM_GW && lj >= 0 && lj < LM_GH && lk >= 0 && lk < LM_GD) {
+        const int2 inf = slot_info[d_phys_slot(gi, gj, gk)];       // {slab, concatenation offset}; slab < 0: not in the window / empty
+        if (inf.x >= 0) {
+          const uint32_t* cs = cellstart + (size_t)inf.x * (LM_NCELL + 1) + (ci + LM_CELLS_AXIS * (cj + LM_CELLS_AXIS * ck));
+          const uint32_t b = cs[0], e = cs[1];
+          cnt = (int)(e - b); start = inf.x * cap + (int)b; bidx = inf.y;
         }
       }
-      p = pn;
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < GROUP; o <<= 1) { const int t = __shfl_up_sync(gmask, incl, o, GROUP); if (sub >= o) incl += t; }
+    const int total = __shfl_sync(gmask, incl, GROUP - 1, GROUP);
+    start -= incl - cnt;                             // flat candidate f of this lane's cell lives at cellpts[start + f]
+    int bound[GROUP > 1 ? GROUP - 1 : 1];
+#pragma unroll
+    for (int c = 0; c < GROUP - 1; ++c) bound[c] = __shfl_sync(gmask, incl, c, GROUP);
+    for (int fb = 0; fb < total; fb += 2 * GROUP) {  // two independent candidates per lane and trip
+      const int fA = fb + sub, fB = fA + GROUP;
+      int cellA = 0, cellB = 0;
+#pragma unroll
+      for (int c = 0; c < GROUP - 1; ++c) { cellA += fA >= bound[c]; cellB += fB >= bound[c]; }
+      const int sA = __shfl_sync(gmask, start, cellA, GROUP), bA = __shfl_sync(gmask, bidx, cellA, GROUP);
+      const int sB = __shfl_sync(gmask, start, cellB, GROUP), bB = __shfl_sync(gmask, bidx, cellB, GROUP);
+      const bool vA = fA < total, vB = fB < total;
+      const int rA = vA ? sA + fA : 0, rB = vB ? sB + fB : 0;
+      const float4 pA = cellpts[rA];
+      const float4 pB = cellpts[rB];
+      {
+        const float dx = __fsub_rn(qx, pA.x), dy = __fsub_rn(qy, pA.y), dz = __fsub_rn(qz, pA.z);
+        float d = __fmul_rn(dx, dx);
+        d = __fadd_rn(d, __fmul_rn(dy, dy));
+        d = __fadd_rn(d, __fmul_rn(dz, dz));
+        if (vA && d < 1.0f)
+          d_top5_insert(tk, tr, ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)(bA + __float_as_int(pA.w)), rA);
+      }
+      {
+        const float dx = __fsub_rn(qx, pB.x), dy = __fsub_rn(qy, pB.y), dz = __fsub_rn(qz, pB.z);
+        float d = __fmul_rn(dx, dx);
+        d = __fadd_rn(d, __fmul_rn(dy, dy));
+        d = __fadd_rn(d, __fmul_rn(dz, dz));
+        if (vB && d < 1.0f)
+          d_top5_insert(tk, tr, ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)(bB + __float_as_int(pB.w)), rB);
+      }
     }
   }
-  // merge the GROUP sorted lists: 5 rounds of (min over lane heads, owner pops)
+  // merge the GROUP sorted lists: 5 rounds of (min over the lane heads, the owner pops); canonical indices are unique,
+  // so exactly one lane holds the minimum
+  unsigned long long ok_[KNN_K]; int or_[KNN_K];
   int head = 0;
 #pragma unroll
   for (int k = 0; k < KNN_K; ++k) {
-    float hd = FLT_MAX; int hi = 0x7fffffff, hr = -1;
+    unsigned long long hk = KNN_NOKEY; int hr = -1;
 #pragma unroll
-    for (int j = 0; j < KNN_K; ++j) if (head == j) { hd = bd[j]; hi = bi[j]; hr = br[j]; }
-    float md = hd; int mi = hi, mr = hr;
+    for (int j = 0; j < KNN_K; ++j) if (head == j) { hk = tk[j]; hr = tr[j]; }
+    unsigned long long mk = hk;
 #pragma unroll
     for (int o = GROUP / 2; o > 0; o >>= 1) {
-      float od2 = __shfl_xor_sync(gmask, md, o);
-      int oi2 = __shfl_xor_sync(gmask, mi, o);
-      int or2 = __shfl_xor_sync(gmask, mr, o);
-      if (cand_less(od2, oi2, md, mi)) { md = od2; mi = oi2; mr = or2; }
+      const unsigned long long t = __shfl_xor_sync(gmask, mk, o);
+      mk = t < mk ? t : mk;
     }
-    if (head < KNN_K && hi == mi && hr == mr && hr >= 0) head++;   // canonical indices are unique
-    od[k] = md; oi[k] = (mr >= 0) ? mi : -1; oref[k] = mr;
+    const bool mine = hk == mk && mk != KNN_NOKEY;
+    const unsigned owners = __ballot_sync(gmask, mine);
+    const int mr = __shfl_sync(gmask, hr, owners ? __ffs(owners) - 1 : 0);
+    if (mine) head++;
+    ok_[k] = mk; or_[k] = owners ? mr : -1;
   }
+#pragma unroll
+  for (int k = 0; k < KNN_K; ++k) { tk[k] = ok_[k]; tr[k] = or_[k]; }
 }
 
 // Association = two launches.  k_assoc_knn: one GROUP-lane group per query (both map types in one launch), light on
 // registers so every query of a sweep is resident at once; it leaves the 5 neighbour references (or -1 when the
 // d2[4] < 1.0 gate of :584,652 fails).  k_assoc_fit: one thread per query for the fp64 line / plane fit -- with the
 // fits inside the search kernel all but one lane of a group idled through the fp64 tail and its registers halved occupancy.
-__global__ void __launch_bounds__(256, 4) k_assoc_knn(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1,
-                                                   const int32_t* __restrict__ slot_valid_rank,
-                                                   const float4* __restrict__ stack0, const float4* __restrict__ stack1,
-                                                   int32_t* __restrict__ nnref) {
+template <int GROUP>
+__device__ __forceinline__ void d_assoc_knn(LmMapState* __restrict__ st, const LmMapType& M0, const LmMapType& M1,
+                                            const int32_t* __restrict__ slot_valid_rank,
+                                            const float4* __restrict__ stack0, const float4* __restrict__ stack1,
+                                            int32_t* __restrict__ nnref) {
   if (!st->optimize) return;
   const int n0 = st->stack_n[0], n1 = st->stack_n[1];
   const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / GROUP;
@@ -433,7 +479,6 @@ __global__ void __launch_bounds__(256, 4) k_assoc_knn(LmMapState* __restrict__ s
   if (gid >= n0 + n1) return;
   const int ty = gid < n0 ? 0 : 1;
   const int qi = ty == 0 ? gid : gid - n0;
-  const LmMapType& M = ty == 0 ? M0 : M1;
   const float4 ori = ty == 0 ? stack0[qi] : stack1[qi];
   const float4 sel = d_associate(st->q_w_curr, st->t_w_curr, ori);
   int32_t* out = nnref + (size_t)gid * KNN_K;
@@ -443,12 +488,26 @@ __global__ void __launch_bounds__(256, 4) k_assoc_knn(LmMapState* __restrict__ s
       return;
     }
   }
-  float d[KNN_K]; int idx[KNN_K], ref[KNN_K];
-  d_knn5_group(M, st, slot_valid_rank, ty, sel.x, sel.y, sel.z, sub, gmask, d, idx, ref);
-  if (sub != 0) return;
-  const bool ok = ref[KNN_K - 1] >= 0 && d[KNN_K - 1] < 1.0f;
+  unsigned long long key[KNN_K]; int ref[KNN_K];
+  d_knn5_group<GROUP>(ty == 0 ? M0.cellpts : M1.cellpts, ty == 0 ? M0.cellstart : M1.cellstart, ty == 0 ? M0.cap : M1.cap,
+               lm_slot_info(slot_valid_rank) + ty * LM_NSLOT, st->cen[0], st->cen[1], st->cen[2],
+               sel.x, sel.y, sel.z, sub, gmask, key, ref);
+  // every kept candidate has d2 < 1.0, so the :584,652 gate is "a 5th neighbour exists"
+  const bool ok = ref[KNN_K - 1] >= 0;
+  if (GROUP >= 8) {          // lanes 0..4 store one reference each
+    int mine = ref[0];
 #pragma unroll
-  for (int k = 0; k < KNN_K; ++k) out[k] = ok ? ref[k] : -1;
+    for (int k = 1; k < KNN_K; ++k) if (sub == k) mine = ref[k];
+    if (sub < KNN_K) out[sub] = ok ? mine : -1;
+  } else if (sub == 0) {
+#pragma unroll
+    for (int k = 0; k < KNN_K; ++k) out[k] = ok ? ref[k] : -1;
+  }
+}
+template <int GROUP>
+__global__ void __launch_bounds__(256, 4) k_assoc_knn(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, const int32_t* __restrict__ slot_valid_rank,
+                                                   const float4* __restrict__ stack0, const float4* __restrict__ stack1, int32_t* __restrict__ nnref) {
+  d_assoc_knn<GROUP>(st, M0, M1, slot_valid_rank, stack0, stack1, nnref);
 }
 
 __global__ void __launch_bounds__(128) k_assoc_fit(const LmMapState* __restrict__ st, LmMapType M0, LmMapType M1,
@@ -478,8 +537,12 @@ __global__ void __launch_bounds__(128) k_assoc_fit(const LmMapState* __restrict_
 int lm_map_associate(lmono_ctx* ctx, int n_max_corner, int n_max_surf) {
   const int nq = n_max_corner + n_max_surf;
   if (nq <= 0) return LMONO_OK;
-  k_assoc_knn<<<lm_div_up(nq * GROUP, 256), 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_slot_valid_rank,
-                                                                  ctx->d_stack[0], ctx->d_stack[1], ctx->d_nnref);
+  static const int group = getenv("LMONO_KNN_GROUP") ? atoi(getenv("LMONO_KNN_GROUP")) : GROUP_DEFAULT;     // experiment switch
+#define KNN_ARGS ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_slot_valid_rank, ctx->d_stack[0], ctx->d_stack[1], ctx->d_nnref
+  if (group == 1) k_assoc_knn<1><<<lm_div_up(nq * 1, 256), 256, 0, ctx->stream>>>(KNN_ARGS);
+  else if (group == 2) k_assoc_knn<2><<<lm_div_up(nq * 2, 256), 256, 0, ctx->stream>>>(KNN_ARGS);
+  else if (group == 4) k_assoc_knn<4><<<lm_div_up(nq * 4, 256), 256, 0, ctx->stream>>>(KNN_ARGS);
+  else k_assoc_knn<8><<<lm_div_up(nq * 8, 256), 256, 0, ctx->stream>>>(KNN_ARGS);   // k_assoc_knn<<<
   LM_LAUNCH_CHECK();
   k_assoc_fit<<<lm_div_up(nq, 128), 128, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_stack[0], ctx->d_stack[1],
                                                           ctx->d_nnref, ctx->d_fac[0], ctx->d_fac[1]);
@@ -487,7 +550,9 @@ int lm_map_associate(lmono_ctx* ctx, int n_max_corner, int n_max_surf) {
   return LMONO_OK;
 }
 
-// test hook: world-frame queries, raw 5-NN output
+// test hook: world-frame queries, 5-NN output restricted to the neighbours the gate can see (d2 < 1.0); entries
+// beyond that are idx = -1, d2 = +inf
+constexpr int GROUP = GROUP_DEFAULT;
 __global__ void __launch_bounds__(256) k_knn5_hook(const LmMapState* __restrict__ st, LmMapType M, int ty,
                                                    const int32_t* __restrict__ slot_valid_rank,
                                                    const float4* __restrict__ q, int n, int32_t* __restrict__ oidx, float* __restrict__ od2) {
@@ -496,14 +561,15 @@ __global__ void __launch_bounds__(256) k_knn5_hook(const LmMapState* __restrict_
   const unsigned gmask = ((1u << GROUP) - 1u) << ((threadIdx.x & 31) & ~(GROUP - 1));
   if (gid >= n) return;
   const float4 p = q[gid];
-  float d[KNN_K]; int idx[KNN_K], ref[KNN_K];
-  d_knn5_group(M, st, slot_valid_rank, ty, p.x, p.y, p.z, sub, gmask, d, idx, ref);
+  unsigned long long key[KNN_K]; int ref[KNN_K];
+  d_knn5_group<GROUP>(M.cellpts, M.cellstart, M.cap, lm_slot_info(slot_valid_rank) + ty * LM_NSLOT, st->cen[0], st->cen[1], st->cen[2],
+               p.x, p.y, p.z, sub, gmask, key, ref);
   if (sub != 0) return;
 #pragma unroll
   for (int k = 0; k < KNN_K; ++k) {
     const bool ok = ref[k] >= 0;
-    oidx[gid * KNN_K + k] = ok ? idx[k] : -1;
-    od2[gid * KNN_K + k] = ok ? d[k] : INFINITY;
+    oidx[gid * KNN_K + k] = ok ? (int)(unsigned)(key[k] & 0xffffffffull) : -1;
+    od2[gid * KNN_K + k] = ok ? __uint_as_float((unsigned)(key[k] >> 32)) : INFINITY;
   }
 }
 

@@ -137,6 +137,7 @@ struct lmono_ctx {
   int last_cuda_error;
   int64_t launches;
   cudaEvent_t ev0, ev1;
+  cudaEvent_t ev_fork;          // fork point of a sequence batch (lmono_map_step_device_batch)
 
   LmMapType map[2];
   LmMapState* d_state;
@@ -210,8 +211,11 @@ static inline int lm_div_up(int a, int b) { return (a + b - 1) / b; }
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned long long d_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define LM_STAMP(buf, slot) do { if ((buf) != nullptr && threadIdx.x == 0 && blockIdx.x == 0) (buf)[(slot)] = d_globaltimer(); } while (0)
-__device__ __forceinline__ int d_pmod(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
+// a mod m in [0, m) for |a| < m * 2^22 (cube coordinates, window offsets): one unsigned remainder by a constant, no sign fix-up
+__device__ __forceinline__ int d_pmod(int a, int m) { return (int)((unsigned)(a + m * (1 << 22)) % (unsigned)m); }
 __device__ __forceinline__ int d_floordiv(int a, int b) { int q = a / b; if ((a % b != 0) && ((a < 0) != (b < 0))) --q; return q; }
+// floor(a / 25) for |a| < 2^25 (2 m cell coordinates): unsigned division by a constant
+__device__ __forceinline__ int d_floordiv25(int a) { return (int)((unsigned)(a + 25 * (1 << 21)) / 25u) - (1 << 21); }
 
 // cube coordinate of a world value: (int)((v + 25.0) / 50.0) + cen, minus one if v + 25.0 < 0
 // (Aloam/src/laserMapping.cpp:312-321, 741-750)
@@ -220,6 +224,11 @@ __device__ __forceinline__ int d_cube_coord(double v, int cen) {
   if (v + 25.0 < 0) c--;
   return c;
 }
+// the slot tables share one allocation: [0, LM_NSLOT) window rank of a physical slot (-1 = outside the window), then
+// int2 {slab id or -1, concatenation offset} per map type (k_begin_step)
+constexpr int LM_SLOT_TABLE_INTS = (LM_NSLOT + 1) + 4 * LM_NSLOT;
+__host__ __device__ __forceinline__ int2* lm_slot_info(int32_t* slot_valid_rank) { return reinterpret_cast<int2*>(slot_valid_rank + LM_NSLOT + 1); }
+__host__ __device__ __forceinline__ const int2* lm_slot_info(const int32_t* slot_valid_rank) { return reinterpret_cast<const int2*>(slot_valid_rank + LM_NSLOT + 1); }
 __device__ __forceinline__ int d_phys_slot(int gi, int gj, int gk) {
   return d_pmod(gi, LM_GW) + LM_GW * d_pmod(gj, LM_GH) + LM_GW * LM_GH * d_pmod(gk, LM_GD);
 }

@@ -78,13 +78,14 @@ extern "C" int lmono_create(int device, const lmono_params* params, void* stream
   if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
   else { LM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
   LM_CUDA(cudaEventCreate(&ctx->ev0)); LM_CUDA(cudaEventCreate(&ctx->ev1));
+  LM_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
 
   LM_CUDA(cudaMalloc((void**)&ctx->d_state, sizeof(LmMapState)));
   LM_CUDA(cudaMallocHost((void**)&ctx->h_state, sizeof(LmMapState)));
   LM_CUDA(cudaMalloc((void**)&ctx->d_lm, sizeof(LmLmState)));
   LM_CUDA(cudaMemsetAsync(ctx->d_lm, 0, sizeof(LmLmState), ctx->stream));
-  LM_CUDA(cudaMalloc((void**)&ctx->d_slot_valid_rank, sizeof(int32_t) * LM_NSLOT));
-  LM_CUDA(cudaMemsetAsync(ctx->d_slot_valid_rank, 0xFF, sizeof(int32_t) * LM_NSLOT, ctx->stream));
+  LM_CUDA(cudaMalloc((void**)&ctx->d_slot_valid_rank, sizeof(int32_t) * LM_SLOT_TABLE_INTS));
+  LM_CUDA(cudaMemsetAsync(ctx->d_slot_valid_rank, 0xFF, sizeof(int32_t) * LM_SLOT_TABLE_INTS, ctx->stream));
   LM_CUDA(cudaMalloc((void**)&ctx->d_partials, sizeof(double) * 32 * (1024 + 8)));
   LM_CUDA(cudaMalloc((void**)&ctx->d_stamps, sizeof(unsigned long long) * 4096));
   LM_CUDA(cudaMemsetAsync(ctx->d_stamps, 0, sizeof(unsigned long long) * 4096, ctx->stream));
@@ -139,7 +140,7 @@ extern "C" void lmono_destroy(lmono_ctx* ctx) {
   for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_in[i]); cudaFree(ctx->d_stack[i]); cudaFree(ctx->d_world[i]); cudaFree(ctx->d_fac[i]); }
   cudaFree(ctx->d_sort_a); cudaFree(ctx->d_sort_b); cudaFree(ctx->d_sort_c); cudaFree(ctx->d_blockcnt); cudaFree(ctx->d_tmp_i32);
   cudaFree(ctx->d_vg); cudaFree(ctx->d_full); cudaFree(ctx->d_slot_first); cudaFree(ctx->d_slot_base); cudaFree(ctx->d_export_off); cudaFree(ctx->d_export);
-  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_fork);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   free(ctx);
 }

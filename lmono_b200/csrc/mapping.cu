@@ -35,10 +35,14 @@ __global__ void k_set_counts(LmMapState* st, int n0, int n1) {
 
 // every per-step scalar (feature counts, odometry pose) enters through this one launch, so the rest of
 // the step is a parameter-free kernel sequence that can be replayed as a CUDA graph
-struct StepArgs { double q[4]; double t[3]; int n0, n1; };
+struct StepArgs { double q[4]; double t[3]; int n0, n1; int set_wmap; double wq[4]; double wt[3]; };
 __global__ void k_step_args(LmMapState* st, StepArgs a) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   st->raw_n[0] = a.n0; st->raw_n[1] = a.n1;
+  if (a.set_wmap) {       // caller-supplied q/t_wmap_wodom (sequence batches; same effect as lmono_map_set_state before the step)
+    for (int k = 0; k < 4; ++k) st->q_wmap_wodom[k] = a.wq[k];
+    for (int k = 0; k < 3; ++k) st->t_wmap_wodom[k] = a.wt[k];
+  }
   for (int k = 0; k < 4; ++k) st->q_wodom_curr[k] = a.q[k];
   for (int k = 0; k < 3; ++k) st->t_wodom_curr[k] = a.t[k];
 }
@@ -88,7 +92,8 @@ static int bucket_up(int n, int cap) {
 }
 
 // enqueue the whole step on inputs that are already float4 XYZI in device memory
-static int enqueue_step(lmono_ctx* ctx, const float4* d_corner, int nc, const float4* d_surf, int ns, const lmono_pose* wodom_curr) {
+static int enqueue_step(lmono_ctx* ctx, const float4* d_corner, int nc, const float4* d_surf, int ns, const lmono_pose* wodom_curr,
+                        const lmono_pose* wmap_in = nullptr) {
   if (nc < 0 || ns < 0 || nc > ctx->max_feat || ns > ctx->max_feat) return LMONO_E_CAPACITY;
   int rc;
   LM_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -97,6 +102,8 @@ static int enqueue_step(lmono_ctx* ctx, const float4* d_corner, int nc, const fl
   for (int k = 0; k < 4; ++k) a.q[k] = wodom_curr->q[k];
   for (int k = 0; k < 3; ++k) a.t[k] = wodom_curr->t[k];
   a.n0 = nc; a.n1 = ns;
+  a.set_wmap = wmap_in != nullptr;
+  if (wmap_in) { for (int k = 0; k < 4; ++k) a.wq[k] = wmap_in->q[k]; for (int k = 0; k < 3; ++k) a.wt[k] = wmap_in->t[k]; }
   k_step_args<<<1, 32, 0, ctx->stream>>>(ctx->d_state, a);
   LM_LAUNCH_CHECK();
   const int nc_cap = bucket_up(nc, ctx->max_feat), ns_cap = bucket_up(ns, ctx->max_feat);
@@ -237,8 +244,8 @@ static void fill_report(const LmMapState* h, lmono_map_report* r, float ms) {
   r->ms_gpu = ms;
 }
 
-static int collect(lmono_ctx* ctx, lmono_pose* w_curr, lmono_pose* wmap_wodom, lmono_map_report* report) {
-  LM_CUDA(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(LmMapState), cudaMemcpyDeviceToHost, ctx->stream));
+static int collect(lmono_ctx* ctx, lmono_pose* w_curr, lmono_pose* wmap_wodom, lmono_map_report* report, bool copy = true) {
+  if (copy) LM_CUDA(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(LmMapState), cudaMemcpyDeviceToHost, ctx->stream));
   LM_CUDA(cudaStreamSynchronize(ctx->stream));
   const LmMapState* h = ctx->h_state;
   if (w_curr) { memcpy(w_curr->q, h->q_w_curr, sizeof(w_curr->q)); memcpy(w_curr->t, h->t_w_curr, sizeof(w_curr->t)); }
@@ -285,6 +292,64 @@ extern "C" int lmono_map_step(lmono_ctx* ctx, lmono_cloud_view corner_last, lmon
   if (want_full) { int rc2 = lm_download_cloud(ctx, ctx->d_full, full_res.n, registered); if (!rc) rc = rc2; }
   else if (registered) registered->n_out = 0;
   return rc;
+}
+
+// ---- sequence batches (config C-4): n independent ctxs driven from one host thread, overlapping on the device
+static int step_async(lmono_ctx* ctx, lmono_cloud_view corner_last, lmono_cloud_view surf_last, const lmono_pose* wodom_curr, const lmono_pose* wmap_in) {
+  if (corner_last.n > ctx->max_feat || surf_last.n > ctx->max_feat) return LMONO_E_CAPACITY;
+  int rc;
+  if ((rc = lm_upload_cloud(ctx, corner_last, ctx->d_raw[0], ctx->d_in[0], nullptr))) return rc;
+  if ((rc = lm_upload_cloud(ctx, surf_last, ctx->d_raw[1], ctx->d_in[1], nullptr))) return rc;
+  return enqueue_step(ctx, ctx->d_in[0], corner_last.n, ctx->d_in[1], surf_last.n, wodom_curr, wmap_in);
+}
+
+extern "C" int lmono_map_step_async(lmono_ctx* ctx, lmono_cloud_view corner_last, lmono_cloud_view surf_last, const lmono_pose* wodom_curr) {
+  if (!ctx || !wodom_curr) return LMONO_E_ARG;
+  return step_async(ctx, corner_last, surf_last, wodom_curr, nullptr);
+}
+
+extern "C" int lmono_map_step_batch(lmono_ctx* const* ctxs, int32_t n, const lmono_cloud_view* corner_last, const lmono_cloud_view* surf_last,
+                                    const lmono_pose* wodom_curr, const lmono_pose* wmap_wodom_in,
+                                    lmono_pose* w_curr, lmono_pose* wmap_wodom, lmono_map_report* reports) {
+  if (!ctxs || n < 0 || !corner_last || !surf_last || !wodom_curr) return LMONO_E_ARG;
+  int first = LMONO_OK;
+  for (int i = 0; i < n; ++i) {
+    if (!ctxs[i]) return LMONO_E_ARG;
+    int rc = step_async(ctxs[i], corner_last[i], surf_last[i], &wodom_curr[i], wmap_wodom_in ? &wmap_wodom_in[i] : nullptr);
+    if (!rc) {     // read-back queued right behind the step, so that the collect loop below only waits
+      lmono_ctx* ctx = ctxs[i];
+      cudaError_t e = cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(LmMapState), cudaMemcpyDeviceToHost, ctx->stream);
+      if (e != cudaSuccess) { ctx->last_cuda_error = (int)e; rc = LMONO_E_CUDA; }
+    }
+    if (rc && !first) first = rc;
+  }
+  for (int i = 0; i < n; ++i) {
+    int rc = collect(ctxs[i], w_curr ? &w_curr[i] : nullptr, wmap_wodom ? &wmap_wodom[i] : nullptr, reports ? &reports[i] : nullptr, false);
+    if (rc && !first) first = rc;
+  }
+  return first;
+}
+
+extern "C" int lmono_map_step_device_batch(lmono_ctx* const* ctxs, int32_t n, const void* const* d_corner, const int32_t* n_corner,
+                                           const void* const* d_surf, const int32_t* n_surf, const lmono_pose* wodom_curr,
+                                           const lmono_pose* wmap_wodom_in, void* join_stream) {
+  if (!ctxs || n < 0 || !d_corner || !d_surf || !n_corner || !n_surf || !wodom_curr) return LMONO_E_ARG;
+  if (n == 0) return LMONO_OK;
+  cudaStream_t js = (cudaStream_t)join_stream;
+  if (js) {
+    lmono_ctx* ctx = ctxs[0];
+    LM_CUDA(cudaEventRecord(ctx->ev_fork, js));
+  }
+  for (int i = 0; i < n; ++i) {
+    lmono_ctx* ctx = ctxs[i];
+    if (!ctx) return LMONO_E_ARG;
+    if (js) LM_CUDA(cudaStreamWaitEvent(ctx->stream, ctxs[0]->ev_fork, 0));
+    int rc;
+    if ((rc = enqueue_step(ctx, (const float4*)d_corner[i], n_corner[i], (const float4*)d_surf[i], n_surf[i], &wodom_curr[i],
+                           wmap_wodom_in ? &wmap_wodom_in[i] : nullptr))) return rc;
+    if (js) LM_CUDA(cudaStreamWaitEvent(js, ctx->ev1, 0));      // ev1 closes the step on the ctx stream
+  }
+  return LMONO_OK;
 }
 
 extern "C" int lmono_map_get_state(lmono_ctx* ctx, lmono_pose* wmap_wodom, int32_t cen[3]) {

@@ -156,7 +156,11 @@ __global__ void __launch_bounds__(256) k_begin_step(LmMapState* __restrict__ st,
       if (all || ((mi >> pi) & 1u) || ((mj >> pj) & 1u) || ((mk >> pk) & 1u)) { d_free_slot(M0, ps); d_free_slot(M1, ps); }
     }
   }
-  for (int ps = threadIdx.x; ps < LM_NSLOT; ps += blockDim.x) slot_valid_rank[ps] = -1;
+  int2* slot_info = lm_slot_info(slot_valid_rank);
+  for (int ps = threadIdx.x; ps < LM_NSLOT; ps += blockDim.x) {
+    slot_valid_rank[ps] = -1;
+    slot_info[ps] = make_int2(-1, 0); slot_info[LM_NSLOT + ps] = make_int2(-1, 0);
+  }
   __syncthreads();
   // valid cubes in the reference's loop order (i outer, j, k inner; :512-529), one thread per cube: the clipped
   // window is a product of index ranges, so the rank of (i, j, k) in loop order is closed-form
@@ -198,6 +202,14 @@ __global__ void __launch_bounds__(256) k_begin_step(LmMapState* __restrict__ st,
   }
   __syncthreads();
   if (threadIdx.x == 0) st->optimize = (s_n[0][127] > 10 && s_n[1][127] > 50) ? 1 : 0;   // :554
+  // search table of the association kernels: physical slot -> (slab id, index of the cube's first point in the
+  // :533-537 concatenation), one 8-byte load per (query, cube) instead of three dependent ones
+  if ((int)threadIdx.x < vn) {
+    const int r = threadIdx.x;
+    const int ps = st->valid_slot[r];
+    slot_info[ps] = make_int2(M0.slot_slab[ps], st->valid_off[0][r]);
+    slot_info[LM_NSLOT + ps] = make_int2(M1.slot_slab[ps], st->valid_off[1][r]);
+  }
 }
 
 int lm_map_begin_step(lmono_ctx* ctx, const lmono_pose* wodom_curr, const double* t_override) {
