@@ -152,18 +152,24 @@ int lmono_map_step_device(lmono_ctx* ctx, const void* d_corner_xyzi, int32_t n_c
                           const void* d_surf_xyzi, int32_t n_surf, const lmono_pose* wodom_curr);
 int lmono_map_collect(lmono_ctx* ctx, lmono_pose* w_curr, lmono_pose* wmap_wodom, lmono_map_report* report);
 
-/* Sequence batches (BASELINE config C-4: independent sequences per GPU).  One ctx per sequence, each created on
- * its own stream; a batch call drives n of them from one host thread so that their registrations overlap on
- * the device (every kernel of a step is small next to 148 SMs).  The reference runs one laserMapping process
- * per sequence (Aloam/src/laserMapping.cpp:931-934); this is the same independence with one process per GPU.
+/* Sequence batches (BASELINE config C-4: independent sequences per GPU).  One ctx per sequence; a batch call
+ * drives n of them from one host thread so that their registrations overlap on the device (every kernel of a
+ * step is small next to 148 SMs).  The reference runs one laserMapping process per sequence
+ * (Aloam/src/laserMapping.cpp:931-934); this is the same independence with one process per GPU.
+ * The steps of all n sequences run as parallel branches of ONE CUDA graph (cached in ctxs[0], max 64 sequences):
+ * a batch step costs the host one small argument launch + one graph launch.  The ctxs may share one stream
+ * (cheapest: nothing else to order) or own their streams (the batch is then ordered after the work already
+ * enqueued on each, and later work on each is ordered after the batch, with events).
  *   lmono_map_step_async        lmono_map_step without the final wait: uploads the features (asynchronous when the
- *                               host buffers are page-locked), enqueues the registration and the read-back of the
- *                               result; lmono_map_collect() waits for this ctx and returns it.
- *   lmono_map_step_batch        step_async on every ctx, then collect on every ctx, in order.  Arrays have n entries;
- *                               wmap_wodom_in (may be NULL) replaces q/t_wmap_wodom of ctx i before its step.
- *   lmono_map_step_device_batch device-resident inputs, enqueue-only.  If join_stream is not NULL the batch is ordered
- *                               after the work already enqueued on it, and work enqueued on it afterwards is ordered
- *                               after the whole batch (fork / join with events; no host synchronisation). */
+ *                               host buffers are page-locked), enqueues the registration;
+ *                               lmono_map_collect() waits for this ctx and returns the result.
+ *   lmono_map_step_batch        uploads for every ctx, the batch graph on the stream of ctxs[0], one wait, results in
+ *                               order.  Arrays have n entries; wmap_wodom_in (may be NULL) replaces q/t_wmap_wodom
+ *                               of ctx i before its step.
+ *   lmono_map_step_device_batch device-resident inputs, enqueue-only, on join_stream (NULL: the stream of ctxs[0]):
+ *                               ordered after the work already enqueued there, and work enqueued there afterwards is
+ *                               ordered after the whole batch (no host synchronisation).  The state of every
+ *                               sequence is read back inside the graph; lmono_map_collect() returns it. */
 int lmono_map_step_async(lmono_ctx* ctx, lmono_cloud_view corner_last, lmono_cloud_view surf_last, const lmono_pose* wodom_curr);
 int lmono_map_step_batch(lmono_ctx* const* ctxs, int32_t n, const lmono_cloud_view* corner_last, const lmono_cloud_view* surf_last,
                          const lmono_pose* wodom_curr, const lmono_pose* wmap_wodom_in /*may be NULL*/,

@@ -465,9 +465,9 @@ class BatchArgs:
 
 
 class SequenceBatch:
-    """n independent sequences on one GPU (BASELINE config C-4): one Context per sequence, each on its own
-    stream, driven together through lmono_map_step_batch / lmono_map_step_device_batch so that their
-    registrations overlap on the device."""
+    """n independent sequences on one GPU (BASELINE config C-4): one Context per sequence (sharing one stream, or
+    each on its own), driven together through lmono_map_step_batch / lmono_map_step_device_batch: the n
+    registrations of a step are parallel branches of one CUDA graph."""
 
     def __init__(self, contexts):
         self.ctxs = list(contexts)

@@ -90,6 +90,9 @@ struct LmMapState {
   // cube-sharded global map (shard.cu): shard_n <= 1 means "not sharded, every cube is mine"
   int32_t shard_rank, shard_n;
   int32_t shard_owned_n[2];              // points of OWNED window cubes (summed over ranks for the :554 gate)
+  // device pointers of this step's corner / surf features (written by k_step_args / k_batch_args), so that the
+  // captured kernel sequence does not depend on where the caller keeps its inputs
+  const float4* in_ptr[2];
 };
 
 struct LmMapType {           // one per map (0 corner, 1 surf); device pointers, passed by value
@@ -124,9 +127,15 @@ enum { LM_PROF_WINDOW = 0, LM_PROF_INDEX, LM_PROF_VOXEL, LM_PROF_ASSOC, LM_PROF_
 constexpr int LM_PROF_MAX_EVENTS = 2048;
 
 // ---------------------------------------------------------------- host ctx
-// One captured CUDA graph per (input pointers, launch-grid capacity bucket) of a laserMapping step.
-struct LmGraphEntry { const void* dc; const void* ds; int nc_cap, ns_cap; cudaGraphExec_t exec; int n_launch; };
+// One captured CUDA graph per launch-grid capacity bucket of a laserMapping step (inputs are read through
+// LmMapState::in_ptr, so the graph does not depend on the caller's buffers).
+struct LmGraphEntry { int nc_cap, ns_cap; cudaGraphExec_t exec; int n_launch; };
 constexpr int LM_MAX_GRAPHS = 64;
+// Sequence batches: ONE graph holds the steps of all n sequences as parallel branches (fork / join inside the
+// graph), so a batch step costs the host one small argument launch + one cudaGraphLaunch.  Cached in ctxs[0].
+constexpr int LM_BATCH_MAX = 64;
+constexpr int LM_MAX_BGRAPHS = 8;
+struct LmBatchGraph { int n; lmono_ctx* ctxs[LM_BATCH_MAX]; int nc_cap[LM_BATCH_MAX], ns_cap[LM_BATCH_MAX]; cudaGraphExec_t exec; int n_launch[LM_BATCH_MAX]; };
 constexpr int LM_GRAPH_BUCKET = 2048;     // launch grids are sized for counts rounded up to this
 
 struct lmono_ctx {
@@ -138,6 +147,12 @@ struct lmono_ctx {
   int64_t launches;
   cudaEvent_t ev0, ev1;
   cudaEvent_t ev_fork;          // fork point of a sequence batch (lmono_map_step_device_batch)
+  cudaEvent_t ev_join;          // end of this ctx's branch of a batch (capture join, or the legacy multi-stream join)
+  cudaEvent_t ev_sync;          // orders a batch graph after earlier work on this ctx's own stream
+  cudaEvent_t ev_done;          // (batch leader) the batch graph has finished on the origin stream
+  cudaStream_t* cap_streams;    // (batch leader) [LM_BATCH_MAX] branch streams, used only while capturing a batch graph
+  LmBatchGraph* bgraphs; int n_bgraphs;      // (batch leader) [LM_MAX_BGRAPHS]
+  bool step_timed;              // ev0 / ev1 bracket the pending step (false for steps that ran inside a batch graph)
 
   LmMapType map[2];
   LmMapState* d_state;
@@ -453,7 +468,8 @@ int lm_sort_u64(lmono_ctx* ctx, const unsigned long long* in, unsigned long long
 // voxel.cu: VoxelGrid of `in` (n_dev points, <= n_max) -> out, *out_n_dev; _multi runs up to LM_SORT_MAXSEG clouds through shared launches
 int lm_voxel_init(lmono_ctx* ctx);
 int lm_voxel_grid_multi(lmono_ctx* ctx, int nseg, const float4* const* in, const int32_t* const* n_dev, const int* n_max,
-                        const float* leaf, float4* const* out, int32_t* const* out_n_dev);
+                        const float* leaf, float4* const* out, int32_t* const* out_n_dev,
+                        const float4* const* const* in_ind = nullptr);   // in_ind[k] != NULL: read the input pointer from device memory
 int lm_voxel_grid_device(lmono_ctx* ctx, const float4* in, const int32_t* n_dev, int n_max, float leaf,
                          float4* out, int32_t* out_n_dev);
 // mapstore.cu

@@ -7,6 +7,7 @@ int lm_map_configure_kernels(lmono_ctx* ctx);
 void lm_scan_free(lmono_ctx* ctx);
 void lm_odom_free(lmono_ctx* ctx);
 void lm_color_free(lmono_ctx* ctx);
+void lm_batch_free(lmono_ctx* ctx);
 
 extern "C" void lmono_default_params(lmono_params* p) {
   memset(p, 0, sizeof(*p));
@@ -79,6 +80,9 @@ extern "C" int lmono_create(int device, const lmono_params* params, void* stream
   else { LM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
   LM_CUDA(cudaEventCreate(&ctx->ev0)); LM_CUDA(cudaEventCreate(&ctx->ev1));
   LM_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  LM_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  LM_CUDA(cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming));
+  LM_CUDA(cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming));
 
   LM_CUDA(cudaMalloc((void**)&ctx->d_state, sizeof(LmMapState)));
   LM_CUDA(cudaMallocHost((void**)&ctx->h_state, sizeof(LmMapState)));
@@ -131,6 +135,7 @@ extern "C" void lmono_destroy(lmono_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < ctx->n_graphs; ++i) cudaGraphExecDestroy(ctx->graphs[i].exec);
+  lm_batch_free(ctx);
   lm_scan_free(ctx);
   lm_odom_free(ctx);
   lm_color_free(ctx);
@@ -140,7 +145,7 @@ extern "C" void lmono_destroy(lmono_ctx* ctx) {
   for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_in[i]); cudaFree(ctx->d_stack[i]); cudaFree(ctx->d_world[i]); cudaFree(ctx->d_fac[i]); }
   cudaFree(ctx->d_sort_a); cudaFree(ctx->d_sort_b); cudaFree(ctx->d_sort_c); cudaFree(ctx->d_blockcnt); cudaFree(ctx->d_tmp_i32);
   cudaFree(ctx->d_vg); cudaFree(ctx->d_full); cudaFree(ctx->d_slot_first); cudaFree(ctx->d_slot_base); cudaFree(ctx->d_export_off); cudaFree(ctx->d_export);
-  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_fork);
+  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); cudaEventDestroy(ctx->ev_sync); cudaEventDestroy(ctx->ev_done);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   free(ctx);
 }

@@ -33,12 +33,12 @@ __global__ void k_set_counts(LmMapState* st, int n0, int n1) {
   if (threadIdx.x == 0 && blockIdx.x == 0) { st->raw_n[0] = n0; st->raw_n[1] = n1; }
 }
 
-// every per-step scalar (feature counts, odometry pose) enters through this one launch, so the rest of
-// the step is a parameter-free kernel sequence that can be replayed as a CUDA graph
-struct StepArgs { double q[4]; double t[3]; int n0, n1; int set_wmap; double wq[4]; double wt[3]; };
-__global__ void k_step_args(LmMapState* st, StepArgs a) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// every per-step scalar (feature counts, odometry pose, input pointers) enters through this one launch, so the rest
+// of the step is a parameter-free kernel sequence that can be replayed as a CUDA graph
+struct StepArgs { double q[4]; double t[3]; int n0, n1; int set_wmap; int pad; double wq[4]; double wt[3]; const float4* in[2]; };
+__device__ __forceinline__ void d_apply_step_args(LmMapState* st, const StepArgs& a) {
   st->raw_n[0] = a.n0; st->raw_n[1] = a.n1;
+  st->in_ptr[0] = a.in[0]; st->in_ptr[1] = a.in[1];
   if (a.set_wmap) {       // caller-supplied q/t_wmap_wodom (sequence batches; same effect as lmono_map_set_state before the step)
     for (int k = 0; k < 4; ++k) st->q_wmap_wodom[k] = a.wq[k];
     for (int k = 0; k < 3; ++k) st->t_wmap_wodom[k] = a.wt[k];
@@ -46,20 +46,34 @@ __global__ void k_step_args(LmMapState* st, StepArgs a) {
   for (int k = 0; k < 4; ++k) st->q_wodom_curr[k] = a.q[k];
   for (int k = 0; k < 3; ++k) st->t_wodom_curr[k] = a.t[k];
 }
+__global__ void k_step_args(LmMapState* st, StepArgs a) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  d_apply_step_args(st, a);
+}
+// the same for up to LM_ARGS_CHUNK sequences of a batch in one launch (one thread per sequence)
+constexpr int LM_ARGS_CHUNK = 16;
+struct BatchStepArgs { LmMapState* st[LM_ARGS_CHUNK]; StepArgs a[LM_ARGS_CHUNK]; int n; };
+static_assert(sizeof(BatchStepArgs) < 4000, "kernel parameter space");
+__global__ void k_batch_args(BatchStepArgs b) {
+  if (threadIdx.x < b.n) d_apply_step_args(b.st[threadIdx.x], b.a[threadIdx.x]);
+}
 
-// :542-550 VoxelGrid of the incoming corner and surf features, both clouds through the same four launches
+// :542-550 VoxelGrid of the incoming corner and surf features, both clouds through the same four launches.
+// d_corner / d_surf == NULL: read the input pointers from LmMapState::in_ptr (graph replay)
 static int voxel_both(lmono_ctx* ctx, const float4* d_corner, int nc, const float4* d_surf, int ns) {
   const float4* in[2] = { d_corner, d_surf };
+  const float4* const* ind[2] = { d_corner ? nullptr : &ctx->d_state->in_ptr[0], d_surf ? nullptr : &ctx->d_state->in_ptr[1] };
   const int32_t* n_dev[2] = { &ctx->d_state->raw_n[0], &ctx->d_state->raw_n[1] };
   const int n_max[2] = { nc, ns };
   const float leaf[2] = { ctx->map[0].leaf, ctx->map[1].leaf };
   float4* out[2] = { ctx->d_stack[0], ctx->d_stack[1] };
   int32_t* out_n[2] = { &ctx->d_state->stack_n[0], &ctx->d_state->stack_n[1] };
-  return lm_voxel_grid_multi(ctx, 2, in, n_dev, n_max, leaf, out, out_n);
+  return lm_voxel_grid_multi(ctx, 2, in, n_dev, n_max, leaf, out, out_n, ind);
 }
 
-// the step body: nc / ns only size the launch grids (every kernel reads the real counts from the state)
-static int enqueue_body(lmono_ctx* ctx, const float4* d_corner, int nc, const float4* d_surf, int ns) {
+// the step body: nc / ns only size the launch grids (every kernel reads the real counts and the input pointers
+// from the state)
+static int enqueue_body(lmono_ctx* ctx, int nc, int ns) {
   int rc;
   lm_prof_begin(ctx, LM_PROF_WINDOW);
   if ((rc = lm_map_begin_step(ctx, nullptr, nullptr))) return rc;           // :309-539
@@ -69,7 +83,7 @@ static int enqueue_body(lmono_ctx* ctx, const float4* d_corner, int nc, const fl
   lm_prof_end(ctx);
   // :542-550 VoxelGrid of the incoming features
   lm_prof_begin(ctx, LM_PROF_VOXEL);
-  if ((rc = voxel_both(ctx, d_corner, nc, d_surf, ns))) return rc;
+  if ((rc = voxel_both(ctx, nullptr, nc, nullptr, ns))) return rc;
   lm_prof_end(ctx);
   for (int iter = 0; iter < 2; ++iter) {                                    // :562
     lm_prof_begin(ctx, LM_PROF_ASSOC);
@@ -91,6 +105,17 @@ static int bucket_up(int n, int cap) {
   return (int)(b > cap ? cap : b);
 }
 
+static void fill_step_args(StepArgs* a, const float4* d_corner, int nc, const float4* d_surf, int ns, const lmono_pose* wodom_curr,
+                           const lmono_pose* wmap_in) {
+  memset(a, 0, sizeof(*a));
+  for (int k = 0; k < 4; ++k) a->q[k] = wodom_curr->q[k];
+  for (int k = 0; k < 3; ++k) a->t[k] = wodom_curr->t[k];
+  a->n0 = nc; a->n1 = ns;
+  a->in[0] = d_corner; a->in[1] = d_surf;
+  a->set_wmap = wmap_in != nullptr;
+  if (wmap_in) { for (int k = 0; k < 4; ++k) a->wq[k] = wmap_in->q[k]; for (int k = 0; k < 3; ++k) a->wt[k] = wmap_in->t[k]; }
+}
+
 // enqueue the whole step on inputs that are already float4 XYZI in device memory
 static int enqueue_step(lmono_ctx* ctx, const float4* d_corner, int nc, const float4* d_surf, int ns, const lmono_pose* wodom_curr,
                         const lmono_pose* wmap_in = nullptr) {
@@ -99,36 +124,32 @@ static int enqueue_step(lmono_ctx* ctx, const float4* d_corner, int nc, const fl
   LM_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
   lm_kmark(ctx, "begin", 0);
   StepArgs a;
-  for (int k = 0; k < 4; ++k) a.q[k] = wodom_curr->q[k];
-  for (int k = 0; k < 3; ++k) a.t[k] = wodom_curr->t[k];
-  a.n0 = nc; a.n1 = ns;
-  a.set_wmap = wmap_in != nullptr;
-  if (wmap_in) { for (int k = 0; k < 4; ++k) a.wq[k] = wmap_in->q[k]; for (int k = 0; k < 3; ++k) a.wt[k] = wmap_in->t[k]; }
+  fill_step_args(&a, d_corner, nc, d_surf, ns, wodom_curr, wmap_in);
   k_step_args<<<1, 32, 0, ctx->stream>>>(ctx->d_state, a);
   LM_LAUNCH_CHECK();
   const int nc_cap = bucket_up(nc, ctx->max_feat), ns_cap = bucket_up(ns, ctx->max_feat);
   if (!ctx->graphs_on || ctx->prof_on || ctx->kmark_on) {
-    if ((rc = enqueue_body(ctx, d_corner, nc_cap, d_surf, ns_cap))) return rc;
+    if ((rc = enqueue_body(ctx, nc_cap, ns_cap))) return rc;
   } else {
     LmGraphEntry* g = nullptr;
     for (int i = 0; i < ctx->n_graphs; ++i) {
       LmGraphEntry& e = ctx->graphs[i];
-      if (e.dc == d_corner && e.ds == d_surf && e.nc_cap == nc_cap && e.ns_cap == ns_cap) { g = &e; break; }
+      if (e.nc_cap == nc_cap && e.ns_cap == ns_cap) { g = &e; break; }
     }
     if (!g) {
-      if (ctx->n_graphs == LM_MAX_GRAPHS) {      // cache full: drop everything (callers normally cycle through few buffers)
+      if (ctx->n_graphs == LM_MAX_GRAPHS) {      // cache full: drop everything
         for (int i = 0; i < ctx->n_graphs; ++i) cudaGraphExecDestroy(ctx->graphs[i].exec);
         ctx->n_graphs = 0;
       }
       const int64_t l0 = ctx->launches;
       cudaGraph_t graph = nullptr;
       LM_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-      rc = enqueue_body(ctx, d_corner, nc_cap, d_surf, ns_cap);
+      rc = enqueue_body(ctx, nc_cap, ns_cap);
       cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
       if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
       LM_CUDA(ce);
       g = &ctx->graphs[ctx->n_graphs];
-      g->dc = d_corner; g->ds = d_surf; g->nc_cap = nc_cap; g->ns_cap = ns_cap;
+      g->nc_cap = nc_cap; g->ns_cap = ns_cap;
       g->n_launch = (int)(ctx->launches - l0);
       ctx->launches = l0;
       ce = cudaGraphInstantiate(&g->exec, graph, 0);
@@ -140,7 +161,7 @@ static int enqueue_step(lmono_ctx* ctx, const float4* d_corner, int nc, const fl
     ctx->launches += g->n_launch;
   }
   LM_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-  ctx->step_pending = true;
+  ctx->step_pending = true; ctx->step_timed = true;
   return LMONO_OK;
 }
 
@@ -225,7 +246,7 @@ extern "C" int lmono_shard_end(lmono_ctx* ctx) {
   int rc = lm_map_insert_and_refilter(ctx, ctx->shard_nc, ctx->shard_ns);
   if (rc) return rc;
   LM_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-  ctx->step_pending = true;
+  ctx->step_pending = true; ctx->step_timed = true;
   return LMONO_OK;
 }
 
@@ -251,7 +272,7 @@ static int collect(lmono_ctx* ctx, lmono_pose* w_curr, lmono_pose* wmap_wodom, l
   if (w_curr) { memcpy(w_curr->q, h->q_w_curr, sizeof(w_curr->q)); memcpy(w_curr->t, h->t_w_curr, sizeof(w_curr->t)); }
   if (wmap_wodom) { memcpy(wmap_wodom->q, h->q_wmap_wodom, sizeof(wmap_wodom->q)); memcpy(wmap_wodom->t, h->t_wmap_wodom, sizeof(wmap_wodom->t)); }
   float ms = 0.f;
-  if (ctx->step_pending) { cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->step_pending = false; }
+  if (ctx->step_pending) { if (ctx->step_timed) cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->step_pending = false; }
   if (report) fill_report(h, report, ms);
   if (h->fault) {
     fprintf(stderr, "[lmono_b200] device fault bits 0x%x\n", h->fault);
@@ -294,40 +315,140 @@ extern "C" int lmono_map_step(lmono_ctx* ctx, lmono_cloud_view corner_last, lmon
   return rc;
 }
 
-// ---- sequence batches (config C-4): n independent ctxs driven from one host thread, overlapping on the device
-static int step_async(lmono_ctx* ctx, lmono_cloud_view corner_last, lmono_cloud_view surf_last, const lmono_pose* wodom_curr, const lmono_pose* wmap_in) {
+// ---- sequence batches (config C-4): n independent ctxs driven from one host thread, overlapping on the device.
+// The steps of all n sequences are captured as parallel branches of ONE CUDA graph (fork / join inside the graph,
+// per-branch read-back of the state into the ctx's pinned mirror), cached in ctxs[0].  A batch step then costs the
+// host one k_batch_args launch (poses, counts, input pointers of every sequence as kernel parameters) and one
+// cudaGraphLaunch on the origin stream, instead of one graph launch + event fork / join per sequence.
+static int step_upload(lmono_ctx* ctx, lmono_cloud_view corner_last, lmono_cloud_view surf_last) {
   if (corner_last.n > ctx->max_feat || surf_last.n > ctx->max_feat) return LMONO_E_CAPACITY;
   int rc;
   if ((rc = lm_upload_cloud(ctx, corner_last, ctx->d_raw[0], ctx->d_in[0], nullptr))) return rc;
-  if ((rc = lm_upload_cloud(ctx, surf_last, ctx->d_raw[1], ctx->d_in[1], nullptr))) return rc;
-  return enqueue_step(ctx, ctx->d_in[0], corner_last.n, ctx->d_in[1], surf_last.n, wodom_curr, wmap_in);
+  return lm_upload_cloud(ctx, surf_last, ctx->d_raw[1], ctx->d_in[1], nullptr);
 }
 
 extern "C" int lmono_map_step_async(lmono_ctx* ctx, lmono_cloud_view corner_last, lmono_cloud_view surf_last, const lmono_pose* wodom_curr) {
   if (!ctx || !wodom_curr) return LMONO_E_ARG;
-  return step_async(ctx, corner_last, surf_last, wodom_curr, nullptr);
+  int rc = step_upload(ctx, corner_last, surf_last);
+  if (rc) return rc;
+  return enqueue_step(ctx, ctx->d_in[0], corner_last.n, ctx->d_in[1], surf_last.n, wodom_curr, nullptr);
 }
 
-extern "C" int lmono_map_step_batch(lmono_ctx* const* ctxs, int32_t n, const lmono_cloud_view* corner_last, const lmono_cloud_view* surf_last,
-                                    const lmono_pose* wodom_curr, const lmono_pose* wmap_wodom_in,
-                                    lmono_pose* w_curr, lmono_pose* wmap_wodom, lmono_map_report* reports) {
-  if (!ctxs || n < 0 || !corner_last || !surf_last || !wodom_curr) return LMONO_E_ARG;
-  int first = LMONO_OK;
+static int batch_lazy_init(lmono_ctx* ctx /*leader*/) {
+  if (ctx->bgraphs) return LMONO_OK;
+  ctx->cap_streams = (cudaStream_t*)calloc(LM_BATCH_MAX, sizeof(cudaStream_t));
+  ctx->bgraphs = (LmBatchGraph*)calloc(LM_MAX_BGRAPHS, sizeof(LmBatchGraph));
+  if (!ctx->cap_streams || !ctx->bgraphs) return LMONO_E_ARG;
+  ctx->n_bgraphs = 0;
+  return LMONO_OK;
+}
+
+void lm_batch_free(lmono_ctx* ctx) {
+  if (ctx->bgraphs) { for (int i = 0; i < ctx->n_bgraphs; ++i) cudaGraphExecDestroy(ctx->bgraphs[i].exec); free(ctx->bgraphs); ctx->bgraphs = nullptr; }
+  if (ctx->cap_streams) { for (int i = 0; i < LM_BATCH_MAX; ++i) if (ctx->cap_streams[i]) cudaStreamDestroy(ctx->cap_streams[i]); free(ctx->cap_streams); ctx->cap_streams = nullptr; }
+}
+
+// capture the n step bodies as parallel branches: origin -> fork -> {body_i ; state read-back_i} -> join -> origin
+static int batch_capture(lmono_ctx* lead, lmono_ctx* const* ctxs, int n, const int* nc_cap, const int* ns_cap, cudaStream_t origin, LmBatchGraph* g) {
+  lmono_ctx* ctx = lead;
+  for (int i = 0; i < n; ++i)
+    if (!lead->cap_streams[i]) LM_CUDA(cudaStreamCreateWithFlags(&lead->cap_streams[i], cudaStreamNonBlocking));
+  cudaGraph_t graph = nullptr;
+  LM_CUDA(cudaStreamBeginCapture(origin, cudaStreamCaptureModeThreadLocal));
+  int rc = LMONO_OK;
+  cudaError_t ce = cudaEventRecord(lead->ev_fork, origin);
+  for (int i = 0; i < n && !rc && ce == cudaSuccess; ++i) {
+    lmono_ctx* c = ctxs[i];
+    cudaStream_t saved = c->stream;
+    const int64_t l0 = c->launches;
+    c->stream = lead->cap_streams[i];
+    ce = cudaStreamWaitEvent(c->stream, lead->ev_fork, 0);
+    if (ce == cudaSuccess) rc = enqueue_body(c, nc_cap[i], ns_cap[i]);
+    if (!rc && ce == cudaSuccess) ce = cudaMemcpyAsync(c->h_state, c->d_state, sizeof(LmMapState), cudaMemcpyDeviceToHost, c->stream);
+    if (!rc && ce == cudaSuccess) ce = cudaEventRecord(c->ev_join, c->stream);
+    if (!rc && ce == cudaSuccess) ce = cudaStreamWaitEvent(origin, c->ev_join, 0);
+    g->n_launch[i] = (int)(c->launches - l0);
+    c->launches = l0;
+    c->stream = saved;
+  }
+  cudaError_t ce2 = cudaStreamEndCapture(origin, &graph);
+  if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+  LM_CUDA(ce); LM_CUDA(ce2);
+  ce = cudaGraphInstantiate(&g->exec, graph, 0);
+  cudaGraphDestroy(graph);
+  LM_CUDA(ce);
+  g->n = n;
+  for (int i = 0; i < n; ++i) { g->ctxs[i] = ctxs[i]; g->nc_cap[i] = nc_cap[i]; g->ns_cap[i] = ns_cap[i]; }
+  return LMONO_OK;
+}
+
+// d_corner[i] / d_surf[i]: float4 XYZI device buffers.  origin: the stream the batch is ordered on.
+static int batch_enqueue(lmono_ctx* const* ctxs, int n, const float4* const* d_corner, const int32_t* n_corner, const float4* const* d_surf,
+                         const int32_t* n_surf, const lmono_pose* wodom_curr, const lmono_pose* wmap_in, cudaStream_t origin) {
+  lmono_ctx* lead = ctxs[0];
+  lmono_ctx* ctx = lead;
+  int rc;
+  if ((rc = batch_lazy_init(lead))) return rc;
+  int nc_cap[LM_BATCH_MAX], ns_cap[LM_BATCH_MAX];
   for (int i = 0; i < n; ++i) {
-    if (!ctxs[i]) return LMONO_E_ARG;
-    int rc = step_async(ctxs[i], corner_last[i], surf_last[i], &wodom_curr[i], wmap_wodom_in ? &wmap_wodom_in[i] : nullptr);
-    if (!rc) {     // read-back queued right behind the step, so that the collect loop below only waits
-      lmono_ctx* ctx = ctxs[i];
-      cudaError_t e = cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(LmMapState), cudaMemcpyDeviceToHost, ctx->stream);
-      if (e != cudaSuccess) { ctx->last_cuda_error = (int)e; rc = LMONO_E_CUDA; }
+    lmono_ctx* c = ctxs[i];
+    if (n_corner[i] < 0 || n_surf[i] < 0 || n_corner[i] > c->max_feat || n_surf[i] > c->max_feat) return LMONO_E_CAPACITY;
+    nc_cap[i] = bucket_up(n_corner[i], c->max_feat); ns_cap[i] = bucket_up(n_surf[i], c->max_feat);
+    // order the batch after whatever the ctx has in flight on its own stream
+    if (c->stream != origin) { LM_CUDA(cudaEventRecord(c->ev_sync, c->stream)); LM_CUDA(cudaStreamWaitEvent(origin, c->ev_sync, 0)); }
+  }
+  LM_CUDA(cudaEventRecord(lead->ev0, origin));
+  for (int base = 0; base < n; base += LM_ARGS_CHUNK) {
+    BatchStepArgs b;
+    b.n = n - base < LM_ARGS_CHUNK ? n - base : LM_ARGS_CHUNK;
+    for (int k = 0; k < LM_ARGS_CHUNK; ++k) {
+      const int i = base + (k < b.n ? k : 0);
+      b.st[k] = ctxs[i]->d_state;
+      fill_step_args(&b.a[k], d_corner[i], n_corner[i], d_surf[i], n_surf[i], &wodom_curr[i], wmap_in ? &wmap_in[i] : nullptr);
     }
-    if (rc && !first) first = rc;
+    k_batch_args<<<1, 32, 0, origin>>>(b);
+    LM_LAUNCH_CHECK();
   }
+  LmBatchGraph* g = nullptr;
+  for (int e = 0; e < lead->n_bgraphs && !g; ++e) {
+    LmBatchGraph& q = lead->bgraphs[e];
+    if (q.n != n) continue;
+    bool same = true;
+    for (int i = 0; i < n && same; ++i) same = q.ctxs[i] == ctxs[i] && q.nc_cap[i] == nc_cap[i] && q.ns_cap[i] == ns_cap[i];
+    if (same) g = &q;
+  }
+  if (!g) {
+    if (lead->n_bgraphs == LM_MAX_BGRAPHS) {
+      for (int e = 0; e < lead->n_bgraphs; ++e) cudaGraphExecDestroy(lead->bgraphs[e].exec);
+      lead->n_bgraphs = 0;
+    }
+    g = &lead->bgraphs[lead->n_bgraphs];
+    if ((rc = batch_capture(lead, ctxs, n, nc_cap, ns_cap, origin, g))) return rc;
+    lead->n_bgraphs++;
+  }
+  LM_CUDA(cudaGraphLaunch(g->exec, origin));
+  LM_CUDA(cudaEventRecord(lead->ev1, origin));
+  bool any_other = false;
   for (int i = 0; i < n; ++i) {
-    int rc = collect(ctxs[i], w_curr ? &w_curr[i] : nullptr, wmap_wodom ? &wmap_wodom[i] : nullptr, reports ? &reports[i] : nullptr, false);
-    if (rc && !first) first = rc;
+    lmono_ctx* c = ctxs[i];
+    c->launches += g->n_launch[i];
+    c->step_pending = true; c->step_timed = (c == lead);
+    any_other |= c->stream != origin;
   }
-  return first;
+  if (any_other) {      // later work on a ctx's own stream is ordered after the batch
+    LM_CUDA(cudaEventRecord(lead->ev_done, origin));
+    for (int i = 0; i < n; ++i) if (ctxs[i]->stream != origin) LM_CUDA(cudaStreamWaitEvent(ctxs[i]->stream, lead->ev_done, 0));
+  }
+  return LMONO_OK;
+}
+
+static bool batch_graph_ok(lmono_ctx* const* ctxs, int n) {
+  if (n > LM_BATCH_MAX) return false;
+  for (int i = 0; i < n; ++i) {
+    if (!ctxs[i]->graphs_on || ctxs[i]->prof_on || ctxs[i]->kmark_on || ctxs[i]->device != ctxs[0]->device) return false;
+    for (int j = 0; j < i; ++j) if (ctxs[j] == ctxs[i]) return false;
+  }
+  return true;
 }
 
 extern "C" int lmono_map_step_device_batch(lmono_ctx* const* ctxs, int32_t n, const void* const* d_corner, const int32_t* n_corner,
@@ -335,21 +456,62 @@ extern "C" int lmono_map_step_device_batch(lmono_ctx* const* ctxs, int32_t n, co
                                            const lmono_pose* wmap_wodom_in, void* join_stream) {
   if (!ctxs || n < 0 || !d_corner || !d_surf || !n_corner || !n_surf || !wodom_curr) return LMONO_E_ARG;
   if (n == 0) return LMONO_OK;
+  for (int i = 0; i < n; ++i) if (!ctxs[i]) return LMONO_E_ARG;
   cudaStream_t js = (cudaStream_t)join_stream;
+  if (batch_graph_ok(ctxs, n))
+    return batch_enqueue(ctxs, n, (const float4* const*)d_corner, n_corner, (const float4* const*)d_surf, n_surf, wodom_curr, wmap_wodom_in,
+                         js ? js : ctxs[0]->stream);
+  // plain launches (LMONO_NO_GRAPH, profiler or kernel marks on): every ctx on its own stream, fork / join with events
   if (js) {
     lmono_ctx* ctx = ctxs[0];
     LM_CUDA(cudaEventRecord(ctx->ev_fork, js));
   }
   for (int i = 0; i < n; ++i) {
     lmono_ctx* ctx = ctxs[i];
-    if (!ctx) return LMONO_E_ARG;
-    if (js) LM_CUDA(cudaStreamWaitEvent(ctx->stream, ctxs[0]->ev_fork, 0));
+    if (js && ctx->stream != js) LM_CUDA(cudaStreamWaitEvent(ctx->stream, ctxs[0]->ev_fork, 0));
     int rc;
     if ((rc = enqueue_step(ctx, (const float4*)d_corner[i], n_corner[i], (const float4*)d_surf[i], n_surf[i], &wodom_curr[i],
                            wmap_wodom_in ? &wmap_wodom_in[i] : nullptr))) return rc;
-    if (js) LM_CUDA(cudaStreamWaitEvent(js, ctx->ev1, 0));      // ev1 closes the step on the ctx stream
+    if (js && ctx->stream != js) { LM_CUDA(cudaEventRecord(ctx->ev_join, ctx->stream)); LM_CUDA(cudaStreamWaitEvent(js, ctx->ev_join, 0)); }
   }
   return LMONO_OK;
+}
+
+extern "C" int lmono_map_step_batch(lmono_ctx* const* ctxs, int32_t n, const lmono_cloud_view* corner_last, const lmono_cloud_view* surf_last,
+                                    const lmono_pose* wodom_curr, const lmono_pose* wmap_wodom_in,
+                                    lmono_pose* w_curr, lmono_pose* wmap_wodom, lmono_map_report* reports) {
+  if (!ctxs || n < 0 || !corner_last || !surf_last || !wodom_curr) return LMONO_E_ARG;
+  if (n == 0) return LMONO_OK;
+  for (int i = 0; i < n; ++i) if (!ctxs[i]) return LMONO_E_ARG;
+  int first = LMONO_OK;
+  if (batch_graph_ok(ctxs, n)) {
+    const float4* dc[LM_BATCH_MAX]; const float4* ds[LM_BATCH_MAX]; int32_t nc[LM_BATCH_MAX], ns[LM_BATCH_MAX];
+    for (int i = 0; i < n; ++i) {     // uploads on the ctx's own stream; the batch is ordered after them
+      int rc = step_upload(ctxs[i], corner_last[i], surf_last[i]);
+      if (rc) return rc;
+      dc[i] = ctxs[i]->d_in[0]; ds[i] = ctxs[i]->d_in[1]; nc[i] = corner_last[i].n; ns[i] = surf_last[i].n;
+    }
+    int rc = batch_enqueue(ctxs, n, dc, nc, ds, ns, wodom_curr, wmap_wodom_in, ctxs[0]->stream);
+    if (rc) return rc;
+    // the state read-backs are part of the graph: one wait on the origin stream covers every sequence
+    { lmono_ctx* ctx = ctxs[0]; LM_CUDA(cudaStreamSynchronize(ctx->stream)); }
+  } else {
+    for (int i = 0; i < n; ++i) {
+      lmono_ctx* ctx = ctxs[i];
+      int rc = step_upload(ctx, corner_last[i], surf_last[i]);
+      if (!rc) rc = enqueue_step(ctx, ctx->d_in[0], corner_last[i].n, ctx->d_in[1], surf_last[i].n, &wodom_curr[i], wmap_wodom_in ? &wmap_wodom_in[i] : nullptr);
+      if (!rc) {     // read-back queued right behind the step, so that the collect loop below only waits
+        cudaError_t e = cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(LmMapState), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) { ctx->last_cuda_error = (int)e; rc = LMONO_E_CUDA; }
+      }
+      if (rc && !first) first = rc;
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    int rc = collect(ctxs[i], w_curr ? &w_curr[i] : nullptr, wmap_wodom ? &wmap_wodom[i] : nullptr, reports ? &reports[i] : nullptr, false);
+    if (rc && !first) first = rc;
+  }
+  return first;
 }
 
 extern "C" int lmono_map_get_state(lmono_ctx* ctx, lmono_pose* wmap_wodom, int32_t cen[3]) {

@@ -21,6 +21,7 @@ constexpr int VW_THREADS = 256, VW_ITEMS = 4, VW_BLOCK = VW_THREADS * VW_ITEMS;
 
 struct VgSegs {
   const float4* in[LM_SORT_MAXSEG]; float4* out[LM_SORT_MAXSEG];
+  const float4* const* in_ind[LM_SORT_MAXSEG];      // not NULL: the input pointer is read from device memory (graph replay)
   const int32_t* n[LM_SORT_MAXSEG]; int32_t* out_n[LM_SORT_MAXSEG];
   float inv_leaf[LM_SORT_MAXSEG];
   int off[LM_SORT_MAXSEG];
@@ -46,7 +47,8 @@ __global__ void __launch_bounds__(256) k_vg_keys(VgSegs sg, VgParams* __restrict
   if (blockIdx.x * blockDim.x >= n) return;
   uint32_t mn[3] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu }, mx[3] = { 0u, 0u, 0u };
   if (i < n) {
-    const float4 p = sg.in[seg][i];
+    const float4* __restrict__ src = sg.in_ind[seg] ? *sg.in_ind[seg] : sg.in[seg];
+    const float4 p = src[i];
     const float il = sg.inv_leaf[seg];
     int v[3] = { (int)floorf(__fmul_rn(p.x, il)), (int)floorf(__fmul_rn(p.y, il)), (int)floorf(__fmul_rn(p.z, il)) };
     bool bad = false;
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(VW_THREADS) k_vg_write(VgSegs sg, VgParams* __
   const int seg = blockIdx.y;
   const int n = *sg.n[seg];
   VgParams& vg = vgs[seg];
-  const float4* __restrict__ pts = sg.in[seg];
+  const float4* __restrict__ pts = sg.in_ind[seg] ? *sg.in_ind[seg] : sg.in[seg];
   float4* __restrict__ out = sg.out[seg];
   const unsigned long long* __restrict__ sorted = sorted_all + sg.off[seg];
   const int base = blockIdx.x * VW_BLOCK;
@@ -168,14 +170,14 @@ __global__ void __launch_bounds__(VW_THREADS) k_vg_write(VgSegs sg, VgParams* __
 // VoxelGrid of up to LM_SORT_MAXSEG clouds with shared launches.  Scratch: ctx->d_sort_a/b/c (segment s at
 // offset sum of n_max of the segments before it), ctx->d_vg.
 int lm_voxel_grid_multi(lmono_ctx* ctx, int nseg, const float4* const* in, const int32_t* const* n_dev, const int* n_max,
-                        const float* leaf, float4* const* out, int32_t* const* out_n_dev) {
+                        const float* leaf, float4* const* out, int32_t* const* out_n_dev, const float4* const* const* in_ind) {
   if (nseg < 1 || nseg > LM_SORT_MAXSEG) return LMONO_E_ARG;
   VgSegs sg; LmSortSegs ss;
   ss.in = ctx->d_sort_a; ss.tmp = ctx->d_sort_b; ss.out = ctx->d_sort_c;
   int off = 0, mx = 0;
   for (int s = 0; s < LM_SORT_MAXSEG; ++s) {
     const int k = s < nseg ? s : 0;
-    sg.in[s] = in[k]; sg.out[s] = out[k]; sg.n[s] = n_dev[k]; sg.out_n[s] = out_n_dev[k]; sg.inv_leaf[s] = 1.0f / leaf[k];
+    sg.in[s] = in ? in[k] : nullptr; sg.in_ind[s] = in_ind ? in_ind[k] : nullptr; sg.out[s] = out[k]; sg.n[s] = n_dev[k]; sg.out_n[s] = out_n_dev[k]; sg.inv_leaf[s] = 1.0f / leaf[k];
     sg.off[s] = s < nseg ? off : 0; ss.off[s] = sg.off[s]; ss.n[s] = n_dev[k];
     if (s < nseg) { off += n_max[s]; mx = n_max[s] > mx ? n_max[s] : mx; }
   }
@@ -192,7 +194,7 @@ int lm_voxel_grid_multi(lmono_ctx* ctx, int nseg, const float4* const* in, const
 
 int lm_voxel_grid_device(lmono_ctx* ctx, const float4* in, const int32_t* n_dev, int n_max, float leaf,
                          float4* out, int32_t* out_n_dev) {
-  return lm_voxel_grid_multi(ctx, 1, &in, &n_dev, &n_max, &leaf, &out, &out_n_dev);
+  return lm_voxel_grid_multi(ctx, 1, &in, &n_dev, &n_max, &leaf, &out, &out_n_dev, nullptr);
 }
 
 int lm_voxel_init(lmono_ctx* ctx) {

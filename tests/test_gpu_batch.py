@@ -31,13 +31,17 @@ def _alone(gpu_ctx_factory, s):
     return out, maps
 
 
-def test_batch_equals_sequences_alone(gpu_ctx_factory):
+@pytest.mark.parametrize("shared_stream", [False, True])
+def test_batch_equals_sequences_alone(gpu_ctx_factory, shared_stream):
     import torch
     from lmono_b200 import api
     cm, sm = scenario.small_map()
     ctxs = []
+    common = torch.cuda.Stream() if shared_stream else None
     for s in range(NSEQ):
-        c = gpu_ctx_factory()          # stream=NULL: every ctx creates its own non-blocking stream
+        # stream=NULL: every ctx creates its own non-blocking stream; shared: all sequences on one stream (the batch
+        # graph forks / joins internally)
+        c = gpu_ctx_factory(stream=common.cuda_stream) if shared_stream else gpu_ctx_factory()
         c.map_import(0, cm)
         c.map_import(1, sm)
         ctxs.append(c)
@@ -61,8 +65,9 @@ def test_batch_equals_sequences_alone(gpu_ctx_factory):
             torch.cuda.synchronize()
             batch.set_device_inputs([a.data_ptr() for a in dc], [a.shape[0] for a in dc],
                                     [a.data_ptr() for a in ds], [a.shape[0] for a in ds])
-            batch.step_device(join_stream=torch.cuda.current_stream().cuda_stream)
-            torch.cuda.current_stream().synchronize()      # the join makes the caller's stream wait for the whole batch
+            js = common if shared_stream else torch.cuda.Stream()
+            batch.step_device(join_stream=js.cuda_stream)
+            js.synchronize()                               # the join makes the caller's stream wait for the whole batch
             for s, (q, t, rep) in enumerate(batch.collect()):
                 got[s].append((q, t, list(rep.corner_num), list(rep.surf_num)))
     for s in range(NSEQ):
