@@ -287,8 +287,10 @@ def run_ours(args):
     value = world * S * args.steps / (total_ms_max * 1e-3)
     reg_err = check_converged(res, W + args.steps - 1)     # the work inside the timed region converged
 
-    # ---- e2e leg: public host API (lmono_map_step_batch), pinned host inputs, H2D of the features and D2H of the pose
-    # + report inside the timed region, S sequences in flight
+    # ---- e2e leg: public host API, page-locked host inputs.  Every step moves the features of all S sequences host ->
+    # device (fetched over PCIe by the first kernel of each registration) and the pose + report of every sequence device
+    # -> host, inside the timed region.  Pipelined as a streaming consumer would (lmono_map_submit_batch /
+    # lmono_map_wait_batch): sweep k+1 is submitted while sweep k runs, every result is read before sweep k+2 goes in.
     for i in range(3):
         batch.step(args=bargs[i % nsw])
     barrier()
@@ -297,9 +299,12 @@ def run_ours(args):
     h2d = 0
     e0.record(main)
     t0 = time.perf_counter()
+    batch.submit(args=bargs[W % nsw])
     for i in range(args.steps):
         a_ = bargs[(W + i) % nsw]
-        res = batch.step(args=a_)
+        if i + 1 < args.steps:
+            batch.submit(args=bargs[(W + i + 1) % nsw])
+        res = batch.wait()
         h2d += sum(a_.cv[s_].n + a_.sv[s_].n for s_ in range(S)) * 16
     e1.record(main)
     barrier()
@@ -308,6 +313,14 @@ def run_ours(args):
     e2e_ms = allmax(max(e0.elapsed_time(e1), e2e_wall * 1e3))
     e2e_value = world * S * args.steps / (e2e_ms * 1e-3)
     d2h = int(ctx.L.lmono_map_result_bytes()) * S * args.steps      # pose + report read back per registration
+    # the same without pipelining: lmono_map_step_batch (submit + wait per step)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        res = batch.step(args=bargs[(W + i) % nsw])
+    barrier()
+    e2e_sync_ms = allmax((time.perf_counter() - t0) * 1e3)
+    e2e_sync_value = world * S * args.steps / (e2e_sync_ms * 1e-3)
 
     # ---- single sequence alone on the GPU (latency of one registration; the round-1 headline): device-resident inputs,
     # CUDA events per step, L2 flushed between steps
@@ -409,7 +422,9 @@ def run_ours(args):
                    "registrations_per_step": S * world,
                    "l2": "flushed between steps (256 MiB write)",
                    "parallelism": f"{S} independent sequences per GPU (one ctx each, BASELINE config C-4); one registration of every sequence per step = one CUDA graph with {S} parallel branches, no collective"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
+                "pipeline": "lmono_map_submit_batch / lmono_map_wait_batch, two steps in flight; every result read on the host",
+                "unpipelined_value": e2e_sync_value},
         "single_sequence": {"value": 1e3 / single_ms * world, "unit": UNIT, "ms_per_registration": single_ms,
                             "e2e_value": 1e3 / single_e2e_ms * world, "e2e_ms_per_registration": single_e2e_ms,
                             "note": "one sequence alone on each GPU: latency of one registration (graph replay, L2 flushed between steps)"},

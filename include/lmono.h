@@ -160,21 +160,35 @@ int lmono_map_collect(lmono_ctx* ctx, lmono_pose* w_curr, lmono_pose* wmap_wodom
  * a batch step costs the host one small argument launch + one graph launch.  The ctxs may share one stream
  * (cheapest: nothing else to order) or own their streams (the batch is then ordered after the work already
  * enqueued on each, and later work on each is ordered after the batch, with events).
- *   lmono_map_step_async        lmono_map_step without the final wait: uploads the features (asynchronous when the
- *                               host buffers are page-locked), enqueues the registration;
+ * Host clouds in page-locked memory (cudaHostAlloc / cudaHostRegister) are never copied by the host: the first
+ * kernel of the step reads them over PCIe while it computes the voxel keys (fused upload, any record stride).  Such
+ * buffers must stay valid and unmodified until the step has been waited for.  Pageable clouds are staged with
+ * cudaMemcpyAsync as before.  LMONO_NO_ZEROCOPY=1 forces staging.
+ *   lmono_map_step_async        lmono_map_step without the final wait: enqueues the registration;
  *                               lmono_map_collect() waits for this ctx and returns the result.
- *   lmono_map_step_batch        uploads for every ctx, the batch graph on the stream of ctxs[0], one wait, results in
- *                               order.  Arrays have n entries; wmap_wodom_in (may be NULL) replaces q/t_wmap_wodom
- *                               of ctx i before its step.
+ *   lmono_map_step_batch        = lmono_map_submit_batch + lmono_map_wait_batch.  Arrays have n entries;
+ *                               wmap_wodom_in (may be NULL) replaces q/t_wmap_wodom of ctx i before its step.
+ *   lmono_map_submit_batch      enqueue-only: the batch graph on the stream of ctxs[0]; every branch ends by storing
+ *                               the sequence's state into one of the ctx's two page-locked result mirrors.  Up to TWO
+ *                               submissions per ctx may be outstanding (LMONO_E_ARG otherwise), so the host can
+ *                               prepare and submit sweep k+1 while sweep k runs (the mapping input of sweep k+1 does
+ *                               not depend on the mapping result of sweep k: laserMapping.cpp:235-305 only pairs
+ *                               odometry outputs).
+ *   lmono_map_wait_batch        waits for the OLDEST outstanding submission of every listed ctx and returns its
+ *                               results (same outputs as lmono_map_step_batch).
  *   lmono_map_step_device_batch device-resident inputs, enqueue-only, on join_stream (NULL: the stream of ctxs[0]):
  *                               ordered after the work already enqueued there, and work enqueued there afterwards is
- *                               ordered after the whole batch (no host synchronisation).  The state of every
- *                               sequence is read back inside the graph; lmono_map_collect() returns it. */
+ *                               ordered after the whole batch (no host synchronisation).
+ *                               lmono_map_collect() returns the state of a sequence. */
 int lmono_map_step_async(lmono_ctx* ctx, lmono_cloud_view corner_last, lmono_cloud_view surf_last, const lmono_pose* wodom_curr);
 int lmono_map_step_batch(lmono_ctx* const* ctxs, int32_t n, const lmono_cloud_view* corner_last, const lmono_cloud_view* surf_last,
                          const lmono_pose* wodom_curr, const lmono_pose* wmap_wodom_in /*may be NULL*/,
                          lmono_pose* w_curr /*out, may be NULL*/, lmono_pose* wmap_wodom /*out, may be NULL*/,
                          lmono_map_report* reports /*out, may be NULL*/);
+int lmono_map_submit_batch(lmono_ctx* const* ctxs, int32_t n, const lmono_cloud_view* corner_last, const lmono_cloud_view* surf_last,
+                           const lmono_pose* wodom_curr, const lmono_pose* wmap_wodom_in /*may be NULL*/);
+int lmono_map_wait_batch(lmono_ctx* const* ctxs, int32_t n, lmono_pose* w_curr /*out, may be NULL*/,
+                         lmono_pose* wmap_wodom /*out, may be NULL*/, lmono_map_report* reports /*out, may be NULL*/);
 int lmono_map_step_device_batch(lmono_ctx* const* ctxs, int32_t n, const void* const* d_corner_xyzi, const int32_t* n_corner,
                                 const void* const* d_surf_xyzi, const int32_t* n_surf, const lmono_pose* wodom_curr,
                                 const lmono_pose* wmap_wodom_in /*may be NULL*/, void* join_stream /*may be NULL*/);

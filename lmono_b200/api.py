@@ -512,6 +512,22 @@ class SequenceBatch:
             raise LmonoError(rc, "map_step_batch")
         return [(np.array(self._w[i].q[:]), np.array(self._w[i].t[:]), self._rep[i]) for i in range(self.n)]
 
+    def submit(self, args=None):
+        """enqueue one registration per sequence on host inputs without waiting (lmono_map_submit_batch).  At most two
+        submissions may be outstanding; page-locked inputs are fetched by the step itself and must stay untouched until
+        the matching wait()."""
+        a = args or self.args
+        rc = self.L.lmono_map_submit_batch(self._h, self.n, a.cv, a.sv, a.odom, a.wmap_in if a.use_wmap_in else None)
+        if rc:
+            raise LmonoError(rc, "map_submit_batch")
+
+    def wait(self):
+        """results of the oldest outstanding submit(): [(q, t, report)] * n (report views are overwritten by the next wait)"""
+        rc = self.L.lmono_map_wait_batch(self._h, self.n, self._w, self._wm, self._rep)
+        if rc:
+            raise LmonoError(rc, "map_wait_batch")
+        return [(np.array(self._w[i].q[:]), np.array(self._w[i].t[:]), self._rep[i]) for i in range(self.n)]
+
     def collect(self):
         return [c.map_collect() for c in self.ctxs]
 

@@ -70,7 +70,7 @@ struct LmProblem {          // one LM solve: factor arrays, pose in/out, report 
   int32_t* count0; int32_t* count1;       // valid factors per array
 };
 
-struct LmMapState {
+struct alignas(16) LmMapState {
   int32_t cen[3];                        // laserCloudCenWidth/Height/Depth
   int32_t center[3];                     // centerCubeI/J/K after the shift
   int32_t valid_num;
@@ -93,7 +93,14 @@ struct LmMapState {
   // device pointers of this step's corner / surf features (written by k_step_args / k_batch_args), so that the
   // captured kernel sequence does not depend on where the caller keeps its inputs
   const float4* in_ptr[2];
+  // fused upload: in_stride != 0 -> this step's features are fetched by k_vg_keys straight from page-locked host
+  // memory (in_src = device alias of the caller's AoS buffer, record stride / intensity offset in bytes) into in_ptr
+  const void* in_src[2];
+  int32_t in_stride[2], in_ioff[2];
+  int32_t result_slot;                   // which pinned result mirror (lmono_ctx::h_ring) k_publish_state writes
+  int32_t pad_[3];
 };
+static_assert(sizeof(LmMapState) % 16 == 0, "k_publish_state copies 16-byte words");
 
 struct LmMapType {           // one per map (0 corner, 1 surf); device pointers, passed by value
   float leaf, inv_leaf;
@@ -134,7 +141,7 @@ constexpr int LM_MAX_GRAPHS = 64;
 // Sequence batches: ONE graph holds the steps of all n sequences as parallel branches (fork / join inside the
 // graph), so a batch step costs the host one small argument launch + one cudaGraphLaunch.  Cached in ctxs[0].
 constexpr int LM_BATCH_MAX = 64;
-constexpr int LM_MAX_BGRAPHS = 8;
+constexpr int LM_MAX_BGRAPHS = 16;
 struct LmBatchGraph { int n; lmono_ctx* ctxs[LM_BATCH_MAX]; int nc_cap[LM_BATCH_MAX], ns_cap[LM_BATCH_MAX]; cudaGraphExec_t exec; int n_launch[LM_BATCH_MAX]; };
 constexpr int LM_GRAPH_BUCKET = 2048;     // launch grids are sized for counts rounded up to this
 
@@ -157,6 +164,11 @@ struct lmono_ctx {
   LmMapType map[2];
   LmMapState* d_state;
   LmMapState* h_state;          // pinned mirror
+  // pipelined host API (lmono_map_submit_batch / _wait_batch): up to two steps of a ctx may be in flight; the step
+  // graph publishes the state into h_ring[slot] (mapped page-locked memory) and ev_res[slot] marks its completion
+  LmMapState* h_ring[2]; cudaEvent_t ev_res[2];
+  uint32_t n_submitted, n_waited;
+  bool zero_copy_on;            // LMONO_NO_ZEROCOPY=1: always stage host inputs through cudaMemcpyAsync
   LmLmState* d_lm;
   int32_t* d_slot_valid_rank;   // [LM_NSLOT]
   double* d_partials;           // reduction partials [max_blocks][32]
@@ -469,7 +481,8 @@ int lm_sort_u64(lmono_ctx* ctx, const unsigned long long* in, unsigned long long
 int lm_voxel_init(lmono_ctx* ctx);
 int lm_voxel_grid_multi(lmono_ctx* ctx, int nseg, const float4* const* in, const int32_t* const* n_dev, const int* n_max,
                         const float* leaf, float4* const* out, int32_t* const* out_n_dev,
-                        const float4* const* const* in_ind = nullptr);   // in_ind[k] != NULL: read the input pointer from device memory
+                        const float4* const* const* in_ind = nullptr,    // in_ind[k] != NULL: read the input pointer from device memory
+                        bool fetch = false);   // honour LmMapState::in_src / in_stride (fused upload from page-locked host memory)
 int lm_voxel_grid_device(lmono_ctx* ctx, const float4* in, const int32_t* n_dev, int n_max, float leaf,
                          float4* out, int32_t* out_n_dev);
 // mapstore.cu

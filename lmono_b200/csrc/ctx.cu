@@ -86,6 +86,13 @@ extern "C" int lmono_create(int device, const lmono_params* params, void* stream
 
   LM_CUDA(cudaMalloc((void**)&ctx->d_state, sizeof(LmMapState)));
   LM_CUDA(cudaMallocHost((void**)&ctx->h_state, sizeof(LmMapState)));
+  for (int i = 0; i < 2; ++i) {
+    LM_CUDA(cudaHostAlloc((void**)&ctx->h_ring[i], sizeof(LmMapState), cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(ctx->h_ring[i], 0, sizeof(LmMapState));
+    LM_CUDA(cudaEventCreateWithFlags(&ctx->ev_res[i], cudaEventDisableTiming));
+  }
+  ctx->n_submitted = ctx->n_waited = 0;
+  { const char* nz = getenv("LMONO_NO_ZEROCOPY"); ctx->zero_copy_on = !(nz && nz[0] == '1'); }
   LM_CUDA(cudaMalloc((void**)&ctx->d_lm, sizeof(LmLmState)));
   LM_CUDA(cudaMemsetAsync(ctx->d_lm, 0, sizeof(LmLmState), ctx->stream));
   LM_CUDA(cudaMalloc((void**)&ctx->d_slot_valid_rank, sizeof(int32_t) * LM_SLOT_TABLE_INTS));
@@ -140,7 +147,7 @@ extern "C" void lmono_destroy(lmono_ctx* ctx) {
   lm_odom_free(ctx);
   lm_color_free(ctx);
   lm_map_free(ctx);
-  cudaFree(ctx->d_state); cudaFreeHost(ctx->h_state); cudaFree(ctx->d_lm); cudaFree(ctx->d_slot_valid_rank); cudaFree(ctx->d_partials); cudaFree(ctx->d_stamps); cudaFree(ctx->d_nnref); cudaFree(ctx->d_rf_nvx); cudaFree(ctx->d_rf_work); cudaFree(ctx->d_rf_meta);
+  cudaFree(ctx->d_state); cudaFreeHost(ctx->h_state); for (int i = 0; i < 2; ++i) { cudaFreeHost(ctx->h_ring[i]); cudaEventDestroy(ctx->ev_res[i]); } cudaFree(ctx->d_lm); cudaFree(ctx->d_slot_valid_rank); cudaFree(ctx->d_partials); cudaFree(ctx->d_stamps); cudaFree(ctx->d_nnref); cudaFree(ctx->d_rf_nvx); cudaFree(ctx->d_rf_work); cudaFree(ctx->d_rf_meta);
   for (int i = 0; i < 3; ++i) cudaFree(ctx->d_raw[i]);
   for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_in[i]); cudaFree(ctx->d_stack[i]); cudaFree(ctx->d_world[i]); cudaFree(ctx->d_fac[i]); }
   cudaFree(ctx->d_sort_a); cudaFree(ctx->d_sort_b); cudaFree(ctx->d_sort_c); cudaFree(ctx->d_blockcnt); cudaFree(ctx->d_tmp_i32);

@@ -35,10 +35,13 @@ __global__ void k_set_counts(LmMapState* st, int n0, int n1) {
 
 // every per-step scalar (feature counts, odometry pose, input pointers) enters through this one launch, so the rest
 // of the step is a parameter-free kernel sequence that can be replayed as a CUDA graph
-struct StepArgs { double q[4]; double t[3]; int n0, n1; int set_wmap; int pad; double wq[4]; double wt[3]; const float4* in[2]; };
+struct StepArgs { double q[4]; double t[3]; int n0, n1; int set_wmap; int slot; double wq[4]; double wt[3]; const float4* in[2];
+                  const void* src[2]; int stride[2]; int ioff[2]; };
 __device__ __forceinline__ void d_apply_step_args(LmMapState* st, const StepArgs& a) {
   st->raw_n[0] = a.n0; st->raw_n[1] = a.n1;
   st->in_ptr[0] = a.in[0]; st->in_ptr[1] = a.in[1];
+  for (int k = 0; k < 2; ++k) { st->in_src[k] = a.src[k]; st->in_stride[k] = a.stride[k]; st->in_ioff[k] = a.ioff[k]; }
+  st->result_slot = a.slot;
   if (a.set_wmap) {       // caller-supplied q/t_wmap_wodom (sequence batches; same effect as lmono_map_set_state before the step)
     for (int k = 0; k < 4; ++k) st->q_wmap_wodom[k] = a.wq[k];
     for (int k = 0; k < 3; ++k) st->t_wmap_wodom[k] = a.wt[k];
@@ -57,6 +60,15 @@ static_assert(sizeof(BatchStepArgs) < 4000, "kernel parameter space");
 __global__ void k_batch_args(BatchStepArgs b) {
   if (threadIdx.x < b.n) d_apply_step_args(b.st[threadIdx.x], b.a[threadIdx.x]);
 }
+// last node of a pipelined step: the state (pose, counts, solver summaries, fault bits) goes to the page-locked result
+// mirror the host reads after the step's event -- a plain store over PCIe instead of a copy-engine node, so that two
+// steps of a ctx can be in flight with one graph (the slot is a per-step argument)
+__global__ void __launch_bounds__(128) k_publish_state(const LmMapState* __restrict__ st, LmMapState* h0, LmMapState* h1) {
+  const int4* __restrict__ src = reinterpret_cast<const int4*>(st);
+  int4* dst = reinterpret_cast<int4*>(st->result_slot ? h1 : h0);
+  for (int i = threadIdx.x; i < (int)(sizeof(LmMapState) / 16); i += blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+}
 
 // :542-550 VoxelGrid of the incoming corner and surf features, both clouds through the same four launches.
 // d_corner / d_surf == NULL: read the input pointers from LmMapState::in_ptr (graph replay)
@@ -68,7 +80,7 @@ static int voxel_both(lmono_ctx* ctx, const float4* d_corner, int nc, const floa
   const float leaf[2] = { ctx->map[0].leaf, ctx->map[1].leaf };
   float4* out[2] = { ctx->d_stack[0], ctx->d_stack[1] };
   int32_t* out_n[2] = { &ctx->d_state->stack_n[0], &ctx->d_state->stack_n[1] };
-  return lm_voxel_grid_multi(ctx, 2, in, n_dev, n_max, leaf, out, out_n, ind);
+  return lm_voxel_grid_multi(ctx, 2, in, n_dev, n_max, leaf, out, out_n, ind, /*fetch=*/!d_corner && !d_surf);
 }
 
 // the step body: nc / ns only size the launch grids (every kernel reads the real counts and the input pointers
@@ -105,26 +117,60 @@ static int bucket_up(int n, int cap) {
   return (int)(b > cap ? cap : b);
 }
 
-static void fill_step_args(StepArgs* a, const float4* d_corner, int nc, const float4* d_surf, int ns, const lmono_pose* wodom_curr,
-                           const lmono_pose* wmap_in) {
+// one step's inputs as the kernels see them: d[k] = float4 XYZI array in device memory that the step reads (for a
+// fused upload: the ctx's own d_in[k], filled by k_vg_keys from src[k]); src / stride / ioff describe the caller's
+// page-locked AoS buffer (stride 0 = d[k] already holds the data)
+struct LmStepIn { const float4* d[2]; int n[2]; const void* src[2]; int stride[2]; int ioff[2]; };
+
+static LmStepIn step_in_device(const float4* d_corner, int nc, const float4* d_surf, int ns) {
+  LmStepIn in;
+  memset(&in, 0, sizeof(in));
+  in.d[0] = d_corner; in.d[1] = d_surf; in.n[0] = nc; in.n[1] = ns;
+  return in;
+}
+
+// host cloud -> step input.  Page-locked memory (cudaHostAlloc / cudaHostRegister: the device can address it) is not
+// copied here at all: k_vg_keys fetches it inside the step.  Anything else is staged with cudaMemcpyAsync (+ unpack) on
+// the ctx stream.
+static int resolve_input(lmono_ctx* ctx, lmono_cloud_view v, int which, LmStepIn* in) {
+  if (v.n < 0 || (v.n > 0 && !v.base) || (v.n > 0 && (v.stride_bytes < 12 || (v.stride_bytes & 3)))) return LMONO_E_ARG;
+  if (v.n > ctx->max_feat) return LMONO_E_CAPACITY;
+  in->d[which] = ctx->d_in[which]; in->n[which] = v.n;
+  in->src[which] = nullptr; in->stride[which] = 0; in->ioff[which] = 0;
+  if (v.n == 0) return LMONO_OK;
+  const bool layout_ok = v.intensity_offset < 0 || ((v.intensity_offset & 3) == 0 && v.intensity_offset + 4 <= v.stride_bytes);
+  if (ctx->zero_copy_on && layout_ok && ((uintptr_t)v.base & 3) == 0) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, v.base) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+      in->src[which] = at.devicePointer;
+      in->stride[which] = v.stride_bytes;
+      in->ioff[which] = v.intensity_offset;
+      return LMONO_OK;
+    } else cudaGetLastError();
+  }
+  return lm_upload_cloud(ctx, v, ctx->d_raw[which], ctx->d_in[which], nullptr);
+}
+
+static void fill_step_args(StepArgs* a, const LmStepIn& in, const lmono_pose* wodom_curr, const lmono_pose* wmap_in, int slot) {
   memset(a, 0, sizeof(*a));
   for (int k = 0; k < 4; ++k) a->q[k] = wodom_curr->q[k];
   for (int k = 0; k < 3; ++k) a->t[k] = wodom_curr->t[k];
-  a->n0 = nc; a->n1 = ns;
-  a->in[0] = d_corner; a->in[1] = d_surf;
+  a->n0 = in.n[0]; a->n1 = in.n[1];
+  for (int k = 0; k < 2; ++k) { a->in[k] = in.d[k]; a->src[k] = in.src[k]; a->stride[k] = in.stride[k]; a->ioff[k] = in.ioff[k]; }
+  a->slot = slot;
   a->set_wmap = wmap_in != nullptr;
   if (wmap_in) { for (int k = 0; k < 4; ++k) a->wq[k] = wmap_in->q[k]; for (int k = 0; k < 3; ++k) a->wt[k] = wmap_in->t[k]; }
 }
 
-// enqueue the whole step on inputs that are already float4 XYZI in device memory
-static int enqueue_step(lmono_ctx* ctx, const float4* d_corner, int nc, const float4* d_surf, int ns, const lmono_pose* wodom_curr,
-                        const lmono_pose* wmap_in = nullptr) {
+// enqueue the whole step
+static int enqueue_step(lmono_ctx* ctx, const LmStepIn& in, const lmono_pose* wodom_curr, const lmono_pose* wmap_in = nullptr, int slot = 0) {
+  const int nc = in.n[0], ns = in.n[1];
   if (nc < 0 || ns < 0 || nc > ctx->max_feat || ns > ctx->max_feat) return LMONO_E_CAPACITY;
   int rc;
   LM_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
   lm_kmark(ctx, "begin", 0);
   StepArgs a;
-  fill_step_args(&a, d_corner, nc, d_surf, ns, wodom_curr, wmap_in);
+  fill_step_args(&a, in, wodom_curr, wmap_in, slot);
   k_step_args<<<1, 32, 0, ctx->stream>>>(ctx->d_state, a);
   LM_LAUNCH_CHECK();
   const int nc_cap = bucket_up(nc, ctx->max_feat), ns_cap = bucket_up(ns, ctx->max_feat);
@@ -265,14 +311,10 @@ static void fill_report(const LmMapState* h, lmono_map_report* r, float ms) {
   r->ms_gpu = ms;
 }
 
-static int collect(lmono_ctx* ctx, lmono_pose* w_curr, lmono_pose* wmap_wodom, lmono_map_report* report, bool copy = true) {
-  if (copy) LM_CUDA(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(LmMapState), cudaMemcpyDeviceToHost, ctx->stream));
-  LM_CUDA(cudaStreamSynchronize(ctx->stream));
-  const LmMapState* h = ctx->h_state;
+// hand a completed state mirror to the caller
+static int deliver(lmono_ctx* ctx, const LmMapState* h, float ms, lmono_pose* w_curr, lmono_pose* wmap_wodom, lmono_map_report* report) {
   if (w_curr) { memcpy(w_curr->q, h->q_w_curr, sizeof(w_curr->q)); memcpy(w_curr->t, h->t_w_curr, sizeof(w_curr->t)); }
   if (wmap_wodom) { memcpy(wmap_wodom->q, h->q_wmap_wodom, sizeof(wmap_wodom->q)); memcpy(wmap_wodom->t, h->t_wmap_wodom, sizeof(wmap_wodom->t)); }
-  float ms = 0.f;
-  if (ctx->step_pending) { if (ctx->step_timed) cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->step_pending = false; }
   if (report) fill_report(h, report, ms);
   if (h->fault) {
     fprintf(stderr, "[lmono_b200] device fault bits 0x%x\n", h->fault);
@@ -282,15 +324,31 @@ static int collect(lmono_ctx* ctx, lmono_pose* w_curr, lmono_pose* wmap_wodom, l
   return LMONO_OK;
 }
 
+static int collect(lmono_ctx* ctx, lmono_pose* w_curr, lmono_pose* wmap_wodom, lmono_map_report* report) {
+  LM_CUDA(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(LmMapState), cudaMemcpyDeviceToHost, ctx->stream));
+  LM_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  if (ctx->step_pending) { if (ctx->step_timed) cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->step_pending = false; }
+  ctx->n_waited = ctx->n_submitted;       // a full synchronisation retires every pipelined step of this ctx as well
+  return deliver(ctx, ctx->h_state, ms, w_curr, wmap_wodom, report);
+}
+
 extern "C" int lmono_map_step_device(lmono_ctx* ctx, const void* d_corner, int32_t nc, const void* d_surf, int32_t ns,
                                      const lmono_pose* wodom_curr) {
   if (!ctx || !wodom_curr) return LMONO_E_ARG;
-  return enqueue_step(ctx, (const float4*)d_corner, nc, (const float4*)d_surf, ns, wodom_curr);
+  return enqueue_step(ctx, step_in_device((const float4*)d_corner, nc, (const float4*)d_surf, ns), wodom_curr);
 }
 
 extern "C" int lmono_map_collect(lmono_ctx* ctx, lmono_pose* w_curr, lmono_pose* wmap_wodom, lmono_map_report* report) {
   if (!ctx) return LMONO_E_ARG;
   return collect(ctx, w_curr, wmap_wodom, report);
+}
+
+static int step_inputs(lmono_ctx* ctx, lmono_cloud_view corner_last, lmono_cloud_view surf_last, LmStepIn* in) {
+  memset(in, 0, sizeof(*in));
+  int rc;
+  if ((rc = resolve_input(ctx, corner_last, 0, in))) return rc;
+  return resolve_input(ctx, surf_last, 1, in);
 }
 
 extern "C" int lmono_map_step(lmono_ctx* ctx, lmono_cloud_view corner_last, lmono_cloud_view surf_last,
@@ -299,9 +357,9 @@ extern "C" int lmono_map_step(lmono_ctx* ctx, lmono_cloud_view corner_last, lmon
   if (!ctx || !wodom_curr) return LMONO_E_ARG;
   if (corner_last.n > ctx->max_feat || surf_last.n > ctx->max_feat || full_res.n > ctx->max_sweep) return LMONO_E_CAPACITY;
   int rc;
-  if ((rc = lm_upload_cloud(ctx, corner_last, ctx->d_raw[0], ctx->d_in[0], nullptr))) return rc;
-  if ((rc = lm_upload_cloud(ctx, surf_last, ctx->d_raw[1], ctx->d_in[1], nullptr))) return rc;
-  if ((rc = enqueue_step(ctx, ctx->d_in[0], corner_last.n, ctx->d_in[1], surf_last.n, wodom_curr))) return rc;
+  LmStepIn in;
+  if ((rc = step_inputs(ctx, corner_last, surf_last, &in))) return rc;
+  if ((rc = enqueue_step(ctx, in, wodom_curr))) return rc;
   const bool want_full = registered && full_res.n > 0;
   if (want_full) {
     float4* d_full_in = (float4*)ctx->d_raw[0];   // raw staging is free again once the step is enqueued
@@ -317,21 +375,16 @@ extern "C" int lmono_map_step(lmono_ctx* ctx, lmono_cloud_view corner_last, lmon
 
 // ---- sequence batches (config C-4): n independent ctxs driven from one host thread, overlapping on the device.
 // The steps of all n sequences are captured as parallel branches of ONE CUDA graph (fork / join inside the graph,
-// per-branch read-back of the state into the ctx's pinned mirror), cached in ctxs[0].  A batch step then costs the
-// host one k_batch_args launch (poses, counts, input pointers of every sequence as kernel parameters) and one
-// cudaGraphLaunch on the origin stream, instead of one graph launch + event fork / join per sequence.
-static int step_upload(lmono_ctx* ctx, lmono_cloud_view corner_last, lmono_cloud_view surf_last) {
-  if (corner_last.n > ctx->max_feat || surf_last.n > ctx->max_feat) return LMONO_E_CAPACITY;
-  int rc;
-  if ((rc = lm_upload_cloud(ctx, corner_last, ctx->d_raw[0], ctx->d_in[0], nullptr))) return rc;
-  return lm_upload_cloud(ctx, surf_last, ctx->d_raw[1], ctx->d_in[1], nullptr);
-}
-
+// every branch ends by publishing its state into the ctx's page-locked result mirror), cached in ctxs[0].  A batch step
+// then costs the host one k_batch_args launch (poses, counts, input pointers / host source descriptors and the result
+// slot of every sequence as kernel parameters) and one cudaGraphLaunch on the origin stream.  Host clouds in
+// page-locked memory are not copied by the host at all: the first kernel of a branch fetches them (resolve_input).
 extern "C" int lmono_map_step_async(lmono_ctx* ctx, lmono_cloud_view corner_last, lmono_cloud_view surf_last, const lmono_pose* wodom_curr) {
   if (!ctx || !wodom_curr) return LMONO_E_ARG;
-  int rc = step_upload(ctx, corner_last, surf_last);
+  LmStepIn in;
+  int rc = step_inputs(ctx, corner_last, surf_last, &in);
   if (rc) return rc;
-  return enqueue_step(ctx, ctx->d_in[0], corner_last.n, ctx->d_in[1], surf_last.n, wodom_curr, nullptr);
+  return enqueue_step(ctx, in, wodom_curr, nullptr);
 }
 
 static int batch_lazy_init(lmono_ctx* ctx /*leader*/) {
@@ -348,7 +401,13 @@ void lm_batch_free(lmono_ctx* ctx) {
   if (ctx->cap_streams) { for (int i = 0; i < LM_BATCH_MAX; ++i) if (ctx->cap_streams[i]) cudaStreamDestroy(ctx->cap_streams[i]); free(ctx->cap_streams); ctx->cap_streams = nullptr; }
 }
 
-// capture the n step bodies as parallel branches: origin -> fork -> {body_i ; state read-back_i} -> join -> origin
+static int publish_state(lmono_ctx* ctx) {
+  k_publish_state<<<1, 128, 0, ctx->stream>>>(ctx->d_state, ctx->h_ring[0], ctx->h_ring[1]);
+  LM_LAUNCH_CHECK();
+  return LMONO_OK;
+}
+
+// capture the n step bodies as parallel branches: origin -> fork -> {body_i ; publish state_i} -> join -> origin
 static int batch_capture(lmono_ctx* lead, lmono_ctx* const* ctxs, int n, const int* nc_cap, const int* ns_cap, cudaStream_t origin, LmBatchGraph* g) {
   lmono_ctx* ctx = lead;
   for (int i = 0; i < n; ++i)
@@ -364,7 +423,7 @@ static int batch_capture(lmono_ctx* lead, lmono_ctx* const* ctxs, int n, const i
     c->stream = lead->cap_streams[i];
     ce = cudaStreamWaitEvent(c->stream, lead->ev_fork, 0);
     if (ce == cudaSuccess) rc = enqueue_body(c, nc_cap[i], ns_cap[i]);
-    if (!rc && ce == cudaSuccess) ce = cudaMemcpyAsync(c->h_state, c->d_state, sizeof(LmMapState), cudaMemcpyDeviceToHost, c->stream);
+    if (!rc && ce == cudaSuccess) rc = publish_state(c);
     if (!rc && ce == cudaSuccess) ce = cudaEventRecord(c->ev_join, c->stream);
     if (!rc && ce == cudaSuccess) ce = cudaStreamWaitEvent(origin, c->ev_join, 0);
     g->n_launch[i] = (int)(c->launches - l0);
@@ -382,19 +441,28 @@ static int batch_capture(lmono_ctx* lead, lmono_ctx* const* ctxs, int n, const i
   return LMONO_OK;
 }
 
-// d_corner[i] / d_surf[i]: float4 XYZI device buffers.  origin: the stream the batch is ordered on.
-static int batch_enqueue(lmono_ctx* const* ctxs, int n, const float4* const* d_corner, const int32_t* n_corner, const float4* const* d_surf,
-                         const int32_t* n_surf, const lmono_pose* wodom_curr, const lmono_pose* wmap_in, cudaStream_t origin) {
+// in[i]: the inputs of sequence i.  origin: the stream the batch is ordered on.  Every ctx's step is a pipelined
+// submission: result slot = n_submitted & 1, completion event ev_res[slot] (at most two may be outstanding per ctx).
+static int batch_enqueue(lmono_ctx* const* ctxs, int n, const LmStepIn* in, const lmono_pose* wodom_curr, const lmono_pose* wmap_in,
+                         cudaStream_t origin) {
   lmono_ctx* lead = ctxs[0];
   lmono_ctx* ctx = lead;
   int rc;
   if ((rc = batch_lazy_init(lead))) return rc;
+  // launch grids of every branch are sized for the largest sequence of the batch (kernels read the real counts from
+  // the state): one graph per (ctx set, bucket of the maximum), not one per combination of per-sequence buckets
+  int mc = 0, ms = 0;
+  for (int i = 0; i < n; ++i) {
+    lmono_ctx* c = ctxs[i];
+    if (in[i].n[0] < 0 || in[i].n[1] < 0 || in[i].n[0] > c->max_feat || in[i].n[1] > c->max_feat) return LMONO_E_CAPACITY;
+    if (c->n_submitted - c->n_waited >= 2) return LMONO_E_ARG;      // both result mirrors of this ctx are still unread
+    mc = in[i].n[0] > mc ? in[i].n[0] : mc; ms = in[i].n[1] > ms ? in[i].n[1] : ms;
+  }
   int nc_cap[LM_BATCH_MAX], ns_cap[LM_BATCH_MAX];
   for (int i = 0; i < n; ++i) {
     lmono_ctx* c = ctxs[i];
-    if (n_corner[i] < 0 || n_surf[i] < 0 || n_corner[i] > c->max_feat || n_surf[i] > c->max_feat) return LMONO_E_CAPACITY;
-    nc_cap[i] = bucket_up(n_corner[i], c->max_feat); ns_cap[i] = bucket_up(n_surf[i], c->max_feat);
-    // order the batch after whatever the ctx has in flight on its own stream
+    nc_cap[i] = bucket_up(mc, c->max_feat); ns_cap[i] = bucket_up(ms, c->max_feat);
+    // order the batch after whatever the ctx has in flight on its own stream (staged uploads, earlier single steps)
     if (c->stream != origin) { LM_CUDA(cudaEventRecord(c->ev_sync, c->stream)); LM_CUDA(cudaStreamWaitEvent(origin, c->ev_sync, 0)); }
   }
   LM_CUDA(cudaEventRecord(lead->ev0, origin));
@@ -404,7 +472,7 @@ static int batch_enqueue(lmono_ctx* const* ctxs, int n, const float4* const* d_c
     for (int k = 0; k < LM_ARGS_CHUNK; ++k) {
       const int i = base + (k < b.n ? k : 0);
       b.st[k] = ctxs[i]->d_state;
-      fill_step_args(&b.a[k], d_corner[i], n_corner[i], d_surf[i], n_surf[i], &wodom_curr[i], wmap_in ? &wmap_in[i] : nullptr);
+      fill_step_args(&b.a[k], in[i], &wodom_curr[i], wmap_in ? &wmap_in[i] : nullptr, (int)(ctxs[i]->n_submitted & 1u));
     }
     k_batch_args<<<1, 32, 0, origin>>>(b);
     LM_LAUNCH_CHECK();
@@ -433,6 +501,8 @@ static int batch_enqueue(lmono_ctx* const* ctxs, int n, const float4* const* d_c
     lmono_ctx* c = ctxs[i];
     c->launches += g->n_launch[i];
     c->step_pending = true; c->step_timed = (c == lead);
+    LM_CUDA(cudaEventRecord(c->ev_res[c->n_submitted & 1u], origin));
+    c->n_submitted++;
     any_other |= c->stream != origin;
   }
   if (any_other) {      // later work on a ctx's own stream is ordered after the batch
@@ -451,17 +521,11 @@ static bool batch_graph_ok(lmono_ctx* const* ctxs, int n) {
   return true;
 }
 
-extern "C" int lmono_map_step_device_batch(lmono_ctx* const* ctxs, int32_t n, const void* const* d_corner, const int32_t* n_corner,
-                                           const void* const* d_surf, const int32_t* n_surf, const lmono_pose* wodom_curr,
-                                           const lmono_pose* wmap_wodom_in, void* join_stream) {
-  if (!ctxs || n < 0 || !d_corner || !d_surf || !n_corner || !n_surf || !wodom_curr) return LMONO_E_ARG;
-  if (n == 0) return LMONO_OK;
-  for (int i = 0; i < n; ++i) if (!ctxs[i]) return LMONO_E_ARG;
-  cudaStream_t js = (cudaStream_t)join_stream;
-  if (batch_graph_ok(ctxs, n))
-    return batch_enqueue(ctxs, n, (const float4* const*)d_corner, n_corner, (const float4* const*)d_surf, n_surf, wodom_curr, wmap_wodom_in,
-                         js ? js : ctxs[0]->stream);
-  // plain launches (LMONO_NO_GRAPH, profiler or kernel marks on): every ctx on its own stream, fork / join with events
+// plain launches (LMONO_NO_GRAPH, profiler or kernel marks on, > LM_BATCH_MAX sequences): every ctx on its own stream,
+// fork / join with events; the same pipelined-submission bookkeeping as batch_enqueue
+static int batch_enqueue_plain(lmono_ctx* const* ctxs, int n, const LmStepIn* in, const lmono_pose* wodom_curr, const lmono_pose* wmap_in,
+                               cudaStream_t js) {
+  for (int i = 0; i < n; ++i) if (ctxs[i]->n_submitted - ctxs[i]->n_waited >= 2) return LMONO_E_ARG;
   if (js) {
     lmono_ctx* ctx = ctxs[0];
     LM_CUDA(cudaEventRecord(ctx->ev_fork, js));
@@ -470,48 +534,83 @@ extern "C" int lmono_map_step_device_batch(lmono_ctx* const* ctxs, int32_t n, co
     lmono_ctx* ctx = ctxs[i];
     if (js && ctx->stream != js) LM_CUDA(cudaStreamWaitEvent(ctx->stream, ctxs[0]->ev_fork, 0));
     int rc;
-    if ((rc = enqueue_step(ctx, (const float4*)d_corner[i], n_corner[i], (const float4*)d_surf[i], n_surf[i], &wodom_curr[i],
-                           wmap_wodom_in ? &wmap_wodom_in[i] : nullptr))) return rc;
+    const int slot = (int)(ctx->n_submitted & 1u);
+    if ((rc = enqueue_step(ctx, in[i], &wodom_curr[i], wmap_in ? &wmap_in[i] : nullptr, slot))) return rc;
+    if ((rc = publish_state(ctx))) return rc;
+    LM_CUDA(cudaEventRecord(ctx->ev_res[slot], ctx->stream));
+    ctx->n_submitted++;
     if (js && ctx->stream != js) { LM_CUDA(cudaEventRecord(ctx->ev_join, ctx->stream)); LM_CUDA(cudaStreamWaitEvent(js, ctx->ev_join, 0)); }
   }
   return LMONO_OK;
 }
 
-extern "C" int lmono_map_step_batch(lmono_ctx* const* ctxs, int32_t n, const lmono_cloud_view* corner_last, const lmono_cloud_view* surf_last,
-                                    const lmono_pose* wodom_curr, const lmono_pose* wmap_wodom_in,
-                                    lmono_pose* w_curr, lmono_pose* wmap_wodom, lmono_map_report* reports) {
+extern "C" int lmono_map_step_device_batch(lmono_ctx* const* ctxs, int32_t n, const void* const* d_corner, const int32_t* n_corner,
+                                           const void* const* d_surf, const int32_t* n_surf, const lmono_pose* wodom_curr,
+                                           const lmono_pose* wmap_wodom_in, void* join_stream) {
+  if (!ctxs || n < 0 || !d_corner || !d_surf || !n_corner || !n_surf || !wodom_curr) return LMONO_E_ARG;
+  if (n == 0) return LMONO_OK;
+  if (n > LM_BATCH_MAX) return LMONO_E_CAPACITY;
+  for (int i = 0; i < n; ++i) if (!ctxs[i]) return LMONO_E_ARG;
+  cudaStream_t js = (cudaStream_t)join_stream;
+  LmStepIn in[LM_BATCH_MAX];
+  for (int i = 0; i < n; ++i) {
+    in[i] = step_in_device((const float4*)d_corner[i], n_corner[i], (const float4*)d_surf[i], n_surf[i]);
+    // device-resident steps are retired by lmono_map_collect / lmono_sync, not by lmono_map_wait_batch: keep the
+    // pipelined-submission window open
+    ctxs[i]->n_waited = ctxs[i]->n_submitted;
+  }
+  if (batch_graph_ok(ctxs, n)) return batch_enqueue(ctxs, n, in, wodom_curr, wmap_wodom_in, js ? js : ctxs[0]->stream);
+  return batch_enqueue_plain(ctxs, n, in, wodom_curr, wmap_wodom_in, js);
+}
+
+extern "C" int lmono_map_submit_batch(lmono_ctx* const* ctxs, int32_t n, const lmono_cloud_view* corner_last, const lmono_cloud_view* surf_last,
+                                      const lmono_pose* wodom_curr, const lmono_pose* wmap_wodom_in) {
   if (!ctxs || n < 0 || !corner_last || !surf_last || !wodom_curr) return LMONO_E_ARG;
   if (n == 0) return LMONO_OK;
+  if (n > LM_BATCH_MAX) return LMONO_E_CAPACITY;
   for (int i = 0; i < n; ++i) if (!ctxs[i]) return LMONO_E_ARG;
-  int first = LMONO_OK;
-  if (batch_graph_ok(ctxs, n)) {
-    const float4* dc[LM_BATCH_MAX]; const float4* ds[LM_BATCH_MAX]; int32_t nc[LM_BATCH_MAX], ns[LM_BATCH_MAX];
-    for (int i = 0; i < n; ++i) {     // uploads on the ctx's own stream; the batch is ordered after them
-      int rc = step_upload(ctxs[i], corner_last[i], surf_last[i]);
-      if (rc) return rc;
-      dc[i] = ctxs[i]->d_in[0]; ds[i] = ctxs[i]->d_in[1]; nc[i] = corner_last[i].n; ns[i] = surf_last[i].n;
-    }
-    int rc = batch_enqueue(ctxs, n, dc, nc, ds, ns, wodom_curr, wmap_wodom_in, ctxs[0]->stream);
+  LmStepIn in[LM_BATCH_MAX];
+  for (int i = 0; i < n; ++i) {     // page-locked clouds: nothing to do here; others: staged on the ctx's own stream
+    int rc = step_inputs(ctxs[i], corner_last[i], surf_last[i], &in[i]);
     if (rc) return rc;
-    // the state read-backs are part of the graph: one wait on the origin stream covers every sequence
-    { lmono_ctx* ctx = ctxs[0]; LM_CUDA(cudaStreamSynchronize(ctx->stream)); }
-  } else {
-    for (int i = 0; i < n; ++i) {
-      lmono_ctx* ctx = ctxs[i];
-      int rc = step_upload(ctx, corner_last[i], surf_last[i]);
-      if (!rc) rc = enqueue_step(ctx, ctx->d_in[0], corner_last[i].n, ctx->d_in[1], surf_last[i].n, &wodom_curr[i], wmap_wodom_in ? &wmap_wodom_in[i] : nullptr);
-      if (!rc) {     // read-back queued right behind the step, so that the collect loop below only waits
-        cudaError_t e = cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(LmMapState), cudaMemcpyDeviceToHost, ctx->stream);
-        if (e != cudaSuccess) { ctx->last_cuda_error = (int)e; rc = LMONO_E_CUDA; }
-      }
-      if (rc && !first) first = rc;
-    }
   }
+  if (batch_graph_ok(ctxs, n)) return batch_enqueue(ctxs, n, in, wodom_curr, wmap_wodom_in, ctxs[0]->stream);
+  return batch_enqueue_plain(ctxs, n, in, wodom_curr, wmap_wodom_in, nullptr);
+}
+
+extern "C" int lmono_map_wait_batch(lmono_ctx* const* ctxs, int32_t n, lmono_pose* w_curr, lmono_pose* wmap_wodom, lmono_map_report* reports) {
+  if (!ctxs || n < 0) return LMONO_E_ARG;
+  for (int i = 0; i < n; ++i) if (!ctxs[i] || ctxs[i]->n_waited == ctxs[i]->n_submitted) return LMONO_E_ARG;
+  int first = LMONO_OK;
   for (int i = 0; i < n; ++i) {
-    int rc = collect(ctxs[i], w_curr ? &w_curr[i] : nullptr, wmap_wodom ? &wmap_wodom[i] : nullptr, reports ? &reports[i] : nullptr, false);
+    lmono_ctx* ctx = ctxs[i];
+    const int slot = (int)(ctx->n_waited & 1u);
+    cudaError_t e = cudaEventSynchronize(ctx->ev_res[slot]);
+    if (e != cudaSuccess) { ctx->last_cuda_error = (int)e; if (!first) first = LMONO_E_CUDA; continue; }
+    const bool last = ctx->n_submitted - ctx->n_waited == 1;
+    float ms = 0.f;
+    if (last && ctx->step_pending) { if (ctx->step_timed) cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->step_pending = false; }
+    ctx->n_waited++;
+    int rc = deliver(ctx, ctx->h_ring[slot], ms, w_curr ? &w_curr[i] : nullptr, wmap_wodom ? &wmap_wodom[i] : nullptr, reports ? &reports[i] : nullptr);
     if (rc && !first) first = rc;
   }
   return first;
+}
+
+extern "C" int lmono_map_step_batch(lmono_ctx* const* ctxs, int32_t n, const lmono_cloud_view* corner_last, const lmono_cloud_view* surf_last,
+                                    const lmono_pose* wodom_curr, const lmono_pose* wmap_wodom_in,
+                                    lmono_pose* w_curr, lmono_pose* wmap_wodom, lmono_map_report* reports) {
+  if (n == 0) return LMONO_OK;
+  // a synchronous step retires anything still in flight first, so that the result returned is this step's
+  if (ctxs && n > 0)
+    for (int i = 0; i < n; ++i) {
+      lmono_ctx* ctx = ctxs[i];
+      if (!ctx) continue;
+      for (; ctx->n_waited != ctx->n_submitted; ctx->n_waited++) LM_CUDA(cudaEventSynchronize(ctx->ev_res[ctx->n_waited & 1u]));
+    }
+  int rc = lmono_map_submit_batch(ctxs, n, corner_last, surf_last, wodom_curr, wmap_wodom_in);
+  if (rc) return rc;
+  return lmono_map_wait_batch(ctxs, n, w_curr, wmap_wodom, reports);
 }
 
 extern "C" int lmono_map_get_state(lmono_ctx* ctx, lmono_pose* wmap_wodom, int32_t cen[3]) {

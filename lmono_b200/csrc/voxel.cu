@@ -25,6 +25,7 @@ struct VgSegs {
   const int32_t* n[LM_SORT_MAXSEG]; int32_t* out_n[LM_SORT_MAXSEG];
   float inv_leaf[LM_SORT_MAXSEG];
   int off[LM_SORT_MAXSEG];
+  int fetch;      // 1: segment s may be fetched from host memory (LmMapState::in_src / in_stride / in_ioff [s]) into in_ptr[s]
 };
 
 __device__ __forceinline__ uint32_t d_f2ord(float f) { uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
@@ -47,8 +48,22 @@ __global__ void __launch_bounds__(256) k_vg_keys(VgSegs sg, VgParams* __restrict
   if (blockIdx.x * blockDim.x >= n) return;
   uint32_t mn[3] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu }, mx[3] = { 0u, 0u, 0u };
   if (i < n) {
-    const float4* __restrict__ src = sg.in_ind[seg] ? *sg.in_ind[seg] : sg.in[seg];
-    const float4 p = src[i];
+    const float4* src = sg.in_ind[seg] ? *sg.in_ind[seg] : sg.in[seg];
+    float4 p;
+    const int stride = sg.fetch ? st->in_stride[seg] : 0;
+    if (stride) {
+      // fused upload: the record comes over PCIe from the caller's page-locked AoS buffer (read once), the float4 copy
+      // that k_vg_write gathers from stays in device memory
+      const uint8_t* rec = (const uint8_t*)st->in_src[seg] + (size_t)i * stride;
+      const int ioff = st->in_ioff[seg];
+      if (stride == 16 && ioff == 12 && ((uintptr_t)st->in_src[seg] & 15) == 0) p = __ldcs(reinterpret_cast<const float4*>(rec));
+      else {
+        const float* f = reinterpret_cast<const float*>(rec);
+        p.x = __ldcs(f); p.y = __ldcs(f + 1); p.z = __ldcs(f + 2);
+        p.w = ioff >= 0 ? __ldcs(reinterpret_cast<const float*>(rec + ioff)) : 0.0f;
+      }
+      const_cast<float4*>(src)[i] = p;
+    } else p = src[i];
     const float il = sg.inv_leaf[seg];
     int v[3] = { (int)floorf(__fmul_rn(p.x, il)), (int)floorf(__fmul_rn(p.y, il)), (int)floorf(__fmul_rn(p.z, il)) };
     bool bad = false;
@@ -170,9 +185,10 @@ __global__ void __launch_bounds__(VW_THREADS) k_vg_write(VgSegs sg, VgParams* __
 // VoxelGrid of up to LM_SORT_MAXSEG clouds with shared launches.  Scratch: ctx->d_sort_a/b/c (segment s at
 // offset sum of n_max of the segments before it), ctx->d_vg.
 int lm_voxel_grid_multi(lmono_ctx* ctx, int nseg, const float4* const* in, const int32_t* const* n_dev, const int* n_max,
-                        const float* leaf, float4* const* out, int32_t* const* out_n_dev, const float4* const* const* in_ind) {
+                        const float* leaf, float4* const* out, int32_t* const* out_n_dev, const float4* const* const* in_ind, bool fetch) {
   if (nseg < 1 || nseg > LM_SORT_MAXSEG) return LMONO_E_ARG;
   VgSegs sg; LmSortSegs ss;
+  sg.fetch = fetch ? 1 : 0;
   ss.in = ctx->d_sort_a; ss.tmp = ctx->d_sort_b; ss.out = ctx->d_sort_c;
   int off = 0, mx = 0;
   for (int s = 0; s < LM_SORT_MAXSEG; ++s) {
@@ -194,7 +210,7 @@ int lm_voxel_grid_multi(lmono_ctx* ctx, int nseg, const float4* const* in, const
 
 int lm_voxel_grid_device(lmono_ctx* ctx, const float4* in, const int32_t* n_dev, int n_max, float leaf,
                          float4* out, int32_t* out_n_dev) {
-  return lm_voxel_grid_multi(ctx, 1, &in, &n_dev, &n_max, &leaf, &out, &out_n_dev, nullptr);
+  return lm_voxel_grid_multi(ctx, 1, &in, &n_dev, &n_max, &leaf, &out, &out_n_dev, nullptr, false);
 }
 
 int lm_voxel_init(lmono_ctx* ctx) {

@@ -99,3 +99,91 @@ def test_batch_wmap_in(gpu_ctx_factory):
         batch.set_host_inputs([c], [su])
         rb = batch.step()[0]
         assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1])
+
+
+def _pinned(a):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    return t, t.numpy()
+
+
+def test_pipelined_submit_wait_equals_sequences_alone(gpu_ctx_factory):
+    """lmono_map_submit_batch / lmono_map_wait_batch with two submissions in flight per sequence (sweep k+1 is
+    submitted before sweep k is waited for; page-locked inputs fetched by the step itself): same bits as lmono_map_step."""
+    import torch
+    from lmono_b200 import api
+    cm, sm = scenario.small_map()
+    common = torch.cuda.Stream()
+    ctxs = []
+    for s in range(NSEQ):
+        c = gpu_ctx_factory(stream=common.cuda_stream)
+        c.map_import(0, cm)
+        c.map_import(1, sm)
+        ctxs.append(c)
+    batch = api.SequenceBatch(ctxs)
+    sweeps = [_seq_sweeps(s) for s in range(NSEQ)]
+    keep, args = [], []
+    for k in range(NSWEEP):
+        a = api.BatchArgs(NSEQ)
+        a.set_odom([(sweeps[s][k][4], sweeps[s][k][5]) for s in range(NSEQ)])
+        hc = [_pinned(sweeps[s][k][0]) for s in range(NSEQ)]
+        hs = [_pinned(sweeps[s][k][1]) for s in range(NSEQ)]
+        keep.append((hc, hs))
+        a.set_host_inputs([x[1] for x in hc], [x[1] for x in hs])
+        args.append(a)
+    got = [[] for _ in range(NSEQ)]
+
+    def take(res):
+        for s in range(NSEQ):
+            q, t, rep = res[s]
+            got[s].append((q, t, list(rep.corner_num), list(rep.surf_num)))
+
+    batch.submit(args[0])
+    for k in range(1, NSWEEP):
+        batch.submit(args[k])            # two in flight
+        with pytest.raises(api.LmonoError):
+            batch.submit(args[k])        # a third is refused: both result mirrors are unread
+        take(batch.wait())
+    take(batch.wait())
+    with pytest.raises(api.LmonoError):
+        batch.wait()                     # nothing outstanding
+    for s in range(NSEQ):
+        ref, ref_maps = _alone(gpu_ctx_factory, s)
+        for k in range(NSWEEP):
+            assert np.array_equal(got[s][k][0], ref[k][0]) and np.array_equal(got[s][k][1], ref[k][1]), (s, k)
+            assert got[s][k][2:] == ref[k][2:], (s, k)
+        for w in (0, 1):
+            m = ctxs[s].map_export(w, 1)
+            assert np.array_equal(m.view(np.uint32), ref_maps[w].view(np.uint32)), (s, w)
+
+
+@pytest.mark.parametrize("layout", ["xyzi32", "xyz12", "pageable", "staged_env"])
+def test_fused_upload_layouts(gpu_ctx_factory, layout, monkeypatch):
+    """page-locked pcl::PointXYZI records (32 B, intensity at byte 16 -- Aloam/include/aloam_velodyne/common.h:43),
+    bare XYZ records and pageable memory all register exactly like the packed float4 upload"""
+    if layout == "staged_env":
+        monkeypatch.setenv("LMONO_NO_ZEROCOPY", "1")
+    cm, sm = scenario.small_map()
+    a = gpu_ctx_factory(); b = gpu_ctx_factory()
+    for c in (a, b):
+        c.map_import(0, cm)
+        c.map_import(1, sm)
+    for (c, su, q, t, qp, tp) in scenario.sweeps(2, seed=77, dt=0.1, drot=0.5):
+        def conv(p):
+            if layout == "xyzi32":
+                w = np.zeros((len(p), 8), np.float32); w[:, :3] = p[:, :3]; w[:, 4] = p[:, 3]; w[:, 3] = 1.0; w[:, 5:] = 7.0
+                return _pinned(w)
+            if layout == "xyz12":
+                return _pinned(p[:, :3])
+            if layout == "pageable":
+                return None, p.copy()
+            return _pinned(p)
+        pc, ps = conv(c), conv(su)
+        if layout == "xyz12":     # the reference copy sees zero intensities as well
+            c = c.copy(); su = su.copy(); c[:, 3] = 0; su[:, 3] = 0
+        ra = a.map_step(c, su, qp, tp)
+        rb = b.map_step(pc[1], ps[1], qp, tp)
+        assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1])
+        assert list(ra[2].corner_num) == list(rb[2].corner_num) and list(ra[2].surf_num) == list(rb[2].surf_num)
+    for w in (0, 1):
+        assert np.array_equal(a.map_export(w, 1).view(np.uint32), b.map_export(w, 1).view(np.uint32))
