@@ -256,6 +256,10 @@ int lmono_voxel_grid(lmono_ctx* ctx, lmono_cloud_view in, float leaf, lmono_clou
  * event (the step then runs as plain launches, not as a graph replay).  lmono_kmarks_dump writes one line
  * "source.cu:line count total_ms" per launch site; bench.py --kernels maps the sites to kernel names. */
 int lmono_kmarks_enable(lmono_ctx* ctx, int on);
+/* With LMONO_TIMELINE=1 in the environment every launch of a mapping step is followed by a one-thread %globaltimer
+ * stamp kernel (also inside the step / batch graphs); lmono_timeline_dump writes "<file>:<line> <ns>" per stamp of the
+ * last step, so the kernels of concurrent sequences can be laid on one time axis (profiles/batch_timeline.py). */
+int lmono_timeline_dump(lmono_ctx* ctx, char* buf, int32_t cap);
 int lmono_kmarks_dump(lmono_ctx* ctx, char* buf, int32_t cap);
 
 /* Latency study hook: %globaltimer stamps (ns) written by instrumented kernels (slot map in DESIGN.md):

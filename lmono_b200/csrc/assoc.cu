@@ -462,6 +462,124 @@ __device__ __forceinline__ void d_knn5_group(const float4* __restrict__ cellpts,
   for (int k = 0; k < KNN_K; ++k) { tk[k] = ok_[k]; tr[k] = or_[k]; }
 }
 
+// ---- one-thread-per-query exact 5-NN (throughput form).  The 8-lane search above replicates the cell arithmetic in
+// every lane and pays a divergent top-5 insertion per candidate trip (342 warp instructions per query); here a thread
+// owns a query, walks the candidate runs itself -- the two x-adjacent cells of a cube are ONE contiguous run of the
+// cell-sorted copy, so the usual query has 4 runs, not 8 cells -- and only PARKS the few candidates with d2 < 1.0
+// (about one in five) in a shared-memory column; the ordered top-5 insertion runs afterwards over the parked ones
+// only.  Same candidate set, same 64-bit (d2, canonical index) ranking, hence the same neighbours bit for bit.
+// Per axis: c0 = (floor(q) - 1) >> 1, cube q0 = floor((c0 + 12) / 25), r0 = c0 + 12 - 25 q0 in [0, 24]; cell c0 is local
+// r0 + 1 of cube q0 (and ALSO local 0 of cube q0 + 1 when r0 == 24), c1 = c0 + 1 likewise.
+constexpr int KNN1_THREADS = 128;
+constexpr int KNN1_SLOTS = 12;
+constexpr int KNN1_SMEM = KNN1_THREADS * KNN1_SLOTS * 12;
+
+__device__ __forceinline__ void d_axis_split(float q, int* q0, int* r0) {
+  constexpr int FQ_MAX = 1 << 24;
+  const int f = min(max((int)floorf(q), -FQ_MAX), FQ_MAX);
+  const int c0 = (f - 1) >> 1;
+  *q0 = d_floordiv25(c0 + 12);
+  *r0 = c0 + 12 - 25 * *q0;
+}
+// entry e (0 .. n-1, n = 2 or 3) of the (cube, local cell) pairs covering cells c0, c1 on one axis
+__device__ __forceinline__ void d_axis_entry(int q0, int r0, int e, int* cube, int* cell) {
+  if (r0 <= 22) { *cube = q0; *cell = r0 + 1 + e; }
+  else { const int s = r0 - 23 + e; *cube = q0 + (s >= 2 ? 1 : 0); *cell = s < 2 ? 24 + s : s - 2; }   // (q0,24) (q0,25) (q0+1,0) (q0+1,1)
+}
+// x axis: contiguous runs (cube, first local cell, cells): one run of 2 cells, or 2 + 1 / 1 + 2 next to a cube border
+__device__ __forceinline__ void d_axis_run(int q0, int r0, int e, int* cube, int* cell, int* len) {
+  if (r0 <= 22) { *cube = q0; *cell = r0 + 1; *len = 2; }
+  else if (r0 == 23) { *cube = q0 + e; *cell = e ? 0 : 24; *len = e ? 1 : 2; }
+  else { *cube = q0 + e; *cell = e ? 0 : 25; *len = e ? 2 : 1; }
+}
+
+__device__ __forceinline__ void d_knn5_thread(const float4* __restrict__ cellpts, const uint32_t* __restrict__ cellstart, int cap,
+                                              const int2* __restrict__ slot_info, int cen0, int cen1, int cen2,
+                                              float qx, float qy, float qz,
+                                              unsigned long long* __restrict__ s_key, int* __restrict__ s_ref,   // this thread's column, stride KNN1_THREADS
+                                              unsigned long long (&tk)[KNN_K], int (&tr)[KNN_K]) {
+#pragma unroll
+  for (int k = 0; k < KNN_K; ++k) { tk[k] = KNN_NOKEY; tr[k] = -1; }
+  int qx0, rx0, qy0, ry0, qz0, rz0;
+  d_axis_split(qx, &qx0, &rx0); d_axis_split(qy, &qy0, &ry0); d_axis_split(qz, &qz0, &rz0);
+  const int nrx = rx0 <= 22 ? 1 : 2, npy = ry0 <= 22 ? 2 : 3, npz = rz0 <= 22 ? 2 : 3;
+  const int nyz = npy * npz, nruns = nrx * nyz;
+  int npark = 0;
+  for (int rb = 0; rb < nruns; rb += 4) {            // 4 runs per round (the usual query has exactly 4): their table look-ups overlap
+    int start[4], cnt[4], bidx[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = rb + u;
+      cnt[u] = 0; start[u] = 0; bidx[u] = 0;
+      if (r < nruns) {
+        const int ex = nrx == 1 ? 0 : (r >= nyz ? 1 : 0);
+        const int ryz = r - ex * nyz;
+        const int ez = npy == 2 ? (ryz >> 1) : (ryz / 3), ey = ryz - ez * npy;
+        int gi, ci, len, gj, cj, gk, ck;
+        d_axis_run(qx0, rx0, ex, &gi, &ci, &len);
+        d_axis_entry(qy0, ry0, ey, &gj, &cj);
+        d_axis_entry(qz0, rz0, ez, &gk, &ck);
+        const int li = gi + cen0, lj = gj + cen1, lk = gk + cen2;
+        if (li >= 0 && li < LM_GW && lj >= 0 && lj < LM_GH && lk >= 0 && lk < LM_GD) {
+          const int2 inf = slot_info[d_phys_slot(gi, gj, gk)];
+          if (inf.x >= 0) {
+            const uint32_t* cs = cellstart + (size_t)inf.x * (LM_NCELL + 1) + (ci + LM_CELLS_AXIS * (cj + LM_CELLS_AXIS * ck));
+            const uint32_t b = cs[0], e = cs[len];
+            cnt[u] = (int)(e - b); start[u] = inf.x * cap + (int)b; bidx[u] = inf.y;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float4* __restrict__ run = cellpts + start[u];
+      const int n = cnt[u], bi = bidx[u];
+      for (int j = 0; j < n; j += 4) {               // four independent loads in flight per trip (the scan is a latency chain)
+        float4 p[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) p[v] = run[min(j + v, n - 1)];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const float dx = __fsub_rn(qx, p[v].x), dy = __fsub_rn(qy, p[v].y), dz = __fsub_rn(qz, p[v].z);
+          const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+          if (j + v < n && d < 1.0f) {
+            const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)(bi + __float_as_int(p[v].w));
+            if (npark < KNN1_SLOTS) { s_key[npark * KNN1_THREADS] = key; s_ref[npark * KNN1_THREADS] = start[u] + j + v; ++npark; }
+            else d_top5_insert(tk, tr, key, start[u] + j + v);
+          }
+        }
+      }
+    }
+  }
+  for (int i = 0; i < npark; ++i) d_top5_insert(tk, tr, s_key[i * KNN1_THREADS], s_ref[i * KNN1_THREADS]);
+}
+
+__global__ void __launch_bounds__(KNN1_THREADS) k_assoc_knn1(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, const int32_t* __restrict__ slot_valid_rank,
+                                                             const float4* __restrict__ stack0, const float4* __restrict__ stack1, int32_t* __restrict__ nnref) {
+  __shared__ unsigned long long s_key[KNN1_SLOTS * KNN1_THREADS];
+  __shared__ int s_ref[KNN1_SLOTS * KNN1_THREADS];
+  if (!st->optimize) return;
+  const int n0 = st->stack_n[0], n1 = st->stack_n[1];
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n0 + n1) return;
+  const int ty = gid < n0 ? 0 : 1;
+  const int qi = ty == 0 ? gid : gid - n0;
+  const float4 sel = d_associate(st->q_w_curr, st->t_w_curr, ty == 0 ? stack0[qi] : stack1[qi]);
+  int32_t* out = nnref + (size_t)gid * KNN_K;
+  if (st->shard_n > 1 &&
+      lm_cube_owner(d_cube_coord((double)sel.x, 0), d_cube_coord((double)sel.y, 0), d_cube_coord((double)sel.z, 0), st->shard_n) != st->shard_rank) {
+    out[0] = -1;
+    return;
+  }
+  unsigned long long key[KNN_K]; int ref[KNN_K];
+  d_knn5_thread(ty == 0 ? M0.cellpts : M1.cellpts, ty == 0 ? M0.cellstart : M1.cellstart, ty == 0 ? M0.cap : M1.cap,
+                lm_slot_info(slot_valid_rank) + ty * LM_NSLOT, st->cen[0], st->cen[1], st->cen[2], sel.x, sel.y, sel.z,
+                s_key + threadIdx.x, s_ref + threadIdx.x, key, ref);
+  const bool ok = ref[KNN_K - 1] >= 0;       // every kept candidate has d2 < 1.0: the :584,652 gate is "a 5th neighbour exists"
+#pragma unroll
+  for (int k = 0; k < KNN_K; ++k) out[k] = ok ? ref[k] : -1;
+}
+
 // Association = two launches.  k_assoc_knn: one GROUP-lane group per query (both map types in one launch), light on
 // registers so every query of a sweep is resident at once; it leaves the 5 neighbour references (or -1 when the
 // d2[4] < 1.0 gate of :584,652 fails).  k_assoc_fit: one thread per query for the fp64 line / plane fit -- with the
@@ -539,7 +657,8 @@ int lm_map_associate(lmono_ctx* ctx, int n_max_corner, int n_max_surf) {
   if (nq <= 0) return LMONO_OK;
   static const int group = getenv("LMONO_KNN_GROUP") ? atoi(getenv("LMONO_KNN_GROUP")) : GROUP_DEFAULT;     // experiment switch
 #define KNN_ARGS ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_slot_valid_rank, ctx->d_stack[0], ctx->d_stack[1], ctx->d_nnref
-  if (group == 1) k_assoc_knn<1><<<lm_div_up(nq * 1, 256), 256, 0, ctx->stream>>>(KNN_ARGS);
+  if (group == 0) k_assoc_knn1<<<lm_div_up(nq, KNN1_THREADS), KNN1_THREADS, 0, ctx->stream>>>(KNN_ARGS);
+  else if (group == 1) k_assoc_knn<1><<<lm_div_up(nq * 1, 256), 256, 0, ctx->stream>>>(KNN_ARGS);
   else if (group == 2) k_assoc_knn<2><<<lm_div_up(nq * 2, 256), 256, 0, ctx->stream>>>(KNN_ARGS);
   else if (group == 4) k_assoc_knn<4><<<lm_div_up(nq * 4, 256), 256, 0, ctx->stream>>>(KNN_ARGS);
   else k_assoc_knn<8><<<lm_div_up(nq * 8, 256), 256, 0, ctx->stream>>>(KNN_ARGS);   // k_assoc_knn<<<
@@ -573,8 +692,32 @@ __global__ void __launch_bounds__(256) k_knn5_hook(const LmMapState* __restrict_
   }
 }
 
+__global__ void __launch_bounds__(KNN1_THREADS) k_knn5_hook1(const LmMapState* __restrict__ st, LmMapType M, int ty,
+                                                             const int32_t* __restrict__ slot_valid_rank,
+                                                             const float4* __restrict__ q, int n, int32_t* __restrict__ oidx, float* __restrict__ od2) {
+  __shared__ unsigned long long s_key[KNN1_SLOTS * KNN1_THREADS];
+  __shared__ int s_ref[KNN1_SLOTS * KNN1_THREADS];
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n) return;
+  const float4 p = q[gid];
+  unsigned long long key[KNN_K]; int ref[KNN_K];
+  d_knn5_thread(M.cellpts, M.cellstart, M.cap, lm_slot_info(slot_valid_rank) + ty * LM_NSLOT, st->cen[0], st->cen[1], st->cen[2],
+                p.x, p.y, p.z, s_key + threadIdx.x, s_ref + threadIdx.x, key, ref);
+#pragma unroll
+  for (int k = 0; k < KNN_K; ++k) {
+    const bool ok = ref[k] >= 0;
+    oidx[gid * KNN_K + k] = ok ? (int)(unsigned)(key[k] & 0xffffffffull) : -1;
+    od2[gid * KNN_K + k] = ok ? __uint_as_float((unsigned)(key[k] >> 32)) : INFINITY;
+  }
+}
+
 int lm_knn5_device(lmono_ctx* ctx, int which, const float4* d_q, int n, int32_t* d_idx, float* d_d2) {
   if (n <= 0) return LMONO_OK;
+  if (getenv("LMONO_KNN_GROUP") && atoi(getenv("LMONO_KNN_GROUP")) == 0) {
+    k_knn5_hook1<<<lm_div_up(n, KNN1_THREADS), KNN1_THREADS, 0, ctx->stream>>>(ctx->d_state, ctx->map[which], which, ctx->d_slot_valid_rank, d_q, n, d_idx, d_d2);
+    LM_LAUNCH_CHECK();
+    return LMONO_OK;
+  }
   const int blocks = lm_div_up(n * GROUP, 256);
   k_knn5_hook<<<blocks, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[which], which, ctx->d_slot_valid_rank, d_q, n, d_idx, d_d2);
   LM_LAUNCH_CHECK();

@@ -23,6 +23,12 @@ constexpr int LM_SORT_MAXSEG = 2;                 // independent segments sorted
 constexpr int LM_TAIL_TILE = 16384;               // max points of a slab the whole-slab fallback refilter can re-voxelise (smem sort)
 constexpr int LM_RF_CHUNK = 1024;                 // points per CTA in the chunked refilter kernels
 constexpr int LM_WIN_MAX = 75;                    // cubes of the 5x5x3 window
+// d_rf_plan layout: counts, then three lists of (type * LM_WIN_MAX + window rank).  The per-step kernels that only a few
+// cubes need (index build, whole-slab re-voxelisation, tail merge) run on small grids that walk these lists instead of
+// one (mostly idle) CTA per window cube: with many sequences per GPU the idle CTAs of all of them queue for SM slots.
+constexpr int LM_PLAN_DIRTY_N = 0, LM_PLAN_WHOLE_N = 1, LM_PLAN_ACTIVE_N = 2, LM_PLAN_TF_N = 3;
+constexpr int LM_PLAN_DIRTY = 16, LM_PLAN_WHOLE = 16 + 2 * LM_WIN_MAX, LM_PLAN_ACTIVE = 16 + 4 * LM_WIN_MAX, LM_PLAN_INTS = 16 + 6 * LM_WIN_MAX;
+constexpr int LM_RF_TF_CHUNK = 256;               // tail points per CTA in k_rf_tailflags
 
 // device fault bits (LmMapState::fault)
 enum : unsigned {
@@ -145,6 +151,7 @@ constexpr int LM_MAX_BGRAPHS = 16;
 struct LmBatchGraph { int n; lmono_ctx* ctxs[LM_BATCH_MAX]; int nc_cap[LM_BATCH_MAX], ns_cap[LM_BATCH_MAX]; cudaGraphExec_t exec; int n_launch[LM_BATCH_MAX]; };
 constexpr int LM_GRAPH_BUCKET = 2048;     // launch grids are sized for counts rounded up to this
 
+constexpr int LM_TL_MAX = 64;
 struct lmono_ctx {
   int device;
   lmono_params prm;
@@ -187,8 +194,11 @@ struct lmono_ctx {
   float4* d_full;                           // full-res sweep
   int32_t* d_slot_first; int32_t* d_slot_base; // insertion run tables [LM_NSLOT]
   int32_t* d_rf_nvx;                        // refilter scratch [2][75][max cap]: (new voxels before j) << 1 | (j starts a new voxel)
+  int32_t* d_rf_tlb;                        // refilter scratch [2][75][max cap]: lower bound of a tail run head's key in the prefix
   int32_t* d_rf_work;                       // [4 + 2*75*chunks]: chunk work list of the cubes being refiltered
   int32_t* d_rf_meta;                       // [2][75][8]: active, total_new, ns, nt, unsorted flag, cur
+  int32_t* d_rf_plan;                       // compact per-step work lists (LM_PLAN_*): dirty cubes, cubes to re-voxelise whole, cubes with a tail
+  int32_t* d_rf_tf;                         // tail-chunk work list of k_rf_tailflags: (type * 75 + window rank) << 16 | chunk
   float4* d_export; size_t export_cap;      // export / import staging
   int32_t* d_export_off;                    // [LM_NSLOT+1]
   int max_feat, max_sweep;
@@ -206,6 +216,9 @@ struct lmono_ctx {
   bool prof_on; int prof_n; int prof_tag[LM_PROF_MAX_EVENTS]; cudaEvent_t prof_ev[LM_PROF_MAX_EVENTS][2];
   // per-launch marks (lmono_kmarks_*): one CUDA event after every kernel launch, keyed by the launch site
   bool kmark_on; int kmark_n; cudaEvent_t* kmark_ev; const char** kmark_file; int* kmark_line;
+  // graph-compatible timeline (LMONO_TIMELINE=1, lmono_timeline_dump): a one-thread %globaltimer stamp kernel after every
+  // launch, captured into the step / batch graphs, so concurrent sequences can be laid on one time axis
+  bool tl_on; int tl_n; unsigned long long* d_tl; const char* tl_file[LM_TL_MAX]; int tl_line[LM_TL_MAX];
 };
 
 static inline void lm_prof_begin(lmono_ctx* ctx, int tag) {
@@ -223,13 +236,24 @@ static inline void lm_prof_end(lmono_ctx* ctx) {
   fprintf(stderr, "[lmono_b200] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); \
   return LMONO_E_CUDA; } } while (0)
 constexpr int LM_KMARK_MAX = 8192;
+#ifdef __CUDACC__
+static __global__ void k_tl_stamp(unsigned long long* p) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); *p = t; }
+static inline void lm_tl(lmono_ctx* ctx, const char* file, int line) {
+  if (!ctx->tl_on || !ctx->d_tl || ctx->tl_n >= LM_TL_MAX) return;
+  ctx->tl_file[ctx->tl_n] = file; ctx->tl_line[ctx->tl_n] = line;
+  k_tl_stamp<<<1, 1, 0, ctx->stream>>>(ctx->d_tl + ctx->tl_n);
+  ctx->tl_n++;
+}
+#else
+static inline void lm_tl(lmono_ctx*, const char*, int) {}
+#endif
 static inline void lm_kmark(lmono_ctx* ctx, const char* file, int line) {
   if (!ctx->kmark_on || ctx->kmark_n >= LM_KMARK_MAX) return;
   ctx->kmark_file[ctx->kmark_n] = file; ctx->kmark_line[ctx->kmark_n] = line;
   cudaEventRecord(ctx->kmark_ev[ctx->kmark_n], ctx->stream);
   ctx->kmark_n++;
 }
-#define LM_LAUNCH_CHECK() do { ctx->launches++; lm_kmark(ctx, __FILE__, __LINE__); cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { ctx->last_cuda_error = (int)_e; \
+#define LM_LAUNCH_CHECK() do { ctx->launches++; lm_kmark(ctx, __FILE__, __LINE__); lm_tl(ctx, __FILE__, __LINE__); cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { ctx->last_cuda_error = (int)_e; \
   fprintf(stderr, "[lmono_b200] launch error %s at %s:%d\n", cudaGetErrorName(_e), __FILE__, __LINE__); return LMONO_E_CUDA; } } while (0)
 
 static inline int lm_div_up(int a, int b) { return (a + b - 1) / b; }
@@ -466,6 +490,30 @@ __device__ __forceinline__ int d_lower_bound_u32(const uint32_t* sorted, int n, 
   int lo = 0, hi = n;
   while (lo < hi) { int mid = (lo + hi) >> 1; if (sorted[mid] < key) lo = mid + 1; else hi = mid; }
   return lo;
+}
+// the same result with eight independent probes per step (9-ary search): ~log9(n) dependent memory round trips instead
+// of log2(n) -- for searches whose cost is the latency of the chain, not the number of loads
+__device__ __forceinline__ int d_lower_bound_u32_wide(const uint32_t* __restrict__ sorted, int n, uint32_t key) {
+  int lo = 0, hi = n;                       // the answer lies in [lo, hi]
+  while (hi - lo > 8) {
+    const int step = (hi - lo) / 9;         // >= 1
+    uint32_t v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = sorted[lo + (k + 1) * step];
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c += v[k] < key ? 1 : 0;
+    const int nlo = c > 0 ? lo + c * step + 1 : lo;
+    const int nhi = c < 8 ? lo + (c + 1) * step : hi;
+    lo = nlo; hi = nhi;
+  }
+  uint32_t v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = lo + k < hi ? sorted[lo + k] : 0xFFFFFFFFu;
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) c += (lo + k < hi && v[k] < key) ? 1 : 0;
+  return lo + c;
 }
 #endif  // __CUDACC__
 

@@ -100,6 +100,7 @@ extern "C" int lmono_create(int device, const lmono_params* params, void* stream
   LM_CUDA(cudaMalloc((void**)&ctx->d_partials, sizeof(double) * 32 * (1024 + 8)));
   LM_CUDA(cudaMalloc((void**)&ctx->d_stamps, sizeof(unsigned long long) * 4096));
   LM_CUDA(cudaMemsetAsync(ctx->d_stamps, 0, sizeof(unsigned long long) * 4096, ctx->stream));
+  LM_CUDA(cudaMalloc((void**)&ctx->d_tl, sizeof(unsigned long long) * LM_TL_MAX));
   const size_t nf = (size_t)ctx->max_feat;
   ctx->raw_bytes = (size_t)ctx->max_sweep * 32;
   for (int i = 0; i < 3; ++i) LM_CUDA(cudaMalloc((void**)&ctx->d_raw[i], ctx->raw_bytes));
@@ -147,7 +148,7 @@ extern "C" void lmono_destroy(lmono_ctx* ctx) {
   lm_odom_free(ctx);
   lm_color_free(ctx);
   lm_map_free(ctx);
-  cudaFree(ctx->d_state); cudaFreeHost(ctx->h_state); for (int i = 0; i < 2; ++i) { cudaFreeHost(ctx->h_ring[i]); cudaEventDestroy(ctx->ev_res[i]); } cudaFree(ctx->d_lm); cudaFree(ctx->d_slot_valid_rank); cudaFree(ctx->d_partials); cudaFree(ctx->d_stamps); cudaFree(ctx->d_nnref); cudaFree(ctx->d_rf_nvx); cudaFree(ctx->d_rf_work); cudaFree(ctx->d_rf_meta);
+  cudaFree(ctx->d_state); cudaFreeHost(ctx->h_state); for (int i = 0; i < 2; ++i) { cudaFreeHost(ctx->h_ring[i]); cudaEventDestroy(ctx->ev_res[i]); } cudaFree(ctx->d_lm); cudaFree(ctx->d_slot_valid_rank); cudaFree(ctx->d_partials); cudaFree(ctx->d_stamps); cudaFree(ctx->d_tl); cudaFree(ctx->d_nnref); cudaFree(ctx->d_rf_nvx); cudaFree(ctx->d_rf_tlb); cudaFree(ctx->d_rf_work); cudaFree(ctx->d_rf_meta); cudaFree(ctx->d_rf_plan); cudaFree(ctx->d_rf_tf);
   for (int i = 0; i < 3; ++i) cudaFree(ctx->d_raw[i]);
   for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_in[i]); cudaFree(ctx->d_stack[i]); cudaFree(ctx->d_world[i]); cudaFree(ctx->d_fac[i]); }
   cudaFree(ctx->d_sort_a); cudaFree(ctx->d_sort_b); cudaFree(ctx->d_sort_c); cudaFree(ctx->d_blockcnt); cudaFree(ctx->d_tmp_i32);

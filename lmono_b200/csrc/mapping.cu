@@ -85,8 +85,19 @@ static int voxel_both(lmono_ctx* ctx, const float4* d_corner, int nc, const floa
 
 // the step body: nc / ns only size the launch grids (every kernel reads the real counts and the input pointers
 // from the state)
+__global__ void k_nop() {}
 static int enqueue_body(lmono_ctx* ctx, int nc, int ns) {
   int rc;
+  static const int n_dummy = getenv("LMONO_DUMMY_LAUNCHES") ? atoi(getenv("LMONO_DUMMY_LAUNCHES")) : 0;   // experiment: is a batch launch-rate bound?
+  for (int i = 0; i < n_dummy; ++i) k_nop<<<1, 32, 0, ctx->stream>>>();
+  static const int n_big = getenv("LMONO_DUMMY_BIG") ? atoi(getenv("LMONO_DUMMY_BIG")) : 0;
+  for (int i = 0; i < n_big; ++i) k_nop<<<dim3(75, 2), 1024, 0, ctx->stream>>>();
+  static const bool tl_env = getenv("LMONO_TIMELINE") && getenv("LMONO_TIMELINE")[0] == '1';
+  if (tl_env) {
+    ctx->tl_on = true; ctx->tl_n = 0;
+    lm_tl(ctx, "begin", 0);
+  }
+  struct TlOff { lmono_ctx* c; ~TlOff() { c->tl_on = false; } } tl_off{ctx};
   lm_prof_begin(ctx, LM_PROF_WINDOW);
   if ((rc = lm_map_begin_step(ctx, nullptr, nullptr))) return rc;           // :309-539
   lm_prof_end(ctx);
@@ -771,6 +782,23 @@ extern "C" int lmono_profile_read(lmono_ctx* ctx, float* ms /*[LM_PROF_NTAGS]*/,
 }
 
 // ---- per-launch marks: a CUDA event after every kernel launch of the (non-graph) step, keyed by launch site ----
+// LMONO_TIMELINE=1: "<file>:<line> <globaltimer ns>" per stamp of the last step of this ctx (lines in launch order; the
+// stamp after a launch runs when that kernel has finished)
+extern "C" int lmono_timeline_dump(lmono_ctx* ctx, char* buf, int32_t cap) {
+  if (!ctx || !buf || cap <= 0) return LMONO_E_ARG;
+  buf[0] = 0;
+  if (!ctx->d_tl || ctx->tl_n <= 0) return LMONO_OK;
+  unsigned long long h[LM_TL_MAX];
+  LM_CUDA(cudaMemcpy(h, ctx->d_tl, sizeof(unsigned long long) * ctx->tl_n, cudaMemcpyDeviceToHost));
+  int off = 0;
+  for (int i = 0; i < ctx->tl_n; ++i) {
+    const char* f = ctx->tl_file[i]; const char* sl = strrchr(f, '/');
+    off += snprintf(buf + off, off < cap ? cap - off : 0, "%s:%d %llu\n", sl ? sl + 1 : f, ctx->tl_line[i], h[i]);
+    if (off >= cap) break;
+  }
+  return LMONO_OK;
+}
+
 extern "C" int lmono_kmarks_enable(lmono_ctx* ctx, int on) {
   if (!ctx) return LMONO_E_ARG;
   if (on && !ctx->kmark_ev) {

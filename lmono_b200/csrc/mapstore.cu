@@ -90,9 +90,11 @@ __device__ __forceinline__ void d_free_slot(const LmMapType& M, int ps) {
 // (:323-507), the valid list (:512-529) and the per-type offsets of the concatenation
 // (:533-539), all on device so consecutive sweeps need no host round trip.
 __global__ void __launch_bounds__(256) k_begin_step(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1,
-                                                    int32_t* __restrict__ slot_valid_rank, PoseArg odom,
+                                                    int32_t* __restrict__ slot_valid_rank, int32_t* __restrict__ plan, PoseArg odom,
                                                     int use_override, double ox, double oy, double oz) {
   __shared__ unsigned clear_mask[3];
+  __shared__ int s_dirty_n;
+  if (threadIdx.x == 0) s_dirty_n = 0;
   __shared__ int s_n[2][128];
   __shared__ int s_own[128];
   __shared__ int s_all, s_center[3], s_cen[3], s_shard[2];
@@ -180,9 +182,14 @@ __global__ void __launch_bounds__(256) k_begin_step(LmMapState* __restrict__ st,
     const int s0 = M0.slot_slab[ps], s1 = M1.slot_slab[ps];
     s_n[0][r] = s0 >= 0 ? M0.slab_n[s0] : 0;
     s_n[1][r] = s1 >= 0 ? M1.slab_n[s1] : 0;
+    // window cubes whose search index is stale (import, points that arrived while the cube was outside the window):
+    // the work list of k_index_build
+    if (s0 >= 0 && M0.slab_dirty[s0]) plan[LM_PLAN_DIRTY + atomicAdd(&s_dirty_n, 1)] = r;
+    if (s1 >= 0 && M1.slab_dirty[s1]) plan[LM_PLAN_DIRTY + atomicAdd(&s_dirty_n, 1)] = LM_WIN_MAX + r;
   }
   if (threadIdx.x == 0) st->valid_num = vn;
   __syncthreads();
+  if (threadIdx.x == 0) plan[LM_PLAN_DIRTY_N] = s_dirty_n;
   // exclusive prefix of the cube sizes per map type (the :533-537 concatenation offsets): warp ty scans 4 entries per lane
   const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
   if (ty < 2) {
@@ -216,7 +223,7 @@ int lm_map_begin_step(lmono_ctx* ctx, const lmono_pose* wodom_curr, const double
   PoseArg pa;
   if (wodom_curr) { for (int k = 0; k < 4; ++k) pa.q[k] = wodom_curr->q[k]; for (int k = 0; k < 3; ++k) pa.t[k] = wodom_curr->t[k]; }
   else { pa.q[0] = pa.q[1] = pa.q[2] = 0; pa.q[3] = 1; pa.t[0] = pa.t[1] = pa.t[2] = 0; }
-  k_begin_step<<<1, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_slot_valid_rank, pa,
+  k_begin_step<<<1, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_slot_valid_rank, ctx->d_rf_plan, pa,
                                            t_override ? 1 : (wodom_curr ? 0 : 2), t_override ? t_override[0] : 0.0,
                                            t_override ? t_override[1] : 0.0, t_override ? t_override[2] : 0.0);
   LM_LAUNCH_CHECK();
@@ -261,27 +268,29 @@ __device__ void d_build_cell_index(const LmMapType& M, int sid, const float4* __
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(1024, 1) k_index_build(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1) {
+constexpr int IDX_GRID = 32;
+__global__ void __launch_bounds__(1024, 1) k_index_build(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, const int32_t* __restrict__ plan) {
   extern __shared__ unsigned char smem_raw[];
   uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem_raw);
   int* ws = reinterpret_cast<int*>(s_cnt + LM_NCELL);
-  const int r = blockIdx.x;
-  if (r >= st->valid_num) return;
-  const LmMapType& M = blockIdx.y == 0 ? M0 : M1;
-  const int ps = st->valid_slot[r];
-  const int sid = M.slot_slab[ps];
-  if (sid < 0) return;
-  if (!M.slab_dirty[sid]) return;
-  const int n = M.slab_n[sid];
-  const float4* src = M.pts + ((size_t)sid * 2 + M.slab_cur[sid]) * M.cap;
-  d_build_cell_index(M, sid, src, n, s_cnt, ws, st);
-  if (threadIdx.x == 0) M.slab_dirty[sid] = 0;
+  const int nd = plan[LM_PLAN_DIRTY_N];
+  for (int w = blockIdx.x; w < nd; w += gridDim.x) {
+    const int e = plan[LM_PLAN_DIRTY + w];
+    const int ty = e / LM_WIN_MAX, r = e - ty * LM_WIN_MAX;
+    const LmMapType& M = ty == 0 ? M0 : M1;
+    const int sid = M.slot_slab[st->valid_slot[r]];
+    const int n = M.slab_n[sid];
+    const float4* src = M.pts + ((size_t)sid * 2 + M.slab_cur[sid]) * M.cap;
+    d_build_cell_index(M, sid, src, n, s_cnt, ws, st);
+    if (threadIdx.x == 0) M.slab_dirty[sid] = 0;
+    __syncthreads();
+  }
 }
 
 static const int kIndexSmem = LM_NCELL * 4 + 64 * 4;
 
 int lm_map_index_build(lmono_ctx* ctx) {
-  k_index_build<<<dim3(75, 2), 1024, kIndexSmem, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1]);
+  k_index_build<<<IDX_GRID, 1024, kIndexSmem, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan);
   LM_LAUNCH_CHECK();
   return LMONO_OK;
 }
@@ -397,7 +406,7 @@ __global__ void __launch_bounds__(256) k_insert_write(LmMapType M0, LmMapType M1
 // re-voxelise): such a slab is flagged and re-voxelised as a whole by k_refilter_whole on the next pass.
 struct RfMeta { int32_t active, total_new, ns, nt, flag, cur, sid, pad; };
 // chunk work list of the active cubes: entry = type << 24 | window rank << 16 | chunk; [0] of the counter array = length
-constexpr int RF_GRID = 592;
+static const int RF_GRID = getenv("LMONO_RF_GRID") ? atoi(getenv("LMONO_RF_GRID")) : 592;   // experiment switch
 
 __device__ __forceinline__ bool d_rf_slab(const LmMapState* st, const LmMapType& M, int r, int* sid) {
   if (r >= st->valid_num) return false;
@@ -406,67 +415,108 @@ __device__ __forceinline__ bool d_rf_slab(const LmMapState* st, const LmMapType&
   return s >= 0;
 }
 
+// per step: classify the window cubes once.  whole list = flagged slabs (re-voxelised as a whole), active list = slabs
+// with a tail (their meta record is armed here: ns, nt, cur, sid), tail-chunk list for k_rf_tailflags.  One CTA.
+__global__ void __launch_bounds__(256) k_rf_plan(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, int32_t* __restrict__ plan,
+                                                 RfMeta* __restrict__ meta_all, int32_t* __restrict__ tfwork, int32_t* __restrict__ work_n) {
+  __shared__ int ws[33];
+  const int e = threadIdx.x;
+  const int ty = e / LM_WIN_MAX, r = e - ty * LM_WIN_MAX;
+  int sid = -1, n = 0, ns = 0, cur = 0;
+  bool whole = false, active = false;
+  if (e < 2 * LM_WIN_MAX) {
+    const LmMapType& M = ty == 0 ? M0 : M1;
+    if (d_rf_slab(st, M, r, &sid)) {
+      n = M.slab_n[sid]; ns = M.slab_nsorted[sid]; cur = M.slab_cur[sid];
+      const bool uns = M.slab_unsorted[sid] != 0;
+      whole = uns && n > 0;
+      active = !uns && n - ns > 0;
+    }
+    RfMeta* meta = meta_all + e;
+    meta->active = active ? 1 : 0;
+    if (active) { meta->total_new = 0; meta->ns = ns; meta->nt = n - ns; meta->flag = 0; meta->cur = cur; meta->sid = sid; }
+  }
+  int tot;
+  const int wpos = d_block_exscan(whole ? 1 : 0, ws, &tot);
+  if (whole) plan[LM_PLAN_WHOLE + wpos] = e;
+  if (threadIdx.x == 0) plan[LM_PLAN_WHOLE_N] = tot;
+  const int apos = d_block_exscan(active ? 1 : 0, ws, &tot);
+  if (active) plan[LM_PLAN_ACTIVE + apos] = e;
+  if (threadIdx.x == 0) plan[LM_PLAN_ACTIVE_N] = tot;
+  const int ntf = active ? (n - ns + LM_RF_TF_CHUNK - 1) / LM_RF_TF_CHUNK : 0;
+  const int tbase = d_block_exscan(ntf, ws, &tot);
+  for (int c = 0; c < ntf; ++c) tfwork[tbase + c] = (e << 16) | c;
+  if (threadIdx.x == 0) { plan[LM_PLAN_TF_N] = tot; *work_n = 0; }
+}
+
 // tail element j opens a NEW voxel iff it is the first of its key run and the key is absent from the prefix:
 // one thread per tail element, so the (dependent, ~15-step) binary searches of a cube spread over many SMs
-__global__ void __launch_bounds__(256) k_rf_tailflags(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1,
-                                                      int32_t* __restrict__ nvx_all, int nvx_stride) {
-  const int r = blockIdx.x, ty = blockIdx.y;
-  const LmMapType& M = ty == 0 ? M0 : M1;
-  int sid;
-  if (!d_rf_slab(st, M, r, &sid)) return;
-  const int n = M.slab_n[sid], ns = M.slab_nsorted[sid], nt = n - ns;
-  if (nt == 0 || M.slab_unsorted[sid]) return;
-  const uint32_t* __restrict__ pkey = M.pkey + ((size_t)sid * 2 + M.slab_cur[sid]) * M.cap;
-  const uint32_t* __restrict__ tkey = pkey + ns;
-  for (int j = blockIdx.z * blockDim.x + threadIdx.x; j < nt; j += gridDim.z * blockDim.x) {
+constexpr int RF_TF_GRID = 296;
+__global__ void __launch_bounds__(LM_RF_TF_CHUNK) k_rf_tailflags(LmMapType M0, LmMapType M1, const int32_t* __restrict__ plan,
+                                                                 const RfMeta* __restrict__ meta_all, const int32_t* __restrict__ tfwork,
+                                                                 int32_t* __restrict__ nvx_all, int32_t* __restrict__ tlb_all, int nvx_stride) {
+  const int ntf = plan[LM_PLAN_TF_N];
+  for (int w = blockIdx.x; w < ntf; w += gridDim.x) {
+    const int we = tfwork[w];
+    const int e = we >> 16, ty = e / LM_WIN_MAX;
+    const LmMapType& M = ty == 0 ? M0 : M1;
+    const RfMeta* meta = meta_all + e;
+    const int ns = meta->ns, nt = meta->nt, sid = meta->sid;
+    const uint32_t* __restrict__ pkey = M.pkey + ((size_t)sid * 2 + meta->cur) * M.cap;
+    const uint32_t* __restrict__ tkey = pkey + ns;
+    const int j = (we & 0xFFFF) * LM_RF_TF_CHUNK + threadIdx.x;
+    if (j >= nt) continue;
     const uint32_t key = tkey[j];
     int nv = 0;
     if (j == 0 || tkey[j - 1] != key) {
-      const int lb = d_lower_bound_u32(pkey, ns, key);
+      const int lb = d_lower_bound_u32_wide(pkey, ns, key);
       nv = !(lb < ns && pkey[lb] == key);
+      tlb_all[(size_t)e * nvx_stride + j] = lb;          // k_rf_merge places a new voxel at lb + (new voxels before it)
     }
-    nvx_all[(size_t)(ty * LM_WIN_MAX + r) * nvx_stride + j] = nv;
+    nvx_all[(size_t)e * nvx_stride + j] = nv;
   }
 }
 
-// per cube: exclusive scan of the new-voxel flags -> output offsets; clears the cell histogram; arms the meta record
-__global__ void __launch_bounds__(1024, 1) k_rf_flags(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1,
-                                                      int32_t* __restrict__ nvx_all, RfMeta* __restrict__ meta_all, int nvx_stride,
-                                                      int32_t* __restrict__ work_n, int32_t* __restrict__ work) {
+// per cube with a tail: exclusive scan of the new-voxel flags -> output offsets; clears the cell histogram; appends the
+// cube's merge chunks to the work list
+constexpr int RF_ACT_GRID = 80;
+static_assert(LM_NCELL % 4 == 0, "vector clear of the cell histogram");
+__global__ void __launch_bounds__(256) k_rf_flags(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, const int32_t* __restrict__ plan,
+                                                  int32_t* __restrict__ nvx_all, RfMeta* __restrict__ meta_all, int nvx_stride,
+                                                  int32_t* __restrict__ work_n, int32_t* __restrict__ work) {
   __shared__ int ws[33];
   __shared__ int s_wbase;
-  const int r = blockIdx.x, ty = blockIdx.y;
-  const LmMapType& M = ty == 0 ? M0 : M1;
-  RfMeta* meta = meta_all + ty * LM_WIN_MAX + r;
-  int sid;
-  const bool have = d_rf_slab(st, M, r, &sid);
-  const int n = have ? M.slab_n[sid] : 0;
-  const int ns = have ? M.slab_nsorted[sid] : 0;
-  const int nt = n - ns;
-  if (!have || nt == 0 || M.slab_unsorted[sid]) { if (threadIdx.x == 0) meta->active = 0; return; }
-  const int cur = M.slab_cur[sid];
-  int32_t* __restrict__ nvx = nvx_all + (size_t)(ty * LM_WIN_MAX + r) * nvx_stride;
-  int32_t* cc = M.cellcount + (size_t)sid * LM_NCELL;
-  for (int c = threadIdx.x; c < LM_NCELL; c += blockDim.x) cc[c] = 0;
-  // chunked scan, coalesced: 1024 flags per round with a running carry
-  int carry = 0, total_new = 0;
-  for (int j0 = 0; j0 < nt; j0 += blockDim.x) {
-    const int j = j0 + threadIdx.x;
-    const int nv = j < nt ? nvx[j] : 0;
-    int tot;
-    const int ex = d_block_exscan(nv, ws, &tot);
-    if (j < nt) nvx[j] = ((carry + ex) << 1) | nv;
-    carry += tot;
+  const int na = plan[LM_PLAN_ACTIVE_N];
+  for (int a = blockIdx.x; a < na; a += gridDim.x) {
+    const int e = plan[LM_PLAN_ACTIVE + a];
+    const int ty = e / LM_WIN_MAX;
+    const LmMapType& M = ty == 0 ? M0 : M1;
+    RfMeta* meta = meta_all + e;
+    const int ns = meta->ns, nt = meta->nt, sid = meta->sid;
+    int32_t* __restrict__ nvx = nvx_all + (size_t)e * nvx_stride;
+    int4* cc4 = reinterpret_cast<int4*>(M.cellcount + (size_t)sid * LM_NCELL);       // LM_NCELL % 4 == 0, slabs 16 B aligned
+    for (int c = threadIdx.x; c < LM_NCELL / 4; c += blockDim.x) cc4[c] = make_int4(0, 0, 0, 0);
+    // chunked scan, coalesced: blockDim flags per round with a running carry
+    int carry = 0;
+    for (int j0 = 0; j0 < nt; j0 += blockDim.x) {
+      const int j = j0 + threadIdx.x;
+      const int nv = j < nt ? nvx[j] : 0;
+      int tot;
+      const int ex = d_block_exscan(nv, ws, &tot);
+      if (j < nt) nvx[j] = ((carry + ex) << 1) | nv;
+      carry += tot;
+    }
+    const int nch = (ns + nt + LM_RF_CHUNK - 1) / LM_RF_CHUNK;
+    if (threadIdx.x == 0) {
+      if (ns + carry > M.cap) atomicOr(&st->fault, LM_FAULT_CUBE_OVERFLOW);
+      meta->total_new = carry;
+      s_wbase = atomicAdd(work_n, nch);
+    }
+    __syncthreads();
+    const int r = e - ty * LM_WIN_MAX;
+    for (int c = threadIdx.x; c < nch; c += blockDim.x) work[s_wbase + c] = (ty << 24) | (r << 16) | c;
+    __syncthreads();
   }
-  total_new = carry;
-  if (threadIdx.x == 0) {
-    if (ns + total_new > M.cap) atomicOr(&st->fault, LM_FAULT_CUBE_OVERFLOW);
-    meta->active = 1; meta->total_new = total_new; meta->ns = ns; meta->nt = nt; meta->flag = 0; meta->cur = cur; meta->sid = sid;
-    s_wbase = atomicAdd(work_n, (ns + nt + LM_RF_CHUNK - 1) / LM_RF_CHUNK);
-  }
-  __syncthreads();
-  const int nch = (ns + nt + LM_RF_CHUNK - 1) / LM_RF_CHUNK;
-  for (int c = threadIdx.x; c < nch; c += blockDim.x) work[s_wbase + c] = (ty << 24) | (r << 16) | c;
 }
 
 __device__ __forceinline__ void d_rf_emit(const LmMapType& M, int sid, int cur, int pos, float4 p, uint32_t key, const int* g3, LmMapState* st) {
@@ -479,9 +529,11 @@ __device__ __forceinline__ void d_rf_emit(const LmMapType& M, int sid, int cur, 
   atomicAdd(&M.cellcount[(size_t)sid * LM_NCELL + c], 1);
 }
 
+constexpr int RF_STAGE = 2048;        // tail keys of a cube staged in shared memory by k_rf_merge (larger tails are searched in global memory)
 __global__ void __launch_bounds__(256) k_rf_merge(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1,
-                                                  const int32_t* __restrict__ nvx_all, RfMeta* __restrict__ meta_all, int nvx_stride,
+                                                  const int32_t* __restrict__ nvx_all, const int32_t* __restrict__ tlb_all, RfMeta* __restrict__ meta_all, int nvx_stride,
                                                   const int32_t* __restrict__ work_n, const int32_t* __restrict__ work) {
+ __shared__ uint32_t s_tkey[RF_STAGE];
  const int nwork = *work_n;
  for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
   const int we = work[w];
@@ -495,17 +547,31 @@ __global__ void __launch_bounds__(256) k_rf_merge(LmMapState* __restrict__ st, L
   const uint32_t* __restrict__ pkey = M.pkey + ((size_t)sid * 2 + cur) * M.cap;
   const uint32_t* __restrict__ tkey = pkey + ns;
   const int32_t* __restrict__ nvx = nvx_all + (size_t)(ty * LM_WIN_MAX + r) * nvx_stride;
+  const int32_t* __restrict__ tlb = tlb_all + (size_t)(ty * LM_WIN_MAX + r) * nvx_stride;
   const int g3[3] = { M.slab_g[sid * 4], M.slab_g[sid * 4 + 1], M.slab_g[sid * 4 + 2] };
   const float il = M.inv_leaf;
+  // a chunk of prefix points looks its keys up in the cube's tail: stage the (few hundred) tail keys once, search in
+  // shared memory -- the per-point binary search in global memory was a chain of ~10 dependent L2 / HBM round trips
+  const bool staged = e0 < ns && nt <= RF_STAGE;
+  __syncthreads();                      // the previous chunk's readers are done with s_tkey
+  if (staged) for (int j = threadIdx.x; j < nt; j += blockDim.x) s_tkey[j] = tkey[j];
+  __syncthreads();
   int bad = 0;
   for (int e = e0 + threadIdx.x; e < min(e0 + LM_RF_CHUNK, ns + nt); e += blockDim.x) {
     if (e < ns) {
       // prefix point: shifted by the number of new voxels sorting before it; merged if the tail hits its voxel
       const uint32_t key = pkey[e];
-      const int lb = d_lower_bound_u32(tkey, nt, key);
+      int lb; bool hit;
+      if (staged) {
+        int lo = 0, hi = nt;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_tkey[mid] < key) lo = mid + 1; else hi = mid; }
+        lb = lo; hit = lb < nt && s_tkey[lb] == key;
+      } else {
+        lb = d_lower_bound_u32(tkey, nt, key); hit = lb < nt && tkey[lb] == key;
+      }
       const int before = lb < nt ? (nvx[lb] >> 1) : total_new;
       float4 p = src[e];
-      if (lb < nt && tkey[lb] == key) {
+      if (hit) {
         float sx = p.x, sy = p.y, sz = p.z, si = p.w;
         int cnt = 1;
         for (int m = lb; m < nt && tkey[m] == key; ++m) {
@@ -533,65 +599,71 @@ __global__ void __launch_bounds__(256) k_rf_merge(LmMapState* __restrict__ st, L
       const float c = (float)cnt;
       const float4 p = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), __fdiv_rn(si, c));
       bad |= d_cube_voxel_key(p, il, g3) != key;
-      d_rf_emit(M, sid, cur, d_lower_bound_u32(pkey, ns, key) + (v >> 1), p, key, g3, st);
+      d_rf_emit(M, sid, cur, tlb[j] + (v >> 1), p, key, g3, st);     // tlb[j] = lower bound of the key in the prefix (k_rf_tailflags)
     }
   }
   if (bad) meta->flag = 1;
  }
 }
 
-__global__ void __launch_bounds__(1024, 1) k_rf_scan(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, RfMeta* __restrict__ meta_all) {
-  __shared__ int wtot[32], wbase[32];
-  const int r = blockIdx.x, ty = blockIdx.y;
-  RfMeta* meta = meta_all + ty * LM_WIN_MAX + r;
-  if (!meta->active) return;
-  const LmMapType& M = ty == 0 ? M0 : M1;
-  const int sid = meta->sid;
-  int32_t* cc = M.cellcount + (size_t)sid * LM_NCELL;
-  uint32_t* cs = M.cellstart + (size_t)sid * (LM_NCELL + 1);
-  // each warp owns a contiguous segment and walks it 32 cells at a time: coalesced loads, values kept in registers
-  constexpr int SEG = (LM_NCELL + 31) / 32;          // 550 cells per warp
-  constexpr int ITERS = (SEG + 31) / 32;             // 18
+constexpr int RF_SCAN_THREADS = 512;
+__global__ void __launch_bounds__(RF_SCAN_THREADS) k_rf_scan(LmMapType M0, LmMapType M1, const int32_t* __restrict__ plan, RfMeta* __restrict__ meta_all) {
+  constexpr int NW = RF_SCAN_THREADS / 32;
+  __shared__ int wtot[NW], wbase[NW];
+  const int na = plan[LM_PLAN_ACTIVE_N];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int seg0 = wid * SEG, seg1 = min(seg0 + SEG, LM_NCELL);
-  int vals[ITERS];
+  // each warp owns a contiguous segment of the 17576 cells and walks it 32 cells at a time: all loads of the segment
+  // are issued up front (values kept in registers), then scanned with a running carry
+  constexpr int SEG = (LM_NCELL + NW - 1) / NW;      // 1099 cells per warp
+  constexpr int ITERS = (SEG + 31) / 32;             // 35
+  for (int a = blockIdx.x; a < na; a += gridDim.x) {
+    const int e = plan[LM_PLAN_ACTIVE + a];
+    const LmMapType& M = e < LM_WIN_MAX ? M0 : M1;
+    RfMeta* meta = meta_all + e;
+    const int sid = meta->sid;
+    int32_t* cc = M.cellcount + (size_t)sid * LM_NCELL;
+    uint32_t* cs = M.cellstart + (size_t)sid * (LM_NCELL + 1);
+    const int seg0 = wid * SEG, seg1 = min(seg0 + SEG, LM_NCELL);
+    int vals[ITERS];
 #pragma unroll
-  for (int it = 0; it < ITERS; ++it) { const int c = seg0 + it * 32 + lane; vals[it] = c < seg1 ? cc[c] : 0; }
-  int carry = 0;
+    for (int it = 0; it < ITERS; ++it) { const int c = seg0 + it * 32 + lane; vals[it] = c < seg1 ? cc[c] : 0; }
+    int carry = 0;
 #pragma unroll
-  for (int it = 0; it < ITERS; ++it) {
-    int incl = vals[it];
+    for (int it = 0; it < ITERS; ++it) {
+      int incl = vals[it];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    const int tot = __shfl_sync(0xffffffffu, incl, 31);
-    vals[it] = carry + incl - vals[it];               // exclusive within the warp segment
-    carry += tot;
-  }
-  if (lane == 0) wtot[wid] = carry;
-  __syncthreads();
-  if (wid == 0) {
-    const int v = wtot[lane];
-    int incl = v;
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      const int tot = __shfl_sync(0xffffffffu, incl, 31);
+      vals[it] = carry + incl - vals[it];               // exclusive within the warp segment
+      carry += tot;
+    }
+    if (lane == 0) wtot[wid] = carry;
+    __syncthreads();
+    if (wid == 0) {
+      const int v = lane < NW ? wtot[lane] : 0;
+      int incl = v;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    wbase[lane] = incl - v;
-  }
-  __syncthreads();
-  const int base = wbase[wid];
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      if (lane < NW) wbase[lane] = incl - v;
+    }
+    __syncthreads();
+    const int base = wbase[wid];
 #pragma unroll
-  for (int it = 0; it < ITERS; ++it) {
-    const int c = seg0 + it * 32 + lane;
-    if (c < seg1) { const int v = base + vals[it]; cs[c] = (uint32_t)v; cc[c] = v; }
-  }
-  if (threadIdx.x == 0) {
-    const int nn = min(meta->ns + meta->total_new, M.cap);
-    cs[LM_NCELL] = (uint32_t)nn;
-    M.slab_n[sid] = nn;
-    M.slab_nsorted[sid] = meta->flag ? 0 : nn;
-    M.slab_unsorted[sid] = meta->flag ? 1 : 0;
-    M.slab_cur[sid] = meta->cur ^ 1;
-    M.slab_dirty[sid] = 0;
-    meta->total_new = nn;         // k_rf_scatter reads the new size here
+    for (int it = 0; it < ITERS; ++it) {
+      const int c = seg0 + it * 32 + lane;
+      if (c < seg1) { const int v = base + vals[it]; cs[c] = (uint32_t)v; cc[c] = v; }
+    }
+    if (threadIdx.x == 0) {
+      const int nn = min(meta->ns + meta->total_new, M.cap);
+      cs[LM_NCELL] = (uint32_t)nn;
+      M.slab_n[sid] = nn;
+      M.slab_nsorted[sid] = meta->flag ? 0 : nn;
+      M.slab_unsorted[sid] = meta->flag ? 1 : 0;
+      M.slab_cur[sid] = meta->cur ^ 1;
+      M.slab_dirty[sid] = 0;
+      meta->total_new = nn;         // k_rf_scatter reads the new size here
+    }
+    __syncthreads();
   }
 }
 
@@ -623,21 +695,24 @@ __global__ void __launch_bounds__(256) k_rf_scatter(LmMapType M0, LmMapType M1, 
 
 // Whole-slab re-voxelisation of a flagged slab (rare): one CTA per window cube and map type sorts every
 // point of the slab by voxel key in shared memory and merges runs -- exactly pcl::VoxelGrid on the cube.
-__global__ void __launch_bounds__(1024, 1) k_refilter_whole(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, int32_t* __restrict__ work_n) {
+constexpr int RF_WHOLE_GRID = 8;
+__global__ void __launch_bounds__(1024, 1) k_refilter_whole(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, const int32_t* __restrict__ plan) {
   extern __shared__ unsigned char smem_raw[];
   unsigned long long* S = reinterpret_cast<unsigned long long*>(smem_raw);              // [LM_TAIL_TILE]
   int* NV = reinterpret_cast<int*>(smem_raw + (size_t)LM_TAIL_TILE * 8);                // [LM_TAIL_TILE]
   int* ws = reinterpret_cast<int*>(smem_raw + (size_t)LM_TAIL_TILE * 12);               // [64]
   __shared__ int s_flag;
-  const int r = blockIdx.x;
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *work_n = 0;      // first kernel of the refilter phase
-  const LmMapType& M = blockIdx.y == 0 ? M0 : M1;
+  const int nw = plan[LM_PLAN_WHOLE_N];
+  for (int w = blockIdx.x; w < nw; w += gridDim.x) {
+  const int e_ = plan[LM_PLAN_WHOLE + w];
+  const LmMapType& M = e_ < LM_WIN_MAX ? M0 : M1;
+  const int r = e_ < LM_WIN_MAX ? e_ : e_ - LM_WIN_MAX;
   int sid;
-  if (!d_rf_slab(st, M, r, &sid)) return;
-  if (!M.slab_unsorted[sid]) return;
+  if (!d_rf_slab(st, M, r, &sid)) continue;
+  if (!M.slab_unsorted[sid]) continue;
   const int nt = M.slab_n[sid];
-  if (nt == 0) return;
-  if (nt > LM_TAIL_TILE) { if (threadIdx.x == 0) atomicOr(&st->fault, LM_FAULT_TAIL_OVERFLOW); return; }
+  if (nt == 0) continue;
+  if (nt > LM_TAIL_TILE) { if (threadIdx.x == 0) atomicOr(&st->fault, LM_FAULT_TAIL_OVERFLOW); continue; }
   const int cur = M.slab_cur[sid];
   const float4* src = M.pts + ((size_t)sid * 2 + cur) * M.cap;
   float4* dst = M.pts + ((size_t)sid * 2 + (cur ^ 1)) * M.cap;
@@ -688,6 +763,8 @@ __global__ void __launch_bounds__(1024, 1) k_refilter_whole(LmMapState* __restri
   // rebuild the search index of this cube from the new buffer (reuses the sort scratch)
   d_build_cell_index(M, sid, dst, total_new, reinterpret_cast<uint32_t*>(smem_raw), ws, st);
   if (threadIdx.x == 0) M.slab_dirty[sid] = 0;
+  __syncthreads();
+  }
 }
 
 static const int kRefilterSmem = LM_TAIL_TILE * 12 + 64 * 4;
@@ -717,15 +794,17 @@ int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf)
   const int cap_max = ctx->map[0].cap > ctx->map[1].cap ? ctx->map[0].cap : ctx->map[1].cap;
   RfMeta* meta = (RfMeta*)ctx->d_rf_meta;
   int32_t* work_n = ctx->d_rf_work; int32_t* work = ctx->d_rf_work + 4;
-  k_refilter_whole<<<dim3(LM_WIN_MAX, 2), 1024, kRefilterSmem, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], work_n);
+  k_rf_plan<<<1, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan, meta, ctx->d_rf_tf, work_n);
   LM_LAUNCH_CHECK();
-  k_rf_tailflags<<<dim3(LM_WIN_MAX, 2, 8), 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_nvx, cap_max);
+  k_refilter_whole<<<RF_WHOLE_GRID, 1024, kRefilterSmem, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan);
   LM_LAUNCH_CHECK();
-  k_rf_flags<<<dim3(LM_WIN_MAX, 2), 1024, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_nvx, meta, cap_max, work_n, work);
+  k_rf_tailflags<<<RF_TF_GRID, LM_RF_TF_CHUNK, 0, ctx->stream>>>(ctx->map[0], ctx->map[1], ctx->d_rf_plan, meta, ctx->d_rf_tf, ctx->d_rf_nvx, ctx->d_rf_tlb, cap_max);
   LM_LAUNCH_CHECK();
-  k_rf_merge<<<RF_GRID, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_nvx, meta, cap_max, work_n, work);
+  k_rf_flags<<<RF_ACT_GRID, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan, ctx->d_rf_nvx, meta, cap_max, work_n, work);
   LM_LAUNCH_CHECK();
-  k_rf_scan<<<dim3(LM_WIN_MAX, 2), 1024, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], meta);
+  k_rf_merge<<<RF_GRID, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_nvx, ctx->d_rf_tlb, meta, cap_max, work_n, work);
+  LM_LAUNCH_CHECK();
+  k_rf_scan<<<RF_ACT_GRID, RF_SCAN_THREADS, 0, ctx->stream>>>(ctx->map[0], ctx->map[1], ctx->d_rf_plan, meta);
   LM_LAUNCH_CHECK();
   k_rf_scatter<<<RF_GRID, 256, 0, ctx->stream>>>(ctx->map[0], ctx->map[1], meta, work_n, work);
   LM_LAUNCH_CHECK();
@@ -738,9 +817,13 @@ int lm_map_configure_kernels(lmono_ctx* ctx) {
   LM_CUDA(cudaFuncSetAttribute(k_refilter_whole, cudaFuncAttributeMaxDynamicSharedMemorySize, kRefilterSmem));
   const int cap_max = ctx->map[0].cap > ctx->map[1].cap ? ctx->map[0].cap : ctx->map[1].cap;
   LM_CUDA(cudaMalloc((void**)&ctx->d_rf_nvx, sizeof(int32_t) * (size_t)2 * LM_WIN_MAX * cap_max));
+  LM_CUDA(cudaMalloc((void**)&ctx->d_rf_tlb, sizeof(int32_t) * (size_t)2 * LM_WIN_MAX * cap_max));
   LM_CUDA(cudaMalloc((void**)&ctx->d_rf_meta, sizeof(RfMeta) * 2 * LM_WIN_MAX));
   LM_CUDA(cudaMalloc((void**)&ctx->d_rf_work, sizeof(int32_t) * (4 + (size_t)2 * LM_WIN_MAX * (lm_div_up(cap_max, LM_RF_CHUNK) + 1))));
   LM_CUDA(cudaMemsetAsync(ctx->d_rf_meta, 0, sizeof(RfMeta) * 2 * LM_WIN_MAX, ctx->stream));
+  LM_CUDA(cudaMalloc((void**)&ctx->d_rf_plan, sizeof(int32_t) * LM_PLAN_INTS));
+  LM_CUDA(cudaMemsetAsync(ctx->d_rf_plan, 0, sizeof(int32_t) * LM_PLAN_INTS, ctx->stream));
+  LM_CUDA(cudaMalloc((void**)&ctx->d_rf_tf, sizeof(int32_t) * (size_t)2 * LM_WIN_MAX * (lm_div_up(cap_max, LM_RF_TF_CHUNK) + 1)));
   return LMONO_OK;
 }
 
