@@ -655,7 +655,10 @@ __global__ void __launch_bounds__(128) k_assoc_fit(const LmMapState* __restrict_
 int lm_map_associate(lmono_ctx* ctx, int n_max_corner, int n_max_surf) {
   const int nq = n_max_corner + n_max_surf;
   if (nq <= 0) return LMONO_OK;
-  static const int group = getenv("LMONO_KNN_GROUP") ? atoi(getenv("LMONO_KNN_GROUP")) : GROUP_DEFAULT;     // experiment switch
+  // latency form (8 lanes per query) for a sequence alone on the GPU, throughput form (one thread per query, a third of
+  // the instructions) when the step is one of several running side by side; LMONO_KNN_GROUP overrides (0 = thread form)
+  static const int group_env = getenv("LMONO_KNN_GROUP") ? atoi(getenv("LMONO_KNN_GROUP")) : -1;
+  const int group = group_env >= 0 ? group_env : (ctx->batch_n >= LM_THROUGHPUT_BATCH ? 0 : GROUP_DEFAULT);
 #define KNN_ARGS ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_slot_valid_rank, ctx->d_stack[0], ctx->d_stack[1], ctx->d_nnref
   if (group == 0) k_assoc_knn1<<<lm_div_up(nq, KNN1_THREADS), KNN1_THREADS, 0, ctx->stream>>>(KNN_ARGS);
   else if (group == 1) k_assoc_knn<1><<<lm_div_up(nq * 1, 256), 256, 0, ctx->stream>>>(KNN_ARGS);

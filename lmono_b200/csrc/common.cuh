@@ -142,7 +142,7 @@ constexpr int LM_PROF_MAX_EVENTS = 2048;
 // ---------------------------------------------------------------- host ctx
 // One captured CUDA graph per launch-grid capacity bucket of a laserMapping step (inputs are read through
 // LmMapState::in_ptr, so the graph does not depend on the caller's buffers).
-struct LmGraphEntry { int nc_cap, ns_cap; cudaGraphExec_t exec; int n_launch; };
+struct LmGraphEntry { int nc_cap, ns_cap; bool throughput; cudaGraphExec_t exec; int n_launch; };
 constexpr int LM_MAX_GRAPHS = 64;
 // Sequence batches: ONE graph holds the steps of all n sequences as parallel branches (fork / join inside the
 // graph), so a batch step costs the host one small argument launch + one cudaGraphLaunch.  Cached in ctxs[0].
@@ -152,6 +152,7 @@ struct LmBatchGraph { int n; lmono_ctx* ctxs[LM_BATCH_MAX]; int nc_cap[LM_BATCH_
 constexpr int LM_GRAPH_BUCKET = 2048;     // launch grids are sized for counts rounded up to this
 
 constexpr int LM_TL_MAX = 64;
+constexpr int LM_THROUGHPUT_BATCH = 4;
 struct lmono_ctx {
   int device;
   lmono_params prm;
@@ -167,6 +168,8 @@ struct lmono_ctx {
   cudaStream_t* cap_streams;    // (batch leader) [LM_BATCH_MAX] branch streams, used only while capturing a batch graph
   LmBatchGraph* bgraphs; int n_bgraphs;      // (batch leader) [LM_MAX_BGRAPHS]
   bool step_timed;              // ev0 / ev1 bracket the pending step (false for steps that ran inside a batch graph)
+  int batch_n;                  // sequences sharing the GPU in the step being enqueued (1 = alone): >= LM_THROUGHPUT_BATCH picks the
+                                // throughput forms of the kernels (one-thread-per-query kNN, 8-CTA LM clusters) over the latency forms
 
   LmMapType map[2];
   LmMapState* d_state;

@@ -471,45 +471,56 @@ k_lm_solve_cluster(LmLmState* __restrict__ lm_g, LmProblem P, int max_iter, int 
     const double* xe = s_lm.phase == 0 ? s_lm.x : s_lm.cand;
     const double q[4] = { xe[0], xe[1], xe[2], xe[3] };
     const double t[3] = { xe[4], xe[5], xe[6] };
+    // The factors are dealt to LMC_CLUSTER x LMC_THREADS VIRTUAL threads whatever the real cluster size is: a CTA of a
+    // smaller cluster evaluates its LMC_CLUSTER / csize virtual CTAs one after the other (own accumulators, own block
+    // reduction, own slice of the factor cache).  The 30-vector is therefore summed in exactly the same order for every
+    // cluster size, and a solve gives the same bits alone on the GPU (16 CTAs) and inside a batch (8 CTAs).
+    const int nvirt = LMC_CLUSTER / csize;
+    const int vcache = LMC_CACHE / nvirt;
+    for (int v = 0; v < nvirt; ++v) {
+    const int vrank = crank + v * csize;
     double acc[32];
 #pragma unroll
     for (int k = 0; k < 32; ++k) acc[k] = 0.0;
-    {   // grid-stride over the cluster.  The first evaluation streams the factors from global memory (next
+    {   // stride over the virtual cluster.  The first evaluation streams the factors from global memory (next
         // factor's 64 B in flight while the current one is evaluated) and parks them in shared memory; the
         // other evaluations of the solve re-read them from there instead of paying L2 latency per factor.
-      const int stride = csize * LMC_THREADS, nf = n0 + n1;
-      int i = crank * LMC_THREADS + threadIdx.x;
+      const int stride = LMC_CLUSTER * LMC_THREADS, nf = n0 + n1;
+      int i = vrank * LMC_THREADS + threadIdx.x;
       int slot = threadIdx.x;
+      const int sbase = v * vcache;
       LmFactor f;
       const bool first = (it == 0);
-      if (i < nf) { if (first || slot >= LMC_CACHE) f = i < n0 ? fac0[i] : fac1[i - n0]; else f = d_cache_load(s_cache, slot); }
+      if (i < nf) { if (first || slot >= vcache) f = i < n0 ? fac0[i] : fac1[i - n0]; else f = d_cache_load(s_cache, sbase + slot); }
       while (i < nf) {
         const int inext = i + stride, snext = slot + LMC_THREADS;
         LmFactor fn;
-        if (inext < nf) { if (first || snext >= LMC_CACHE) fn = inext < n0 ? fac0[inext] : fac1[inext - n0]; else fn = d_cache_load(s_cache, snext); }
-        if (first && slot < LMC_CACHE) d_cache_store(s_cache, slot, f);
+        if (inext < nf) { if (first || snext >= vcache) fn = inext < n0 ? fac0[inext] : fac1[inext - n0]; else fn = d_cache_load(s_cache, sbase + snext); }
+        if (first && slot < vcache) d_cache_store(s_cache, sbase + slot, f);
         if (f.kind >= 0) { if (i < n0) acc[28] += 1.0; else acc[29] += 1.0; }
         d_eval_factor(f, q, t, acc);
         f = fn; i = inext; slot = snext;
       }
     }
-    LM_STAMP(stamps, 8 + 8 * it);
+    if (v == nvirt - 1) LM_STAMP(stamps, 8 + 8 * it);
     d_warp_transpose_reduce32(acc, lane);
     s_part[wid][lane] = acc[0];
     __syncthreads();
     if (threadIdx.x < 32) {
-      double v = 0.0;
+      double sum = 0.0;
 #pragma unroll
-      for (int w = 0; w < LMC_THREADS / 32; ++w) v += s_part[w][threadIdx.x];
-      double* mine = &s_all[it & 1][crank][threadIdx.x];
-      for (int r = 0; r < csize; ++r) *cluster.map_shared_rank(mine, r) = v;
+      for (int w = 0; w < LMC_THREADS / 32; ++w) sum += s_part[w][threadIdx.x];
+      double* mine = &s_all[it & 1][vrank][threadIdx.x];
+      for (int r = 0; r < csize; ++r) *cluster.map_shared_rank(mine, r) = sum;
+    }
+    __syncthreads();            // s_part is reused by the next virtual CTA
     }
     LM_STAMP(stamps, 9 + 8 * it);
     cluster.sync();
     LM_STAMP(stamps, 10 + 8 * it);
     if (threadIdx.x < 32) {
       double v = 0.0;
-      for (int r = 0; r < csize; ++r) v += s_all[it & 1][r][threadIdx.x];     // fixed order
+      for (int r = 0; r < LMC_CLUSTER; ++r) v += s_all[it & 1][r][threadIdx.x];     // fixed order over the virtual CTAs
       s_fin[threadIdx.x] = v;
     }
     __syncthreads();
@@ -568,10 +579,19 @@ static int lm_cluster_size(lmono_ctx* ctx) {
     if (cudaOccupancyMaxActiveClusters(&n, k_lm_solve_cluster, &cfg) == cudaSuccess && n >= 1) best = LMC_CLUSTER;
   }
   cudaGetLastError();
-  const char* e = getenv("LMONO_LM_CLUSTER");
-  if (e && atoi(e) >= 1 && atoi(e) <= best) best = atoi(e);
   cached[d] = best;
   return best;
+}
+// 16 CTAs minimise the latency of one solve; with several sequences side by side 8-CTA clusters leave room for the
+// other sequences' solves (each CTA holds a whole SM's register file).  LMONO_LM_CLUSTER overrides.
+static int lm_cluster_pick(lmono_ctx* ctx) {
+  const int best = lm_cluster_size(ctx);
+  if (best < 0) return best;
+  static const int env = getenv("LMONO_LM_CLUSTER") ? atoi(getenv("LMONO_LM_CLUSTER")) : 0;
+  int want = env >= 1 ? env : (ctx->batch_n >= LM_THROUGHPUT_BATCH ? 8 : best);
+  want = want < best ? want : best;
+  int p2 = 1; while (p2 * 2 <= want) p2 *= 2;      // the virtual-CTA scheme needs a divisor of LMC_CLUSTER
+  return p2;
 }
 
 static int eval_blocks(lmono_ctx* ctx, int n) {
@@ -583,7 +603,7 @@ static int eval_blocks(lmono_ctx* ctx, int n) {
 
 int lm_solve_problem(lmono_ctx* ctx, const LmProblem& P, int n_max, int max_iter, int write_back) {
   if (!lm_use_launch_per_eval()) {
-    const int cs = lm_cluster_size(ctx);
+    const int cs = lm_cluster_pick(ctx);
     if (cs < 0) return LMONO_E_CUDA;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(cs); cfg.blockDim = dim3(LMC_THREADS); cfg.dynamicSmemBytes = LMC_SMEM; cfg.stream = ctx->stream;

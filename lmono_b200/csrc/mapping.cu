@@ -191,7 +191,7 @@ static int enqueue_step(lmono_ctx* ctx, const LmStepIn& in, const lmono_pose* wo
     LmGraphEntry* g = nullptr;
     for (int i = 0; i < ctx->n_graphs; ++i) {
       LmGraphEntry& e = ctx->graphs[i];
-      if (e.nc_cap == nc_cap && e.ns_cap == ns_cap) { g = &e; break; }
+      if (e.nc_cap == nc_cap && e.ns_cap == ns_cap && e.throughput == (ctx->batch_n >= LM_THROUGHPUT_BATCH)) { g = &e; break; }
     }
     if (!g) {
       if (ctx->n_graphs == LM_MAX_GRAPHS) {      // cache full: drop everything
@@ -206,7 +206,7 @@ static int enqueue_step(lmono_ctx* ctx, const LmStepIn& in, const lmono_pose* wo
       if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
       LM_CUDA(ce);
       g = &ctx->graphs[ctx->n_graphs];
-      g->nc_cap = nc_cap; g->ns_cap = ns_cap;
+      g->nc_cap = nc_cap; g->ns_cap = ns_cap; g->throughput = ctx->batch_n >= LM_THROUGHPUT_BATCH;
       g->n_launch = (int)(ctx->launches - l0);
       ctx->launches = l0;
       ce = cudaGraphInstantiate(&g->exec, graph, 0);
@@ -432,6 +432,7 @@ static int batch_capture(lmono_ctx* lead, lmono_ctx* const* ctxs, int n, const i
     cudaStream_t saved = c->stream;
     const int64_t l0 = c->launches;
     c->stream = lead->cap_streams[i];
+    c->batch_n = n;
     ce = cudaStreamWaitEvent(c->stream, lead->ev_fork, 0);
     if (ce == cudaSuccess) rc = enqueue_body(c, nc_cap[i], ns_cap[i]);
     if (!rc && ce == cudaSuccess) rc = publish_state(c);
@@ -440,6 +441,7 @@ static int batch_capture(lmono_ctx* lead, lmono_ctx* const* ctxs, int n, const i
     g->n_launch[i] = (int)(c->launches - l0);
     c->launches = l0;
     c->stream = saved;
+    c->batch_n = 1;
   }
   cudaError_t ce2 = cudaStreamEndCapture(origin, &graph);
   if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -546,7 +548,10 @@ static int batch_enqueue_plain(lmono_ctx* const* ctxs, int n, const LmStepIn* in
     if (js && ctx->stream != js) LM_CUDA(cudaStreamWaitEvent(ctx->stream, ctxs[0]->ev_fork, 0));
     int rc;
     const int slot = (int)(ctx->n_submitted & 1u);
-    if ((rc = enqueue_step(ctx, in[i], &wodom_curr[i], wmap_in ? &wmap_in[i] : nullptr, slot))) return rc;
+    ctx->batch_n = n;
+    rc = enqueue_step(ctx, in[i], &wodom_curr[i], wmap_in ? &wmap_in[i] : nullptr, slot);
+    ctx->batch_n = 1;
+    if (rc) return rc;
     if ((rc = publish_state(ctx))) return rc;
     LM_CUDA(cudaEventRecord(ctx->ev_res[slot], ctx->stream));
     ctx->n_submitted++;
