@@ -322,6 +322,45 @@ def run_ours(args):
     e2e_sync_ms = allmax((time.perf_counter() - t0) * 1e3)
     e2e_sync_value = world * S * args.steps / (e2e_sync_ms * 1e-3)
 
+    # ---- the same value leg with twice the sequences per GPU (how far the GPU is from saturated at S)
+    more = None
+    if args.more_sequences > S:
+        S2 = args.more_sequences
+        ctxs2 = list(ctxs)
+        for s_ in range(S, S2):
+            c_ = api.Context(device=local, stream=main.cuda_stream)
+            c_.map_import(0, cm)
+            c_.map_import(1, sm)
+            c_.sync()
+            ctxs2.append(c_)
+        batch2 = api.SequenceBatch(ctxs2)
+        bargs2 = []
+        for i in range(nsw):
+            ks = [sweep_of(i, s_) for s_ in range(S2)]
+            a_ = api.BatchArgs(S2)
+            a_.set_odom([(sweeps[k][4], sweeps[k][5]) for k in ks]).set_wmap_in([ident] * S2)
+            a_.set_device_inputs([d_sweeps[k][0].data_ptr() for k in ks], [d_sweeps[k][0].shape[0] for k in ks],
+                                 [d_sweeps[k][1].data_ptr() for k in ks], [d_sweeps[k][1].shape[0] for k in ks])
+            bargs2.append(a_)
+        for i in range(W):
+            batch2.step_device(join_stream=main.cuda_stream, args=bargs2[i % nsw])
+        batch2.collect()
+        barrier()
+        m0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        m1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        for i in range(args.steps):
+            flush.fill_(i & 0xFF)
+            m0[i].record(main)
+            batch2.step_device(join_stream=main.cuda_stream, args=bargs2[(W + i) % nsw])
+            m1[i].record(main)
+        barrier()
+        batch2.collect()
+        ms2 = allmax(float(sum(a.elapsed_time(b) for a, b in zip(m0, m1))))
+        more = {"sequences_per_gpu": S2, "value": world * S2 * args.steps / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / args.steps,
+                "note": "same measurement as `value` with more independent sequences per GPU"}
+        for c_ in ctxs2[S:]:
+            c_.close()
+
     # ---- single sequence alone on the GPU (latency of one registration; the round-1 headline): device-resident inputs,
     # CUDA events per step, L2 flushed between steps
     def step_single(i):
@@ -354,23 +393,34 @@ def run_ours(args):
     # order and cache state as the timed leg: L2 flushed before each step); a GPU-side sleep in front of each step lets
     # the host enqueue the whole step before the device starts it, so the deltas are device durations, not launch latency
     nprof = min(args.steps, 24)
-    ctx.kernel_marks_enable(True)
-    for i in range(nprof):
-        flush.fill_(1)
-        torch.cuda._sleep(4_000_000)
-        step_single(W + i)
-    marks = ctx.kernel_marks()
-    ctx.kernel_marks_enable(False)
+
+    def marks_leg():
+        ctx.kernel_marks_enable(True)
+        for i in range(nprof):
+            flush.fill_(1)
+            torch.cuda._sleep(4_000_000)
+            step_single(W + i)
+        m_ = ctx.kernel_marks()
+        ctx.kernel_marks_enable(False)
+        m_.pop("k_set_wmap", None)          # first mark of a step: its delta contains the flush + sleep
+        return m_
+
+    marks = marks_leg()                      # latency forms (a sequence alone on the GPU)
+    ctx.set_concurrency_hint(max(S, 4))      # throughput forms, as the batched legs above ran them
+    marks_tp = marks_leg()
+    ctx.set_concurrency_hint(1)
     q_last, t_last, rep = ctx.map_collect()
-    marks.pop("k_set_wmap", None)          # first mark of a step: its delta contains the flush + sleep
     kern_us = {k: 1e3 * v[1] / nprof for k, v in marks.items()}                    # us per step
+    kern_us_tp = {k: 1e3 * v[1] / nprof for k, v in marks_tp.items()}
     kern_launch_ms = {k: v[1] / max(v[0], 1) for k, v in marks.items()}            # ms per launch
+    for k, v in marks_tp.items():
+        kern_launch_ms.setdefault(k, v[1] / max(v[0], 1))                          # kernels only the throughput form launches
     nq = rep.corner_stack + rep.surf_stack
     nmap = rep.corner_from_map + rep.surf_from_map
     nfac = rep.corner_num[1] + rep.surf_num[1]
     evals = sum(s_.iterations + 1 for s_ in rep.solve)
     ncu = {}
-    ncu_file = "ncu_r01_full_metrics.json"
+    ncu_file = "ncu_r01_h_full_metrics.json"
     try:
         for l in json.load(open(os.path.join(ROOT, "profiles", ncu_file)))["launches"]:
             ncu.setdefault(l["kernel"], []).append(l)
@@ -395,22 +445,29 @@ def run_ours(args):
               roof("k_sort_tiles", 16.0 * nraw, "register bitonic tile sort: 8 B key read + write"),
               roof("k_merge_ranks_smem", 16.0 * nraw, "rank merge of the sorted tiles in shared memory"),
               roof("k_vg_write", 8.0 * nraw + 16.0 * nraw + 16.0 * nq, "VoxelGrid centroids of both feature clouds")]
-    knn = roof("k_assoc_knn", 116.0 * nq, "exact 5-NN: 16 B query + 5 x 16 B neighbours + 5 x 4 B indices per query (SURVEY 8d)") or {}
+    knn8 = roof("k_assoc_knn", 116.0 * nq, "latency form of the exact 5-NN (8 lanes per query), used when a sequence runs alone on the GPU")
+    if knn8:
+        others.insert(0, knn8)
+    knn = roof("k_assoc_knn1", 116.0 * nq, "exact 5-NN: 16 B query + 5 x 16 B neighbours + 5 x 4 B indices per query (SURVEY 8d)") or {}
     roofline = {
-        "bound": "hbm", "kernel": "k_assoc_knn (exact 5-NN of every feature against the cube map, one launch per outer iteration)",
+        "bound": "hbm", "kernel": "k_assoc_knn1 (exact 5-NN of every feature against the cube map, throughput form = the one the batched step runs; one launch per outer iteration)",
         "achieved": knn.get("achieved"), "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
         "frac": knn.get("frac"), "traffic": knn.get("traffic"),
         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture committed as profiles/" + ncu_file + " (cold caches per ncu replay)",
         "algorithmic_bytes_per_launch": knn.get("algorithmic_bytes_per_launch"), "avg_launch_ms": knn.get("avg_launch_ms"),
         "timing": "one sequence alone on the GPU, un-graphed step, CUDA event after every launch",
         "queries_per_launch": int(nq), "knn_queries_per_s": nq / (knn["avg_launch_ms"] * 1e-3) if knn.get("avg_launch_ms") else None,
+        "knn_queries_per_s_batched": 2.0 * nq * value,
         "l2_hit_pct_ncu": knn.get("l2_hit_pct_ncu"),
         "kernel_us_per_step": {k: round(v, 2) for k, v in sorted(kern_us.items(), key=lambda kv: -kv[1])},
-        "kernel_us_note": "CUDA-event deltas between consecutive launches of the un-graphed step: each includes ~3 us of event + launch gap, "
-                          "so the sum exceeds ms_per_step (graph replay); profiles/ holds the ncu launch list of the same command",
+        "kernel_us_per_step_throughput_forms": {k: round(v, 2) for k, v in sorted(kern_us_tp.items(), key=lambda kv: -kv[1])},
+        "kernel_us_note": "CUDA-event deltas between consecutive launches of the un-graphed step of ONE sequence: each includes ~3 us of event + launch gap, "
+                          "so the sum exceeds ms_per_step (graph replay); profiles/ holds the ncu launch list of the same command and the "
+                          "timeline of the batched step (profiles/batch_timeline_r01.txt)",
         "other_kernels": [r for r in others if r],
         "note": "the map (~16 MB + 16 MB index) fits the 126 MB L2 and one registration moves ~30-60 MB algorithmically (5-10 us of HBM time): "
-                "the step is bound by dependent L2 gathers, fp64 latency and ~26 launches, not by HBM bandwidth (DESIGN.md section 4)",
+                "the step is bound by dependent L2 / HBM round trips, fp64 latency and ~27 launches, not by HBM bandwidth (DESIGN.md section 4); "
+                "whole-GPU counters of the batched step: profiles/batch_range_r01.csv",
     }
 
     line = {
@@ -428,6 +485,7 @@ def run_ours(args):
         "single_sequence": {"value": 1e3 / single_ms * world, "unit": UNIT, "ms_per_registration": single_ms,
                             "e2e_value": 1e3 / single_e2e_ms * world, "e2e_ms_per_registration": single_e2e_ms,
                             "note": "one sequence alone on each GPU: latency of one registration (graph replay, L2 flushed between steps)"},
+        "more_sequences": more,
         "host_enqueue_ms_per_step": 1e3 * host_enqueue_s / args.steps,
         "gpu_launches": int(n_launch),
         "clocks": clocks,
@@ -464,6 +522,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sequences", type=int, default=8, help="independent sequences per GPU (one ctx + stream each)")
+    ap.add_argument("--more-sequences", type=int, default=16, help="extra value leg with this many sequences per GPU (0 = skip)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-steps", type=int, default=60)
     args = ap.parse_args()

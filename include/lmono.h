@@ -256,6 +256,11 @@ int lmono_voxel_grid(lmono_ctx* ctx, lmono_cloud_view in, float leaf, lmono_clou
  * event (the step then runs as plain launches, not as a graph replay).  lmono_kmarks_dump writes one line
  * "source.cu:line count total_ms" per launch site; bench.py --kernels maps the sites to kernel names. */
 int lmono_kmarks_enable(lmono_ctx* ctx, int on);
+/* Kernel forms.  A step that runs alone on the GPU uses the latency forms of the kernels (8 lanes per kNN query, 16-CTA
+ * LM clusters); steps of >= 4 sequences enqueued together (lmono_map_*_batch) use the throughput forms (one thread per
+ * kNN query, 8-CTA clusters above 8 sequences).  Both give the same bits.  A caller that overlaps sequences itself
+ * (one host thread / stream per ctx) states the concurrency here. */
+int lmono_set_concurrency_hint(lmono_ctx* ctx, int32_t n_sequences_on_this_gpu);
 /* With LMONO_TIMELINE=1 in the environment every launch of a mapping step is followed by a one-thread %globaltimer
  * stamp kernel (also inside the step / batch graphs); lmono_timeline_dump writes "<file>:<line> <ns>" per stamp of the
  * last step, so the kernels of concurrent sequences can be laid on one time axis (profiles/batch_timeline.py). */

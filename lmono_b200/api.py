@@ -215,6 +215,10 @@ class Context:
         self._chk(self.L.lmono_profile_read(self._h, ms, cnt), "profile_read")
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROFILE_PHASES)}
 
+    def set_concurrency_hint(self, n):
+        """n sequences run side by side on this GPU outside the batch calls: n >= 4 picks the throughput kernel forms."""
+        self._chk(self.L.lmono_set_concurrency_hint(self._h, C.c_int32(int(n))), "set_concurrency_hint")
+
     def kernel_marks_enable(self, on=True):
         """Per-launch CUDA events on every kernel of map_step* (the step then runs as plain launches, not a graph replay)."""
         self._chk(self.L.lmono_kmarks_enable(self._h, 1 if on else 0), "kmarks_enable")

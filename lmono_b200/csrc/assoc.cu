@@ -660,12 +660,16 @@ int lm_map_associate(lmono_ctx* ctx, int n_max_corner, int n_max_surf) {
   static const int group_env = getenv("LMONO_KNN_GROUP") ? atoi(getenv("LMONO_KNN_GROUP")) : -1;
   const int group = group_env >= 0 ? group_env : (ctx->batch_n >= LM_THROUGHPUT_BATCH ? 0 : GROUP_DEFAULT);
 #define KNN_ARGS ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_slot_valid_rank, ctx->d_stack[0], ctx->d_stack[1], ctx->d_nnref
-  if (group == 0) k_assoc_knn1<<<lm_div_up(nq, KNN1_THREADS), KNN1_THREADS, 0, ctx->stream>>>(KNN_ARGS);
-  else if (group == 1) k_assoc_knn<1><<<lm_div_up(nq * 1, 256), 256, 0, ctx->stream>>>(KNN_ARGS);
+  if (group == 0) {
+    k_assoc_knn1<<<lm_div_up(nq, KNN1_THREADS), KNN1_THREADS, 0, ctx->stream>>>(KNN_ARGS);
+    LM_LAUNCH_CHECK();
+  } else {
+  if (group == 1) k_assoc_knn<1><<<lm_div_up(nq * 1, 256), 256, 0, ctx->stream>>>(KNN_ARGS);
   else if (group == 2) k_assoc_knn<2><<<lm_div_up(nq * 2, 256), 256, 0, ctx->stream>>>(KNN_ARGS);
   else if (group == 4) k_assoc_knn<4><<<lm_div_up(nq * 4, 256), 256, 0, ctx->stream>>>(KNN_ARGS);
   else k_assoc_knn<8><<<lm_div_up(nq * 8, 256), 256, 0, ctx->stream>>>(KNN_ARGS);   // k_assoc_knn<<<
   LM_LAUNCH_CHECK();
+  }
   k_assoc_fit<<<lm_div_up(nq, 128), 128, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_stack[0], ctx->d_stack[1],
                                                           ctx->d_nnref, ctx->d_fac[0], ctx->d_fac[1]);
   LM_LAUNCH_CHECK();

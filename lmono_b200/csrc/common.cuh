@@ -168,6 +168,7 @@ struct lmono_ctx {
   cudaStream_t* cap_streams;    // (batch leader) [LM_BATCH_MAX] branch streams, used only while capturing a batch graph
   LmBatchGraph* bgraphs; int n_bgraphs;      // (batch leader) [LM_MAX_BGRAPHS]
   bool step_timed;              // ev0 / ev1 bracket the pending step (false for steps that ran inside a batch graph)
+  int batch_hint;               // lmono_set_concurrency_hint: what batch_n falls back to outside a batch call (default 1)
   int batch_n;                  // sequences sharing the GPU in the step being enqueued (1 = alone): >= LM_THROUGHPUT_BATCH picks the
                                 // throughput forms of the kernels (one-thread-per-query kNN, 8-CTA LM clusters) over the latency forms
 

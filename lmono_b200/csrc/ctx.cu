@@ -68,7 +68,7 @@ extern "C" int lmono_create(int device, const lmono_params* params, void* stream
   if (P.mapping_line_resolution < 0.06f || P.mapping_plane_resolution < 0.06f) { free(ctx); return LMONO_E_ARG; }
   if (P.scan_line != 16 && P.scan_line != 32 && P.scan_line != 64) { free(ctx); return LMONO_E_ARG; }
   ctx->device = device;
-  ctx->batch_n = 1;
+  ctx->batch_n = 1; ctx->batch_hint = 1;
   { const char* ng = getenv("LMONO_NO_GRAPH"); ctx->graphs_on = !(ng && ng[0] == '1'); }
   ctx->max_feat = P.max_feature_points; ctx->max_sweep = P.max_sweep_points;
   cudaError_t e = cudaSetDevice(device);

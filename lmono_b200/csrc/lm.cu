@@ -588,7 +588,7 @@ static int lm_cluster_pick(lmono_ctx* ctx) {
   const int best = lm_cluster_size(ctx);
   if (best < 0) return best;
   static const int env = getenv("LMONO_LM_CLUSTER") ? atoi(getenv("LMONO_LM_CLUSTER")) : 0;
-  int want = env >= 1 ? env : (ctx->batch_n >= LM_THROUGHPUT_BATCH ? 8 : best);
+  int want = env >= 1 ? env : (ctx->batch_n > 8 ? 8 : best);      // 8 GPCs: at most eight 16-CTA clusters are resident at once
   want = want < best ? want : best;
   int p2 = 1; while (p2 * 2 <= want) p2 *= 2;      // the virtual-CTA scheme needs a divisor of LMC_CLUSTER
   return p2;

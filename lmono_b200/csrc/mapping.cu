@@ -441,7 +441,7 @@ static int batch_capture(lmono_ctx* lead, lmono_ctx* const* ctxs, int n, const i
     g->n_launch[i] = (int)(c->launches - l0);
     c->launches = l0;
     c->stream = saved;
-    c->batch_n = 1;
+    c->batch_n = c->batch_hint;
   }
   cudaError_t ce2 = cudaStreamEndCapture(origin, &graph);
   if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -550,7 +550,7 @@ static int batch_enqueue_plain(lmono_ctx* const* ctxs, int n, const LmStepIn* in
     const int slot = (int)(ctx->n_submitted & 1u);
     ctx->batch_n = n;
     rc = enqueue_step(ctx, in[i], &wodom_curr[i], wmap_in ? &wmap_in[i] : nullptr, slot);
-    ctx->batch_n = 1;
+    ctx->batch_n = ctx->batch_hint;
     if (rc) return rc;
     if ((rc = publish_state(ctx))) return rc;
     LM_CUDA(cudaEventRecord(ctx->ev_res[slot], ctx->stream));
@@ -789,6 +789,14 @@ extern "C" int lmono_profile_read(lmono_ctx* ctx, float* ms /*[LM_PROF_NTAGS]*/,
 // ---- per-launch marks: a CUDA event after every kernel launch of the (non-graph) step, keyed by launch site ----
 // LMONO_TIMELINE=1: "<file>:<line> <globaltimer ns>" per stamp of the last step of this ctx (lines in launch order; the
 // stamp after a launch runs when that kernel has finished)
+// How many sequences the caller runs side by side on this GPU OUTSIDE lmono_map_*_batch calls (e.g. one host thread and
+// stream per sequence): n >= 4 selects the throughput forms of the kernels for this ctx's single steps too.
+extern "C" int lmono_set_concurrency_hint(lmono_ctx* ctx, int32_t n) {
+  if (!ctx || n < 1) return LMONO_E_ARG;
+  ctx->batch_hint = n; ctx->batch_n = n;
+  return LMONO_OK;
+}
+
 extern "C" int lmono_timeline_dump(lmono_ctx* ctx, char* buf, int32_t cap) {
   if (!ctx || !buf || cap <= 0) return LMONO_E_ARG;
   buf[0] = 0;

@@ -481,6 +481,7 @@ __global__ void __launch_bounds__(LM_RF_TF_CHUNK) k_rf_tailflags(LmMapType M0, L
 // cube's merge chunks to the work list
 constexpr int RF_ACT_GRID = 80;
 static_assert(LM_NCELL % 4 == 0, "vector clear of the cell histogram");
+static_assert(LM_RF_CHUNK % 256 == 0, "k_rf_merge / k_rf_scatter: whole elements per thread");
 __global__ void __launch_bounds__(256) k_rf_flags(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, const int32_t* __restrict__ plan,
                                                   int32_t* __restrict__ nvx_all, RfMeta* __restrict__ meta_all, int nvx_stride,
                                                   int32_t* __restrict__ work_n, int32_t* __restrict__ work) {
@@ -557,20 +558,52 @@ __global__ void __launch_bounds__(256) k_rf_merge(LmMapState* __restrict__ st, L
   if (staged) for (int j = threadIdx.x; j < nt; j += blockDim.x) s_tkey[j] = tkey[j];
   __syncthreads();
   int bad = 0;
-  for (int e = e0 + threadIdx.x; e < min(e0 + LM_RF_CHUNK, ns + nt); e += blockDim.x) {
-    if (e < ns) {
-      // prefix point: shifted by the number of new voxels sorting before it; merged if the tail hits its voxel
-      const uint32_t key = pkey[e];
-      int lb; bool hit;
+  // LM_RF_CHUNK / blockDim elements per thread.  The output buffer is the other half of the array the inputs live in, so
+  // the compiler must assume every store aliases the next load: gather the inputs of all of a thread's elements first
+  // (independent loads in flight together), then merge and emit.
+  constexpr int PER = LM_RF_CHUNK / 256;
+  const int eend = min(e0 + LM_RF_CHUNK, ns + nt);
+  uint32_t key_[PER]; float4 p_[PER]; int aux_[PER];       // prefix: aux = lower bound in the tail; tail: aux = nvx flag word
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    const int e = e0 + threadIdx.x + u * 256;
+    key_[u] = 0; aux_[u] = 0; p_[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e < eend) {
+      key_[u] = pkey[e];              // pkey and tkey are one array: tkey[j] = pkey[ns + j]
+      if (e < ns) p_[u] = src[e]; else aux_[u] = nvx[e - ns];
+    }
+  }
+  int before_[PER];
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    const int e = e0 + threadIdx.x + u * 256;
+    before_[u] = 0;
+    if (e < eend && e < ns) {
+      const uint32_t key = key_[u];
+      int lb;
       if (staged) {
         int lo = 0, hi = nt;
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_tkey[mid] < key) lo = mid + 1; else hi = mid; }
-        lb = lo; hit = lb < nt && s_tkey[lb] == key;
+        lb = lo;
       } else {
-        lb = d_lower_bound_u32(tkey, nt, key); hit = lb < nt && tkey[lb] == key;
+        lb = d_lower_bound_u32(tkey, nt, key);
       }
-      const int before = lb < nt ? (nvx[lb] >> 1) : total_new;
-      float4 p = src[e];
+      aux_[u] = lb;
+      before_[u] = lb < nt ? (nvx[lb] >> 1) : total_new;
+    } else if (e < eend && (aux_[u] & 1)) {
+      before_[u] = tlb[e - ns];       // lower bound of the key in the prefix (k_rf_tailflags)
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    const int e = e0 + threadIdx.x + u * 256;
+    if (e >= eend) continue;
+    const uint32_t key = key_[u];
+    if (e < ns) {
+      // prefix point: shifted by the number of new voxels sorting before it; merged if the tail hits its voxel
+      const int lb = aux_[u];
+      float4 p = p_[u];
+      const bool hit = lb < nt && (staged ? s_tkey[lb] : tkey[lb]) == key;
       if (hit) {
         float sx = p.x, sy = p.y, sz = p.z, si = p.w;
         int cnt = 1;
@@ -583,12 +616,11 @@ __global__ void __launch_bounds__(256) k_rf_merge(LmMapState* __restrict__ st, L
         p = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), __fdiv_rn(si, c));
         bad |= d_cube_voxel_key(p, il, g3) != key;      // the centroid left its voxel
       }
-      d_rf_emit(M, sid, cur, e + before, p, key, g3, st);
+      d_rf_emit(M, sid, cur, e + before_[u], p, key, g3, st);
     } else {
       const int j = e - ns;
-      const int v = nvx[j];
+      const int v = aux_[u];
       if (!(v & 1)) continue;
-      const uint32_t key = tkey[j];
       float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
       int cnt = 0;
       for (int m = j; m < nt && tkey[m] == key; ++m) {
@@ -599,7 +631,7 @@ __global__ void __launch_bounds__(256) k_rf_merge(LmMapState* __restrict__ st, L
       const float c = (float)cnt;
       const float4 p = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), __fdiv_rn(si, c));
       bad |= d_cube_voxel_key(p, il, g3) != key;
-      d_rf_emit(M, sid, cur, tlb[j] + (v >> 1), p, key, g3, st);     // tlb[j] = lower bound of the key in the prefix (k_rf_tailflags)
+      d_rf_emit(M, sid, cur, before_[u] + (v >> 1), p, key, g3, st);
     }
   }
   if (bad) meta->flag = 1;
@@ -682,13 +714,20 @@ __global__ void __launch_bounds__(256) k_rf_scatter(LmMapType M0, LmMapType M1, 
   float4* __restrict__ cp = M.cellpts + (size_t)sid * M.cap;
   int32_t* cc = M.cellcount + (size_t)sid * LM_NCELL;
   const int g3[3] = { M.slab_g[sid * 4], M.slab_g[sid * 4 + 1], M.slab_g[sid * 4 + 2] };
-  for (int i = e0 + threadIdx.x; i < min(e0 + LM_RF_CHUNK, nn); i += blockDim.x) {
-    float4 p = src[i];
-    int c = d_cube_cell(p, g3);
-    if (c < 0) c = 0;
-    const int pos = atomicAdd(&cc[c], 1);
-    p.w = __int_as_float(i);
-    cp[pos] = p;
+  constexpr int PER = LM_RF_CHUNK / 256;
+  const int iend = min(e0 + LM_RF_CHUNK, nn);
+  float4 p_[PER]; int pos_[PER];
+#pragma unroll
+  for (int u = 0; u < PER; ++u) { const int i = e0 + threadIdx.x + u * 256; if (i < iend) p_[u] = src[i]; }
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    const int i = e0 + threadIdx.x + u * 256;
+    if (i < iend) { int c = d_cube_cell(p_[u], g3); if (c < 0) c = 0; pos_[u] = atomicAdd(&cc[c], 1); }
+  }
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    const int i = e0 + threadIdx.x + u * 256;
+    if (i < iend) { float4 p = p_[u]; p.w = __int_as_float(i); cp[pos_[u]] = p; }
   }
  }
 }
