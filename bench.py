@@ -169,7 +169,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -509,10 +509,13 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": ncpu / dt, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": f"{ncpu} registrations of the same workload on 1 host thread (the reference nodes are single-threaded)"}
     if rank == 0:
-        print(json.dumps(line))
-    batch.close()
-    if world > 1:
-        dist.destroy_process_group()
+        print(json.dumps(line), flush=True)          # before any teardown: a crash while freeing must not eat the result
+    try:
+        batch.close()
+        if world > 1:
+            dist.destroy_process_group()
+    except Exception as e:                           # noqa: BLE001
+        print(f"[bench] teardown: {e}", file=sys.stderr)
 
 
 def main():
