@@ -26,9 +26,8 @@ constexpr int LM_WIN_MAX = 75;                    // cubes of the 5x5x3 window
 // d_rf_plan layout: counts, then three lists of (type * LM_WIN_MAX + window rank).  The per-step kernels that only a few
 // cubes need (index build, whole-slab re-voxelisation, tail merge) run on small grids that walk these lists instead of
 // one (mostly idle) CTA per window cube: with many sequences per GPU the idle CTAs of all of them queue for SM slots.
-constexpr int LM_PLAN_DIRTY_N = 0, LM_PLAN_WHOLE_N = 1, LM_PLAN_ACTIVE_N = 2, LM_PLAN_TF_N = 3;
+constexpr int LM_PLAN_DIRTY_N = 0, LM_PLAN_WHOLE_N = 1, LM_PLAN_ACTIVE_N = 2;
 constexpr int LM_PLAN_DIRTY = 16, LM_PLAN_WHOLE = 16 + 2 * LM_WIN_MAX, LM_PLAN_ACTIVE = 16 + 4 * LM_WIN_MAX, LM_PLAN_INTS = 16 + 6 * LM_WIN_MAX;
-constexpr int LM_RF_TF_CHUNK = 256;               // tail points per CTA in k_rf_tailflags
 
 // device fault bits (LmMapState::fault)
 enum : unsigned {
@@ -158,6 +157,7 @@ struct lmono_ctx {
   lmono_params prm;
   cudaStream_t stream;
   bool own_stream;
+  cudaStream_t side_stream; cudaEvent_t ev_side0, ev_side1;   // fork / join of the independent head of a captured step (window upkeep || feature VoxelGrid)
   int last_cuda_error;
   int64_t launches;
   cudaEvent_t ev0, ev1;
@@ -202,7 +202,6 @@ struct lmono_ctx {
   int32_t* d_rf_work;                       // [4 + 2*75*chunks]: chunk work list of the cubes being refiltered
   int32_t* d_rf_meta;                       // [2][75][8]: active, total_new, ns, nt, unsorted flag, cur
   int32_t* d_rf_plan;                       // compact per-step work lists (LM_PLAN_*): dirty cubes, cubes to re-voxelise whole, cubes with a tail
-  int32_t* d_rf_tf;                         // tail-chunk work list of k_rf_tailflags: (type * 75 + window rank) << 16 | chunk
   float4* d_export; size_t export_cap;      // export / import staging
   int32_t* d_export_off;                    // [LM_NSLOT+1]
   int max_feat, max_sweep;
@@ -314,6 +313,16 @@ __device__ __forceinline__ float4 d_associate(const double* q, const double* t, 
   float4 r;
   r.x = (float)(o[0] + t[0]); r.y = (float)(o[1] + t[1]); r.z = (float)(o[2] + t[2]); r.w = pi.w;
   return r;
+}
+
+// transformUpdate (laserMapping.cpp:148-152) + frame counter; one thread
+__device__ __forceinline__ void d_transform_update(LmMapState* st) {
+  double qi[4]; d_qinv(st->q_wodom_curr, qi);
+  double qn[4]; d_qmul(st->q_w_curr, qi, qn);
+  for (int k = 0; k < 4; ++k) st->q_wmap_wodom[k] = qn[k];
+  double tmp[3]; d_qrot(qn, st->t_wodom_curr, tmp);
+  for (int k = 0; k < 3; ++k) st->t_wmap_wodom[k] = st->t_w_curr[k] - tmp[k];
+  st->frame_count++;
 }
 
 // voxel coordinate of PCL VoxelGrid: floor(x * inverse_leaf) in fp32
@@ -543,7 +552,7 @@ void lm_map_free(lmono_ctx* ctx);
 // pose source: wodom_curr (by value), else t_override (test hooks), else the q/t_wodom_curr already in the state
 int lm_map_begin_step(lmono_ctx* ctx, const lmono_pose* wodom_curr, const double* t_override);
 int lm_map_index_build(lmono_ctx* ctx);
-int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf);
+int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf, bool transform_update = false);
 // assoc.cu
 int lm_map_associate(lmono_ctx* ctx, int n_max_corner, int n_max_surf);
 int lm_knn5_device(lmono_ctx* ctx, int which, const float4* d_q, int n, int32_t* d_idx, float* d_d2);

@@ -84,6 +84,9 @@ extern "C" int lmono_create(int device, const lmono_params* params, void* stream
   LM_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   LM_CUDA(cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming));
   LM_CUDA(cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming));
+  LM_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+  LM_CUDA(cudaEventCreateWithFlags(&ctx->ev_side0, cudaEventDisableTiming));
+  LM_CUDA(cudaEventCreateWithFlags(&ctx->ev_side1, cudaEventDisableTiming));
 
   LM_CUDA(cudaMalloc((void**)&ctx->d_state, sizeof(LmMapState)));
   LM_CUDA(cudaMallocHost((void**)&ctx->h_state, sizeof(LmMapState)));
@@ -149,12 +152,13 @@ extern "C" void lmono_destroy(lmono_ctx* ctx) {
   lm_odom_free(ctx);
   lm_color_free(ctx);
   lm_map_free(ctx);
-  cudaFree(ctx->d_state); cudaFreeHost(ctx->h_state); for (int i = 0; i < 2; ++i) { cudaFreeHost(ctx->h_ring[i]); cudaEventDestroy(ctx->ev_res[i]); } cudaFree(ctx->d_lm); cudaFree(ctx->d_slot_valid_rank); cudaFree(ctx->d_partials); cudaFree(ctx->d_stamps); cudaFree(ctx->d_tl); cudaFree(ctx->d_nnref); cudaFree(ctx->d_rf_nvx); cudaFree(ctx->d_rf_tlb); cudaFree(ctx->d_rf_work); cudaFree(ctx->d_rf_meta); cudaFree(ctx->d_rf_plan); cudaFree(ctx->d_rf_tf);
+  cudaFree(ctx->d_state); cudaFreeHost(ctx->h_state); for (int i = 0; i < 2; ++i) { cudaFreeHost(ctx->h_ring[i]); cudaEventDestroy(ctx->ev_res[i]); } cudaFree(ctx->d_lm); cudaFree(ctx->d_slot_valid_rank); cudaFree(ctx->d_partials); cudaFree(ctx->d_stamps); cudaFree(ctx->d_tl); cudaFree(ctx->d_nnref); cudaFree(ctx->d_rf_nvx); cudaFree(ctx->d_rf_tlb); cudaFree(ctx->d_rf_work); cudaFree(ctx->d_rf_meta); cudaFree(ctx->d_rf_plan);
   for (int i = 0; i < 3; ++i) cudaFree(ctx->d_raw[i]);
   for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_in[i]); cudaFree(ctx->d_stack[i]); cudaFree(ctx->d_world[i]); cudaFree(ctx->d_fac[i]); }
   cudaFree(ctx->d_sort_a); cudaFree(ctx->d_sort_b); cudaFree(ctx->d_sort_c); cudaFree(ctx->d_blockcnt); cudaFree(ctx->d_tmp_i32);
   cudaFree(ctx->d_vg); cudaFree(ctx->d_full); cudaFree(ctx->d_slot_first); cudaFree(ctx->d_slot_base); cudaFree(ctx->d_export_off); cudaFree(ctx->d_export);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); cudaEventDestroy(ctx->ev_sync); cudaEventDestroy(ctx->ev_done);
+  if (ctx->side_stream) { cudaStreamDestroy(ctx->side_stream); cudaEventDestroy(ctx->ev_side0); cudaEventDestroy(ctx->ev_side1); }
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   free(ctx);
 }

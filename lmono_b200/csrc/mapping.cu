@@ -14,12 +14,7 @@ int lm_map_import_device(lmono_ctx* ctx, int which, const float4* d_pts, int n,
 // transformUpdate (:148-152) + frame counter
 __global__ void k_transform_update(LmMapState* st) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double qi[4]; d_qinv(st->q_wodom_curr, qi);
-  double qn[4]; d_qmul(st->q_w_curr, qi, qn);
-  for (int k = 0; k < 4; ++k) st->q_wmap_wodom[k] = qn[k];
-  double tmp[3]; d_qrot(st->q_wmap_wodom, st->t_wodom_curr, tmp);
-  for (int k = 0; k < 3; ++k) st->t_wmap_wodom[k] = st->t_w_curr[k] - tmp[k];
-  st->frame_count++;
+  d_transform_update(st);
 }
 
 // :838-842 full-resolution sweep to the world frame
@@ -98,16 +93,33 @@ static int enqueue_body(lmono_ctx* ctx, int nc, int ns) {
     lm_tl(ctx, "begin", 0);
   }
   struct TlOff { lmono_ctx* c; ~TlOff() { c->tl_on = false; } } tl_off{ctx};
+  // window upkeep + index build (:309-539, :558-559) and the VoxelGrid of the incoming features (:542-550) do not
+  // depend on each other: inside a graph capture they become two parallel branches
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(ctx->stream, &cap);
+  const bool fork = cap == cudaStreamCaptureStatusActive && ctx->side_stream != nullptr && !ctx->tl_on;
+  cudaStream_t main_stream = ctx->stream;
+  if (fork) {
+    LM_CUDA(cudaEventRecord(ctx->ev_side0, main_stream));
+    LM_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_side0, 0));
+    ctx->stream = ctx->side_stream;
+  }
   lm_prof_begin(ctx, LM_PROF_WINDOW);
-  if ((rc = lm_map_begin_step(ctx, nullptr, nullptr))) return rc;           // :309-539
+  rc = lm_map_begin_step(ctx, nullptr, nullptr);                            // :309-539
   lm_prof_end(ctx);
   lm_prof_begin(ctx, LM_PROF_INDEX);
-  if ((rc = lm_map_index_build(ctx))) return rc;                            // replaces kdtree setInputCloud :558-559
+  if (!rc) rc = lm_map_index_build(ctx);                                    // replaces kdtree setInputCloud :558-559
   lm_prof_end(ctx);
+  if (fork) {
+    ctx->stream = main_stream;
+    if (!rc) LM_CUDA(cudaEventRecord(ctx->ev_side1, ctx->side_stream));
+  }
+  if (rc) return rc;
   // :542-550 VoxelGrid of the incoming features
   lm_prof_begin(ctx, LM_PROF_VOXEL);
   if ((rc = voxel_both(ctx, nullptr, nc, nullptr, ns))) return rc;
   lm_prof_end(ctx);
+  if (fork) LM_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_side1, 0));
   for (int iter = 0; iter < 2; ++iter) {                                    // :562
     lm_prof_begin(ctx, LM_PROF_ASSOC);
     if ((rc = lm_map_associate(ctx, nc, ns))) return rc;                    // :577-687
@@ -116,9 +128,13 @@ static int enqueue_body(lmono_ctx* ctx, int nc, int ns) {
     if ((rc = lm_solve_enqueue(ctx, iter, nc, ns, 4))) return rc;           // :713-720
     lm_prof_end(ctx);
   }
-  k_transform_update<<<1, 32, 0, ctx->stream>>>(ctx->d_state);              // :734
-  LM_LAUNCH_CHECK();
-  if ((rc = lm_map_insert_and_refilter(ctx, nc, ns))) return rc;            // :737-801
+  if (nc + ns > 0) {
+    if ((rc = lm_map_insert_and_refilter(ctx, nc, ns, /*transform_update=*/true))) return rc;   // :734, :737-801
+  } else {
+    k_transform_update<<<1, 32, 0, ctx->stream>>>(ctx->d_state);            // :734
+    LM_LAUNCH_CHECK();
+    if ((rc = lm_map_insert_and_refilter(ctx, nc, ns, false))) return rc;
+  }
   return LMONO_OK;
 }
 

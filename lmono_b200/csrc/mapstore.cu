@@ -306,10 +306,12 @@ __device__ __forceinline__ uint32_t d_ins_index(unsigned long long c) { return (
 __global__ void __launch_bounds__(256) k_insert_prepare(LmMapState* __restrict__ st, const float4* __restrict__ stack0,
                                                         const float4* __restrict__ stack1, float4* __restrict__ world0,
                                                         float4* __restrict__ world1, unsigned long long* __restrict__ comp,
-                                                        int32_t* __restrict__ n_ins, float leaf0, float inv_leaf0, float leaf1, float inv_leaf1) {
+                                                        int32_t* __restrict__ n_ins, float leaf0, float inv_leaf0, float leaf1, float inv_leaf1,
+                                                        int transform_update) {
   const int n0 = st->stack_n[0], n1 = st->stack_n[1];
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e == 0) *n_ins = n0 + n1;
+  if (e == 0 && transform_update) d_transform_update(st);     // :734 rides along (writes q/t_wmap_wodom only; nobody here reads them)
   if (e >= n0 + n1) return;
   const int ty = e < n0 ? 0 : 1;
   const int i = ty == 0 ? e : e - n0;
@@ -416,9 +418,9 @@ __device__ __forceinline__ bool d_rf_slab(const LmMapState* st, const LmMapType&
 }
 
 // per step: classify the window cubes once.  whole list = flagged slabs (re-voxelised as a whole), active list = slabs
-// with a tail (their meta record is armed here: ns, nt, cur, sid), tail-chunk list for k_rf_tailflags.  One CTA.
+// with a tail (their meta record is armed here: ns, nt, cur, sid).  One CTA.
 __global__ void __launch_bounds__(256) k_rf_plan(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, int32_t* __restrict__ plan,
-                                                 RfMeta* __restrict__ meta_all, int32_t* __restrict__ tfwork, int32_t* __restrict__ work_n) {
+                                                 RfMeta* __restrict__ meta_all, int32_t* __restrict__ work_n) {
   __shared__ int ws[33];
   const int e = threadIdx.x;
   const int ty = e / LM_WIN_MAX, r = e - ty * LM_WIN_MAX;
@@ -443,48 +445,19 @@ __global__ void __launch_bounds__(256) k_rf_plan(LmMapState* __restrict__ st, Lm
   const int apos = d_block_exscan(active ? 1 : 0, ws, &tot);
   if (active) plan[LM_PLAN_ACTIVE + apos] = e;
   if (threadIdx.x == 0) plan[LM_PLAN_ACTIVE_N] = tot;
-  const int ntf = active ? (n - ns + LM_RF_TF_CHUNK - 1) / LM_RF_TF_CHUNK : 0;
-  const int tbase = d_block_exscan(ntf, ws, &tot);
-  for (int c = 0; c < ntf; ++c) tfwork[tbase + c] = (e << 16) | c;
-  if (threadIdx.x == 0) { plan[LM_PLAN_TF_N] = tot; *work_n = 0; }
+  if (threadIdx.x == 0) *work_n = 0;
 }
 
-// tail element j opens a NEW voxel iff it is the first of its key run and the key is absent from the prefix:
-// one thread per tail element, so the (dependent, ~15-step) binary searches of a cube spread over many SMs
-constexpr int RF_TF_GRID = 296;
-__global__ void __launch_bounds__(LM_RF_TF_CHUNK) k_rf_tailflags(LmMapType M0, LmMapType M1, const int32_t* __restrict__ plan,
-                                                                 const RfMeta* __restrict__ meta_all, const int32_t* __restrict__ tfwork,
-                                                                 int32_t* __restrict__ nvx_all, int32_t* __restrict__ tlb_all, int nvx_stride) {
-  const int ntf = plan[LM_PLAN_TF_N];
-  for (int w = blockIdx.x; w < ntf; w += gridDim.x) {
-    const int we = tfwork[w];
-    const int e = we >> 16, ty = e / LM_WIN_MAX;
-    const LmMapType& M = ty == 0 ? M0 : M1;
-    const RfMeta* meta = meta_all + e;
-    const int ns = meta->ns, nt = meta->nt, sid = meta->sid;
-    const uint32_t* __restrict__ pkey = M.pkey + ((size_t)sid * 2 + meta->cur) * M.cap;
-    const uint32_t* __restrict__ tkey = pkey + ns;
-    const int j = (we & 0xFFFF) * LM_RF_TF_CHUNK + threadIdx.x;
-    if (j >= nt) continue;
-    const uint32_t key = tkey[j];
-    int nv = 0;
-    if (j == 0 || tkey[j - 1] != key) {
-      const int lb = d_lower_bound_u32_wide(pkey, ns, key);
-      nv = !(lb < ns && pkey[lb] == key);
-      tlb_all[(size_t)e * nvx_stride + j] = lb;          // k_rf_merge places a new voxel at lb + (new voxels before it)
-    }
-    nvx_all[(size_t)e * nvx_stride + j] = nv;
-  }
-}
-
-// per cube with a tail: exclusive scan of the new-voxel flags -> output offsets; clears the cell histogram; appends the
-// cube's merge chunks to the work list
+// per cube with a tail, one CTA: tail element j opens a NEW voxel iff it is the first of its key run and the key is absent
+// from the prefix (9-ary search, the lower bound is kept for k_rf_merge); exclusive scan of those flags -> output
+// offsets; clears the cell histogram; appends the cube's merge chunks to the work list.
 constexpr int RF_ACT_GRID = 80;
+constexpr int RF_TS_THREADS = 1024;
 static_assert(LM_NCELL % 4 == 0, "vector clear of the cell histogram");
 static_assert(LM_RF_CHUNK % 256 == 0, "k_rf_merge / k_rf_scatter: whole elements per thread");
-__global__ void __launch_bounds__(256) k_rf_flags(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, const int32_t* __restrict__ plan,
-                                                  int32_t* __restrict__ nvx_all, RfMeta* __restrict__ meta_all, int nvx_stride,
-                                                  int32_t* __restrict__ work_n, int32_t* __restrict__ work) {
+__global__ void __launch_bounds__(RF_TS_THREADS) k_rf_tailscan(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, const int32_t* __restrict__ plan,
+                                                               int32_t* __restrict__ nvx_all, int32_t* __restrict__ tlb_all, RfMeta* __restrict__ meta_all,
+                                                               int nvx_stride, int32_t* __restrict__ work_n, int32_t* __restrict__ work) {
   __shared__ int ws[33];
   __shared__ int s_wbase;
   const int na = plan[LM_PLAN_ACTIVE_N];
@@ -494,14 +467,24 @@ __global__ void __launch_bounds__(256) k_rf_flags(LmMapState* __restrict__ st, L
     const LmMapType& M = ty == 0 ? M0 : M1;
     RfMeta* meta = meta_all + e;
     const int ns = meta->ns, nt = meta->nt, sid = meta->sid;
+    const uint32_t* __restrict__ pkey = M.pkey + ((size_t)sid * 2 + meta->cur) * M.cap;
+    const uint32_t* __restrict__ tkey = pkey + ns;
     int32_t* __restrict__ nvx = nvx_all + (size_t)e * nvx_stride;
+    int32_t* __restrict__ tlb = tlb_all + (size_t)e * nvx_stride;
     int4* cc4 = reinterpret_cast<int4*>(M.cellcount + (size_t)sid * LM_NCELL);       // LM_NCELL % 4 == 0, slabs 16 B aligned
     for (int c = threadIdx.x; c < LM_NCELL / 4; c += blockDim.x) cc4[c] = make_int4(0, 0, 0, 0);
-    // chunked scan, coalesced: blockDim flags per round with a running carry
     int carry = 0;
     for (int j0 = 0; j0 < nt; j0 += blockDim.x) {
       const int j = j0 + threadIdx.x;
-      const int nv = j < nt ? nvx[j] : 0;
+      int nv = 0;
+      if (j < nt) {
+        const uint32_t key = tkey[j];
+        if (j == 0 || tkey[j - 1] != key) {
+          const int lb = d_lower_bound_u32_wide(pkey, ns, key);
+          nv = !(lb < ns && pkey[lb] == key);
+          tlb[j] = lb;
+        }
+      }
       int tot;
       const int ex = d_block_exscan(nv, ws, &tot);
       if (j < nt) nvx[j] = ((carry + ex) << 1) | nv;
@@ -808,7 +791,7 @@ __global__ void __launch_bounds__(1024, 1) k_refilter_whole(LmMapState* __restri
 
 static const int kRefilterSmem = LM_TAIL_TILE * 12 + 64 * 4;
 
-int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf) {
+int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf, bool transform_update) {
   const int n_max = n_max_corner + n_max_surf;
   lm_prof_begin(ctx, LM_PROF_INSERT);
   if (n_max > 0) {
@@ -817,7 +800,7 @@ int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf)
     const int blocks = lm_div_up(n_max, 256);
     k_insert_prepare<<<blocks, 256, 0, ctx->stream>>>(ctx->d_state, ctx->d_stack[0], ctx->d_stack[1], ctx->d_world[0],
                                                       ctx->d_world[1], ctx->d_sort_a, n_ins, ctx->map[0].leaf, ctx->map[0].inv_leaf,
-                                                      ctx->map[1].leaf, ctx->map[1].inv_leaf);
+                                                      ctx->map[1].leaf, ctx->map[1].inv_leaf, transform_update ? 1 : 0);
     LM_LAUNCH_CHECK();
     int rc = lm_sort_u64(ctx, ctx->d_sort_a, ctx->d_sort_b, ctx->d_sort_c, n_ins, n_max);
     if (rc) return rc;
@@ -833,13 +816,11 @@ int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf)
   const int cap_max = ctx->map[0].cap > ctx->map[1].cap ? ctx->map[0].cap : ctx->map[1].cap;
   RfMeta* meta = (RfMeta*)ctx->d_rf_meta;
   int32_t* work_n = ctx->d_rf_work; int32_t* work = ctx->d_rf_work + 4;
-  k_rf_plan<<<1, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan, meta, ctx->d_rf_tf, work_n);
+  k_rf_plan<<<1, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan, meta, work_n);
   LM_LAUNCH_CHECK();
   k_refilter_whole<<<RF_WHOLE_GRID, 1024, kRefilterSmem, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan);
   LM_LAUNCH_CHECK();
-  k_rf_tailflags<<<RF_TF_GRID, LM_RF_TF_CHUNK, 0, ctx->stream>>>(ctx->map[0], ctx->map[1], ctx->d_rf_plan, meta, ctx->d_rf_tf, ctx->d_rf_nvx, ctx->d_rf_tlb, cap_max);
-  LM_LAUNCH_CHECK();
-  k_rf_flags<<<RF_ACT_GRID, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan, ctx->d_rf_nvx, meta, cap_max, work_n, work);
+  k_rf_tailscan<<<RF_ACT_GRID, RF_TS_THREADS, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan, ctx->d_rf_nvx, ctx->d_rf_tlb, meta, cap_max, work_n, work);
   LM_LAUNCH_CHECK();
   k_rf_merge<<<RF_GRID, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_nvx, ctx->d_rf_tlb, meta, cap_max, work_n, work);
   LM_LAUNCH_CHECK();
@@ -862,7 +843,7 @@ int lm_map_configure_kernels(lmono_ctx* ctx) {
   LM_CUDA(cudaMemsetAsync(ctx->d_rf_meta, 0, sizeof(RfMeta) * 2 * LM_WIN_MAX, ctx->stream));
   LM_CUDA(cudaMalloc((void**)&ctx->d_rf_plan, sizeof(int32_t) * LM_PLAN_INTS));
   LM_CUDA(cudaMemsetAsync(ctx->d_rf_plan, 0, sizeof(int32_t) * LM_PLAN_INTS, ctx->stream));
-  LM_CUDA(cudaMalloc((void**)&ctx->d_rf_tf, sizeof(int32_t) * (size_t)2 * LM_WIN_MAX * (lm_div_up(cap_max, LM_RF_TF_CHUNK) + 1)));
+
   return LMONO_OK;
 }
 

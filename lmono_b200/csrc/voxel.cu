@@ -17,7 +17,7 @@
 
 constexpr int VG_BIAS = 16384;           // voxel coordinates in [-16384, 16383]
 constexpr int VG_IDX_BITS = 19;          // input index < 524288
-constexpr int VW_THREADS = 256, VW_ITEMS = 4, VW_BLOCK = VW_THREADS * VW_ITEMS;
+constexpr int VW_THREADS = 256, VW_BLOCK = VW_THREADS;      // one sorted position per thread
 
 struct VgSegs {
   const float4* in[LM_SORT_MAXSEG]; float4* out[LM_SORT_MAXSEG];
@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(256) k_vg_keys(VgSegs sg, VgParams* __restrict
 __global__ void __launch_bounds__(VW_THREADS) k_vg_write(VgSegs sg, VgParams* __restrict__ vgs, const unsigned long long* __restrict__ sorted_all) {
   __shared__ int ws[33];
   __shared__ int s_guard;
+  __shared__ unsigned long long s_key[VW_THREADS];
+  __shared__ float4 s_pt[VW_THREADS];
   const int seg = blockIdx.y;
   const int n = *sg.n[seg];
   VgParams& vg = vgs[seg];
@@ -126,49 +128,49 @@ __global__ void __launch_bounds__(VW_THREADS) k_vg_write(VgSegs sg, VgParams* __
     for (int i = base + threadIdx.x; i < min(n, base + VW_BLOCK); i += VW_THREADS) out[i] = pts[i];
     if (blockIdx.x == 0 && threadIdx.x == 0) *sg.out_n[seg] = n;
   } else {
-    // heads before this block
+    // one sorted position per thread: its composite and its point are fetched at once (two dependent round trips for the
+    // whole block), a run head then sums its members out of shared memory in sorted (= input index) order; only a run
+    // that crosses the block's end goes back to global memory
+    const int p = base + threadIdx.x;
+    const bool valid = p < n;
+    const unsigned long long me = valid ? sorted[p] : ~0ULL;
+    const unsigned long long key = me >> VG_IDX_BITS;
+    const unsigned long long prevk = (valid && p > 0) ? (sorted[p - 1] >> VG_IDX_BITS) : ~0ULL;
+    const float4 mine = valid ? pts[(uint32_t)(me & ((1u << VG_IDX_BITS) - 1u))] : make_float4(0.f, 0.f, 0.f, 0.f);
+    // heads before this block (independent loads, 16 in flight)
     int before = 0;
-#pragma unroll 8
-    for (int i = threadIdx.x; i < base; i += VW_THREADS)          // independent loads: keep 16 in flight
+#pragma unroll 16
+    for (int i = threadIdx.x; i < base; i += VW_THREADS)
       before += (i == 0) || ((sorted[i] >> VG_IDX_BITS) != (sorted[i > 0 ? i - 1 : 0] >> VG_IDX_BITS));
+    s_key[threadIdx.x] = valid ? key : ~0ULL;
+    s_pt[threadIdx.x] = mine;
     int total_before;
-    d_block_exscan(before, ws, &total_before);
-    // my VW_ITEMS consecutive positions
-    const int p0 = base + threadIdx.x * VW_ITEMS;
-    unsigned long long me[VW_ITEMS];
-    int head[VW_ITEMS], cnt = 0;
-    unsigned long long prev = (p0 > 0 && p0 < n) ? (sorted[p0 - 1] >> VG_IDX_BITS) : ~0ULL;
-#pragma unroll
-    for (int r = 0; r < VW_ITEMS; ++r) {
-      const int p = p0 + r;
-      head[r] = 0; me[r] = 0;
-      if (p < n) {
-        me[r] = sorted[p];
-        const unsigned long long k = me[r] >> VG_IDX_BITS;
-        head[r] = (p == 0) || (k != prev);
-        prev = k;
-      }
-      cnt += head[r];
-    }
+    d_block_exscan(before, ws, &total_before);           // (its barriers also publish s_key / s_pt)
+    const int head = valid && (p == 0 || key != prevk);
     int total;
-    int off = total_before + d_block_exscan(cnt, ws, &total);
-#pragma unroll
-    for (int r = 0; r < VW_ITEMS; ++r) {
-      if (!head[r]) continue;
-      const unsigned long long key = me[r] >> VG_IDX_BITS;
-      float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-      int c = 0;
-      for (int j = p0 + r; j < n; ++j) {
-        const unsigned long long cj = sorted[j];
-        if ((cj >> VG_IDX_BITS) != key) break;
-        const float4 p = pts[(uint32_t)(cj & ((1u << VG_IDX_BITS) - 1u))];
-        sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
+    const int off = total_before + d_block_exscan(head, ws, &total);
+    if (head) {
+      float sx = mine.x, sy = mine.y, sz = mine.z, si = mine.w;
+      int c = 1;
+      int m = threadIdx.x + 1;
+      for (; m < VW_THREADS && s_key[m] == key; ++m) {
+        const float4 q = s_pt[m];
+        sx = __fadd_rn(sx, q.x); sy = __fadd_rn(sy, q.y); sz = __fadd_rn(sz, q.z); si = __fadd_rn(si, q.w);
         ++c;
       }
+      if (m == VW_THREADS) {
+        for (int j = base + VW_THREADS; j < n; ++j) {
+          const unsigned long long cj = sorted[j];
+          if ((cj >> VG_IDX_BITS) != key) break;
+          const float4 q = pts[(uint32_t)(cj & ((1u << VG_IDX_BITS) - 1u))];
+          sx = __fadd_rn(sx, q.x); sy = __fadd_rn(sy, q.y); sz = __fadd_rn(sz, q.z); si = __fadd_rn(si, q.w);
+          ++c;
+        }
+      }
       const float cf = (float)c;
-      out[off++] = make_float4(__fdiv_rn(sx, cf), __fdiv_rn(sy, cf), __fdiv_rn(sz, cf), __fdiv_rn(si, cf));
+      out[off] = make_float4(__fdiv_rn(sx, cf), __fdiv_rn(sy, cf), __fdiv_rn(sz, cf), __fdiv_rn(si, cf));
     }
-    if (p0 <= n - 1 && n - 1 < p0 + VW_ITEMS) *sg.out_n[seg] = off;     // the thread that owns the last position
+    if (p == n - 1) *sg.out_n[seg] = off + head;          // the thread that owns the last position
   }
   // the last block to finish re-arms the bounding box for the next call
   __syncthreads();
