@@ -459,22 +459,26 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_compact(const float4* __res
     if (b == n_scans - 1 && threadIdx.x == 0) meta->out_n[3] = off + cnt;
     return;
   }
-  // picks: (ring, sector) major, pick order inside
-  __shared__ int s_off[3];
-  if (threadIdx.x == 0) { s_off[0] = s_off[1] = s_off[2] = 0; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int a0 = 0, a1 = 0, a2 = 0;
-    for (int e = 0; e < n_scans * 6; ++e) {
-      const int c0 = pick_cnt[e * 3], c1 = pick_cnt[e * 3 + 1], c2 = pick_cnt[e * 3 + 2];
+  // picks: (ring, sector) major, pick order inside.  One thread per (ring, sector): exclusive scans of the three counts
+  // give every entry its output offsets, the <= 26 picked points of an entry are independent gathers
+  __shared__ int ws[33];
+  const int ne = n_scans * 6;
+  int a0 = 0, a1 = 0, a2 = 0;
+  for (int e0 = 0; e0 < ne; e0 += blockDim.x) {
+    const int e = e0 + threadIdx.x;
+    int c0 = 0, c1 = 0, c2 = 0;
+    if (e < ne) { c0 = pick_cnt[e * 3]; c1 = pick_cnt[e * 3 + 1]; c2 = pick_cnt[e * 3 + 2]; }
+    int t0, t1, t2;
+    const int x0 = d_block_exscan(c0, ws, &t0), x1 = d_block_exscan(c1, ws, &t1), x2 = d_block_exscan(c2, ws, &t2);
+    if (e < ne) {
       const int* idx = pick_idx + e * SC_PICK_STRIDE;
-      for (int k = 0; k < c0; ++k) o_sharp[a0 + k] = full[idx[k]];
-      for (int k = 0; k < c1; ++k) o_ls[a1 + k] = full[idx[2 + k]];
-      for (int k = 0; k < c2; ++k) o_flat[a2 + k] = full[idx[22 + k]];
-      a0 += c0; a1 += c1; a2 += c2;
+      for (int k = 0; k < c0; ++k) o_sharp[a0 + x0 + k] = full[idx[k]];
+      for (int k = 0; k < c1; ++k) o_ls[a1 + x1 + k] = full[idx[2 + k]];
+      for (int k = 0; k < c2; ++k) o_flat[a2 + x2 + k] = full[idx[22 + k]];
     }
-    meta->out_n[0] = a0; meta->out_n[1] = a1; meta->out_n[2] = a2;
+    a0 += t0; a1 += t1; a2 += t2;
   }
+  if (threadIdx.x == 0) { meta->out_n[0] = a0; meta->out_n[1] = a1; meta->out_n[2] = a2; }
 }
 
 __global__ void k_scan_meta_init(ScanMeta* meta) {
