@@ -720,7 +720,9 @@ __global__ void __launch_bounds__(KNN1_THREADS) k_knn5_hook1(const LmMapState* _
 
 int lm_knn5_device(lmono_ctx* ctx, int which, const float4* d_q, int n, int32_t* d_idx, float* d_d2) {
   if (n <= 0) return LMONO_OK;
-  if (getenv("LMONO_KNN_GROUP") && atoi(getenv("LMONO_KNN_GROUP")) == 0) {
+  // same choice of form as lm_map_associate: LMONO_KNN_GROUP=0, or a ctx that runs the throughput forms
+  const char* ge = getenv("LMONO_KNN_GROUP");
+  if (ge ? atoi(ge) == 0 : ctx->batch_n >= LM_THROUGHPUT_BATCH) {
     k_knn5_hook1<<<lm_div_up(n, KNN1_THREADS), KNN1_THREADS, 0, ctx->stream>>>(ctx->d_state, ctx->map[which], which, ctx->d_slot_valid_rank, d_q, n, d_idx, d_d2);
     LM_LAUNCH_CHECK();
     return LMONO_OK;

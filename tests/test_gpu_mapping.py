@@ -64,8 +64,11 @@ def test_import_export_bit_exact(loaded):
         assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
 
 
-def test_knn5_bit_exact(loaded):
+@pytest.mark.parametrize("form", ["latency", "throughput"])
+def test_knn5_bit_exact(loaded, form):
+    """both forms of the search kernel (8 lanes per query / one thread per query) against the oracle's brute force"""
     ctx, om = loaded
+    ctx.set_concurrency_hint(8 if form == "throughput" else 1)
     w = scenario.world()
     from lmono_b200 import synth
     q0, t0 = synth.loop_pose(w, 0.0)
@@ -93,6 +96,43 @@ def test_knn5_bit_exact(loaded):
         # ties among the 6 nearest would make FLANN order-dependent: report, do not hide
         ties = (np.diff(rd[accept], axis=1) == 0).any(axis=1).sum()
         print(f"which={which} accepted={accept.sum()} rejected={rej.sum()} exact-distance ties in top-5={ties}")
+    ctx.set_concurrency_hint(1)
+
+
+@pytest.mark.parametrize("form", ["latency", "throughput"])
+def test_knn5_dense_map_at_cube_corner(gpu_ctx_factory, oracle, form):
+    """Worst case for the cell search: a dense 3-D lattice (one point per 0.4 m voxel: ~65 points within 1 m of a query,
+    far more than the thread-per-query kernel parks in shared memory) around the corner (25, 25, 25) shared by 8 cubes,
+    so that queries see cells straddling cube borders on all three axes (up to 27 cube/cell pairs, 18 runs)."""
+    rng = np.random.default_rng(77)
+    g = np.arange(19.0, 31.0, 0.4, dtype=np.float32) + np.float32(0.2)
+    xx, yy, zz = np.meshgrid(g, g, g, indexing="ij")
+    pts = np.stack([xx.ravel(), yy.ravel(), zz.ravel(), np.zeros(xx.size, np.float32)], 1).astype(np.float32)
+    pts[:, :3] += rng.uniform(-0.15, 0.15, (len(pts), 3)).astype(np.float32)
+    ctx = gpu_ctx_factory()
+    om = oracle.Mapper()
+    for which in (0, 1):
+        ctx.map_import(which, pts)
+        om.import_points(which, pts)
+    ctx.set_concurrency_hint(8 if form == "throughput" else 1)
+    t0 = np.array([25.0, 25.0, 25.0])
+    ctx.map_prepare_window(t0)
+    om.prepare_window(t0)
+    n = 6000
+    q = np.zeros((n, 4), np.float32)
+    q[:, :3] = rng.uniform(21.0, 29.0, (n, 3)).astype(np.float32)
+    q[: n // 3, :3] = (25.0 + rng.uniform(-1.2, 1.2, (n // 3, 3))).astype(np.float32)       # around the shared corner
+    q[n // 3: n // 2, 0] = np.float32(25.0)                                                   # exactly on a cube border
+    q[n // 2: 2 * n // 3, 1] = np.float32(24.99999)
+    for which in (0, 1):
+        assert np.array_equal(ctx.map_export(which, 0).view(np.uint32), om.export(which, 0).view(np.uint32))
+        gi, gd = ctx.knn5(which, q)
+        ri, rd = om.knn5(which, q)
+        accept = rd[:, 4] < 1.0
+        assert accept.sum() > n // 2
+        assert np.array_equal(gi[accept], ri[accept])
+        assert np.array_equal(gd[accept].view(np.uint32), rd[accept].view(np.uint32))
+        assert np.all(~(gd[~accept, 4] < 1.0))
 
 
 def test_knn_brute_matches_kdtree_here(loaded, oracle):
