@@ -289,6 +289,15 @@ int lmono_scan_register(lmono_ctx* ctx, lmono_cloud_view raw, lmono_cloud_out* f
 
 /* test hook: curvature (scanRegistration.cpp:262) and index into the raw input of the first n
  * points of the last sweep's ring-sorted cloud */
+/* Fused sweep: the three A-LOAM stages of one sweep in one call (a host that owns scanRegistration, laserOdometry and
+ * laserMapping of a sequence; replaces the topic hand-offs scanRegistration.cpp:413-441 -> laserOdometry.cpp:511-590 ->
+ * laserMapping.cpp:204-305).  The raw sweep is uploaded once; feature clouds and the odometry pose stay in device
+ * memory between the stages.  Outputs (all optional): q/t_last_curr and q/t_w_curr of the odometry, q/t_w_curr and
+ * q/t_wmap_wodom of the mapping, the three stage reports.  Bit-identical to lmono_scan_register -> lmono_odom_step ->
+ * lmono_map_step(less_sharp, less_flat, odometry pose). */
+int lmono_sweep_step(lmono_ctx* ctx, lmono_cloud_view raw, lmono_pose* odom_last_curr, lmono_pose* odom_w_curr,
+                     lmono_pose* map_w_curr, lmono_pose* wmap_wodom,
+                     lmono_scan_report* scan_report, lmono_odom_report* odom_report, lmono_map_report* map_report);
 int lmono_scan_debug(lmono_ctx* ctx, float* curvature, int32_t* src_index, int32_t n);
 
 /* ------------------------------------------------------------------ L2: laserOdometry */

@@ -367,6 +367,16 @@ class Context:
         return res
 
     # -- laserOdometry
+    def sweep_step(self, raw):
+        """Fused scanRegistration -> laserOdometry -> laserMapping of one raw sweep (lmono_sweep_step).
+        Returns ((q, t) last_curr, (q, t) odometry w_curr, (q, t) mapped w_curr, scan report, odom report, map report)."""
+        raw = np.ascontiguousarray(raw, np.float32)
+        lc, ow, mw, wm = Pose(), Pose(), Pose(), Pose()
+        srep, orep, mrep = ScanReport(), OdomReport(), MapReport()
+        self._chk(self.L.lmono_sweep_step(self._h, view_of(raw), C.byref(lc), C.byref(ow), C.byref(mw), C.byref(wm),
+                                          C.byref(srep), C.byref(orep), C.byref(mrep)), "sweep_step")
+        return lc.as_np(), ow.as_np(), mw.as_np(), srep, orep, mrep
+
     def odom_step(self, sharp, less_sharp, flat, less_flat):
         a, b, c, d = (_xyzi(x) for x in (sharp, less_sharp, flat, less_flat))
         lc, wc, rep = Pose(), Pose(), OdomReport()

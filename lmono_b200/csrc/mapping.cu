@@ -31,7 +31,8 @@ __global__ void k_set_counts(LmMapState* st, int n0, int n1) {
 // every per-step scalar (feature counts, odometry pose, input pointers) enters through this one launch, so the rest
 // of the step is a parameter-free kernel sequence that can be replayed as a CUDA graph
 struct StepArgs { double q[4]; double t[3]; int n0, n1; int set_wmap; int slot; double wq[4]; double wt[3]; const float4* in[2];
-                  const void* src[2]; int stride[2]; int ioff[2]; };
+                  const void* src[2]; int stride[2]; int ioff[2];
+                  const double* pose_src; };    // not NULL: q[4], t[3] of wodom_curr are read from device memory (fused sweep: the odometry stage's result)
 __device__ __forceinline__ void d_apply_step_args(LmMapState* st, const StepArgs& a) {
   st->raw_n[0] = a.n0; st->raw_n[1] = a.n1;
   st->in_ptr[0] = a.in[0]; st->in_ptr[1] = a.in[1];
@@ -41,8 +42,13 @@ __device__ __forceinline__ void d_apply_step_args(LmMapState* st, const StepArgs
     for (int k = 0; k < 4; ++k) st->q_wmap_wodom[k] = a.wq[k];
     for (int k = 0; k < 3; ++k) st->t_wmap_wodom[k] = a.wt[k];
   }
-  for (int k = 0; k < 4; ++k) st->q_wodom_curr[k] = a.q[k];
-  for (int k = 0; k < 3; ++k) st->t_wodom_curr[k] = a.t[k];
+  if (a.pose_src) {
+    for (int k = 0; k < 4; ++k) st->q_wodom_curr[k] = a.pose_src[k];
+    for (int k = 0; k < 3; ++k) st->t_wodom_curr[k] = a.pose_src[4 + k];
+  } else {
+    for (int k = 0; k < 4; ++k) st->q_wodom_curr[k] = a.q[k];
+    for (int k = 0; k < 3; ++k) st->t_wodom_curr[k] = a.t[k];
+  }
 }
 __global__ void k_step_args(LmMapState* st, StepArgs a) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -147,7 +153,7 @@ static int bucket_up(int n, int cap) {
 // one step's inputs as the kernels see them: d[k] = float4 XYZI array in device memory that the step reads (for a
 // fused upload: the ctx's own d_in[k], filled by k_vg_keys from src[k]); src / stride / ioff describe the caller's
 // page-locked AoS buffer (stride 0 = d[k] already holds the data)
-struct LmStepIn { const float4* d[2]; int n[2]; const void* src[2]; int stride[2]; int ioff[2]; };
+struct LmStepIn { const float4* d[2]; int n[2]; const void* src[2]; int stride[2]; int ioff[2]; const double* pose_src; };
 
 static LmStepIn step_in_device(const float4* d_corner, int nc, const float4* d_surf, int ns) {
   LmStepIn in;
@@ -180,8 +186,8 @@ static int resolve_input(lmono_ctx* ctx, lmono_cloud_view v, int which, LmStepIn
 
 static void fill_step_args(StepArgs* a, const LmStepIn& in, const lmono_pose* wodom_curr, const lmono_pose* wmap_in, int slot) {
   memset(a, 0, sizeof(*a));
-  for (int k = 0; k < 4; ++k) a->q[k] = wodom_curr->q[k];
-  for (int k = 0; k < 3; ++k) a->t[k] = wodom_curr->t[k];
+  a->pose_src = in.pose_src;
+  if (wodom_curr) { for (int k = 0; k < 4; ++k) a->q[k] = wodom_curr->q[k]; for (int k = 0; k < 3; ++k) a->t[k] = wodom_curr->t[k]; }
   a->n0 = in.n[0]; a->n1 = in.n[1];
   for (int k = 0; k < 2; ++k) { a->in[k] = in.d[k]; a->src[k] = in.src[k]; a->stride[k] = in.stride[k]; a->ioff[k] = in.ioff[k]; }
   a->slot = slot;
@@ -364,6 +370,49 @@ extern "C" int lmono_map_step_device(lmono_ctx* ctx, const void* d_corner, int32
                                      const lmono_pose* wodom_curr) {
   if (!ctx || !wodom_curr) return LMONO_E_ARG;
   return enqueue_step(ctx, step_in_device((const float4*)d_corner, nc, (const float4*)d_surf, ns), wodom_curr);
+}
+
+// ------------------------------------------------------------------ fused sweep: scanRegistration -> laserOdometry -> laserMapping
+// The reference runs the three stages as three ROS nodes that hand clouds to each other through topics
+// (scanRegistration.cpp:413-441 -> laserOdometry.cpp:195-213,511-590 -> laserMapping.cpp:204-305).  A host that owns all
+// three (one process per sequence, BASELINE config C-4) calls this instead: the raw sweep goes up once, the feature
+// clouds and the odometry pose stay in device memory between the stages, one small read-back in the middle (the feature
+// counts size the next launches) and one at the end.  Results are bit-identical to the three separate calls.
+int lm_scan_upload(lmono_ctx* ctx, lmono_cloud_view raw, const float4** d_in);
+int lm_scan_enqueue(lmono_ctx* ctx, const float4* d_in, int n);
+int lm_scan_fetch(lmono_ctx* ctx, int n_in, int32_t counts[5], lmono_scan_report* report);
+int lm_scan_outputs(lmono_ctx* ctx, const float4** full, const float4** sharp, const float4** less_sharp, const float4** flat,
+                    const float4** less_flat, const int32_t** counts);
+int lm_odom_enqueue_auto(lmono_ctx* ctx, const float4* sharp, int n_sharp, const float4* less_sharp, int n_ls,
+                         const float4* flat, int n_flat, const float4* less_flat, int n_lf, const double** d_pose7);
+int lm_odom_readback(lmono_ctx* ctx);
+int lm_odom_deliver(lmono_ctx* ctx, lmono_pose* last_curr, lmono_pose* w_curr, lmono_odom_report* report);
+
+extern "C" int lmono_sweep_step(lmono_ctx* ctx, lmono_cloud_view raw, lmono_pose* odom_last_curr, lmono_pose* odom_w_curr,
+                                lmono_pose* map_w_curr, lmono_pose* wmap_wodom,
+                                lmono_scan_report* scan_report, lmono_odom_report* odom_report, lmono_map_report* map_report) {
+  if (!ctx) return LMONO_E_ARG;
+  if (raw.n > ctx->max_sweep) return LMONO_E_CAPACITY;
+  int rc;
+  const float4* d_in = nullptr;
+  if ((rc = lm_scan_upload(ctx, raw, &d_in))) return rc;
+  if ((rc = lm_scan_enqueue(ctx, d_in, raw.n))) return rc;
+  int32_t counts[5];
+  if ((rc = lm_scan_fetch(ctx, raw.n, counts, scan_report))) return rc;            // sync #1: n_kept, sharp, less_sharp, flat, less_flat
+  const float4 *sharp, *less_sharp, *flat, *less_flat;
+  if ((rc = lm_scan_outputs(ctx, nullptr, &sharp, &less_sharp, &flat, &less_flat, nullptr))) return rc;
+  if (counts[2] > ctx->max_feat || counts[4] > ctx->max_feat) return LMONO_E_CAPACITY;
+  const double* d_pose7 = nullptr;
+  if ((rc = lm_odom_enqueue_auto(ctx, sharp, counts[1], less_sharp, counts[2], flat, counts[3], less_flat, counts[4], &d_pose7))) return rc;
+  if ((rc = lm_odom_readback(ctx))) return rc;
+  // laserMapping consumes /laser_cloud_corner_last = less-sharp and /laser_cloud_surf_last = less-flat of this sweep
+  // (laserOdometry.cpp:554-590) with /laser_odom_to_init as the prior
+  LmStepIn in = step_in_device(less_sharp, counts[2], less_flat, counts[4]);
+  in.pose_src = d_pose7;
+  if ((rc = enqueue_step(ctx, in, nullptr))) return rc;
+  rc = collect(ctx, map_w_curr, wmap_wodom, map_report);                           // sync #2
+  const int rc2 = lm_odom_deliver(ctx, odom_last_curr, odom_w_curr, odom_report);
+  return rc ? rc : rc2;
 }
 
 extern "C" int lmono_map_collect(lmono_ctx* ctx, lmono_pose* w_curr, lmono_pose* wmap_wodom, lmono_map_report* report) {

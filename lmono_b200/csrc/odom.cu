@@ -297,6 +297,45 @@ int lm_odom_enqueue(lmono_ctx* ctx, const float4* sharp, int n_sharp, const floa
   return LMONO_OK;
 }
 
+// fused sweep (mapping.cu: lmono_sweep_step): the features are the scan stage's device buffers; the result pose
+// (q_w_curr[4], t_w_curr[3], contiguous) is handed to the mapping stage as a device pointer
+int lm_odom_enqueue_auto(lmono_ctx* ctx, const float4* sharp, int n_sharp, const float4* less_sharp, int n_ls,
+                         const float4* flat, int n_flat, const float4* less_flat, int n_lf, const double** d_pose7) {
+  OdomState* s; int rc = odom_state(ctx, &s); if (rc) return rc;
+  if (n_sharp > s->cap || n_ls > s->cap || n_flat > s->cap || n_lf > s->cap) return LMONO_E_CAPACITY;
+  static_assert(offsetof(OdomDev, t_w_curr) == offsetof(OdomDev, q_w_curr) + 4 * sizeof(double), "pose7 layout");
+  if ((rc = lm_odom_enqueue(ctx, sharp, n_sharp, less_sharp, n_ls, flat, n_flat, less_flat, n_lf,
+                            s->h->n_corner_last > 0 ? s->h->n_corner_last : s->cap, s->h->n_surf_last > 0 ? s->h->n_surf_last : s->cap))) return rc;
+  *d_pose7 = s->d->q_w_curr;
+  return LMONO_OK;
+}
+int lm_odom_readback(lmono_ctx* ctx) {
+  OdomState* s; int rc = odom_state(ctx, &s); if (rc) return rc;
+  LM_CUDA(cudaMemcpyAsync(s->h, s->d, sizeof(OdomDev), cudaMemcpyDeviceToHost, ctx->stream));
+  return LMONO_OK;
+}
+static void odom_fill(const OdomDev* h, lmono_pose* last_curr, lmono_pose* w_curr, lmono_odom_report* report) {
+  if (last_curr) { memcpy(last_curr->q, h->para_q, 32); memcpy(last_curr->t, h->para_t, 24); }
+  if (w_curr) { memcpy(w_curr->q, h->q_w_curr, 32); memcpy(w_curr->t, h->t_w_curr, 24); }
+  if (report) {
+    memset(report, 0, sizeof(*report));
+    report->inited = h->do_solve;
+    for (int k = 0; k < 2; ++k) {
+      report->corner_corr[k] = h->corner_corr[k]; report->plane_corr[k] = h->plane_corr[k];
+      report->solve[k].iterations = h->solve[k].iterations; report->solve[k].num_successful = h->solve[k].num_successful;
+      report->solve[k].termination = h->solve[k].termination; report->solve[k].num_factors = h->solve[k].num_factors;
+      report->solve[k].initial_cost = h->solve[k].initial_cost; report->solve[k].final_cost = h->solve[k].final_cost;
+    }
+  }
+}
+// after a stream synchronisation that followed lm_odom_readback
+int lm_odom_deliver(lmono_ctx* ctx, lmono_pose* last_curr, lmono_pose* w_curr, lmono_odom_report* report) {
+  OdomState* s = (OdomState*)ctx->odom_state;
+  if (!s) return LMONO_E_STATE;
+  odom_fill(s->h, last_curr, w_curr, report);
+  return LMONO_OK;
+}
+
 extern "C" int lmono_odom_step(lmono_ctx* ctx, lmono_cloud_view sharp, lmono_cloud_view less_sharp, lmono_cloud_view flat,
                                lmono_cloud_view less_flat, lmono_pose* last_curr, lmono_pose* w_curr, lmono_odom_report* report) {
   if (!ctx) return LMONO_E_ARG;

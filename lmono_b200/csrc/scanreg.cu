@@ -560,6 +560,36 @@ int lm_scan_outputs(lmono_ctx* ctx, const float4** full, const float4** sharp, c
   return LMONO_OK;
 }
 
+// fused sweep (mapping.cu: lmono_sweep_step): upload into the stage's input buffer; read the counts + report back
+int lm_scan_upload(lmono_ctx* ctx, lmono_cloud_view raw, const float4** d_in) {
+  ScanState* s; int rc = scan_state(ctx, &s); if (rc) return rc;
+  LM_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  if ((rc = lm_upload_cloud(ctx, raw, ctx->d_raw[2], s->d_in, nullptr))) return rc;
+  *d_in = s->d_in;
+  return LMONO_OK;
+}
+static void scan_fill_report(lmono_ctx* ctx, const ScanMeta* m, int n_in, lmono_scan_report* report) {
+  memset(report, 0, sizeof(*report));
+  report->n_in = n_in; report->n_kept = m->n_kept;
+  report->n_sharp = m->out_n[0]; report->n_less_sharp = m->out_n[1]; report->n_flat = m->out_n[2]; report->n_less_flat = m->out_n[3];
+  for (int r = 0; r < 64; ++r) {
+    report->ring_start[r] = r < ctx->prm.scan_line ? m->ring_start[r] + 5 : 0;
+    report->ring_end[r] = r < ctx->prm.scan_line ? m->ring_start[r + 1] - 6 : 0;
+  }
+  report->start_ori = m->start_ori; report->end_ori = m->end_ori;
+}
+int lm_scan_fetch(lmono_ctx* ctx, int n_in, int32_t counts[5], lmono_scan_report* report) {
+  ScanState* s; int rc = scan_state(ctx, &s); if (rc) return rc;
+  LM_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  LM_CUDA(cudaMemcpyAsync(s->h_meta, s->d_meta, sizeof(ScanMeta), cudaMemcpyDeviceToHost, ctx->stream));
+  LM_CUDA(cudaStreamSynchronize(ctx->stream));
+  const ScanMeta* m = s->h_meta;
+  counts[0] = m->n_kept; for (int k = 0; k < 4; ++k) counts[1 + k] = m->out_n[k];
+  if (report) { scan_fill_report(ctx, m, n_in, report); float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); report->ms_gpu = ms; }
+  if (m->fault) { fprintf(stderr, "[lmono_b200] scan_register fault bits 0x%x (ring or sector larger than the kernel limit)\n", m->fault); return LMONO_E_DEVICE; }
+  return LMONO_OK;
+}
+
 extern "C" int lmono_scan_register(lmono_ctx* ctx, lmono_cloud_view raw, lmono_cloud_out* full, lmono_cloud_out* sharp,
                                    lmono_cloud_out* less_sharp, lmono_cloud_out* flat, lmono_cloud_out* less_flat,
                                    int32_t* labels, lmono_scan_report* report) {

@@ -36,6 +36,14 @@ for k, raw in enumerate(raws):
     if k >= 5:
         G["scan"].append(r["report"].ms_gpu); G["odom"].append(orep.ms_gpu); G["map"].append(mrep.ms_gpu if hasattr(mrep, "ms_gpu") else float("nan"))
         T["scan"].append(t1 - t0); T["odom"].append(t2 - t1); T["map"].append(t3 - t2); T["color"].append(t4 - t3)
+ctx2 = api.Context(device=0)
+F = []
+for k, raw in enumerate(raws):
+    t0 = time.perf_counter()
+    ctx2.sweep_step(raw)
+    if k >= 5:
+        F.append(time.perf_counter() - t0)
+print(f"fused  {1e3 * float(np.mean(F)):8.3f} ms per sweep (min {1e3 * min(F):.3f}) -> {1.0 / float(np.mean(F)):.0f} sweeps/s for one sequence (lmono_sweep_step)")
 tot = 0.0
 for k, v in T.items():
     ms = 1e3 * float(np.mean(v))

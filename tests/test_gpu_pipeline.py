@@ -51,6 +51,24 @@ def test_three_stage_chain_matches_oracle(gpu_ctx_factory, oracle):
     print("worst mapped-pose deviation vs oracle over 8 sweeps: %.3e m" % worst)
 
 
+def test_fused_sweep_equals_three_calls(gpu_ctx_factory):
+    """lmono_sweep_step (features and odometry pose stay in device memory) against the three separate calls: same bits"""
+    a, b = gpu_ctx_factory(), gpu_ctx_factory()
+    for k, (raw, q, t) in enumerate(_raw_sweeps(8, seed=4)):
+        r, (oq, ot), (mq, mt), orep, mrep = _chain_gpu(a, raw)
+        (lq, lt), (foq, fot), (fmq, fmt), srep, forep, fmrep = b.sweep_step(raw)
+        assert (srep.n_kept, srep.n_sharp, srep.n_less_sharp, srep.n_flat, srep.n_less_flat) == \
+               (len(r["full"]), len(r["sharp"]), len(r["less_sharp"]), len(r["flat"]), len(r["less_flat"]))
+        assert np.array_equal(foq, oq) and np.array_equal(fot, ot), k
+        assert np.array_equal(fmq, mq) and np.array_equal(fmt, mt), k
+        assert list(forep.corner_corr) == list(orep.corner_corr) and list(forep.plane_corr) == list(orep.plane_corr)
+        assert list(fmrep.corner_num) == list(mrep.corner_num) and list(fmrep.surf_num) == list(mrep.surf_num)
+        assert (fmrep.corner_from_map, fmrep.surf_from_map, fmrep.optimized) == (mrep.corner_from_map, mrep.surf_from_map, mrep.optimized)
+    for w in (0, 1):
+        assert np.array_equal(a.map_export(w, 1).view(np.uint32), b.map_export(w, 1).view(np.uint32))
+    assert fmrep.optimized == 1
+
+
 def test_cpp_replay_harness_matches_python_binding(gpu_ctx_factory, tmp_path):
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "nodes")], check=True)
     sweeps = _raw_sweeps(4, seed=6)
