@@ -493,6 +493,33 @@ def run_ours(args):
         "registration_error_m": reg_err,
     }
 
+    # ---- the whole A-LOAM chain of one sequence (BASELINE config C-4 "fused L1 -> L2 -> L3"): raw 64-ring sweeps of
+    # ~113 k points through lmono_sweep_step (scanRegistration -> laserOdometry -> laserMapping, host sweep in, poses out)
+    if rank == 0 and not args.no_pipeline:
+        try:
+            wld = synth.make_world()
+            rng_p = np.random.default_rng(2)
+            raws = []
+            for k in range(30):
+                q_, t_ = synth.loop_pose(wld, 1.0 * k)
+                raws.append(np.ascontiguousarray(synth.raycast_sweep(wld, q_, t_, 64, 1875, rng_p), np.float32))
+            pctx = api.Context(device=local, stream=main.cuda_stream)
+            tp_ = []
+            for k, raw in enumerate(raws):
+                t0 = time.perf_counter()
+                out_ = pctx.sweep_step(raw)
+                if k >= 6:
+                    tp_.append(time.perf_counter() - t0)
+            truth = float(np.linalg.norm(synth.loop_pose(wld, 29.0)[1] - synth.loop_pose(wld, 0.0)[1]))
+            drift = float(np.linalg.norm(out_[2][1])) - truth      # mapped translation of the last sweep vs the true chord
+            line["fused_sweep"] = {"sweeps_per_s": 1.0 / float(np.mean(tp_)), "ms_per_sweep": 1e3 * float(np.mean(tp_)),
+                                   "points_per_sweep": int(len(raws[0])), "sequences": 1, "travelled_minus_truth_m": drift,
+                                   "what": "lmono_sweep_step: raw HDL-64 sweep (pageable host memory) -> scanRegistration -> laserOdometry -> "
+                                           "laserMapping -> poses on the host; one sequence, synchronous calls, wall clock"}
+            pctx.close()
+        except Exception as e:                                      # noqa: BLE001  (never lose the headline line to the extra leg)
+            line["fused_sweep"] = {"error": str(e)}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
     if rank == 0 and world == 1 and not args.no_cpu:
         import oracle_lib as O
@@ -527,6 +554,7 @@ def main():
     ap.add_argument("--sequences", type=int, default=8, help="independent sequences per GPU (one ctx + stream each)")
     ap.add_argument("--more-sequences", type=int, default=16, help="extra value leg with this many sequences per GPU (0 = skip)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the fused-sweep (scanRegistration -> odometry -> mapping) leg")
     ap.add_argument("--cpu-steps", type=int, default=60)
     args = ap.parse_args()
     if args.impl == "reference":
