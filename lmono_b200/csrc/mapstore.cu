@@ -368,10 +368,10 @@ __global__ void __launch_bounds__(256) k_insert_heads(LmMapState* __restrict__ s
   M.slab_dirty[sid] = 1;
 }
 
-__global__ void __launch_bounds__(256) k_insert_write(LmMapType M0, LmMapType M1, const unsigned long long* __restrict__ sorted,
-                                                      const int32_t* __restrict__ n_ins, const float4* __restrict__ world0,
-                                                      const float4* __restrict__ world1, const int32_t* __restrict__ slot_first,
-                                                      const int32_t* __restrict__ slot_base, const int32_t* __restrict__ slot_len) {
+__device__ __forceinline__ void d_insert_write(const LmMapType& M0, const LmMapType& M1, const unsigned long long* __restrict__ sorted,
+                                               const int32_t* __restrict__ n_ins, const float4* __restrict__ world0,
+                                               const float4* __restrict__ world1, const int32_t* __restrict__ slot_first,
+                                               const int32_t* __restrict__ slot_base, const int32_t* __restrict__ slot_len) {
   const int n = *n_ins;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
@@ -419,9 +419,8 @@ __device__ __forceinline__ bool d_rf_slab(const LmMapState* st, const LmMapType&
 
 // per step: classify the window cubes once.  whole list = flagged slabs (re-voxelised as a whole), active list = slabs
 // with a tail (their meta record is armed here: ns, nt, cur, sid).  One CTA.
-__global__ void __launch_bounds__(256) k_rf_plan(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, int32_t* __restrict__ plan,
-                                                 RfMeta* __restrict__ meta_all, int32_t* __restrict__ work_n) {
-  __shared__ int ws[33];
+__device__ __forceinline__ void d_rf_plan(LmMapState* __restrict__ st, const LmMapType& M0, const LmMapType& M1, int32_t* __restrict__ plan,
+                                          RfMeta* __restrict__ meta_all, int32_t* __restrict__ work_n, int* ws /* shared int[33] */) {
   const int e = threadIdx.x;
   const int ty = e / LM_WIN_MAX, r = e - ty * LM_WIN_MAX;
   int sid = -1, n = 0, ns = 0, cur = 0;
@@ -446,6 +445,24 @@ __global__ void __launch_bounds__(256) k_rf_plan(LmMapState* __restrict__ st, Lm
   if (active) plan[LM_PLAN_ACTIVE + apos] = e;
   if (threadIdx.x == 0) plan[LM_PLAN_ACTIVE_N] = tot;
   if (threadIdx.x == 0) *work_n = 0;
+}
+
+__global__ void __launch_bounds__(256) k_rf_plan(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, int32_t* __restrict__ plan,
+                                                 RfMeta* __restrict__ meta_all, int32_t* __restrict__ work_n) {
+  __shared__ int ws[33];
+  d_rf_plan(st, M0, M1, plan, meta_all, work_n, ws);
+}
+
+// k_insert_write + the refilter plan in one launch: the extra last CTA plans while the others copy the new points (the
+// plan only reads what k_insert_heads finalised)
+__global__ void __launch_bounds__(256) k_insert_write_plan(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, const unsigned long long* __restrict__ sorted,
+                                                           const int32_t* __restrict__ n_ins, const float4* __restrict__ world0,
+                                                           const float4* __restrict__ world1, const int32_t* __restrict__ slot_first,
+                                                           const int32_t* __restrict__ slot_base, const int32_t* __restrict__ slot_len,
+                                                           int32_t* __restrict__ plan, RfMeta* __restrict__ meta_all, int32_t* __restrict__ work_n) {
+  __shared__ int ws[33];
+  if (blockIdx.x == gridDim.x - 1) { d_rf_plan(st, M0, M1, plan, meta_all, work_n, ws); return; }
+  d_insert_write(M0, M1, sorted, n_ins, world0, world1, slot_first, slot_base, slot_len);
 }
 
 // per cube with a tail, one CTA: tail element j opens a NEW voxel iff it is the first of its key run and the key is absent
@@ -807,8 +824,9 @@ int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf,
     k_insert_heads<<<blocks, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_sort_c, n_ins,
                                                     ctx->d_world[0], ctx->d_world[1], ctx->d_slot_first, ctx->d_slot_base, slot_len);
     LM_LAUNCH_CHECK();
-    k_insert_write<<<blocks, 256, 0, ctx->stream>>>(ctx->map[0], ctx->map[1], ctx->d_sort_c, n_ins, ctx->d_world[0],
-                                                    ctx->d_world[1], ctx->d_slot_first, ctx->d_slot_base, slot_len);
+    k_insert_write_plan<<<blocks + 1, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_sort_c, n_ins, ctx->d_world[0],
+                                                             ctx->d_world[1], ctx->d_slot_first, ctx->d_slot_base, slot_len,
+                                                             ctx->d_rf_plan, (RfMeta*)ctx->d_rf_meta, ctx->d_rf_work);
     LM_LAUNCH_CHECK();
   }
   lm_prof_end(ctx);
@@ -816,9 +834,23 @@ int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf,
   const int cap_max = ctx->map[0].cap > ctx->map[1].cap ? ctx->map[0].cap : ctx->map[1].cap;
   RfMeta* meta = (RfMeta*)ctx->d_rf_meta;
   int32_t* work_n = ctx->d_rf_work; int32_t* work = ctx->d_rf_work + 4;
-  k_rf_plan<<<1, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan, meta, work_n);
-  LM_LAUNCH_CHECK();
+  if (n_max <= 0) {
+    k_rf_plan<<<1, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan, meta, work_n);
+    LM_LAUNCH_CHECK();
+  }
+  // flagged slabs (rare) are re-voxelised as a whole beside the tail merge of the others: disjoint slabs, so inside a
+  // graph capture the kernel is a parallel branch
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(ctx->stream, &cap);
+  const bool fork = cap == cudaStreamCaptureStatusActive && ctx->side_stream != nullptr && !ctx->tl_on;
+  cudaStream_t main_stream = ctx->stream;
+  if (fork) {
+    LM_CUDA(cudaEventRecord(ctx->ev_side0, main_stream));
+    LM_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_side0, 0));
+    ctx->stream = ctx->side_stream;
+  }
   k_refilter_whole<<<RF_WHOLE_GRID, 1024, kRefilterSmem, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan);
+  if (fork) { ctx->stream = main_stream; LM_CUDA(cudaEventRecord(ctx->ev_side1, ctx->side_stream)); }
   LM_LAUNCH_CHECK();
   k_rf_tailscan<<<RF_ACT_GRID, RF_TS_THREADS, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan, ctx->d_rf_nvx, ctx->d_rf_tlb, meta, cap_max, work_n, work);
   LM_LAUNCH_CHECK();
@@ -828,6 +860,7 @@ int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf,
   LM_LAUNCH_CHECK();
   k_rf_scatter<<<RF_GRID, 256, 0, ctx->stream>>>(ctx->map[0], ctx->map[1], meta, work_n, work);
   LM_LAUNCH_CHECK();
+  if (fork) LM_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_side1, 0));
   lm_prof_end(ctx);
   return LMONO_OK;
 }
