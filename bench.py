@@ -420,7 +420,7 @@ def run_ours(args):
     nfac = rep.corner_num[1] + rep.surf_num[1]
     evals = sum(s_.iterations + 1 for s_ in rep.solve)
     ncu = {}
-    ncu_file = "ncu_r01_h_full_metrics.json"
+    ncu_file = "ncu_r01_j_full_metrics.json"
     try:
         for l in json.load(open(os.path.join(ROOT, "profiles", ncu_file)))["launches"]:
             ncu.setdefault(l["kernel"], []).append(l)
