@@ -280,7 +280,8 @@ constexpr int SCR_INT_BYTES = SC_RING_MAX * 4;                        // intensi
 constexpr int SCR_PICK_BYTES = SC_RING_MAX + 32;                      // picked flags
 constexpr int SCR_LABEL_BYTES = SC_RING_MAX;                          // labels (int8)
 constexpr int SCR_LF_BYTES = SC_RING_MAX * 2;                         // less-flat local indices (uint16)
-constexpr int SCR_TOTAL = SCR_SEC_BYTES + SCR_XYZ_BYTES + SCR_INT_BYTES + SCR_PICK_BYTES + SCR_LABEL_BYTES + SCR_LF_BYTES + 256;
+constexpr int SCR_GAP_BYTES = SC_RING_MAX;                            // gap[i] = |p[i] - p[i-1]|^2 > 0.05 (the +-5 suppression test), precomputed in parallel
+constexpr int SCR_TOTAL = SCR_SEC_BYTES + SCR_XYZ_BYTES + SCR_INT_BYTES + SCR_PICK_BYTES + SCR_LABEL_BYTES + SCR_LF_BYTES + 256 + SCR_GAP_BYTES;
 
 __global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __restrict__ full, const float* __restrict__ curv,
                                                              ScanMeta* __restrict__ meta, int32_t* __restrict__ label_out,
@@ -294,6 +295,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __res
   signed char* label = reinterpret_cast<signed char*>(picked + SCR_PICK_BYTES);
   uint16_t* lf = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(label) + SCR_LABEL_BYTES);
   int* ws = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(lf) + SCR_LF_BYTES);     // [64]
+  unsigned char* gap = reinterpret_cast<unsigned char*>(ws) + 256;                            // [SC_RING_MAX]
   __shared__ int s_vg[8];
   __shared__ float s_mn[3][SC_THREADS / 32], s_mx[3][SC_THREADS / 32];
 
@@ -312,6 +314,11 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __res
     xyz[i * 3] = p.x; xyz[i * 3 + 1] = p.y; xyz[i * 3 + 2] = p.z; inten[i] = p.w;
     picked[i] = 0; label[i] = 0;
   }
+  __syncthreads();
+  // the serial greedy pick below tests |p[i] - p[i-1]|^2 > 0.05 up to ten times per pick (:319-342, 365-388): the test
+  // is a pure function of two neighbours, so every thread evaluates its share once here and the one picking thread only
+  // reads a byte ((a - b)^2 == (b - a)^2 exactly, one array serves both walking directions)
+  for (int i = threadIdx.x; i < L; i += blockDim.x) gap[i] = (i > 0 && d_gap_exceeds(xyz, i, i - 1)) ? 1 : 0;
   // :284-288 six sector sorts, one warp each, (curvature, index) ascending
   if (wid < 6) {
     const int sp = S + (E - S) * wid / 6, ep = S + (E - S) * (wid + 1) / 6 - 1;
@@ -345,8 +352,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __res
         else if (largest <= 20) { label[li] = 1; out[2 + n_ls++] = ind; }
         else break;
         picked[li] = 1;
-        for (int l = 1; l <= 5; l++) { if (d_gap_exceeds(xyz, li + l, li + l - 1)) break; picked[li + l] = 1; }
-        for (int l = -1; l >= -5; l--) { if (d_gap_exceeds(xyz, li + l, li + l + 1)) break; picked[li + l] = 1; }
+        for (int l = 1; l <= 5; l++) { if (gap[li + l]) break; picked[li + l] = 1; }
+        for (int l = -1; l >= -5; l--) { if (gap[li + l + 1]) break; picked[li + l] = 1; }
       }
       int smallest = 0;
       for (int k = 0; k < len; ++k) {
@@ -358,8 +365,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __res
         smallest++;
         if (smallest >= 4) break;                                             // :359-362
         picked[li] = 1;
-        for (int l = 1; l <= 5; l++) { if (d_gap_exceeds(xyz, li + l, li + l - 1)) break; picked[li + l] = 1; }
-        for (int l = -1; l >= -5; l--) { if (d_gap_exceeds(xyz, li + l, li + l + 1)) break; picked[li + l] = 1; }
+        for (int l = 1; l <= 5; l++) { if (gap[li + l]) break; picked[li + l] = 1; }
+        for (int l = -1; l >= -5; l--) { if (gap[li + l + 1]) break; picked[li + l] = 1; }
       }
       pick_cnt[r * 18 + j * 3 + 0] = n_sharp; pick_cnt[r * 18 + j * 3 + 1] = n_ls; pick_cnt[r * 18 + j * 3 + 2] = n_flat;
     }

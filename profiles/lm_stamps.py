@@ -1,3 +1,5 @@
+"""In-kernel %globaltimer stamps of the last LM solve of a registration (k_lm_solve_cluster): evaluation, block
+reduction + DSMEM push, cluster barrier, controller, per pass."""
 import sys, ctypes as C, numpy as np
 sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
 import torch
@@ -20,13 +22,3 @@ for e in range(5):
     b=a[8+8*e:12+8*e]
     prev = a[1] if e==0 else a[11+8*(e-1)]
     print(e, "eval", b[0]-prev, "reduce", b[1]-b[0], "cluster", b[2]-b[1], "control", b[3]-b[2])
-out=(C.c_uint64*4096)()
-ctx.L.lmono_debug_stamps(ctx._h,out,4096)
-a=np.array(out[:],dtype=np.int64)[256:256+150*8].reshape(150,8)
-t0=a[:,0].min()
-print("refilter: CTA start spread", a[:,0].max()-t0)
-act=[i for i in range(150) if a[i,6]>0]
-print("active CTAs", len(act))
-for i in sorted(act, key=lambda i:-(a[i,7]-a[i,0]))[:12]:
-    r=a[i]
-    print(f"cta {i:3d} ty {i//75} ns {r[5]:6d} nt {r[6]:5d} | keys {r[1]-r[0]:6d} sort {r[2]-r[1]:6d} merge {r[3]-r[2]:6d} verify {r[4]-r[3]:6d} index {r[7]-r[4]:6d} | total {r[7]-r[0]:6d} end@{r[7]-t0}")
