@@ -36,7 +36,7 @@ struct OdomState {
   int cap;
 };
 
-constexpr int NN_QB = 64, NN_SUB = 4, NN_TILE = 256, NN_CHUNK = 4096;
+constexpr int NN_QB = 64, NN_SUB = 4, NN_TILE = 256, NN_CHUNK = 1024;     // 1024 targets per CTA: ~28 x 20 CTAs for an HDL-64 sweep instead of 7 x 20 long ones
 
 __global__ void k_odom_begin(OdomDev* o, int n_sharp, int n_ls, int n_flat, int n_lf) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
