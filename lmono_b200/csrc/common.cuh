@@ -18,7 +18,7 @@ constexpr int LM_MAX_VALID = 125;                 // :85 (<=75 used)
 // each side) spans 26 cells per axis.
 constexpr int LM_CELLS_AXIS = 26;
 constexpr int LM_NCELL = LM_CELLS_AXIS * LM_CELLS_AXIS * LM_CELLS_AXIS;   // 17576
-constexpr int LM_SORT_TILE = 2048;                // elements per CTA in the global tile sort
+constexpr int LM_SORT_TILE = 1024;                // elements per CTA in the global tile sort (1024: twice the CTAs of 2048, each less than half the network)
 constexpr int LM_SORT_MAXSEG = 2;                 // independent segments sorted by one pair of launches
 constexpr int LM_TAIL_TILE = 16384;               // max points of a slab the whole-slab fallback refilter can re-voxelise (smem sort)
 constexpr int LM_RF_CHUNK = 1024;                 // points per CTA in the chunked refilter kernels

@@ -1,7 +1,7 @@
 // Device sort of unique 64-bit keys whose counts live in device memory; up to LM_SORT_MAXSEG
 // independent segments per call (e.g. the corner and the surf VoxelGrid of one sweep share launches).
 // Two launches, no host synchronisation:
-//   k_sort_tiles : each CTA bitonic-sorts one 2048-key tile held in registers (8 keys/thread x 256
+//   k_sort_tiles : each CTA bitonic-sorts one 1024-key tile held in registers (4 keys/thread x 256
 //                  threads: 3 in-thread + 5 warp-shuffle partner distances, only 6 of the 66 stages go
 //                  through shared memory).  Small tiles on many SMs: the network is issue-bound, so
 //                  16 k keys on 8 SMs finish in a fraction of the time of 4 SMs x 4096.
@@ -16,9 +16,9 @@
 // unstable std::sort.
 #include "common.cuh"
 
-constexpr int ST_THREADS = 512;
+constexpr int ST_THREADS = 256;
 constexpr int ST_ITEMS = LM_SORT_TILE / ST_THREADS;
-static_assert(LM_SORT_TILE == 2048 && ST_ITEMS == 4, "tile geometry");
+static_assert(LM_SORT_TILE == 1024 && ST_ITEMS == 4, "tile geometry");
 
 __global__ void __launch_bounds__(ST_THREADS) k_sort_tiles(LmSortSegs sg, int dst_is_tmp) {
   __shared__ unsigned long long s[LM_SORT_TILE];
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) k_merge_ranks(LmSortSegs sg, int run, int
 // accesses per key is what the global-memory searches cost (~0.15 us each on B200), so each CTA first copies
 // ALL runs of its segment into shared memory (<= 12 x 16 KB, coalesced, one L2 pass) and ranks its 1024 keys
 // against them there (~30-cycle accesses).
-constexpr int LM_MERGE_SMEM_RUNS = 12;
+constexpr int LM_MERGE_SMEM_RUNS = 24;
 constexpr int MS_THREADS = 1024;
 
 __global__ void __launch_bounds__(MS_THREADS, 1) k_merge_ranks_smem(LmSortSegs sg, int src_is_tmp) {
@@ -105,14 +105,23 @@ __global__ void __launch_bounds__(MS_THREADS, 1) k_merge_ranks_smem(LmSortSegs s
   const unsigned long long key = s_runs[e];
   const int my_run = e / LM_SORT_TILE;
   int rank = e - my_run * LM_SORT_TILE;
-  for (int t = 0; t < nruns; ++t) {
-    if (t == my_run) continue;
-    const unsigned long long* a = s_runs + t * LM_SORT_TILE;     // padded with ~0ULL: no length checks needed
-    int pos = 0;
+  // four runs at a time, their binary searches interleaved step by step (independent shared-memory loads in flight
+  // instead of one chain of ~30-cycle accesses per run); runs are padded with ~0ULL: no length checks
+  for (int t0 = 0; t0 < nruns; t0 += 4) {
+    const unsigned long long* a[4];
+    int pos[4] = { 0, 0, 0, 0 };
 #pragma unroll
-    for (int s = LM_SORT_TILE / 2; s > 0; s >>= 1) if (a[pos + s - 1] < key) pos += s;
-    pos += (a[pos] < key);                                        // tile of 2048: 11 halvings + the last element
-    rank += pos;
+    for (int u = 0; u < 4; ++u) a[u] = s_runs + min(t0 + u, nruns - 1) * LM_SORT_TILE;
+#pragma unroll
+    for (int s = LM_SORT_TILE / 2; s > 0; s >>= 1) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) if (a[u][pos[u] + s - 1] < key) pos[u] += s;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      pos[u] += (a[u][pos[u]] < key);                              // 10 halvings + the last element
+      if (t0 + u < nruns && t0 + u != my_run) rank += pos[u];
+    }
   }
   dst[rank] = key;
 }
