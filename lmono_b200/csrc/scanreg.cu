@@ -309,10 +309,15 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __res
   if (L > SC_RING_MAX) { if (threadIdx.x == 0) atomicOr(&meta->fault, 1u); return; }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
-  for (int i = threadIdx.x; i < L; i += blockDim.x) {
-    const float4 p = full[rs + i];
-    xyz[i * 3] = p.x; xyz[i * 3 + 1] = p.y; xyz[i * 3 + 2] = p.z; inten[i] = p.w;
-    picked[i] = 0; label[i] = 0;
+  for (int i0 = threadIdx.x; i0 < L; i0 += 4 * SC_THREADS) {      // four loads in flight per thread, then the shared-memory stores
+    float4 p[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int i = i0 + u * SC_THREADS; if (i < L) p[u] = full[rs + i]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * SC_THREADS;
+      if (i < L) { xyz[i * 3] = p[u].x; xyz[i * 3 + 1] = p[u].y; xyz[i * 3 + 2] = p[u].z; inten[i] = p[u].w; picked[i] = 0; label[i] = 0; }
+    }
   }
   __syncthreads();
   // the serial greedy pick below tests |p[i] - p[i-1]|^2 > 0.05 up to ten times per pick (:319-342, 365-388): the test

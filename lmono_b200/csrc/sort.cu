@@ -98,7 +98,16 @@ __global__ void __launch_bounds__(MS_THREADS, 1) k_merge_ranks_smem(LmSortSegs s
   const unsigned long long* __restrict__ src = (src_is_tmp ? sg.tmp : sg.out) + sg.off[seg];
   unsigned long long* __restrict__ dst = (src_is_tmp ? sg.out : sg.tmp) + sg.off[seg];
   const int nruns = (n + LM_SORT_TILE - 1) / LM_SORT_TILE;
-  for (int i = threadIdx.x; i < nruns * LM_SORT_TILE; i += MS_THREADS) s_runs[i] = i < n ? src[i] : ~0ULL;
+  // stage every run of the segment: eight independent loads in flight per thread (a plain copy loop waits for each
+  // load before it issues the next one: ~16 dependent L2 round trips for a 16 k-key segment)
+  const int total = nruns * LM_SORT_TILE;
+  for (int i0 = threadIdx.x; i0 < total; i0 += 8 * MS_THREADS) {
+    unsigned long long v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int i = i0 + u * MS_THREADS; v[u] = i < n ? src[i] : ~0ULL; }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int i = i0 + u * MS_THREADS; if (i < total) s_runs[i] = v[u]; }
+  }
   __syncthreads();
   const int e = e0 + threadIdx.x;
   if (e >= n) return;
