@@ -169,7 +169,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -185,7 +185,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     peaks = {}
@@ -537,7 +536,7 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": ncpu / dt, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": f"{ncpu} registrations of the same workload on 1 host thread (the reference nodes are single-threaded)"}
     if rank == 0:
-        print(json.dumps(line), flush=True)          # before any teardown: a crash while freeing must not eat the result
+        emit(line)                                   # before any teardown: a crash while freeing must not eat the result
     try:
         batch.close()
         if world > 1:
@@ -546,7 +545,25 @@ def run_ours(args):
         print(f"[bench] teardown: {e}", file=sys.stderr)
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line of this run, on the process's original stdout"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    # stdout carries exactly one JSON line: whatever libraries print while we run (NCCL's version banner, ...) goes to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
