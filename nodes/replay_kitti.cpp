@@ -26,7 +26,8 @@ static bool read_bin(const std::string& path, std::vector<float>& buf) {
 #define CHECK(expr) do { int _rc = (expr); if (_rc != LMONO_OK) { fprintf(stderr, "%s -> %d (%s)\n", #expr, _rc, lmono_strerror(_rc)); return 2; } } while (0)
 
 int main(int argc, char** argv) {
-  if (argc < 3) { fprintf(stderr, "usage: %s <dir with 000000.bin ...> <n_sweeps> [scan_line=64] [minimum_range=5]\n", argv[0]); return 1; }
+  if (argc < 3) { fprintf(stderr, "usage: %s <dir with 000000.bin ...> <n_sweeps> [scan_line=64] [minimum_range=5] [fused]\n", argv[0]); return 1; }
+  const bool fused = argc > 5 && strcmp(argv[5], "fused") == 0;     // one lmono_sweep_step per sweep instead of the three stage calls
   const std::string dir = argv[1];
   const int n_sweeps = atoi(argv[2]);
   lmono_params prm;
@@ -43,6 +44,16 @@ int main(int argc, char** argv) {
     const int n = static_cast<int>(raw.size() / 4);
     full.resize(static_cast<size_t>(n) * 4 + 4); less_flat.resize(static_cast<size_t>(n) * 4 + 4); registered.resize(static_cast<size_t>(n) * 4 + 4);
     lmono_cloud_view v_raw = { raw.data(), n, 16, 12 };
+    if (fused) {
+      lmono_pose last_curr, odom, mapped, wm; lmono_scan_report srep; lmono_odom_report orep; lmono_map_report mrep;
+      CHECK(lmono_sweep_step(ctx, v_raw, &last_curr, &odom, &mapped, &wm, &srep, &orep, &mrep));
+      printf("%d  %.9f %.9f %.9f %.9f %.6f %.6f %.6f  %.9f %.9f %.9f %.9f %.6f %.6f %.6f  kept %d sharp %d flat %d corr %d %d map %d %d opt %d\n",
+             k, odom.q[0], odom.q[1], odom.q[2], odom.q[3], odom.t[0], odom.t[1], odom.t[2],
+             mapped.q[0], mapped.q[1], mapped.q[2], mapped.q[3], mapped.t[0], mapped.t[1], mapped.t[2],
+             srep.n_kept, srep.n_sharp, srep.n_flat, orep.corner_corr[1], orep.plane_corr[1],
+             mrep.corner_from_map, mrep.surf_from_map, mrep.optimized);
+      continue;
+    }
     lmono_cloud_out o_full = { full.data(), n, 16, 12, 0 }, o_sharp = { sharp.data(), 64 * 12, 16, 12, 0 },
                     o_ls = { less_sharp.data(), 64 * 120, 16, 12, 0 }, o_flat = { flat.data(), 64 * 24, 16, 12, 0 },
                     o_lf = { less_flat.data(), n, 16, 12, 0 };

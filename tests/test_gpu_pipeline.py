@@ -74,9 +74,13 @@ def test_cpp_replay_harness_matches_python_binding(gpu_ctx_factory, tmp_path):
     sweeps = _raw_sweeps(4, seed=6)
     for k, (raw, _, _) in enumerate(sweeps):
         raw.astype(np.float32).tofile(tmp_path / f"{k:06d}.bin")
-    out = subprocess.run([os.path.join(ROOT, "nodes", "replay_kitti"), str(tmp_path), "4"], check=True, capture_output=True, text=True).stdout
+    exe = os.path.join(ROOT, "nodes", "replay_kitti")
+    out = subprocess.run([exe, str(tmp_path), "4"], check=True, capture_output=True, text=True).stdout
     lines = [l.split() for l in out.strip().splitlines()]
     assert len(lines) == 4
+    # the same sweeps through one lmono_sweep_step each: identical lines
+    out_f = subprocess.run([exe, str(tmp_path), "4", "64", "5", "fused"], check=True, capture_output=True, text=True).stdout
+    assert out_f == out
     ctx = gpu_ctx_factory()
     for k, (raw, _, _) in enumerate(sweeps):
         _, (oq, ot), (mq, mt), _, _ = _chain_gpu(ctx, raw)
