@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(256) k_insert_prepare(LmMapState* __restrict__
                                                         const float4* __restrict__ stack1, float4* __restrict__ world0,
                                                         float4* __restrict__ world1, unsigned long long* __restrict__ comp,
                                                         int32_t* __restrict__ n_ins, float leaf0, float inv_leaf0, float leaf1, float inv_leaf1,
-                                                        int transform_update) {
+                                                        int transform_update, const int32_t* __restrict__ slot_valid_rank) {
   const int n0 = st->stack_n[0], n1 = st->stack_n[1];
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e == 0) *n_ins = n0 + n1;
@@ -325,7 +325,10 @@ __global__ void __launch_bounds__(256) k_insert_prepare(LmMapState* __restrict__
       d_shard_keep(pw, ty == 0 ? leaf0 : leaf1, ty == 0 ? inv_leaf0 : inv_leaf1, st->shard_rank, st->shard_n)) {
     const int g3[3] = { cI - st->cen[0], cJ - st->cen[1], cK - st->cen[2] };
     ps = (uint32_t)d_phys_slot(g3[0], g3[1], g3[2]);
-    vkey = d_cube_voxel_key(pw, ty == 0 ? inv_leaf0 : inv_leaf1, g3);
+    // a cube outside the 5x5x3 window is not refiltered this sweep (:788-801 walks laserCloudValidInd only): the reference
+    // leaves its new points appended in ARRIVAL order, and so do we (sort key without the voxel key); k_insert_heads flags
+    // the slab, so it is re-voxelised as a whole once it is inside the window
+    vkey = slot_valid_rank[ps] >= 0 ? d_cube_voxel_key(pw, ty == 0 ? inv_leaf0 : inv_leaf1, g3) : 0u;
   }
   comp[e] = ((unsigned long long)(((uint32_t)ty << 13) | ps) << (30 + INS_IDX_BITS)) | ((unsigned long long)vkey << INS_IDX_BITS) | (unsigned long long)i;
 }
@@ -334,7 +337,7 @@ __global__ void __launch_bounds__(256) k_insert_heads(LmMapState* __restrict__ s
                                                       const unsigned long long* __restrict__ sorted, const int32_t* __restrict__ n_ins,
                                                       const float4* __restrict__ world0, const float4* __restrict__ world1,
                                                       int32_t* __restrict__ slot_first, int32_t* __restrict__ slot_base,
-                                                      int32_t* __restrict__ slot_len) {
+                                                      int32_t* __restrict__ slot_len, const int32_t* __restrict__ slot_valid_rank) {
   const int n = *n_ins;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
@@ -364,6 +367,10 @@ __global__ void __launch_bounds__(256) k_insert_heads(LmMapState* __restrict__ s
   slot_first[ty * LM_NSLOT + ps] = p;
   slot_base[ty * LM_NSLOT + ps] = base;
   slot_len[ty * LM_NSLOT + ps] = len;
+  // the tail merge needs ONE batch of new points in voxel-key order behind a filtered prefix: a cube outside the window
+  // (arrival order, see k_insert_prepare) or one that still carries an earlier unmerged batch goes through the
+  // whole-slab re-voxelisation instead
+  if (len > 0 && (slot_valid_rank[ps] < 0 || base > M.slab_nsorted[sid])) M.slab_unsorted[sid] = 1;
   M.slab_n[sid] = base + len;
   M.slab_dirty[sid] = 1;
 }
@@ -817,12 +824,12 @@ int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf,
     const int blocks = lm_div_up(n_max, 256);
     k_insert_prepare<<<blocks, 256, 0, ctx->stream>>>(ctx->d_state, ctx->d_stack[0], ctx->d_stack[1], ctx->d_world[0],
                                                       ctx->d_world[1], ctx->d_sort_a, n_ins, ctx->map[0].leaf, ctx->map[0].inv_leaf,
-                                                      ctx->map[1].leaf, ctx->map[1].inv_leaf, transform_update ? 1 : 0);
+                                                      ctx->map[1].leaf, ctx->map[1].inv_leaf, transform_update ? 1 : 0, ctx->d_slot_valid_rank);
     LM_LAUNCH_CHECK();
     int rc = lm_sort_u64(ctx, ctx->d_sort_a, ctx->d_sort_b, ctx->d_sort_c, n_ins, n_max);
     if (rc) return rc;
     k_insert_heads<<<blocks, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_sort_c, n_ins,
-                                                    ctx->d_world[0], ctx->d_world[1], ctx->d_slot_first, ctx->d_slot_base, slot_len);
+                                                    ctx->d_world[0], ctx->d_world[1], ctx->d_slot_first, ctx->d_slot_base, slot_len, ctx->d_slot_valid_rank);
     LM_LAUNCH_CHECK();
     k_insert_write_plan<<<blocks + 1, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_sort_c, n_ins, ctx->d_world[0],
                                                              ctx->d_world[1], ctx->d_slot_first, ctx->d_slot_base, slot_len,

@@ -34,6 +34,22 @@ def gpu_ctx_factory():
         made.append(c)
         return c
 
+    make.made = made
     yield make
     for c in made:
         c.close()
+
+
+@pytest.fixture(autouse=True)
+def _close_contexts_of_this_test(request):
+    """A ctx holds ~3 GB of device memory (slab pool of the cube map).  Contexts a test creates itself are closed when
+    the test ends; those of module-scoped fixtures (set up before this function-scoped fixture runs) live on."""
+    if "gpu_ctx_factory" not in request.fixturenames:
+        yield
+        return
+    fac = request.getfixturevalue("gpu_ctx_factory")
+    n0 = len(fac.made)
+    yield
+    for c in fac.made[n0:]:
+        c.close()
+    del fac.made[n0:]

@@ -217,3 +217,54 @@ def test_full_res_registration(loaded, oracle):
     ref = (full[:, :3].astype(np.float64) @ R.T + gt).astype(np.float32)
     assert np.abs(greg[:, :3] - ref).max() < 2e-5
     assert np.array_equal(greg[:, 3], full[:, 3])
+
+
+@pytest.mark.parametrize("form", ["latency", "throughput"])
+def test_map_step_empty_and_degenerate_inputs(gpu_ctx_factory, oracle, form):
+    """Edge cases of one laserMapping pass against the oracle, step by step on the same state: nothing at all, a first
+    sweep into an empty map (laserMapping.cpp:554 gate fails: no optimisation, the sweep only fills the map), a sweep
+    without corner features, a sweep without any feature, and a sweep whose features find no neighbour within 1 m
+    (:584,652 gates reject every query: Ceres gets zero residual blocks and leaves the pose at the prior)."""
+    e = np.zeros((0, 4), np.float32)
+    sw = scenario.sweeps(3, seed=3)
+    ctx = gpu_ctx_factory()
+    ctx.set_concurrency_hint(8 if form == "throughput" else 1)
+    om = oracle.Mapper()
+
+    def both(c, s, q, t, tag):
+        gq, gt, grep, _ = ctx.map_step(c, s, q, t)
+        rq, rt, rrep, _ = om.step(c, s, q, t)
+        assert (grep.optimized, grep.corner_from_map, grep.surf_from_map, grep.corner_stack, grep.surf_stack) == \
+               (rrep.optimized, rrep.corner_from_map, rrep.surf_from_map, rrep.corner_stack, rrep.surf_stack), tag
+        assert list(grep.corner_num) == list(rrep.corner_num) and list(grep.surf_num) == list(rrep.surf_num), tag
+        assert np.linalg.norm(gt - rt) <= 1e-4 and rot_angle(gq, rq) <= 1e-4, (tag, gt, rt)
+        return grep
+
+    ident = (np.array([0.0, 0.0, 0.0, 1.0]), np.zeros(3))
+    rep = both(e, e, *ident, "nothing")
+    assert rep.optimized == 0
+    c, s, q, t, qp, tp = sw[0]
+    rep = both(c, s, q, t, "first sweep into an empty map")
+    assert rep.optimized == 0 and rep.corner_stack > 0
+    for which in (0, 1):
+        assert np.array_equal(ctx.map_export(which, 1).view(np.uint32), om.export(which, 1).view(np.uint32)), which
+    # the rest against a loaded map (fresh state on both sides)
+    cm, sm = scenario.small_map()
+    ctx = gpu_ctx_factory()
+    ctx.set_concurrency_hint(8 if form == "throughput" else 1)
+    om = oracle.Mapper()
+    for which, pts in ((0, cm), (1, sm)):
+        ctx.map_import(which, pts)
+        om.import_points(which, pts)
+    c, s, q, t, qp, tp = sw[1]
+    rep = both(e, s, qp, tp, "no corner features")
+    assert rep.optimized == 1 and list(rep.corner_num) == [0, 0] and rep.surf_num[1] > 1000
+    rep = both(e, e, qp, tp, "no features")
+    assert list(rep.surf_num) == [0, 0]
+    cf, sf = c.copy(), s.copy()
+    cf[:, 0] += np.float32(300.0)
+    sf[:, 0] += np.float32(300.0)
+    rep = both(cf, sf, qp, tp, "no neighbour within the gate")
+    assert rep.optimized == 1 and list(rep.corner_num) == [0, 0] and list(rep.surf_num) == [0, 0]
+    for which in (0, 1):
+        assert np.array_equal(ctx.map_export(which, 1).view(np.uint32), om.export(which, 1).view(np.uint32)), which
