@@ -268,3 +268,22 @@ def test_map_step_empty_and_degenerate_inputs(gpu_ctx_factory, oracle, form):
     assert rep.optimized == 1 and list(rep.corner_num) == [0, 0] and list(rep.surf_num) == [0, 0]
     for which in (0, 1):
         assert np.array_equal(ctx.map_export(which, 1).view(np.uint32), om.export(which, 1).view(np.uint32)), which
+    # those points sit, unfiltered and in arrival order, in cubes outside the window.  Move the window over them: the cubes
+    # are indexed for the search and re-voxelised (the reference's VoxelGrid over prefix + appended points)
+    from lmono_b200 import synth
+    t_far = tp + synth.quat_to_rot(qp) @ np.array([250.0, 0.0, 0.0])       # the sweep was displaced along the sensor's x axis
+    rep = both(e, e, qp, t_far, "window moves over the appended cubes")
+    assert rep.corner_from_map > 0 and rep.surf_from_map > 0
+    for which in (0, 1):
+        assert np.array_equal(ctx.map_export(which, 0).view(np.uint32), om.export(which, 0).view(np.uint32)), which
+        assert np.array_equal(ctx.map_export(which, 1).view(np.uint32), om.export(which, 1).view(np.uint32)), which
+    # a second displaced sweep lands on the now filtered cubes (tail merge on top of the re-voxelised prefix)
+    # a second displaced sweep (the window is back at the start): appended, in arrival order, behind the filtered prefix
+    rep = both(cf, sf, qp, tp, "second sweep into the same cubes")
+    for which in (0, 1):
+        assert np.array_equal(ctx.map_export(which, 1).view(np.uint32), om.export(which, 1).view(np.uint32)), which
+    # and back over them: VoxelGrid over (filtered prefix ++ appended points)
+    rep = both(e, e, qp, t_far, "window over the cubes again")
+    for which in (0, 1):
+        assert np.array_equal(ctx.map_export(which, 0).view(np.uint32), om.export(which, 0).view(np.uint32)), which
+        assert np.array_equal(ctx.map_export(which, 1).view(np.uint32), om.export(which, 1).view(np.uint32)), which
