@@ -472,7 +472,6 @@ __device__ __forceinline__ void d_knn5_group(const float4* __restrict__ cellpts,
 // r0 + 1 of cube q0 (and ALSO local 0 of cube q0 + 1 when r0 == 24), c1 = c0 + 1 likewise.
 constexpr int KNN1_THREADS = 128;
 constexpr int KNN1_SLOTS = 12;
-constexpr int KNN1_SMEM = KNN1_THREADS * KNN1_SLOTS * 12;
 
 __device__ __forceinline__ void d_axis_split(float q, int* q0, int* r0) {
   constexpr int FQ_MAX = 1 << 24;
