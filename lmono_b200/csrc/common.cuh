@@ -201,6 +201,7 @@ struct lmono_ctx {
   int32_t* d_rf_tlb;                        // refilter scratch [2][75][max cap]: lower bound of a tail run head's key in the prefix
   int32_t* d_rf_work;                       // [4 + 2*75*chunks]: chunk work list of the cubes being refiltered
   int32_t* d_rf_meta;                       // [2][75][8]: active, total_new, ns, nt, unsorted flag, cur
+  unsigned long long* d_rf_big_s; int32_t* d_rf_big_nv;   // global-memory sort scratch of k_refilter_whole for slabs above LM_TAIL_TILE points
   int32_t* d_rf_plan;                       // compact per-step work lists (LM_PLAN_*): dirty cubes, cubes to re-voxelise whole, cubes with a tail
   float4* d_export; size_t export_cap;      // export / import staging
   int32_t* d_export_off;                    // [LM_NSLOT+1]

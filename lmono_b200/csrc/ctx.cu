@@ -152,7 +152,7 @@ extern "C" void lmono_destroy(lmono_ctx* ctx) {
   lm_odom_free(ctx);
   lm_color_free(ctx);
   lm_map_free(ctx);
-  cudaFree(ctx->d_state); cudaFreeHost(ctx->h_state); for (int i = 0; i < 2; ++i) { cudaFreeHost(ctx->h_ring[i]); cudaEventDestroy(ctx->ev_res[i]); } cudaFree(ctx->d_lm); cudaFree(ctx->d_slot_valid_rank); cudaFree(ctx->d_partials); cudaFree(ctx->d_stamps); cudaFree(ctx->d_tl); cudaFree(ctx->d_nnref); cudaFree(ctx->d_rf_nvx); cudaFree(ctx->d_rf_tlb); cudaFree(ctx->d_rf_work); cudaFree(ctx->d_rf_meta); cudaFree(ctx->d_rf_plan);
+  cudaFree(ctx->d_state); cudaFreeHost(ctx->h_state); for (int i = 0; i < 2; ++i) { cudaFreeHost(ctx->h_ring[i]); cudaEventDestroy(ctx->ev_res[i]); } cudaFree(ctx->d_lm); cudaFree(ctx->d_slot_valid_rank); cudaFree(ctx->d_partials); cudaFree(ctx->d_stamps); cudaFree(ctx->d_tl); cudaFree(ctx->d_nnref); cudaFree(ctx->d_rf_nvx); cudaFree(ctx->d_rf_tlb); cudaFree(ctx->d_rf_work); cudaFree(ctx->d_rf_meta); cudaFree(ctx->d_rf_plan); cudaFree(ctx->d_rf_big_s); cudaFree(ctx->d_rf_big_nv);
   for (int i = 0; i < 3; ++i) cudaFree(ctx->d_raw[i]);
   for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_in[i]); cudaFree(ctx->d_stack[i]); cudaFree(ctx->d_world[i]); cudaFree(ctx->d_fac[i]); }
   cudaFree(ctx->d_sort_a); cudaFree(ctx->d_sort_b); cudaFree(ctx->d_sort_c); cudaFree(ctx->d_blockcnt); cudaFree(ctx->d_tmp_i32);

@@ -742,10 +742,12 @@ __global__ void __launch_bounds__(256) k_rf_scatter(LmMapType M0, LmMapType M1, 
 // Whole-slab re-voxelisation of a flagged slab (rare): one CTA per window cube and map type sorts every
 // point of the slab by voxel key in shared memory and merges runs -- exactly pcl::VoxelGrid on the cube.
 constexpr int RF_WHOLE_GRID = 8;
-__global__ void __launch_bounds__(1024, 1) k_refilter_whole(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, const int32_t* __restrict__ plan) {
+constexpr int RF_BIG_TILE = 65536;          // slabs above LM_TAIL_TILE points sort in a per-CTA global-memory scratch (slow, rare)
+__global__ void __launch_bounds__(1024, 1) k_refilter_whole(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, const int32_t* __restrict__ plan,
+                                                            unsigned long long* __restrict__ big_s, int32_t* __restrict__ big_nv) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned long long* S = reinterpret_cast<unsigned long long*>(smem_raw);              // [LM_TAIL_TILE]
-  int* NV = reinterpret_cast<int*>(smem_raw + (size_t)LM_TAIL_TILE * 8);                // [LM_TAIL_TILE]
+  unsigned long long* S_sm = reinterpret_cast<unsigned long long*>(smem_raw);           // [LM_TAIL_TILE]
+  int* NV_sm = reinterpret_cast<int*>(smem_raw + (size_t)LM_TAIL_TILE * 8);             // [LM_TAIL_TILE]
   int* ws = reinterpret_cast<int*>(smem_raw + (size_t)LM_TAIL_TILE * 12);               // [64]
   __shared__ int s_flag;
   const int nw = plan[LM_PLAN_WHOLE_N];
@@ -758,7 +760,12 @@ __global__ void __launch_bounds__(1024, 1) k_refilter_whole(LmMapState* __restri
   if (!M.slab_unsorted[sid]) continue;
   const int nt = M.slab_n[sid];
   if (nt == 0) continue;
-  if (nt > LM_TAIL_TILE) { if (threadIdx.x == 0) atomicOr(&st->fault, LM_FAULT_TAIL_OVERFLOW); continue; }
+  if (nt > RF_BIG_TILE) { if (threadIdx.x == 0) atomicOr(&st->fault, LM_FAULT_TAIL_OVERFLOW); continue; }
+  // the sort keys and the run flags of a slab live in shared memory; a slab too large for that (a full surf cube that
+  // has to be re-voxelised as a whole) uses this CTA's slice of a global-memory scratch: same code, ~100x slower, rare
+  const bool big = nt > LM_TAIL_TILE;
+  unsigned long long* S = big ? big_s + (size_t)blockIdx.x * RF_BIG_TILE : S_sm;
+  int* NV = big ? big_nv + (size_t)blockIdx.x * RF_BIG_TILE : NV_sm;
   const int cur = M.slab_cur[sid];
   const float4* src = M.pts + ((size_t)sid * 2 + cur) * M.cap;
   float4* dst = M.pts + ((size_t)sid * 2 + (cur ^ 1)) * M.cap;
@@ -856,7 +863,7 @@ int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf,
     LM_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_side0, 0));
     ctx->stream = ctx->side_stream;
   }
-  k_refilter_whole<<<RF_WHOLE_GRID, 1024, kRefilterSmem, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan);
+  k_refilter_whole<<<RF_WHOLE_GRID, 1024, kRefilterSmem, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan, ctx->d_rf_big_s, ctx->d_rf_big_nv);
   if (fork) { ctx->stream = main_stream; LM_CUDA(cudaEventRecord(ctx->ev_side1, ctx->side_stream)); }
   LM_LAUNCH_CHECK();
   k_rf_tailscan<<<RF_ACT_GRID, RF_TS_THREADS, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan, ctx->d_rf_nvx, ctx->d_rf_tlb, meta, cap_max, work_n, work);
@@ -881,6 +888,8 @@ int lm_map_configure_kernels(lmono_ctx* ctx) {
   LM_CUDA(cudaMalloc((void**)&ctx->d_rf_meta, sizeof(RfMeta) * 2 * LM_WIN_MAX));
   LM_CUDA(cudaMalloc((void**)&ctx->d_rf_work, sizeof(int32_t) * (4 + (size_t)2 * LM_WIN_MAX * (lm_div_up(cap_max, LM_RF_CHUNK) + 1))));
   LM_CUDA(cudaMemsetAsync(ctx->d_rf_meta, 0, sizeof(RfMeta) * 2 * LM_WIN_MAX, ctx->stream));
+  LM_CUDA(cudaMalloc((void**)&ctx->d_rf_big_s, sizeof(unsigned long long) * (size_t)RF_WHOLE_GRID * RF_BIG_TILE));
+  LM_CUDA(cudaMalloc((void**)&ctx->d_rf_big_nv, sizeof(int32_t) * (size_t)RF_WHOLE_GRID * RF_BIG_TILE));
   LM_CUDA(cudaMalloc((void**)&ctx->d_rf_plan, sizeof(int32_t) * LM_PLAN_INTS));
   LM_CUDA(cudaMemsetAsync(ctx->d_rf_plan, 0, sizeof(int32_t) * LM_PLAN_INTS, ctx->stream));
 

@@ -287,3 +287,39 @@ def test_map_step_empty_and_degenerate_inputs(gpu_ctx_factory, oracle, form):
     for which in (0, 1):
         assert np.array_equal(ctx.map_export(which, 0).view(np.uint32), om.export(which, 0).view(np.uint32)), which
         assert np.array_equal(ctx.map_export(which, 1).view(np.uint32), om.export(which, 1).view(np.uint32)), which
+
+
+def test_whole_slab_revoxelisation_of_a_full_cube(gpu_ctx_factory, oracle):
+    """A cube that already holds ~27 k filtered surf points (more than the shared-memory sort of the whole-slab path
+    takes) collects a sweep while it is outside the window; when the window reaches it, it is re-voxelised as a whole
+    through the global-memory scratch: pcl::VoxelGrid over prefix ++ appended points, bit for bit."""
+    from lmono_b200 import synth
+    e = np.zeros((0, 4), np.float32)
+    c, s, q, t, qp, tp = scenario.sweeps(3, seed=3)[1]
+    R = synth.quat_to_rot(qp)
+    far = tp + R @ np.array([300.0, 0.0, 0.0])
+    centre = np.round(far / 50.0) * 50.0
+    g = np.arange(-12.0, 12.0, 0.8, dtype=np.float32) + np.float32(0.4)
+    xx, yy, zz = np.meshgrid(g, g, g, indexing="ij")
+    blob = np.stack([xx.ravel(), yy.ravel(), zz.ravel(), np.zeros(xx.size, np.float32)], 1).astype(np.float32)
+    blob[:, :3] += centre.astype(np.float32)
+    assert len(blob) > 16384
+    cm, sm = scenario.small_map()
+    sm2 = np.concatenate([sm, blob])
+    ctx = gpu_ctx_factory()
+    om = oracle.Mapper()
+    for which, pts in ((0, cm), (1, sm2)):
+        ctx.map_import(which, pts)
+        om.import_points(which, pts)
+    cf, sf = c.copy(), s.copy()
+    cf[:, 0] += np.float32(300.0)
+    sf[:, 0] += np.float32(300.0)
+    for (a, b, tt, tag) in ((cf, sf, tp, "sweep into cubes outside the window"), (e, e, tp + R @ np.array([250.0, 0.0, 0.0]), "window over them")):
+        gq, gt, grep, _ = ctx.map_step(a, b, qp, tt)
+        rq, rt, rrep, _ = om.step(a, b, qp, tt)
+        assert (grep.optimized, grep.corner_from_map, grep.surf_from_map) == (rrep.optimized, rrep.corner_from_map, rrep.surf_from_map), tag
+        assert np.linalg.norm(gt - rt) <= 1e-4, tag
+    assert rrep.surf_from_map > 16384
+    for which in (0, 1):
+        assert np.array_equal(ctx.map_export(which, 0).view(np.uint32), om.export(which, 0).view(np.uint32)), which
+        assert np.array_equal(ctx.map_export(which, 1).view(np.uint32), om.export(which, 1).view(np.uint32)), which
