@@ -92,3 +92,36 @@ def test_mapping_window_shift_keeps_points(oracle):
     assert np.array_equal(np.sort(after.view(np.uint32), axis=0), np.sort(before.view(np.uint32), axis=0))
     m.prepare_window([2000.0, 0.0, 0.0])                # far away: everything scrolled out
     assert len(m.export(1, 1)) == 0
+
+
+def test_mapping_cubes_outside_the_window_keep_arrival_order_until_they_enter_it(oracle):
+    """laserMapping.cpp:737-801: every feature is pushed into its cube, but only the cubes of laserCloudValidInd are
+    re-filtered.  A cube outside the 5x5x3 window therefore keeps its new points appended in arrival order, over as many
+    sweeps as it takes, and is voxel-filtered (prefix ++ appended, summed in that order) the first time the window
+    covers it.  Independent restatement: numpy VoxelGrid of test_oracle_primitives."""
+    from test_oracle_primitives import np_voxel_grid
+    rng = np.random.default_rng(9)
+    e = np.zeros((0, 4), np.float32)
+
+    def batch(n):
+        p = np.zeros((n, 4), np.float32)
+        p[:, 0] = rng.uniform(130.0, 145.0, n)          # cube +3 in x: outside the window around the origin
+        p[:, 1:3] = rng.uniform(-10.0, 10.0, (n, 2))
+        p[:, 3] = rng.uniform(0, 50, n)
+        return p
+
+    m = oracle.Mapper()
+    ident = ([0, 0, 0, 1], [0, 0, 0])
+    s1, s2 = batch(3000), batch(2500)
+    _, _, rep, _ = m.step(e, s1, *ident)
+    assert rep.optimized == 0                             # empty map: the sweep only fills it, pose = prior
+    v1 = np_voxel_grid(s1, 0.8)
+    assert np.array_equal(m.export(1, 1), v1)             # appended in the order of the (voxel-filtered) sweep, not re-filtered
+    m.set_state(*ident)
+    m.step(e, s2, *ident)
+    v2 = np_voxel_grid(s2, 0.8)
+    assert np.array_equal(m.export(1, 1), np.concatenate([v1, v2]))
+    m.set_state(*ident)
+    _, _, rep, _ = m.step(e, e, [0, 0, 0, 1], [150.0, 0.0, 0.0])      # the window now covers the cube
+    assert rep.surf_from_map == len(v1) + len(v2)         # the search sees prefix ++ appended ...
+    assert np.array_equal(m.export(1, 1), np_voxel_grid(np.concatenate([v1, v2]), 0.8))    # ... and the refilter merges them
