@@ -152,7 +152,7 @@ def py_scan_registration(raw, n_scans, minimum_range, scan_period=0.1):
             "less_flat": np.concatenate(less_flat) if less_flat else np.zeros((0, 4), np.float32)}
 
 
-@pytest.mark.parametrize("n_scans,min_range", [(16, 0.3), (64, 5.0)])
+@pytest.mark.parametrize("n_scans,min_range", [(16, 0.3), (32, 0.3), (64, 5.0)])
 def test_oracle_scan_registration_equals_python_restatement(oracle, n_scans, min_range):
     w = synth.make_world()
     rng = np.random.default_rng(3)
