@@ -100,3 +100,54 @@ def test_oracle_mapping_steps_equal_python_composition(oracle):
         for which in (0, 1):
             a, b = om.export(which, 1), pm.export_all(which)
             assert a.shape == b.shape and np.allclose(a, b, rtol=0, atol=2e-5), (k, which)
+
+
+def py_shift_window(cubes, cen, t_w):
+    """:312-507 restated on a dict {(i, j, k): points}: returns the new dict, the new cen and the centre cube."""
+    dims = (W, H, D)
+    cen = list(cen)
+    c = [cube_coord(t_w[a], cen[a]) for a in range(3)]
+    for a in range(3):
+        while c[a] < 3:                                 # contents move up one cube, the top plane is recycled empty
+            cubes = {tuple(k[b] + (1 if b == a else 0) for b in range(3)): v for k, v in cubes.items() if k[a] + 1 < dims[a]}
+            c[a] += 1
+            cen[a] += 1
+        while c[a] >= dims[a] - 3:                      # contents move down one cube, plane 0 is recycled empty
+            cubes = {tuple(k[b] - (1 if b == a else 0) for b in range(3)): v for k, v in cubes.items() if k[a] - 1 >= 0}
+            c[a] -= 1
+            cen[a] -= 1
+    return cubes, tuple(cen), tuple(c)
+
+
+def test_oracle_window_shift_equals_python_restatement(oracle):
+    rng = np.random.default_rng(31)
+    pts = np.zeros((6000, 4), np.float32)
+    pts[:, :3] = rng.uniform(-180, 180, (6000, 3)) * np.array([1.0, 1.0, 0.5], np.float32)
+    pts[:, 3] = np.arange(6000) % 50
+    om = oracle.Mapper()
+    om.import_points(1, pts)
+    cubes, cen = {}, (10, 10, 5)
+    for p in pts:                                        # import: by cube index, then VoxelGrid per cube
+        key = tuple(cube_coord(p[a], cen[a]) for a in range(3))
+        if all(0 <= key[a] < (W, H, D)[a] for a in range(3)):
+            cubes.setdefault(key, []).append(p)
+    cubes = {k: list(np_voxel_grid(np.array(v, np.float32), 0.8)) for k, v in cubes.items()}
+
+    def flat(cs):
+        keys = sorted(cs, key=lambda k: k[0] + W * k[1] + W * H * k[2])
+        return np.concatenate([np.array(cs[k], np.float32) for k in keys]) if keys else np.zeros((0, 4), np.float32)
+
+    assert np.array_equal(om.export(1, 1), flat(cubes))
+    for t_w in ([420.0, 0.0, 0.0], [470.0, -380.0, 0.0], [470.0, -460.0, 130.0], [-300.0, 100.0, -160.0], [0.0, 0.0, 0.0],
+                [760.0, 0.0, 0.0], [0.0, 0.0, 0.0]):
+        om.prepare_window(t_w)
+        cubes, cen, centre = py_shift_window(cubes, cen, t_w)
+        _, _, ocen = om.get_state()
+        assert tuple(ocen) == cen, (t_w, ocen, cen)
+        assert np.array_equal(om.export(1, 1), flat(cubes)), t_w
+        valid = [(i, j, k) for i in range(centre[0] - 2, centre[0] + 3) for j in range(centre[1] - 2, centre[1] + 3)
+                 for k in range(centre[2] - 1, centre[2] + 2) if 0 <= i < W and 0 <= j < H and 0 <= k < D]
+        win = [np.array(cubes[v], np.float32) for v in valid if v in cubes]
+        win = np.concatenate(win) if win else np.zeros((0, 4), np.float32)
+        assert np.array_equal(om.export(1, 0), win), t_w            # the :512-537 concatenation = index space of the kNN
+    assert len(flat(cubes)) < len(pts)                               # some planes were recycled on the way
