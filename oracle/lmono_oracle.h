@@ -14,8 +14,13 @@
  * citations of the reference call sites, (2) restatements of the published
  * algorithms of the un-vendored third-party code (PCL 1.8 VoxelGrid /
  * KdTreeFLANN, FLANN 1.8/1.9 KDTreeSingleIndex, Ceres 1.14 trust-region LM,
- * Eigen 3.3 SelfAdjointEigenSolver / ColPivHouseholderQR), and (3)
- * cross-checks against scipy / numpy / cv2 in tests/.
+ * Eigen 3.3 SelfAdjointEigenSolver / ColPivHouseholderQR), (3)
+ * cross-checks against scipy / numpy / cv2 in tests/, and (4) independent
+ * Python restatements of every stage written separately from this C code
+ * (tests/test_oracle_*_python.py: scanRegistration, odometry correspondences
+ * and a whole odometry step, map association, the Ceres-style solve with
+ * numeric Jacobians, whole mapping passes incl. the window shifts, the colour
+ * raster and lift), which must agree with it on seeded inputs.
  *
  * Every function cites the reference file:line it follows (paths relative to
  * /root/reference).
