@@ -141,18 +141,23 @@ constexpr int LM_PROF_MAX_EVENTS = 2048;
 // ---------------------------------------------------------------- host ctx
 // One captured CUDA graph per launch-grid capacity bucket of a laserMapping step (inputs are read through
 // LmMapState::in_ptr, so the graph does not depend on the caller's buffers).
-struct LmGraphEntry { int nc_cap, ns_cap; bool throughput; cudaGraphExec_t exec; int n_launch; };
+struct LmGraphEntry { int nc_cap, ns_cap; int form; cudaGraphExec_t exec; int n_launch; };   // form: every host-side choice baked in at capture (lm_graph_form)
 constexpr int LM_MAX_GRAPHS = 64;
 // Sequence batches: ONE graph holds the steps of all n sequences as parallel branches (fork / join inside the
 // graph), so a batch step costs the host one small argument launch + one cudaGraphLaunch.  Cached in ctxs[0].
 constexpr int LM_BATCH_MAX = 64;
 constexpr int LM_MAX_BGRAPHS = 16;
-struct LmBatchGraph { int n; lmono_ctx* ctxs[LM_BATCH_MAX]; int nc_cap[LM_BATCH_MAX], ns_cap[LM_BATCH_MAX]; cudaGraphExec_t exec; int n_launch[LM_BATCH_MAX]; };
+struct LmBatchGraph { int n; lmono_ctx* ctxs[LM_BATCH_MAX]; unsigned long long uids[LM_BATCH_MAX];   // uids: a ctx address can be reused after lmono_destroy, its uid never is
+                       int nc_cap[LM_BATCH_MAX], ns_cap[LM_BATCH_MAX]; cudaGraphExec_t exec; int n_launch[LM_BATCH_MAX]; };
 constexpr int LM_GRAPH_BUCKET = 2048;     // launch grids are sized for counts rounded up to this
 
 constexpr int LM_TL_MAX = 64;
 constexpr int LM_THROUGHPUT_BATCH = 4;
+// kernel-form class of a step enqueued with `batch_n` sequences sharing the GPU: 0 latency forms, 1 throughput forms with the
+// full LM cluster, 2 throughput forms with 8-CTA LM clusters (lm_cluster_pick).  Part of every graph cache key.
+static inline int lm_graph_form(int batch_n) { return batch_n >= LM_THROUGHPUT_BATCH ? (batch_n > 8 ? 2 : 1) : 0; }
 struct lmono_ctx {
+  unsigned long long uid;       // process-wide unique, never reused (keys of graph caches held by OTHER ctxs)
   int device;
   lmono_params prm;
   cudaStream_t stream;

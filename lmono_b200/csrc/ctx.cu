@@ -45,6 +45,10 @@ __global__ void k_state_init(LmMapState* st) {
   for (int k = 0; k < 3; ++k) { st->t_wmap_wodom[k] = 0; st->t_wodom_curr[k] = 0; st->t_w_curr[k] = 0; }
 }
 
+static int create_impl(lmono_ctx* ctx, void* stream);
+
+// Failures after the ctx exists are routed through lmono_destroy (every member is calloc-zeroed, cudaFree(NULL) and the
+// NULL-guarded destroys are no-ops), so a failed creation of the Nth sequence of a batch leaks nothing.
 extern "C" int lmono_create(int device, const lmono_params* params, void* stream, lmono_ctx** out) {
   if (!out) return LMONO_E_ARG;
   *out = nullptr;
@@ -65,17 +69,31 @@ extern "C" int lmono_create(int device, const lmono_params* params, void* stream
   if (P.max_cubes_surf <= 0) P.max_cubes_surf = def.max_cubes_surf;
   if (P.image_width <= 0) P.image_width = def.image_width;
   if (P.image_height <= 0) P.image_height = def.image_height;
+  // every argument check comes before the first device allocation
   if (P.mapping_line_resolution < 0.06f || P.mapping_plane_resolution < 0.06f) { free(ctx); return LMONO_E_ARG; }
   if (P.scan_line != 16 && P.scan_line != 32 && P.scan_line != 64) { free(ctx); return LMONO_E_ARG; }
+  if (P.max_feature_points > (1 << 19)) { fprintf(stderr, "[lmono_b200] max_feature_points must be <= 524288\n"); free(ctx); return LMONO_E_ARG; }
+  if (P.max_cubes_corner > 8190 || P.max_cubes_surf > 8190) { free(ctx); return LMONO_E_ARG; }
+  static unsigned long long next_uid = 0;
+  ctx->uid = __atomic_add_fetch(&next_uid, 1ull, __ATOMIC_RELAXED);
   ctx->device = device;
   ctx->batch_n = 1; ctx->batch_hint = 1;
   { const char* ng = getenv("LMONO_NO_GRAPH"); ctx->graphs_on = !(ng && ng[0] == '1'); }
   ctx->max_feat = P.max_feature_points; ctx->max_sweep = P.max_sweep_points;
+  int rc = create_impl(ctx, stream);
+  if (rc) { lmono_destroy(ctx); return rc; }
+  *out = ctx;
+  return LMONO_OK;
+}
+
+static int create_impl(lmono_ctx* ctx, void* stream) {
+  const int device = ctx->device;
+  lmono_params& P = ctx->prm; (void)P;
   cudaError_t e = cudaSetDevice(device);
-  if (e != cudaSuccess) { fprintf(stderr, "[lmono_b200] cudaSetDevice(%d): %s\n", device, cudaGetErrorString(e)); free(ctx); return LMONO_E_CUDA; }
+  if (e != cudaSuccess) { fprintf(stderr, "[lmono_b200] cudaSetDevice(%d): %s\n", device, cudaGetErrorString(e)); return LMONO_E_CUDA; }
   cudaDeviceProp prop;
   e = cudaGetDeviceProperties(&prop, device);
-  if (e != cudaSuccess) { free(ctx); return LMONO_E_CUDA; }
+  if (e != cudaSuccess) return LMONO_E_CUDA;
   ctx->sm_count = prop.multiProcessorCount;
   if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
   else { LM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
@@ -123,7 +141,6 @@ extern "C" int lmono_create(int device, const lmono_params* params, void* stream
   LM_CUDA(cudaMalloc((void**)&ctx->d_tmp_i32, sizeof(int32_t) * (2 * LM_NSLOT + 64 + nsort)));
   LM_CUDA(cudaMalloc((void**)&ctx->d_vg, sizeof(VgParams) * 4));
   { int rcv = lm_voxel_init(ctx); if (rcv) return rcv; }
-  if (ctx->max_feat > (1 << 19)) { fprintf(stderr, "[lmono_b200] max_feature_points must be <= 524288\n"); return LMONO_E_ARG; }
   LM_CUDA(cudaMalloc((void**)&ctx->d_full, (size_t)ctx->max_sweep * sizeof(float4)));
   LM_CUDA(cudaMalloc((void**)&ctx->d_slot_first, sizeof(int32_t) * 2 * LM_NSLOT));
   LM_CUDA(cudaMalloc((void**)&ctx->d_slot_base, sizeof(int32_t) * 2 * LM_NSLOT));
@@ -138,28 +155,29 @@ extern "C" int lmono_create(int device, const lmono_params* params, void* stream
   if (rc) return rc;
   if ((rc = lm_sort_configure(ctx))) return rc;
   LM_CUDA(cudaStreamSynchronize(ctx->stream));
-  *out = ctx;
   return LMONO_OK;
 }
 
 extern "C" void lmono_destroy(lmono_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < ctx->n_graphs; ++i) cudaGraphExecDestroy(ctx->graphs[i].exec);
   lm_batch_free(ctx);
   lm_scan_free(ctx);
   lm_odom_free(ctx);
   lm_color_free(ctx);
   lm_map_free(ctx);
-  cudaFree(ctx->d_state); cudaFreeHost(ctx->h_state); for (int i = 0; i < 2; ++i) { cudaFreeHost(ctx->h_ring[i]); cudaEventDestroy(ctx->ev_res[i]); } cudaFree(ctx->d_lm); cudaFree(ctx->d_slot_valid_rank); cudaFree(ctx->d_partials); cudaFree(ctx->d_stamps); cudaFree(ctx->d_tl); cudaFree(ctx->d_nnref); cudaFree(ctx->d_rf_nvx); cudaFree(ctx->d_rf_tlb); cudaFree(ctx->d_rf_work); cudaFree(ctx->d_rf_meta); cudaFree(ctx->d_rf_plan); cudaFree(ctx->d_rf_big_s); cudaFree(ctx->d_rf_big_nv);
+  cudaFree(ctx->d_state); cudaFreeHost(ctx->h_state); for (int i = 0; i < 2; ++i) { cudaFreeHost(ctx->h_ring[i]); if (ctx->ev_res[i]) cudaEventDestroy(ctx->ev_res[i]); } cudaFree(ctx->d_lm); cudaFree(ctx->d_slot_valid_rank); cudaFree(ctx->d_partials); cudaFree(ctx->d_stamps); cudaFree(ctx->d_tl); cudaFree(ctx->d_nnref); cudaFree(ctx->d_rf_nvx); cudaFree(ctx->d_rf_tlb); cudaFree(ctx->d_rf_work); cudaFree(ctx->d_rf_meta); cudaFree(ctx->d_rf_plan); cudaFree(ctx->d_rf_big_s); cudaFree(ctx->d_rf_big_nv);
   for (int i = 0; i < 3; ++i) cudaFree(ctx->d_raw[i]);
   for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_in[i]); cudaFree(ctx->d_stack[i]); cudaFree(ctx->d_world[i]); cudaFree(ctx->d_fac[i]); }
   cudaFree(ctx->d_sort_a); cudaFree(ctx->d_sort_b); cudaFree(ctx->d_sort_c); cudaFree(ctx->d_blockcnt); cudaFree(ctx->d_tmp_i32);
   cudaFree(ctx->d_vg); cudaFree(ctx->d_full); cudaFree(ctx->d_slot_first); cudaFree(ctx->d_slot_base); cudaFree(ctx->d_export_off); cudaFree(ctx->d_export);
-  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); cudaEventDestroy(ctx->ev_sync); cudaEventDestroy(ctx->ev_done);
-  if (ctx->side_stream) { cudaStreamDestroy(ctx->side_stream); cudaEventDestroy(ctx->ev_side0); cudaEventDestroy(ctx->ev_side1); }
-  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  cudaEvent_t evs[] = { ctx->ev0, ctx->ev1, ctx->ev_fork, ctx->ev_join, ctx->ev_sync, ctx->ev_done, ctx->ev_side0, ctx->ev_side1 };
+  for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+  if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  cudaGetLastError();
   free(ctx);
 }
 

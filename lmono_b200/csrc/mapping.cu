@@ -213,7 +213,7 @@ static int enqueue_step(lmono_ctx* ctx, const LmStepIn& in, const lmono_pose* wo
     LmGraphEntry* g = nullptr;
     for (int i = 0; i < ctx->n_graphs; ++i) {
       LmGraphEntry& e = ctx->graphs[i];
-      if (e.nc_cap == nc_cap && e.ns_cap == ns_cap && e.throughput == (ctx->batch_n >= LM_THROUGHPUT_BATCH)) { g = &e; break; }
+      if (e.nc_cap == nc_cap && e.ns_cap == ns_cap && e.form == lm_graph_form(ctx->batch_n)) { g = &e; break; }
     }
     if (!g) {
       if (ctx->n_graphs == LM_MAX_GRAPHS) {      // cache full: drop everything
@@ -228,7 +228,7 @@ static int enqueue_step(lmono_ctx* ctx, const LmStepIn& in, const lmono_pose* wo
       if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
       LM_CUDA(ce);
       g = &ctx->graphs[ctx->n_graphs];
-      g->nc_cap = nc_cap; g->ns_cap = ns_cap; g->throughput = ctx->batch_n >= LM_THROUGHPUT_BATCH;
+      g->nc_cap = nc_cap; g->ns_cap = ns_cap; g->form = lm_graph_form(ctx->batch_n);
       g->n_launch = (int)(ctx->launches - l0);
       ctx->launches = l0;
       ce = cudaGraphInstantiate(&g->exec, graph, 0);
@@ -515,7 +515,7 @@ static int batch_capture(lmono_ctx* lead, lmono_ctx* const* ctxs, int n, const i
   cudaGraphDestroy(graph);
   LM_CUDA(ce);
   g->n = n;
-  for (int i = 0; i < n; ++i) { g->ctxs[i] = ctxs[i]; g->nc_cap[i] = nc_cap[i]; g->ns_cap[i] = ns_cap[i]; }
+  for (int i = 0; i < n; ++i) { g->ctxs[i] = ctxs[i]; g->uids[i] = ctxs[i]->uid; g->nc_cap[i] = nc_cap[i]; g->ns_cap[i] = ns_cap[i]; }
   return LMONO_OK;
 }
 
@@ -560,7 +560,7 @@ static int batch_enqueue(lmono_ctx* const* ctxs, int n, const LmStepIn* in, cons
     LmBatchGraph& q = lead->bgraphs[e];
     if (q.n != n) continue;
     bool same = true;
-    for (int i = 0; i < n && same; ++i) same = q.ctxs[i] == ctxs[i] && q.nc_cap[i] == nc_cap[i] && q.ns_cap[i] == ns_cap[i];
+    for (int i = 0; i < n && same; ++i) same = q.ctxs[i] == ctxs[i] && q.uids[i] == ctxs[i]->uid && q.nc_cap[i] == nc_cap[i] && q.ns_cap[i] == ns_cap[i];
     if (same) g = &q;
   }
   if (!g) {

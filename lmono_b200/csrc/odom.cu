@@ -234,6 +234,7 @@ static int odom_state(lmono_ctx* ctx, OdomState** out) {
   const size_t n = (size_t)s->cap;
   LM_CUDA(cudaMalloc((void**)&s->d, sizeof(OdomDev)));
   LM_CUDA(cudaMallocHost((void**)&s->h, sizeof(OdomDev)));
+  memset(s->h, 0, sizeof(OdomDev));      // the grid sizes of the first step are read from this mirror before any read-back
   for (int k = 0; k < 4; ++k) LM_CUDA(cudaMalloc((void**)&s->d_feat[k], n * sizeof(float4)));
   for (int k = 0; k < 2; ++k) { LM_CUDA(cudaMalloc((void**)&s->d_last[k], n * sizeof(float4))); LM_CUDA(cudaMalloc((void**)&s->d_best[k], n * sizeof(unsigned long long))); }
   LM_CUDA(cudaMalloc((void**)&s->d_corr, n * 10 * sizeof(int32_t)));
