@@ -71,6 +71,12 @@ def make_workload(rank=0, n_sweeps=N_DISTINCT_SWEEPS):
     return city, cm, sm, sweeps
 
 
+def shared_config(map_points):
+    """the keys that name the workload: identical in our arm and the reference arm"""
+    return {"workload": WORKLOAD, "map_points": int(map_points), "raw_features_per_sweep": [RAW_CORNER, RAW_SURF],
+            "distinct_sweeps": N_DISTINCT_SWEEPS, "pose_perturbation": "U(+-0.2 m, +-1 deg), q/t_wmap_wodom reset before every registration"}
+
+
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -128,6 +134,7 @@ def _oracle_worker(args):
     m = O.Mapper(0.4, 0.8, 0, 1)
     m.import_points(0, cm)
     m.import_points(1, sm)
+    nmap0 = len(m.export(0)) + len(m.export(1))        # right after the import: the same number in both arms
     phases = {"ms_tree": 0.0, "ms_assoc": 0.0, "ms_solver": 0.0, "ms_filter": 0.0, "ms_add": 0.0, "ms_shift": 0.0}
     for i in range(warmup):
         c, s, q, t, qp, tp = sweeps[i % len(sweeps)]
@@ -141,8 +148,7 @@ def _oracle_worker(args):
         for k in phases:
             phases[k] += getattr(rep, k)
     dt = time.perf_counter() - t0
-    nmap = len(m.export(0)) + len(m.export(1))
-    return dt, phases, nmap
+    return dt, phases, nmap0
 
 
 def run_reference(args):
@@ -161,7 +167,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps / procs * procs, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "map_points": res[0][2], "parallelism": f"{procs} independent sequences on {procs} host processes"},
+        "config": shared_config(res[0][2]),
+        "arm": {"parallelism": f"{procs} independent sequences on {procs} host processes"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
                          "sample": f"{args.steps} registrations per process x {procs} processes (oracle restatement of the PCL/FLANN/Ceres path: "
                                    "per-sweep KD-tree rebuild, 5-NN, fits, Ceres-style LM, per-cube VoxelGrid refilter)",
@@ -212,6 +219,7 @@ def run_ours(args):
         c_.sync()
         ctxs.append(c_)
     ctx = ctxs[0]
+    nmap_import = len(ctx.map_export(0, 1)) + len(ctx.map_export(1, 1))
     batch = api.SequenceBatch(ctxs)
 
     # device-resident copies of the sweeps (value leg) and pinned host copies (e2e leg)
@@ -474,11 +482,10 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32+f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "map_points": int(nmap), "queries_per_sweep": int(nq),
-                   "raw_features_per_sweep": [RAW_CORNER, RAW_SURF], "sequences_per_gpu": S,
-                   "registrations_per_step": S * world,
-                   "l2": "flushed between steps (256 MiB write)",
-                   "parallelism": f"{S} independent sequences per GPU (one ctx each, BASELINE config C-4); one registration of every sequence per step = one CUDA graph with {S} parallel branches, no collective"},
+        "config": shared_config(nmap_import),
+        "arm": {"queries_per_sweep": int(nq), "sequences_per_gpu": S, "registrations_per_step": S * world,
+                "l2": "flushed between steps (256 MiB write)",
+                "parallelism": f"{S} independent sequences per GPU (one ctx each, BASELINE config C-4); one registration of every sequence per step = one CUDA graph with {S} parallel branches, no collective"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
                 "pipeline": "lmono_map_submit_batch / lmono_map_wait_batch, two steps in flight; every result read on the host",
                 "unpipelined_value": e2e_sync_value},
@@ -493,32 +500,28 @@ def run_ours(args):
         "registration_error_m": reg_err,
     }
 
-    # ---- the whole A-LOAM chain of one sequence (BASELINE config C-4 "fused L1 -> L2 -> L3"): raw 64-ring sweeps of
-    # ~113 k points through lmono_sweep_step (scanRegistration -> laserOdometry -> laserMapping, host sweep in, poses out)
-    if rank == 0 and not args.no_pipeline:
+    # ---- the other configurations of BASELINE.json, each a leg of its own (extra keys of the same line)
+    legs = set(args.legs.split(",")) if args.legs else set()
+    ctxb = LegCtx(api=api, torch=torch, dev=dev, local=local, rank=rank, world=world, main=main, flush=flush, hbm_peak=hbm_peak,
+                  peak_src=peak_src, cpu=(rank == 0 and world == 1 and not args.no_cpu), steps=args.steps)
+    if rank == 0:
+        for name, fn in (("fused_sweep", leg_fused_sweep), ("c2_odometry", leg_c2_odometry), ("colour_frame", leg_colour_frame),
+                         ("c1_cpu_pipeline", leg_c1_cpu_pipeline)):
+            if name not in legs:
+                continue
+            try:
+                line[name] = fn(ctxb, cm, sm)
+            except Exception as e:                                  # noqa: BLE001  (never lose the headline line to an extra leg)
+                import traceback
+                line[name] = {"error": f"{type(e).__name__}: {e}", "trace": traceback.format_exc()[-600:]}
+    if world > 1 and "c5_sharded" in legs:                          # every rank takes part
         try:
-            wld = synth.make_world()
-            rng_p = np.random.default_rng(2)
-            raws = []
-            for k in range(30):
-                q_, t_ = synth.loop_pose(wld, 1.0 * k)
-                raws.append(np.ascontiguousarray(synth.raycast_sweep(wld, q_, t_, 64, 1875, rng_p), np.float32))
-            pctx = api.Context(device=local, stream=main.cuda_stream)
-            tp_ = []
-            for k, raw in enumerate(raws):
-                t0 = time.perf_counter()
-                out_ = pctx.sweep_step(raw)
-                if k >= 6:
-                    tp_.append(time.perf_counter() - t0)
-            truth = float(np.linalg.norm(synth.loop_pose(wld, 29.0)[1] - synth.loop_pose(wld, 0.0)[1]))
-            drift = float(np.linalg.norm(out_[2][1])) - truth      # mapped translation of the last sweep vs the true chord
-            line["fused_sweep"] = {"sweeps_per_s": 1.0 / float(np.mean(tp_)), "ms_per_sweep": 1e3 * float(np.mean(tp_)),
-                                   "points_per_sweep": int(len(raws[0])), "sequences": 1, "travelled_minus_truth_m": drift,
-                                   "what": "lmono_sweep_step: raw HDL-64 sweep (pageable host memory) -> scanRegistration -> laserOdometry -> "
-                                           "laserMapping -> poses on the host; one sequence, synchronous calls, wall clock"}
-            pctx.close()
-        except Exception as e:                                      # noqa: BLE001  (never lose the headline line to the extra leg)
-            line["fused_sweep"] = {"error": str(e)}
+            r5 = leg_c5_sharded(ctxb, args)
+            if rank == 0:
+                line["c5_sharded"] = r5
+        except Exception as e:                                      # noqa: BLE001
+            import traceback
+            line["c5_sharded"] = {"error": f"{type(e).__name__}: {e}", "trace": traceback.format_exc()[-600:]}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -543,6 +546,417 @@ def run_ours(args):
             dist.destroy_process_group()
     except Exception as e:                           # noqa: BLE001
         print(f"[bench] teardown: {e}", file=sys.stderr)
+
+
+# ----------------------------------------------------------------------------- extra legs (the other BASELINE configs)
+class LegCtx:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def _roof(kernel, alg_bytes, ms, hbm_peak, what):
+    if not ms:
+        return None
+    gbs = alg_bytes / (ms * 1e-3) / 1e9
+    return {"kernel": kernel, "what": what, "algorithmic_bytes_per_launch": float(alg_bytes), "avg_launch_ms": ms,
+            "achieved": gbs, "frac": gbs / hbm_peak, "unit": "GB/s"}
+
+
+def _marks_per_launch(ctx):
+    m = ctx.kernel_marks()
+    return {k: v[1] / max(v[0], 1) for k, v in m.items()}, {k: v[0] for k, v in m.items()}
+
+
+def leg_fused_sweep(L, cm, sm):
+    """north_star: a ~120 k-point HDL-64 sweep against the ~1 M-point map.  Raw 64-ring sweeps ray-cast in the C-3 city
+    (the world the map was sampled from) go through lmono_sweep_step -- scanRegistration -> laserOdometry -> laserMapping
+    -- against the IMPORTED C-3 map; q/t_wmap_wodom starts at the first pose (the map is in the world frame)."""
+    api, torch = L.api, L.torch
+    city = synth.make_city(seed=7, pole_pitch=3.7, street_radius=18.0)
+    rng = np.random.default_rng(2)
+    n_sw = 40
+    poses = [synth.city_pose(city, 0.5 * k) for k in range(n_sw)]
+    raws = [np.ascontiguousarray(synth.raycast_sweep_torch(city, q_, t_, 64, 1875, rng, device=L.dev), np.float32) for (q_, t_) in poses]
+    pinned = [torch.from_numpy(r).pin_memory() for r in raws]
+    # the busiest corner cube of the C-3 city already holds ~13 k points and every sweep appends ~3 k more before the
+    # refilter merges them: twice the default slab capacities
+    ctx = api.Context(device=L.local, stream=L.main.cuda_stream, cube_capacity_corner=32768, cube_capacity_surf=65536)
+    ctx.map_import(0, cm)
+    ctx.map_import(1, sm)
+    nmap = len(ctx.map_export(0, 1)) + len(ctx.map_export(1, 1))
+    ctx.map_set_state(*poses[0])
+    tp_, ms_dev, errs, stack = [], [], [], []
+    for k, raw in enumerate(pinned):
+        t0 = time.perf_counter()
+        out_ = ctx.sweep_step(raw.numpy())
+        dt = time.perf_counter() - t0
+        if k >= 8:
+            tp_.append(dt)
+            ms_dev.append(out_[3].ms_gpu + out_[4].ms_gpu + out_[5].ms_gpu)
+        errs.append(float(np.linalg.norm(out_[2][1] - poses[k][1])))
+        stack.append(out_[5].corner_stack + out_[5].surf_stack)
+        assert out_[5].optimized == 1 and errs[-1] < 0.25, (k, errs[-1])
+    res = {"sweeps_per_s": 1.0 / float(np.mean(tp_)), "ms_per_sweep": 1e3 * float(np.mean(tp_)),
+           "points_per_sweep": int(len(raws[0])), "map_points": int(nmap), "queries_per_sweep": int(np.mean(stack)), "sequences": 1,
+           "worst_position_error_m": max(errs),
+           "what": "lmono_sweep_step: raw HDL-64 sweep (page-locked host memory) -> scanRegistration -> laserOdometry -> laserMapping "
+                   "against the imported ~1 M-point C-3 map -> poses on the host; one sequence, synchronous calls, wall clock "
+                   "(H2D of the sweep and D2H of the poses inside)",
+           "e2e": {"value": 1.0 / float(np.mean(tp_)), "unit": "sweeps/s", "h2d_bytes_per_step": int(raws[0].nbytes), "d2h_bytes_per_step": 3000}}
+    if L.cpu:
+        import oracle_lib as O
+        om = O.Mapper()
+        om.import_points(0, cm)
+        om.import_points(1, sm)
+        om.set_state(*poses[0])
+        od = O.Odometry()
+        t0 = time.perf_counter()
+        ncpu = 6
+        for k in range(ncpu):
+            r = O.scan_register(raws[k], 64, 5.0)
+            _, (wq, wt), _ = od.step(r["sharp"], r["less_sharp"], r["flat"], r["less_flat"])
+            om.step(r["less_sharp"], r["less_flat"], wq, wt)
+        res["cpu_baseline"] = {"value": ncpu / (time.perf_counter() - t0), "unit": "sweeps/s", "cores": 1, "kind": "port",
+                               "sample": f"the first {ncpu} sweeps of the same sequence through the oracle's three stages on 1 host thread"}
+        om.close()
+    ctx.close()
+    return res
+
+
+def leg_c2_odometry(L, cm, sm):
+    """BASELINE config C-2: HDL-32 synthetic sweeps (~52 k returns), scan-to-scan laserOdometry (lmono_odom_step) on the
+    four feature clouds of our scanRegistration; CPU beside it = oracle Odometry on the same clouds."""
+    api, torch = L.api, L.torch
+    wld = synth.make_world(seed=20261018)
+    rng = np.random.default_rng(3)
+    n_sw = 26
+    ctx = api.Context(device=L.local, stream=L.main.cuda_stream, scan_line=32, minimum_range=0.3,
+                      mapping_line_resolution=0.2, mapping_plane_resolution=0.4, max_cubes_corner=8, max_cubes_surf=8,
+                      cube_capacity_corner=1024, cube_capacity_surf=1024)          # Aloam/launch/aloam_velodyne_HDL_32.launch:3-13
+    feats, npts = [], []
+    for k in range(n_sw):
+        q_, t_ = synth.loop_pose(wld, 1.0 * k)
+        raw = np.ascontiguousarray(synth.raycast_sweep_torch(wld, q_, t_, 32, 1875, rng, device=L.dev), np.float32)
+        r = ctx.scan_register(raw)
+        feats.append(tuple(torch.from_numpy(np.ascontiguousarray(r[k_])).pin_memory() for k_ in ("sharp", "less_sharp", "flat", "less_flat")))
+        npts.append(len(raw))
+    ctx.odom_reset()
+    wall, ker, e2e_dev = [], [], []
+    for k, f in enumerate(feats):
+        L.flush.fill_(k & 0xFF)
+        L.torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        (lq, lt), (wq, wt), rep = ctx.odom_step(*[a.numpy() for a in f])
+        dt = time.perf_counter() - t0
+        a_, b_ = ctx.stage_times()
+        if k >= 4:
+            wall.append(dt)
+            e2e_dev.append(a_)
+            ker.append(b_)
+    truth = float(np.linalg.norm(synth.loop_pose(wld, float(n_sw - 1))[1] - synth.loop_pose(wld, 0.0)[1]))
+    drift = float(np.linalg.norm(wt)) - truth       # scan-to-scan odometry warm-starts from the previous increment: the first sweeps lag (the oracle too)
+    assert rep.inited == 1 and abs(float(np.linalg.norm(lt)) - 1.0) < 0.08, (lt, drift)      # the sensor moves 1 m per sweep
+    gpu_final = (wq.copy(), wt.copy())
+    # per-kernel device times (event after every launch)
+    ctx.odom_reset()
+    ctx.kernel_marks_enable(True)
+    for f in feats[:12]:
+        ctx.odom_step(*[a.numpy() for a in f])
+    per, cnt = _marks_per_launch(ctx)
+    ctx.kernel_marks_enable(False)
+    n_s, n_ls, n_f, n_lf = (int(np.mean([len(f[i]) for f in feats])) for i in range(4))
+    nn_bytes = 16.0 * (n_ls + n_lf) + 24.0 * (n_s + n_f)
+    value = 1e3 / float(np.mean(ker))
+    res = {"metric": "scan-to-scan odometry sweeps/s (HDL-32)", "value": value, "unit": "sweeps/s", "ms_per_sweep_kernels": float(np.mean(ker)),
+           "config": {"workload": "C-2 HDL-32 synthetic sweeps (32 beams x 1875 azimuth steps), lmono_odom_step on sharp / less-sharp / flat / less-flat",
+                      "points_per_sweep": int(np.mean(npts)), "features": [n_s, n_ls, n_f, n_lf], "sweeps_timed": len(ker),
+                      "l2": "flushed before every sweep (256 MiB write)"},
+           "e2e": {"value": 1.0 / float(np.mean(wall)), "unit": "sweeps/s", "h2d_bytes_per_step": 16 * (n_s + n_ls + n_f + n_lf), "d2h_bytes_per_step": 400,
+                   "ms_per_sweep_device_with_uploads": float(np.mean(e2e_dev))},
+           "corner_corr": list(rep.corner_corr), "plane_corr": list(rep.plane_corr), "travelled_minus_truth_m": drift,
+           "kernel_us_per_launch": {k: round(1e3 * v, 2) for k, v in sorted(per.items(), key=lambda kv: -kv[1] * cnt[kv[0]])},
+           "roofline": dict(_roof("k_odom_nn1", nn_bytes, per.get("k_odom_nn1"), L.hbm_peak,
+                                  "1-NN of every sharp / flat feature in the previous sweep's less-sharp / less-flat cloud: every target read once (16 B), "
+                                  "16 B query + 8 B result per feature") or {}, bound="hbm", peak=L.hbm_peak, peak_source=L.peak_src, traffic=None,
+                            note="targets are L2 / shared-memory resident: the kernel is bound by the distance evaluations, not by HBM")}
+    if L.cpu:
+        import oracle_lib as O
+        od = O.Odometry()
+        t0 = time.perf_counter()
+        for f in feats:
+            _, (oq, ot), _ = od.step(*[a.numpy() for a in f])
+        res["max_position_difference_vs_cpu_m"] = float(np.linalg.norm(ot - gpu_final[1]))
+        assert res["max_position_difference_vs_cpu_m"] < 1e-3
+        res["cpu_baseline"] = {"value": len(feats) / (time.perf_counter() - t0), "unit": "sweeps/s", "cores": 1, "kind": "port",
+                               "sample": f"{len(feats)} sweeps of the same sequence through the oracle's laserOdometry (KD-tree rebuild, 2 x Ceres-style solve) on 1 host thread"}
+    ctx.close()
+    return res
+
+
+def leg_colour_frame(L, cm, sm):
+    """BASELINE config C-5, second half: lmono_project_color of a ~120 k-point sweep into a 1241 x 376 BGR frame (pinhole
+    of kitti00_cam.yaml, FULL 5 kernel + bilateral blur), cloud lifted and transformed to the world."""
+    api, torch = L.api, L.torch
+    W, H = 1241, 376
+    rng = np.random.default_rng(5)
+    bgr = torch.from_numpy(rng.integers(0, 256, (H, W, 3), dtype=np.uint8)).pin_memory()
+    wld = synth.make_world()
+    q_, t_ = synth.loop_pose(wld, 40.0)
+    raw = np.ascontiguousarray(synth.raycast_sweep_torch(wld, q_, t_, 64, 1875, rng, device=L.dev), np.float32)
+    # LiDAR frame (x forward, y left, z up) -> camera frame (z forward, x right, y down)
+    T = np.array([[0.0, -1.0, 0.0, 0.0], [0.0, 0.0, -1.0, -0.08], [1.0, 0.0, 0.0, -0.27]])
+    cam = api.Pinhole(718.856, 718.856, 607.1928, 185.2157, 0.0, 0.0, 0.0, 0.0, W, H, 0, 5, 0)
+    ctx = api.Context(device=L.local, stream=L.main.cuda_stream, max_cubes_corner=8, max_cubes_surf=8, cube_capacity_corner=1024, cube_capacity_surf=1024)
+    pts = torch.from_numpy(raw).pin_memory()
+    outbuf = api.ColorBuffers(W, H, pinned=True)                       # caller-owned page-locked outputs, reused every frame
+    wall, ker, dev_all = [], [], []
+    nrep = 24
+    for k in range(nrep):
+        L.flush.fill_(k & 0xFF)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = ctx.project_color(pts.numpy(), bgr.numpy(), cam, q_, t_, T_cam_lidar=T, out=outbuf)
+        dt = time.perf_counter() - t0
+        a_, b_ = ctx.stage_times()
+        if k >= 4:
+            wall.append(dt)
+            dev_all.append(a_)
+            ker.append(b_)
+    n_out = len(out["cloud_world"])
+    assert n_out > 10_000
+    ctx.kernel_marks_enable(True)
+    for k in range(8):
+        ctx.project_color(pts.numpy(), bgr.numpy(), cam, q_, t_, T_cam_lidar=T)
+    per, cnt = _marks_per_launch(ctx)
+    ctx.kernel_marks_enable(False)
+    npix = W * H
+    alg = 16.0 * len(raw) + 3.0 * npix + 2.0 * npix * 8 + 4.0 * npix + 27.0 * n_out      # SURVEY 8d: <= 24 MB / frame
+    tot_ms = float(np.mean(ker))
+    top = max(per.items(), key=lambda kv: kv[1] * cnt[kv[0]])[0] if per else None
+    res = {"metric": "colour frames/s (120 k points -> 1241 x 376)", "value": 1e3 / tot_ms, "unit": "frames/s", "ms_per_frame_kernels": tot_ms,
+           "config": {"workload": "lmono_project_color: extrinsic transform, 8-bit inverse-depth raster (last point wins), depthFill "
+                                  "(dilate FULL 5, close, dilate 7, median 5, bilateral 5), per-pixel lift + colour + world transform",
+                      "points": int(len(raw)), "image": [W, H], "points_out": int(n_out), "l2": "flushed before every frame"},
+           "e2e": {"value": 1.0 / float(np.mean(wall)), "unit": "frames/s",
+                   "h2d_bytes_per_step": int(raw.nbytes + bgr.numel()), "d2h_bytes_per_step": int(2 * npix + n_out * 27 + 4),
+                   "ms_per_frame_device_with_uploads": float(np.mean(dev_all))},
+           "kernel_us_per_launch": {k: round(1e3 * v, 2) for k, v in sorted(per.items(), key=lambda kv: -kv[1] * cnt[kv[0]])},
+           "roofline": {"bound": "hbm", "kernel": "all 13 launches of one frame (k_col_*): a chain of 466 k-pixel image passes", "what": "SURVEY 8d colour frame: "
+                        "16 B x points + 3 B x pixels (frame) + 8 image passes x (1 r + 1 w) B x pixels + 4 B x pixels (winner) + 27 B x lifted points",
+                        "algorithmic_bytes_per_launch": alg, "avg_launch_ms": tot_ms, "achieved": alg / (tot_ms * 1e-3) / 1e9, "peak": L.hbm_peak,
+                        "frac": alg / (tot_ms * 1e-3) / 1e9 / L.hbm_peak, "unit": "GB/s", "peak_source": L.peak_src, "traffic": None, "largest_kernel": top}}
+    if L.cpu:
+        import oracle_lib as O
+        ocam = O.make_camera(width=W, height=H)
+        t0 = time.perf_counter()
+        ncpu = 3
+        for _ in range(ncpu):
+            pc = O.transform_cloud(raw, T)
+            dr = O.project_raster(np.concatenate([pc, np.zeros((len(pc), 1), np.float32)], 1), ocam)
+            df = O.depth_fill(dr, ocam)
+            O.lift_cloud(df, bgr.numpy(), ocam, q_, t_)
+        res["cpu_baseline"] = {"value": ncpu / (time.perf_counter() - t0), "unit": "frames/s", "cores": 1, "kind": "port",
+                               "sample": f"{ncpu} frames of the same input through the oracle's colour path (transform, raster, depthFill, lift) on 1 host thread"}
+        assert np.array_equal(df, out["depth"]), "colour frame differs from the oracle"
+    ctx.close()
+    return res
+
+
+def leg_c1_cpu_pipeline(L, cm, sm):
+    """BASELINE config C-1: the reference's own CPU-runnable case -- HDL-64 sweeps through scanRegistration + laserOdometry +
+    laserMapping on ONE host thread per stage (oracle restatement of the PCL / Ceres path), per-stage milliseconds like the
+    reference's own timers (scanRegistration.cpp:409-410, laserOdometry.cpp:592-593, laserMapping.cpp:784-804); the same
+    sweeps through lmono_sweep_step beside it."""
+    if not L.cpu:
+        return {"skipped": "CPU legs run on rank 0 of a 1-GPU run only"}
+    import oracle_lib as O
+    api = L.api
+    wld = synth.make_world()
+    rng = np.random.default_rng(4)
+    n_sw = 16
+    raws = [np.ascontiguousarray(synth.raycast_sweep_torch(wld, *synth.loop_pose(wld, 1.0 * k), 64, 1875, rng, device=L.dev), np.float32) for k in range(n_sw)]
+    od, om = O.Odometry(), O.Mapper()
+    ms = {"scan_registration": [], "odometry": [], "mapping": []}
+    sub = {"ms_tree": 0.0, "ms_assoc": 0.0, "ms_solver": 0.0, "ms_filter": 0.0, "ms_add": 0.0, "ms_shift": 0.0}
+    cpu_t = []
+    for k, raw in enumerate(raws):
+        t0 = time.perf_counter()
+        r = O.scan_register(raw, 64, 5.0)
+        t1 = time.perf_counter()
+        _, (wq, wt), _ = od.step(r["sharp"], r["less_sharp"], r["flat"], r["less_flat"])
+        t2 = time.perf_counter()
+        mq, mt, mrep, _ = om.step(r["less_sharp"], r["less_flat"], wq, wt)
+        t3 = time.perf_counter()
+        cpu_t.append(mt)
+        if k >= 2:
+            ms["scan_registration"].append(1e3 * (t1 - t0)); ms["odometry"].append(1e3 * (t2 - t1)); ms["mapping"].append(1e3 * (t3 - t2))
+            for key in sub:
+                sub[key] += getattr(mrep, key)
+    nt = len(ms["mapping"])
+    stage = {k: float(np.mean(v)) for k, v in ms.items()}
+    ctx = api.Context(device=L.local, stream=L.main.cuda_stream)
+    gpu_wall, gms = [], {"scan_registration": [], "odometry": [], "mapping": []}
+    worst = 0.0
+    for k, raw in enumerate(raws):
+        t0 = time.perf_counter()
+        o = ctx.sweep_step(raw)
+        dt = time.perf_counter() - t0
+        worst = max(worst, float(np.linalg.norm(o[2][1] - cpu_t[k])))
+        if k >= 2:
+            gpu_wall.append(dt)
+            gms["scan_registration"].append(o[3].ms_gpu); gms["odometry"].append(o[4].ms_gpu); gms["mapping"].append(o[5].ms_gpu)
+    ctx.close()
+    od.close() if hasattr(od, "close") else None
+    om.close()
+    assert worst < 1e-3, worst
+    tot = sum(stage.values())
+    return {"config": {"workload": "C-1 HDL-64 synthetic KITTI-shaped sweeps (64 beams x 1875 azimuth steps, ~113 k returns) through scanRegistration -> "
+                                   "laserOdometry -> laserMapping, map grown from empty", "sweeps_timed": nt, "points_per_sweep": int(len(raws[0]))},
+            "cpu_ms_per_sweep": {k: round(v, 2) for k, v in stage.items()}, "cpu_ms_per_sweep_total": round(tot, 2),
+            "cpu_mapping_phases_ms": {k: round(v / nt, 3) for k, v in sub.items()},
+            "cpu_baseline": {"value": 1e3 / tot, "unit": "sweeps/s", "cores": 1, "kind": "port",
+                             "sample": f"{nt} sweeps, one host thread (the reference runs one single-threaded node per stage: 3 cores give 1000 / max(stage) = "
+                                       f"{1e3 / max(stage.values()):.1f} sweeps/s pipelined)"},
+            "gpu_ms_per_sweep_device": {k: round(float(np.mean(v)), 4) for k, v in gms.items()},
+            "gpu_sweeps_per_s_e2e": 1.0 / float(np.mean(gpu_wall)),
+            "max_position_difference_vs_cpu_m": worst}
+
+
+def c5_map(tiles, cm, sm):
+    """the C-3 tile (250 x 250 m, cube-aligned) repeated on a lattice of 250 m pitch and cropped to the cube ring the
+    reference's 21 x 21 x 11 grid can hold around the origin (+-525 m): C-3 density everywhere"""
+    offs = (np.arange(tiles) - (tiles - 1) / 2.0) * 250.0
+    out = []
+    for pts in (cm, sm):
+        reps = []
+        for ox in offs:
+            for oy in offs:
+                p = pts.copy()
+                p[:, 0] += np.float32(ox)
+                p[:, 1] += np.float32(oy)
+                reps.append(p)
+        a = np.concatenate(reps)
+        keep = (np.abs(a[:, 0]) < 524.0) & (np.abs(a[:, 1]) < 524.0)
+        out.append(np.ascontiguousarray(a[keep]))
+    return out[0], out[1]
+
+
+def leg_c5_sharded(L, args):
+    """BASELINE config C-5: the largest map the reference's cube ring holds at C-3 density, sharded by cube over the N GPUs
+    (lmono_shard_owner_of_cube), C-3 sweeps at 64 poses spread over it.  Two exchange modes: "nccl" = the host issues a
+    real ncclAllReduce of the 35 doubles after every evaluation (11 per registration, torch.distributed); "p2p" = the
+    kernels all-gather over NVLink peer memory themselves (one graph launch per registration, no host collective)."""
+    import torch.distributed as dist
+    from lmono_b200 import shard
+    api, torch = L.api, L.torch
+    rank, world = L.rank, L.world
+    _, cm, sm, sweeps = make_workload(0, n_sweeps=8)                 # identical on every rank: queries and poses are replicated
+    gcm, gsm = c5_map(args.c5_tiles, cm, sm)
+    inner = [o for o in (np.arange(args.c5_tiles) - (args.c5_tiles - 1) / 2.0) * 250.0 if abs(o) <= 260.0]     # the window must not push the ring
+    poses = []
+    for i in range(64):
+        c, s, q, t, qp, tp = sweeps[i % len(sweeps)]
+        off = np.array([inner[(i // len(sweeps)) % len(inner)], inner[(i // (len(sweeps) * len(inner))) % len(inner)], 0.0])
+        poses.append((i % len(sweeps), qp, tp + off, t + off))
+    d_sw = [(torch.from_numpy(c).to(L.dev), torch.from_numpy(s).to(L.dev)) for (c, s, *_r) in sweeps]
+    big = dict(max_cubes_corner=1024, max_cubes_surf=1024)
+    ident = ([0, 0, 0, 1], [0, 0, 0])
+
+    def sync_all():
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+
+    out = {"config": {"workload": "C-5 cube-sharded global map: C-3 tile repeated over the 1050 x 1050 m cube ring of the reference's 21x21x11 grid "
+                                  "(laserMapping.cpp:74-82: the ring is the limit, a 50 M-point map would not fit it at this density), "
+                                  "C-3 sweeps (~16 k queries) at 64 poses on a 3 x 3 lattice of tile centres, map update included",
+                      "global_map_points": int(len(gcm) + len(gsm)), "ranks": world, "ownership": "cyclic (gi + 3 gj + 5 gk) mod N, 1.25 m voxel-complete halo"}}
+    # parity reference: rank 0 also holds the whole map unsharded
+    ref = None
+    if rank == 0:
+        ref = api.Context(device=L.local, stream=L.main.cuda_stream, **big)
+        for which, pts in ((0, gcm), (1, gsm)):
+            for chunk in shard.cube_chunks(pts):
+                ref.map_import(which, np.ascontiguousarray(chunk))
+    n_par = 6
+    ref_res = []
+    if rank == 0:
+        for i in range(n_par):
+            k, qp, tp, tt = poses[i]
+            ref.map_set_state(*ident)
+            ref.map_step_device(d_sw[k][0].data_ptr(), d_sw[k][0].shape[0], d_sw[k][1].data_ptr(), d_sw[k][1].shape[0], qp, tp)
+            ref_res.append(ref.map_collect())
+        ref.close()
+    steps = max(8, min(args.steps, 64))
+    for mode in ("nccl", "p2p"):
+        ctx = api.Context(device=L.local, stream=L.main.cuda_stream, **big)
+        if mode == "nccl":
+            m = shard.ShardedMapper.on_gpu(ctx, L.dev)
+            ar_ev = []
+            base_ar = m._allreduce
+
+            def timed_allreduce(m=m, ar_ev=ar_ev, base_ar=base_ar):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(L.main); base_ar(); e1.record(L.main)
+                ar_ev.append((e0, e1))
+            m._allreduce = timed_allreduce
+            imp = lambda which, pts: [m.e.import_points(which, np.ascontiguousarray(ch)) for ch in shard.cube_chunks(pts)]
+        else:
+            m = shard.PeerMemoryMapper.connect(ctx)
+            imp = lambda which, pts: m.import_global(which, pts, prefilter=False)
+        imp(0, gcm); imp(1, gsm)                                       # the device keeps owner + halo points (d_shard_keep)
+        kept = len(ctx.map_export(0, 1)) + len(ctx.map_export(1, 1))
+        worst = 0.0
+        for i in range(n_par):                                         # parity vs the unsharded ctx (rank 0 holds the reference results)
+            k, qp, tp, tt = poses[i]
+            ctx.map_set_state(*ident)
+            m.step(d_sw[k][0].data_ptr(), d_sw[k][0].shape[0], d_sw[k][1].data_ptr(), d_sw[k][1].shape[0], qp, tp)
+            gq, gt, grep = m.collect()
+            if rank == 0:
+                rq, rt, rrep = ref_res[i]
+                assert list(grep.corner_num) == list(rrep.corner_num) and list(grep.surf_num) == list(rrep.surf_num), (mode, i)
+                assert [x.iterations for x in grep.solve] == [x.iterations for x in rrep.solve], (mode, i)
+                worst = max(worst, float(np.linalg.norm(gt - rt)))
+                assert worst <= 1e-4, (mode, i, worst)
+            assert grep.optimized == 1 and np.linalg.norm(gt - tt) < 0.1, (mode, i)
+        if mode == "nccl":
+            ar_ev.clear()
+        else:
+            ctx.shard_xchg_stats(reset=True)
+        sync_all()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t0 = time.perf_counter()
+        for i in range(steps):
+            k, qp, tp, tt = poses[(n_par + i) % len(poses)]
+            L.flush.fill_(i & 0xFF)
+            ctx.map_set_state(*ident)
+            ev[i][0].record(L.main)
+            m.step(d_sw[k][0].data_ptr(), d_sw[k][0].shape[0], d_sw[k][1].data_ptr(), d_sw[k][1].shape[0], qp, tp)
+            ev[i][1].record(L.main)
+        host_s = time.perf_counter() - t0
+        sync_all()
+        gq, gt, grep = m.collect()
+        assert grep.optimized == 1 and np.linalg.norm(gt - poses[(n_par + steps - 1) % len(poses)][3]) < 0.1
+        tot_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+        t_ = torch.tensor([tot_ms, host_s * 1e3], dtype=torch.float64, device=L.dev)
+        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        tot_ms, host_ms = float(t_[0]), float(t_[1])
+        r = {"value": steps / (max(tot_ms, host_ms) * 1e-3), "unit": "registrations/s", "ms_per_registration_device": tot_ms / steps,
+             "ms_per_registration_host_enqueue": host_ms / steps, "registrations_timed": steps, "points_kept_this_rank": int(kept),
+             "max_translation_difference_vs_unsharded_m": worst if rank == 0 else None}
+        if mode == "nccl":
+            ar_ms = float(sum(a.elapsed_time(b) for a, b in ar_ev))
+            r["allreduce_ms_per_registration"] = ar_ms / steps
+            r["kernel_ms_per_registration"] = (tot_ms - ar_ms) / steps
+            r["host_allreduces_per_registration"] = len(ar_ev) / steps
+        else:
+            st = ctx.shard_xchg_stats()
+            r["device_exchanges_per_registration"] = st["exchanges"] / steps
+            r["exchange_us_each_post_plus_wait"] = st["wait_ns"] / max(st["exchanges"], 1) / 1e3
+            r["exchange_ms_per_registration"] = st["wait_ns"] / 1e6 / steps
+        out[mode] = r
+        sync_all()
+        ctx.close()
+    return out
+
 
 
 _REAL_STDOUT = None
@@ -572,9 +986,14 @@ def main():
     ap.add_argument("--sequences", type=int, default=8, help="independent sequences per GPU (one ctx + stream each)")
     ap.add_argument("--more-sequences", type=int, default=16, help="extra value leg with this many sequences per GPU (0 = skip)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-pipeline", action="store_true", help="skip the fused-sweep (scanRegistration -> odometry -> mapping) leg")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip every extra leg")
     ap.add_argument("--cpu-steps", type=int, default=60)
+    ap.add_argument("--legs", default="fused_sweep,c2_odometry,colour_frame,c1_cpu_pipeline,c5_sharded",
+                    help="extra legs (keys of the same JSON line): the other BASELINE configs; c5_sharded runs when N > 1")
+    ap.add_argument("--c5-tiles", type=int, default=5, help="C-5 map = the C-3 tile repeated on a tiles x tiles lattice of 250 m pitch, cropped to the 1050 m cube ring")
     args = ap.parse_args()
+    if args.no_pipeline:
+        args.legs = ""
     if args.impl == "reference":
         if args.steps > 40:
             args.steps = 40          # bounded sample: ~1 s of CPU per registration

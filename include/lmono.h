@@ -131,6 +131,9 @@ const char* lmono_strerror(int code);
 /* device-side fault bits raised since the last call (0 = none); clears them. */
 int  lmono_last_fault(lmono_ctx* ctx, uint32_t* bits);
 int  lmono_sync(lmono_ctx* ctx);
+/* Device time (CUDA events on the ctx stream) of the most recent lmono_scan_register / lmono_odom_step /
+ * lmono_project_color call: uploads + kernels, and kernels only (inputs resident in HBM). */
+int  lmono_stage_times(lmono_ctx* ctx, float* ms_with_uploads /*may be NULL*/, float* ms_kernels /*may be NULL*/);
 /* number of kernels this ctx has launched so far (bench.py reports it as gpu_launches). */
 int64_t lmono_launch_count(const lmono_ctx* ctx);
 
@@ -231,6 +234,22 @@ int lmono_shard_lm_begin(lmono_ctx* ctx, int32_t solve_index);
 int lmono_shard_lm_eval(lmono_ctx* ctx, int32_t solve_index);
 int lmono_shard_lm_control(lmono_ctx* ctx, int32_t solve_index);
 int lmono_shard_end(lmono_ctx* ctx);
+/* Peer-memory mode of the sharded map: the all-reduce is done by the kernels themselves over NVLink peer memory, so a
+ * sharded registration is ONE enqueue (lmono_map_step_device / lmono_map_step, replayed as one CUDA graph) with no host
+ * call, NCCL launch or synchronisation inside it.  Setup, once per rank (one rank = one GPU = one ctx, <= 16 ranks):
+ *   lmono_shard_xchg_create  allocates this rank's exchange block; returns its cudaIpcMemHandle_t (64 bytes) for ranks
+ *                            in other processes and its device pointer for ranks that are contexts of this process;
+ *   [the host gathers the handles of all ranks over any transport: torch.distributed, MPI, a file]
+ *   lmono_shard_xchg_open    maps the peers' blocks (ipc_handles: [nranks][64]; same_process_ptrs[r] != NULL replaces
+ *                            handle r) and switches the ctx to this mode; also sets rank / nranks like
+ *                            lmono_shard_configure.  All ranks must then issue the same sequence of registrations.
+ * A rank whose peer does not answer within 2 s raises fault bit 6 (LMONO_E_DEVICE from lmono_map_collect) instead of
+ * hanging.  lmono_shard_xchg_stats: {exchanges completed, ns spent posting + waiting for the slowest rank, exchanges
+ * counted in the ns figure}. */
+int lmono_shard_xchg_create(lmono_ctx* ctx, void* ipc_handle_out /*[64], may be NULL*/, void** local_ptr_out /*may be NULL*/);
+int lmono_shard_xchg_open(lmono_ctx* ctx, int32_t rank, int32_t nranks, const void* ipc_handles /*[nranks][64], may be NULL*/,
+                          void* const* same_process_ptrs /*[nranks], may be NULL*/);
+int lmono_shard_xchg_stats(lmono_ctx* ctx, uint64_t out[3], int32_t reset);
 /* owner rank of the cube containing a world point / of an absolute cube coordinate (cube 0 is centred on the origin) */
 int32_t lmono_shard_owner_of_cube(int32_t gi, int32_t gj, int32_t gk, int32_t nranks);
 

@@ -199,6 +199,12 @@ class Context:
     def launch_count(self) -> int:
         return int(self.L.lmono_launch_count(self._h))
 
+    def stage_times(self):
+        """(ms uploads + kernels, ms kernels only) of the last scan_register / odom_step / project_color call"""
+        a, b = C.c_float(0), C.c_float(0)
+        self._chk(self.L.lmono_stage_times(self._h, C.byref(a), C.byref(b)), "stage_times")
+        return a.value, b.value
+
     def last_fault(self) -> int:
         bits = C.c_uint32(0)
         self._chk(self.L.lmono_last_fault(self._h, C.byref(bits)), "last_fault")
@@ -340,6 +346,29 @@ class Context:
                                              g.ctypes.data_as(C.c_void_p), C.byref(cost), C.byref(nc), C.byref(ns)), "map_normal_eq")
         return H.reshape(6, 6), g, cost.value, nc.value, ns.value
 
+    # -- cube-sharded map, peer-memory mode (include/lmono.h: lmono_shard_xchg_*)
+    def shard_xchg_create(self):
+        """(64-byte cudaIpcMemHandle_t as bytes, device pointer) of this rank's exchange block"""
+        h = C.create_string_buffer(64)
+        p = C.c_void_p()
+        self._chk(self.L.lmono_shard_xchg_create(self._h, h, C.byref(p)), "shard_xchg_create")
+        return h.raw, p.value
+
+    def shard_xchg_open(self, rank, nranks, handles=None, same_process_ptrs=None):
+        hb = None
+        if handles is not None:
+            assert len(handles) == nranks and all(len(x) == 64 for x in handles)
+            hb = C.create_string_buffer(b"".join(handles), 64 * nranks)
+        pp = None
+        if same_process_ptrs is not None:
+            pp = (C.c_void_p * nranks)(*[C.c_void_p(x) if x else None for x in same_process_ptrs])
+        self._chk(self.L.lmono_shard_xchg_open(self._h, rank, nranks, hb, pp), "shard_xchg_open")
+
+    def shard_xchg_stats(self, reset=False):
+        out = (C.c_uint64 * 3)()
+        self._chk(self.L.lmono_shard_xchg_stats(self._h, out, 1 if reset else 0), "shard_xchg_stats")
+        return {"epoch": int(out[0]), "wait_ns": int(out[1]), "exchanges": int(out[2])}
+
     # -- scanRegistration
     def scan_register(self, raw, want_debug=False):
         """raw: float32 [n,4] (KITTI .bin layout) or [n,3].  Returns dict of clouds, labels, report."""
@@ -395,18 +424,16 @@ class Context:
         return ci[:n_sharp], pi[:n_flat]
 
     # -- colour projection (mono_lidar_mapping map builder)
-    def project_color(self, pts, bgr, cam: "Pinhole", q, t, T_cam_lidar=None, want_cam=True):
-        """pts: float32 [n,3|4] (camera frame, or LiDAR frame with T_cam_lidar = 3x4); bgr: uint8 [H,W,3]."""
-        p = np.ascontiguousarray(pts, np.float32)
-        img = np.ascontiguousarray(bgr, np.uint8)
+    def project_color(self, pts, bgr, cam: "Pinhole", q, t, T_cam_lidar=None, want_cam=True, out: "ColorBuffers" = None):
+        """pts: float32 [n,3|4] (camera frame, or LiDAR frame with T_cam_lidar = 3x4); bgr: uint8 [H,W,3].
+        out: caller-owned output buffers to reuse (ColorBuffers; page-locked ones make the read-back a DMA)."""
+        p = pts if (pts.dtype == np.float32 and pts.flags["C_CONTIGUOUS"]) else np.ascontiguousarray(pts, np.float32)
+        img = bgr if (bgr.dtype == np.uint8 and bgr.flags["C_CONTIGUOUS"]) else np.ascontiguousarray(bgr, np.uint8)
         H, W = img.shape[:2]
         assert (W, H) == (cam.width, cam.height)
         npix = W * H
-        raw = np.zeros((H, W), np.uint8)
-        fill = np.zeros((H, W), np.uint8)
-        cc = np.zeros((npix, 3), np.float32)
-        cw = np.zeros((npix, 3), np.float32)
-        rgb = np.zeros((npix, 3), np.uint8)
+        b = out or ColorBuffers(W, H)
+        assert (b.W, b.H) == (W, H)
         n = C.c_int32(0)
         pose = Pose.make(q, t)
         T = None
@@ -414,16 +441,35 @@ class Context:
             T = np.ascontiguousarray(T_cam_lidar, np.float64).reshape(12)
         vp = lambda a: a.ctypes.data_as(C.c_void_p)
         rc = self.L.lmono_project_color(self._h, view_of(p), vp(T) if T is not None else None, vp(img), C.c_int32(img.strides[0]),
-                                        C.byref(cam), C.byref(pose), vp(raw), vp(fill), vp(cc) if want_cam else None,
-                                        vp(cw), vp(rgb), npix, C.byref(n))
+                                        C.byref(cam), C.byref(pose), vp(b.raw), vp(b.fill), vp(b.cc) if want_cam else None,
+                                        vp(b.cw), vp(b.rgb), npix, C.byref(n))
         self._chk(rc, "project_color")
-        return {"depth_raw": raw, "depth": fill, "cloud_cam": cc[: n.value], "cloud_world": cw[: n.value], "rgb": rgb[: n.value]}
+        return {"depth_raw": b.raw, "depth": b.fill, "cloud_cam": b.cc[: n.value], "cloud_world": b.cw[: n.value], "rgb": b.rgb[: n.value]}
 
     def voxel_grid(self, pts, leaf):
         p = _xyzi(pts)
         buf, out = _out(len(p))
         self._chk(self.L.lmono_voxel_grid(self._h, view_of(p), C.c_float(leaf), C.byref(out)), "voxel_grid")
         return buf[: out.n_out].copy()
+
+
+class ColorBuffers:
+    """caller-owned outputs of lmono_project_color for a W x H frame (pinned=True: page-locked, via torch)"""
+
+    def __init__(self, W, H, pinned=False):
+        self.W, self.H = W, H
+        npix = W * H
+        if pinned:
+            import torch
+            self._keep = [torch.zeros(s_, dtype=d_).pin_memory() for s_, d_ in (((H, W), torch.uint8), ((H, W), torch.uint8), ((npix, 3), torch.float32),
+                                                                                ((npix, 3), torch.float32), ((npix, 3), torch.uint8))]
+            self.raw, self.fill, self.cc, self.cw, self.rgb = (t_.numpy() for t_ in self._keep)
+        else:
+            self.raw = np.zeros((H, W), np.uint8)
+            self.fill = np.zeros((H, W), np.uint8)
+            self.cc = np.zeros((npix, 3), np.float32)
+            self.cw = np.zeros((npix, 3), np.float32)
+            self.rgb = np.zeros((npix, 3), np.uint8)
 
 
 class BatchArgs:

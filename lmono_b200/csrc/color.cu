@@ -305,6 +305,8 @@ extern "C" int lmono_project_color(lmono_ctx* ctx, lmono_cloud_view pts, const d
   LM_CUDA(cudaMemcpyAsync(s->d_bgr, bgr, (size_t)step_bytes * H, cudaMemcpyHostToDevice, ctx->stream));
   if ((rc = lm_upload_cloud(ctx, pts, ctx->d_raw[2], s->d_pts, nullptr))) return rc;
   const int nb_pts = lm_div_up(pts.n > 0 ? pts.n : 1, 256), nb_pix = lm_div_up(npix, 256);
+  LM_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
+  lm_kmark(ctx, "begin", 0);
   if (T_cam_lidar && pts.n > 0) {
     Mat34 T; memcpy(T.m, T_cam_lidar, sizeof(T.m));
     k_col_transform<<<nb_pts, 256, 0, ctx->stream>>>(s->d_pts, pts.n, T); LM_LAUNCH_CHECK();

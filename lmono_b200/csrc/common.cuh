@@ -37,7 +37,27 @@ enum : unsigned {
   LM_FAULT_CELL_RANGE = 1u << 3,      // point outside its cube's cell table (internal error)
   LM_FAULT_FEATURE_OVERFLOW = 1u << 4,
   LM_FAULT_IMPORT_NONEMPTY = 1u << 5,
+  LM_FAULT_SHARD_TIMEOUT = 1u << 6,   // a peer rank did not post its partial sums within LM_XCHG_TIMEOUT_NS
 };
+
+// ---------------------------------------------------------------- cube-sharded map: peer-memory exchange block
+// One per rank, in that rank's HBM, mapped into every peer.  An exchange with sequence number `epoch` (1, 2, ...; the
+// same on every rank because all ranks run the same kernel sequence) uses slot epoch & 1: rank s stores its partial
+// sums into payload[slot][s] of EVERY rank (stores over NVLink), fences, then stores `epoch` into flag[slot][s] of every
+// rank with release semantics; a rank acquires its OWN flag[slot][0..n) (local polling, no NVLink reads) and sums the
+// payloads in rank order -> every rank gets the same bits.  Two slots suffice because a rank posts epoch e+1 only after
+// all its CTAs consumed epoch e (cluster barrier / kernel boundary between consecutive exchanges).
+constexpr int LM_SHARD_MAX = 16;
+constexpr int LM_XCHG_DOUBLES = 40;
+constexpr unsigned long long LM_XCHG_TIMEOUT_NS = 2000000000ull;   // a dead peer raises a fault instead of hanging the GPU
+struct LmShardXchg {
+  unsigned long long flag[2][LM_SHARD_MAX];
+  double payload[2][LM_SHARD_MAX][LM_XCHG_DOUBLES];
+  unsigned long long epoch;          // exchanges completed by this rank (advanced by the last kernel that exchanged)
+  unsigned long long wait_ns;        // time the publisher spent waiting for the slowest peer (statistics)
+  unsigned long long n_xchg;
+};
+struct LmShardPeers { LmShardXchg* peer[LM_SHARD_MAX]; int32_t rank, n; };
 
 // ---------------------------------------------------------------- device structs
 struct LmFactor {           // 64 B, one per query (kind < 0: no factor)
@@ -166,6 +186,8 @@ struct lmono_ctx {
   int last_cuda_error;
   int64_t launches;
   cudaEvent_t ev0, ev1;
+  cudaEvent_t ev_o0, ev_o1;     // odometry stage of a fused sweep (lmono_sweep_step)
+  cudaEvent_t ev_k0;            // after the uploads of a stage call: ev_k0 .. ev1 = the stage's kernels with inputs resident in HBM (lmono_stage_times)
   cudaEvent_t ev_fork;          // fork point of a sequence batch (lmono_map_step_device_batch)
   cudaEvent_t ev_join;          // end of this ctx's branch of a batch (capture join, or the legacy multi-stream join)
   cudaEvent_t ev_sync;          // orders a batch graph after earlier work on this ctx's own stream
@@ -215,6 +237,9 @@ struct lmono_ctx {
   bool step_pending;
   // cube-sharded mode (shard.cu): caller-owned device workspace the host all-reduces between kernels
   double* d_shard_ws; int shard_nc, shard_ns;
+  // peer-memory mode of the sharded map (shard.cu): every rank's exchange block is mapped into every other rank
+  // (cudaIpc over NVLink, or plain pointers inside one process); the LM solve kernel all-gathers its partial sums itself
+  bool shard_p2p; LmShardXchg* d_xchg; LmShardPeers* d_shard_peers; void* xchg_opened[LM_SHARD_MAX];
   // CUDA-graph replay of the laserMapping step (mapping.cu); LMONO_NO_GRAPH=1 disables it
   bool graphs_on; int n_graphs; LmGraphEntry graphs[LM_MAX_GRAPHS];
   // in-kernel %globaltimer stamps (ns) for latency studies (lmono_debug_stamps); 256 slots, written by thread 0 of CTA 0
@@ -362,11 +387,13 @@ __device__ __forceinline__ int d_cube_cell(float4 p, const int* g) {
 // every owned query's 5-NN local and exact; voxel-complete halos make the per-cube VoxelGrid
 // refilter of a halo copy reproduce the owner's centroids bit for bit.
 #define LM_SHARD_HALO 1.25
+// Cyclic: owner = (gi + 3 gj + 5 gk) mod n.  A 5x5x3 search window (and its ground layer, where most points are) then
+// spreads almost evenly over the ranks -- 1.07x (1.28x) the mean on the busiest of 8 ranks; a hash gave 1.5x (1.9x) --
+// and the busiest rank bounds every registration.  Not contiguous blocks: a window must not land on one GPU.
 __host__ __device__ __forceinline__ int lm_cube_owner(int gi, int gj, int gk, int nranks) {
   if (nranks <= 1) return 0;
-  uint32_t h = ((uint32_t)gi * 73856093u) ^ ((uint32_t)gj * 19349663u) ^ ((uint32_t)gk * 83492791u);
-  h ^= h >> 15; h *= 0x2c1b3c6du; h ^= h >> 12;
-  return (int)(h % (uint32_t)nranks);
+  const int v = (gi + 3 * gj + 5 * gk) % nranks;
+  return v < 0 ? v + nranks : v;
 }
 __device__ __forceinline__ bool d_shard_keep(float4 p, float leaf, float inv_leaf, int rank, int nranks) {
   if (nranks <= 1) return true;
@@ -393,6 +420,44 @@ __device__ __forceinline__ bool d_shard_keep(float4 p, float leaf, float inv_lea
     }
   }
   return false;
+}
+
+// ---- peer-memory all-gather + fixed-order sum of `nvals` doubles (cube-sharded map).  Called by ALL threads of a CTA
+// (blockDim.x >= max(nvals, n)); `in` / `out` are shared-memory arrays (may alias), `publisher` is CTA-uniform: exactly
+// one CTA per rank and exchange publishes, any number of CTAs may consume.
+__device__ __forceinline__ void d_st_release_sys_u64(unsigned long long* p, unsigned long long v) { asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long d_ld_acquire_sys_u64(const unsigned long long* p) { unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void d_st_relaxed_sys_f64(double* p, double v) { asm volatile("st.relaxed.sys.global.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory"); }
+__device__ __forceinline__ double d_ld_relaxed_sys_f64(const double* p) { double v; asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void d_shard_exchange(const LmShardPeers* __restrict__ peers, unsigned long long epoch, const double* in, double* out,
+                                                 int nvals, bool publisher, uint32_t* fault) {
+  const int rank = peers->rank, n = peers->n;
+  const int par = (int)(epoch & 1ull);
+  LmShardXchg* mine = peers->peer[rank];
+  const unsigned long long t_enter = d_globaltimer();
+  if (publisher) {
+    if ((int)threadIdx.x < nvals) {
+      const double v = in[threadIdx.x];
+      for (int r = 0; r < n; ++r) d_st_relaxed_sys_f64(&peers->peer[r]->payload[par][rank][threadIdx.x], v);
+      __threadfence_system();
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < n) d_st_release_sys_u64(&peers->peer[threadIdx.x]->flag[par][rank], epoch);
+  }
+  if ((int)threadIdx.x < n) {
+    const unsigned long long t0 = d_globaltimer();
+    while (d_ld_acquire_sys_u64(&mine->flag[par][threadIdx.x]) < epoch) {
+      if (d_globaltimer() - t0 > LM_XCHG_TIMEOUT_NS) { atomicOr(fault, LM_FAULT_SHARD_TIMEOUT); break; }
+    }
+  }
+  __syncthreads();
+  if (publisher && threadIdx.x == 0) { mine->wait_ns += d_globaltimer() - t_enter; mine->n_xchg += 1; }   // statistics: post + wait for the slowest rank
+  if ((int)threadIdx.x < nvals) {
+    double s = 0.0;
+    for (int r = 0; r < n; ++r) s += d_ld_relaxed_sys_f64(&mine->payload[par][r][threadIdx.x]);
+    out[threadIdx.x] = s;
+  }
+  __syncthreads();
 }
 
 // block-wide exclusive scan of one int per thread (blockDim.x <= 1024, multiple of 32).
@@ -565,7 +630,10 @@ int lm_knn5_device(lmono_ctx* ctx, int which, const float4* d_q, int n, int32_t*
 // lm.cu
 int lm_solve_enqueue(lmono_ctx* ctx, int solve_index, int n_max_corner, int n_max_surf, int max_iter);
 int lm_normal_eq_enqueue(lmono_ctx* ctx, int n_max_corner, int n_max_surf);
-int lm_solve_problem(lmono_ctx* ctx, const LmProblem& P, int n_max, int max_iter, int write_back);
+int lm_solve_problem(lmono_ctx* ctx, const LmProblem& P, int n_max, int max_iter, int write_back, bool shard_exchange = false);
+// shard.cu: peer-memory gate exchange (owned window counts -> the global :554 gate), one launch
+int lm_shard_gate_xchg(lmono_ctx* ctx);
+void lm_shard_free(lmono_ctx* ctx);
 // sharded LM pieces: begin / partial evaluation into the workspace / controller from the reduced workspace
 int lm_shard_lm_begin(lmono_ctx* ctx, int solve_index);
 int lm_shard_lm_eval(lmono_ctx* ctx, int solve_index);

@@ -97,7 +97,7 @@ static int create_impl(lmono_ctx* ctx, void* stream) {
   ctx->sm_count = prop.multiProcessorCount;
   if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
   else { LM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
-  LM_CUDA(cudaEventCreate(&ctx->ev0)); LM_CUDA(cudaEventCreate(&ctx->ev1));
+  LM_CUDA(cudaEventCreate(&ctx->ev0)); LM_CUDA(cudaEventCreate(&ctx->ev1)); LM_CUDA(cudaEventCreate(&ctx->ev_k0)); LM_CUDA(cudaEventCreate(&ctx->ev_o0)); LM_CUDA(cudaEventCreate(&ctx->ev_o1));
   LM_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   LM_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   LM_CUDA(cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming));
@@ -164,6 +164,7 @@ extern "C" void lmono_destroy(lmono_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < ctx->n_graphs; ++i) cudaGraphExecDestroy(ctx->graphs[i].exec);
   lm_batch_free(ctx);
+  lm_shard_free(ctx);
   lm_scan_free(ctx);
   lm_odom_free(ctx);
   lm_color_free(ctx);
@@ -173,7 +174,7 @@ extern "C" void lmono_destroy(lmono_ctx* ctx) {
   for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_in[i]); cudaFree(ctx->d_stack[i]); cudaFree(ctx->d_world[i]); cudaFree(ctx->d_fac[i]); }
   cudaFree(ctx->d_sort_a); cudaFree(ctx->d_sort_b); cudaFree(ctx->d_sort_c); cudaFree(ctx->d_blockcnt); cudaFree(ctx->d_tmp_i32);
   cudaFree(ctx->d_vg); cudaFree(ctx->d_full); cudaFree(ctx->d_slot_first); cudaFree(ctx->d_slot_base); cudaFree(ctx->d_export_off); cudaFree(ctx->d_export);
-  cudaEvent_t evs[] = { ctx->ev0, ctx->ev1, ctx->ev_fork, ctx->ev_join, ctx->ev_sync, ctx->ev_done, ctx->ev_side0, ctx->ev_side1 };
+  cudaEvent_t evs[] = { ctx->ev0, ctx->ev1, ctx->ev_k0, ctx->ev_o0, ctx->ev_o1, ctx->ev_fork, ctx->ev_join, ctx->ev_sync, ctx->ev_done, ctx->ev_side0, ctx->ev_side1 };
   for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
   if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -191,6 +192,19 @@ extern "C" int lmono_debug_stamps(lmono_ctx* ctx, uint64_t* out, int32_t n) {
   if (!ctx || !out || n < 0 || n > 4096) return LMONO_E_ARG;
   LM_CUDA(cudaMemcpyAsync(out, ctx->d_stamps, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   LM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return LMONO_OK;
+}
+
+// device time of the most recent lmono_scan_register / lmono_odom_step / lmono_project_color call: whole call on the
+// stream (uploads + kernels) and kernels only (inputs resident in HBM)
+extern "C" int lmono_stage_times(lmono_ctx* ctx, float* ms_with_uploads, float* ms_kernels) {
+  if (!ctx) return LMONO_E_ARG;
+  LM_CUDA(cudaStreamSynchronize(ctx->stream));
+  float a = 0.f, b = 0.f;
+  if (cudaEventElapsedTime(&a, ctx->ev0, ctx->ev1) != cudaSuccess) { cudaGetLastError(); a = 0.f; }
+  if (cudaEventElapsedTime(&b, ctx->ev_k0, ctx->ev1) != cudaSuccess) { cudaGetLastError(); b = 0.f; }
+  if (ms_with_uploads) *ms_with_uploads = a;
+  if (ms_kernels) *ms_kernels = b;
   return LMONO_OK;
 }
 

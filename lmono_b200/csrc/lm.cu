@@ -431,7 +431,8 @@ __device__ __forceinline__ void d_warp_transpose_reduce32(double (&v)[32], int l
 }
 
 __global__ void __launch_bounds__(LMC_THREADS, 1)
-k_lm_solve_cluster(LmLmState* __restrict__ lm_g, LmProblem P, int max_iter, int write_back, unsigned long long* __restrict__ stamps) {
+k_lm_solve_cluster(LmLmState* __restrict__ lm_g, LmProblem P, int max_iter, int write_back, unsigned long long* __restrict__ stamps,
+                   const LmShardPeers* __restrict__ peers /*NULL: map not sharded over GPUs*/, uint32_t* __restrict__ fault) {
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank();
   const int csize = (int)cluster.num_blocks();
@@ -442,6 +443,11 @@ k_lm_solve_cluster(LmLmState* __restrict__ lm_g, LmProblem P, int max_iter, int 
   extern __shared__ uint4 s_cache[];                // [4][LMC_CACHE]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   LM_STAMP(stamps, 0);
+  // cube-sharded map (peer-memory mode): after the cluster-wide sum every rank all-gathers the 30-vectors of all ranks
+  // through the exchange blocks mapped over NVLink and adds them in rank order, so the replicated controllers of all
+  // GPUs see the same bits -- the collective is part of this kernel, there is no host or NCCL call inside a solve
+  const unsigned long long epoch0 = peers ? peers->peer[peers->rank]->epoch : 0ull;
+  unsigned int n_xchg = 0;
   const int n0 = *P.n0, n1 = *P.n1;
   const LmFactor* __restrict__ fac0 = P.fac0; const LmFactor* __restrict__ fac1 = P.fac1;
   if (threadIdx.x == 0) {
@@ -524,6 +530,7 @@ k_lm_solve_cluster(LmLmState* __restrict__ lm_g, LmProblem P, int max_iter, int 
       s_fin[threadIdx.x] = v;
     }
     __syncthreads();
+    if (peers) d_shard_exchange(peers, epoch0 + (++n_xchg), s_fin, s_fin, 32, crank == 0, fault);
     if (threadIdx.x == 0) {
       LmLmState* lm = &s_lm;
       if (lm->phase == 0) {
@@ -541,7 +548,10 @@ k_lm_solve_cluster(LmLmState* __restrict__ lm_g, LmProblem P, int max_iter, int 
     __syncthreads();
   }
   LM_STAMP(stamps, 2);
-  if (crank == 0 && threadIdx.x == 0) *lm_g = s_lm;     // test hooks read H, g, cost from here
+  if (crank == 0 && threadIdx.x == 0) {
+    *lm_g = s_lm;     // test hooks read H, g, cost from here
+    if (peers) peers->peer[peers->rank]->epoch = epoch0 + n_xchg;
+  }
   cluster.sync();                                        // nobody leaves while its shared memory may still be written
 }
 
@@ -601,8 +611,8 @@ static int eval_blocks(lmono_ctx* ctx, int n) {
   return b;
 }
 
-int lm_solve_problem(lmono_ctx* ctx, const LmProblem& P, int n_max, int max_iter, int write_back) {
-  if (!lm_use_launch_per_eval()) {
+int lm_solve_problem(lmono_ctx* ctx, const LmProblem& P, int n_max, int max_iter, int write_back, bool shard_exchange) {
+  if (!lm_use_launch_per_eval() || shard_exchange) {
     const int cs = lm_cluster_pick(ctx);
     if (cs < 0) return LMONO_E_CUDA;
     cudaLaunchConfig_t cfg = {};
@@ -610,7 +620,8 @@ int lm_solve_problem(lmono_ctx* ctx, const LmProblem& P, int n_max, int max_iter
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    LM_CUDA(cudaLaunchKernelEx(&cfg, k_lm_solve_cluster, ctx->d_lm, P, max_iter, write_back, ctx->d_stamps));
+    const LmShardPeers* peers = shard_exchange ? ctx->d_shard_peers : nullptr;
+    LM_CUDA(cudaLaunchKernelEx(&cfg, k_lm_solve_cluster, ctx->d_lm, P, max_iter, write_back, ctx->d_stamps, peers, &ctx->d_state->fault));
     LM_LAUNCH_CHECK();
     return LMONO_OK;
   }
@@ -637,7 +648,7 @@ static LmProblem map_problem(lmono_ctx* ctx, int solve_index) {
 }
 
 int lm_solve_enqueue(lmono_ctx* ctx, int solve_index, int n_max_corner, int n_max_surf, int max_iter) {
-  return lm_solve_problem(ctx, map_problem(ctx, solve_index), n_max_corner + n_max_surf, max_iter, 1);
+  return lm_solve_problem(ctx, map_problem(ctx, solve_index), n_max_corner + n_max_surf, max_iter, 1, ctx->shard_p2p);
 }
 
 int lm_normal_eq_enqueue(lmono_ctx* ctx, int n_max_corner, int n_max_surf) {

@@ -126,6 +126,7 @@ static int enqueue_body(lmono_ctx* ctx, int nc, int ns) {
   if ((rc = voxel_both(ctx, nullptr, nc, nullptr, ns))) return rc;
   lm_prof_end(ctx);
   if (fork) LM_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_side1, 0));
+  if (ctx->shard_p2p && (rc = lm_shard_gate_xchg(ctx))) return rc;          // :554 on the global window content (shard.cu)
   for (int iter = 0; iter < 2; ++iter) {                                    // :562
     lm_prof_begin(ctx, LM_PROF_ASSOC);
     if ((rc = lm_map_associate(ctx, nc, ns))) return rc;                    // :577-687
@@ -403,7 +404,9 @@ extern "C" int lmono_sweep_step(lmono_ctx* ctx, lmono_cloud_view raw, lmono_pose
   if ((rc = lm_scan_outputs(ctx, nullptr, &sharp, &less_sharp, &flat, &less_flat, nullptr))) return rc;
   if (counts[2] > ctx->max_feat || counts[4] > ctx->max_feat) return LMONO_E_CAPACITY;
   const double* d_pose7 = nullptr;
+  LM_CUDA(cudaEventRecord(ctx->ev_o0, ctx->stream));
   if ((rc = lm_odom_enqueue_auto(ctx, sharp, counts[1], less_sharp, counts[2], flat, counts[3], less_flat, counts[4], &d_pose7))) return rc;
+  LM_CUDA(cudaEventRecord(ctx->ev_o1, ctx->stream));
   if ((rc = lm_odom_readback(ctx))) return rc;
   // laserMapping consumes /laser_cloud_corner_last = less-sharp and /laser_cloud_surf_last = less-flat of this sweep
   // (laserOdometry.cpp:554-590) with /laser_odom_to_init as the prior
@@ -412,6 +415,7 @@ extern "C" int lmono_sweep_step(lmono_ctx* ctx, lmono_cloud_view raw, lmono_pose
   if ((rc = enqueue_step(ctx, in, nullptr))) return rc;
   rc = collect(ctx, map_w_curr, wmap_wodom, map_report);                           // sync #2
   const int rc2 = lm_odom_deliver(ctx, odom_last_curr, odom_w_curr, odom_report);
+  if (odom_report) { float ms = 0.f; if (cudaEventElapsedTime(&ms, ctx->ev_o0, ctx->ev_o1) == cudaSuccess) odom_report->ms_gpu = ms; else cudaGetLastError(); }
   return rc ? rc : rc2;
 }
 

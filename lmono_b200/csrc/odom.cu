@@ -345,6 +345,8 @@ extern "C" int lmono_odom_step(lmono_ctx* ctx, lmono_cloud_view sharp, lmono_clo
   LM_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
   lmono_cloud_view v[4] = { sharp, less_sharp, flat, less_flat };
   for (int k = 0; k < 4; ++k) if ((rc = lm_upload_cloud(ctx, v[k], ctx->d_raw[k < 3 ? k : 0], s->d_feat[k], nullptr))) return rc;
+  LM_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
+  lm_kmark(ctx, "begin", 0);
   // sizes of the previous sweep's clouds bound the search grids; cap is always safe
   if ((rc = lm_odom_enqueue(ctx, s->d_feat[0], sharp.n, s->d_feat[1], less_sharp.n, s->d_feat[2], flat.n, s->d_feat[3], less_flat.n,
                             s->h->n_corner_last > 0 ? s->h->n_corner_last : s->cap, s->h->n_surf_last > 0 ? s->h->n_surf_last : s->cap))) return rc;

@@ -610,6 +610,8 @@ extern "C" int lmono_scan_register(lmono_ctx* ctx, lmono_cloud_view raw, lmono_c
   ScanState* s; int rc = scan_state(ctx, &s); if (rc) return rc;
   LM_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
   if ((rc = lm_upload_cloud(ctx, raw, ctx->d_raw[2], s->d_in, nullptr))) return rc;
+  LM_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
+  lm_kmark(ctx, "begin", 0);
   if ((rc = lm_scan_enqueue(ctx, s->d_in, raw.n))) return rc;
   LM_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
   LM_CUDA(cudaMemcpyAsync(s->h_meta, s->d_meta, sizeof(ScanMeta), cudaMemcpyDeviceToHost, ctx->stream));

@@ -35,17 +35,11 @@ def cube_coord(v):
 
 
 def cube_owner(gi, gj, gk, nranks):
-    """lm_cube_owner of csrc/common.cuh (uint32 arithmetic)."""
+    """lm_cube_owner of csrc/common.cuh: cyclic, (gi + 3 gj + 5 gk) mod n -- a 5x5x3 window spreads evenly over the ranks."""
     gi, gj, gk = (np.asarray(a, np.int64) for a in (gi, gj, gk))
     if nranks <= 1:
         return np.zeros(np.broadcast(gi, gj, gk).shape, np.int64)
-    m = np.uint64(0xFFFFFFFF)
-    u = lambda a: (a.astype(np.int64) & 0xFFFFFFFF).astype(np.uint64)
-    h = ((u(gi) * np.uint64(73856093)) & m) ^ ((u(gj) * np.uint64(19349663)) & m) ^ ((u(gk) * np.uint64(83492791)) & m)
-    h ^= h >> np.uint64(15)
-    h = (h * np.uint64(0x2C1B3C6D)) & m
-    h ^= h >> np.uint64(12)
-    return (h % np.uint64(nranks)).astype(np.int64)
+    return np.mod(gi + 3 * gj + 5 * gk, nranks).astype(np.int64)
 
 
 def keep_mask(pts, leaf, rank, nranks):
@@ -147,6 +141,50 @@ class CtxEngine:
 
     def import_points(self, which, pts):
         self.ctx.map_import(which, pts)
+
+
+class PeerMemoryMapper:
+    """One rank of the cube-sharded registration in PEER-MEMORY mode (csrc/shard.cu): the 35-double exchange is done by
+    the kernels over NVLink-mapped exchange blocks, a registration is one enqueue-only call with no collective issued
+    by the host.  Same ownership / halo rules and the same import path as ShardedMapper."""
+
+    def __init__(self, ctx, rank, nranks, leaves=(0.4, 0.8)):
+        self.ctx, self.rank, self.nranks, self.leaves = ctx, rank, nranks, leaves
+
+    @classmethod
+    def connect(cls, ctx, group=None, leaves=(0.4, 0.8)):
+        """one process per GPU: exchange the cudaIpc handles over torch.distributed (setup only)"""
+        import torch.distributed as dist
+        rank, n = dist.get_rank(group), dist.get_world_size(group)
+        handle, _ = ctx.shard_xchg_create()
+        handles = [None] * n
+        dist.all_gather_object(handles, handle, group=group)
+        ctx.shard_xchg_open(rank, n, handles=handles)
+        dist.barrier(group)                  # nobody starts exchanging before every rank has mapped every block
+        return cls(ctx, rank, n, leaves)
+
+    @classmethod
+    def connect_local(cls, ctxs, leaves=(0.4, 0.8)):
+        """ranks = contexts of THIS process on one device (tests): plain device pointers, no IPC"""
+        ptrs = [c.shard_xchg_create()[1] for c in ctxs]
+        out = []
+        for r, c in enumerate(ctxs):
+            c.shard_xchg_open(r, len(ctxs), same_process_ptrs=[None if k == r else p for k, p in enumerate(ptrs)])
+            out.append(cls(c, r, len(ctxs), leaves))
+        return out
+
+    def import_global(self, which, pts, prefilter=True):
+        pts = np.ascontiguousarray(pts, np.float32)
+        mine = pts[keep_mask(pts, self.leaves[which], self.rank, self.nranks)] if prefilter else pts
+        for chunk in cube_chunks(mine):
+            self.ctx.map_import(which, np.ascontiguousarray(chunk))
+        return len(mine)
+
+    def step(self, d_corner, nc, d_surf, ns, q_odom, t_odom):
+        self.ctx.map_step_device(d_corner, nc, d_surf, ns, q_odom, t_odom)
+
+    def collect(self):
+        return self.ctx.map_collect()
 
 
 class ShardedMapper:

@@ -303,6 +303,61 @@ def raycast_sweep(world: World, q, t, n_scans=64, n_az=1875, rng=None, noise=0.0
     return out
 
 
+def raycast_sweep_torch(world: World, q, t, n_scans=64, n_az=1875, rng=None, noise=0.02,
+                        max_range=80.0, min_range=0.5, device="cuda"):
+    """raycast_sweep with the ray / primitive tests evaluated by torch on `device` (float64, chunked over the
+    primitives): the same geometry and output layout, fast enough for the pole-dense bench city (thousands of
+    cylinders in range).  Workload generation only -- not part of the product path."""
+    import torch
+    rng = rng or np.random.default_rng(0)
+    elev = np.deg2rad(beam_elevations_deg(n_scans))
+    az0 = rng.uniform(-0.01, 0.01)
+    az = az0 - (np.arange(n_az) + 0.25) * (2 * math.pi / n_az)
+    ee, aa = np.meshgrid(elev, az, indexing="ij")
+    d_s = np.stack([np.cos(ee) * np.cos(aa), np.cos(ee) * np.sin(aa), np.sin(ee)], -1).reshape(-1, 3)
+    R = quat_to_rot(q)
+    o = np.asarray(t, np.float64)
+    boxes, poles = _nearby(world, o, max_range)
+    dev = torch.device(device)
+    dw = torch.from_numpy(d_s @ R.T).to(dev)                      # [n, 3]
+    ot = torch.from_numpy(o).to(dev)
+    inf = torch.tensor(float("inf"), dtype=torch.float64, device=dev)
+    best = torch.full((dw.shape[0],), float("inf"), dtype=torch.float64, device=dev)
+    dz = dw[:, 2]
+    tg = (world.ground_z - ot[2]) / dz
+    best = torch.minimum(best, torch.where((dz < -1e-9) & (tg > 0), tg, inf))
+    inv = 1.0 / dw                                                # +-inf for axis-parallel rays, as numpy's division
+    for b0 in range(0, len(boxes), 32):
+        bx = torch.from_numpy(boxes[b0:b0 + 32]).to(dev)          # [m, 6]
+        t1 = (bx[None, :, 0:3] - ot) * inv[:, None, :]
+        t2 = (bx[None, :, 3:6] - ot) * inv[:, None, :]
+        lo = torch.nan_to_num(torch.minimum(t1, t2), nan=-float("inf"))
+        hi = torch.nan_to_num(torch.maximum(t1, t2), nan=float("inf"))
+        tmin = lo.amax(dim=2)
+        tmax = hi.amin(dim=2)
+        hit = (tmax >= torch.clamp(tmin, min=0.0)) & (tmin > 0)
+        best = torch.minimum(best, torch.where(hit, tmin, inf).amin(dim=1))
+    dxy2 = dw[:, 0] ** 2 + dw[:, 1] ** 2
+    for p0 in range(0, len(poles), 64):
+        pl = torch.from_numpy(poles[p0:p0 + 64]).to(dev)          # [m, 4] x, y, radius, height
+        ox, oy = ot[0] - pl[None, :, 0], ot[1] - pl[None, :, 1]
+        bq = ox * dw[:, None, 0] + oy * dw[:, None, 1]
+        cq = ox * ox + oy * oy - pl[None, :, 2] ** 2
+        disc = bq * bq - dxy2[:, None] * cq
+        th = (-bq - torch.sqrt(torch.clamp(disc, min=0.0))) / dxy2[:, None]
+        zh = ot[2] + th * dw[:, None, 2]
+        hit = (disc > 0) & (th > 0) & (zh >= 0) & (zh <= pl[None, :, 3])
+        best = torch.minimum(best, torch.where(hit, th, inf).amin(dim=1))
+    best = best.cpu().numpy()
+    ok = np.isfinite(best) & (best < max_range) & (best > min_range)
+    rr = best + rng.normal(0, noise, best.shape)
+    pts = d_s * np.where(ok, rr, 0.0)[:, None]
+    out = np.zeros((int(ok.sum()), 4), np.float32)
+    out[:, :3] = pts[ok]
+    out[:, 3] = 0.5
+    return out
+
+
 # --------------------------------------------------------------------------- bench city (C-3)
 def make_city(center=(0.0, 0.0), half=125.0, seed=7, pitch=15.0, footprint=(9.0, 12.0),
               height=(12.0, 40.0), pole_pitch=4.2, street_radius=30.0) -> World:

@@ -31,40 +31,46 @@ def main():
     torch.cuda.set_stream(ts)
     stream = ts.cuda_stream
     cm, sm = scenario.small_map(half_xy=80.0, n_surf=250_000, n_corner=60_000)
-    ref = api.Context(device=local, stream=stream)
-    ref.map_import(0, cm); ref.map_import(1, sm)
-    ctx = api.Context(device=local, stream=stream)
-    m = shard.ShardedMapper.on_gpu(ctx, dev)
-    kept = (m.import_global(0, cm), m.import_global(1, sm))
-    worst = 0.0
-    times = []
-    for (c, s, q, t, qp, tp) in scenario.sweeps(6, seed=8, n_corner=1500, n_surf=8000, ds=9.0):
-        dc, ds_ = torch.from_numpy(c).to(dev), torch.from_numpy(s).to(dev)
-        rq, rt, rrep, _ = ref.map_step(c, s, qp, tp)
-        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        m.step(dc.data_ptr(), len(c), ds_.data_ptr(), len(s), qp, tp)
-        gq, gt, grep = m.collect()
-        times.append(time.perf_counter() - t0)
-        assert list(grep.corner_num) == list(rrep.corner_num) and list(grep.surf_num) == list(rrep.surf_num), (list(grep.corner_num), list(rrep.corner_num))
-        assert np.linalg.norm(gt - rt) <= 1e-4 and 2 * np.arccos(min(1.0, abs(float(np.dot(gq, rq))))) <= 1e-4
-        worst = max(worst, float(np.linalg.norm(gt - rt)))
-        # all ranks hold the same pose bit for bit
-        pose = torch.tensor(np.concatenate([gq, gt]), device=dev)
-        lo, hi = pose.clone(), pose.clone()
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        assert torch.equal(lo, hi)
-    for which in (0, 1):
-        full, part = ref.map_export(which, 1), ctx.map_export(which, 1)
-        a = part[shard.owner_of_points(part, world) == rank]
-        b = full[shard.owner_of_points(full, world) == rank]
-        assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
-    print(json.dumps({"rank": rank, "world": world, "kept": kept, "of": (len(cm), len(sm)), "worst_dt_m": worst,
-                      "allreduces": m.n_allreduce, "ms_per_registration_wall": 1e3 * float(np.median(times))}))
+    results = {}
+    for mode in ("nccl", "p2p"):
+        ctx = api.Context(device=local, stream=stream)
+        m = shard.ShardedMapper.on_gpu(ctx, dev) if mode == "nccl" else shard.PeerMemoryMapper.connect(ctx)
+        kept = (m.import_global(0, cm), m.import_global(1, sm))
+        ref = api.Context(device=local, stream=stream)
+        ref.map_import(0, cm); ref.map_import(1, sm)
+        worst = 0.0
+        times = []
+        for (c, s, q, t, qp, tp) in scenario.sweeps(6, seed=8, n_corner=1500, n_surf=8000, ds=9.0):
+            dc, ds_ = torch.from_numpy(c).to(dev), torch.from_numpy(s).to(dev)
+            rq, rt, rrep, _ = ref.map_step(c, s, qp, tp)
+            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            m.step(dc.data_ptr(), len(c), ds_.data_ptr(), len(s), qp, tp)
+            gq, gt, grep = m.collect()
+            times.append(time.perf_counter() - t0)
+            assert list(grep.corner_num) == list(rrep.corner_num) and list(grep.surf_num) == list(rrep.surf_num), (mode, list(grep.corner_num), list(rrep.corner_num))
+            assert [x.iterations for x in grep.solve] == [x.iterations for x in rrep.solve], mode
+            assert np.linalg.norm(gt - rt) <= 1e-4 and 2 * np.arccos(min(1.0, abs(float(np.dot(gq, rq))))) <= 1e-4
+            worst = max(worst, float(np.linalg.norm(gt - rt)))
+            # all ranks hold the same pose bit for bit
+            pose = torch.tensor(np.concatenate([gq, gt]), device=dev)
+            lo, hi = pose.clone(), pose.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            assert torch.equal(lo, hi), mode
+        for which in (0, 1):
+            full, part = ref.map_export(which, 1), ctx.map_export(which, 1)
+            a = part[shard.owner_of_points(part, world) == rank]
+            b = full[shard.owner_of_points(full, world) == rank]
+            assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), mode
+        results[mode] = {"kept": kept, "worst_dt_m": worst, "ms_per_registration_wall": 1e3 * float(np.median(times)),
+                         "host_allreduces": getattr(m, "n_allreduce", 0),
+                         "device_exchanges": ctx.shard_xchg_stats()["epoch"] if mode == "p2p" else 0}
+        torch.cuda.synchronize(); dist.barrier()
+        ctx.close(); ref.close()
+    print(json.dumps({"rank": rank, "world": world, "of": (len(cm), len(sm)), **results}))
     dist.barrier()
     if rank == 0:
         print("SHARD_NCCL_OK")
-    ctx.close(); ref.close()
     dist.destroy_process_group()
 
 

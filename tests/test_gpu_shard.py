@@ -85,6 +85,61 @@ def test_sharded_registration_matches_unsharded_on_one_gpu(gpu_ctx_factory, nran
             c.close()
 
 
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_peer_memory_mode_matches_unsharded_on_one_gpu(gpu_ctx_factory, nranks):
+    """Peer-memory mode (csrc/shard.cu): the ranks are contexts of this process, each on its own stream, their exchange
+    blocks plain device pointers.  A registration is ONE enqueue per rank (the step graph with the gate exchange and the
+    LM cluster kernel that all-gathers its sums itself); the kernels of the ranks run concurrently on the GPU and meet
+    in the exchanges.  Against the unsharded ctx: same counts and LM trace, poses within 1e-4, owned cubes bit-identical."""
+    import torch
+    from lmono_b200 import api
+    dev = torch.device("cuda", 0)
+    cm, sm = scenario.small_map(half_xy=80.0, n_surf=250_000, n_corner=60_000)
+    ref = api.Context(device=0)
+    ref.map_import(0, cm); ref.map_import(1, sm)
+    ctxs = [api.Context(device=0) for _ in range(nranks)]          # stream=NULL: every ctx owns a non-blocking stream
+    mappers = shard.PeerMemoryMapper.connect_local(ctxs)
+    kept = [(m.import_global(0, cm), m.import_global(1, sm)) for m in mappers]
+    assert all(k[1] < len(sm) for k in kept)
+    try:
+        worst = 0.0
+        for k, (c, s, q, t, qp, tp) in enumerate(scenario.sweeps(5, seed=8, n_corner=1500, n_surf=8000, ds=9.0)):
+            dc, ds_ = torch.from_numpy(c).to(dev), torch.from_numpy(s).to(dev)
+            torch.cuda.synchronize()
+            rq, rt, rrep, _ = ref.map_step(c, s, qp, tp)
+            for m in mappers:
+                m.step(dc.data_ptr(), len(c), ds_.data_ptr(), len(s), qp, tp)       # enqueue-only
+            outs = [m.collect() for m in mappers]
+            for (gq, gt, grep) in outs:
+                assert list(grep.corner_num) == list(rrep.corner_num) and list(grep.surf_num) == list(rrep.surf_num), k
+                assert (grep.corner_from_map, grep.surf_from_map, grep.optimized) == (rrep.corner_from_map, rrep.surf_from_map, rrep.optimized)
+                assert np.linalg.norm(gt - rt) <= 1e-4 and 2 * np.arccos(min(1.0, abs(float(np.dot(gq, rq))))) <= 1e-4
+                assert [s_.iterations for s_ in grep.solve] == [s_.iterations for s_ in rrep.solve]
+                assert [s_.termination for s_ in grep.solve] == [s_.termination for s_ in rrep.solve]
+                worst = max(worst, float(np.linalg.norm(gt - rt)))
+            assert all(np.array_equal(outs[0][1], o[1]) and np.array_equal(outs[0][0], o[0]) for o in outs)   # replicated controllers, same bits
+        st = [c.shard_xchg_stats() for c in ctxs]
+        assert all(x["epoch"] == st[0]["epoch"] and x["epoch"] >= 5 * 3 for x in st), st
+        print(f"peer-memory x{nranks} vs unsharded: worst |dt| = {worst:.2e} m; exchanges {st[0]['epoch']}, "
+              f"{st[0]['wait_ns'] / max(st[0]['exchanges'], 1) / 1e3:.1f} us per exchange (ranks share ONE GPU here)")
+        for which in (0, 1):
+            full = ref.map_export(which, 1)
+            own_full = shard.owner_of_points(full, nranks)
+            n_union = 0
+            for r, c in enumerate(ctxs):
+                part = c.map_export(which, 1)
+                own = shard.owner_of_points(part, nranks) == r
+                a, b = part[own], full[own_full == r]
+                assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), (which, r)
+                n_union += len(a)
+            assert n_union == len(full)
+    finally:
+        torch.cuda.synchronize()
+        for c in ctxs:
+            c.close()
+        ref.close()
+
+
 def test_device_import_applies_the_same_rule_as_the_host_prefilter(gpu_ctx_factory):
     """lmono_map_import on a sharded ctx keeps owner + halo points itself: importing the whole cloud
     gives the same map as importing the numpy-prefiltered subset (host rule == device rule)."""
