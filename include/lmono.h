@@ -203,8 +203,9 @@ int lmono_map_set_state(lmono_ctx* ctx, const lmono_pose* wmap_wodom);   /* enqu
 int32_t lmono_map_result_bytes(void);
 
 /* Map exchange (the publishers at laserMapping.cpp:806-836 and checkpoint/restore).
- * which: 0 corner, 1 surf.  scope: 0 = the <=75 cubes of the current window in the order of
- * :512-537, 1 = all 4851 cubes in the order of :826-830. */
+ * which: 0 corner, 1 surf, 2 both, interleaved cube by cube (corner cube, then surf cube) exactly as the reference's
+ * /laser_cloud_surround and /laser_cloud_map messages are assembled (:808-816, :826-830).  scope: 0 = the <=75 cubes
+ * of the current window in the order of :512-537, 1 = all 4851 cubes in the order of :826-830. */
 int lmono_map_export(lmono_ctx* ctx, int which, int scope, lmono_cloud_out* out);
 /* Load world-frame points into an EMPTY map: every point goes to its cube
  * (laserMapping.cpp:741-758 arithmetic) and every cube is VoxelGrid-filtered (:788-801). */
@@ -342,6 +343,12 @@ int lmono_project_color(lmono_ctx* ctx, lmono_cloud_view pts, const double* T_ca
                         uint8_t* depth_raw /*may be NULL*/, uint8_t* depth_filled /*may be NULL*/,
                         float* cloud_cam_xyz /*may be NULL*/, float* cloud_world_xyz, uint8_t* cloud_rgb,
                         int32_t capacity, int32_t* n_out);
+
+/* Per-point projection of the most recent lmono_project_color call, cloud order: u, v (the cv::Point2f of
+ * Map_Builder.cc:234; NaN where the point was not rasterised) and camera-frame depth z.  The ~pro_map debug image
+ * (Map_Builder.cc:240-265: r = 3 HSV discs drawn in cloud order) is drawn from it on the host with the reference's own
+ * cv::circle call (nodes/map_build_node_b200.cpp). */
+int lmono_color_projection(lmono_ctx* ctx, float* uvz /*[n][3]*/, int32_t n);
 
 #ifdef __cplusplus
 }

@@ -446,6 +446,12 @@ class Context:
         self._chk(rc, "project_color")
         return {"depth_raw": b.raw, "depth": b.fill, "cloud_cam": b.cc[: n.value], "cloud_world": b.cw[: n.value], "rgb": b.rgb[: n.value]}
 
+    def color_projection(self, n):
+        """(u, v, z) of the first n points of the last project_color call (u = NaN: not rasterised)"""
+        uvz = np.zeros((max(n, 1), 3), np.float32)
+        self._chk(self.L.lmono_color_projection(self._h, uvz.ctypes.data_as(C.c_void_p), n), "color_projection")
+        return uvz[:n]
+
     def voxel_grid(self, pts, leaf):
         p = _xyzi(pts)
         buf, out = _out(len(p))

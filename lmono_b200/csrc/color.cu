@@ -25,6 +25,7 @@ struct ColorState {
   float4* d_pts; int32_t* d_winner; uint8_t* d_img[4]; uint8_t* d_bgr; size_t bgr_bytes;
   ColorTables* d_tab; ColorTables h_tab;
   int32_t* d_blockcnt; int32_t* d_nout;
+  float* d_proj; int n_proj;        // (u, v, z) of every point of the last frame, u = NaN where the point was not rasterised
   float* d_cam; float* d_world; uint8_t* d_rgb;
 };
 
@@ -51,17 +52,21 @@ __global__ void __launch_bounds__(256) k_col_transform(float4* __restrict__ pts,
   pts[i] = o;
 }
 
-__global__ void __launch_bounds__(256) k_col_winner(const float4* __restrict__ pts, int n, ColorCam c, int32_t* __restrict__ winner) {
+__global__ void __launch_bounds__(256) k_col_winner(const float4* __restrict__ pts, int n, ColorCam c, int32_t* __restrict__ winner, float* __restrict__ proj) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 p = pts[i];
+  proj[3 * i + 0] = __int_as_float(0x7fc00000); proj[3 * i + 1] = __int_as_float(0x7fc00000); proj[3 * i + 2] = p.z;
   if (p.z < 0) return;
   const double X = p.x, Y = p.y, Z = p.z;
   const double ux = X / Z, uy = Y / Z;
   double dxp = ux, dyp = uy;
   if (!c.nod) { double ddx, ddy; d_distortion(c, ux, uy, &ddx, &ddy); dxp = ux + ddx; dyp = uy + ddy; }
   const float fx = (float)(c.fx * dxp + c.cx), fy = (float)(c.fy * dyp + c.cy);     // cv::Point2f
-  if (fx > 0 && fx < (float)c.W && fy > 0 && fy < (float)c.H) atomicMax(&winner[(int)fy * c.W + (int)fx], i + 1);
+  if (fx > 0 && fx < (float)c.W && fy > 0 && fy < (float)c.H) {
+    atomicMax(&winner[(int)fy * c.W + (int)fx], i + 1);
+    proj[3 * i + 0] = fx; proj[3 * i + 1] = fy;       // what the reference draws its r = 3 HSV disc at (Map_Builder.cc:243)
+  }
 }
 
 __global__ void __launch_bounds__(256) k_col_raster(const float4* __restrict__ pts, const int32_t* __restrict__ winner, int npix, uint8_t* __restrict__ depth) {
@@ -260,6 +265,7 @@ static int color_state(lmono_ctx* ctx, int W, int H, ColorState** out) {
   LM_CUDA(cudaMalloc((void**)&s->d_tab, sizeof(ColorTables)));
   LM_CUDA(cudaMalloc((void**)&s->d_blockcnt, sizeof(int32_t) * (npix / 256 + 8)));
   LM_CUDA(cudaMalloc((void**)&s->d_nout, sizeof(int32_t)));
+  LM_CUDA(cudaMalloc((void**)&s->d_proj, (size_t)s->cap_pts * 3 * sizeof(float)));
   LM_CUDA(cudaMalloc((void**)&s->d_cam, npix * 3 * sizeof(float)));
   LM_CUDA(cudaMalloc((void**)&s->d_world, npix * 3 * sizeof(float)));
   LM_CUDA(cudaMalloc((void**)&s->d_rgb, npix * 3));
@@ -272,7 +278,7 @@ void lm_color_free(lmono_ctx* ctx) {
   ColorState* s = (ColorState*)ctx->color_state;
   if (!s) return;
   cudaFree(s->d_pts); cudaFree(s->d_winner); for (int k = 0; k < 4; ++k) cudaFree(s->d_img[k]);
-  cudaFree(s->d_bgr); cudaFree(s->d_tab); cudaFree(s->d_blockcnt); cudaFree(s->d_nout); cudaFree(s->d_cam); cudaFree(s->d_world); cudaFree(s->d_rgb);
+  cudaFree(s->d_bgr); cudaFree(s->d_tab); cudaFree(s->d_blockcnt); cudaFree(s->d_nout); cudaFree(s->d_proj); cudaFree(s->d_cam); cudaFree(s->d_world); cudaFree(s->d_rgb);
   free(s); ctx->color_state = nullptr;
 }
 
@@ -312,7 +318,8 @@ extern "C" int lmono_project_color(lmono_ctx* ctx, lmono_cloud_view pts, const d
     k_col_transform<<<nb_pts, 256, 0, ctx->stream>>>(s->d_pts, pts.n, T); LM_LAUNCH_CHECK();
   }
   LM_CUDA(cudaMemsetAsync(s->d_winner, 0, (size_t)npix * sizeof(int32_t), ctx->stream));
-  if (pts.n > 0) { k_col_winner<<<nb_pts, 256, 0, ctx->stream>>>(s->d_pts, pts.n, c, s->d_winner); LM_LAUNCH_CHECK(); }
+  if (pts.n > 0) { k_col_winner<<<nb_pts, 256, 0, ctx->stream>>>(s->d_pts, pts.n, c, s->d_winner, s->d_proj); LM_LAUNCH_CHECK(); }
+  s->n_proj = pts.n;
   uint8_t *raw = s->d_img[0], *a = s->d_img[1], *b = s->d_img[2], *cc = s->d_img[3];
   k_col_raster<<<nb_pix, 256, 0, ctx->stream>>>(s->d_pts, s->d_winner, npix, raw); LM_LAUNCH_CHECK();
   const dim3 g2(lm_div_up(W, 256), H);
@@ -351,5 +358,19 @@ extern "C" int lmono_project_color(lmono_ctx* ctx, lmono_cloud_view pts, const d
     LM_CUDA(cudaMemcpyAsync(cloud_rgb, s->d_rgb, (size_t)n * 3, cudaMemcpyDeviceToHost, ctx->stream));
     LM_CUDA(cudaStreamSynchronize(ctx->stream));
   }
+  return LMONO_OK;
+}
+
+// Per-point projection of the most recent lmono_project_color call, in cloud order: uvz[3 i] = u, [3 i + 1] = v (the
+// cv::Point2f of Map_Builder.cc:234, NaN where the point was behind the camera or outside the frame), [3 i + 2] = depth
+// z in the camera frame.  The node draws the ~pro_map debug image from it exactly as the reference does
+// (cv::circle(HSV, xy, 3, Scalar(int(clip(z, 0, 100) * 6), 255, 255), -1) in cloud order, Map_Builder.cc:240-243).
+extern "C" int lmono_color_projection(lmono_ctx* ctx, float* uvz, int32_t n) {
+  ColorState* s = ctx ? (ColorState*)ctx->color_state : nullptr;
+  if (!s || !uvz || n < 0) return LMONO_E_ARG;
+  if (n > s->n_proj) return LMONO_E_STATE;
+  if (n == 0) return LMONO_OK;
+  LM_CUDA(cudaMemcpyAsync(uvz, s->d_proj, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  LM_CUDA(cudaStreamSynchronize(ctx->stream));
   return LMONO_OK;
 }

@@ -144,7 +144,7 @@ static int create_impl(lmono_ctx* ctx, void* stream) {
   LM_CUDA(cudaMalloc((void**)&ctx->d_full, (size_t)ctx->max_sweep * sizeof(float4)));
   LM_CUDA(cudaMalloc((void**)&ctx->d_slot_first, sizeof(int32_t) * 2 * LM_NSLOT));
   LM_CUDA(cudaMalloc((void**)&ctx->d_slot_base, sizeof(int32_t) * 2 * LM_NSLOT));
-  LM_CUDA(cudaMalloc((void**)&ctx->d_export_off, sizeof(int32_t) * (2 * LM_NSLOT + 32)));
+  LM_CUDA(cudaMalloc((void**)&ctx->d_export_off, sizeof(int32_t) * (4 * LM_NSLOT + 64)));
   ctx->export_cap = 1 << 20;
   LM_CUDA(cudaMalloc((void**)&ctx->d_export, ctx->export_cap * sizeof(float4)));
   k_state_init<<<1, 32, 0, ctx->stream>>>(ctx->d_state);

@@ -37,60 +37,106 @@ __device__ __forceinline__ void d_acc_row(const double* J, double r, double* acc
   for (int a = 0; a < 6; ++a) acc[21 + a] = fma(J[a], r, acc[21 + a]);
 }
 
-__device__ __forceinline__ void d_eval_factor(const LmFactor& f, const double* q, const double* t, double* acc) {
+// rotation matrix of a (unit) quaternion, Eigen's toRotationMatrix() operation order; computed once per pass and thread
+__device__ __forceinline__ void d_rot_of_q(const double* q, double* R) {
+  const double tx = 2.0 * q[0], ty = 2.0 * q[1], tz = 2.0 * q[2];
+  const double twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
+  const double txx = tx * q[0], txy = ty * q[0], txz = tz * q[0], tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
+  R[0] = 1.0 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+  R[3] = txy + twz; R[4] = 1.0 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1.0 - (txx + tyy);
+}
+
+// One factor at the pose (R, t).  COST_ONLY: only the robustified cost (a candidate point whose Jacobian cannot be used
+// any more: the last evaluation of a solve).  Explicit fp64 FMAs in the rotation and the sums: the normal equations are
+// compared at 1e-5 relative (north_star), not bit for bit.  The edge residual divides by |a - b| ONCE (one reciprocal
+// square root instead of twelve IEEE divisions -- each a ~20-instruction software sequence on the hottest path).
+template <bool COST_ONLY>
+__device__ __forceinline__ void d_eval_factor(const LmFactor& f, const double* R, const double* t, double* acc) {
   if (f.kind < 0) return;
-  const double p[3] = { (double)f.p[0], (double)f.p[1], (double)f.p[2] };
-  double rp[3]; d_qrot(q, p, rp);                       // R p
+  const double px = (double)f.p[0], py = (double)f.p[1], pz = (double)f.p[2];
+  const double rp[3] = { fma(R[0], px, fma(R[1], py, R[2] * pz)), fma(R[3], px, fma(R[4], py, R[5] * pz)), fma(R[6], px, fma(R[7], py, R[8] * pz)) };
   const double lp[3] = { rp[0] + t[0], rp[1] + t[1], rp[2] + t[2] };
   // d lp / d delta = -2 [R p]x  (columns), d lp / d t = I
-  // row k of a 1x3 covector c maps to: J_rot = c^T * (-2 [rp]x) = -2 (c x rp)^T ... computed per case
   if (f.kind == 0) {
-    double da[3] = { lp[0] - f.a[0], lp[1] - f.a[1], lp[2] - f.a[2] };
-    double db[3] = { lp[0] - f.b[0], lp[1] - f.b[1], lp[2] - f.b[2] };
+    const double da[3] = { lp[0] - f.a[0], lp[1] - f.a[1], lp[2] - f.a[2] };
+    const double db[3] = { lp[0] - f.b[0], lp[1] - f.b[1], lp[2] - f.b[2] };
     double nu[3]; d_cross(da, db, nu);
-    double de[3] = { f.a[0] - f.b[0], f.a[1] - f.b[1], f.a[2] - f.b[2] };
-    double den = sqrt(de[0] * de[0] + de[1] * de[1] + de[2] * de[2]);
-    double r[3] = { nu[0] / den, nu[1] / den, nu[2] / den };
-    double s = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
-    double rho0, rho1;
-    if (s > 0.01) { double rs = sqrt(s); rho0 = 2.0 * 0.1 * rs - 0.01; rho1 = fmax(DBL_MIN, 0.1 / rs); } else { rho0 = s; rho1 = 1.0; }
+    const double de[3] = { f.a[0] - f.b[0], f.a[1] - f.b[1], f.a[2] - f.b[2] };
+    const double inv = rsqrt(fma(de[0], de[0], fma(de[1], de[1], de[2] * de[2])));
+    const double r[3] = { nu[0] * inv, nu[1] * inv, nu[2] * inv };
+    const double s = fma(r[0], r[0], fma(r[1], r[1], r[2] * r[2]));
+    double rho0 = s, sr = 1.0;
+    if (s > 0.01) { const double rs = sqrt(s); rho0 = 2.0 * 0.1 * rs - 0.01; sr = sqrt(fmax(DBL_MIN, 0.1 / rs)); }
     acc[27] += 0.5 * rho0;
-    const double sr = sqrt(rho1);
-    // dr/dlp = [b - a]x / den = -[de]x / den.  Row k of [v]x: e_k^T [v]x.
-    // M = -[de]x / den  (3x3); J_t = M ; J_rot = M * (-2 [rp]x)
-    double Mx[3][3] = { { 0.0, de[2], -de[1] }, { -de[2], 0.0, de[0] }, { de[1], -de[0], 0.0 } };   // -[de]x
-    for (int k = 0; k < 3; ++k) {
-      double m[3] = { Mx[k][0] / den, Mx[k][1] / den, Mx[k][2] / den };
-      // m^T (-2 [rp]x) = -2 (m^T [rp]x) ; m^T [v]x = (v x m)^T ... use: m^T [v]x w = m . (v x w) = (m x v) . w
-      double mxv[3]; d_cross(m, rp, mxv);
-      double J[6] = { -2.0 * mxv[0] * sr, -2.0 * mxv[1] * sr, -2.0 * mxv[2] * sr, m[0] * sr, m[1] * sr, m[2] * sr };
-      d_acc_row(J, r[k] * sr, acc);
+    if (COST_ONLY) return;
+    // dr/dlp = -[de]x / |de| = M (rows m_k); J_t = M, J_rot = M (-2 [rp]x): row k = -2 (m_k x rp)
+    const double w = inv * sr;
+    const double e0 = de[0] * w, e1 = de[1] * w, e2 = de[2] * w;     // rows of M, scaled by the corrector: (0, e2, -e1), (-e2, 0, e0), (e1, -e0, 0)
+    {
+      const double J[6] = { -2.0 * fma(e2, rp[2], e1 * rp[1]), 2.0 * (e1 * rp[0]), 2.0 * (e2 * rp[0]), 0.0, e2, -e1 };
+      d_acc_row(J, r[0] * sr, acc);
+    }
+    {
+      const double J[6] = { 2.0 * (e0 * rp[1]), -2.0 * fma(e0, rp[0], e2 * rp[2]), 2.0 * (e2 * rp[1]), -e2, 0.0, e0 };
+      d_acc_row(J, r[1] * sr, acc);
+    }
+    {
+      const double J[6] = { 2.0 * (e0 * rp[2]), 2.0 * (e1 * rp[2]), -2.0 * fma(e1, rp[1], e0 * rp[0]), e1, -e0, 0.0 };
+      d_acc_row(J, r[2] * sr, acc);
     }
   } else {
     double r, n[3];
-    if (f.kind == 1) { n[0] = f.b[0]; n[1] = f.b[1]; n[2] = f.b[2]; r = (lp[0] - f.a[0]) * n[0] + (lp[1] - f.a[1]) * n[1] + (lp[2] - f.a[2]) * n[2]; }
-    else { n[0] = f.a[0]; n[1] = f.a[1]; n[2] = f.a[2]; r = (n[0] * lp[0] + n[1] * lp[1] + n[2] * lp[2]) + f.b[0]; }
-    double s = r * r;
-    double rho0, rho1;
-    if (s > 0.01) { double rs = sqrt(s); rho0 = 2.0 * 0.1 * rs - 0.01; rho1 = fmax(DBL_MIN, 0.1 / rs); } else { rho0 = s; rho1 = 1.0; }
+    if (f.kind == 1) { n[0] = f.b[0]; n[1] = f.b[1]; n[2] = f.b[2]; r = fma(lp[0] - f.a[0], n[0], fma(lp[1] - f.a[1], n[1], (lp[2] - f.a[2]) * n[2])); }
+    else { n[0] = f.a[0]; n[1] = f.a[1]; n[2] = f.a[2]; r = fma(n[0], lp[0], fma(n[1], lp[1], n[2] * lp[2])) + f.b[0]; }
+    const double s = r * r;
+    double rho0 = s, sr = 1.0;
+    if (s > 0.01) { const double rs = sqrt(s); rho0 = 2.0 * 0.1 * rs - 0.01; sr = sqrt(fmax(DBL_MIN, 0.1 / rs)); }
     acc[27] += 0.5 * rho0;
-    const double sr = sqrt(rho1);
+    if (COST_ONLY) return;
     double nxv[3]; d_cross(n, rp, nxv);
-    double J[6] = { -2.0 * nxv[0] * sr, -2.0 * nxv[1] * sr, -2.0 * nxv[2] * sr, n[0] * sr, n[1] * sr, n[2] * sr };
+    const double m2 = -2.0 * sr;
+    const double J[6] = { m2 * nxv[0], m2 * nxv[1], m2 * nxv[2], n[0] * sr, n[1] * sr, n[2] * sr };
     d_acc_row(J, r * sr, acc);
   }
 }
 
 // ---- trust-region controller (single thread) -------------------------------------------
+// EigenQuaternionParameterization::Plus: q+ = [sin|d| d/|d|, cos|d|] (x) q, t+ = t + dt.  sin(|d|)/|d| and cos(|d|) are
+// even functions of |d|: for |d| < 0.25 rad (every trust-region step of a registration) both are evaluated as Horner
+// polynomials in |d|^2 (truncation < 1e-22) -- no square root, no division, no sincos() call on the controller's
+// dependent chain; larger steps take the general path.
 __device__ void d_plus(const double* x, const double* d, double* out) {
-  const double nd = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-  if (nd > 0.0) {
-    double sn, cs;
+  const double n2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+  double sbd, cs;
+  if (n2 < 0.0625) {
+    // sin(a)/a = sum (-1)^k a^2k / (2k+1)!,  cos(a) = sum (-1)^k a^2k / (2k)!,  k = 0..8
+    sbd = -1.0 / 355687428096000.0;        // 17!
+    sbd = fma(sbd, n2, 1.0 / 1307674368000.0);       // 15!
+    sbd = fma(sbd, n2, -1.0 / 6227020800.0);         // 13!
+    sbd = fma(sbd, n2, 1.0 / 39916800.0);            // 11!
+    sbd = fma(sbd, n2, -1.0 / 362880.0);             // 9!
+    sbd = fma(sbd, n2, 1.0 / 5040.0);
+    sbd = fma(sbd, n2, -1.0 / 120.0);
+    sbd = fma(sbd, n2, 1.0 / 6.0);
+    sbd = fma(-sbd, n2, 1.0);
+    cs = 1.0 / 20922789888000.0;           // 16!
+    cs = fma(cs, n2, -1.0 / 87178291200.0);          // 14!
+    cs = fma(cs, n2, 1.0 / 479001600.0);             // 12!
+    cs = fma(cs, n2, -1.0 / 3628800.0);              // 10!
+    cs = fma(cs, n2, 1.0 / 40320.0);
+    cs = fma(cs, n2, -1.0 / 720.0);
+    cs = fma(cs, n2, 1.0 / 24.0);
+    cs = fma(cs, n2, -0.5);
+    cs = fma(cs, n2, 1.0);
+  } else {
+    const double nd = sqrt(n2);
+    double sn;
     sincos(nd, &sn, &cs);
-    const double sbd = sn / nd;
-    const double a[4] = { sbd * d[0], sbd * d[1], sbd * d[2], cs };
-    d_qmul(a, x, out);
-  } else { out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; out[3] = x[3]; }
+    sbd = sn / nd;
+  }
+  const double a[4] = { sbd * d[0], sbd * d[1], sbd * d[2], cs };
+  d_qmul(a, x, out);
   out[4] = x[4] + d[3]; out[5] = x[5] + d[4]; out[6] = x[6] + d[5];
 }
 __device__ __forceinline__ double d_norm7(const double* v) {
@@ -102,7 +148,12 @@ __device__ __forceinline__ double d_norm7(const double* v) {
 // upper-triangular packed index of (a, b), a <= b; constant-folds when a, b are unrolled loop indices
 __device__ __forceinline__ constexpr int d_tri(int a, int b) { return a <= b ? a * 6 - (a * (a - 1)) / 2 + (b - a) : b * 6 - (b * (b - 1)) / 2 + (a - b); }
 __device__ __forceinline__ double d_Hat(const double* H, int a, int b) { return H[d_tri(a, b)]; }
+// Ceres' gradient tolerance: max |x - Plus(x, -g)| <= 1e-10.  The translation block of that difference is |g_t| itself
+// (up to an ulp of x): whenever a translation gradient exceeds 2e-10 the test has failed and the rotation block -- a
+// sincos of a large angle on the controller's dependent chain -- need not be formed.
 __device__ double d_gradient_max_norm(const double* x, const double* g) {
+  const double gt = fmax(fmax(fabs(g[3]), fabs(g[4])), fabs(g[5]));
+  if (gt > 2e-10) return gt;
   double ng[6], xp[7];
 #pragma unroll
   for (int i = 0; i < 6; ++i) ng[i] = -g[i];
@@ -312,12 +363,13 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_lm_eval(LmLmState* __restrict_
   const double* xe = lm->phase == 0 ? lm->x : lm->cand;
   const double q[4] = { xe[0], xe[1], xe[2], xe[3] };
   const double t[3] = { xe[4], xe[5], xe[6] };
+  double R[9]; d_rot_of_q(q, R);
   double acc[NRED];
 #pragma unroll
   for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1; i += gridDim.x * blockDim.x) {
     const LmFactor f = i < n0 ? fac0[i] : fac1[i - n0];
-    d_eval_factor(f, q, t, acc);
+    d_eval_factor<false>(f, R, t, acc);
   }
 #pragma unroll
   for (int k = 0; k < NRED; ++k) {
@@ -477,6 +529,10 @@ k_lm_solve_cluster(LmLmState* __restrict__ lm_g, LmProblem P, int max_iter, int 
     const double* xe = s_lm.phase == 0 ? s_lm.x : s_lm.cand;
     const double q[4] = { xe[0], xe[1], xe[2], xe[3] };
     const double t[3] = { xe[4], xe[5], xe[6] };
+    double R[9]; d_rot_of_q(q, R);
+    // the Jacobian of the last candidate of a solve is never used (no step follows): cost only.  s_lm.iteration is the
+    // number of steps computed so far, replicated in every CTA.
+    const bool cost_only = s_lm.phase != 0 && s_lm.iteration >= max_iter;
     // The factors are dealt to LMC_CLUSTER x LMC_THREADS VIRTUAL threads whatever the real cluster size is: a CTA of a
     // smaller cluster evaluates its LMC_CLUSTER / csize virtual CTAs one after the other (own accumulators, own block
     // reduction, own slice of the factor cache).  The 30-vector is therefore summed in exactly the same order for every
@@ -504,7 +560,7 @@ k_lm_solve_cluster(LmLmState* __restrict__ lm_g, LmProblem P, int max_iter, int 
         if (inext < nf) { if (first || snext >= vcache) fn = inext < n0 ? fac0[inext] : fac1[inext - n0]; else fn = d_cache_load(s_cache, sbase + snext); }
         if (first && slot < vcache) d_cache_store(s_cache, sbase + slot, f);
         if (f.kind >= 0) { if (i < n0) acc[28] += 1.0; else acc[29] += 1.0; }
-        d_eval_factor(f, q, t, acc);
+        if (cost_only) d_eval_factor<true>(f, R, t, acc); else d_eval_factor<false>(f, R, t, acc);
         f = fn; i = inext; slot = snext;
       }
     }

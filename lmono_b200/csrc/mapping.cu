@@ -397,6 +397,7 @@ extern "C" int lmono_sweep_step(lmono_ctx* ctx, lmono_cloud_view raw, lmono_pose
   int rc;
   const float4* d_in = nullptr;
   if ((rc = lm_scan_upload(ctx, raw, &d_in))) return rc;
+  lm_kmark(ctx, "begin", 0);
   if ((rc = lm_scan_enqueue(ctx, d_in, raw.n))) return rc;
   int32_t counts[5];
   if ((rc = lm_scan_fetch(ctx, raw.n, counts, scan_report))) return rc;            // sync #1: n_kept, sharp, less_sharp, flat, less_flat
@@ -729,7 +730,7 @@ extern "C" int lmono_map_clear(lmono_ctx* ctx) {
 }
 
 extern "C" int lmono_map_export(lmono_ctx* ctx, int which, int scope, lmono_cloud_out* out) {
-  if (!ctx || !out || which < 0 || which > 1 || scope < 0 || scope > 1) return LMONO_E_ARG;
+  if (!ctx || !out || which < 0 || which > 2 || scope < 0 || scope > 1) return LMONO_E_ARG;
   int total = 0;
   int rc = lm_map_export_device(ctx, which, scope, &total);
   if (rc) return rc;

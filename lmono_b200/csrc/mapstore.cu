@@ -941,7 +941,56 @@ __global__ void __launch_bounds__(256) k_export_copy(LmMapType M, const int32_t*
   for (int i = threadIdx.x; i < n; i += blockDim.x) if (o + i < cap_out) out[o + i] = src[i];
 }
 
+// which = 2: corner and surf interleaved cube by cube -- the order of the reference's publishers
+// (laserMapping.cpp:808-816: surround += corner[ind]; surround += surf[ind]; :826-830 likewise over all 4851 cubes)
+__global__ void __launch_bounds__(256) k_export_copy2(LmMapType M0, LmMapType M1, const int32_t* __restrict__ off0, const int32_t* __restrict__ off1,
+                                                      const int32_t* __restrict__ order, int count_slots, float4* __restrict__ out, int cap_out) {
+  const int e = blockIdx.x >> 1, ty = blockIdx.x & 1;
+  if (e >= count_slots) return;
+  const LmMapType& M = ty == 0 ? M0 : M1;
+  const int ps = order[e];
+  const int sid = M.slot_slab[ps];
+  if (sid < 0) return;
+  const int n = M.slab_n[sid];
+  const float4* src = M.pts + ((size_t)sid * 2 + M.slab_cur[sid]) * M.cap;
+  const int o = ty == 0 ? off0[e] + off1[e] : off0[e + 1] + off1[e];      // corner cubes 0..e and surf cubes 0..e-1 precede surf cube e
+  for (int i = threadIdx.x; i < n; i += blockDim.x) if (o + i < cap_out) out[o + i] = src[i];
+}
+
+static int export_interleaved(lmono_ctx* ctx, int scope, int* n_total) {
+  int32_t* off0 = ctx->d_export_off;
+  int32_t* order = ctx->d_export_off + LM_NSLOT + 8;
+  int32_t* off1 = ctx->d_export_off + 2 * LM_NSLOT + 16;
+  int32_t* order1 = ctx->d_export_off + 3 * LM_NSLOT + 24;
+  k_export_offsets<<<1, 1024, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], scope, off0, order);
+  LM_LAUNCH_CHECK();
+  k_export_offsets<<<1, 1024, 0, ctx->stream>>>(ctx->d_state, ctx->map[1], scope, off1, order1);
+  LM_LAUNCH_CHECK();
+  int valid_num = LM_NSLOT;
+  if (scope == 0) {
+    LM_CUDA(cudaMemcpyAsync(&ctx->h_state->valid_num, &ctx->d_state->valid_num, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LM_CUDA(cudaStreamSynchronize(ctx->stream));
+    valid_num = ctx->h_state->valid_num;
+  }
+  int t0 = 0, t1 = 0;
+  LM_CUDA(cudaMemcpyAsync(&t0, off0 + valid_num, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  LM_CUDA(cudaMemcpyAsync(&t1, off1 + valid_num, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  LM_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int total = t0 + t1;
+  *n_total = total;
+  if (total == 0) return LMONO_OK;
+  if ((size_t)total > ctx->export_cap) {
+    cudaFree(ctx->d_export);
+    ctx->export_cap = (size_t)total + (total >> 2) + 1024;
+    LM_CUDA(cudaMalloc((void**)&ctx->d_export, ctx->export_cap * sizeof(float4)));
+  }
+  k_export_copy2<<<2 * valid_num, 256, 0, ctx->stream>>>(ctx->map[0], ctx->map[1], off0, off1, order, valid_num, ctx->d_export, total);
+  LM_LAUNCH_CHECK();
+  return LMONO_OK;
+}
+
 int lm_map_export_device(lmono_ctx* ctx, int which, int scope, int* n_total) {
+  if (which == 2) return export_interleaved(ctx, scope, n_total);
   LmMapType& M = ctx->map[which];
   int32_t* order = ctx->d_export_off + LM_NSLOT + 8;
   k_export_offsets<<<1, 1024, 0, ctx->stream>>>(ctx->d_state, M, scope, ctx->d_export_off, order);

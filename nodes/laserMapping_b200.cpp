@@ -35,6 +35,11 @@ nav_msgs::Odometry to_odom(const lmono_pose& p, const ros::Time& stamp) {
   return o;
 }
 
+// named handlers: a lambda is ambiguous between roscpp's function-pointer and boost::function overloads of subscribe()
+void on_corner(const sensor_msgs::PointCloud2ConstPtr& m) { std::lock_guard<std::mutex> l(m_buf); q_corner.push(m); }
+void on_surf(const sensor_msgs::PointCloud2ConstPtr& m) { std::lock_guard<std::mutex> l(m_buf); q_surf.push(m); }
+void on_full(const sensor_msgs::PointCloud2ConstPtr& m) { std::lock_guard<std::mutex> l(m_buf); q_full.push(m); }
+
 void on_odom(const nav_msgs::Odometry::ConstPtr& m) {
   { std::lock_guard<std::mutex> l(m_buf); q_odom.push(m); }
   lmono_pose wm; { std::lock_guard<std::mutex> l(m_pose); wm = g_wmap_wodom; }
@@ -47,19 +52,18 @@ void on_odom(const nav_msgs::Odometry::ConstPtr& m) {
   pub_aft_hf.publish(to_odom(w, m->header.stamp));
 }
 
+// /laser_cloud_surround and /laser_cloud_map: corner and surf clouds interleaved cube by cube, the byte order of the
+// reference's messages (laserMapping.cpp:808-816, 826-830) -- lmono_map_export(which = 2)
 void publish_map(ros::Publisher& pub, int scope, const ros::Time& stamp) {
-  pcl::PointCloud<pcl::PointXYZI> all, part;
-  for (int which = 0; which < 2; ++which) {
-    size_t cap = 1 << 20;
-    for (;;) {
-      lmono_cloud_out o = lmono_glue::out(part, cap);
-      const int rc = lmono_map_export(g_ctx, which, scope, &o);
-      if (rc == LMONO_E_CAPACITY) { cap = static_cast<size_t>(o.n_out); continue; }
-      lmono_glue::check(rc, "lmono_map_export");
-      lmono_glue::trim(part, o);
-      break;
-    }
-    all += part;       // note: the reference interleaves corner and surf per cube; consumers are order-agnostic (rviz)
+  pcl::PointCloud<pcl::PointXYZI> all;
+  size_t cap = 1 << 20;
+  for (;;) {
+    lmono_cloud_out o = lmono_glue::out(all, cap);
+    const int rc = lmono_map_export(g_ctx, 2, scope, &o);
+    if (rc == LMONO_E_CAPACITY) { cap = static_cast<size_t>(o.n_out); continue; }
+    if (rc != LMONO_OK) { ROS_WARN("lmono_map_export: %s", lmono_strerror(rc)); return; }
+    lmono_glue::trim(all, o);
+    break;
   }
   sensor_msgs::PointCloud2 msg; pcl::toROSMsg(all, msg);
   msg.header.stamp = stamp; msg.header.frame_id = "/camera_init";
@@ -96,8 +100,15 @@ void process() {
                          {mo->pose.pose.position.x, mo->pose.pose.position.y, mo->pose.pose.position.z}};
       lmono_pose w_curr, wm; lmono_map_report rep;
       lmono_cloud_out o_reg = lmono_glue::out(registered, full.points.size());
-      lmono_glue::check(lmono_map_step(g_ctx, lmono_glue::view(corner), lmono_glue::view(surf), &odom, &w_curr, &wm, &rep,
-                                       lmono_glue::view(full), &o_reg), "lmono_map_step");
+      const int rc_step = lmono_map_step(g_ctx, lmono_glue::view(corner), lmono_glue::view(surf), &odom, &w_curr, &wm, &rep,
+                                         lmono_glue::view(full), &o_reg);
+      if (rc_step == LMONO_E_DEVICE) {      // a map capacity limit was hit (slab pool / cube slab): the pose is valid, some new points were dropped
+        uint32_t bits = 0; lmono_last_fault(g_ctx, &bits);
+        ROS_WARN("lmono_map_step: map capacity reached (fault bits 0x%x): raise max_cubes_* / cube_capacity_* (INTEGRATION.md)", bits);
+      } else if (rc_step != LMONO_OK) {
+        ROS_ERROR("lmono_map_step: %s -- sweep skipped", lmono_strerror(rc_step));
+        continue;
+      }
       lmono_glue::trim(registered, o_reg);
       { std::lock_guard<std::mutex> l(m_pose); g_wmap_wodom = wm; }
       printf("map corner num %d  surf num %d \n", rep.corner_from_map, rep.surf_from_map);
@@ -136,13 +147,10 @@ int main(int argc, char** argv) {
   lmono_params prm; lmono_default_params(&prm);
   prm.mapping_line_resolution = line_res; prm.mapping_plane_resolution = plane_res;
   lmono_glue::check(lmono_create(0, &prm, nullptr, &g_ctx), "lmono_create");
-  ros::Subscriber s0 = nh.subscribe<sensor_msgs::PointCloud2>("/laser_cloud_corner_last", 100,
-      [](const sensor_msgs::PointCloud2ConstPtr& m) { std::lock_guard<std::mutex> l(m_buf); q_corner.push(m); });
-  ros::Subscriber s1 = nh.subscribe<sensor_msgs::PointCloud2>("/laser_cloud_surf_last", 100,
-      [](const sensor_msgs::PointCloud2ConstPtr& m) { std::lock_guard<std::mutex> l(m_buf); q_surf.push(m); });
+  ros::Subscriber s0 = nh.subscribe<sensor_msgs::PointCloud2>("/laser_cloud_corner_last", 100, on_corner);
+  ros::Subscriber s1 = nh.subscribe<sensor_msgs::PointCloud2>("/laser_cloud_surf_last", 100, on_surf);
   ros::Subscriber s2 = nh.subscribe<nav_msgs::Odometry>("/laser_odom_to_init", 100, on_odom);
-  ros::Subscriber s3 = nh.subscribe<sensor_msgs::PointCloud2>("/velodyne_cloud_3", 100,
-      [](const sensor_msgs::PointCloud2ConstPtr& m) { std::lock_guard<std::mutex> l(m_buf); q_full.push(m); });
+  ros::Subscriber s3 = nh.subscribe<sensor_msgs::PointCloud2>("/velodyne_cloud_3", 100, on_full);
   pub_surround = nh.advertise<sensor_msgs::PointCloud2>("/laser_cloud_surround", 100);
   pub_map = nh.advertise<sensor_msgs::PointCloud2>("/laser_cloud_map", 100);
   pub_registered = nh.advertise<sensor_msgs::PointCloud2>("/velodyne_cloud_registered", 100);

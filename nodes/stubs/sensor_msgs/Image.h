@@ -1,0 +1,4 @@
+#pragma once
+#include <std_msgs/Header.h>
+namespace sensor_msgs { struct Image { std_msgs::Header header; unsigned height = 0, width = 0, step = 0; std::string encoding; unsigned char is_bigendian = 0; std::vector<unsigned char> data; };
+typedef boost::shared_ptr<Image const> ImageConstPtr; typedef boost::shared_ptr<Image> ImagePtr; }

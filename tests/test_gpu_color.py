@@ -57,3 +57,25 @@ def test_extrinsic_transform_and_empty(gpu_ctx_factory, oracle):
     assert np.array_equal(got["depth_raw"], raw)
     got = ctx.project_color(pts[:0], img, gcam, [0, 0, 0, 1], [0, 0, 0])
     assert got["depth_raw"].max() == 0 and len(got["cloud_world"]) == 0
+
+
+def test_projection_for_the_pro_map_discs(gpu_ctx_factory, oracle):
+    """lmono_color_projection: the cv::Point2f and depth of every point, in cloud order (what the node draws the r = 3 HSV
+    discs of ~pro_map at, Map_Builder.cc:234-243).  Writing 100 - z at (int(v), int(u)) point after point on the host must
+    rebuild the oracle's raster (last point wins), with and without lens distortion."""
+    from lmono_b200 import api
+    ctx = gpu_ctx_factory()
+    pts, img = _scene(60_000, 12)
+    for kw in ({}, dict(k1=-0.05, k2=0.01, p1=0.001, p2=-0.002)):
+        ocam = oracle.make_camera(**kw)
+        gcam = api.Pinhole(ocam.fx, ocam.fy, ocam.cx, ocam.cy, ocam.k1, ocam.k2, ocam.p1, ocam.p2, ocam.width, ocam.height, 0, 5, 0)
+        ctx.project_color(pts, img, gcam, [0, 0, 0, 1], [0, 0, 0])
+        uvz = ctx.color_projection(len(pts))
+        assert np.array_equal(uvz[:, 2], pts[:, 2])
+        ok = ~np.isnan(uvz[:, 0])
+        assert 1000 < ok.sum() < len(pts) and not np.any(ok & (pts[:, 2] < 0))
+        raster = np.zeros((ocam.height, ocam.width), np.uint8)
+        u, v = uvz[ok, 0].astype(np.int64), uvz[ok, 1].astype(np.int64)
+        val = (100.0 - uvz[ok, 2].astype(np.float64)).astype(np.int64).astype(np.uint8)       # double -> int -> low byte, as the reference's implicit conversion
+        raster[v, u] = val                                                                     # numpy assigns in order: the last point wins
+        assert np.array_equal(raster, oracle.project_raster(pts, ocam))

@@ -323,3 +323,32 @@ def test_whole_slab_revoxelisation_of_a_full_cube(gpu_ctx_factory, oracle):
     for which in (0, 1):
         assert np.array_equal(ctx.map_export(which, 0).view(np.uint32), om.export(which, 0).view(np.uint32)), which
         assert np.array_equal(ctx.map_export(which, 1).view(np.uint32), om.export(which, 1).view(np.uint32)), which
+
+
+def test_export_interleaved_like_the_reference_publishers(gpu_ctx_factory):
+    """lmono_map_export(which = 2): corner cube, surf cube, corner cube, ... in the cube order of the publishers
+    (laserMapping.cpp:808-816 over laserCloudSurroundInd, :826-830 over all 4851 cubes)."""
+    rng = np.random.default_rng(9)
+    def cloud(n, tag):
+        p = np.zeros((n, 4), np.float32)
+        p[:, :3] = rng.uniform([-180, -180, -40], [180, 180, 40], (n, 3))
+        p[:, 3] = tag                       # the VoxelGrid centroid of equal intensities keeps the tag
+        return p
+    ctx = gpu_ctx_factory()
+    ctx.map_import(0, cloud(30_000, 1.0))
+    ctx.map_import(1, cloud(80_000, 2.0))
+    ctx.map_prepare_window(np.array([30.0, -20.0, 5.0]))
+    q, t, cen = ctx.map_get_state()
+    for scope in (0, 1):
+        c, s, both = ctx.map_export(0, scope), ctx.map_export(1, scope), ctx.map_export(2, scope)
+        assert len(both) == len(c) + len(s) and len(c) > 0 and len(s) > 0
+        assert np.array_equal(both[both[:, 3] == 1.0].view(np.uint32), c.view(np.uint32))
+        assert np.array_equal(both[both[:, 3] == 2.0].view(np.uint32), s.view(np.uint32))
+        g = np.floor((both[:, :3].astype(np.float64) + 25.0) / 50.0).astype(np.int64) + np.array(cen)
+        if scope == 1:
+            cube = g[:, 0] + 21 * g[:, 1] + 441 * g[:, 2]            # :826-830 linear index
+        else:
+            cube = (g[:, 0] * 64 + g[:, 1]) * 64 + g[:, 2]            # :512-529 loop order: i outer, j, k inner
+        key = cube * 4 + both[:, 3].astype(np.int64)
+        assert np.all(np.diff(key) >= 0), scope                      # grouped by cube, corner before surf inside a cube
+        assert len(np.unique(cube)) > 5
