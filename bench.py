@@ -506,7 +506,7 @@ def run_ours(args):
                   peak_src=peak_src, cpu=(rank == 0 and world == 1 and not args.no_cpu), steps=args.steps)
     if rank == 0:
         for name, fn in (("fused_sweep", leg_fused_sweep), ("c2_odometry", leg_c2_odometry), ("colour_frame", leg_colour_frame),
-                         ("c1_cpu_pipeline", leg_c1_cpu_pipeline)):
+                         ("c1_cpu_pipeline", leg_c1_cpu_pipeline), ("c4_fused_batch", leg_c4_fused_batch)):
             if name not in legs:
                 continue
             try:
@@ -822,6 +822,56 @@ def leg_c1_cpu_pipeline(L, cm, sm):
             "max_position_difference_vs_cpu_m": worst}
 
 
+def leg_c4_fused_batch(L, cm, sm):
+    """BASELINE config C-4: independent C-1-style sequences (seeds 100..), fused scanRegistration -> laserOdometry ->
+    laserMapping, all sequences of this GPU per call (lmono_sweep_step_batch: every sweep enqueued without a host round
+    trip, each sequence on its own stream).  A KITTI-length sequence is 4541 sweeps; a sample of it is timed."""
+    api, torch = L.api, L.torch
+    S, NSW = 8, 12
+    seqs = []
+    for s_ in range(S):
+        wld = synth.make_world(seed=100 + s_ + 8 * L.rank)
+        rng = np.random.default_rng(100 + s_)
+        seqs.append([torch.from_numpy(np.ascontiguousarray(synth.raycast_sweep_torch(wld, *synth.loop_pose(wld, 1.0 * k), 64, 1875, rng, device=L.dev),
+                                                            np.float32)).pin_memory() for k in range(NSW)])
+    ctxs = [api.Context(device=L.local, stream=L.main.cuda_stream) for _ in range(S)]
+    batch = api.SweepBatch(ctxs)
+
+    def sweep_index(i):                  # 0, 1, ..., NSW-1, NSW-2, ..., 1, 0, 1, ...: consecutive sweeps are always 1 m apart
+        p = i % (2 * NSW - 2)
+        return p if p < NSW else 2 * NSW - 2 - p
+
+    nwarm, nstep = 6, max(12, min(L.steps, 40))
+    for i in range(nwarm):
+        res = batch.step([seqs[s_][sweep_index(i)].numpy() for s_ in range(S)])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(nwarm, nwarm + nstep):
+        res = batch.step([seqs[s_][sweep_index(i)].numpy() for s_ in range(S)])
+    wall = time.perf_counter() - t0
+    assert all(r[4].optimized == 1 for r in res)
+    # one sequence alone, synchronous lmono_sweep_step, for comparison
+    one = api.Context(device=L.local, stream=L.main.cuda_stream)
+    for i in range(nwarm):
+        one.sweep_step(seqs[0][sweep_index(i)].numpy())
+    t1 = time.perf_counter()
+    for i in range(nwarm, nwarm + nstep):
+        one.sweep_step(seqs[0][sweep_index(i)].numpy())
+    wall1 = time.perf_counter() - t1
+    one.close()
+    for c_ in ctxs:
+        c_.close()
+    npts = int(np.mean([len(a) for a in seqs[0]]))
+    return {"metric": "fused sweeps/s (scanRegistration + laserOdometry + laserMapping), 8 sequences per GPU", "value": S * nstep / wall, "unit": "sweeps/s",
+            "ms_per_batch_step": 1e3 * wall / nstep,
+            "config": {"workload": "C-4: independent C-1-style HDL-64 sequences (seeds 100..), fused L1 -> L2 -> L3 per sweep, maps grown from empty",
+                       "sequences_per_gpu": S, "points_per_sweep": npts, "batch_steps_timed": nstep,
+                       "sample": f"{nstep} consecutive sweeps of each sequence (a KITTI-length sequence has 4541)"},
+            "e2e": {"value": S * nstep / wall, "unit": "sweeps/s", "h2d_bytes_per_step": S * npts * 16, "d2h_bytes_per_step": S * 4000,
+                    "note": "raw sweeps in page-locked host memory, poses and reports read back every sweep; wall clock"},
+            "single_sequence_synchronous": {"value": nstep / wall1, "unit": "sweeps/s", "what": "one sequence, lmono_sweep_step per sweep"}}
+
+
 def c5_map(tiles, cm, sm):
     """the C-3 tile (250 x 250 m, cube-aligned) repeated on a lattice of 250 m pitch and cropped to the cube ring the
     reference's 21 x 21 x 11 grid can hold around the origin (+-525 m): C-3 density everywhere"""
@@ -988,7 +1038,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-pipeline", action="store_true", help="skip every extra leg")
     ap.add_argument("--cpu-steps", type=int, default=60)
-    ap.add_argument("--legs", default="fused_sweep,c2_odometry,colour_frame,c1_cpu_pipeline,c5_sharded",
+    ap.add_argument("--legs", default="fused_sweep,c2_odometry,colour_frame,c1_cpu_pipeline,c4_fused_batch,c5_sharded",
                     help="extra legs (keys of the same JSON line): the other BASELINE configs; c5_sharded runs when N > 1")
     ap.add_argument("--c5-tiles", type=int, default=5, help="C-5 map = the C-3 tile repeated on a tiles x tiles lattice of 250 m pitch, cropped to the 1050 m cube ring")
     args = ap.parse_args()

@@ -73,7 +73,7 @@ typedef struct {
   /* capacities (0 = default) */
   int32_t max_sweep_points;          /* raw points per sweep            (default 262144) */
   int32_t max_feature_points;        /* points per feature cloud        (default 131072) */
-  int32_t cube_capacity_corner;      /* points per 50 m cube, corner map (default 16384) */
+  int32_t cube_capacity_corner;      /* points per 50 m cube, corner map (default 32768) */
   int32_t cube_capacity_surf;        /* points per 50 m cube, surf map   (default 49152) */
   int32_t max_cubes_corner;          /* non-empty cubes held at once     (default 768) */
   int32_t max_cubes_surf;            /*                                  (default 768) */
@@ -318,6 +318,19 @@ int lmono_scan_register(lmono_ctx* ctx, lmono_cloud_view raw, lmono_cloud_out* f
 int lmono_sweep_step(lmono_ctx* ctx, lmono_cloud_view raw, lmono_pose* odom_last_curr, lmono_pose* odom_w_curr,
                      lmono_pose* map_w_curr, lmono_pose* wmap_wodom,
                      lmono_scan_report* scan_report, lmono_odom_report* odom_report, lmono_map_report* map_report);
+/* The same without any host synchronisation inside the sweep: lmono_sweep_submit enqueues upload, the three stages and the
+ * result read-backs (the feature counts stay on the device; grids are sized from bounds), lmono_sweep_wait blocks until the
+ * sweep is done and returns what lmono_sweep_step returns (bit-identical).  One sweep per ctx may be outstanding and no other
+ * call on the ctx may come between the two.  own_stream != 0: a ctx that was created on a caller-supplied stream shared
+ * with other sequences runs the sweep on a private stream (ordered after what the caller's stream holds at submit time;
+ * later work is ordered by lmono_sweep_wait, which blocks the host), so that the sweeps of several ctxs overlap.  A page-locked `raw` buffer must stay valid until
+ * the wait.  lmono_sweep_step_batch = submit for every ctx, then wait for every ctx (BASELINE config C-4: n independent
+ * sequences per GPU, fused L1 -> L2 -> L3); array arguments have n entries and may be NULL. */
+int lmono_sweep_submit(lmono_ctx* ctx, lmono_cloud_view raw, int own_stream);
+int lmono_sweep_wait(lmono_ctx* ctx, lmono_pose* odom_last_curr, lmono_pose* odom_w_curr, lmono_pose* map_w_curr, lmono_pose* wmap_wodom,
+                     lmono_scan_report* scan_report, lmono_odom_report* odom_report, lmono_map_report* map_report);
+int lmono_sweep_step_batch(lmono_ctx* const* ctxs, int32_t n, const lmono_cloud_view* raws, lmono_pose* odom_w_curr, lmono_pose* map_w_curr,
+                           lmono_scan_report* scan_reports, lmono_odom_report* odom_reports, lmono_map_report* map_reports);
 int lmono_scan_debug(lmono_ctx* ctx, float* curvature, int32_t* src_index, int32_t n);
 
 /* ------------------------------------------------------------------ L2: laserOdometry */

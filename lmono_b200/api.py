@@ -406,6 +406,23 @@ class Context:
                                           C.byref(srep), C.byref(orep), C.byref(mrep)), "sweep_step")
         return lc.as_np(), ow.as_np(), mw.as_np(), srep, orep, mrep
 
+    def sweep_submit(self, raw, own_stream=True):
+        """enqueue-only fused sweep (lmono_sweep_submit): `raw` (float32 [n, 3|4], C-contiguous; page-locked memory makes the
+        upload asynchronous) must stay untouched until sweep_wait()"""
+        if raw.dtype != np.float32 or not raw.flags["C_CONTIGUOUS"]:
+            raise ValueError("sweep_submit needs a C-contiguous float32 array (it is read after the call returns)")
+        self._sweep_keep = raw
+        self._chk(self.L.lmono_sweep_submit(self._h, view_of(raw), 1 if own_stream else 0), "sweep_submit")
+
+    def sweep_wait(self):
+        """results of the outstanding sweep_submit(): the same tuple sweep_step returns"""
+        lc, ow, mw, wm = Pose(), Pose(), Pose(), Pose()
+        srep, orep, mrep = ScanReport(), OdomReport(), MapReport()
+        self._chk(self.L.lmono_sweep_wait(self._h, C.byref(lc), C.byref(ow), C.byref(mw), C.byref(wm),
+                                          C.byref(srep), C.byref(orep), C.byref(mrep)), "sweep_wait")
+        self._sweep_keep = None
+        return lc.as_np(), ow.as_np(), mw.as_np(), srep, orep, mrep
+
     def odom_step(self, sharp, less_sharp, flat, less_flat):
         a, b, c, d = (_xyzi(x) for x in (sharp, less_sharp, flat, less_flat))
         lc, wc, rep = Pose(), Pose(), OdomReport()
@@ -457,6 +474,33 @@ class Context:
         buf, out = _out(len(p))
         self._chk(self.L.lmono_voxel_grid(self._h, view_of(p), C.c_float(leaf), C.byref(out)), "voxel_grid")
         return buf[: out.n_out].copy()
+
+
+class SweepBatch:
+    """n independent sequences, one fused sweep each per call (lmono_sweep_step_batch, BASELINE config C-4): every ctx runs
+    its sweep on its own stream, all are enqueued before the first is waited for."""
+
+    def __init__(self, contexts):
+        self.ctxs = list(contexts)
+        n = self.n = len(self.ctxs)
+        self.L = self.ctxs[0].L
+        self._h = (C.c_void_p * n)(*[c._h for c in self.ctxs])
+        self._views = (CloudView * n)()
+        self._ow, self._mw = (Pose * n)(), (Pose * n)()
+        self._srep, self._orep, self._mrep = (ScanReport * n)(), (OdomReport * n)(), (MapReport * n)()
+
+    def step(self, raws):
+        """raws: n float32 [n_i, 3|4] arrays.  Returns [((q, t) odometry, (q, t) mapped, scan, odom, map report)] * n;
+        the reports are views of buffers the next call overwrites."""
+        assert len(raws) == self.n
+        for i, r in enumerate(raws):
+            if r.dtype != np.float32 or not r.flags["C_CONTIGUOUS"]:
+                raise ValueError("C-contiguous float32 arrays expected")
+            self._views[i] = view_of(r)
+        rc = self.L.lmono_sweep_step_batch(self._h, self.n, self._views, self._ow, self._mw, self._srep, self._orep, self._mrep)
+        if rc:
+            raise LmonoError(rc, "sweep_step_batch")
+        return [(self._ow[i].as_np(), self._mw[i].as_np(), self._srep[i], self._orep[i], self._mrep[i]) for i in range(self.n)]
 
 
 class ColorBuffers:

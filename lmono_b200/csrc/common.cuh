@@ -186,6 +186,10 @@ struct lmono_ctx {
   int last_cuda_error;
   int64_t launches;
   cudaEvent_t ev0, ev1;
+  // asynchronous fused sweep (lmono_sweep_submit / _wait): its own stream when the ctx shares the caller's stream with other sequences
+  cudaStream_t sweep_stream; cudaEvent_t ev_sweep; int sweep_n_in, sweep_prev_n; bool sweep_outstanding;
+  // the whole sweep (scanRegistration + laserOdometry + laserMapping) as ONE CUDA graph per raw-size bucket
+  struct { int n_cap; int form; cudaGraphExec_t exec; int n_launch; } sweep_graphs[8]; int n_sweep_graphs;
   cudaEvent_t ev_o0, ev_o1;     // odometry stage of a fused sweep (lmono_sweep_step)
   cudaEvent_t ev_k0;            // after the uploads of a stage call: ev_k0 .. ev1 = the stage's kernels with inputs resident in HBM (lmono_stage_times)
   cudaEvent_t ev_fork;          // fork point of a sequence batch (lmono_map_step_device_batch)

@@ -16,7 +16,7 @@ extern "C" void lmono_default_params(lmono_params* p) {
   p->mapping_line_resolution = 0.4f; p->mapping_plane_resolution = 0.8f;
   p->mapping_skip_frame = 1;
   p->max_sweep_points = 262144; p->max_feature_points = 131072;
-  p->cube_capacity_corner = 16384; p->cube_capacity_surf = 49152;
+  p->cube_capacity_corner = 32768; p->cube_capacity_surf = 49152;
   p->max_cubes_corner = 768; p->max_cubes_surf = 768;
   p->image_width = 1241; p->image_height = 376;
 }
@@ -163,6 +163,7 @@ extern "C" void lmono_destroy(lmono_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < ctx->n_graphs; ++i) cudaGraphExecDestroy(ctx->graphs[i].exec);
+  for (int i = 0; i < ctx->n_sweep_graphs; ++i) cudaGraphExecDestroy(ctx->sweep_graphs[i].exec);
   lm_batch_free(ctx);
   lm_shard_free(ctx);
   lm_scan_free(ctx);
@@ -177,6 +178,8 @@ extern "C" void lmono_destroy(lmono_ctx* ctx) {
   cudaEvent_t evs[] = { ctx->ev0, ctx->ev1, ctx->ev_k0, ctx->ev_o0, ctx->ev_o1, ctx->ev_fork, ctx->ev_join, ctx->ev_sync, ctx->ev_done, ctx->ev_side0, ctx->ev_side1 };
   for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
   if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+  if (ctx->sweep_stream) cudaStreamDestroy(ctx->sweep_stream);
+  if (ctx->ev_sweep) cudaEventDestroy(ctx->ev_sweep);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   cudaGetLastError();
   free(ctx);

@@ -32,9 +32,15 @@ __global__ void k_set_counts(LmMapState* st, int n0, int n1) {
 // of the step is a parameter-free kernel sequence that can be replayed as a CUDA graph
 struct StepArgs { double q[4]; double t[3]; int n0, n1; int set_wmap; int slot; double wq[4]; double wt[3]; const float4* in[2];
                   const void* src[2]; int stride[2]; int ioff[2];
-                  const double* pose_src; };    // not NULL: q[4], t[3] of wodom_curr are read from device memory (fused sweep: the odometry stage's result)
+                  const double* pose_src;       // not NULL: q[4], t[3] of wodom_curr are read from device memory (fused sweep: the odometry stage's result)
+                  const int32_t* n_src; int n_cap; };   // not NULL: feature counts read from device memory, n_src[2] corner, n_src[4] surf (scanRegistration's counts); n0 / n1 are bounds
 __device__ __forceinline__ void d_apply_step_args(LmMapState* st, const StepArgs& a) {
   st->raw_n[0] = a.n0; st->raw_n[1] = a.n1;
+  if (a.n_src) {
+    const int c = a.n_src[2], s = a.n_src[4];
+    if (c > a.n0 || s > a.n1 || c > a.n_cap || s > a.n_cap) atomicOr(&st->fault, LM_FAULT_FEATURE_OVERFLOW);
+    st->raw_n[0] = min(c, min(a.n0, a.n_cap)); st->raw_n[1] = min(s, min(a.n1, a.n_cap));
+  }
   st->in_ptr[0] = a.in[0]; st->in_ptr[1] = a.in[1];
   for (int k = 0; k < 2; ++k) { st->in_src[k] = a.src[k]; st->in_stride[k] = a.stride[k]; st->in_ioff[k] = a.ioff[k]; }
   st->result_slot = a.slot;
@@ -154,7 +160,7 @@ static int bucket_up(int n, int cap) {
 // one step's inputs as the kernels see them: d[k] = float4 XYZI array in device memory that the step reads (for a
 // fused upload: the ctx's own d_in[k], filled by k_vg_keys from src[k]); src / stride / ioff describe the caller's
 // page-locked AoS buffer (stride 0 = d[k] already holds the data)
-struct LmStepIn { const float4* d[2]; int n[2]; const void* src[2]; int stride[2]; int ioff[2]; const double* pose_src; };
+struct LmStepIn { const float4* d[2]; int n[2]; const void* src[2]; int stride[2]; int ioff[2]; const double* pose_src; const int32_t* n_src; };
 
 static LmStepIn step_in_device(const float4* d_corner, int nc, const float4* d_surf, int ns) {
   LmStepIn in;
@@ -187,7 +193,7 @@ static int resolve_input(lmono_ctx* ctx, lmono_cloud_view v, int which, LmStepIn
 
 static void fill_step_args(StepArgs* a, const LmStepIn& in, const lmono_pose* wodom_curr, const lmono_pose* wmap_in, int slot) {
   memset(a, 0, sizeof(*a));
-  a->pose_src = in.pose_src;
+  a->pose_src = in.pose_src; a->n_src = in.n_src; a->n_cap = 1 << 30;
   if (wodom_curr) { for (int k = 0; k < 4; ++k) a->q[k] = wodom_curr->q[k]; for (int k = 0; k < 3; ++k) a->t[k] = wodom_curr->t[k]; }
   a->n0 = in.n[0]; a->n1 = in.n[1];
   for (int k = 0; k < 2; ++k) { a->in[k] = in.d[k]; a->src[k] = in.src[k]; a->stride[k] = in.stride[k]; a->ioff[k] = in.ioff[k]; }
@@ -380,13 +386,16 @@ extern "C" int lmono_map_step_device(lmono_ctx* ctx, const void* d_corner, int32
 // clouds and the odometry pose stay in device memory between the stages, one small read-back in the middle (the feature
 // counts size the next launches) and one at the end.  Results are bit-identical to the three separate calls.
 int lm_scan_upload(lmono_ctx* ctx, lmono_cloud_view raw, const float4** d_in);
-int lm_scan_enqueue(lmono_ctx* ctx, const float4* d_in, int n);
+int lm_scan_enqueue(lmono_ctx* ctx, const float4* d_in, int n, bool n_on_device = false);
+int lm_scan_set_n(lmono_ctx* ctx, int n);
+int lm_scan_input_buffer(lmono_ctx* ctx, float4** d_in);
 int lm_scan_fetch(lmono_ctx* ctx, int n_in, int32_t counts[5], lmono_scan_report* report);
 int lm_scan_outputs(lmono_ctx* ctx, const float4** full, const float4** sharp, const float4** less_sharp, const float4** flat,
                     const float4** less_flat, const int32_t** counts);
 int lm_odom_enqueue_auto(lmono_ctx* ctx, const float4* sharp, int n_sharp, const float4* less_sharp, int n_ls,
                          const float4* flat, int n_flat, const float4* less_flat, int n_lf, const double** d_pose7);
 int lm_odom_readback(lmono_ctx* ctx);
+int lm_odom_prepare(lmono_ctx* ctx);
 int lm_odom_deliver(lmono_ctx* ctx, lmono_pose* last_curr, lmono_pose* w_curr, lmono_odom_report* report);
 
 extern "C" int lmono_sweep_step(lmono_ctx* ctx, lmono_cloud_view raw, lmono_pose* odom_last_curr, lmono_pose* odom_w_curr,
@@ -418,6 +427,157 @@ extern "C" int lmono_sweep_step(lmono_ctx* ctx, lmono_cloud_view raw, lmono_pose
   const int rc2 = lm_odom_deliver(ctx, odom_last_curr, odom_w_curr, odom_report);
   if (odom_report) { float ms = 0.f; if (cudaEventElapsedTime(&ms, ctx->ev_o0, ctx->ev_o1) == cudaSuccess) odom_report->ms_gpu = ms; else cudaGetLastError(); }
   return rc ? rc : rc2;
+}
+
+// ---- asynchronous fused sweep: no host round trip inside a sweep --------------------------------------------------
+// lmono_sweep_step synchronises in the middle (the feature counts size the later launches).  Here every cloud size stays
+// on the device: the odometry and mapping stages read scanRegistration's counts there and their grids are sized from
+// bounds the host knows (picks per ring and sector, the raw size of this and the previous sweep), so a sweep is one
+// run of enqueues and a host that drives several sequences can have all their sweeps in flight at once (config C-4).
+int lm_scan_readback(lmono_ctx* ctx);
+int lm_scan_deliver(lmono_ctx* ctx, int n_in, lmono_scan_report* report);
+int lm_odom_enqueue_devcounts(lmono_ctx* ctx, const float4* sharp, const float4* less_sharp, const float4* flat, const float4* less_flat,
+                              const int32_t* d_counts, int n_raw, int n_raw_prev, const double** d_pose7);
+
+constexpr int LM_SWEEP_BUCKET = 16384;
+// stages of one sweep on device-resident input, every size read on the device; n_cap bounds the raw sweep
+static int sweep_enqueue_stages(lmono_ctx* ctx, const float4* d_in, int n_cap) {
+  int rc;
+  if ((rc = lm_scan_enqueue(ctx, d_in, n_cap, /*n_on_device=*/true))) return rc;
+  const float4 *sharp, *less_sharp, *flat, *less_flat; const int32_t* d_counts;
+  if ((rc = lm_scan_outputs(ctx, nullptr, &sharp, &less_sharp, &flat, &less_flat, &d_counts))) return rc;
+  const double* d_pose7 = nullptr;
+  if ((rc = lm_odom_enqueue_devcounts(ctx, sharp, less_sharp, flat, less_flat, d_counts, n_cap, n_cap, &d_pose7))) return rc;
+  const int b_ls = ctx->prm.scan_line * 6 * 20;
+  LmStepIn in = step_in_device(less_sharp, b_ls < ctx->max_feat ? b_ls : ctx->max_feat, less_flat, n_cap < ctx->max_feat ? n_cap : ctx->max_feat);
+  in.pose_src = d_pose7; in.n_src = d_counts;
+  StepArgs a;
+  fill_step_args(&a, in, nullptr, nullptr, 0);
+  a.n_cap = ctx->max_feat;
+  k_step_args<<<1, 32, 0, ctx->stream>>>(ctx->d_state, a);
+  LM_LAUNCH_CHECK();
+  return enqueue_body(ctx, bucket_up(in.n[0], ctx->max_feat), bucket_up(in.n[1], ctx->max_feat));
+}
+
+static int sweep_graph_launch(lmono_ctx* ctx, const float4* d_in, int n) {
+  const int n_cap = lm_div_up(n > 0 ? n : 1, LM_SWEEP_BUCKET) * LM_SWEEP_BUCKET;
+  const int form = lm_graph_form(ctx->batch_n);
+  int gi = -1;
+  for (int i = 0; i < ctx->n_sweep_graphs; ++i) if (ctx->sweep_graphs[i].n_cap == n_cap && ctx->sweep_graphs[i].form == form) gi = i;
+  if (gi < 0) {
+    if (ctx->n_sweep_graphs == 8) { for (int i = 0; i < 8; ++i) cudaGraphExecDestroy(ctx->sweep_graphs[i].exec); ctx->n_sweep_graphs = 0; }
+    const int64_t l0 = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    LM_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = sweep_enqueue_stages(ctx, d_in, n_cap);
+    const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    LM_CUDA(ce);
+    gi = ctx->n_sweep_graphs;
+    ctx->sweep_graphs[gi].n_cap = n_cap; ctx->sweep_graphs[gi].form = form;
+    ctx->sweep_graphs[gi].n_launch = (int)(ctx->launches - l0);
+    ctx->launches = l0;
+    const cudaError_t ci = cudaGraphInstantiate(&ctx->sweep_graphs[gi].exec, graph, 0);
+    cudaGraphDestroy(graph);
+    LM_CUDA(ci);
+    ctx->n_sweep_graphs++;
+  }
+  LM_CUDA(cudaGraphLaunch(ctx->sweep_graphs[gi].exec, ctx->stream));
+  ctx->launches += ctx->sweep_graphs[gi].n_launch;
+  LM_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  LM_CUDA(cudaEventRecord(ctx->ev_o0, ctx->stream)); LM_CUDA(cudaEventRecord(ctx->ev_o1, ctx->stream));      // stages are not timed separately inside the graph
+  ctx->step_pending = true; ctx->step_timed = true;
+  return LMONO_OK;
+}
+
+extern "C" int lmono_sweep_submit(lmono_ctx* ctx, lmono_cloud_view raw, int own_stream) {
+  if (!ctx) return LMONO_E_ARG;
+  if (raw.n > ctx->max_sweep) return LMONO_E_CAPACITY;
+  if (ctx->sweep_outstanding) return LMONO_E_STATE;
+  if (!ctx->ev_sweep) LM_CUDA(cudaEventCreateWithFlags(&ctx->ev_sweep, cudaEventDisableTiming));
+  cudaStream_t caller = ctx->stream;
+  if (own_stream && !ctx->own_stream) {
+    // the ctx shares its stream with other sequences: run the sweep on a private stream, ordered after the caller's
+    if (!ctx->sweep_stream) LM_CUDA(cudaStreamCreateWithFlags(&ctx->sweep_stream, cudaStreamNonBlocking));
+    LM_CUDA(cudaEventRecord(ctx->ev_sync, caller));
+    LM_CUDA(cudaStreamWaitEvent(ctx->sweep_stream, ctx->ev_sync, 0));
+    ctx->stream = ctx->sweep_stream;
+  }
+  struct Restore { lmono_ctx* c; cudaStream_t s; ~Restore() { c->stream = s; } } restore{ctx, caller};
+  int rc;
+  const float4* d_in = nullptr;
+  if ((rc = lm_scan_upload(ctx, raw, &d_in))) return rc;                       // records ev0
+  if (ctx->graphs_on && !ctx->prof_on && !ctx->kmark_on && !ctx->shard_p2p) {
+    // the three stages as ONE graph per raw-size bucket: nothing in it depends on the host (sweep size, feature counts and
+    // the odometry pose are read from device memory), so a sweep costs the host an upload, one argument launch, one
+    // graph launch and the read-backs
+    if ((rc = lm_odom_prepare(ctx))) return rc;
+    if ((rc = lm_scan_set_n(ctx, raw.n))) return rc;
+    rc = sweep_graph_launch(ctx, d_in, raw.n);
+    if (rc) return rc;
+    if ((rc = lm_odom_readback(ctx))) return rc;
+    if ((rc = lm_scan_readback(ctx))) return rc;
+  } else {
+  lm_kmark(ctx, "begin", 0);
+  if ((rc = lm_scan_enqueue(ctx, d_in, raw.n))) return rc;
+  LM_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
+  const float4 *sharp, *less_sharp, *flat, *less_flat; const int32_t* d_counts;
+  if ((rc = lm_scan_outputs(ctx, nullptr, &sharp, &less_sharp, &flat, &less_flat, &d_counts))) return rc;
+  const double* d_pose7 = nullptr;
+  LM_CUDA(cudaEventRecord(ctx->ev_o0, ctx->stream));
+  if ((rc = lm_odom_enqueue_devcounts(ctx, sharp, less_sharp, flat, less_flat, d_counts, raw.n, ctx->sweep_prev_n > 0 ? ctx->sweep_prev_n : raw.n, &d_pose7))) return rc;
+  LM_CUDA(cudaEventRecord(ctx->ev_o1, ctx->stream));
+  if ((rc = lm_odom_readback(ctx))) return rc;
+  if ((rc = lm_scan_readback(ctx))) return rc;
+  const int b_ls = ctx->prm.scan_line * 6 * 20;
+  LmStepIn in = step_in_device(less_sharp, b_ls < ctx->max_feat ? b_ls : ctx->max_feat, less_flat, raw.n < ctx->max_feat ? raw.n : ctx->max_feat);
+  in.pose_src = d_pose7; in.n_src = d_counts;
+  if ((rc = enqueue_step(ctx, in, nullptr))) return rc;                          // records ev0 (again) .. ev1 around the mapping stage
+  }
+  LM_CUDA(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(LmMapState), cudaMemcpyDeviceToHost, ctx->stream));
+  LM_CUDA(cudaEventRecord(ctx->ev_sweep, ctx->stream));
+  // no join back into the caller's stream here (it would chain the sweeps of ctxs that share that stream one behind the
+  // other): lmono_sweep_wait blocks the host until the sweep is done, so whatever is enqueued afterwards sees the new map
+  ctx->sweep_n_in = raw.n; ctx->sweep_prev_n = raw.n; ctx->sweep_outstanding = true;
+  return LMONO_OK;
+}
+
+extern "C" int lmono_sweep_wait(lmono_ctx* ctx, lmono_pose* odom_last_curr, lmono_pose* odom_w_curr, lmono_pose* map_w_curr, lmono_pose* wmap_wodom,
+                                lmono_scan_report* scan_report, lmono_odom_report* odom_report, lmono_map_report* map_report) {
+  if (!ctx) return LMONO_E_ARG;
+  if (!ctx->sweep_outstanding) return LMONO_E_STATE;
+  LM_CUDA(cudaEventSynchronize(ctx->ev_sweep));
+  ctx->sweep_outstanding = false;
+  float ms_map = 0.f, ms_scan = 0.f, ms_odom = 0.f;
+  if (cudaEventElapsedTime(&ms_map, ctx->ev0, ctx->ev1) != cudaSuccess) cudaGetLastError();
+  if (cudaEventElapsedTime(&ms_odom, ctx->ev_o0, ctx->ev_o1) != cudaSuccess) cudaGetLastError();
+  ctx->step_pending = false;
+  const int rc_scan = lm_scan_deliver(ctx, ctx->sweep_n_in, scan_report);
+  if (scan_report) scan_report->ms_gpu = ms_scan;       // the stage start event is reused by the mapping stage: not timed in this path
+  const int rc_odom = lm_odom_deliver(ctx, odom_last_curr, odom_w_curr, odom_report);
+  if (odom_report) odom_report->ms_gpu = ms_odom;
+  const int rc_map = deliver(ctx, ctx->h_state, ms_map, map_w_curr, wmap_wodom, map_report);
+  return rc_scan ? rc_scan : (rc_map ? rc_map : rc_odom);
+}
+
+// n independent sequences, one fused sweep each (BASELINE config C-4): all sweeps are enqueued before the first result is
+// waited for, every ctx on its own stream, so the stages of different sequences overlap on the device
+extern "C" int lmono_sweep_step_batch(lmono_ctx* const* ctxs, int32_t n, const lmono_cloud_view* raws, lmono_pose* odom_w_curr, lmono_pose* map_w_curr,
+                                      lmono_scan_report* scan_reports, lmono_odom_report* odom_reports, lmono_map_report* map_reports) {
+  if (!ctxs || n < 0 || !raws) return LMONO_E_ARG;
+  for (int i = 0; i < n; ++i) if (!ctxs[i]) return LMONO_E_ARG;
+  int first = LMONO_OK, n_sub = 0;
+  for (int i = 0; i < n; ++i) {
+    const int rc = lmono_sweep_submit(ctxs[i], raws[i], 1);
+    if (rc) { first = rc; break; }
+    ++n_sub;
+  }
+  for (int i = 0; i < n_sub; ++i) {
+    const int rc = lmono_sweep_wait(ctxs[i], nullptr, odom_w_curr ? &odom_w_curr[i] : nullptr, map_w_curr ? &map_w_curr[i] : nullptr, nullptr,
+                                    scan_reports ? &scan_reports[i] : nullptr, odom_reports ? &odom_reports[i] : nullptr, map_reports ? &map_reports[i] : nullptr);
+    if (rc && !first) first = rc;
+  }
+  return first;
 }
 
 extern "C" int lmono_map_collect(lmono_ctx* ctx, lmono_pose* w_curr, lmono_pose* wmap_wodom, lmono_map_report* report) {

@@ -38,8 +38,11 @@ struct OdomState {
 
 constexpr int NN_QB = 64, NN_SUB = 4, NN_TILE = 256, NN_CHUNK = 1024;     // 1024 targets per CTA: ~28 x 20 CTAs for an HDL-64 sweep instead of 7 x 20 long ones
 
-__global__ void k_odom_begin(OdomDev* o, int n_sharp, int n_ls, int n_flat, int n_lf) {
+// counts: NULL = the host knows the cloud sizes (arguments); else device counts {n_kept, sharp, less_sharp, flat, less_flat}
+// as scanRegistration leaves them (fused sweep without a host round trip between the stages)
+__global__ void k_odom_begin(OdomDev* o, int n_sharp, int n_ls, int n_flat, int n_lf, const int32_t* __restrict__ counts, int cap) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (counts) { n_sharp = min(counts[1], cap); n_ls = min(counts[2], cap); n_flat = min(counts[3], cap); n_lf = min(counts[4], cap); }   // an oversize cloud also raises LM_FAULT_FEATURE_OVERFLOW in the mapping stage
   o->n_sharp = n_sharp; o->n_less_sharp = n_ls; o->n_flat = n_flat; o->n_less_flat = n_lf;
   o->do_solve = o->inited;                       // first frame only initialises (:267-271)
   for (int k = 0; k < 2; ++k) {
@@ -72,13 +75,14 @@ __global__ void __launch_bounds__(NN_QB * NN_SUB) k_odom_nn1(const OdomDev* __re
   const float4* __restrict__ ts = which == 0 ? corner_last : surf_last;
   unsigned long long* __restrict__ best = which == 0 ? best0 : best1;
   const int q0 = blockIdx.x * NN_QB;
-  const int c0 = blockIdx.y * NN_CHUNK;
-  if (q0 >= nq || c0 >= nt) return;
+  if (q0 >= nq) return;
   const int qi = q0 + (threadIdx.x / NN_SUB);
   const int sub = threadIdx.x % NN_SUB;
   float4 sel = make_float4(0.f, 0.f, 0.f, 0.f);
   if (qi < nq) sel = d_to_start(o, qs[qi]);
   unsigned long long bestk = ~0ULL;
+  // target chunks are dealt round-robin over gridDim.y: the grid does not depend on the (device-side) target count
+  for (int c0 = blockIdx.y * NN_CHUNK; c0 < nt; c0 += gridDim.y * NN_CHUNK) {
   const int c1 = min(c0 + NN_CHUNK, nt);
   for (int tb = c0; tb < c1; tb += NN_TILE) {
     __syncthreads();
@@ -94,6 +98,7 @@ __global__ void __launch_bounds__(NN_QB * NN_SUB) k_odom_nn1(const OdomDev* __re
       const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)(tb + k);
       bestk = key < bestk ? key : bestk;
     }
+  }
   }
 #pragma unroll
   for (int ofs = NN_SUB / 2; ofs > 0; ofs >>= 1) {
@@ -219,6 +224,15 @@ __global__ void k_odom_finish(OdomDev* o) {
   o->n_corner_last = o->n_less_sharp; o->n_surf_last = o->n_less_flat;   // :554-563
 }
 
+// :554-563 the less-sharp / less-flat clouds of this sweep become the "last" clouds (sizes read on the device)
+__global__ void __launch_bounds__(256) k_odom_keep_last(const OdomDev* __restrict__ o, const float4* __restrict__ ls, const float4* __restrict__ lf,
+                                                        float4* __restrict__ last0, float4* __restrict__ last1) {
+  const int n0 = o->n_less_sharp, n1 = o->n_less_flat;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1; i += gridDim.x * blockDim.x) {
+    if (i < n0) last0[i] = ls[i]; else last1[i - n0] = lf[i - n0];
+  }
+}
+
 __global__ void k_odom_reset(OdomDev* o) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   o->inited = 0; o->do_solve = 0;
@@ -245,6 +259,9 @@ static int odom_state(lmono_ctx* ctx, OdomState** out) {
   return LMONO_OK;
 }
 
+// allocate the stage's state outside any stream capture (cudaMalloc is not allowed while this thread captures)
+int lm_odom_prepare(lmono_ctx* ctx) { OdomState* s; return odom_state(ctx, &s); }
+
 void lm_odom_free(lmono_ctx* ctx) {
   OdomState* s = (OdomState*)ctx->odom_state;
   if (!s) return;
@@ -263,7 +280,8 @@ static int odom_associate(lmono_ctx* ctx, OdomState* s, const float4* sharp, int
   LM_LAUNCH_CHECK();
   const int nlm = nl_max0 > nl_max1 ? nl_max0 : nl_max1;
   if (nlm > 0) {
-    dim3 grid(lm_div_up(nq, NN_QB), lm_div_up(nlm, NN_CHUNK), 2);
+    const int gy = lm_div_up(nlm, NN_CHUNK);
+    dim3 grid(lm_div_up(nq, NN_QB), gy < 48 ? gy : 48, 2);
     k_odom_nn1<<<grid, NN_QB * NN_SUB, 0, ctx->stream>>>(s->d, sharp, flat, s->d_last[0], s->d_last[1], s->d_best[0], s->d_best[1]);
     LM_LAUNCH_CHECK();
   }
@@ -275,10 +293,12 @@ static int odom_associate(lmono_ctx* ctx, OdomState* s, const float4* sharp, int
 }
 
 // enqueue one odometry step on device-resident feature clouds (sizes known to the host)
+// d_counts != NULL: the cloud sizes are read on the device (n_* are then upper bounds that only size the grids)
 int lm_odom_enqueue(lmono_ctx* ctx, const float4* sharp, int n_sharp, const float4* less_sharp, int n_ls,
-                    const float4* flat, int n_flat, const float4* less_flat, int n_lf, int prev_ls_max, int prev_lf_max) {
+                    const float4* flat, int n_flat, const float4* less_flat, int n_lf, int prev_ls_max, int prev_lf_max,
+                    const int32_t* d_counts = nullptr) {
   OdomState* s; int rc = odom_state(ctx, &s); if (rc) return rc;
-  k_odom_begin<<<1, 32, 0, ctx->stream>>>(s->d, n_sharp, n_ls, n_flat, n_lf);
+  k_odom_begin<<<1, 32, 0, ctx->stream>>>(s->d, n_sharp, n_ls, n_flat, n_lf, d_counts, s->cap);
   LM_LAUNCH_CHECK();
   for (int opti = 0; opti < 2; ++opti) {                       // :278
     if ((rc = odom_associate(ctx, s, sharp, n_sharp, flat, n_flat, prev_ls_max, prev_lf_max, opti))) return rc;
@@ -293,8 +313,29 @@ int lm_odom_enqueue(lmono_ctx* ctx, const float4* sharp, int n_sharp, const floa
   }
   k_odom_finish<<<1, 32, 0, ctx->stream>>>(s->d);
   LM_LAUNCH_CHECK();
+  if (d_counts) {
+    const int nb = lm_div_up(n_ls + n_lf > 0 ? n_ls + n_lf : 1, 256);
+    k_odom_keep_last<<<nb < 296 ? nb : 296, 256, 0, ctx->stream>>>(s->d, less_sharp, less_flat, s->d_last[0], s->d_last[1]);
+    LM_LAUNCH_CHECK();
+    return LMONO_OK;
+  }
   if (n_ls > 0) LM_CUDA(cudaMemcpyAsync(s->d_last[0], less_sharp, (size_t)n_ls * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
   if (n_lf > 0) LM_CUDA(cudaMemcpyAsync(s->d_last[1], less_flat, (size_t)n_lf * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+  return LMONO_OK;
+}
+
+// fused sweep without a host round trip after scanRegistration: every cloud size stays on the device.  Grids are sized
+// from bounds the host knows: <= 2 / 20 / 4 picks per (ring, sector) (scanRegistration.cpp:297-310,352-358), the less-flat
+// cloud and the previous sweep's clouds by the raw sizes of this and the previous sweep.
+int lm_odom_enqueue_devcounts(lmono_ctx* ctx, const float4* sharp, const float4* less_sharp, const float4* flat, const float4* less_flat,
+                              const int32_t* d_counts, int n_raw, int n_raw_prev, const double** d_pose7) {
+  OdomState* s; int rc = odom_state(ctx, &s); if (rc) return rc;
+  const int rings = ctx->prm.scan_line;
+  const int b_sharp = rings * 6 * 2, b_ls = rings * 6 * 20, b_flat = rings * 6 * 4;
+  const int b_lf = n_raw < s->cap ? n_raw : s->cap, b_lf_prev = n_raw_prev < s->cap ? n_raw_prev : s->cap;
+  if (b_ls > s->cap) return LMONO_E_CAPACITY;
+  if ((rc = lm_odom_enqueue(ctx, sharp, b_sharp, less_sharp, b_ls, flat, b_flat, less_flat, b_lf, b_ls, b_lf_prev > 0 ? b_lf_prev : 1, d_counts))) return rc;
+  *d_pose7 = s->d->q_w_curr;
   return LMONO_OK;
 }
 

@@ -17,6 +17,7 @@
 // fp32 arithmetic uses __fmul_rn/__fadd_rn in the reference's association order; comparisons
 // against the double literals 0.1 / 0.05 widen the float first, as C++ does.
 #include "common.cuh"
+#include <stddef.h>
 #include <string.h>
 #include <stdlib.h>
 #include <float.h>
@@ -30,12 +31,15 @@ constexpr int SC_PICK_STRIDE = 26;      // per (ring, sector): 2 sharp + 20 less
 
 struct ScanMeta {
   int32_t first_valid, last_valid, i_star, n_kept;
+  int32_t out_n[4];                     // sharp, less_sharp, flat, less_flat -- directly behind n_kept: &n_kept is the 5-count array the later stages read on the device
   int32_t ring_total[SC_NRING + 3];
   int32_t ring_start[SC_NRING + 3];
-  int32_t out_n[4];                     // sharp, less_sharp, flat, less_flat
   float start_ori, end_ori;
   uint32_t fault;
+  int32_t n_in;                         // raw sweep size for launches that do not carry it as an argument (graph replay of the fused sweep); survives k_scan_meta_init
 };
+
+static_assert(offsetof(ScanMeta, out_n) == offsetof(ScanMeta, n_kept) + sizeof(int32_t), "lm_scan_outputs hands out &n_kept as counts[5]");
 
 struct ScanState {
   int cap, nb_max;
@@ -82,6 +86,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_classify(const float4* __re
   for (int e = threadIdx.x; e < (SC_THREADS / 32) * SC_NRING; e += blockDim.x) (&counts[0][0])[e] = 0;
   int ring = 64;
   bool valid0 = false;
+  if (n < 0) n = meta->n_in;
   if (i < n) {
     const float4 p = in[i];
     if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
@@ -132,6 +137,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_halfpass(const float4* __re
   __shared__ float s_so, s_eo;
   __shared__ int s_min[SC_THREADS / 32];
   if (meta->last_valid < 0) return;
+  if (n < 0) n = meta->n_in;
   if (threadIdx.x == 0) d_start_end_ori(in, meta, &s_so, &s_eo);
   __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -191,6 +197,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_scatter(const float4* __res
     }
   }
   __syncthreads();
+  if (n < 0) n = meta->n_in;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int k = key[i];
@@ -542,10 +549,26 @@ void lm_scan_free(lmono_ctx* ctx) {
 }
 
 // enqueue the whole stage on a device-resident float4 input; results stay on the device
-int lm_scan_enqueue(lmono_ctx* ctx, const float4* d_in, int n) {
+__global__ void k_scan_set_n(ScanMeta* meta, int n) { if (threadIdx.x == 0 && blockIdx.x == 0) meta->n_in = n; }
+int lm_scan_set_n(lmono_ctx* ctx, int n) {
+  ScanState* s; int rc = scan_state(ctx, &s); if (rc) return rc;
+  k_scan_set_n<<<1, 32, 0, ctx->stream>>>(s->d_meta, n);
+  LM_LAUNCH_CHECK();
+  return LMONO_OK;
+}
+int lm_scan_input_buffer(lmono_ctx* ctx, float4** d_in) {
+  ScanState* s; int rc = scan_state(ctx, &s); if (rc) return rc;
+  *d_in = s->d_in;
+  return LMONO_OK;
+}
+
+// n_on_device: `n` is only an upper bound that sizes the grids; the kernels read the sweep size from ScanMeta::n_in
+// (lm_scan_set_n), so the launch sequence carries no per-sweep argument and can be replayed as a CUDA graph
+int lm_scan_enqueue(lmono_ctx* ctx, const float4* d_in, int n, bool n_on_device) {
   ScanState* s; int rc = scan_state(ctx, &s); if (rc) return rc;
   const int n_scans = ctx->prm.scan_line;
   const int nb = lm_div_up(n > 0 ? n : 1, SC_THREADS);
+  if (n_on_device) n = -1;
   k_scan_meta_init<<<1, 32, 0, ctx->stream>>>(s->d_meta); LM_LAUNCH_CHECK();
   k_scan_classify<<<nb, SC_THREADS, 0, ctx->stream>>>(d_in, n, n_scans, ctx->prm.minimum_range, s->d_key, s->d_block_hist, nb, s->d_meta); LM_LAUNCH_CHECK();
   k_scan_halfpass<<<nb, SC_THREADS, 0, ctx->stream>>>(d_in, n, s->d_key, s->d_meta); LM_LAUNCH_CHECK();
@@ -590,6 +613,20 @@ static void scan_fill_report(lmono_ctx* ctx, const ScanMeta* m, int n_in, lmono_
   }
   report->start_ori = m->start_ori; report->end_ori = m->end_ori;
 }
+// sync-free sweep: enqueue the read-back of the stage's meta record; lm_scan_deliver fills the report once the stream
+// (or an event behind this copy) has been waited for
+int lm_scan_readback(lmono_ctx* ctx) {
+  ScanState* s; int rc = scan_state(ctx, &s); if (rc) return rc;
+  LM_CUDA(cudaMemcpyAsync(s->h_meta, s->d_meta, sizeof(ScanMeta), cudaMemcpyDeviceToHost, ctx->stream));
+  return LMONO_OK;
+}
+int lm_scan_deliver(lmono_ctx* ctx, int n_in, lmono_scan_report* report) {
+  ScanState* s = (ScanState*)ctx->scan_state;
+  if (!s) return LMONO_E_STATE;
+  if (report) scan_fill_report(ctx, s->h_meta, n_in, report);
+  if (s->h_meta->fault) { fprintf(stderr, "[lmono_b200] scan_register fault bits 0x%x (ring or sector larger than the kernel limit)\n", s->h_meta->fault); return LMONO_E_DEVICE; }
+  return LMONO_OK;
+}
 int lm_scan_fetch(lmono_ctx* ctx, int n_in, int32_t counts[5], lmono_scan_report* report) {
   ScanState* s; int rc = scan_state(ctx, &s); if (rc) return rc;
   LM_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -612,7 +649,7 @@ extern "C" int lmono_scan_register(lmono_ctx* ctx, lmono_cloud_view raw, lmono_c
   if ((rc = lm_upload_cloud(ctx, raw, ctx->d_raw[2], s->d_in, nullptr))) return rc;
   LM_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
   lm_kmark(ctx, "begin", 0);
-  if ((rc = lm_scan_enqueue(ctx, s->d_in, raw.n))) return rc;
+  if ((rc = lm_scan_enqueue(ctx, s->d_in, raw.n, false))) return rc;
   LM_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
   LM_CUDA(cudaMemcpyAsync(s->h_meta, s->d_meta, sizeof(ScanMeta), cudaMemcpyDeviceToHost, ctx->stream));
   LM_CUDA(cudaStreamSynchronize(ctx->stream));

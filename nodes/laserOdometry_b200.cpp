@@ -27,6 +27,7 @@ int main(int argc, char** argv) {
   printf("Mapping %d Hz \n", 10 / skip_frame_num);
   lmono_params prm; lmono_default_params(&prm); prm.mapping_skip_frame = skip_frame_num;
   lmono_ctx* ctx = nullptr;
+  prm.max_cubes_corner = prm.max_cubes_surf = 1;      // this node never touches the cube map: no slab pool
   lmono_glue::check(lmono_create(0, &prm, nullptr, &ctx), "lmono_create");
 
   ros::Subscriber s0 = nh.subscribe<sensor_msgs::PointCloud2>("/laser_cloud_sharp", 100, push<&q_sharp>);

@@ -55,6 +55,7 @@ int main(int argc, char** argv) {
   printf("scan line number %d \n", scan_line);
   if (scan_line != 16 && scan_line != 32 && scan_line != 64) { printf("only support velodyne with 16, 32 or 64 scan line!"); return 0; }
   prm.scan_line = scan_line; prm.minimum_range = static_cast<float>(minimum_range);
+  prm.max_cubes_corner = prm.max_cubes_surf = 1;      // this node never touches the cube map: no slab pool
   lmono_glue::check(lmono_create(0, &prm, nullptr, &g_ctx), "lmono_create");
   ros::Subscriber sub = nh.subscribe<sensor_msgs::PointCloud2>("/velodyne_points", 100, on_sweep);
   pub_full = nh.advertise<sensor_msgs::PointCloud2>("/velodyne_cloud_2", 100);

@@ -69,6 +69,53 @@ def test_fused_sweep_equals_three_calls(gpu_ctx_factory):
     assert fmrep.optimized == 1
 
 
+def test_async_sweep_and_sweep_batch_equal_the_synchronous_sweep(gpu_ctx_factory):
+    """lmono_sweep_submit / _wait (no host round trip inside a sweep: the feature counts stay on the device, grids are sized
+    from bounds) and lmono_sweep_step_batch (4 sequences on one shared caller stream, each sweep on a private stream) must
+    give exactly what lmono_sweep_step gives, sequence by sequence and bit for bit."""
+    import torch
+    from lmono_b200 import api
+    NS, NK = 4, 6
+    seqs = [_raw_sweeps(NK, seed=20 + s) for s in range(NS)]
+    ref = []
+    for s in range(NS):
+        c = gpu_ctx_factory()
+        ref.append([c.sweep_step(raw) for (raw, _, _) in seqs[s]])
+        ref[-1].append([c.map_export(w, 1) for w in (0, 1)])
+        c.close()
+    # (1) one sequence through submit / wait
+    c = gpu_ctx_factory()
+    for k, (raw, _, _) in enumerate(seqs[0]):
+        raw = np.ascontiguousarray(raw, np.float32)
+        c.sweep_submit(raw)
+        got = c.sweep_wait()
+        exp = ref[0][k]
+        for a in range(3):
+            assert np.array_equal(got[a][0], exp[a][0]) and np.array_equal(got[a][1], exp[a][1]), (k, a)
+        assert (got[3].n_kept, got[3].n_sharp, got[3].n_less_sharp, got[3].n_flat, got[3].n_less_flat) == \
+               (exp[3].n_kept, exp[3].n_sharp, exp[3].n_less_sharp, exp[3].n_flat, exp[3].n_less_flat)
+        assert list(got[4].corner_corr) == list(exp[4].corner_corr) and list(got[4].plane_corr) == list(exp[4].plane_corr)
+        assert list(got[5].corner_num) == list(exp[5].corner_num) and list(got[5].surf_num) == list(exp[5].surf_num)
+    for w in (0, 1):
+        assert np.array_equal(c.map_export(w, 1).view(np.uint32), ref[0][NK][w].view(np.uint32))
+    # (2) four sequences per call, all created on ONE caller stream
+    st = torch.cuda.Stream()
+    ctxs = [gpu_ctx_factory(stream=st.cuda_stream) for _ in range(NS)]
+    batch = api.SweepBatch(ctxs)
+    for k in range(NK):
+        raws = [torch.from_numpy(np.ascontiguousarray(seqs[s][k][0], np.float32)).pin_memory() for s in range(NS)]
+        res = batch.step([r.numpy() for r in raws])
+        for s in range(NS):
+            (oq, ot), (mq, mt), srep, orep, mrep = res[s]
+            exp = ref[s][k]
+            assert np.array_equal(oq, exp[1][0]) and np.array_equal(ot, exp[1][1]), (s, k)
+            assert np.array_equal(mq, exp[2][0]) and np.array_equal(mt, exp[2][1]), (s, k)
+            assert list(mrep.corner_num) == list(exp[5].corner_num) and list(mrep.surf_num) == list(exp[5].surf_num)
+    for s in range(NS):
+        for w in (0, 1):
+            assert np.array_equal(ctxs[s].map_export(w, 1).view(np.uint32), ref[s][NK][w].view(np.uint32)), (s, w)
+
+
 def test_cpp_replay_harness_matches_python_binding(gpu_ctx_factory, tmp_path):
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "nodes")], check=True)
     sweeps = _raw_sweeps(4, seed=6)
