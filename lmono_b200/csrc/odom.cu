@@ -33,15 +33,19 @@ struct OdomState {
   float4* d_last[2];                // laserCloudCornerLast, laserCloudSurfLast
   unsigned long long* d_best[2];    // packed 1-NN result per sharp / flat feature
   int32_t* d_corr;                  // test hook: [n_sharp*2] + [n_flat*3]
+  int32_t* d_ringtab;               // [2][RT_STRIDE]: per last cloud, first index with ring >= r (r = 0..65) and a "sorted by ring" flag at [66]
   int cap;
 };
 
+constexpr int RT_STRIDE = 68;
 constexpr int NN_QB = 64, NN_SUB = 4, NN_TILE = 256, NN_CHUNK = 1024;     // 1024 targets per CTA: ~28 x 20 CTAs for an HDL-64 sweep instead of 7 x 20 long ones
 
 // counts: NULL = the host knows the cloud sizes (arguments); else device counts {n_kept, sharp, less_sharp, flat, less_flat}
 // as scanRegistration leaves them (fused sweep without a host round trip between the stages)
-__global__ void k_odom_begin(OdomDev* o, int n_sharp, int n_ls, int n_flat, int n_lf, const int32_t* __restrict__ counts, int cap) {
+__global__ void k_odom_begin(OdomDev* o, int n_sharp, int n_ls, int n_flat, int n_lf, const int32_t* __restrict__ counts, int cap, int32_t* __restrict__ ringtab) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  ringtab[66] = 1; ringtab[RT_STRIDE + 66] = 1;          // "sorted by ring" until k_odom_ring_table finds a descent
+  for (int r = 0; r < 66; ++r) { ringtab[r] = o->n_corner_last; ringtab[RT_STRIDE + r] = o->n_surf_last; }
   if (counts) { n_sharp = min(counts[1], cap); n_ls = min(counts[2], cap); n_flat = min(counts[3], cap); n_lf = min(counts[4], cap); }   // an oversize cloud also raises LM_FAULT_FEATURE_OVERFLOW in the mapping stage
   o->n_sharp = n_sharp; o->n_less_sharp = n_ls; o->n_flat = n_flat; o->n_less_flat = n_lf;
   o->do_solve = o->inited;                       // first frame only initialises (:267-271)
@@ -120,12 +124,54 @@ __device__ __forceinline__ unsigned long long d_warp_min_u64(unsigned long long 
   return v;
 }
 
+// Ring tables of the two "last" clouds.  scanRegistration emits its clouds ring by ring, so the ring id (integer part of the
+// intensity) is non-decreasing along a cloud and the reference's window scans -- "walk up until ring > id + 2.5" / "walk
+// down until ring < id - 2.5" (:315-319,341-345) -- visit exactly the index ranges [closest + 1, first(ring >= id + 3)) and
+// [first(ring >= id - 2), closest).  With the bounds known up front the scan needs no early-exit test per step and its
+// loads are independent.  A cloud that is NOT monotonic in the ring id (a caller may pass anything) keeps the step-wise
+// scan with the reference's break rule.  blockIdx.x: 0 corner_last, 1 surf_last.
+constexpr int RT_CTAS = 16;       // CTAs per cloud for the monotonicity check (k_odom_begin arms the flags)
+__global__ void __launch_bounds__(256) k_odom_ring_table(const OdomDev* __restrict__ o, const float4* __restrict__ corner_last,
+                                                         const float4* __restrict__ surf_last, int32_t* __restrict__ tab_all) {
+  const int c = blockIdx.y;
+  const float4* __restrict__ pts = c == 0 ? corner_last : surf_last;
+  const int n = c == 0 ? o->n_corner_last : o->n_surf_last;
+  int32_t* tab = tab_all + c * RT_STRIDE;
+  int bad = 0;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {   // ring ids outside [0, 64] (never produced by scanRegistration) also take the step-wise scan
+    const int r = (int)pts[j].w;
+    const int rp = j > 0 ? (int)pts[j - 1].w : -1;
+    bad |= (r < 0) | (r > 64) | (rp > r);
+    // j is the first index of every ring in (rp, r]: tab[ring] = first index with ring id >= ring.  Entries above the last
+    // ring keep the n that k_odom_begin stored.
+    if (r >= 0 && r <= 64) for (int rr = max(rp + 1, 0); rr <= r; ++rr) tab[rr] = j;
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicAnd(&tab[66], 0);
+}
+
+template <bool IS_CORNER>
+__device__ __forceinline__ void d_corr_candidate(float4 p, float4 sel, int id, uint32_t rank, bool ascending, unsigned long long gate_hi,
+                                                 unsigned long long& m2, unsigned long long& m3) {
+  const float d = d_sqdis(p, sel);
+  const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | rank;
+  if ((key >> 32) < gate_hi) {
+    const int ring = (int)p.w;
+    if (ascending) {
+      if (IS_CORNER) { if (ring > id) m2 = key < m2 ? key : m2; }
+      else { if (ring <= id) m2 = key < m2 ? key : m2; else m3 = key < m3 ? key : m3; }
+    } else {
+      if (IS_CORNER) { if (ring < id) m2 = key < m2 ? key : m2; }
+      else { if (ring >= id) m2 = key < m2 ? key : m2; else m3 = key < m3 ? key : m3; }
+    }
+  }
+}
+
 // one warp per feature; features [0, n_sharp) are corners, [n_sharp, n_sharp + n_flat) planes
 __global__ void __launch_bounds__(256) k_odom_corr(const OdomDev* __restrict__ o, const float4* __restrict__ sharp,
                                                    const float4* __restrict__ flat, const float4* __restrict__ corner_last,
                                                    const float4* __restrict__ surf_last, const unsigned long long* __restrict__ best0,
                                                    const unsigned long long* __restrict__ best1, LmFactor* __restrict__ fac0,
-                                                   LmFactor* __restrict__ fac1, int32_t* __restrict__ corr_out) {
+                                                   LmFactor* __restrict__ fac1, int32_t* __restrict__ corr_out, const int32_t* __restrict__ ringtab) {
   if (!o->do_solve) return;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -147,6 +193,33 @@ __global__ void __launch_bounds__(256) k_odom_corr(const OdomDev* __restrict__ o
     const int id = (int)last[closest].w;                       // closestPointScanID
     unsigned long long m2 = ~0ULL, m3 = ~0ULL;
     const unsigned long long gate = (unsigned long long)__float_as_uint(25.0f) << 32;   // candidates need d2 < 25
+    const int32_t* tab = ringtab + (is_corner ? 0 : RT_STRIDE);
+    const uint32_t rank0 = 1u << 30;
+    if (tab[66]) {
+      // ring-sorted cloud: the two windows as index ranges, four independent loads per lane and trip
+      const int hi = tab[min(max(id + 3, 0), 65)], lo = tab[min(max(id - 2, 0), 65)];
+      const unsigned long long ghi = gate >> 32;
+      for (int j0 = closest + 1 + lane; j0 < hi; j0 += 128) {
+        float4 p[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (j0 + 32 * u < hi) p[u] = last[j0 + 32 * u];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (j0 + 32 * u < hi) {
+          if (is_corner) d_corr_candidate<true>(p[u], sel, id, (uint32_t)(j0 + 32 * u - closest), true, ghi, m2, m3);
+          else d_corr_candidate<false>(p[u], sel, id, (uint32_t)(j0 + 32 * u - closest), true, ghi, m2, m3);
+        }
+      }
+      for (int j0 = closest - 1 - lane; j0 >= lo; j0 -= 128) {
+        float4 p[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (j0 - 32 * u >= lo) p[u] = last[j0 - 32 * u];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (j0 - 32 * u >= lo) {
+          if (is_corner) d_corr_candidate<true>(p[u], sel, id, rank0 + (uint32_t)(closest - (j0 - 32 * u)), false, ghi, m2, m3);
+          else d_corr_candidate<false>(p[u], sel, id, rank0 + (uint32_t)(closest - (j0 - 32 * u)), false, ghi, m2, m3);
+        }
+      }
+    } else {
     // ascending j (:312-335, 402-427)
     bool stop = false;
     for (int base = closest + 1; base < nl && !stop; base += 32) {
@@ -166,7 +239,6 @@ __global__ void __launch_bounds__(256) k_odom_corr(const OdomDev* __restrict__ o
       stop = om != 0;
     }
     // descending j (:338-361, 430-455); visit ranks continue after the ascending pass
-    const uint32_t rank0 = 1u << 30;
     stop = false;
     for (int base = closest - 1; base >= 0 && !stop; base -= 32) {
       const int j = base - lane;
@@ -183,6 +255,7 @@ __global__ void __launch_bounds__(256) k_odom_corr(const OdomDev* __restrict__ o
         }
       }
       stop = um != 0;
+    }
     }
     m2 = d_warp_min_u64(m2); m3 = d_warp_min_u64(m3);
     if (m2 != ~0ULL) { const uint32_t r = (uint32_t)m2; ind2 = r >= rank0 ? closest - (int)(r - rank0) : closest + (int)r; }
@@ -252,6 +325,7 @@ static int odom_state(lmono_ctx* ctx, OdomState** out) {
   for (int k = 0; k < 4; ++k) LM_CUDA(cudaMalloc((void**)&s->d_feat[k], n * sizeof(float4)));
   for (int k = 0; k < 2; ++k) { LM_CUDA(cudaMalloc((void**)&s->d_last[k], n * sizeof(float4))); LM_CUDA(cudaMalloc((void**)&s->d_best[k], n * sizeof(unsigned long long))); }
   LM_CUDA(cudaMalloc((void**)&s->d_corr, n * 10 * sizeof(int32_t)));
+  LM_CUDA(cudaMalloc((void**)&s->d_ringtab, 2 * RT_STRIDE * sizeof(int32_t)));
   k_odom_reset<<<1, 32, 0, ctx->stream>>>(s->d);
   LM_LAUNCH_CHECK();
   ctx->odom_state = s;
@@ -268,7 +342,7 @@ void lm_odom_free(lmono_ctx* ctx) {
   cudaFree(s->d); cudaFreeHost(s->h);
   for (int k = 0; k < 4; ++k) cudaFree(s->d_feat[k]);
   for (int k = 0; k < 2; ++k) { cudaFree(s->d_last[k]); cudaFree(s->d_best[k]); }
-  cudaFree(s->d_corr);
+  cudaFree(s->d_corr); cudaFree(s->d_ringtab);
   free(s); ctx->odom_state = nullptr;
 }
 
@@ -287,7 +361,7 @@ static int odom_associate(lmono_ctx* ctx, OdomState* s, const float4* sharp, int
   }
   const int warps = n_sharp + n_flat;
   k_odom_corr<<<lm_div_up(warps * 32, 256), 256, 0, ctx->stream>>>(s->d, sharp, flat, s->d_last[0], s->d_last[1], s->d_best[0], s->d_best[1],
-                                                                  ctx->d_fac[0], ctx->d_fac[1], s->d_corr + (size_t)pass * s->cap * 5);
+                                                                  ctx->d_fac[0], ctx->d_fac[1], s->d_corr + (size_t)pass * s->cap * 5, s->d_ringtab);
   LM_LAUNCH_CHECK();
   return LMONO_OK;
 }
@@ -298,7 +372,9 @@ int lm_odom_enqueue(lmono_ctx* ctx, const float4* sharp, int n_sharp, const floa
                     const float4* flat, int n_flat, const float4* less_flat, int n_lf, int prev_ls_max, int prev_lf_max,
                     const int32_t* d_counts = nullptr) {
   OdomState* s; int rc = odom_state(ctx, &s); if (rc) return rc;
-  k_odom_begin<<<1, 32, 0, ctx->stream>>>(s->d, n_sharp, n_ls, n_flat, n_lf, d_counts, s->cap);
+  k_odom_begin<<<1, 32, 0, ctx->stream>>>(s->d, n_sharp, n_ls, n_flat, n_lf, d_counts, s->cap, s->d_ringtab);
+  LM_LAUNCH_CHECK();
+  k_odom_ring_table<<<dim3(RT_CTAS, 2), 256, 0, ctx->stream>>>(s->d, s->d_last[0], s->d_last[1], s->d_ringtab);
   LM_LAUNCH_CHECK();
   for (int opti = 0; opti < 2; ++opti) {                       // :278
     if ((rc = odom_associate(ctx, s, sharp, n_sharp, flat, n_flat, prev_ls_max, prev_lf_max, opti))) return rc;

@@ -343,9 +343,13 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __res
   }
   __syncthreads();
 
-  // :291-390 greedy picking: sectors of a ring are order dependent (suppression crosses the
-  // sector border), so one thread walks them in sequence; all its data is in shared memory.
-  if (threadIdx.x == 0) {
+  // :291-390 greedy picking.  The sectors of a ring are order dependent (suppression crosses the sector border) and so are
+  // the picks inside a sector, but one pick is wide: ONE WARP walks the sorted list 32 entries at a time -- every lane
+  // holds one entry, a ballot over "still unpicked" finds the next pick (the reference's `continue` over picked entries),
+  // lanes 1..5 / 6..10 test the five forward / backward gap bytes of the pick at once and mark the suppressed neighbours
+  // (the reference's two `break`-on-gap loops = first set bit of the ballot).  Same picks in the same order as the
+  // single-thread walk, at a few shared-memory round trips per pick instead of ~25.
+  if (wid == 0) {
     for (int j = 0; j < 6; ++j) {
       const int sp = S + (E - S) * j / 6, ep = S + (E - S) * (j + 1) / 6 - 1;
       const int len = ep - sp + 1;
@@ -354,33 +358,76 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __res
       int* out = pick_idx + (r * 6 + j) * SC_PICK_STRIDE;
       int n_sharp = 0, n_ls = 0, n_flat = 0;
       int largest = 0;
-      for (int k = len - 1; k >= 0; --k) {
-        const unsigned long long c = sk[k];
-        if (!((double)__uint_as_float((uint32_t)(c >> 32)) > 0.1)) break;     // sorted: nothing below qualifies either
-        const int ind = (int)(uint32_t)c, li = ind - rs;
-        if (picked[li]) continue;
-        largest++;
-        if (largest <= 2) { label[li] = 2; out[n_sharp++] = ind; out[2 + n_ls++] = ind; }
-        else if (largest <= 20) { label[li] = 1; out[2 + n_ls++] = ind; }
-        else break;
-        picked[li] = 1;
-        for (int l = 1; l <= 5; l++) { if (gap[li + l]) break; picked[li + l] = 1; }
-        for (int l = -1; l >= -5; l--) { if (gap[li + l + 1]) break; picked[li + l] = 1; }
+      bool done = false;
+      for (int k_hi = len - 1; k_hi >= 0 && !done; k_hi -= 32) {          // descending curvature
+        const int k = k_hi - lane;
+        const unsigned long long c = k >= 0 ? sk[k] : 0ull;
+        const bool qual = k >= 0 && (double)__uint_as_float((uint32_t)(c >> 32)) > 0.1;
+        const int li = (int)(uint32_t)c - rs;
+        const unsigned qm = __ballot_sync(0xffffffffu, qual);
+        const int nvalid = qm == 0xffffffffu ? 32 : __ffs(~qm) - 1;      // sorted: nothing behind the first non-qualifying entry qualifies
+        unsigned live = nvalid == 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
+        while (live) {
+          const bool cand = lane < nvalid && !picked[li];
+          const unsigned cm = __ballot_sync(0xffffffffu, cand) & live;
+          if (!cm) break;
+          const int src = __ffs(cm) - 1;
+          live &= src == 31 ? 0u : ~((2u << src) - 1u);
+          const int pli = __shfl_sync(0xffffffffu, li, src);
+          largest++;
+          if (largest > 20) { done = true; break; }
+          if (lane == 0) {
+            const int ind = pli + rs;
+            if (largest <= 2) { label[pli] = 2; out[n_sharp] = ind; out[2 + n_ls] = ind; }
+            else { label[pli] = 1; out[2 + n_ls] = ind; }
+            picked[pli] = 1;
+          }
+          if (largest <= 2) n_sharp++;
+          n_ls++;
+          const bool gf = lane >= 1 && lane <= 5 && gap[pli + lane];                // :319-330
+          const bool gb = lane >= 6 && lane <= 10 && gap[pli - (lane - 5) + 1];     // :331-342
+          const unsigned fm = (__ballot_sync(0xffffffffu, gf) >> 1) & 31u, bm = (__ballot_sync(0xffffffffu, gb) >> 6) & 31u;
+          const int nf = fm ? __ffs(fm) - 1 : 5, nb = bm ? __ffs(bm) - 1 : 5;
+          if (lane >= 1 && lane <= nf) picked[pli + lane] = 1;
+          if (lane >= 6 && lane - 5 <= nb) picked[pli - (lane - 5)] = 1;
+          __syncwarp();
+        }
+        if (nvalid < 32) break;
       }
       int smallest = 0;
-      for (int k = 0; k < len; ++k) {
-        const unsigned long long c = sk[k];
-        if (!((double)__uint_as_float((uint32_t)(c >> 32)) < 0.1)) break;
-        const int ind = (int)(uint32_t)c, li = ind - rs;
-        if (picked[li]) continue;
-        label[li] = -1; out[22 + n_flat++] = ind;
-        smallest++;
-        if (smallest >= 4) break;                                             // :359-362
-        picked[li] = 1;
-        for (int l = 1; l <= 5; l++) { if (gap[li + l]) break; picked[li + l] = 1; }
-        for (int l = -1; l >= -5; l--) { if (gap[li + l + 1]) break; picked[li + l] = 1; }
+      done = false;
+      for (int k_lo = 0; k_lo < len && !done; k_lo += 32) {               // ascending curvature
+        const int k = k_lo + lane;
+        const unsigned long long c = k < len ? sk[k] : 0ull;
+        const bool qual = k < len && (double)__uint_as_float((uint32_t)(c >> 32)) < 0.1;
+        const int li = (int)(uint32_t)c - rs;
+        const unsigned qm = __ballot_sync(0xffffffffu, qual);
+        const int nvalid = qm == 0xffffffffu ? 32 : __ffs(~qm) - 1;
+        unsigned live = nvalid == 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
+        while (live) {
+          const bool cand = lane < nvalid && !picked[li];
+          const unsigned cm = __ballot_sync(0xffffffffu, cand) & live;
+          if (!cm) break;
+          const int src = __ffs(cm) - 1;
+          live &= src == 31 ? 0u : ~((2u << src) - 1u);
+          const int pli = __shfl_sync(0xffffffffu, li, src);
+          if (lane == 0) { label[pli] = -1; out[22 + n_flat] = pli + rs; }
+          n_flat++;
+          smallest++;
+          if (smallest >= 4) { done = true; break; }                      // :359-362: the 4th flat point is neither marked nor suppressing
+          if (lane == 0) picked[pli] = 1;
+          const bool gf = lane >= 1 && lane <= 5 && gap[pli + lane];
+          const bool gb = lane >= 6 && lane <= 10 && gap[pli - (lane - 5) + 1];
+          const unsigned fm = (__ballot_sync(0xffffffffu, gf) >> 1) & 31u, bm = (__ballot_sync(0xffffffffu, gb) >> 6) & 31u;
+          const int nf = fm ? __ffs(fm) - 1 : 5, nb = bm ? __ffs(bm) - 1 : 5;
+          if (lane >= 1 && lane <= nf) picked[pli + lane] = 1;
+          if (lane >= 6 && lane - 5 <= nb) picked[pli - (lane - 5)] = 1;
+          __syncwarp();
+        }
+        if (nvalid < 32) break;
       }
-      pick_cnt[r * 18 + j * 3 + 0] = n_sharp; pick_cnt[r * 18 + j * 3 + 1] = n_ls; pick_cnt[r * 18 + j * 3 + 2] = n_flat;
+      __syncwarp();
+      if (lane == 0) { pick_cnt[r * 18 + j * 3 + 0] = n_sharp; pick_cnt[r * 18 + j * 3 + 1] = n_ls; pick_cnt[r * 18 + j * 3 + 2] = n_flat; }
     }
   }
   __syncthreads();
@@ -478,9 +525,11 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_compact(const float4* __res
     if (b == n_scans - 1 && threadIdx.x == 0) meta->out_n[3] = off + cnt;
     return;
   }
-  // picks: (ring, sector) major, pick order inside.  One thread per (ring, sector): exclusive scans of the three counts
-  // give every entry its output offsets, the <= 26 picked points of an entry are independent gathers
+  // picks: (ring, sector) major, pick order inside.  Every pick CTA scans the three counts of all (ring, sector) entries
+  // (a few hundred integers) to get the output offsets, then gathers ITS share of the entries, one warp per entry and one
+  // lane per picked point: the <= 26 gathers of an entry are in flight together instead of one behind the other.
   __shared__ int ws[33];
+  __shared__ int s_off[3][64 * 6 + 1];
   const int ne = n_scans * 6;
   int a0 = 0, a1 = 0, a2 = 0;
   for (int e0 = 0; e0 < ne; e0 += blockDim.x) {
@@ -489,14 +538,20 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_compact(const float4* __res
     if (e < ne) { c0 = pick_cnt[e * 3]; c1 = pick_cnt[e * 3 + 1]; c2 = pick_cnt[e * 3 + 2]; }
     int t0, t1, t2;
     const int x0 = d_block_exscan(c0, ws, &t0), x1 = d_block_exscan(c1, ws, &t1), x2 = d_block_exscan(c2, ws, &t2);
-    if (e < ne) {
-      const int* idx = pick_idx + e * SC_PICK_STRIDE;
-      for (int k = 0; k < c0; ++k) o_sharp[a0 + x0 + k] = full[idx[k]];
-      for (int k = 0; k < c1; ++k) o_ls[a1 + x1 + k] = full[idx[2 + k]];
-      for (int k = 0; k < c2; ++k) o_flat[a2 + x2 + k] = full[idx[22 + k]];
-    }
+    if (e < ne) { s_off[0][e] = a0 + x0; s_off[1][e] = a1 + x1; s_off[2][e] = a2 + x2; }
     a0 += t0; a1 += t1; a2 += t2;
   }
+  __syncthreads();
+  const int pc = b - n_scans, npc = gridDim.x - n_scans;               // this pick CTA, number of pick CTAs
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int e = pc * nw + wid; e < ne; e += npc * nw) {
+    const int c0 = pick_cnt[e * 3], c1 = pick_cnt[e * 3 + 1], c2 = pick_cnt[e * 3 + 2];
+    const int* idx = pick_idx + e * SC_PICK_STRIDE;
+    if (lane < c0) o_sharp[s_off[0][e] + lane] = full[idx[lane]];
+    if (lane < c1) o_ls[s_off[1][e] + lane] = full[idx[2 + lane]];
+    if (lane < c2) o_flat[s_off[2][e] + lane] = full[idx[22 + lane]];
+  }
+  if (pc != 0) return;
   if (threadIdx.x == 0) { meta->out_n[0] = a0; meta->out_n[1] = a1; meta->out_n[2] = a2; }
 }
 
@@ -576,7 +631,7 @@ int lm_scan_enqueue(lmono_ctx* ctx, const float4* d_in, int n, bool n_on_device)
   k_scan_scatter<<<nb, SC_THREADS, 0, ctx->stream>>>(d_in, n, n_scans, s->d_key, s->d_block_off, nb, s->d_meta, s->d_full, s->d_src); LM_LAUNCH_CHECK();
   k_scan_curvature<<<nb, SC_THREADS, 0, ctx->stream>>>(s->d_full, s->d_meta, s->d_curv, s->d_label); LM_LAUNCH_CHECK();
   k_scan_ring<<<n_scans, SC_THREADS, SCR_TOTAL, ctx->stream>>>(s->d_full, s->d_curv, s->d_meta, s->d_label, s->d_pick_idx, s->d_pick_cnt, s->d_lf_tmp, s->d_lf_cnt); LM_LAUNCH_CHECK();
-  k_scan_compact<<<n_scans + 1, SC_THREADS, 0, ctx->stream>>>(s->d_full, s->d_meta, n_scans, s->d_pick_idx, s->d_pick_cnt, s->d_lf_tmp, s->d_lf_cnt,
+  k_scan_compact<<<n_scans + 16, SC_THREADS, 0, ctx->stream>>>(s->d_full, s->d_meta, n_scans, s->d_pick_idx, s->d_pick_cnt, s->d_lf_tmp, s->d_lf_cnt,
                                                               s->d_out[0], s->d_out[1], s->d_out[2], s->d_out[3]); LM_LAUNCH_CHECK();
   return LMONO_OK;
 }
