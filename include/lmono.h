@@ -78,7 +78,9 @@ typedef struct {
   int32_t max_cubes_corner;          /* non-empty cubes held at once     (default 768) */
   int32_t max_cubes_surf;            /*                                  (default 768) */
   int32_t image_width, image_height; /* colour projection raster (default 1241 x 376) */
-  int32_t reserved[8];
+  int32_t distortion;                /* #define DISTORTION of laserOdometry.cpp:59 (default 0, as compiled in the reference): 1 = per-point
+                                        interpolation ratio s = (intensity - int(intensity)) / 0.1 in TransformToStart and the factors */
+  int32_t reserved[7];
 } lmono_params;
 
 void lmono_default_params(lmono_params* p);

@@ -64,8 +64,8 @@ class Params(C.Structure):
                 ("max_sweep_points", C.c_int32), ("max_feature_points", C.c_int32),
                 ("cube_capacity_corner", C.c_int32), ("cube_capacity_surf", C.c_int32),
                 ("max_cubes_corner", C.c_int32), ("max_cubes_surf", C.c_int32),
-                ("image_width", C.c_int32), ("image_height", C.c_int32),
-                ("reserved", C.c_int32 * 8)]
+                ("image_width", C.c_int32), ("image_height", C.c_int32), ("distortion", C.c_int32),
+                ("reserved", C.c_int32 * 7)]
 
 
 class SolveSummary(C.Structure):
@@ -242,7 +242,7 @@ class Context:
             try:
                 src = open(os.path.join(_CSRC, f)).read().splitlines()
                 for k in range(int(l) - 1, max(int(l) - 8, -1), -1):
-                    m = re.search(r"(k_\w+)\s*(?:<<<|,)", src[k]) if k < len(src) else None
+                    m = re.search(r"(k_\w+)(?:<\w+>)?\s*(?:<<<|,)", src[k]) if k < len(src) else None
                     if m:
                         name = m.group(1)
                         break

@@ -93,6 +93,9 @@ struct LmProblem {          // one LM solve: factor arrays, pose in/out, report 
   double* pose_q; double* pose_t;         // q (x,y,z,w), t: initial value in, result out
   LmSolveSummary* summary;
   int32_t* count0; int32_t* count1;       // valid factors per array
+  // DISTORTION 1 (laserOdometry.cpp:59): fractional part of the intensity of every factor's point (its interpolation ratio is
+  // s = frac / SCAN_PERIOD, lidarFactor.hpp:14,60); NULL = every factor has s = 1
+  const float* frac0; const float* frac1;
 };
 
 struct alignas(16) LmMapState {

@@ -101,6 +101,77 @@ __device__ __forceinline__ void d_eval_factor(const LmFactor& f, const double* R
   }
 }
 
+// ---- DISTORTION 1: factors with an interpolation ratio s != 1 (lidarFactor.hpp:27-34, 73-79) ---------------------------
+// q_last_curr = Identity.slerp(s, q), t_last_curr = s t, lp = q_last_curr * cp + t_last_curr.  The reference differentiates
+// this with Ceres Jets through Eigen's slerp (acos / sin of the quaternion's w) and multiplies by the local
+// parameterisation; here the same expressions are evaluated on forward-mode dual numbers seeded with d q / d delta
+// (EigenQuaternionParameterization::ComputeJacobian) and d t / d t = I, which is the same derivative by the chain rule.
+// Compile-time off in the reference, so this path is written for exactness, not speed.
+struct J6 { double v; double d[6]; };
+__device__ __forceinline__ J6 jc(double v) { J6 r; r.v = v; for (int k = 0; k < 6; ++k) r.d[k] = 0.0; return r; }
+__device__ __forceinline__ J6 operator+(const J6& a, const J6& b) { J6 r; r.v = a.v + b.v; for (int k = 0; k < 6; ++k) r.d[k] = a.d[k] + b.d[k]; return r; }
+__device__ __forceinline__ J6 operator-(const J6& a, const J6& b) { J6 r; r.v = a.v - b.v; for (int k = 0; k < 6; ++k) r.d[k] = a.d[k] - b.d[k]; return r; }
+__device__ __forceinline__ J6 operator-(const J6& a) { J6 r; r.v = -a.v; for (int k = 0; k < 6; ++k) r.d[k] = -a.d[k]; return r; }
+__device__ __forceinline__ J6 operator*(const J6& a, const J6& b) { J6 r; r.v = a.v * b.v; for (int k = 0; k < 6; ++k) r.d[k] = a.v * b.d[k] + a.d[k] * b.v; return r; }
+__device__ __forceinline__ J6 operator*(double a, const J6& b) { J6 r; r.v = a * b.v; for (int k = 0; k < 6; ++k) r.d[k] = a * b.d[k]; return r; }
+__device__ __forceinline__ J6 operator/(const J6& a, const J6& b) { J6 r; const double i = 1.0 / b.v; r.v = a.v * i; for (int k = 0; k < 6; ++k) r.d[k] = (a.d[k] - r.v * b.d[k]) * i; return r; }
+__device__ __forceinline__ J6 jsin(const J6& a) { J6 r; const double c = cos(a.v); r.v = sin(a.v); for (int k = 0; k < 6; ++k) r.d[k] = c * a.d[k]; return r; }
+__device__ __forceinline__ J6 jacos(const J6& a) { J6 r; const double g = -1.0 / sqrt(1.0 - a.v * a.v); r.v = acos(a.v); for (int k = 0; k < 6; ++k) r.d[k] = g * a.d[k]; return r; }
+__device__ __forceinline__ void jcross(const J6* a, const J6* b, J6* o) { o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0]; }
+
+__device__ __noinline__ void d_eval_factor_ratio(const LmFactor& f, const double* q, const double* t, double s, double* acc) {
+  // seeds: rows of the 4x3 local Jacobian for q = (x, y, z, w), identity for t
+  J6 Q[4], T[3];
+  Q[0] = jc(q[0]); Q[0].d[0] = q[3];  Q[0].d[1] = q[2];  Q[0].d[2] = -q[1];
+  Q[1] = jc(q[1]); Q[1].d[0] = -q[2]; Q[1].d[1] = q[3];  Q[1].d[2] = q[0];
+  Q[2] = jc(q[2]); Q[2].d[0] = q[1];  Q[2].d[1] = -q[0]; Q[2].d[2] = q[3];
+  Q[3] = jc(q[3]); Q[3].d[0] = -q[0]; Q[3].d[1] = -q[1]; Q[3].d[2] = -q[2];
+  for (int k = 0; k < 3; ++k) { T[k] = jc(t[k]); T[k].d[3 + k] = 1.0; }
+  // Eigen 3.3 slerp from the identity
+  const J6 dq = Q[3];
+  const J6 absD = dq.v < 0.0 ? -dq : dq;
+  J6 scale0, scale1;
+  if (absD.v >= 1.0 - DBL_EPSILON) { scale0 = jc(1.0 - s); scale1 = jc(s); }
+  else {
+    const J6 theta = jacos(absD), sinTheta = jsin(theta);
+    scale0 = jsin((1.0 - s) * theta) / sinTheta;
+    scale1 = jsin(s * theta) / sinTheta;
+  }
+  if (dq.v < 0.0) scale1 = -scale1;
+  J6 u[3] = { scale1 * Q[0], scale1 * Q[1], scale1 * Q[2] };
+  const J6 w = scale0 + scale1 * Q[3];
+  // QuaternionBase::_transformVector: uv = u x v; uv += uv; v + w uv + u x uv
+  const J6 v[3] = { jc((double)f.p[0]), jc((double)f.p[1]), jc((double)f.p[2]) };
+  J6 uv[3]; jcross(u, v, uv);
+  for (int k = 0; k < 3; ++k) uv[k] = uv[k] + uv[k];
+  J6 uuv[3]; jcross(u, uv, uuv);
+  J6 lp[3];
+  for (int k = 0; k < 3; ++k) lp[k] = ((v[k] + w * uv[k]) + uuv[k]) + s * T[k];
+  J6 r[3]; int nr;
+  if (f.kind == 0) {
+    J6 da[3], db[3], nu[3];
+    for (int k = 0; k < 3; ++k) { da[k] = lp[k] - jc(f.a[k]); db[k] = lp[k] - jc(f.b[k]); }
+    jcross(da, db, nu);
+    const double de[3] = { f.a[0] - f.b[0], f.a[1] - f.b[1], f.a[2] - f.b[2] };
+    const double inv = 1.0 / sqrt(de[0] * de[0] + de[1] * de[1] + de[2] * de[2]);
+    for (int k = 0; k < 3; ++k) r[k] = inv * nu[k];
+    nr = 3;
+  } else {
+    r[0] = (lp[0] - jc(f.a[0])) * jc(f.b[0]) + (lp[1] - jc(f.a[1])) * jc(f.b[1]) + (lp[2] - jc(f.a[2])) * jc(f.b[2]);
+    nr = 1;
+  }
+  double sq = 0.0;
+  for (int k = 0; k < nr; ++k) sq += r[k].v * r[k].v;
+  double rho0 = sq, sr = 1.0;
+  if (sq > 0.01) { const double rs = sqrt(sq); rho0 = 2.0 * 0.1 * rs - 0.01; sr = sqrt(fmax(DBL_MIN, 0.1 / rs)); }
+  acc[27] += 0.5 * rho0;
+  for (int k = 0; k < nr; ++k) {
+    double J[6];
+    for (int a = 0; a < 6; ++a) J[a] = r[k].d[a] * sr;
+    d_acc_row(J, r[k].v * sr, acc);
+  }
+}
+
 // ---- trust-region controller (single thread) -------------------------------------------
 // EigenQuaternionParameterization::Plus: q+ = [sin|d| d/|d|, cos|d|] (x) q, t+ = t + dt.  sin(|d|)/|d| and cos(|d|) are
 // even functions of |d|: for |d| < 0.25 rad (every trust-region step of a registration) both are evaluated as Horner
@@ -369,7 +440,8 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_lm_eval(LmLmState* __restrict_
   for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1; i += gridDim.x * blockDim.x) {
     const LmFactor f = i < n0 ? fac0[i] : fac1[i - n0];
-    d_eval_factor<false>(f, R, t, acc);
+    if (P.frac0 && f.kind >= 0 && f.kind <= 1) d_eval_factor_ratio(f, q, t, (double)(i < n0 ? P.frac0[i] : P.frac1[i - n0]) / 0.1, acc);
+    else d_eval_factor<false>(f, R, t, acc);
   }
 #pragma unroll
   for (int k = 0; k < NRED; ++k) {
@@ -482,6 +554,9 @@ __device__ __forceinline__ void d_warp_transpose_reduce32(double (&v)[32], int l
   }
 }
 
+// RATIO: the problem carries per-factor interpolation ratios (DISTORTION 1); a separate instantiation, so that the
+// dual-number path (a call with a large stack frame) costs the common kernel neither registers nor spills
+template <bool RATIO>
 __global__ void __launch_bounds__(LMC_THREADS, 1)
 k_lm_solve_cluster(LmLmState* __restrict__ lm_g, LmProblem P, int max_iter, int write_back, unsigned long long* __restrict__ stamps,
                    const LmShardPeers* __restrict__ peers /*NULL: map not sharded over GPUs*/, uint32_t* __restrict__ fault) {
@@ -560,7 +635,8 @@ k_lm_solve_cluster(LmLmState* __restrict__ lm_g, LmProblem P, int max_iter, int 
         if (inext < nf) { if (first || snext >= vcache) fn = inext < n0 ? fac0[inext] : fac1[inext - n0]; else fn = d_cache_load(s_cache, sbase + snext); }
         if (first && slot < vcache) d_cache_store(s_cache, sbase + slot, f);
         if (f.kind >= 0) { if (i < n0) acc[28] += 1.0; else acc[29] += 1.0; }
-        if (cost_only) d_eval_factor<true>(f, R, t, acc); else d_eval_factor<false>(f, R, t, acc);
+        if (RATIO && f.kind >= 0 && f.kind <= 1) d_eval_factor_ratio(f, q, t, (double)(i < n0 ? P.frac0[i] : P.frac1[i - n0]) / 0.1, acc);
+        else if (cost_only) d_eval_factor<true>(f, R, t, acc); else d_eval_factor<false>(f, R, t, acc);
         f = fn; i = inext; slot = snext;
       }
     }
@@ -634,15 +710,18 @@ static int lm_cluster_size(lmono_ctx* ctx) {
   const int d = ctx->device & 63;
   if (cached[d]) return cached[d];
   int best = 8;
-  if (cudaFuncSetAttribute(k_lm_solve_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, LMC_SMEM) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(k_lm_solve_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+  if (cudaFuncSetAttribute(k_lm_solve_cluster<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LMC_SMEM) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(k_lm_solve_cluster<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LMC_SMEM) != cudaSuccess) return -1;
+  cudaFuncSetAttribute(k_lm_solve_cluster<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  if (cudaFuncSetAttribute(k_lm_solve_cluster<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(LMC_CLUSTER); cfg.blockDim = dim3(LMC_THREADS); cfg.dynamicSmemBytes = LMC_SMEM;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = LMC_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, k_lm_solve_cluster, &cfg) == cudaSuccess && n >= 1) best = LMC_CLUSTER;
+    if (cudaOccupancyMaxActiveClusters(&n, k_lm_solve_cluster<false>, &cfg) == cudaSuccess && n >= 1 &&
+        cudaOccupancyMaxActiveClusters(&n, k_lm_solve_cluster<true>, &cfg) == cudaSuccess && n >= 1) best = LMC_CLUSTER;
   }
   cudaGetLastError();
   cached[d] = best;
@@ -677,7 +756,8 @@ int lm_solve_problem(lmono_ctx* ctx, const LmProblem& P, int n_max, int max_iter
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     const LmShardPeers* peers = shard_exchange ? ctx->d_shard_peers : nullptr;
-    LM_CUDA(cudaLaunchKernelEx(&cfg, k_lm_solve_cluster, ctx->d_lm, P, max_iter, write_back, ctx->d_stamps, peers, &ctx->d_state->fault));
+    if (P.frac0) LM_CUDA(cudaLaunchKernelEx(&cfg, k_lm_solve_cluster<true>, ctx->d_lm, P, max_iter, write_back, ctx->d_stamps, peers, &ctx->d_state->fault));
+    else LM_CUDA(cudaLaunchKernelEx(&cfg, k_lm_solve_cluster<false>, ctx->d_lm, P, max_iter, write_back, ctx->d_stamps, peers, &ctx->d_state->fault));
     LM_LAUNCH_CHECK();
     return LMONO_OK;
   }
@@ -700,6 +780,7 @@ static LmProblem map_problem(lmono_ctx* ctx, int solve_index) {
   P.pose_q = st->q_w_curr; P.pose_t = st->t_w_curr;
   P.summary = &st->solve[solve_index];
   P.count0 = &st->corner_num[solve_index]; P.count1 = &st->surf_num[solve_index];
+  P.frac0 = nullptr; P.frac1 = nullptr;
   return P;
 }
 

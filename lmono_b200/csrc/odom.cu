@@ -21,6 +21,7 @@ struct OdomDev {
   int32_t inited, do_solve;
   int32_t n_sharp, n_flat, n_less_sharp, n_less_flat;
   int32_t n_corner_last, n_surf_last;
+  int32_t distortion;               // #define DISTORTION (:59), from lmono_params
   int32_t corner_corr[2], plane_corr[2];
   LmSolveSummary solve[2];
   double para_q[4], para_t[3];      // q_last_curr (x,y,z,w), t_last_curr  (laserOdometry.cpp:97-98)
@@ -33,6 +34,7 @@ struct OdomState {
   float4* d_last[2];                // laserCloudCornerLast, laserCloudSurfLast
   unsigned long long* d_best[2];    // packed 1-NN result per sharp / flat feature
   int32_t* d_corr;                  // test hook: [n_sharp*2] + [n_flat*3]
+  float* d_frac[2];                 // DISTORTION 1: fractional intensity of every sharp / flat feature (factor ratio s = frac / 0.1)
   int32_t* d_ringtab;               // [2][RT_STRIDE]: per last cloud, first index with ring >= r (r = 0..65) and a "sorted by ring" flag at [66]
   int cap;
 };
@@ -62,8 +64,25 @@ __global__ void __launch_bounds__(256) k_odom_best_init(unsigned long long* b0, 
   if (i < n1) b1[i] = ~0ULL;
 }
 
-// TransformToStart (:111-129) with DISTORTION 0 (s = 1): q_last_curr * p + t_last_curr in double, stored float
-__device__ __forceinline__ float4 d_to_start(const OdomDev* o, float4 p) { return d_associate(o->para_q, o->para_t, p); }
+// TransformToStart (:111-129).  DISTORTION 0: s = 1, q_last_curr * p + t_last_curr in double, stored float.  DISTORTION 1:
+// s = (intensity - int(intensity)) / SCAN_PERIOD -- the subtraction is float arithmetic (float - int), the division double --
+// q_point_last = Identity.slerp(s, q_last_curr) (Eigen 3.3: acos / sin of w, NOT renormalised), t_point_last = s t_last_curr.
+__device__ __forceinline__ void d_slerp_identity(double s, const double* q, double* qs) {
+  const double d = q[3], absD = fabs(d);
+  double scale0, scale1;
+  if (absD >= 1.0 - DBL_EPSILON) { scale0 = 1.0 - s; scale1 = s; }
+  else { const double theta = acos(absD), sinTheta = sin(theta); scale0 = sin((1.0 - s) * theta) / sinTheta; scale1 = sin(s * theta) / sinTheta; }
+  if (d < 0.0) scale1 = -scale1;
+  qs[0] = scale1 * q[0]; qs[1] = scale1 * q[1]; qs[2] = scale1 * q[2]; qs[3] = scale0 + scale1 * q[3];
+}
+__device__ __forceinline__ float d_frac_of(float intensity) { return __fsub_rn(intensity, (float)(int)intensity); }
+__device__ __forceinline__ float4 d_to_start(const OdomDev* o, float4 p) {
+  if (!o->distortion) return d_associate(o->para_q, o->para_t, p);
+  const double s = (double)d_frac_of(p.w) / 0.1;
+  double qs[4]; d_slerp_identity(s, o->para_q, qs);
+  const double ts[3] = { s * o->para_t[0], s * o->para_t[1], s * o->para_t[2] };
+  return d_associate(qs, ts, p);
+}
 
 // blockIdx.z: 0 = sharp vs corner_last, 1 = flat vs surf_last
 __global__ void __launch_bounds__(NN_QB * NN_SUB) k_odom_nn1(const OdomDev* __restrict__ o, const float4* __restrict__ sharp,
@@ -171,7 +190,8 @@ __global__ void __launch_bounds__(256) k_odom_corr(const OdomDev* __restrict__ o
                                                    const float4* __restrict__ flat, const float4* __restrict__ corner_last,
                                                    const float4* __restrict__ surf_last, const unsigned long long* __restrict__ best0,
                                                    const unsigned long long* __restrict__ best1, LmFactor* __restrict__ fac0,
-                                                   LmFactor* __restrict__ fac1, int32_t* __restrict__ corr_out, const int32_t* __restrict__ ringtab) {
+                                                   LmFactor* __restrict__ fac1, int32_t* __restrict__ corr_out, const int32_t* __restrict__ ringtab,
+                                                   float* __restrict__ frac0, float* __restrict__ frac1) {
   if (!o->do_solve) return;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -262,6 +282,7 @@ __global__ void __launch_bounds__(256) k_odom_corr(const OdomDev* __restrict__ o
     if (m3 != ~0ULL) { const uint32_t r = (uint32_t)m3; ind3 = r >= rank0 ? closest - (int)(r - rank0) : closest + (int)r; }
   }
   if (lane != 0) return;
+  (is_corner ? frac0 : frac1)[qi] = d_frac_of(ori.w);
   if (co) { co[0] = closest; co[1] = ind2; if (!is_corner) co[2] = ind3; }
   if (is_corner) {
     if (ind2 < 0) { f->kind = -1; return; }                    // :363
@@ -306,8 +327,9 @@ __global__ void __launch_bounds__(256) k_odom_keep_last(const OdomDev* __restric
   }
 }
 
-__global__ void k_odom_reset(OdomDev* o) {
+__global__ void k_odom_reset(OdomDev* o, int distortion) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  o->distortion = distortion;
   o->inited = 0; o->do_solve = 0;
   o->n_corner_last = 0; o->n_surf_last = 0;
   for (int k = 0; k < 4; ++k) { o->para_q[k] = k == 3; o->q_w_curr[k] = k == 3; }
@@ -326,7 +348,8 @@ static int odom_state(lmono_ctx* ctx, OdomState** out) {
   for (int k = 0; k < 2; ++k) { LM_CUDA(cudaMalloc((void**)&s->d_last[k], n * sizeof(float4))); LM_CUDA(cudaMalloc((void**)&s->d_best[k], n * sizeof(unsigned long long))); }
   LM_CUDA(cudaMalloc((void**)&s->d_corr, n * 10 * sizeof(int32_t)));
   LM_CUDA(cudaMalloc((void**)&s->d_ringtab, 2 * RT_STRIDE * sizeof(int32_t)));
-  k_odom_reset<<<1, 32, 0, ctx->stream>>>(s->d);
+  for (int k = 0; k < 2; ++k) LM_CUDA(cudaMalloc((void**)&s->d_frac[k], n * sizeof(float)));
+  k_odom_reset<<<1, 32, 0, ctx->stream>>>(s->d, ctx->prm.distortion ? 1 : 0);
   LM_LAUNCH_CHECK();
   ctx->odom_state = s;
   *out = s;
@@ -342,7 +365,7 @@ void lm_odom_free(lmono_ctx* ctx) {
   cudaFree(s->d); cudaFreeHost(s->h);
   for (int k = 0; k < 4; ++k) cudaFree(s->d_feat[k]);
   for (int k = 0; k < 2; ++k) { cudaFree(s->d_last[k]); cudaFree(s->d_best[k]); }
-  cudaFree(s->d_corr); cudaFree(s->d_ringtab);
+  cudaFree(s->d_corr); cudaFree(s->d_ringtab); cudaFree(s->d_frac[0]); cudaFree(s->d_frac[1]);
   free(s); ctx->odom_state = nullptr;
 }
 
@@ -361,7 +384,7 @@ static int odom_associate(lmono_ctx* ctx, OdomState* s, const float4* sharp, int
   }
   const int warps = n_sharp + n_flat;
   k_odom_corr<<<lm_div_up(warps * 32, 256), 256, 0, ctx->stream>>>(s->d, sharp, flat, s->d_last[0], s->d_last[1], s->d_best[0], s->d_best[1],
-                                                                  ctx->d_fac[0], ctx->d_fac[1], s->d_corr + (size_t)pass * s->cap * 5, s->d_ringtab);
+                                                                  ctx->d_fac[0], ctx->d_fac[1], s->d_corr + (size_t)pass * s->cap * 5, s->d_ringtab, s->d_frac[0], s->d_frac[1]);
   LM_LAUNCH_CHECK();
   return LMONO_OK;
 }
@@ -385,6 +408,7 @@ int lm_odom_enqueue(lmono_ctx* ctx, const float4* sharp, int n_sharp, const floa
     P.pose_q = s->d->para_q; P.pose_t = s->d->para_t;
     P.summary = &s->d->solve[opti];
     P.count0 = &s->d->corner_corr[opti]; P.count1 = &s->d->plane_corr[opti];
+    P.frac0 = ctx->prm.distortion ? s->d_frac[0] : nullptr; P.frac1 = ctx->prm.distortion ? s->d_frac[1] : nullptr;
     if ((rc = lm_solve_problem(ctx, P, n_sharp + n_flat, 4, 1))) return rc;
   }
   k_odom_finish<<<1, 32, 0, ctx->stream>>>(s->d);
@@ -490,7 +514,7 @@ extern "C" int lmono_odom_step(lmono_ctx* ctx, lmono_cloud_view sharp, lmono_clo
 extern "C" int lmono_odom_reset(lmono_ctx* ctx) {
   if (!ctx) return LMONO_E_ARG;
   OdomState* s; int rc = odom_state(ctx, &s); if (rc) return rc;
-  k_odom_reset<<<1, 32, 0, ctx->stream>>>(s->d);
+  k_odom_reset<<<1, 32, 0, ctx->stream>>>(s->d, ctx->prm.distortion ? 1 : 0);
   LM_LAUNCH_CHECK();
   memset(s->h, 0, sizeof(OdomDev));
   return LMONO_OK;

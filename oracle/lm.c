@@ -46,6 +46,33 @@ static void transform_point(const double q[4], const double t[3], const double p
   }
 }
 
+/* Eigen 3.3 QuaternionBase::slerp(t, other) with *this = Identity (lidarFactor.hpp:29-31, laserOdometry.cpp:120):
+ *   d = dot = other.w; absD = |d|; if (absD >= 1 - eps) { scale0 = 1 - t; scale1 = t; }
+ *   else { theta = acos(absD); scale0 = sin((1 - t) theta) / sin(theta); scale1 = sin(t theta) / sin(theta); }
+ *   if (d < 0) scale1 = -scale1;  result = scale0 * Identity + scale1 * other        (not renormalised)
+ * dqs[4][4]: derivative of the result (x,y,z,w) w.r.t. other (x,y,z,w), as Ceres' Jets propagate it (the scales depend
+ * on other.w only; constant in the linear branch). */
+void lmono_cpu_slerp_identity(double t, const double q[4], double qs[4], double dqs[4][4]) {
+  const double d = q[3], absD = fabs(d);
+  double scale0, scale1, ds0 = 0.0, ds1 = 0.0;      /* d scale / d other.w */
+  if (absD >= 1.0 - DBL_EPSILON) { scale0 = 1.0 - t; scale1 = t; }
+  else {
+    const double theta = acos(absD), sinTheta = sin(theta), cosTheta = cos(theta);
+    const double a0 = (1.0 - t) * theta, a1 = t * theta;
+    scale0 = sin(a0) / sinTheta; scale1 = sin(a1) / sinTheta;
+    const double dtheta = -(d < 0.0 ? -1.0 : 1.0) / sqrt(1.0 - absD * absD);      /* d acos(|w|) / dw */
+    ds0 = ((1.0 - t) * cos(a0) * sinTheta - sin(a0) * cosTheta) / (sinTheta * sinTheta) * dtheta;
+    ds1 = (t * cos(a1) * sinTheta - sin(a1) * cosTheta) / (sinTheta * sinTheta) * dtheta;
+  }
+  if (d < 0.0) { scale1 = -scale1; ds1 = -ds1; }
+  qs[0] = scale1 * q[0]; qs[1] = scale1 * q[1]; qs[2] = scale1 * q[2]; qs[3] = scale0 + scale1 * q[3];
+  if (dqs) {
+    memset(dqs, 0, 16 * sizeof(double));
+    for (int k = 0; k < 3; ++k) { dqs[k][k] = scale1; dqs[k][3] = ds1 * q[k]; }
+    dqs[3][3] = ds0 + ds1 * q[3] + scale1;
+  }
+}
+
 /* EigenQuaternionParameterization::ComputeJacobian, x = (x,y,z,w): 4x3 */
 static void local_jacobian(const double q[4], double P[4][3]) {
   P[0][0] =  q[3]; P[0][1] =  q[2]; P[0][2] = -q[1];
@@ -57,7 +84,17 @@ static void local_jacobian(const double q[4], double P[4][3]) {
 /* raw (uncorrected) residual r[nr] and Jacobian Jq[nr][4], Jt[nr][3] of one block */
 static int eval_block(const o_factor* f, const double q[4], const double t[3], double r[3], double Jq[3][4], double Jt[3][3], int want_jac) {
   double lp[3], dlp[3][4];
-  transform_point(q, t, f->p, lp, want_jac ? dlp : NULL);
+  const double s = (f->type != O_FACTOR_PLANE_NORM && f->s != 0.0) ? f->s : 1.0;
+  if (s == 1.0) transform_point(q, t, f->p, lp, want_jac ? dlp : NULL);
+  else {
+    /* lidarFactor.hpp:27-34,73-79: q_last_curr = Identity.slerp(s, q); t_last_curr = s * t; lp = q_last_curr * cp + t_last_curr */
+    double qs[4], dqs[4][4], ts[3] = { s * t[0], s * t[1], s * t[2] }, dl[3][4];
+    lmono_cpu_slerp_identity(s, q, qs, want_jac ? dqs : NULL);
+    transform_point(qs, ts, f->p, lp, want_jac ? dl : NULL);
+    if (want_jac)
+      for (int k = 0; k < 3; ++k)
+        for (int j = 0; j < 4; ++j) { double a = 0.0; for (int m = 0; m < 4; ++m) a += dl[k][m] * dqs[m][j]; dlp[k][j] = a; }
+  }
   if (f->type == O_FACTOR_EDGE) {
     /* lidarFactor.hpp:35-40 */
     double da[3] = { lp[0] - f->a[0], lp[1] - f->a[1], lp[2] - f->a[2] };
@@ -73,7 +110,7 @@ static int eval_block(const o_factor* f, const double q[4], const double t[3], d
         for (int k = 0; k < 3; ++k) Jq[k][j] = (c1[k] + c2[k]) / den;
       }
       for (int j = 0; j < 3; ++j) {
-        double d[3] = { 0, 0, 0 }; d[j] = 1.0;
+        double d[3] = { 0, 0, 0 }; d[j] = s;            /* d lp / d t = s I */
         double c1[3], c2[3]; cross3(d, db, c1); cross3(da, d, c2);
         for (int k = 0; k < 3; ++k) Jt[k][j] = (c1[k] + c2[k]) / den;
       }
@@ -85,7 +122,7 @@ static int eval_block(const o_factor* f, const double q[4], const double t[3], d
     r[0] = (lp[0] - f->a[0]) * n[0] + (lp[1] - f->a[1]) * n[1] + (lp[2] - f->a[2]) * n[2];
     if (want_jac) {
       for (int j = 0; j < 4; ++j) Jq[0][j] = dlp[0][j] * n[0] + dlp[1][j] * n[1] + dlp[2][j] * n[2];
-      for (int j = 0; j < 3; ++j) Jt[0][j] = n[j];
+      for (int j = 0; j < 3; ++j) Jt[0][j] = s * n[j];
     }
     return 1;
   } else {

@@ -72,6 +72,7 @@ typedef struct {
   double p[3];   /* curr_point (sensor frame) */
   double a[3];   /* EDGE: last_point_a ; PLANE: last_point_j ; PLANE_NORM: unit normal */
   double b[3];   /* EDGE: last_point_b ; PLANE: ljm_norm (unit) ; PLANE_NORM: b[0] = negative_OA_dot_norm */
+  double s;      /* EDGE / PLANE: interpolation ratio (lidarFactor.hpp:14,60; 1.0 with DISTORTION 0); 0.0 is read as 1.0 (zero-initialised records) */
 } o_factor;
 
 /* cost = sum 0.5*rho(|r|^2) with HuberLoss(0.1); H = J^T J (6x6, row-major),
@@ -162,6 +163,9 @@ typedef struct {
 } o_odom_report;
 o_odom* lmono_cpu_odom_create(void);
 void    lmono_cpu_odom_destroy(o_odom*);
+/* #define DISTORTION (Aloam/src/laserOdometry.cpp:59): 1 = every point is interpolated to the sweep start with
+ * s = (intensity - int(intensity)) / SCAN_PERIOD (:111-129) and the factors carry that s (:374-381,472-479) */
+void    lmono_cpu_odom_set_distortion(o_odom*, int on);
 int lmono_cpu_odom_step(o_odom*, const o_pt* sharp, int n_sharp, const o_pt* less_sharp, int n_less_sharp,
                         const o_pt* flat, int n_flat, const o_pt* less_flat, int n_less_flat,
                         o_pose* last_curr /*out*/, o_pose* w_curr /*out*/, o_odom_report* rep);

@@ -223,7 +223,7 @@ static int corner_factor(const o_mapper* m, const o_kdtree* tree, const double q
   lmono_cpu_eigh3(cov, w, V);
   if (!(w[2] > 3 * w[1])) return 0;
   double dir[3] = { V[0 * 3 + 2], V[1 * 3 + 2], V[2 * 3 + 2] };
-  f->type = O_FACTOR_EDGE; f->pad = 0;
+  f->type = O_FACTOR_EDGE; f->s = 1.0; f->pad = 0;
   f->p[0] = ori->x; f->p[1] = ori->y; f->p[2] = ori->z;
   for (int k = 0; k < 3; ++k) { f->a[k] = 0.1 * dir[k] + center[k]; f->b[k] = -0.1 * dir[k] + center[k]; }
   return 1;
@@ -251,7 +251,7 @@ static int surf_factor(const o_mapper* m, const o_kdtree* tree, const double q[4
   for (int j = 0; j < 5; ++j) {
     if (fabs(n[0] * A[j * 3 + 0] + n[1] * A[j * 3 + 1] + n[2] * A[j * 3 + 2] + negative_OA_dot_norm) > 0.2) return 0;
   }
-  f->type = O_FACTOR_PLANE_NORM; f->pad = 0;
+  f->type = O_FACTOR_PLANE_NORM; f->s = 1.0; f->pad = 0;
   f->p[0] = ori->x; f->p[1] = ori->y; f->p[2] = ori->z;
   f->a[0] = n[0]; f->a[1] = n[1]; f->a[2] = n[2];
   f->b[0] = negative_OA_dot_norm; f->b[1] = 0; f->b[2] = 0;

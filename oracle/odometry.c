@@ -22,6 +22,7 @@ struct o_odom {
   o_pt* surf_last; int n_surf_last;
   o_kdtree* kd_corner; o_kdtree* kd_surf;
   int use_kdtree;
+  int distortion;                    /* #define DISTORTION :59 */
 };
 
 static void qmul(const double a[4], const double b[4], double o[4]) {
@@ -44,6 +45,7 @@ o_odom* lmono_cpu_odom_create(void) {
   o->use_kdtree = 1;
   return o;
 }
+void lmono_cpu_odom_set_distortion(o_odom* o, int on) { if (o) o->distortion = on ? 1 : 0; }
 void lmono_cpu_odom_destroy(o_odom* o) {
   if (!o) return;
   free(o->corner_last); free(o->surf_last);
@@ -51,14 +53,33 @@ void lmono_cpu_odom_destroy(o_odom* o) {
   free(o);
 }
 
-/* TransformToStart :111-129 with s = 1: Identity.slerp(1, q) is q or -q (same rotation,
- * bit-identical result through Eigen's formula), t_point_last = 1.0 * t */
-static void transform_to_start(const double q[4], const double t[3], const o_pt* pi, o_pt* po) {
+void lmono_cpu_slerp_identity(double t, const double q[4], double qs[4], double dqs[4][4]);
+
+/* interpolation ratio of a point, :114-118 / :375-379: (intensity - int(intensity)) is FLOAT arithmetic (float - int), the
+ * division by SCAN_PERIOD = 0.1 double */
+static double ratio_of(const o_pt* p, int distortion) {
+  if (!distortion) return 1.0;
+  const float frac = p->i - (float)(int)p->i;
+  return (double)frac / 0.1;
+}
+
+/* TransformToStart :111-129.  s = 1 (DISTORTION 0): Identity.slerp(1, q) is q or -q (same rotation, bit-identical result
+ * through Eigen's formula), t_point_last = 1.0 * t.  Otherwise q_point_last = Identity.slerp(s, q_last_curr) (not
+ * renormalised), t_point_last = s * t_last_curr. */
+static void transform_to_start_s(const double q[4], const double t[3], const o_pt* pi, o_pt* po, double s) {
   double p[3] = { pi->x, pi->y, pi->z }, r[3];
-  qrot(q, p, r);
-  po->x = (float)(r[0] + t[0]); po->y = (float)(r[1] + t[1]); po->z = (float)(r[2] + t[2]);
+  if (s == 1.0) {
+    qrot(q, p, r);
+    po->x = (float)(r[0] + t[0]); po->y = (float)(r[1] + t[1]); po->z = (float)(r[2] + t[2]);
+  } else {
+    double qs[4];
+    lmono_cpu_slerp_identity(s, q, qs, NULL);
+    qrot(qs, p, r);
+    po->x = (float)(r[0] + s * t[0]); po->y = (float)(r[1] + s * t[1]); po->z = (float)(r[2] + s * t[2]);
+  }
   po->i = pi->i;
 }
+static void transform_to_start(const double q[4], const double t[3], const o_pt* pi, o_pt* po) { transform_to_start_s(q, t, pi, po, 1.0); }
 
 static inline double sqdis(const o_pt* a, const o_pt* sel) {
   /* :322-327: float products and sums, widened on assignment */
@@ -162,11 +183,12 @@ int lmono_cpu_odom_step(o_odom* o, const o_pt* sharp, int n_sharp, const o_pt* l
       double ta = now_ms();
       int nf = 0, cc = 0, pc = 0;
       for (int i = 0; i < n_sharp; ++i) {
-        o_pt sel; transform_to_start(o->para_q, o->para_t, &sharp[i], &sel);
+        const double s = ratio_of(&sharp[i], o->distortion);
+        o_pt sel; transform_to_start_s(o->para_q, o->para_t, &sharp[i], &sel, s);
         int a, b; corner_corr(o->corner_last, o->n_corner_last, o->kd_corner, &sel, &a, &b);
         if (b >= 0) {                                   /* :363 */
           o_factor* f = &fac[nf++];
-          f->type = O_FACTOR_EDGE; f->pad = 0;
+          f->type = O_FACTOR_EDGE; f->pad = 0; f->s = s;
           f->p[0] = sharp[i].x; f->p[1] = sharp[i].y; f->p[2] = sharp[i].z;
           f->a[0] = o->corner_last[a].x; f->a[1] = o->corner_last[a].y; f->a[2] = o->corner_last[a].z;
           f->b[0] = o->corner_last[b].x; f->b[1] = o->corner_last[b].y; f->b[2] = o->corner_last[b].z;
@@ -174,11 +196,12 @@ int lmono_cpu_odom_step(o_odom* o, const o_pt* sharp, int n_sharp, const o_pt* l
         }
       }
       for (int i = 0; i < n_flat; ++i) {
-        o_pt sel; transform_to_start(o->para_q, o->para_t, &flat[i], &sel);
+        const double s = ratio_of(&flat[i], o->distortion);
+        o_pt sel; transform_to_start_s(o->para_q, o->para_t, &flat[i], &sel, s);
         int a, b, c; plane_corr(o->surf_last, o->n_surf_last, o->kd_surf, &sel, &a, &b, &c);
         if (b >= 0 && c >= 0) {                         /* :457 */
           o_factor* f = &fac[nf++];
-          f->type = O_FACTOR_PLANE; f->pad = 0;
+          f->type = O_FACTOR_PLANE; f->pad = 0; f->s = s;
           f->p[0] = flat[i].x; f->p[1] = flat[i].y; f->p[2] = flat[i].z;
           const o_pt *pj = &o->surf_last[a], *pl = &o->surf_last[b], *pm = &o->surf_last[c];
           double j[3] = { pj->x, pj->y, pj->z }, l[3] = { pl->x, pl->y, pl->z }, m[3] = { pm->x, pm->y, pm->z };

@@ -48,7 +48,7 @@ for line in buf.value.decode().splitlines():
     src = open(os.path.join(ROOT, "lmono_b200", "csrc", f)).read().splitlines()
     name = "?"
     for k in range(int(l) - 1, max(int(l) - 8, -1), -1):
-        m = re.search(r"(k_\w+)\s*(?:<<<|,)", src[k]) if k < len(src) else None
+        m = re.search(r"(k_\w+)(?:<\w+>)?\s*(?:<<<|,)", src[k]) if k < len(src) else None
         if m:
             name = m.group(1); break
     rows.append((name, site, int(n), float(ms)))

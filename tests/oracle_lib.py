@@ -29,10 +29,10 @@ class Pose(C.Structure):
 
 class Factor(C.Structure):
     _fields_ = [("type", C.c_int32), ("pad", C.c_int32), ("p", C.c_double * 3),
-                ("a", C.c_double * 3), ("b", C.c_double * 3)]
+                ("a", C.c_double * 3), ("b", C.c_double * 3), ("s", C.c_double)]
 
 
-FACTOR_DTYPE = np.dtype([("type", "<i4"), ("pad", "<i4"), ("p", "<f8", 3), ("a", "<f8", 3), ("b", "<f8", 3)])
+FACTOR_DTYPE = np.dtype([("type", "<i4"), ("pad", "<i4"), ("p", "<f8", 3), ("a", "<f8", 3), ("b", "<f8", 3), ("s", "<f8")])
 
 
 class SolveSummary(C.Structure):
@@ -288,6 +288,10 @@ class Odometry:
             self.close()
         except Exception:
             pass
+
+    def set_distortion(self, on=True):
+        """#define DISTORTION 1 of Aloam/src/laserOdometry.cpp:59"""
+        self.L.lmono_cpu_odom_set_distortion(self.h, 1 if on else 0)
 
     def step(self, sharp, less_sharp, flat, less_flat):
         a, b, c, d = (_f32(x).reshape(-1, 4) for x in (sharp, less_sharp, flat, less_flat))

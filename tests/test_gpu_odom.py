@@ -73,3 +73,33 @@ def test_odometry_first_frame_and_reset(gpu_ctx_factory, oracle):
     e = np.zeros((0, 4), np.float32)
     _, _, rep = ctx.odom_step(e, e, e, e)
     assert rep.corner_corr[0] == 0 and rep.plane_corr[0] == 0
+
+
+def test_odometry_with_motion_distortion(gpu_ctx_factory, oracle):
+    """#define DISTORTION 1 (laserOdometry.cpp:59, compile-time off in the reference): every point is interpolated to the
+    sweep start with s = (intensity - int(intensity)) / SCAN_PERIOD through Eigen's slerp (:111-129) and the factors carry
+    that s (:374-381, 472-479; lidarFactor.hpp:27-34, 73-79).  The oracle differentiates slerp analytically, the device
+    evaluates the same expressions on dual numbers: counts, LM trace and poses must agree, and differ from the s = 1 run."""
+    feats = _features(oracle, 64, 5.0, 6, seed=3)
+    ctx = gpu_ctx_factory(distortion=1)
+    plain = gpu_ctx_factory()
+    od = oracle.Odometry()
+    od.set_distortion(True)
+    differs = 0.0
+    for k, (r, q, t) in enumerate(feats):
+        assert np.any(r["sharp"][:, 3] != np.floor(r["sharp"][:, 3]))          # relTime fractions are there
+        (glq, glt), (gwq, gwt), grep = ctx.odom_step(r["sharp"], r["less_sharp"], r["flat"], r["less_flat"])
+        (rlq, rlt), (rwq, rwt), rrep = od.step(r["sharp"], r["less_sharp"], r["flat"], r["less_flat"])
+        (plq, plt), _, _ = plain.odom_step(r["sharp"], r["less_sharp"], r["flat"], r["less_flat"])
+        assert grep.inited == rrep.inited
+        assert list(grep.corner_corr) == list(rrep.corner_corr), (k, list(grep.corner_corr), list(rrep.corner_corr))
+        assert list(grep.plane_corr) == list(rrep.plane_corr), (k, list(grep.plane_corr), list(rrep.plane_corr))
+        for it in range(2 if rrep.inited else 0):
+            assert grep.solve[it].iterations == rrep.solve[it].iterations, (k, it)
+            assert grep.solve[it].termination == rrep.solve[it].termination, (k, it)
+            assert abs(grep.solve[it].final_cost - rrep.solve[it].final_cost) <= 1e-7 * max(1.0, rrep.solve[it].final_cost)
+        assert np.linalg.norm(glt - rlt) <= 1e-4 and rot_angle(glq, rlq) <= 1e-4, (k, glt, rlt)
+        assert np.linalg.norm(gwt - rwt) <= 1e-4 and rot_angle(gwq, rwq) <= 1e-4
+        differs = max(differs, float(np.linalg.norm(glt - plt)))
+    assert differs > 1e-3, differs          # the interpolation changes the estimate: the path is really taken
+    print(f"DISTORTION 1: last t_last_curr {glt} (s = 1 run: {plt}), |dt| vs oracle {np.linalg.norm(glt - rlt):.2e}")
