@@ -428,7 +428,7 @@ def run_ours(args):
     nfac = rep.corner_num[1] + rep.surf_num[1]
     evals = sum(s_.iterations + 1 for s_ in rep.solve)
     ncu = {}
-    ncu_file = "ncu_r01_j_full_metrics.json"
+    ncu_file = "ncu_r02_full_metrics.json"
     try:
         for l in json.load(open(os.path.join(ROOT, "profiles", ncu_file)))["launches"]:
             ncu.setdefault(l["kernel"], []).append(l)
@@ -461,7 +461,7 @@ def run_ours(args):
         "bound": "hbm", "kernel": "k_assoc_knn1 (exact 5-NN of every feature against the cube map, throughput form = the one the batched step runs; one launch per outer iteration)",
         "achieved": knn.get("achieved"), "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
         "frac": knn.get("frac"), "traffic": knn.get("traffic"),
-        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture committed as profiles/" + ncu_file + " (cold caches per ncu replay)",
+        "traffic_source": "STATIC: dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture committed as profiles/" + ncu_file + " (cold caches per ncu replay; not re-measured in this run)",
         "algorithmic_bytes_per_launch": knn.get("algorithmic_bytes_per_launch"), "avg_launch_ms": knn.get("avg_launch_ms"),
         "timing": "one sequence alone on the GPU, un-graphed step, CUDA event after every launch",
         "queries_per_launch": int(nq), "knn_queries_per_s": nq / (knn["avg_launch_ms"] * 1e-3) if knn.get("avg_launch_ms") else None,

@@ -38,7 +38,7 @@ def site_name(site):
         SRC[f] = open(os.path.join(ROOT, "lmono_b200", "csrc", f)).read().splitlines()
     src = SRC[f]
     for k in range(int(l) - 1, max(int(l) - 8, -1), -1):
-        m = re.search(r"(k_\w+)\s*(?:<<<|,)", src[k]) if k < len(src) else None
+        m = re.search(r"(k_\w+)(?:<\w+>)?\s*(?:<<<|,)", src[k]) if k < len(src) else None
         if m:
             return "k_assoc_knn" if m.group(1) == "k_assoc_knn1" else m.group(1)     # latency / throughput form share a row
     return site
