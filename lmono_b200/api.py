@@ -20,7 +20,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-_SO = os.path.join(_CSRC, "liblmono_b200.so")
+_SO = os.environ.get("LMONO_SO") or os.path.join(_CSRC, "liblmono_b200.so")      # LMONO_SO: an experiment build of the same sources
 
 
 class LmonoError(RuntimeError):

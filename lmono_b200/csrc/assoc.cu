@@ -555,6 +555,7 @@ __device__ __forceinline__ void d_knn5_thread(const float4* __restrict__ cellpts
 
 __global__ void __launch_bounds__(KNN1_THREADS) k_assoc_knn1(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, const int32_t* __restrict__ slot_valid_rank,
                                                              const float4* __restrict__ stack0, const float4* __restrict__ stack1, int32_t* __restrict__ nnref) {
+  lm_pdl_enter();
   __shared__ unsigned long long s_key[KNN1_SLOTS * KNN1_THREADS];
   __shared__ int s_ref[KNN1_SLOTS * KNN1_THREADS];
   if (!st->optimize) return;
@@ -624,6 +625,7 @@ __device__ __forceinline__ void d_assoc_knn(LmMapState* __restrict__ st, const L
 template <int GROUP>
 __global__ void __launch_bounds__(256, 4) k_assoc_knn(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, const int32_t* __restrict__ slot_valid_rank,
                                                    const float4* __restrict__ stack0, const float4* __restrict__ stack1, int32_t* __restrict__ nnref) {
+  lm_pdl_enter();
   d_assoc_knn<GROUP>(st, M0, M1, slot_valid_rank, stack0, stack1, nnref);
 }
 
@@ -631,6 +633,7 @@ __global__ void __launch_bounds__(128) k_assoc_fit(const LmMapState* __restrict_
                                                    const float4* __restrict__ stack0, const float4* __restrict__ stack1,
                                                    const int32_t* __restrict__ nnref,
                                                    LmFactor* __restrict__ fac0, LmFactor* __restrict__ fac1) {
+  lm_pdl_enter();
   if (!st->optimize) return;
   const int n0 = st->stack_n[0], n1 = st->stack_n[1];
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -660,16 +663,16 @@ int lm_map_associate(lmono_ctx* ctx, int n_max_corner, int n_max_surf) {
   const int group = group_env >= 0 ? group_env : (ctx->batch_n >= LM_THROUGHPUT_BATCH ? 0 : GROUP_DEFAULT);
 #define KNN_ARGS ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_slot_valid_rank, ctx->d_stack[0], ctx->d_stack[1], ctx->d_nnref
   if (group == 0) {
-    k_assoc_knn1<<<lm_div_up(nq, KNN1_THREADS), KNN1_THREADS, 0, ctx->stream>>>(KNN_ARGS);
+    LM_LAUNCH_PDL(k_assoc_knn1, lm_div_up(nq, KNN1_THREADS), KNN1_THREADS, 0, KNN_ARGS);
     LM_LAUNCH_CHECK();
   } else {
-  if (group == 1) k_assoc_knn<1><<<lm_div_up(nq * 1, 256), 256, 0, ctx->stream>>>(KNN_ARGS);
-  else if (group == 2) k_assoc_knn<2><<<lm_div_up(nq * 2, 256), 256, 0, ctx->stream>>>(KNN_ARGS);
-  else if (group == 4) k_assoc_knn<4><<<lm_div_up(nq * 4, 256), 256, 0, ctx->stream>>>(KNN_ARGS);
-  else k_assoc_knn<8><<<lm_div_up(nq * 8, 256), 256, 0, ctx->stream>>>(KNN_ARGS);   // k_assoc_knn<<<
+  if (group == 1) LM_LAUNCH_PDL(k_assoc_knn<1>, lm_div_up(nq * 1, 256), 256, 0, KNN_ARGS);
+  else if (group == 2) LM_LAUNCH_PDL(k_assoc_knn<2>, lm_div_up(nq * 2, 256), 256, 0, KNN_ARGS);
+  else if (group == 4) LM_LAUNCH_PDL(k_assoc_knn<4>, lm_div_up(nq * 4, 256), 256, 0, KNN_ARGS);
+  else LM_LAUNCH_PDL(k_assoc_knn<8>, lm_div_up(nq * 8, 256), 256, 0, KNN_ARGS);
   LM_LAUNCH_CHECK();
   }
-  k_assoc_fit<<<lm_div_up(nq, 128), 128, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_stack[0], ctx->d_stack[1],
+  LM_LAUNCH_PDL(k_assoc_fit, lm_div_up(nq, 128), 128, 0, ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_stack[0], ctx->d_stack[1],
                                                           ctx->d_nnref, ctx->d_fac[0], ctx->d_fac[1]);
   LM_LAUNCH_CHECK();
   return LMONO_OK;

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <math.h>
 #include "../../include/lmono.h"
 
@@ -278,11 +279,25 @@ static inline void lm_prof_end(lmono_ctx* ctx) {
   return LMONO_E_CUDA; } } while (0)
 constexpr int LM_KMARK_MAX = 8192;
 #ifdef __CUDACC__
-static __global__ void k_tl_stamp(unsigned long long* p) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); *p = t; }
+// launched like the step kernels (programmatic dependent launch, see lm_pdl_enter below): the stamp is taken once the
+// preceding kernel has completed, and the following kernel may already be resident
+static __global__ void k_tl_stamp(unsigned long long* p) {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); *p = t;
+}
+static inline bool lm_pdl_on();
 static inline void lm_tl(lmono_ctx* ctx, const char* file, int line) {
   if (!ctx->tl_on || !ctx->d_tl || ctx->tl_n >= LM_TL_MAX) return;
   ctx->tl_file[ctx->tl_n] = file; ctx->tl_line[ctx->tl_n] = line;
-  k_tl_stamp<<<1, 1, 0, ctx->stream>>>(ctx->d_tl + ctx->tl_n);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1); cfg.blockDim = dim3(1); cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = lm_pdl_on() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, k_tl_stamp, ctx->d_tl + ctx->tl_n);
+  }
   ctx->tl_n++;
 }
 #else
@@ -298,6 +313,64 @@ static inline void lm_kmark(lmono_ctx* ctx, const char* file, int line) {
   fprintf(stderr, "[lmono_b200] launch error %s at %s:%d\n", cudaGetErrorName(_e), __FILE__, __LINE__); return LMONO_E_CUDA; } } while (0)
 
 static inline int lm_div_up(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------- programmatic dependent launch
+// A registration is a chain of ~20 small dependent kernels.  Kernels on the step path are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and start with griddepcontrol.wait (lm_pdl_enter): the successor
+// grid may be scheduled as soon as every CTA of its predecessor has exited, instead of after the predecessor's
+// completion has been processed, and the wait orders it behind the predecessor's memory flush.  Completion is
+// transitive (a grid cannot complete before its own wait returns), hence every kernel launched through LM_LAUNCH_PDL
+// MUST call lm_pdl_enter() first thing in every thread (tests/test_abi.py checks the sources).  The instruction is a
+// no-op for a kernel launched without the attribute.  LMONO_PDL=0 launches everything with plain stream order.
+//
+// Measured on B200 (profiles/pdl_variants_r02.log, C-3 workload, one sequence alone / 8 sequences per GPU):
+//   plain launches                                  243.4 us / 403 us per step
+//   LM_PDL_MODE 2  wait only (the default)          240.5 us / 392 us
+//   LM_PDL_MODE 1  wait, then launch_dependents     246.0 us / 508 us   the early-resident successor CTAs hold registers and
+//                                                                        shared memory that the other sequences' running kernels need
+//   LM_PDL_MODE 0  launch_dependents, then wait     WRONG RESULTS: a successor that became resident before its predecessor
+//                                                   had written a buffer later read that buffer through stale L1 / read-only
+//                                                   (LDG.NC, const __restrict__) lines -- griddepcontrol.wait orders the
+//                                                   grids but does not invalidate them;
+//   LM_PDL_MODE 3  as 0 + fence.acq_rel.gpu         correct, 259.9 us / 541 us
+// i.e. the chain is bound by what happens inside its kernels (dependent L2 / HBM round trips after the L2 flush), not by
+// the launch gaps between them; early release of the successor only takes SM resources away from the other sequences.
+static inline bool lm_pdl_on() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LMONO_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+#ifdef __CUDACC__
+#ifndef LM_PDL_MODE
+#define LM_PDL_MODE 2
+#endif
+__device__ __forceinline__ void lm_pdl_enter() {
+#if LM_PDL_MODE == 0
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#elif LM_PDL_MODE == 1
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;");
+#elif LM_PDL_MODE == 2
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#elif LM_PDL_MODE == 3
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
+}
+template <typename... P, typename... A>
+static inline void lm_launch_pdl(cudaStream_t stream, void (*kern)(P...), dim3 grid, dim3 block, size_t smem, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = lm_pdl_on() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);     // a failure is picked up by LM_LAUNCH_CHECK (cudaGetLastError)
+}
+#define LM_LAUNCH_PDL(kern, grid, block, smem, ...) lm_launch_pdl(ctx->stream, kern, dim3(grid), dim3(block), (size_t)(smem), __VA_ARGS__)
+#endif
 
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__

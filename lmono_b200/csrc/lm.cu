@@ -560,6 +560,7 @@ template <bool RATIO>
 __global__ void __launch_bounds__(LMC_THREADS, 1)
 k_lm_solve_cluster(LmLmState* __restrict__ lm_g, LmProblem P, int max_iter, int write_back, unsigned long long* __restrict__ stamps,
                    const LmShardPeers* __restrict__ peers /*NULL: map not sharded over GPUs*/, uint32_t* __restrict__ fault) {
+  lm_pdl_enter();
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank();
   const int csize = (int)cluster.num_blocks();
@@ -752,9 +753,10 @@ int lm_solve_problem(lmono_ctx* ctx, const LmProblem& P, int n_max, int max_iter
     if (cs < 0) return LMONO_E_CUDA;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(cs); cfg.blockDim = dim3(LMC_THREADS); cfg.dynamicSmemBytes = LMC_SMEM; cfg.stream = ctx->stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = lm_pdl_on() ? 2 : 1;
     const LmShardPeers* peers = shard_exchange ? ctx->d_shard_peers : nullptr;
     if (P.frac0) LM_CUDA(cudaLaunchKernelEx(&cfg, k_lm_solve_cluster<true>, ctx->d_lm, P, max_iter, write_back, ctx->d_stamps, peers, &ctx->d_state->fault));
     else LM_CUDA(cudaLaunchKernelEx(&cfg, k_lm_solve_cluster<false>, ctx->d_lm, P, max_iter, write_back, ctx->d_stamps, peers, &ctx->d_state->fault));

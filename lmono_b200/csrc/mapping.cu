@@ -13,12 +13,14 @@ int lm_map_import_device(lmono_ctx* ctx, int which, const float4* d_pts, int n,
 
 // transformUpdate (:148-152) + frame counter
 __global__ void k_transform_update(LmMapState* st) {
+  lm_pdl_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   d_transform_update(st);
 }
 
 // :838-842 full-resolution sweep to the world frame
 __global__ void __launch_bounds__(256) k_transform_cloud(const LmMapState* __restrict__ st, const float4* __restrict__ in, int n, float4* __restrict__ out) {
+  lm_pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   out[i] = d_associate(st->q_w_curr, st->t_w_curr, in[i]);
@@ -71,6 +73,7 @@ __global__ void k_batch_args(BatchStepArgs b) {
 // mirror the host reads after the step's event -- a plain store over PCIe instead of a copy-engine node, so that two
 // steps of a ctx can be in flight with one graph (the slot is a per-step argument)
 __global__ void __launch_bounds__(128) k_publish_state(const LmMapState* __restrict__ st, LmMapState* h0, LmMapState* h1) {
+  lm_pdl_enter();
   const int4* __restrict__ src = reinterpret_cast<const int4*>(st);
   int4* dst = reinterpret_cast<int4*>(st->result_slot ? h1 : h0);
   for (int i = threadIdx.x; i < (int)(sizeof(LmMapState) / 16); i += blockDim.x) dst[i] = src[i];
@@ -144,7 +147,7 @@ static int enqueue_body(lmono_ctx* ctx, int nc, int ns) {
   if (nc + ns > 0) {
     if ((rc = lm_map_insert_and_refilter(ctx, nc, ns, /*transform_update=*/true))) return rc;   // :734, :737-801
   } else {
-    k_transform_update<<<1, 32, 0, ctx->stream>>>(ctx->d_state);            // :734
+    LM_LAUNCH_PDL(k_transform_update, 1, 32, 0, ctx->d_state);            // :734
     LM_LAUNCH_CHECK();
     if ((rc = lm_map_insert_and_refilter(ctx, nc, ns, false))) return rc;
   }
@@ -327,7 +330,7 @@ extern "C" int lmono_shard_lm_control(lmono_ctx* ctx, int32_t solve_index) {
 }
 extern "C" int lmono_shard_end(lmono_ctx* ctx) {
   if (!ctx || !ctx->d_shard_ws) return LMONO_E_ARG;
-  k_transform_update<<<1, 32, 0, ctx->stream>>>(ctx->d_state);
+  LM_LAUNCH_PDL(k_transform_update, 1, 32, 0, ctx->d_state);
   LM_LAUNCH_CHECK();
   int rc = lm_map_insert_and_refilter(ctx, ctx->shard_nc, ctx->shard_ns);
   if (rc) return rc;
@@ -605,7 +608,7 @@ extern "C" int lmono_map_step(lmono_ctx* ctx, lmono_cloud_view corner_last, lmon
   if (want_full) {
     float4* d_full_in = (float4*)ctx->d_raw[0];   // raw staging is free again once the step is enqueued
     if ((rc = lm_upload_cloud(ctx, full_res, ctx->d_raw[2], d_full_in, nullptr))) return rc;
-    k_transform_cloud<<<lm_div_up(full_res.n, 256), 256, 0, ctx->stream>>>(ctx->d_state, d_full_in, full_res.n, ctx->d_full);
+    LM_LAUNCH_PDL(k_transform_cloud, lm_div_up(full_res.n, 256), 256, 0, ctx->d_state, d_full_in, full_res.n, ctx->d_full);
     LM_LAUNCH_CHECK();
   }
   rc = collect(ctx, w_curr, wmap_wodom, report);
@@ -643,7 +646,7 @@ void lm_batch_free(lmono_ctx* ctx) {
 }
 
 static int publish_state(lmono_ctx* ctx) {
-  k_publish_state<<<1, 128, 0, ctx->stream>>>(ctx->d_state, ctx->h_ring[0], ctx->h_ring[1]);
+  LM_LAUNCH_PDL(k_publish_state, 1, 128, 0, ctx->d_state, ctx->h_ring[0], ctx->h_ring[1]);
   LM_LAUNCH_CHECK();
   return LMONO_OK;
 }

@@ -92,6 +92,7 @@ __device__ __forceinline__ void d_free_slot(const LmMapType& M, int ps) {
 __global__ void __launch_bounds__(256) k_begin_step(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1,
                                                     int32_t* __restrict__ slot_valid_rank, int32_t* __restrict__ plan, PoseArg odom,
                                                     int use_override, double ox, double oy, double oz) {
+  lm_pdl_enter();
   __shared__ unsigned clear_mask[3];
   __shared__ int s_dirty_n;
   if (threadIdx.x == 0) s_dirty_n = 0;
@@ -223,7 +224,7 @@ int lm_map_begin_step(lmono_ctx* ctx, const lmono_pose* wodom_curr, const double
   PoseArg pa;
   if (wodom_curr) { for (int k = 0; k < 4; ++k) pa.q[k] = wodom_curr->q[k]; for (int k = 0; k < 3; ++k) pa.t[k] = wodom_curr->t[k]; }
   else { pa.q[0] = pa.q[1] = pa.q[2] = 0; pa.q[3] = 1; pa.t[0] = pa.t[1] = pa.t[2] = 0; }
-  k_begin_step<<<1, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_slot_valid_rank, ctx->d_rf_plan, pa,
+  LM_LAUNCH_PDL(k_begin_step, 1, 256, 0, ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_slot_valid_rank, ctx->d_rf_plan, pa,
                                            t_override ? 1 : (wodom_curr ? 0 : 2), t_override ? t_override[0] : 0.0,
                                            t_override ? t_override[1] : 0.0, t_override ? t_override[2] : 0.0);
   LM_LAUNCH_CHECK();
@@ -270,6 +271,7 @@ __device__ void d_build_cell_index(const LmMapType& M, int sid, const float4* __
 
 constexpr int IDX_GRID = 32;
 __global__ void __launch_bounds__(1024, 1) k_index_build(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, const int32_t* __restrict__ plan) {
+  lm_pdl_enter();
   extern __shared__ unsigned char smem_raw[];
   uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem_raw);
   int* ws = reinterpret_cast<int*>(s_cnt + LM_NCELL);
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(1024, 1) k_index_build(LmMapState* __restrict_
 static const int kIndexSmem = LM_NCELL * 4 + 64 * 4;
 
 int lm_map_index_build(lmono_ctx* ctx) {
-  k_index_build<<<IDX_GRID, 1024, kIndexSmem, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan);
+  LM_LAUNCH_PDL(k_index_build, IDX_GRID, 1024, kIndexSmem, ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan);
   LM_LAUNCH_CHECK();
   return LMONO_OK;
 }
@@ -308,6 +310,7 @@ __global__ void __launch_bounds__(256) k_insert_prepare(LmMapState* __restrict__
                                                         float4* __restrict__ world1, unsigned long long* __restrict__ comp,
                                                         int32_t* __restrict__ n_ins, float leaf0, float inv_leaf0, float leaf1, float inv_leaf1,
                                                         int transform_update, const int32_t* __restrict__ slot_valid_rank) {
+  lm_pdl_enter();
   const int n0 = st->stack_n[0], n1 = st->stack_n[1];
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e == 0) *n_ins = n0 + n1;
@@ -338,6 +341,7 @@ __global__ void __launch_bounds__(256) k_insert_heads(LmMapState* __restrict__ s
                                                       const float4* __restrict__ world0, const float4* __restrict__ world1,
                                                       int32_t* __restrict__ slot_first, int32_t* __restrict__ slot_base,
                                                       int32_t* __restrict__ slot_len, const int32_t* __restrict__ slot_valid_rank) {
+  lm_pdl_enter();
   const int n = *n_ins;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
@@ -456,6 +460,7 @@ __device__ __forceinline__ void d_rf_plan(LmMapState* __restrict__ st, const LmM
 
 __global__ void __launch_bounds__(256) k_rf_plan(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, int32_t* __restrict__ plan,
                                                  RfMeta* __restrict__ meta_all, int32_t* __restrict__ work_n) {
+  lm_pdl_enter();
   __shared__ int ws[33];
   d_rf_plan(st, M0, M1, plan, meta_all, work_n, ws);
 }
@@ -467,6 +472,7 @@ __global__ void __launch_bounds__(256) k_insert_write_plan(LmMapState* __restric
                                                            const float4* __restrict__ world1, const int32_t* __restrict__ slot_first,
                                                            const int32_t* __restrict__ slot_base, const int32_t* __restrict__ slot_len,
                                                            int32_t* __restrict__ plan, RfMeta* __restrict__ meta_all, int32_t* __restrict__ work_n) {
+  lm_pdl_enter();
   __shared__ int ws[33];
   if (blockIdx.x == gridDim.x - 1) { d_rf_plan(st, M0, M1, plan, meta_all, work_n, ws); return; }
   d_insert_write(M0, M1, sorted, n_ins, world0, world1, slot_first, slot_base, slot_len);
@@ -482,6 +488,7 @@ static_assert(LM_RF_CHUNK % 256 == 0, "k_rf_merge / k_rf_scatter: whole elements
 __global__ void __launch_bounds__(RF_TS_THREADS) k_rf_tailscan(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, const int32_t* __restrict__ plan,
                                                                int32_t* __restrict__ nvx_all, int32_t* __restrict__ tlb_all, RfMeta* __restrict__ meta_all,
                                                                int nvx_stride, int32_t* __restrict__ work_n, int32_t* __restrict__ work) {
+  lm_pdl_enter();
   __shared__ int ws[33];
   __shared__ int s_wbase;
   const int na = plan[LM_PLAN_ACTIVE_N];
@@ -541,6 +548,7 @@ constexpr int RF_STAGE = 2048;        // tail keys of a cube staged in shared me
 __global__ void __launch_bounds__(256) k_rf_merge(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1,
                                                   const int32_t* __restrict__ nvx_all, const int32_t* __restrict__ tlb_all, RfMeta* __restrict__ meta_all, int nvx_stride,
                                                   const int32_t* __restrict__ work_n, const int32_t* __restrict__ work) {
+  lm_pdl_enter();
  __shared__ uint32_t s_tkey[RF_STAGE];
  const int nwork = *work_n;
  for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
@@ -647,6 +655,7 @@ __global__ void __launch_bounds__(256) k_rf_merge(LmMapState* __restrict__ st, L
 
 constexpr int RF_SCAN_THREADS = 512;
 __global__ void __launch_bounds__(RF_SCAN_THREADS) k_rf_scan(LmMapType M0, LmMapType M1, const int32_t* __restrict__ plan, RfMeta* __restrict__ meta_all) {
+  lm_pdl_enter();
   constexpr int NW = RF_SCAN_THREADS / 32;
   __shared__ int wtot[NW], wbase[NW];
   const int na = plan[LM_PLAN_ACTIVE_N];
@@ -708,6 +717,7 @@ __global__ void __launch_bounds__(RF_SCAN_THREADS) k_rf_scan(LmMapType M0, LmMap
 
 __global__ void __launch_bounds__(256) k_rf_scatter(LmMapType M0, LmMapType M1, const RfMeta* __restrict__ meta_all,
                                                     const int32_t* __restrict__ work_n, const int32_t* __restrict__ work) {
+  lm_pdl_enter();
  const int nwork = *work_n;
  for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
   const int we = work[w];
@@ -745,6 +755,7 @@ constexpr int RF_WHOLE_GRID = 8;
 constexpr int RF_BIG_TILE = 65536;          // slabs above LM_TAIL_TILE points sort in a per-CTA global-memory scratch (slow, rare)
 __global__ void __launch_bounds__(1024, 1) k_refilter_whole(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, const int32_t* __restrict__ plan,
                                                             unsigned long long* __restrict__ big_s, int32_t* __restrict__ big_nv) {
+  lm_pdl_enter();
   extern __shared__ unsigned char smem_raw[];
   unsigned long long* S_sm = reinterpret_cast<unsigned long long*>(smem_raw);           // [LM_TAIL_TILE]
   int* NV_sm = reinterpret_cast<int*>(smem_raw + (size_t)LM_TAIL_TILE * 8);             // [LM_TAIL_TILE]
@@ -829,16 +840,16 @@ int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf,
     int32_t* n_ins = ctx->d_tmp_i32;                 // [0]
     int32_t* slot_len = ctx->d_tmp_i32 + 16;         // [2*LM_NSLOT]
     const int blocks = lm_div_up(n_max, 256);
-    k_insert_prepare<<<blocks, 256, 0, ctx->stream>>>(ctx->d_state, ctx->d_stack[0], ctx->d_stack[1], ctx->d_world[0],
+    LM_LAUNCH_PDL(k_insert_prepare, blocks, 256, 0, ctx->d_state, ctx->d_stack[0], ctx->d_stack[1], ctx->d_world[0],
                                                       ctx->d_world[1], ctx->d_sort_a, n_ins, ctx->map[0].leaf, ctx->map[0].inv_leaf,
                                                       ctx->map[1].leaf, ctx->map[1].inv_leaf, transform_update ? 1 : 0, ctx->d_slot_valid_rank);
     LM_LAUNCH_CHECK();
     int rc = lm_sort_u64(ctx, ctx->d_sort_a, ctx->d_sort_b, ctx->d_sort_c, n_ins, n_max);
     if (rc) return rc;
-    k_insert_heads<<<blocks, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_sort_c, n_ins,
+    LM_LAUNCH_PDL(k_insert_heads, blocks, 256, 0, ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_sort_c, n_ins,
                                                     ctx->d_world[0], ctx->d_world[1], ctx->d_slot_first, ctx->d_slot_base, slot_len, ctx->d_slot_valid_rank);
     LM_LAUNCH_CHECK();
-    k_insert_write_plan<<<blocks + 1, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_sort_c, n_ins, ctx->d_world[0],
+    LM_LAUNCH_PDL(k_insert_write_plan, blocks + 1, 256, 0, ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_sort_c, n_ins, ctx->d_world[0],
                                                              ctx->d_world[1], ctx->d_slot_first, ctx->d_slot_base, slot_len,
                                                              ctx->d_rf_plan, (RfMeta*)ctx->d_rf_meta, ctx->d_rf_work);
     LM_LAUNCH_CHECK();
@@ -849,7 +860,7 @@ int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf,
   RfMeta* meta = (RfMeta*)ctx->d_rf_meta;
   int32_t* work_n = ctx->d_rf_work; int32_t* work = ctx->d_rf_work + 4;
   if (n_max <= 0) {
-    k_rf_plan<<<1, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan, meta, work_n);
+    LM_LAUNCH_PDL(k_rf_plan, 1, 256, 0, ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan, meta, work_n);
     LM_LAUNCH_CHECK();
   }
   // flagged slabs (rare) are re-voxelised as a whole beside the tail merge of the others: disjoint slabs, so inside a
@@ -863,16 +874,16 @@ int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf,
     LM_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_side0, 0));
     ctx->stream = ctx->side_stream;
   }
-  k_refilter_whole<<<RF_WHOLE_GRID, 1024, kRefilterSmem, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan, ctx->d_rf_big_s, ctx->d_rf_big_nv);
+  LM_LAUNCH_PDL(k_refilter_whole, RF_WHOLE_GRID, 1024, kRefilterSmem, ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan, ctx->d_rf_big_s, ctx->d_rf_big_nv);
   if (fork) { ctx->stream = main_stream; LM_CUDA(cudaEventRecord(ctx->ev_side1, ctx->side_stream)); }
   LM_LAUNCH_CHECK();
-  k_rf_tailscan<<<RF_ACT_GRID, RF_TS_THREADS, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan, ctx->d_rf_nvx, ctx->d_rf_tlb, meta, cap_max, work_n, work);
+  LM_LAUNCH_PDL(k_rf_tailscan, RF_ACT_GRID, RF_TS_THREADS, 0, ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan, ctx->d_rf_nvx, ctx->d_rf_tlb, meta, cap_max, work_n, work);
   LM_LAUNCH_CHECK();
-  k_rf_merge<<<RF_GRID, 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_nvx, ctx->d_rf_tlb, meta, cap_max, work_n, work);
+  LM_LAUNCH_PDL(k_rf_merge, RF_GRID, 256, 0, ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_nvx, ctx->d_rf_tlb, meta, cap_max, work_n, work);
   LM_LAUNCH_CHECK();
-  k_rf_scan<<<RF_ACT_GRID, RF_SCAN_THREADS, 0, ctx->stream>>>(ctx->map[0], ctx->map[1], ctx->d_rf_plan, meta);
+  LM_LAUNCH_PDL(k_rf_scan, RF_ACT_GRID, RF_SCAN_THREADS, 0, ctx->map[0], ctx->map[1], ctx->d_rf_plan, meta);
   LM_LAUNCH_CHECK();
-  k_rf_scatter<<<RF_GRID, 256, 0, ctx->stream>>>(ctx->map[0], ctx->map[1], meta, work_n, work);
+  LM_LAUNCH_PDL(k_rf_scatter, RF_GRID, 256, 0, ctx->map[0], ctx->map[1], meta, work_n, work);
   LM_LAUNCH_CHECK();
   if (fork) LM_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_side1, 0));
   lm_prof_end(ctx);

@@ -45,6 +45,7 @@ constexpr int NN_QB = 64, NN_SUB = 4, NN_TILE = 256, NN_CHUNK = 1024;     // 102
 // counts: NULL = the host knows the cloud sizes (arguments); else device counts {n_kept, sharp, less_sharp, flat, less_flat}
 // as scanRegistration leaves them (fused sweep without a host round trip between the stages)
 __global__ void k_odom_begin(OdomDev* o, int n_sharp, int n_ls, int n_flat, int n_lf, const int32_t* __restrict__ counts, int cap, int32_t* __restrict__ ringtab) {
+  lm_pdl_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   ringtab[66] = 1; ringtab[RT_STRIDE + 66] = 1;          // "sorted by ring" until k_odom_ring_table finds a descent
   for (int r = 0; r < 66; ++r) { ringtab[r] = o->n_corner_last; ringtab[RT_STRIDE + r] = o->n_surf_last; }
@@ -59,6 +60,7 @@ __global__ void k_odom_begin(OdomDev* o, int n_sharp, int n_ls, int n_flat, int 
 }
 
 __global__ void __launch_bounds__(256) k_odom_best_init(unsigned long long* b0, int n0, unsigned long long* b1, int n1) {
+  lm_pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n0) b0[i] = ~0ULL;
   if (i < n1) b1[i] = ~0ULL;
@@ -89,6 +91,7 @@ __global__ void __launch_bounds__(NN_QB * NN_SUB) k_odom_nn1(const OdomDev* __re
                                                              const float4* __restrict__ flat, const float4* __restrict__ corner_last,
                                                              const float4* __restrict__ surf_last, unsigned long long* __restrict__ best0,
                                                              unsigned long long* __restrict__ best1) {
+  lm_pdl_enter();
   __shared__ float4 tile[NN_TILE];
   if (!o->do_solve) return;
   const int which = blockIdx.z;
@@ -152,6 +155,7 @@ __device__ __forceinline__ unsigned long long d_warp_min_u64(unsigned long long 
 constexpr int RT_CTAS = 16;       // CTAs per cloud for the monotonicity check (k_odom_begin arms the flags)
 __global__ void __launch_bounds__(256) k_odom_ring_table(const OdomDev* __restrict__ o, const float4* __restrict__ corner_last,
                                                          const float4* __restrict__ surf_last, int32_t* __restrict__ tab_all) {
+  lm_pdl_enter();
   const int c = blockIdx.y;
   const float4* __restrict__ pts = c == 0 ? corner_last : surf_last;
   const int n = c == 0 ? o->n_corner_last : o->n_surf_last;
@@ -192,6 +196,7 @@ __global__ void __launch_bounds__(256) k_odom_corr(const OdomDev* __restrict__ o
                                                    const unsigned long long* __restrict__ best1, LmFactor* __restrict__ fac0,
                                                    LmFactor* __restrict__ fac1, int32_t* __restrict__ corr_out, const int32_t* __restrict__ ringtab,
                                                    float* __restrict__ frac0, float* __restrict__ frac1) {
+  lm_pdl_enter();
   if (!o->do_solve) return;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -307,6 +312,7 @@ __global__ void __launch_bounds__(256) k_odom_corr(const OdomDev* __restrict__ o
 }
 
 __global__ void k_odom_finish(OdomDev* o) {
+  lm_pdl_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (o->do_solve) {
     double tmp[3]; d_qrot(o->q_w_curr, o->para_t, tmp);
@@ -321,6 +327,7 @@ __global__ void k_odom_finish(OdomDev* o) {
 // :554-563 the less-sharp / less-flat clouds of this sweep become the "last" clouds (sizes read on the device)
 __global__ void __launch_bounds__(256) k_odom_keep_last(const OdomDev* __restrict__ o, const float4* __restrict__ ls, const float4* __restrict__ lf,
                                                         float4* __restrict__ last0, float4* __restrict__ last1) {
+  lm_pdl_enter();
   const int n0 = o->n_less_sharp, n1 = o->n_less_flat;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1; i += gridDim.x * blockDim.x) {
     if (i < n0) last0[i] = ls[i]; else last1[i - n0] = lf[i - n0];
@@ -373,17 +380,17 @@ void lm_odom_free(lmono_ctx* ctx) {
 static int odom_associate(lmono_ctx* ctx, OdomState* s, const float4* sharp, int n_sharp, const float4* flat, int n_flat, int nl_max0, int nl_max1, int pass) {
   const int nq = n_sharp > n_flat ? n_sharp : n_flat;
   if (nq <= 0) return LMONO_OK;
-  k_odom_best_init<<<lm_div_up(nq, 256), 256, 0, ctx->stream>>>(s->d_best[0], n_sharp, s->d_best[1], n_flat);
+  LM_LAUNCH_PDL(k_odom_best_init, lm_div_up(nq, 256), 256, 0, s->d_best[0], n_sharp, s->d_best[1], n_flat);
   LM_LAUNCH_CHECK();
   const int nlm = nl_max0 > nl_max1 ? nl_max0 : nl_max1;
   if (nlm > 0) {
     const int gy = lm_div_up(nlm, NN_CHUNK);
     dim3 grid(lm_div_up(nq, NN_QB), gy < 48 ? gy : 48, 2);
-    k_odom_nn1<<<grid, NN_QB * NN_SUB, 0, ctx->stream>>>(s->d, sharp, flat, s->d_last[0], s->d_last[1], s->d_best[0], s->d_best[1]);
+    LM_LAUNCH_PDL(k_odom_nn1, grid, NN_QB * NN_SUB, 0, s->d, sharp, flat, s->d_last[0], s->d_last[1], s->d_best[0], s->d_best[1]);
     LM_LAUNCH_CHECK();
   }
   const int warps = n_sharp + n_flat;
-  k_odom_corr<<<lm_div_up(warps * 32, 256), 256, 0, ctx->stream>>>(s->d, sharp, flat, s->d_last[0], s->d_last[1], s->d_best[0], s->d_best[1],
+  LM_LAUNCH_PDL(k_odom_corr, lm_div_up(warps * 32, 256), 256, 0, s->d, sharp, flat, s->d_last[0], s->d_last[1], s->d_best[0], s->d_best[1],
                                                                   ctx->d_fac[0], ctx->d_fac[1], s->d_corr + (size_t)pass * s->cap * 5, s->d_ringtab, s->d_frac[0], s->d_frac[1]);
   LM_LAUNCH_CHECK();
   return LMONO_OK;
@@ -395,9 +402,9 @@ int lm_odom_enqueue(lmono_ctx* ctx, const float4* sharp, int n_sharp, const floa
                     const float4* flat, int n_flat, const float4* less_flat, int n_lf, int prev_ls_max, int prev_lf_max,
                     const int32_t* d_counts = nullptr) {
   OdomState* s; int rc = odom_state(ctx, &s); if (rc) return rc;
-  k_odom_begin<<<1, 32, 0, ctx->stream>>>(s->d, n_sharp, n_ls, n_flat, n_lf, d_counts, s->cap, s->d_ringtab);
+  LM_LAUNCH_PDL(k_odom_begin, 1, 32, 0, s->d, n_sharp, n_ls, n_flat, n_lf, d_counts, s->cap, s->d_ringtab);
   LM_LAUNCH_CHECK();
-  k_odom_ring_table<<<dim3(RT_CTAS, 2), 256, 0, ctx->stream>>>(s->d, s->d_last[0], s->d_last[1], s->d_ringtab);
+  LM_LAUNCH_PDL(k_odom_ring_table, dim3(RT_CTAS, 2), 256, 0, s->d, s->d_last[0], s->d_last[1], s->d_ringtab);
   LM_LAUNCH_CHECK();
   for (int opti = 0; opti < 2; ++opti) {                       // :278
     if ((rc = odom_associate(ctx, s, sharp, n_sharp, flat, n_flat, prev_ls_max, prev_lf_max, opti))) return rc;
@@ -411,11 +418,11 @@ int lm_odom_enqueue(lmono_ctx* ctx, const float4* sharp, int n_sharp, const floa
     P.frac0 = ctx->prm.distortion ? s->d_frac[0] : nullptr; P.frac1 = ctx->prm.distortion ? s->d_frac[1] : nullptr;
     if ((rc = lm_solve_problem(ctx, P, n_sharp + n_flat, 4, 1))) return rc;
   }
-  k_odom_finish<<<1, 32, 0, ctx->stream>>>(s->d);
+  LM_LAUNCH_PDL(k_odom_finish, 1, 32, 0, s->d);
   LM_LAUNCH_CHECK();
   if (d_counts) {
     const int nb = lm_div_up(n_ls + n_lf > 0 ? n_ls + n_lf : 1, 256);
-    k_odom_keep_last<<<nb < 296 ? nb : 296, 256, 0, ctx->stream>>>(s->d, less_sharp, less_flat, s->d_last[0], s->d_last[1]);
+    LM_LAUNCH_PDL(k_odom_keep_last, nb < 296 ? nb : 296, 256, 0, s->d, less_sharp, less_flat, s->d_last[0], s->d_last[1]);
     LM_LAUNCH_CHECK();
     return LMONO_OK;
   }

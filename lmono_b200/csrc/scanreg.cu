@@ -79,6 +79,7 @@ __device__ __forceinline__ float d_neg_atan2f(float y, float x) {
 __global__ void __launch_bounds__(SC_THREADS) k_scan_classify(const float4* __restrict__ in, int n, int n_scans, float thres,
                                                               int32_t* __restrict__ key, int32_t* __restrict__ block_hist, int nb,
                                                               ScanMeta* __restrict__ meta) {
+  lm_pdl_enter();
   __shared__ int counts[SC_THREADS / 32][SC_NRING];
   __shared__ int s_first[SC_THREADS / 32], s_last[SC_THREADS / 32];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -134,6 +135,7 @@ __device__ __forceinline__ void d_start_end_ori(const float4* __restrict__ in, c
 
 __global__ void __launch_bounds__(SC_THREADS) k_scan_halfpass(const float4* __restrict__ in, int n, const int32_t* __restrict__ key,
                                                               ScanMeta* __restrict__ meta) {
+  lm_pdl_enter();
   __shared__ float s_so, s_eo;
   __shared__ int s_min[SC_THREADS / 32];
   if (meta->last_valid < 0) return;
@@ -162,6 +164,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_halfpass(const float4* __re
 
 __global__ void __launch_bounds__(1024) k_scan_blockscan(const int32_t* __restrict__ block_hist, int32_t* __restrict__ block_off, int nb,
                                                          ScanMeta* __restrict__ meta) {
+  lm_pdl_enter();
   __shared__ int ws[33];
   __shared__ int s_carry;
   const int r = blockIdx.x;
@@ -183,6 +186,7 @@ __global__ void __launch_bounds__(1024) k_scan_blockscan(const int32_t* __restri
 __global__ void __launch_bounds__(SC_THREADS) k_scan_scatter(const float4* __restrict__ in, int n, int n_scans, const int32_t* __restrict__ key,
                                                              const int32_t* __restrict__ block_off, int nb, ScanMeta* __restrict__ meta,
                                                              float4* __restrict__ full, int32_t* __restrict__ src) {
+  lm_pdl_enter();
   __shared__ int s_start[SC_NRING + 1];
   __shared__ float s_so, s_eo;
   if (threadIdx.x == 0) {
@@ -222,6 +226,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_scatter(const float4* __res
 
 __global__ void __launch_bounds__(SC_THREADS) k_scan_curvature(const float4* __restrict__ full, const ScanMeta* __restrict__ meta,
                                                                float* __restrict__ curv, int32_t* __restrict__ label) {
+  lm_pdl_enter();
   const int N = meta->n_kept;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
@@ -294,6 +299,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __res
                                                              ScanMeta* __restrict__ meta, int32_t* __restrict__ label_out,
                                                              int32_t* __restrict__ pick_idx, int32_t* __restrict__ pick_cnt,
                                                              float4* __restrict__ lf_tmp, int32_t* __restrict__ lf_cnt) {
+  lm_pdl_enter();
   extern __shared__ __align__(16) unsigned char smem[];
   unsigned long long* sec = reinterpret_cast<unsigned long long*>(smem);
   float* xyz = reinterpret_cast<float*>(smem + SCR_SEC_BYTES);
@@ -515,6 +521,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_compact(const float4* __res
                                                              const float4* __restrict__ lf_tmp, const int32_t* __restrict__ lf_cnt,
                                                              float4* __restrict__ o_sharp, float4* __restrict__ o_ls,
                                                              float4* __restrict__ o_flat, float4* __restrict__ o_lf) {
+  lm_pdl_enter();
   const int b = blockIdx.x;
   if (b < n_scans) {
     int off = 0;
@@ -556,6 +563,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_compact(const float4* __res
 }
 
 __global__ void k_scan_meta_init(ScanMeta* meta) {
+  lm_pdl_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   meta->first_valid = 0x7fffffff; meta->last_valid = -1; meta->i_star = 0x7fffffff; meta->n_kept = 0;
   for (int r = 0; r < SC_NRING + 3; ++r) { meta->ring_total[r] = 0; meta->ring_start[r] = 0; }
@@ -604,10 +612,11 @@ void lm_scan_free(lmono_ctx* ctx) {
 }
 
 // enqueue the whole stage on a device-resident float4 input; results stay on the device
-__global__ void k_scan_set_n(ScanMeta* meta, int n) { if (threadIdx.x == 0 && blockIdx.x == 0) meta->n_in = n; }
+__global__ void k_scan_set_n(ScanMeta* meta, int n) {
+  lm_pdl_enter(); if (threadIdx.x == 0 && blockIdx.x == 0) meta->n_in = n; }
 int lm_scan_set_n(lmono_ctx* ctx, int n) {
   ScanState* s; int rc = scan_state(ctx, &s); if (rc) return rc;
-  k_scan_set_n<<<1, 32, 0, ctx->stream>>>(s->d_meta, n);
+  LM_LAUNCH_PDL(k_scan_set_n, 1, 32, 0, s->d_meta, n);
   LM_LAUNCH_CHECK();
   return LMONO_OK;
 }
@@ -624,14 +633,14 @@ int lm_scan_enqueue(lmono_ctx* ctx, const float4* d_in, int n, bool n_on_device)
   const int n_scans = ctx->prm.scan_line;
   const int nb = lm_div_up(n > 0 ? n : 1, SC_THREADS);
   if (n_on_device) n = -1;
-  k_scan_meta_init<<<1, 32, 0, ctx->stream>>>(s->d_meta); LM_LAUNCH_CHECK();
-  k_scan_classify<<<nb, SC_THREADS, 0, ctx->stream>>>(d_in, n, n_scans, ctx->prm.minimum_range, s->d_key, s->d_block_hist, nb, s->d_meta); LM_LAUNCH_CHECK();
-  k_scan_halfpass<<<nb, SC_THREADS, 0, ctx->stream>>>(d_in, n, s->d_key, s->d_meta); LM_LAUNCH_CHECK();
-  k_scan_blockscan<<<64, 1024, 0, ctx->stream>>>(s->d_block_hist, s->d_block_off, nb, s->d_meta); LM_LAUNCH_CHECK();
-  k_scan_scatter<<<nb, SC_THREADS, 0, ctx->stream>>>(d_in, n, n_scans, s->d_key, s->d_block_off, nb, s->d_meta, s->d_full, s->d_src); LM_LAUNCH_CHECK();
-  k_scan_curvature<<<nb, SC_THREADS, 0, ctx->stream>>>(s->d_full, s->d_meta, s->d_curv, s->d_label); LM_LAUNCH_CHECK();
-  k_scan_ring<<<n_scans, SC_THREADS, SCR_TOTAL, ctx->stream>>>(s->d_full, s->d_curv, s->d_meta, s->d_label, s->d_pick_idx, s->d_pick_cnt, s->d_lf_tmp, s->d_lf_cnt); LM_LAUNCH_CHECK();
-  k_scan_compact<<<n_scans + 16, SC_THREADS, 0, ctx->stream>>>(s->d_full, s->d_meta, n_scans, s->d_pick_idx, s->d_pick_cnt, s->d_lf_tmp, s->d_lf_cnt,
+  LM_LAUNCH_PDL(k_scan_meta_init, 1, 32, 0, s->d_meta); LM_LAUNCH_CHECK();
+  LM_LAUNCH_PDL(k_scan_classify, nb, SC_THREADS, 0, d_in, n, n_scans, ctx->prm.minimum_range, s->d_key, s->d_block_hist, nb, s->d_meta); LM_LAUNCH_CHECK();
+  LM_LAUNCH_PDL(k_scan_halfpass, nb, SC_THREADS, 0, d_in, n, s->d_key, s->d_meta); LM_LAUNCH_CHECK();
+  LM_LAUNCH_PDL(k_scan_blockscan, 64, 1024, 0, s->d_block_hist, s->d_block_off, nb, s->d_meta); LM_LAUNCH_CHECK();
+  LM_LAUNCH_PDL(k_scan_scatter, nb, SC_THREADS, 0, d_in, n, n_scans, s->d_key, s->d_block_off, nb, s->d_meta, s->d_full, s->d_src); LM_LAUNCH_CHECK();
+  LM_LAUNCH_PDL(k_scan_curvature, nb, SC_THREADS, 0, s->d_full, s->d_meta, s->d_curv, s->d_label); LM_LAUNCH_CHECK();
+  LM_LAUNCH_PDL(k_scan_ring, n_scans, SC_THREADS, SCR_TOTAL, s->d_full, s->d_curv, s->d_meta, s->d_label, s->d_pick_idx, s->d_pick_cnt, s->d_lf_tmp, s->d_lf_cnt); LM_LAUNCH_CHECK();
+  LM_LAUNCH_PDL(k_scan_compact, n_scans + 16, SC_THREADS, 0, s->d_full, s->d_meta, n_scans, s->d_pick_idx, s->d_pick_cnt, s->d_lf_tmp, s->d_lf_cnt,
                                                               s->d_out[0], s->d_out[1], s->d_out[2], s->d_out[3]); LM_LAUNCH_CHECK();
   return LMONO_OK;
 }

@@ -21,6 +21,7 @@ constexpr int ST_ITEMS = LM_SORT_TILE / ST_THREADS;
 static_assert(LM_SORT_TILE == 1024 && ST_ITEMS == 4, "tile geometry");
 
 __global__ void __launch_bounds__(ST_THREADS) k_sort_tiles(LmSortSegs sg, int dst_is_tmp) {
+  lm_pdl_enter();
   __shared__ unsigned long long s[LM_SORT_TILE];
   const int seg = blockIdx.y;
   const int n = *sg.n[seg];
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_sort_tiles(LmSortSegs sg, int ds
 constexpr int LM_MERGE_GROUP = 16;
 
 __global__ void __launch_bounds__(256) k_merge_ranks(LmSortSegs sg, int run, int src_is_tmp) {
+  lm_pdl_enter();
   const int seg = blockIdx.y;
   const int n = *sg.n[seg];
   const unsigned long long* __restrict__ src = (src_is_tmp ? sg.tmp : sg.out) + sg.off[seg];
@@ -90,6 +92,7 @@ constexpr int LM_MERGE_SMEM_RUNS = 24;
 constexpr int MS_THREADS = 1024;
 
 __global__ void __launch_bounds__(MS_THREADS, 1) k_merge_ranks_smem(LmSortSegs sg, int src_is_tmp) {
+  lm_pdl_enter();
   extern __shared__ unsigned long long s_runs[];        // [nruns][LM_SORT_TILE]
   const int seg = blockIdx.y;
   const int n = *sg.n[seg];
@@ -147,20 +150,20 @@ int lm_sort_u64_segs(lmono_ctx* ctx, const LmSortSegs& sg, int nseg, const int* 
   if (mx <= 0 || nseg <= 0) return LMONO_OK;
   const int ntiles = lm_div_up(mx, LM_SORT_TILE);
   if (ntiles > 1 && ntiles <= LM_MERGE_SMEM_RUNS) {
-    k_sort_tiles<<<dim3(ntiles, nseg), ST_THREADS, 0, ctx->stream>>>(sg, 1);
+    LM_LAUNCH_PDL(k_sort_tiles, dim3(ntiles, nseg), ST_THREADS, 0, sg, 1);
     LM_LAUNCH_CHECK();
-    k_merge_ranks_smem<<<dim3(lm_div_up(mx, MS_THREADS), nseg), MS_THREADS, (size_t)ntiles * LM_SORT_TILE * 8, ctx->stream>>>(sg, 1);
+    LM_LAUNCH_PDL(k_merge_ranks_smem, dim3(lm_div_up(mx, MS_THREADS), nseg), MS_THREADS, (size_t)ntiles * LM_SORT_TILE * 8, sg, 1);
     LM_LAUNCH_CHECK();
     return LMONO_OK;
   }
   const int passes = merge_passes(mx);
   // buffers alternate tmp <-> out per pass and the last pass must land in `out`
   int cur_is_tmp = (passes & 1) ? 1 : 0;
-  k_sort_tiles<<<dim3(ntiles, nseg), ST_THREADS, 0, ctx->stream>>>(sg, cur_is_tmp);
+  LM_LAUNCH_PDL(k_sort_tiles, dim3(ntiles, nseg), ST_THREADS, 0, sg, cur_is_tmp);
   LM_LAUNCH_CHECK();
   long long run = LM_SORT_TILE;
   for (int p = 0; p < passes; ++p, run *= LM_MERGE_GROUP) {
-    k_merge_ranks<<<dim3(lm_div_up(mx, 256), nseg), 256, 0, ctx->stream>>>(sg, (int)run, cur_is_tmp);
+    LM_LAUNCH_PDL(k_merge_ranks, dim3(lm_div_up(mx, 256), nseg), 256, 0, sg, (int)run, cur_is_tmp);
     LM_LAUNCH_CHECK();
     cur_is_tmp ^= 1;
   }

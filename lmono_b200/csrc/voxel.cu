@@ -41,6 +41,7 @@ __global__ void k_vg_reset(VgParams* vg) {
 
 __global__ void __launch_bounds__(256) k_vg_keys(VgSegs sg, VgParams* __restrict__ vgs, unsigned long long* __restrict__ comp,
                                                  LmMapState* __restrict__ st) {
+  lm_pdl_enter();
   __shared__ uint32_t smn[3][8], smx[3][8];
   const int seg = blockIdx.y;
   const int n = *sg.n[seg];
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(256) k_vg_keys(VgSegs sg, VgParams* __restrict
 // sorted positions; its output offset = number of run heads before it, recounted from the (L2-resident,
 // <= 128 KB) sorted array instead of a separate scan launch.
 __global__ void __launch_bounds__(VW_THREADS) k_vg_write(VgSegs sg, VgParams* __restrict__ vgs, const unsigned long long* __restrict__ sorted_all) {
+  lm_pdl_enter();
   __shared__ int ws[33];
   __shared__ int s_guard;
   __shared__ unsigned long long s_key[VW_THREADS];
@@ -200,12 +202,12 @@ int lm_voxel_grid_multi(lmono_ctx* ctx, int nseg, const float4* const* in, const
     if (s < nseg) { off += n_max[s]; mx = n_max[s] > mx ? n_max[s] : mx; }
   }
   if (mx > 0) {
-    k_vg_keys<<<dim3(lm_div_up(mx, 256), nseg), 256, 0, ctx->stream>>>(sg, ctx->d_vg, ctx->d_sort_a, ctx->d_state);
+    LM_LAUNCH_PDL(k_vg_keys, dim3(lm_div_up(mx, 256), nseg), 256, 0, sg, ctx->d_vg, ctx->d_sort_a, ctx->d_state);
     LM_LAUNCH_CHECK();
     int rc = lm_sort_u64_segs(ctx, ss, nseg, n_max);
     if (rc) return rc;
   }
-  k_vg_write<<<dim3(max(1, lm_div_up(mx, VW_BLOCK)), nseg), VW_THREADS, 0, ctx->stream>>>(sg, ctx->d_vg, ctx->d_sort_c);
+  LM_LAUNCH_PDL(k_vg_write, dim3(max(1, lm_div_up(mx, VW_BLOCK)), nseg), VW_THREADS, 0, sg, ctx->d_vg, ctx->d_sort_c);
   LM_LAUNCH_CHECK();
   return LMONO_OK;
 }

@@ -64,3 +64,28 @@ def test_product_code_never_touches_the_oracle():
     assert not bad, bad
     out = subprocess.run(["ldd", os.path.join(pkg, "csrc", "liblmono_b200.so")], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_every_pdl_launched_kernel_waits_for_its_predecessor():
+    """Kernels launched with programmatic dependent launch (LM_LAUNCH_PDL, common.cuh) may start before the previous
+    kernel of the stream has finished: each of them must execute lm_pdl_enter() (griddepcontrol.wait) as its first
+    statement, or the transitive ordering of the step chain is lost."""
+    csrc = os.path.join(ROOT, "lmono_b200", "csrc")
+    src = {f: open(os.path.join(csrc, f)).read() for f in os.listdir(csrc) if f.endswith((".cu", ".cuh"))}
+    launched = set()
+    for txt in src.values():
+        launched |= set(re.findall(r"LM_LAUNCH_PDL\(\s*(k_\w+)", txt))
+    assert len(launched) >= 30, launched
+    alltxt = "\n".join(src.values())
+    for k in sorted(launched):
+        defs = [m for m in re.finditer(r"__global__[^;{]*?\b%s\s*\(" % k, alltxt)]
+        assert defs, k
+        ok = False
+        for m in defs:
+            i = m.end(); d = 1
+            while d > 0:
+                d += {"(": 1, ")": -1}.get(alltxt[i], 0); i += 1
+            body = alltxt[i:i + 80].lstrip()
+            if body.startswith("{") and body[1:].lstrip().startswith("lm_pdl_enter();"):
+                ok = True
+        assert ok, f"{k} is launched with LM_LAUNCH_PDL but does not start with lm_pdl_enter()"
