@@ -291,8 +291,13 @@ int lmono_kmarks_dump(lmono_ctx* ctx, char* buf, int32_t cap);
 
 /* Latency study hook: %globaltimer stamps (ns) written by instrumented kernels (slot map in DESIGN.md):
  * [0..63] the LM solve kernel of the most recent solve: 0 start, 1 armed, then per evaluation e (8 slots from
- * 8 + 8 e): factors evaluated, warp+block reduced, cluster exchanged, controller done. */
+ * 8 + 8 e): factors evaluated, warp+block reduced, cluster exchanged, controller done;
+ * [200..207] k_scan_ring of ring 32: start, ring staged, sectors sorted, greedy pick done, less-flat list, voxel bounds,
+ * voxel keys sorted, centroids written. */
 int lmono_debug_stamps(lmono_ctx* ctx, uint64_t* out /*[n]*/, int32_t n /*<= 4096*/);
+/* Study hook: the per-cube refilter records of the last mapping step, [2 map types][75 window cubes] x 8 ints
+ * {has a tail, size after the merge, filtered prefix before it, tail points, re-voxelise flag, buffer, slab, -}. */
+int lmono_debug_rf_meta(lmono_ctx* ctx, int32_t* out, int32_t n_ints /*<= 1200*/);
 
 /* Per-phase device timing (CUDA events on the ctx stream) of lmono_map_step, used by bench.py
  * for the roofline numbers.  Phases: 0 window shift, 1 cell-index build, 2 VoxelGrid of the

@@ -85,6 +85,9 @@ struct LmLmState {          // Levenberg-Marquardt controller state (one solve a
   // scratch for the grid reduction
   unsigned int ticket;
   unsigned int pad2;
+  // reciprocals kept beside radius / model_cost_change so that the controller's dependent chain (step quality -> radius ->
+  // damped normal equations -> Cholesky -> candidate) carries one fp64 division less per pass each
+  double inv_radius, inv_model_cost_change;
 };
 
 struct LmProblem {          // one LM solve: factor arrays, pose in/out, report slots (device pointers)
@@ -228,6 +231,7 @@ struct lmono_ctx {
   int32_t* d_nnref;                         // [2 * max_feat][5] neighbour references of the association pass (-1 = gate failed)
   unsigned long long* d_sort_a; unsigned long long* d_sort_b; unsigned long long* d_sort_c;
   int32_t* d_blockcnt;                      // block counts for 2-kernel scans
+  int32_t* d_sort_done;                     // [LM_SORT_MAXSEG] sort.cu: the segment was merged by the single shared-memory pass
   int32_t* d_tmp_i32;                       // misc int scratch [max_feature_points*2]
   VgParams* d_vg;
   float4* d_full;                           // full-res sweep

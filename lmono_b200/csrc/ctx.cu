@@ -138,6 +138,7 @@ static int create_impl(lmono_ctx* ctx, void* stream) {
   LM_CUDA(cudaMalloc((void**)&ctx->d_sort_b, nsort * sizeof(unsigned long long)));
   LM_CUDA(cudaMalloc((void**)&ctx->d_sort_c, nsort * sizeof(unsigned long long)));
   LM_CUDA(cudaMalloc((void**)&ctx->d_blockcnt, sizeof(int32_t) * (nsort / 256 + 64)));
+  LM_CUDA(cudaMalloc((void**)&ctx->d_sort_done, sizeof(int32_t) * 8));
   LM_CUDA(cudaMalloc((void**)&ctx->d_tmp_i32, sizeof(int32_t) * (2 * LM_NSLOT + 64 + nsort)));
   LM_CUDA(cudaMalloc((void**)&ctx->d_vg, sizeof(VgParams) * 4));
   { int rcv = lm_voxel_init(ctx); if (rcv) return rcv; }
@@ -173,7 +174,7 @@ extern "C" void lmono_destroy(lmono_ctx* ctx) {
   cudaFree(ctx->d_state); cudaFreeHost(ctx->h_state); for (int i = 0; i < 2; ++i) { cudaFreeHost(ctx->h_ring[i]); if (ctx->ev_res[i]) cudaEventDestroy(ctx->ev_res[i]); } cudaFree(ctx->d_lm); cudaFree(ctx->d_slot_valid_rank); cudaFree(ctx->d_partials); cudaFree(ctx->d_stamps); cudaFree(ctx->d_tl); cudaFree(ctx->d_nnref); cudaFree(ctx->d_rf_nvx); cudaFree(ctx->d_rf_tlb); cudaFree(ctx->d_rf_work); cudaFree(ctx->d_rf_meta); cudaFree(ctx->d_rf_plan); cudaFree(ctx->d_rf_big_s); cudaFree(ctx->d_rf_big_nv);
   for (int i = 0; i < 3; ++i) cudaFree(ctx->d_raw[i]);
   for (int i = 0; i < 2; ++i) { cudaFree(ctx->d_in[i]); cudaFree(ctx->d_stack[i]); cudaFree(ctx->d_world[i]); cudaFree(ctx->d_fac[i]); }
-  cudaFree(ctx->d_sort_a); cudaFree(ctx->d_sort_b); cudaFree(ctx->d_sort_c); cudaFree(ctx->d_blockcnt); cudaFree(ctx->d_tmp_i32);
+  cudaFree(ctx->d_sort_a); cudaFree(ctx->d_sort_b); cudaFree(ctx->d_sort_c); cudaFree(ctx->d_blockcnt); cudaFree(ctx->d_sort_done); cudaFree(ctx->d_tmp_i32);
   cudaFree(ctx->d_vg); cudaFree(ctx->d_full); cudaFree(ctx->d_slot_first); cudaFree(ctx->d_slot_base); cudaFree(ctx->d_export_off); cudaFree(ctx->d_export);
   cudaEvent_t evs[] = { ctx->ev0, ctx->ev1, ctx->ev_k0, ctx->ev_o0, ctx->ev_o1, ctx->ev_fork, ctx->ev_join, ctx->ev_sync, ctx->ev_done, ctx->ev_side0, ctx->ev_side1 };
   for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);

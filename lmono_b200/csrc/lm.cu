@@ -297,7 +297,7 @@ __device__ int d_compute_step(LmLmState* lm) {
     double A[21];
 #pragma unroll
     for (int k = 0; k < 21; ++k) A[k] = Hs[k];
-    const double inv_radius = 1.0 / lm->radius;
+    const double inv_radius = lm->inv_radius;
 #pragma unroll
     for (int j = 0; j < 6; ++j) A[d_tri(j, j)] += lm->diagonal[j] * inv_radius;     // D^2 = diagonal / radius
     double y[6];
@@ -321,11 +321,12 @@ __device__ int d_compute_step(LmLmState* lm) {
         sHs += step[a] * row;
       }
       lm->model_cost_change = -(sg + 0.5 * sHs);
+      lm->inv_model_cost_change = 1.0 / lm->model_cost_change;      // off the chain: overlaps the candidate's Plus below
       valid = lm->model_cost_change > 0.0;
     }
     if (!valid) {
       if (++lm->num_invalid >= 5) { lm->termination = 5; lm->done = 1; return 0; }
-      lm->radius *= 0.5; lm->reuse_diagonal = 1;
+      lm->radius *= 0.5; lm->inv_radius *= 2.0; lm->reuse_diagonal = 1;
       continue;
     }
     lm->num_invalid = 0;
@@ -359,7 +360,7 @@ __device__ void d_lm_control(LmLmState* lm, const double* red /*28*/, const LmPr
       const double cost_change = lm->cost - cost_e;
       if (fabs(cost_change) <= 1e-6 * lm->cost) { lm->termination = 3; lm->done = 1; }
       else {
-        const double rd = cost_change / lm->model_cost_change;
+        const double rd = cost_change * lm->inv_model_cost_change;
         if (rd > 1e-3) {
           _Pragma("unroll") for (int i = 0; i < 7; ++i) lm->x[i] = lm->cand[i];
           lm->x_norm = d_norm7(lm->x);
@@ -368,12 +369,15 @@ __device__ void d_lm_control(LmLmState* lm, const double* red /*28*/, const LmPr
           _Pragma("unroll") for (int k = 0; k < 6; ++k) lm->g[k] = red[21 + k];
           const double tq = 2.0 * rd - 1.0;
           double den = 1.0 - tq * tq * tq; if (den < 1.0 / 3.0) den = 1.0 / 3.0;
-          lm->radius = lm->radius / den; if (lm->radius > 1e16) lm->radius = 1e16;
+          lm->inv_radius = lm->inv_radius * den;      // den in [1/3, 2]
+          lm->radius = lm->radius / den;
+          if (lm->radius > 1e16) { lm->radius = 1e16; lm->inv_radius = 1e-16; }
           lm->decrease_factor = 2.0; lm->reuse_diagonal = 0;
           lm->num_successful++;
           if (lm->iteration < lm->max_iter && d_gradient_max_norm(lm->x, lm->g) <= 1e-10) { lm->termination = 1; lm->done = 1; }
         } else {
-          lm->radius = lm->radius / lm->decrease_factor; lm->decrease_factor *= 2.0; lm->reuse_diagonal = 1;
+          lm->radius = lm->radius / lm->decrease_factor; lm->inv_radius *= lm->decrease_factor;   // a power of two: exact
+          lm->decrease_factor *= 2.0; lm->reuse_diagonal = 1;
         }
         if (!lm->done) d_compute_step(lm);
       }
@@ -409,7 +413,7 @@ __global__ void k_lm_begin(LmLmState* __restrict__ lm, LmProblem P, int max_iter
     for (int k = 0; k < 4; ++k) lm->x[k] = P.pose_q[k];
     for (int k = 0; k < 3; ++k) lm->x[4 + k] = P.pose_t[k];
     for (int k = 0; k < 7; ++k) lm->cand[k] = lm->x[k];
-    lm->radius = 1e4; lm->decrease_factor = 2.0; lm->reuse_diagonal = 0; lm->num_invalid = 0;
+    lm->radius = 1e4; lm->inv_radius = 1e-4; lm->inv_model_cost_change = 0.0; lm->decrease_factor = 2.0; lm->reuse_diagonal = 0; lm->num_invalid = 0;
     lm->iteration = 0; lm->num_successful = 0; lm->termination = 0; lm->phase = 0; lm->max_iter = max_iter;
     lm->nfactors = t0 + t1; lm->ticket = 0; lm->initial_cost = 0.0; lm->cost = 0.0;
     lm->done = (!gate || (!sharded && (t0 + t1) == 0)) ? 1 : 0;   // sharded: the global count decides (k_lm_control)
@@ -587,7 +591,7 @@ k_lm_solve_cluster(LmLmState* __restrict__ lm_g, LmProblem P, int max_iter, int 
     for (int k = 0; k < 21; ++k) lm->H[k] = 0.0;
     for (int k = 0; k < 6; ++k) { lm->g[k] = 0.0; lm->scaling[k] = 1.0; lm->diagonal[k] = 0.0; }
     lm->x_norm = 0.0; lm->model_cost_change = 0.0;
-    lm->radius = 1e4; lm->decrease_factor = 2.0; lm->reuse_diagonal = 0; lm->num_invalid = 0;
+    lm->radius = 1e4; lm->inv_radius = 1e-4; lm->inv_model_cost_change = 0.0; lm->decrease_factor = 2.0; lm->reuse_diagonal = 0; lm->num_invalid = 0;
     lm->iteration = 0; lm->num_successful = 0; lm->termination = 0; lm->phase = 0; lm->max_iter = max_iter;
     lm->nfactors = 0; lm->ticket = 0; lm->initial_cost = 0.0; lm->cost = 0.0; lm->pad = 0; lm->pad2 = 0;
     lm->done = gate ? 0 : 1;

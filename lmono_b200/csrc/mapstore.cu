@@ -480,17 +480,18 @@ __global__ void __launch_bounds__(256) k_insert_write_plan(LmMapState* __restric
 
 // per cube with a tail, one CTA: tail element j opens a NEW voxel iff it is the first of its key run and the key is absent
 // from the prefix (9-ary search, the lower bound is kept for k_rf_merge); exclusive scan of those flags -> output
-// offsets; clears the cell histogram; appends the cube's merge chunks to the work list.
+// offsets.  A cube without a new voxel is finished here (centroids updated in place, see below); the others get their
+// cell histogram cleared and their merge chunks appended to the work list.
 constexpr int RF_ACT_GRID = 80;
 constexpr int RF_TS_THREADS = 1024;
 static_assert(LM_NCELL % 4 == 0, "vector clear of the cell histogram");
 static_assert(LM_RF_CHUNK % 256 == 0, "k_rf_merge / k_rf_scatter: whole elements per thread");
 __global__ void __launch_bounds__(RF_TS_THREADS) k_rf_tailscan(LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, const int32_t* __restrict__ plan,
                                                                int32_t* __restrict__ nvx_all, int32_t* __restrict__ tlb_all, RfMeta* __restrict__ meta_all,
-                                                               int nvx_stride, int32_t* __restrict__ work_n, int32_t* __restrict__ work) {
+                                                               int nvx_stride, int32_t* __restrict__ work_n, int32_t* __restrict__ work, int inplace) {
   lm_pdl_enter();
   __shared__ int ws[33];
-  __shared__ int s_wbase;
+  __shared__ int s_wbase, s_fallback, s_badkey;
   const int na = plan[LM_PLAN_ACTIVE_N];
   for (int a = blockIdx.x; a < na; a += gridDim.x) {
     const int e = plan[LM_PLAN_ACTIVE + a];
@@ -502,8 +503,6 @@ __global__ void __launch_bounds__(RF_TS_THREADS) k_rf_tailscan(LmMapState* __res
     const uint32_t* __restrict__ tkey = pkey + ns;
     int32_t* __restrict__ nvx = nvx_all + (size_t)e * nvx_stride;
     int32_t* __restrict__ tlb = tlb_all + (size_t)e * nvx_stride;
-    int4* cc4 = reinterpret_cast<int4*>(M.cellcount + (size_t)sid * LM_NCELL);       // LM_NCELL % 4 == 0, slabs 16 B aligned
-    for (int c = threadIdx.x; c < LM_NCELL / 4; c += blockDim.x) cc4[c] = make_int4(0, 0, 0, 0);
     int carry = 0;
     for (int j0 = 0; j0 < nt; j0 += blockDim.x) {
       const int j = j0 + threadIdx.x;
@@ -521,6 +520,72 @@ __global__ void __launch_bounds__(RF_TS_THREADS) k_rf_tailscan(LmMapState* __res
       if (j < nt) nvx[j] = ((carry + ex) << 1) | nv;
       carry += tot;
     }
+    // ---- no new voxel in this cube (the usual case once an area is mapped): VoxelGrid(prefix ++ tail) leaves every
+    // point where it is and only moves the centroids of the voxels the tail hits.  They are updated IN PLACE -- in the
+    // canonical buffer and in the cell-sorted copy -- instead of rewriting the whole slab (points, keys, cell table,
+    // cell-sorted copy: ~60 B per stored point) through merge / scan / scatter.  Same summation order as k_rf_merge
+    // (prefix point, then the tail members in arrival order, one division), so the bits are the same.  A centroid that
+    // changes its 2 m search cell would have to move inside the cell-sorted copy: such a cube takes the merge path.
+    if (inplace && carry == 0 && nt > 0) {
+      float4* pts = M.pts + ((size_t)sid * 2 + meta->cur) * M.cap;
+      const int g3[3] = { M.slab_g[sid * 4], M.slab_g[sid * 4 + 1], M.slab_g[sid * 4 + 2] };
+      const float il = M.inv_leaf;
+      if (threadIdx.x == 0) { s_fallback = 0; s_badkey = 0; }
+      __syncthreads();
+      for (int phase = 0; phase < 2; ++phase) {
+        for (int j = threadIdx.x; j < nt; j += blockDim.x) {
+          const uint32_t key = tkey[j];
+          if (j > 0 && tkey[j - 1] == key) continue;           // not a run head
+          const int lb = tlb[j];
+          const float4 po = pts[lb];
+          float sx = po.x, sy = po.y, sz = po.z, si = po.w;
+          int cnt = 1;
+          for (int m = j; m < nt && tkey[m] == key; ++m) {
+            const float4 t = pts[ns + m];
+            sx = __fadd_rn(sx, t.x); sy = __fadd_rn(sy, t.y); sz = __fadd_rn(sz, t.z); si = __fadd_rn(si, t.w);
+            ++cnt;
+          }
+          const float c = (float)cnt;
+          const float4 pn = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), __fdiv_rn(si, c));
+          const int cell = d_cube_cell(po, g3);
+          if (phase == 0) {
+            if (cell < 0 || d_cube_cell(pn, g3) != cell) s_fallback = 1;
+            if (d_cube_voxel_key(pn, il, g3) != key) s_badkey = 1;          // the centroid left its voxel: re-voxelise the cube as a whole next time
+          } else {
+            pts[lb] = pn;
+            float4* cp = M.cellpts + (size_t)sid * M.cap;
+            const uint32_t* cs = M.cellstart + (size_t)sid * (LM_NCELL + 1) + cell;
+            const int cb = (int)cs[0], ce = (int)cs[1];
+            bool found = false;
+            for (int q0 = cb; q0 < ce && !found; q0 += 4) {    // the cell holds this point exactly once
+              float w[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) w[u] = q0 + u < ce ? cp[q0 + u].w : __int_as_float(-1);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) if (__float_as_int(w[u]) == lb) { cp[q0 + u] = make_float4(pn.x, pn.y, pn.z, w[u]); found = true; }
+            }
+            if (!found) atomicOr(&st->fault, LM_FAULT_CELL_RANGE);      // the search index did not cover the prefix (internal error)
+          }
+        }
+        __syncthreads();
+        if (s_fallback) break;
+      }
+      if (!s_fallback) {
+        if (threadIdx.x == 0) {
+          M.slab_n[sid] = ns;
+          M.slab_nsorted[sid] = s_badkey ? 0 : ns;
+          M.slab_unsorted[sid] = s_badkey ? 1 : 0;
+          M.slab_dirty[sid] = 0;
+          meta->active = 2;                                    // done: k_rf_scan skips it, no merge chunks
+          meta->total_new = ns;
+        }
+        __syncthreads();
+        continue;
+      }
+      __syncthreads();
+    }
+    int4* cc4 = reinterpret_cast<int4*>(M.cellcount + (size_t)sid * LM_NCELL);       // LM_NCELL % 4 == 0, slabs 16 B aligned
+    for (int c = threadIdx.x; c < LM_NCELL / 4; c += blockDim.x) cc4[c] = make_int4(0, 0, 0, 0);
     const int nch = (ns + nt + LM_RF_CHUNK - 1) / LM_RF_CHUNK;
     if (threadIdx.x == 0) {
       if (ns + carry > M.cap) atomicOr(&st->fault, LM_FAULT_CUBE_OVERFLOW);
@@ -668,6 +733,7 @@ __global__ void __launch_bounds__(RF_SCAN_THREADS) k_rf_scan(LmMapType M0, LmMap
     const int e = plan[LM_PLAN_ACTIVE + a];
     const LmMapType& M = e < LM_WIN_MAX ? M0 : M1;
     RfMeta* meta = meta_all + e;
+    if (meta->active != 1) continue;                 // updated in place by k_rf_tailscan
     const int sid = meta->sid;
     int32_t* cc = M.cellcount + (size_t)sid * LM_NCELL;
     uint32_t* cs = M.cellstart + (size_t)sid * (LM_NCELL + 1);
@@ -859,6 +925,7 @@ int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf,
   const int cap_max = ctx->map[0].cap > ctx->map[1].cap ? ctx->map[0].cap : ctx->map[1].cap;
   RfMeta* meta = (RfMeta*)ctx->d_rf_meta;
   int32_t* work_n = ctx->d_rf_work; int32_t* work = ctx->d_rf_work + 4;
+  static const bool rf_inplace = !(getenv("LMONO_RF_INPLACE") && getenv("LMONO_RF_INPLACE")[0] == '0');      // A/B switch
   if (n_max <= 0) {
     LM_LAUNCH_PDL(k_rf_plan, 1, 256, 0, ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan, meta, work_n);
     LM_LAUNCH_CHECK();
@@ -877,7 +944,7 @@ int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf,
   LM_LAUNCH_PDL(k_refilter_whole, RF_WHOLE_GRID, 1024, kRefilterSmem, ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan, ctx->d_rf_big_s, ctx->d_rf_big_nv);
   if (fork) { ctx->stream = main_stream; LM_CUDA(cudaEventRecord(ctx->ev_side1, ctx->side_stream)); }
   LM_LAUNCH_CHECK();
-  LM_LAUNCH_PDL(k_rf_tailscan, RF_ACT_GRID, RF_TS_THREADS, 0, ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan, ctx->d_rf_nvx, ctx->d_rf_tlb, meta, cap_max, work_n, work);
+  LM_LAUNCH_PDL(k_rf_tailscan, RF_ACT_GRID, RF_TS_THREADS, 0, ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_plan, ctx->d_rf_nvx, ctx->d_rf_tlb, meta, cap_max, work_n, work, rf_inplace ? 1 : 0);
   LM_LAUNCH_CHECK();
   LM_LAUNCH_PDL(k_rf_merge, RF_GRID, 256, 0, ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_nvx, ctx->d_rf_tlb, meta, cap_max, work_n, work);
   LM_LAUNCH_CHECK();
@@ -887,6 +954,14 @@ int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf,
   LM_LAUNCH_CHECK();
   if (fork) LM_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_side1, 0));
   lm_prof_end(ctx);
+  return LMONO_OK;
+}
+
+// study hook: the refilter records of the last step, [2][LM_WIN_MAX] x {active, new size, prefix size, tail size, flag, cur, slab, -}
+extern "C" int lmono_debug_rf_meta(lmono_ctx* ctx, int32_t* out, int32_t n_ints) {
+  if (!ctx || !out || n_ints < 0 || n_ints > (int)(sizeof(RfMeta) / 4) * 2 * LM_WIN_MAX) return LMONO_E_ARG;
+  LM_CUDA(cudaMemcpyAsync(out, ctx->d_rf_meta, sizeof(int32_t) * (size_t)n_ints, cudaMemcpyDeviceToHost, ctx->stream));
+  LM_CUDA(cudaStreamSynchronize(ctx->stream));
   return LMONO_OK;
 }
 

@@ -36,6 +36,8 @@ struct OdomState {
   int32_t* d_corr;                  // test hook: [n_sharp*2] + [n_flat*3]
   float* d_frac[2];                 // DISTORTION 1: fractional intensity of every sharp / flat feature (factor ratio s = frac / 0.1)
   int32_t* d_ringtab;               // [2][RT_STRIDE]: per last cloud, first index with ring >= r (r = 0..65) and a "sorted by ring" flag at [66]
+  float4* d_box;                    // [2][box_stride][2]: bounding box of every 32-point tile of the two last clouds (k_odom_ring_table)
+  int box_stride;
   int cap;
 };
 
@@ -134,6 +136,106 @@ __global__ void __launch_bounds__(NN_QB * NN_SUB) k_odom_nn1(const OdomDev* __re
   if (sub == 0 && qi < nq && bestk != ~0ULL) atomicMin(&best[qi], bestk);
 }
 
+// ---- exact 1-NN by bounding-box pruning (replaces the tiled brute force above; LMONO_ODOM_NN=brute keeps it for A/B runs)
+// The last clouds come ring by ring in firing order, so 32 consecutive points are a short arc of one ring: a compact
+// box.  One warp per feature: lane l computes the lower bound of the fp32 squared distance to the boxes of tiles l, l + 32,
+// ...; the tile with the smallest bound seeds the best (d2, index) key; afterwards only tiles whose bound does not exceed
+// the best d2 so far are scanned (one coalesced 512-byte load each).  The bound is evaluated with the same rounded
+// operations as the distance itself (fl(a - b), fl(x * x), fl(x + y) are monotonic), so bound <= d2 holds bit for bit and
+// the result -- including the (d2, index) tie rule -- equals the brute-force scan.  ~400 of the ~25 000 candidates of an
+// HDL-64 less-flat cloud are touched per feature.
+__device__ __forceinline__ float d_box_lb(float4 b0, float4 b1, float4 q) {
+  const float ex = fmaxf(fmaxf(__fsub_rn(b0.x, q.x), __fsub_rn(q.x, b0.w)), 0.f);
+  const float ey = fmaxf(fmaxf(__fsub_rn(b0.y, q.y), __fsub_rn(q.y, b1.x)), 0.f);
+  const float ez = fmaxf(fmaxf(__fsub_rn(b0.z, q.z), __fsub_rn(q.z, b1.y)), 0.f);
+  return __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
+}
+__device__ __forceinline__ unsigned long long d_nn_point_key(float4 sel, float4 p, int j) {
+  const float dx = __fsub_rn(sel.x, p.x), dy = __fsub_rn(sel.y, p.y), dz = __fsub_rn(sel.z, p.z);
+  float d = __fmul_rn(dx, dx);
+  d = __fadd_rn(d, __fmul_rn(dy, dy));
+  d = __fadd_rn(d, __fmul_rn(dz, dz));
+  return ((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)j;
+}
+__device__ __forceinline__ unsigned long long d_warp_min_u64(unsigned long long v);
+
+constexpr int NB_LIST = 64;       // tiles a warp collects before it scans them (four coalesced loads in flight per step)
+__device__ __forceinline__ unsigned long long d_nn_scan_list(const float4* __restrict__ last, int nl, float4 sel, const unsigned short* list, int cnt,
+                                                             int tile0, int lane, unsigned long long bestk) {
+  for (int i = 0; i < cnt; i += 4) {
+    int j[4]; float4 p[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { j[u] = i + u < cnt ? (tile0 + (int)list[i + u]) * 32 + lane : nl; if (j[u] < nl) p[u] = last[j[u]]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) if (j[u] < nl) { const unsigned long long k = d_nn_point_key(sel, p[u], j[u]); bestk = k < bestk ? k : bestk; }
+  }
+  return d_warp_min_u64(bestk);
+}
+
+__global__ void __launch_bounds__(256, 2) k_odom_nn_box(const OdomDev* __restrict__ o, const float4* __restrict__ sharp, const float4* __restrict__ flat,
+                                                     const float4* __restrict__ corner_last, const float4* __restrict__ surf_last,
+                                                     const float4* __restrict__ box_all, int box_stride,
+                                                     unsigned long long* __restrict__ best0, unsigned long long* __restrict__ best1) {
+  lm_pdl_enter();
+  __shared__ unsigned short s_list[8][NB_LIST];
+  if (!o->do_solve) return;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int ns = o->n_sharp, nf = o->n_flat;
+  if (warp >= ns + nf) return;
+  const bool is_corner = warp < ns;
+  const int qi = is_corner ? warp : warp - ns;
+  const float4* __restrict__ last = is_corner ? corner_last : surf_last;
+  const int nl = is_corner ? o->n_corner_last : o->n_surf_last;
+  unsigned long long* __restrict__ best = is_corner ? best0 : best1;
+  if (nl <= 0) { if (lane == 0) best[qi] = ~0ULL; return; }
+  const float4 sel = d_to_start(o, is_corner ? sharp[qi] : flat[qi]);
+  const float4* __restrict__ box = box_all + (size_t)(is_corner ? 0 : 1) * box_stride * 2;
+  const int ntile = (nl + 31) >> 5;
+  unsigned short* list = s_list[threadIdx.x >> 5];
+  unsigned long long bestk = ~0ULL;
+  // 1024 tiles (32 768 points) per outer trip: lane l keeps the bounds of tiles l, l + 32, ... in registers
+  for (int tile0 = 0; tile0 < ntile; tile0 += 1024) {
+    uint32_t lbs[32];
+#pragma unroll
+    for (int k0 = 0; k0 < 32; k0 += 4) {             // four tiles' boxes (eight independent loads) in flight
+      float4 b0[4], b1[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int t = tile0 + (k0 + u) * 32 + lane; if (t < ntile) { b0[u] = box[2 * t]; b1[u] = box[2 * t + 1]; } }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int t = tile0 + (k0 + u) * 32 + lane; lbs[k0 + u] = t < ntile ? __float_as_uint(d_box_lb(b0[u], b1[u], sel)) : 0xffffffffu; }
+    }
+    if (tile0 == 0) {                                // seed: the tile with the smallest bound
+      unsigned long long seedk = ~0ULL;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) { const unsigned long long v = ((unsigned long long)lbs[k] << 32) | (uint32_t)(k * 32 + lane); seedk = v < seedk ? v : seedk; }
+      const int seed = (int)(uint32_t)d_warp_min_u64(seedk);
+      const int j = seed * 32 + lane;
+      if (j < nl) bestk = d_nn_point_key(sel, last[j], j);
+      bestk = d_warp_min_u64(bestk);
+    }
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      if (tile0 + k * 32 >= ntile) break;            // warp-uniform
+      unsigned m = __ballot_sync(0xffffffffu, lbs[k] <= (uint32_t)(bestk >> 32));
+      if (!m) continue;
+      if (cnt + __popc(m) > NB_LIST) {               // list full: scan what is collected, the tighter bound prunes the rest
+        __syncwarp();
+        bestk = d_nn_scan_list(last, nl, sel, list, cnt, tile0, lane, bestk);
+        cnt = 0;
+        m = __ballot_sync(0xffffffffu, lbs[k] <= (uint32_t)(bestk >> 32));
+      }
+      if ((m >> lane) & 1u) list[cnt + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(k * 32 + lane);
+      cnt += __popc(m);
+    }
+    __syncwarp();
+    bestk = d_nn_scan_list(last, nl, sel, list, cnt, tile0, lane, bestk);
+    __syncwarp();
+  }
+  if (lane == 0) best[qi] = bestk;
+}
+
 __device__ __forceinline__ float d_sqdis(float4 a, float4 sel) {
   // (a.x - sel.x)*(a.x - sel.x) + (a.y - sel.y)*(a.y - sel.y) + (a.z - sel.z)*(a.z - sel.z), fp32 (:322-327)
   const float dx = __fsub_rn(a.x, sel.x), dy = __fsub_rn(a.y, sel.y), dz = __fsub_rn(a.z, sel.z);
@@ -154,12 +256,28 @@ __device__ __forceinline__ unsigned long long d_warp_min_u64(unsigned long long 
 // scan with the reference's break rule.  blockIdx.x: 0 corner_last, 1 surf_last.
 constexpr int RT_CTAS = 16;       // CTAs per cloud for the monotonicity check (k_odom_begin arms the flags)
 __global__ void __launch_bounds__(256) k_odom_ring_table(const OdomDev* __restrict__ o, const float4* __restrict__ corner_last,
-                                                         const float4* __restrict__ surf_last, int32_t* __restrict__ tab_all) {
+                                                         const float4* __restrict__ surf_last, int32_t* __restrict__ tab_all,
+                                                         float4* __restrict__ box_all, int box_stride) {
   lm_pdl_enter();
   const int c = blockIdx.y;
   const float4* __restrict__ pts = c == 0 ? corner_last : surf_last;
   const int n = c == 0 ? o->n_corner_last : o->n_surf_last;
   int32_t* tab = tab_all + c * RT_STRIDE;
+  {   // bounding boxes of the 32-point tiles (k_odom_nn_box): one warp per tile
+    float4* __restrict__ box = box_all + (size_t)c * box_stride * 2;
+    const int lane = threadIdx.x & 31, ntile = (n + 31) >> 5;
+    for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < ntile; t += (gridDim.x * blockDim.x) >> 5) {
+      const int j = t * 32 + lane;
+      float mn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, mx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+      if (j < n) { const float4 p = pts[j]; mn[0] = mx[0] = p.x; mn[1] = mx[1] = p.y; mn[2] = mx[2] = p.z; }
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+#pragma unroll
+        for (int ofs = 16; ofs > 0; ofs >>= 1) { mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], ofs)); mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], ofs)); }
+      }
+      if (lane == 0) { box[2 * t] = make_float4(mn[0], mn[1], mn[2], mx[0]); box[2 * t + 1] = make_float4(mx[1], mx[2], 0.f, 0.f); }
+    }
+  }
   int bad = 0;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {   // ring ids outside [0, 64] (never produced by scanRegistration) also take the step-wise scan
     const int r = (int)pts[j].w;
@@ -355,6 +473,8 @@ static int odom_state(lmono_ctx* ctx, OdomState** out) {
   for (int k = 0; k < 2; ++k) { LM_CUDA(cudaMalloc((void**)&s->d_last[k], n * sizeof(float4))); LM_CUDA(cudaMalloc((void**)&s->d_best[k], n * sizeof(unsigned long long))); }
   LM_CUDA(cudaMalloc((void**)&s->d_corr, n * 10 * sizeof(int32_t)));
   LM_CUDA(cudaMalloc((void**)&s->d_ringtab, 2 * RT_STRIDE * sizeof(int32_t)));
+  s->box_stride = (int)(n / 32 + 2);
+  LM_CUDA(cudaMalloc((void**)&s->d_box, (size_t)2 * s->box_stride * 2 * sizeof(float4)));
   for (int k = 0; k < 2; ++k) LM_CUDA(cudaMalloc((void**)&s->d_frac[k], n * sizeof(float)));
   k_odom_reset<<<1, 32, 0, ctx->stream>>>(s->d, ctx->prm.distortion ? 1 : 0);
   LM_LAUNCH_CHECK();
@@ -372,7 +492,7 @@ void lm_odom_free(lmono_ctx* ctx) {
   cudaFree(s->d); cudaFreeHost(s->h);
   for (int k = 0; k < 4; ++k) cudaFree(s->d_feat[k]);
   for (int k = 0; k < 2; ++k) { cudaFree(s->d_last[k]); cudaFree(s->d_best[k]); }
-  cudaFree(s->d_corr); cudaFree(s->d_ringtab); cudaFree(s->d_frac[0]); cudaFree(s->d_frac[1]);
+  cudaFree(s->d_corr); cudaFree(s->d_ringtab); cudaFree(s->d_box); cudaFree(s->d_frac[0]); cudaFree(s->d_frac[1]);
   free(s); ctx->odom_state = nullptr;
 }
 
@@ -380,6 +500,11 @@ void lm_odom_free(lmono_ctx* ctx) {
 static int odom_associate(lmono_ctx* ctx, OdomState* s, const float4* sharp, int n_sharp, const float4* flat, int n_flat, int nl_max0, int nl_max1, int pass) {
   const int nq = n_sharp > n_flat ? n_sharp : n_flat;
   if (nq <= 0) return LMONO_OK;
+  static const bool brute = getenv("LMONO_ODOM_NN") && !strcmp(getenv("LMONO_ODOM_NN"), "brute");
+  if (!brute) {
+    LM_LAUNCH_PDL(k_odom_nn_box, lm_div_up((n_sharp + n_flat) * 32, 256), 256, 0, s->d, sharp, flat, s->d_last[0], s->d_last[1], s->d_box, s->box_stride, s->d_best[0], s->d_best[1]);
+    LM_LAUNCH_CHECK();
+  } else {
   LM_LAUNCH_PDL(k_odom_best_init, lm_div_up(nq, 256), 256, 0, s->d_best[0], n_sharp, s->d_best[1], n_flat);
   LM_LAUNCH_CHECK();
   const int nlm = nl_max0 > nl_max1 ? nl_max0 : nl_max1;
@@ -388,6 +513,7 @@ static int odom_associate(lmono_ctx* ctx, OdomState* s, const float4* sharp, int
     dim3 grid(lm_div_up(nq, NN_QB), gy < 48 ? gy : 48, 2);
     LM_LAUNCH_PDL(k_odom_nn1, grid, NN_QB * NN_SUB, 0, s->d, sharp, flat, s->d_last[0], s->d_last[1], s->d_best[0], s->d_best[1]);
     LM_LAUNCH_CHECK();
+  }
   }
   const int warps = n_sharp + n_flat;
   LM_LAUNCH_PDL(k_odom_corr, lm_div_up(warps * 32, 256), 256, 0, s->d, sharp, flat, s->d_last[0], s->d_last[1], s->d_best[0], s->d_best[1],
@@ -404,7 +530,7 @@ int lm_odom_enqueue(lmono_ctx* ctx, const float4* sharp, int n_sharp, const floa
   OdomState* s; int rc = odom_state(ctx, &s); if (rc) return rc;
   LM_LAUNCH_PDL(k_odom_begin, 1, 32, 0, s->d, n_sharp, n_ls, n_flat, n_lf, d_counts, s->cap, s->d_ringtab);
   LM_LAUNCH_CHECK();
-  LM_LAUNCH_PDL(k_odom_ring_table, dim3(RT_CTAS, 2), 256, 0, s->d, s->d_last[0], s->d_last[1], s->d_ringtab);
+  LM_LAUNCH_PDL(k_odom_ring_table, dim3(RT_CTAS, 2), 256, 0, s->d, s->d_last[0], s->d_last[1], s->d_ringtab, s->d_box, s->box_stride);
   LM_LAUNCH_CHECK();
   for (int opti = 0; opti < 2; ++opti) {                       // :278
     if ((rc = odom_associate(ctx, s, sharp, n_sharp, flat, n_flat, prev_ls_max, prev_lf_max, opti))) return rc;

@@ -298,8 +298,11 @@ constexpr int SCR_TOTAL = SCR_SEC_BYTES + SCR_XYZ_BYTES + SCR_INT_BYTES + SCR_PI
 __global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __restrict__ full, const float* __restrict__ curv,
                                                              ScanMeta* __restrict__ meta, int32_t* __restrict__ label_out,
                                                              int32_t* __restrict__ pick_idx, int32_t* __restrict__ pick_cnt,
-                                                             float4* __restrict__ lf_tmp, int32_t* __restrict__ lf_cnt) {
+                                                             float4* __restrict__ lf_tmp, int32_t* __restrict__ lf_cnt,
+                                                             unsigned long long* __restrict__ stamps) {
   lm_pdl_enter();
+#define SCR_STAMP(slot) do { if (stamps != nullptr && threadIdx.x == 0 && blockIdx.x == 32) stamps[200 + (slot)] = d_globaltimer(); } while (0)
+  SCR_STAMP(0);
   extern __shared__ __align__(16) unsigned char smem[];
   unsigned long long* sec = reinterpret_cast<unsigned long long*>(smem);
   float* xyz = reinterpret_cast<float*>(smem + SCR_SEC_BYTES);
@@ -333,6 +336,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __res
     }
   }
   __syncthreads();
+  SCR_STAMP(1);
   // the serial greedy pick below tests |p[i] - p[i-1]|^2 > 0.05 up to ten times per pick (:319-342, 365-388): the test
   // is a pure function of two neighbours, so every thread evaluates its share once here and the one picking thread only
   // reads a byte ((a - b)^2 == (b - a)^2 exactly, one array serves both walking directions)
@@ -348,6 +352,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __res
     else d_warp_sort_sector<32>(dst, curv, sp, len, lane);
   }
   __syncthreads();
+  SCR_STAMP(2);
 
   // :291-390 greedy picking.  The sectors of a ring are order dependent (suppression crosses the sector border) and so are
   // the picks inside a sector, but one pick is wide: ONE WARP walks the sorted list 32 entries at a time -- every lane
@@ -437,6 +442,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __res
     }
   }
   __syncthreads();
+  SCR_STAMP(3);
   for (int i = threadIdx.x; i < L; i += blockDim.x) label_out[rs + i] = (int)label[i];
 
   // :392-398 less-flat = every k in [sp_0, ep_5] with label <= 0, in index order
@@ -451,6 +457,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __res
     n_lf += total;
   }
   __syncthreads();
+  SCR_STAMP(4);
   if (n_lf == 0) return;
 
   // :401-405 VoxelGrid(0.2) of the ring's less-flat points (PCL arithmetic, see voxel.cu)
@@ -482,6 +489,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __res
     s_vg[5] = (dd[0] * dd[1] * dd[2] > (long long)INT32_MAX) ? 1 : 0;
   }
   __syncthreads();
+  SCR_STAMP(5);
   float4* outp = lf_tmp + rs;
   if (s_vg[5]) {                                   // PCL: leaf too small -> cloud returned unchanged
     for (int e = threadIdx.x; e < n_lf; e += blockDim.x) { const int li = lf[e]; outp[e] = make_float4(xyz[li * 3], xyz[li * 3 + 1], xyz[li * 3 + 2], inten[li]); }
@@ -491,6 +499,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __res
   if (n_lf <= SC_THREADS * 4) d_block_sort_lf<4>(sec, n_lf, xyz, lf, s_vg, inv);
   else if (n_lf <= SC_THREADS * 8) d_block_sort_lf<8>(sec, n_lf, xyz, lf, s_vg, inv);
   else d_block_sort_lf<16>(sec, n_lf, xyz, lf, s_vg, inv);
+  SCR_STAMP(6);
   int n_out = 0;
   for (int base = 0; base < n_lf; base += blockDim.x) {
     const int e = base + threadIdx.x;
@@ -514,6 +523,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __res
     n_out += total;
   }
   if (threadIdx.x == 0) lf_cnt[r] = n_out;
+  SCR_STAMP(7);
+#undef SCR_STAMP
 }
 
 __global__ void __launch_bounds__(SC_THREADS) k_scan_compact(const float4* __restrict__ full, ScanMeta* __restrict__ meta, int n_scans,
@@ -639,7 +650,7 @@ int lm_scan_enqueue(lmono_ctx* ctx, const float4* d_in, int n, bool n_on_device)
   LM_LAUNCH_PDL(k_scan_blockscan, 64, 1024, 0, s->d_block_hist, s->d_block_off, nb, s->d_meta); LM_LAUNCH_CHECK();
   LM_LAUNCH_PDL(k_scan_scatter, nb, SC_THREADS, 0, d_in, n, n_scans, s->d_key, s->d_block_off, nb, s->d_meta, s->d_full, s->d_src); LM_LAUNCH_CHECK();
   LM_LAUNCH_PDL(k_scan_curvature, nb, SC_THREADS, 0, s->d_full, s->d_meta, s->d_curv, s->d_label); LM_LAUNCH_CHECK();
-  LM_LAUNCH_PDL(k_scan_ring, n_scans, SC_THREADS, SCR_TOTAL, s->d_full, s->d_curv, s->d_meta, s->d_label, s->d_pick_idx, s->d_pick_cnt, s->d_lf_tmp, s->d_lf_cnt); LM_LAUNCH_CHECK();
+  LM_LAUNCH_PDL(k_scan_ring, n_scans, SC_THREADS, SCR_TOTAL, s->d_full, s->d_curv, s->d_meta, s->d_label, s->d_pick_idx, s->d_pick_cnt, s->d_lf_tmp, s->d_lf_cnt, ctx->d_stamps); LM_LAUNCH_CHECK();
   LM_LAUNCH_PDL(k_scan_compact, n_scans + 16, SC_THREADS, 0, s->d_full, s->d_meta, n_scans, s->d_pick_idx, s->d_pick_cnt, s->d_lf_tmp, s->d_lf_cnt,
                                                               s->d_out[0], s->d_out[1], s->d_out[2], s->d_out[3]); LM_LAUNCH_CHECK();
   return LMONO_OK;

@@ -48,12 +48,18 @@ __global__ void __launch_bounds__(ST_THREADS) k_sort_tiles(LmSortSegs sg, int ds
 // branch-free binary searches, four of them interleaved so their loads overlap.
 constexpr int LM_MERGE_GROUP = 16;
 
-__global__ void __launch_bounds__(256) k_merge_ranks(LmSortSegs sg, int run, int src_is_tmp) {
+__global__ void __launch_bounds__(256) k_merge_ranks(LmSortSegs sg, int run, int src_is_tmp, const int32_t* __restrict__ done, int pass) {
   lm_pdl_enter();
   const int seg = blockIdx.y;
   const int n = *sg.n[seg];
   const unsigned long long* __restrict__ src = (src_is_tmp ? sg.tmp : sg.out) + sg.off[seg];
   unsigned long long* __restrict__ dst = (src_is_tmp ? sg.out : sg.tmp) + sg.off[seg];
+  if (done && done[seg]) {
+    // the segment turned out small enough for the single shared-memory pass (k_merge_ranks_smem below), which left the
+    // sorted keys where pass 0 would have: pass 0 has nothing to do, the later passes only carry them to the next buffer
+    if (pass > 0) for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) dst[e] = src[e];
+    return;
+  }
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
     const unsigned long long key = src[e];
     const int my_run = e / run;
@@ -88,15 +94,23 @@ __global__ void __launch_bounds__(256) k_merge_ranks(LmSortSegs sg, int run, int
 // accesses per key is what the global-memory searches cost (~0.15 us each on B200), so each CTA first copies
 // ALL runs of its segment into shared memory (<= 12 x 16 KB, coalesced, one L2 pass) and ranks its 1024 keys
 // against them there (~30-cycle accesses).
-constexpr int LM_MERGE_SMEM_RUNS = 24;
+constexpr int LM_MERGE_SMEM_RUNS = 28;            // 28 x 8 KB = 224 KB of the 227 KB a CTA may have
 constexpr int MS_THREADS = 1024;
 
-__global__ void __launch_bounds__(MS_THREADS, 1) k_merge_ranks_smem(LmSortSegs sg, int src_is_tmp) {
+// `done` != NULL: the launch grids were sized for a bound far above the real count (the fused sweep only knows the raw
+// sweep size): the kernel decides on the device whether the segment fits this path and tells the global-memory passes
+// that follow (k_merge_ranks) through done[seg].
+__global__ void __launch_bounds__(MS_THREADS, 1) k_merge_ranks_smem(LmSortSegs sg, int src_is_tmp, int32_t* __restrict__ done) {
   lm_pdl_enter();
   extern __shared__ unsigned long long s_runs[];        // [nruns][LM_SORT_TILE]
   const int seg = blockIdx.y;
   const int n = *sg.n[seg];
   const int e0 = blockIdx.x * MS_THREADS;
+  if (done) {
+    const bool fits = n <= LM_MERGE_SMEM_RUNS * LM_SORT_TILE;
+    if (blockIdx.x == 0 && threadIdx.x == 0) done[seg] = fits ? 1 : 0;
+    if (!fits) return;
+  }
   if (e0 >= n) return;
   const unsigned long long* __restrict__ src = (src_is_tmp ? sg.tmp : sg.out) + sg.off[seg];
   unsigned long long* __restrict__ dst = (src_is_tmp ? sg.out : sg.tmp) + sg.off[seg];
@@ -152,7 +166,7 @@ int lm_sort_u64_segs(lmono_ctx* ctx, const LmSortSegs& sg, int nseg, const int* 
   if (ntiles > 1 && ntiles <= LM_MERGE_SMEM_RUNS) {
     LM_LAUNCH_PDL(k_sort_tiles, dim3(ntiles, nseg), ST_THREADS, 0, sg, 1);
     LM_LAUNCH_CHECK();
-    LM_LAUNCH_PDL(k_merge_ranks_smem, dim3(lm_div_up(mx, MS_THREADS), nseg), MS_THREADS, (size_t)ntiles * LM_SORT_TILE * 8, sg, 1);
+    LM_LAUNCH_PDL(k_merge_ranks_smem, dim3(lm_div_up(mx, MS_THREADS), nseg), MS_THREADS, (size_t)ntiles * LM_SORT_TILE * 8, sg, 1, (int32_t*)nullptr);
     LM_LAUNCH_CHECK();
     return LMONO_OK;
   }
@@ -161,9 +175,18 @@ int lm_sort_u64_segs(lmono_ctx* ctx, const LmSortSegs& sg, int nseg, const int* 
   int cur_is_tmp = (passes & 1) ? 1 : 0;
   LM_LAUNCH_PDL(k_sort_tiles, dim3(ntiles, nseg), ST_THREADS, 0, sg, cur_is_tmp);
   LM_LAUNCH_CHECK();
+  // per-sweep sorts whose grids are sized for a loose bound: try the single shared-memory pass first (decided on the
+  // device from the real count); the global passes then skip / copy.  The map import (millions of keys) goes straight
+  // to the global passes.
+  int32_t* done = nullptr;
+  if (passes >= 1 && mx <= 262144) {
+    done = ctx->d_sort_done;
+    LM_LAUNCH_PDL(k_merge_ranks_smem, dim3(LM_MERGE_SMEM_RUNS, nseg), MS_THREADS, (size_t)LM_MERGE_SMEM_RUNS * LM_SORT_TILE * 8, sg, cur_is_tmp, done);
+    LM_LAUNCH_CHECK();
+  }
   long long run = LM_SORT_TILE;
   for (int p = 0; p < passes; ++p, run *= LM_MERGE_GROUP) {
-    LM_LAUNCH_PDL(k_merge_ranks, dim3(lm_div_up(mx, 256), nseg), 256, 0, sg, (int)run, cur_is_tmp);
+    LM_LAUNCH_PDL(k_merge_ranks, dim3(lm_div_up(mx, 256), nseg), 256, 0, sg, (int)run, cur_is_tmp, (const int32_t*)done, p);
     LM_LAUNCH_CHECK();
     cur_is_tmp ^= 1;
   }

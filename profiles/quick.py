@@ -61,6 +61,14 @@ if "single" in parts:
     ms = np.array([a.elapsed_time(b) for a, b in zip(e0, e1)])
     q, t, rep = ctx.map_collect()
     P(f"single sequence: {1e3 * ms.mean():.1f} us per registration (median {1e3 * np.median(ms):.1f}), launches/step {ctx.launch_count()}")
+    if hasattr(ctx.L, "lmono_debug_rf_meta"):
+        mo = (C.c_int32 * (2 * 75 * 8))()
+        ctx.L.lmono_debug_rf_meta(ctx._h, mo, 2 * 75 * 8)
+        m_ = np.array(mo[:], dtype=np.int64).reshape(150, 8)
+        act = m_[m_[:, 0] == 1]
+        newv = act[:, 1] - act[:, 2]
+        P(f"   refilter of the last step: {len(act)} slabs with a tail, {int((newv == 0).sum())} of them without a new voxel; points in those slabs {int(act[:, 2].sum())} "
+          f"(in slabs without a new voxel {int(act[newv == 0, 2].sum())}), tail points {int(act[:, 3].sum())}, new voxels {int(newv.sum())}")
 
 if "batch" in parts:
     batch = api.SequenceBatch(ctxs)
@@ -132,6 +140,11 @@ if "sweep" in parts:
     ms = np.array(ms[4:])
     P(f"--- fused sweep (map grown from empty): scanRegistration {1e3 * ms[:, 0].mean():.0f} us, odometry {1e3 * ms[:, 1].mean():.0f} us, "
       f"mapping {1e3 * ms[:, 2].mean():.0f} us device; wall {1e3 * np.mean(wall[4:]):.3f} ms per sweep")
+    o = (C.c_uint64 * 256)()
+    pctx.L.lmono_debug_stamps(pctx._h, o, 256)
+    a = np.array(o[200:208], dtype=np.int64)
+    P("   k_scan_ring (ring 32) ns: load %d, sector sorts %d, greedy pick %d, labels + less-flat list %d, voxel bounds %d, voxel sort %d, centroids %d; total %d"
+      % tuple(list(np.diff(a)) + [a[7] - a[0]]))
     pctx.kernel_marks_enable(True)
     for raw in raws[:8]:
         pctx.sweep_step(raw)
