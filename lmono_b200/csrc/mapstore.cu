@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(RF_TS_THREADS) k_rf_tailscan(LmMapState* __res
                                                                int nvx_stride, int32_t* __restrict__ work_n, int32_t* __restrict__ work, int inplace) {
   lm_pdl_enter();
   __shared__ int ws[33];
-  __shared__ int s_wbase, s_fallback, s_badkey;
+  __shared__ int s_wbase, s_mover, s_badkey;
   const int na = plan[LM_PLAN_ACTIVE_N];
   for (int a = blockIdx.x; a < na; a += gridDim.x) {
     const int e = plan[LM_PLAN_ACTIVE + a];
@@ -521,18 +521,21 @@ __global__ void __launch_bounds__(RF_TS_THREADS) k_rf_tailscan(LmMapState* __res
       carry += tot;
     }
     // ---- no new voxel in this cube (the usual case once an area is mapped): VoxelGrid(prefix ++ tail) leaves every
-    // point where it is and only moves the centroids of the voxels the tail hits.  They are updated IN PLACE -- in the
-    // canonical buffer and in the cell-sorted copy -- instead of rewriting the whole slab (points, keys, cell table,
-    // cell-sorted copy: ~60 B per stored point) through merge / scan / scatter.  Same summation order as k_rf_merge
-    // (prefix point, then the tail members in arrival order, one division), so the bits are the same.  A centroid that
-    // changes its 2 m search cell would have to move inside the cell-sorted copy: such a cube takes the merge path.
+    // point where it is and only moves the centroids of the voxels the tail hits.  They are updated IN PLACE instead of
+    // rewriting the whole slab (points, keys, cell table, cell-sorted copy: ~70 B per stored point) through merge / scan /
+    // scatter.  Same summation order as k_rf_merge (prefix point, then the tail members in arrival order, one division),
+    // so the bits are the same.  The cell-sorted copy is patched too (the entry is looked up in its 2 m cell) unless some
+    // centroid changed its cell (a 0.8 m surf voxel can straddle a cell border): then the copy stays stale, the slab
+    // stays `dirty`, and k_index_build rebuilds that cube's index at the start of the next step -- beside the feature
+    // VoxelGrid, off the critical path -- as it does for imported cubes.
     if (inplace && carry == 0 && nt > 0) {
       float4* pts = M.pts + ((size_t)sid * 2 + meta->cur) * M.cap;
       const int g3[3] = { M.slab_g[sid * 4], M.slab_g[sid * 4 + 1], M.slab_g[sid * 4 + 2] };
       const float il = M.inv_leaf;
-      if (threadIdx.x == 0) { s_fallback = 0; s_badkey = 0; }
+      if (threadIdx.x == 0) { s_mover = 0; s_badkey = 0; }
       __syncthreads();
       for (int phase = 0; phase < 2; ++phase) {
+        const bool patch = phase == 1 && !s_mover;
         for (int j = threadIdx.x; j < nt; j += blockDim.x) {
           const uint32_t key = tkey[j];
           if (j > 0 && tkey[j - 1] == key) continue;           // not a run head
@@ -549,40 +552,37 @@ __global__ void __launch_bounds__(RF_TS_THREADS) k_rf_tailscan(LmMapState* __res
           const float4 pn = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), __fdiv_rn(si, c));
           const int cell = d_cube_cell(po, g3);
           if (phase == 0) {
-            if (cell < 0 || d_cube_cell(pn, g3) != cell) s_fallback = 1;
+            if (cell < 0 || d_cube_cell(pn, g3) != cell) s_mover = 1;
             if (d_cube_voxel_key(pn, il, g3) != key) s_badkey = 1;          // the centroid left its voxel: re-voxelise the cube as a whole next time
-          } else {
-            pts[lb] = pn;
-            float4* cp = M.cellpts + (size_t)sid * M.cap;
-            const uint32_t* cs = M.cellstart + (size_t)sid * (LM_NCELL + 1) + cell;
-            const int cb = (int)cs[0], ce = (int)cs[1];
-            bool found = false;
-            for (int q0 = cb; q0 < ce && !found; q0 += 4) {    // the cell holds this point exactly once
-              float w[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) w[u] = q0 + u < ce ? cp[q0 + u].w : __int_as_float(-1);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) if (__float_as_int(w[u]) == lb) { cp[q0 + u] = make_float4(pn.x, pn.y, pn.z, w[u]); found = true; }
-            }
-            if (!found) atomicOr(&st->fault, LM_FAULT_CELL_RANGE);      // the search index did not cover the prefix (internal error)
+            continue;
           }
+          pts[lb] = pn;
+          if (!patch) continue;
+          float4* cp = M.cellpts + (size_t)sid * M.cap;
+          const uint32_t* cs = M.cellstart + (size_t)sid * (LM_NCELL + 1) + cell;
+          const int cb = (int)cs[0], ce = (int)cs[1];
+          bool found = false;
+          for (int q0 = cb; q0 < ce && !found; q0 += 4) {      // the cell holds this point exactly once
+            float w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) w[u] = q0 + u < ce ? cp[q0 + u].w : __int_as_float(-1);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (__float_as_int(w[u]) == lb) { cp[q0 + u] = make_float4(pn.x, pn.y, pn.z, w[u]); found = true; }
+          }
+          if (!found) atomicOr(&st->fault, LM_FAULT_CELL_RANGE);      // the search index did not cover the prefix (internal error)
         }
         __syncthreads();
-        if (s_fallback) break;
       }
-      if (!s_fallback) {
-        if (threadIdx.x == 0) {
-          M.slab_n[sid] = ns;
-          M.slab_nsorted[sid] = s_badkey ? 0 : ns;
-          M.slab_unsorted[sid] = s_badkey ? 1 : 0;
-          M.slab_dirty[sid] = 0;
-          meta->active = 2;                                    // done: k_rf_scan skips it, no merge chunks
-          meta->total_new = ns;
-        }
-        __syncthreads();
-        continue;
+      if (threadIdx.x == 0) {
+        M.slab_n[sid] = ns;
+        M.slab_nsorted[sid] = s_badkey ? 0 : ns;
+        M.slab_unsorted[sid] = s_badkey ? 1 : 0;
+        M.slab_dirty[sid] = s_mover ? 1 : 0;
+        meta->active = s_mover ? 3 : 2;                        // done: k_rf_scan skips it, no merge chunks (3: index rebuild pending)
+        meta->total_new = ns;
       }
       __syncthreads();
+      continue;
     }
     int4* cc4 = reinterpret_cast<int4*>(M.cellcount + (size_t)sid * LM_NCELL);       // LM_NCELL % 4 == 0, slabs 16 B aligned
     for (int c = threadIdx.x; c < LM_NCELL / 4; c += blockDim.x) cc4[c] = make_int4(0, 0, 0, 0);

@@ -159,53 +159,49 @@ __device__ __forceinline__ unsigned long long d_nn_point_key(float4 sel, float4 
 }
 __device__ __forceinline__ unsigned long long d_warp_min_u64(unsigned long long v);
 
-constexpr int NB_LIST = 64;       // tiles a warp collects before it scans them (four coalesced loads in flight per step)
+constexpr int NB_LIST = 64;       // tiles a warp collects before it scans them (eight coalesced loads in flight per step)
+constexpr int NB_CHUNK = 1024;    // tiles (32 768 points) whose boxes a CTA stages in shared memory per outer trip
 __device__ __forceinline__ unsigned long long d_nn_scan_list(const float4* __restrict__ last, int nl, float4 sel, const unsigned short* list, int cnt,
                                                              int tile0, int lane, unsigned long long bestk) {
-  for (int i = 0; i < cnt; i += 4) {
-    int j[4]; float4 p[4];
+  for (int i = 0; i < cnt; i += 8) {
+    int j[8]; float4 p[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { j[u] = i + u < cnt ? (tile0 + (int)list[i + u]) * 32 + lane : nl; if (j[u] < nl) p[u] = last[j[u]]; }
+    for (int u = 0; u < 8; ++u) { j[u] = i + u < cnt ? (tile0 + (int)list[i + u]) * 32 + lane : nl; if (j[u] < nl) p[u] = last[j[u]]; }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) if (j[u] < nl) { const unsigned long long k = d_nn_point_key(sel, p[u], j[u]); bestk = k < bestk ? k : bestk; }
+    for (int u = 0; u < 8; ++u) if (j[u] < nl) { const unsigned long long k = d_nn_point_key(sel, p[u], j[u]); bestk = k < bestk ? k : bestk; }
   }
   return d_warp_min_u64(bestk);
 }
 
-__global__ void __launch_bounds__(256, 2) k_odom_nn_box(const OdomDev* __restrict__ o, const float4* __restrict__ sharp, const float4* __restrict__ flat,
-                                                     const float4* __restrict__ corner_last, const float4* __restrict__ surf_last,
-                                                     const float4* __restrict__ box_all, int box_stride,
-                                                     unsigned long long* __restrict__ best0, unsigned long long* __restrict__ best1) {
+// flat features against surf_last (the corner cloud is sparse along its rings -- its tiles are long arcs with useless
+// boxes -- and small: it keeps the brute-force kernel)
+__global__ void __launch_bounds__(256, 2) k_odom_nn_box(const OdomDev* __restrict__ o, const float4* __restrict__ flat, const float4* __restrict__ surf_last,
+                                                        const float4* __restrict__ box, unsigned long long* __restrict__ best) {
   lm_pdl_enter();
+  __shared__ float4 s_b0[NB_CHUNK], s_b1[NB_CHUNK];
   __shared__ unsigned short s_list[8][NB_LIST];
   if (!o->do_solve) return;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  const int ns = o->n_sharp, nf = o->n_flat;
-  if (warp >= ns + nf) return;
-  const bool is_corner = warp < ns;
-  const int qi = is_corner ? warp : warp - ns;
-  const float4* __restrict__ last = is_corner ? corner_last : surf_last;
-  const int nl = is_corner ? o->n_corner_last : o->n_surf_last;
-  unsigned long long* __restrict__ best = is_corner ? best0 : best1;
-  if (nl <= 0) { if (lane == 0) best[qi] = ~0ULL; return; }
-  const float4 sel = d_to_start(o, is_corner ? sharp[qi] : flat[qi]);
-  const float4* __restrict__ box = box_all + (size_t)(is_corner ? 0 : 1) * box_stride * 2;
+  const int nf = o->n_flat, nl = o->n_surf_last;
+  if ((int)(blockIdx.x * blockDim.x) >> 5 >= nf) return;          // CTA-uniform
+  const bool active = warp < nf;
+  const int qi = active ? warp : 0;
+  if (nl <= 0) { if (active && lane == 0) best[qi] = ~0ULL; return; }
+  const float4* __restrict__ last = surf_last;
+  const float4 sel = d_to_start(o, flat[qi]);
   const int ntile = (nl + 31) >> 5;
   unsigned short* list = s_list[threadIdx.x >> 5];
   unsigned long long bestk = ~0ULL;
-  // 1024 tiles (32 768 points) per outer trip: lane l keeps the bounds of tiles l, l + 32, ... in registers
-  for (int tile0 = 0; tile0 < ntile; tile0 += 1024) {
-    uint32_t lbs[32];
+  for (int tile0 = 0; tile0 < ntile; tile0 += NB_CHUNK) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < NB_CHUNK && tile0 + t < ntile; t += blockDim.x) { s_b0[t] = box[2 * (tile0 + t)]; s_b1[t] = box[2 * (tile0 + t) + 1]; }
+    __syncthreads();
+    if (!active) continue;
+    uint32_t lbs[32];                                 // lane l keeps the bounds of tiles l, l + 32, ... of this chunk
 #pragma unroll
-    for (int k0 = 0; k0 < 32; k0 += 4) {             // four tiles' boxes (eight independent loads) in flight
-      float4 b0[4], b1[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { const int t = tile0 + (k0 + u) * 32 + lane; if (t < ntile) { b0[u] = box[2 * t]; b1[u] = box[2 * t + 1]; } }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { const int t = tile0 + (k0 + u) * 32 + lane; lbs[k0 + u] = t < ntile ? __float_as_uint(d_box_lb(b0[u], b1[u], sel)) : 0xffffffffu; }
-    }
-    if (tile0 == 0) {                                // seed: the tile with the smallest bound
+    for (int k = 0; k < 32; ++k) { const int t = k * 32 + lane; lbs[k] = tile0 + t < ntile ? __float_as_uint(d_box_lb(s_b0[t], s_b1[t], sel)) : 0xffffffffu; }
+    if (tile0 == 0) {                                 // seed: the tile with the smallest bound
       unsigned long long seedk = ~0ULL;
 #pragma unroll
       for (int k = 0; k < 32; ++k) { const unsigned long long v = ((unsigned long long)lbs[k] << 32) | (uint32_t)(k * 32 + lane); seedk = v < seedk ? v : seedk; }
@@ -217,10 +213,10 @@ __global__ void __launch_bounds__(256, 2) k_odom_nn_box(const OdomDev* __restric
     int cnt = 0;
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
-      if (tile0 + k * 32 >= ntile) break;            // warp-uniform
+      if (tile0 + k * 32 >= ntile) break;             // warp-uniform
       unsigned m = __ballot_sync(0xffffffffu, lbs[k] <= (uint32_t)(bestk >> 32));
       if (!m) continue;
-      if (cnt + __popc(m) > NB_LIST) {               // list full: scan what is collected, the tighter bound prunes the rest
+      if (cnt + __popc(m) > NB_LIST) {                // list full: scan what is collected, the tighter bound prunes the rest
         __syncwarp();
         bestk = d_nn_scan_list(last, nl, sel, list, cnt, tile0, lane, bestk);
         cnt = 0;
@@ -233,7 +229,7 @@ __global__ void __launch_bounds__(256, 2) k_odom_nn_box(const OdomDev* __restric
     bestk = d_nn_scan_list(last, nl, sel, list, cnt, tile0, lane, bestk);
     __syncwarp();
   }
-  if (lane == 0) best[qi] = bestk;
+  if (active && lane == 0) best[qi] = bestk;
 }
 
 __device__ __forceinline__ float d_sqdis(float4 a, float4 sel) {
@@ -501,19 +497,20 @@ static int odom_associate(lmono_ctx* ctx, OdomState* s, const float4* sharp, int
   const int nq = n_sharp > n_flat ? n_sharp : n_flat;
   if (nq <= 0) return LMONO_OK;
   static const bool brute = getenv("LMONO_ODOM_NN") && !strcmp(getenv("LMONO_ODOM_NN"), "brute");
-  if (!brute) {
-    LM_LAUNCH_PDL(k_odom_nn_box, lm_div_up((n_sharp + n_flat) * 32, 256), 256, 0, s->d, sharp, flat, s->d_last[0], s->d_last[1], s->d_box, s->box_stride, s->d_best[0], s->d_best[1]);
-    LM_LAUNCH_CHECK();
-  } else {
-  LM_LAUNCH_PDL(k_odom_best_init, lm_div_up(nq, 256), 256, 0, s->d_best[0], n_sharp, s->d_best[1], n_flat);
+  // corner features: tiled brute force (blockIdx.z = 0 only); flat features: box-pruned search unless LMONO_ODOM_NN=brute
+  LM_LAUNCH_PDL(k_odom_best_init, lm_div_up(nq, 256), 256, 0, s->d_best[0], n_sharp, s->d_best[1], brute ? n_flat : 0);
   LM_LAUNCH_CHECK();
-  const int nlm = nl_max0 > nl_max1 ? nl_max0 : nl_max1;
-  if (nlm > 0) {
+  const int nlm = brute ? (nl_max0 > nl_max1 ? nl_max0 : nl_max1) : nl_max0;
+  const int nqb = brute ? nq : n_sharp;
+  if (nlm > 0 && nqb > 0) {
     const int gy = lm_div_up(nlm, NN_CHUNK);
-    dim3 grid(lm_div_up(nq, NN_QB), gy < 48 ? gy : 48, 2);
+    dim3 grid(lm_div_up(nqb, NN_QB), gy < 48 ? gy : 48, brute ? 2 : 1);
     LM_LAUNCH_PDL(k_odom_nn1, grid, NN_QB * NN_SUB, 0, s->d, sharp, flat, s->d_last[0], s->d_last[1], s->d_best[0], s->d_best[1]);
     LM_LAUNCH_CHECK();
   }
+  if (!brute && n_flat > 0) {
+    LM_LAUNCH_PDL(k_odom_nn_box, lm_div_up(n_flat * 32, 256), 256, 0, s->d, flat, s->d_last[1], s->d_box + (size_t)s->box_stride * 2, s->d_best[1]);
+    LM_LAUNCH_CHECK();
   }
   const int warps = n_sharp + n_flat;
   LM_LAUNCH_PDL(k_odom_corr, lm_div_up(warps * 32, 256), 256, 0, s->d, sharp, flat, s->d_last[0], s->d_last[1], s->d_best[0], s->d_best[1],

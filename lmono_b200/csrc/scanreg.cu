@@ -242,17 +242,32 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_curvature(const float4* __r
 }
 
 // ---------------------------------------------------------------------------------------------
+constexpr int SCR_THREADS = 1024;          // k_scan_ring: one CTA per ring; the two sorts are block-wide networks with 2 (4) keys per thread
+// :284-288 the six sector sorts of a ring as ONE block-wide bitonic network over the composite key
+// sector (3 bits) | curvature bits (32) | local index (12): ascending (curvature, index) inside each sector, the sectors one
+// behind the other.  (One warp per sector with 16 keys per lane took 12 us of a 73 us kernel; 1024 threads with two keys
+// each run the same 66 stages in ~2 us.)
 template <int ITEMS>
-__device__ __forceinline__ void d_warp_sort_sector(unsigned long long* dst, const float* __restrict__ curv, int sp, int len, int lane) {
+__device__ __forceinline__ void d_block_sort_sectors(unsigned long long* xch, const float* __restrict__ curv, int rs, int S, int E) {
   unsigned long long v[ITEMS];
+  const int n = E - S;
 #pragma unroll
   for (int r = 0; r < ITEMS; ++r) {
-    const int e = lane * ITEMS + r;
-    v[r] = e < len ? (((unsigned long long)__float_as_uint(curv[sp + e]) << 32) | (uint32_t)(sp + e)) : ~0ULL;
+    const int e = threadIdx.x * ITEMS + r;
+    unsigned long long c = ~0ULL;
+    if (e < n) {
+      // sector j holds [S + n j / 6, S + n (j + 1) / 6): the largest j with S + n j / 6 <= S + e
+      int j = (int)(((long long)e * 6 + 5) / n);
+      while (j > 0 && (long long)n * j / 6 > e) --j;
+      while (j < 5 && (long long)n * (j + 1) / 6 <= e) ++j;
+      c = ((unsigned long long)j << 44) | ((unsigned long long)__float_as_uint(curv[S + e]) << 12) | (unsigned long long)(S + e - rs);
+    }
+    v[r] = c;
   }
-  d_bitonic_regs<ITEMS, 32>(v, lane, nullptr);
+  d_bitonic_regs<ITEMS, SCR_THREADS>(v, threadIdx.x, xch);
 #pragma unroll
-  for (int r = 0; r < ITEMS; ++r) dst[lane * ITEMS + r] = v[r];
+  for (int r = 0; r < ITEMS; ++r) xch[threadIdx.x * ITEMS + r] = v[r];
+  __syncthreads();
 }
 
 __device__ __forceinline__ bool d_gap_exceeds(const float* xyz, int a, int b) {
@@ -279,7 +294,7 @@ __device__ __forceinline__ void d_block_sort_lf(unsigned long long* xch, int n, 
     }
     v[r] = c;
   }
-  d_bitonic_regs<ITEMS, SC_THREADS>(v, threadIdx.x, xch);
+  d_bitonic_regs<ITEMS, SCR_THREADS>(v, threadIdx.x, xch);
 #pragma unroll
   for (int r = 0; r < ITEMS; ++r) xch[threadIdx.x * ITEMS + r] = v[r];
   __syncthreads();
@@ -295,7 +310,7 @@ constexpr int SCR_LF_BYTES = SC_RING_MAX * 2;                         // less-fl
 constexpr int SCR_GAP_BYTES = SC_RING_MAX;                            // gap[i] = |p[i] - p[i-1]|^2 > 0.05 (the +-5 suppression test), precomputed in parallel
 constexpr int SCR_TOTAL = SCR_SEC_BYTES + SCR_XYZ_BYTES + SCR_INT_BYTES + SCR_PICK_BYTES + SCR_LABEL_BYTES + SCR_LF_BYTES + 256 + SCR_GAP_BYTES;
 
-__global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __restrict__ full, const float* __restrict__ curv,
+__global__ void __launch_bounds__(SCR_THREADS, 1) k_scan_ring(const float4* __restrict__ full, const float* __restrict__ curv,
                                                              ScanMeta* __restrict__ meta, int32_t* __restrict__ label_out,
                                                              int32_t* __restrict__ pick_idx, int32_t* __restrict__ pick_cnt,
                                                              float4* __restrict__ lf_tmp, int32_t* __restrict__ lf_cnt,
@@ -313,7 +328,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __res
   int* ws = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(lf) + SCR_LF_BYTES);     // [64]
   unsigned char* gap = reinterpret_cast<unsigned char*>(ws) + 256;                            // [SC_RING_MAX]
   __shared__ int s_vg[8];
-  __shared__ float s_mn[3][SC_THREADS / 32], s_mx[3][SC_THREADS / 32];
+  __shared__ float s_mn[3][SCR_THREADS / 32], s_mx[3][SCR_THREADS / 32];
 
   const int r = blockIdx.x;
   const int rs = meta->ring_start[r], re = meta->ring_start[r + 1];
@@ -325,13 +340,13 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __res
   if (L > SC_RING_MAX) { if (threadIdx.x == 0) atomicOr(&meta->fault, 1u); return; }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
-  for (int i0 = threadIdx.x; i0 < L; i0 += 4 * SC_THREADS) {      // four loads in flight per thread, then the shared-memory stores
+  for (int i0 = threadIdx.x; i0 < L; i0 += 4 * SCR_THREADS) {      // four loads in flight per thread, then the shared-memory stores
     float4 p[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { const int i = i0 + u * SC_THREADS; if (i < L) p[u] = full[rs + i]; }
+    for (int u = 0; u < 4; ++u) { const int i = i0 + u * SCR_THREADS; if (i < L) p[u] = full[rs + i]; }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * SC_THREADS;
+      const int i = i0 + u * SCR_THREADS;
       if (i < L) { xyz[i * 3] = p[u].x; xyz[i * 3 + 1] = p[u].y; xyz[i * 3 + 2] = p[u].z; inten[i] = p[u].w; picked[i] = 0; label[i] = 0; }
     }
   }
@@ -341,17 +356,10 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __res
   // is a pure function of two neighbours, so every thread evaluates its share once here and the one picking thread only
   // reads a byte ((a - b)^2 == (b - a)^2 exactly, one array serves both walking directions)
   for (int i = threadIdx.x; i < L; i += blockDim.x) gap[i] = (i > 0 && d_gap_exceeds(xyz, i, i - 1)) ? 1 : 0;
-  // :284-288 six sector sorts, one warp each, (curvature, index) ascending
-  if (wid < 6) {
-    const int sp = S + (E - S) * wid / 6, ep = S + (E - S) * (wid + 1) / 6 - 1;
-    const int len = ep - sp + 1;
-    unsigned long long* dst = sec + wid * SC_SECTOR_MAX;
-    if (len > SC_SECTOR_MAX) { if (lane == 0) atomicOr(&meta->fault, 2u); }
-    else if (len <= 256) d_warp_sort_sector<8>(dst, curv, sp, len, lane);
-    else if (len <= 512) d_warp_sort_sector<16>(dst, curv, sp, len, lane);
-    else d_warp_sort_sector<32>(dst, curv, sp, len, lane);
-  }
   __syncthreads();
+  // :284-288 six sector sorts, (curvature, index) ascending: one block-wide network
+  if (E - S <= 2 * SCR_THREADS) d_block_sort_sectors<2>(sec, curv, rs, S, E);
+  else d_block_sort_sectors<4>(sec, curv, rs, S, E);
   SCR_STAMP(2);
 
   // :291-390 greedy picking.  The sectors of a ring are order dependent (suppression crosses the sector border) and so are
@@ -364,8 +372,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __res
     for (int j = 0; j < 6; ++j) {
       const int sp = S + (E - S) * j / 6, ep = S + (E - S) * (j + 1) / 6 - 1;
       const int len = ep - sp + 1;
-      if (len > SC_SECTOR_MAX) continue;
-      const unsigned long long* sk = sec + j * SC_SECTOR_MAX;
+      const unsigned long long* sk = sec + (sp - S);             // the sectors lie one behind the other in the sorted array
       int* out = pick_idx + (r * 6 + j) * SC_PICK_STRIDE;
       int n_sharp = 0, n_ls = 0, n_flat = 0;
       int largest = 0;
@@ -373,8 +380,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __res
       for (int k_hi = len - 1; k_hi >= 0 && !done; k_hi -= 32) {          // descending curvature
         const int k = k_hi - lane;
         const unsigned long long c = k >= 0 ? sk[k] : 0ull;
-        const bool qual = k >= 0 && (double)__uint_as_float((uint32_t)(c >> 32)) > 0.1;
-        const int li = (int)(uint32_t)c - rs;
+        const bool qual = k >= 0 && (double)__uint_as_float((uint32_t)(c >> 12)) > 0.1;
+        const int li = (int)(c & 0xfffull);
         const unsigned qm = __ballot_sync(0xffffffffu, qual);
         const int nvalid = qm == 0xffffffffu ? 32 : __ffs(~qm) - 1;      // sorted: nothing behind the first non-qualifying entry qualifies
         unsigned live = nvalid == 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
@@ -410,8 +417,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __res
       for (int k_lo = 0; k_lo < len && !done; k_lo += 32) {               // ascending curvature
         const int k = k_lo + lane;
         const unsigned long long c = k < len ? sk[k] : 0ull;
-        const bool qual = k < len && (double)__uint_as_float((uint32_t)(c >> 32)) < 0.1;
-        const int li = (int)(uint32_t)c - rs;
+        const bool qual = k < len && (double)__uint_as_float((uint32_t)(c >> 12)) < 0.1;
+        const int li = (int)(c & 0xfffull);
         const unsigned qm = __ballot_sync(0xffffffffu, qual);
         const int nvalid = qm == 0xffffffffu ? 32 : __ffs(~qm) - 1;
         unsigned live = nvalid == 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
@@ -479,7 +486,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __res
     long long dd[3]; int minb[3], divb[3];
     for (int d = 0; d < 3; ++d) {
       float a = s_mn[d][0], b = s_mx[d][0];
-      for (int w = 1; w < SC_THREADS / 32; ++w) { a = fminf(a, s_mn[d][w]); b = fmaxf(b, s_mx[d][w]); }
+      for (int w = 1; w < SCR_THREADS / 32; ++w) { a = fminf(a, s_mn[d][w]); b = fmaxf(b, s_mx[d][w]); }
       dd[d] = (long long)(__fmul_rn(__fsub_rn(b, a), inv)) + 1;
       minb[d] = (int)floorf(__fmul_rn(a, inv));
       divb[d] = (int)floorf(__fmul_rn(b, inv)) - minb[d] + 1;
@@ -496,9 +503,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) k_scan_ring(const float4* __res
     if (threadIdx.x == 0) lf_cnt[r] = n_lf;
     return;
   }
-  if (n_lf <= SC_THREADS * 4) d_block_sort_lf<4>(sec, n_lf, xyz, lf, s_vg, inv);
-  else if (n_lf <= SC_THREADS * 8) d_block_sort_lf<8>(sec, n_lf, xyz, lf, s_vg, inv);
-  else d_block_sort_lf<16>(sec, n_lf, xyz, lf, s_vg, inv);
+  if (n_lf <= SCR_THREADS * 2) d_block_sort_lf<2>(sec, n_lf, xyz, lf, s_vg, inv);
+  else d_block_sort_lf<4>(sec, n_lf, xyz, lf, s_vg, inv);
   SCR_STAMP(6);
   int n_out = 0;
   for (int base = 0; base < n_lf; base += blockDim.x) {
@@ -650,7 +656,7 @@ int lm_scan_enqueue(lmono_ctx* ctx, const float4* d_in, int n, bool n_on_device)
   LM_LAUNCH_PDL(k_scan_blockscan, 64, 1024, 0, s->d_block_hist, s->d_block_off, nb, s->d_meta); LM_LAUNCH_CHECK();
   LM_LAUNCH_PDL(k_scan_scatter, nb, SC_THREADS, 0, d_in, n, n_scans, s->d_key, s->d_block_off, nb, s->d_meta, s->d_full, s->d_src); LM_LAUNCH_CHECK();
   LM_LAUNCH_PDL(k_scan_curvature, nb, SC_THREADS, 0, s->d_full, s->d_meta, s->d_curv, s->d_label); LM_LAUNCH_CHECK();
-  LM_LAUNCH_PDL(k_scan_ring, n_scans, SC_THREADS, SCR_TOTAL, s->d_full, s->d_curv, s->d_meta, s->d_label, s->d_pick_idx, s->d_pick_cnt, s->d_lf_tmp, s->d_lf_cnt, ctx->d_stamps); LM_LAUNCH_CHECK();
+  LM_LAUNCH_PDL(k_scan_ring, n_scans, SCR_THREADS, SCR_TOTAL, s->d_full, s->d_curv, s->d_meta, s->d_label, s->d_pick_idx, s->d_pick_cnt, s->d_lf_tmp, s->d_lf_cnt, ctx->d_stamps); LM_LAUNCH_CHECK();
   LM_LAUNCH_PDL(k_scan_compact, n_scans + 16, SC_THREADS, 0, s->d_full, s->d_meta, n_scans, s->d_pick_idx, s->d_pick_cnt, s->d_lf_tmp, s->d_lf_cnt,
                                                               s->d_out[0], s->d_out[1], s->d_out[2], s->d_out[3]); LM_LAUNCH_CHECK();
   return LMONO_OK;
