@@ -25,7 +25,6 @@
 constexpr int SC_THREADS = 256;
 constexpr int SC_NRING = 65;            // 64 rings + bucket 64 = dropped
 constexpr int SC_RING_MAX = 4096;       // points per ring handled by k_scan_ring
-constexpr int SC_SECTOR_MAX = 1024;
 constexpr int SC_PICK_STRIDE = 26;      // per (ring, sector): 2 sharp + 20 less-sharp + 4 flat indices
 #define SC_PI 3.14159265358979323846
 
@@ -242,33 +241,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_curvature(const float4* __r
 }
 
 // ---------------------------------------------------------------------------------------------
-constexpr int SCR_THREADS = 1024;          // k_scan_ring: one CTA per ring; the two sorts are block-wide networks with 2 (4) keys per thread
-// :284-288 the six sector sorts of a ring as ONE block-wide bitonic network over the composite key
-// sector (3 bits) | curvature bits (32) | local index (12): ascending (curvature, index) inside each sector, the sectors one
-// behind the other.  (One warp per sector with 16 keys per lane took 12 us of a 73 us kernel; 1024 threads with two keys
-// each run the same 66 stages in ~2 us.)
-template <int ITEMS>
-__device__ __forceinline__ void d_block_sort_sectors(unsigned long long* xch, const float* __restrict__ curv, int rs, int S, int E) {
-  unsigned long long v[ITEMS];
-  const int n = E - S;
-#pragma unroll
-  for (int r = 0; r < ITEMS; ++r) {
-    const int e = threadIdx.x * ITEMS + r;
-    unsigned long long c = ~0ULL;
-    if (e < n) {
-      // sector j holds [S + n j / 6, S + n (j + 1) / 6): the largest j with S + n j / 6 <= S + e
-      int j = (int)(((long long)e * 6 + 5) / n);
-      while (j > 0 && (long long)n * j / 6 > e) --j;
-      while (j < 5 && (long long)n * (j + 1) / 6 <= e) ++j;
-      c = ((unsigned long long)j << 44) | ((unsigned long long)__float_as_uint(curv[S + e]) << 12) | (unsigned long long)(S + e - rs);
-    }
-    v[r] = c;
-  }
-  d_bitonic_regs<ITEMS, SCR_THREADS>(v, threadIdx.x, xch);
-#pragma unroll
-  for (int r = 0; r < ITEMS; ++r) xch[threadIdx.x * ITEMS + r] = v[r];
-  __syncthreads();
-}
+constexpr int SCR_THREADS = 1024;          // k_scan_ring: one CTA per ring
 
 __device__ __forceinline__ bool d_gap_exceeds(const float* xyz, int a, int b) {
   // (p[a] - p[b]) squared norm > 0.05 (double literal), fp32 left to right
@@ -277,38 +250,122 @@ __device__ __forceinline__ bool d_gap_exceeds(const float* xyz, int a, int b) {
   return (double)d > 0.05;
 }
 
+// Two independent block-wide bitonic networks run stage by stage side by side (a dependent chain of 66 stages for 2048
+// keys is latency-bound: the second network rides in the first one's issue slots).  Same stages as d_bitonic_regs.
+template <int ITEMS, int NTHREADS>
+__device__ __forceinline__ void d_bitonic_regs2(unsigned long long (&va)[ITEMS], unsigned long long (&vb)[ITEMS], int t,
+                                                unsigned long long* xa, unsigned long long* xb) {
+  constexpr int N = ITEMS * NTHREADS;
+  constexpr int LOGN = (N <= 1) ? 0 : (31 - __builtin_clz((unsigned)N));
+  static_assert((1 << LOGN) == N, "ITEMS * NTHREADS must be a power of two");
+#pragma unroll
+  for (int lk = 1; lk <= LOGN; ++lk) {
+    const int k = 1 << lk;
+#pragma unroll
+    for (int lj = lk - 1; lj >= 0; --lj) {
+      const int j = 1 << lj;
+      if (j >= 32 * ITEMS) {
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) { xa[t * ITEMS + r] = va[r]; xb[t * ITEMS + r] = vb[r]; }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) {
+          const int i = t * ITEMS + r;
+          const unsigned long long oa = xa[i ^ j], ob = xb[i ^ j];
+          const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+          va[r] = keep_min ? (va[r] < oa ? va[r] : oa) : (va[r] < oa ? oa : va[r]);
+          vb[r] = keep_min ? (vb[r] < ob ? vb[r] : ob) : (vb[r] < ob ? ob : vb[r]);
+        }
+        __syncthreads();
+      } else if (j >= ITEMS) {
+        const int lane_x = j / ITEMS;
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) {
+          const int i = t * ITEMS + r;
+          const unsigned long long oa = __shfl_xor_sync(0xffffffffu, va[r], lane_x), ob = __shfl_xor_sync(0xffffffffu, vb[r], lane_x);
+          const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+          va[r] = keep_min ? (va[r] < oa ? va[r] : oa) : (va[r] < oa ? oa : va[r]);
+          vb[r] = keep_min ? (vb[r] < ob ? vb[r] : ob) : (vb[r] < ob ? ob : vb[r]);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) {
+          if ((r & j) == 0 && (r | j) < ITEMS) {
+            const int i = t * ITEMS + r;
+            d_cmpx(va[r], va[r | j], (i & k) == 0);
+            d_cmpx(vb[r], vb[r | j], (i & k) == 0);
+          }
+        }
+      }
+    }
+  }
+}
+
+// The two sorts of a ring, over the same n = E - S points, as one pass:
+//  A  :284-288 the six sector sorts as ONE network over sector (3 bits) | curvature bits (32) | local index (12):
+//     ascending (curvature, index) inside each sector, the sectors one behind the other;
+//  B  :401-405 the VoxelGrid order of the ring's less-flat cloud.  PCL sorts by idx = i0 + i1 d0 + i2 d0 d1 with
+//     (i0, i1, i2) = floor(p / leaf) - minb: that is the lexicographic order of the ABSOLUTE voxel coordinates (z, y, x),
+//     whatever the bounding box is, so the keys can be formed before the greedy pick has decided which points belong to
+//     the cloud: (vz, vy, vx) + 2^15 in 16 bits each | local index (12).  The picked (sharp / less-sharp) points are
+//     dropped from the sorted sequence afterwards.
 template <int ITEMS>
-__device__ __forceinline__ void d_block_sort_lf(unsigned long long* xch, int n, const float* xyz, const uint16_t* lf, const int* vgp, float inv) {
-  unsigned long long v[ITEMS];
+__device__ __forceinline__ void d_block_sort_ring(unsigned long long* xa, unsigned long long* xb, const float* __restrict__ curv,
+                                                  const float* xyz, int rs, int S, int E, float inv) {
+  unsigned long long va[ITEMS], vb[ITEMS];
+  const int n = E - S;
 #pragma unroll
   for (int r = 0; r < ITEMS; ++r) {
     const int e = threadIdx.x * ITEMS + r;
-    unsigned long long c = ~0ULL;
+    unsigned long long ca = ~0ULL, cb = ~0ULL;
     if (e < n) {
-      const int li = lf[e];
-      int ijk0 = (int)(__fsub_rn(floorf(__fmul_rn(xyz[li * 3], inv)), (float)vgp[0]));
-      int ijk1 = (int)(__fsub_rn(floorf(__fmul_rn(xyz[li * 3 + 1], inv)), (float)vgp[1]));
-      int ijk2 = (int)(__fsub_rn(floorf(__fmul_rn(xyz[li * 3 + 2], inv)), (float)vgp[2]));
-      int idx = ijk0 + ijk1 * vgp[3] + ijk2 * vgp[4];
-      c = ((unsigned long long)(uint32_t)idx << 32) | (uint32_t)e;
+      // sector j holds the offsets [n j / 6, n (j + 1) / 6)
+      int j = (int)(((long long)e * 6 + 5) / n);
+      while (j > 0 && (long long)n * j / 6 > e) --j;
+      while (j < 5 && (long long)n * (j + 1) / 6 <= e) ++j;
+      const int li = S + e - rs;
+      ca = ((unsigned long long)j << 44) | ((unsigned long long)__float_as_uint(curv[S + e]) << 12) | (unsigned long long)li;
+      const int vx = min(max((int)floorf(__fmul_rn(xyz[li * 3], inv)), -32768), 32767) + 32768;
+      const int vy = min(max((int)floorf(__fmul_rn(xyz[li * 3 + 1], inv)), -32768), 32767) + 32768;
+      const int vz = min(max((int)floorf(__fmul_rn(xyz[li * 3 + 2], inv)), -32768), 32767) + 32768;
+      cb = ((unsigned long long)vz << 44) | ((unsigned long long)vy << 28) | ((unsigned long long)vx << 12) | (unsigned long long)li;
     }
-    v[r] = c;
+    va[r] = ca; vb[r] = cb;
   }
-  d_bitonic_regs<ITEMS, SCR_THREADS>(v, threadIdx.x, xch);
+  d_bitonic_regs2<ITEMS, SCR_THREADS>(va, vb, threadIdx.x, xa, xb);
 #pragma unroll
-  for (int r = 0; r < ITEMS; ++r) xch[threadIdx.x * ITEMS + r] = v[r];
+  for (int r = 0; r < ITEMS; ++r) { xa[threadIdx.x * ITEMS + r] = va[r]; xb[threadIdx.x * ITEMS + r] = vb[r]; }
   __syncthreads();
 }
 
 // dynamic shared memory layout of k_scan_ring
-constexpr int SCR_SEC_BYTES = 6 * SC_SECTOR_MAX * 8;                  // 49152: sector sort keys / voxel sort keys
+constexpr int SCR_SEC_BYTES = SC_RING_MAX * 8;                        // sector-sorted keys; later the compacted voxel-sorted keys
+constexpr int SCR_VOX_BYTES = SC_RING_MAX * 8;                        // voxel-sorted keys
 constexpr int SCR_XYZ_BYTES = SC_RING_MAX * 12;                       // 49152
 constexpr int SCR_INT_BYTES = SC_RING_MAX * 4;                        // intensity
 constexpr int SCR_PICK_BYTES = SC_RING_MAX + 32;                      // picked flags
 constexpr int SCR_LABEL_BYTES = SC_RING_MAX;                          // labels (int8)
-constexpr int SCR_LF_BYTES = SC_RING_MAX * 2;                         // less-flat local indices (uint16)
 constexpr int SCR_GAP_BYTES = SC_RING_MAX;                            // gap[i] = |p[i] - p[i-1]|^2 > 0.05 (the +-5 suppression test), precomputed in parallel
-constexpr int SCR_TOTAL = SCR_SEC_BYTES + SCR_XYZ_BYTES + SCR_INT_BYTES + SCR_PICK_BYTES + SCR_LABEL_BYTES + SCR_LF_BYTES + 256 + SCR_GAP_BYTES;
+constexpr int SCR_TOTAL = SCR_SEC_BYTES + SCR_VOX_BYTES + SCR_XYZ_BYTES + SCR_INT_BYTES + SCR_PICK_BYTES + SCR_LABEL_BYTES + 256 + SCR_GAP_BYTES;
+
+// one greedy pick, warp-wide (:297-342 / :352-388).  Every lane holds one entry of the current 32-entry window of the
+// sorted sector: its local index li, whether it is still pickable (`alive`, a register) and the ten gap bits around it.
+// The pick is the first alive lane; its index and gap bits are broadcast, every lane clears `alive` if it falls in the
+// suppressed span (the reference's two break-on-gap walks = first set gap bit), lanes 1..10 mark the span in shared
+// memory for the windows / sectors that follow.  No shared-memory round trip sits between two picks of a window.
+__device__ __forceinline__ int d_pick_one(unsigned m, int li, uint32_t gbits, bool& alive, unsigned char* picked, int lane, bool suppress) {
+  const int src = __ffs(m) - 1;
+  const uint32_t pk = __shfl_sync(0xffffffffu, (uint32_t)li | (gbits << 12), src);
+  const int pli = (int)(pk & 0xfffu);
+  if (!suppress) { if (lane == src) alive = false; return pli; }
+  const uint32_t fm = (pk >> 12) & 31u, bm = (pk >> 17) & 31u;
+  const int nf = fm ? __ffs(fm) - 1 : 5, nb = bm ? __ffs(bm) - 1 : 5;
+  if (li >= pli - nb && li <= pli + nf) alive = false;
+  if (lane == 0) picked[pli] = 1;
+  if (lane >= 1 && lane <= nf) picked[pli + lane] = 1;
+  if (lane >= 6 && lane - 5 <= nb) picked[pli - (lane - 5)] = 1;
+  return pli;
+}
 
 __global__ void __launch_bounds__(SCR_THREADS, 1) k_scan_ring(const float4* __restrict__ full, const float* __restrict__ curv,
                                                              ScanMeta* __restrict__ meta, int32_t* __restrict__ label_out,
@@ -320,13 +377,13 @@ __global__ void __launch_bounds__(SCR_THREADS, 1) k_scan_ring(const float4* __re
   SCR_STAMP(0);
   extern __shared__ __align__(16) unsigned char smem[];
   unsigned long long* sec = reinterpret_cast<unsigned long long*>(smem);
-  float* xyz = reinterpret_cast<float*>(smem + SCR_SEC_BYTES);
-  float* inten = reinterpret_cast<float*>(smem + SCR_SEC_BYTES + SCR_XYZ_BYTES);
-  unsigned char* picked = smem + SCR_SEC_BYTES + SCR_XYZ_BYTES + SCR_INT_BYTES;
+  unsigned long long* vox = reinterpret_cast<unsigned long long*>(smem + SCR_SEC_BYTES);
+  float* xyz = reinterpret_cast<float*>(smem + SCR_SEC_BYTES + SCR_VOX_BYTES);
+  float* inten = reinterpret_cast<float*>(smem + SCR_SEC_BYTES + SCR_VOX_BYTES + SCR_XYZ_BYTES);
+  unsigned char* picked = smem + SCR_SEC_BYTES + SCR_VOX_BYTES + SCR_XYZ_BYTES + SCR_INT_BYTES;
   signed char* label = reinterpret_cast<signed char*>(picked + SCR_PICK_BYTES);
-  uint16_t* lf = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(label) + SCR_LABEL_BYTES);
-  int* ws = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(lf) + SCR_LF_BYTES);     // [64]
-  unsigned char* gap = reinterpret_cast<unsigned char*>(ws) + 256;                            // [SC_RING_MAX]
+  int* ws = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(label) + SCR_LABEL_BYTES);     // [64]
+  unsigned char* gap = reinterpret_cast<unsigned char*>(ws) + 256;                                  // [SC_RING_MAX]
   __shared__ int s_vg[8];
   __shared__ float s_mn[3][SCR_THREADS / 32], s_mx[3][SCR_THREADS / 32];
 
@@ -339,6 +396,8 @@ __global__ void __launch_bounds__(SCR_THREADS, 1) k_scan_ring(const float4* __re
   if (E - S < 6) return;                                  // :279
   if (L > SC_RING_MAX) { if (threadIdx.x == 0) atomicOr(&meta->fault, 1u); return; }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int n = E - S;
+  const float inv = 1.0f / 0.2f;
 
   for (int i0 = threadIdx.x; i0 < L; i0 += 4 * SCR_THREADS) {      // four loads in flight per thread, then the shared-memory stores
     float4 p[4];
@@ -352,25 +411,19 @@ __global__ void __launch_bounds__(SCR_THREADS, 1) k_scan_ring(const float4* __re
   }
   __syncthreads();
   SCR_STAMP(1);
-  // the serial greedy pick below tests |p[i] - p[i-1]|^2 > 0.05 up to ten times per pick (:319-342, 365-388): the test
-  // is a pure function of two neighbours, so every thread evaluates its share once here and the one picking thread only
-  // reads a byte ((a - b)^2 == (b - a)^2 exactly, one array serves both walking directions)
+  // the greedy pick below tests |p[i] - p[i-1]|^2 > 0.05 up to ten times per pick (:319-342, 365-388): the test is a pure
+  // function of two neighbours, so every thread evaluates its share once here ((a - b)^2 == (b - a)^2 exactly, one array
+  // serves both walking directions)
   for (int i = threadIdx.x; i < L; i += blockDim.x) gap[i] = (i > 0 && d_gap_exceeds(xyz, i, i - 1)) ? 1 : 0;
-  __syncthreads();
-  // :284-288 six sector sorts, (curvature, index) ascending: one block-wide network
-  if (E - S <= 2 * SCR_THREADS) d_block_sort_sectors<2>(sec, curv, rs, S, E);
-  else d_block_sort_sectors<4>(sec, curv, rs, S, E);
+  if (n <= 2 * SCR_THREADS) d_block_sort_ring<2>(sec, vox, curv, xyz, rs, S, E, inv);
+  else d_block_sort_ring<4>(sec, vox, curv, xyz, rs, S, E, inv);
   SCR_STAMP(2);
 
-  // :291-390 greedy picking.  The sectors of a ring are order dependent (suppression crosses the sector border) and so are
-  // the picks inside a sector, but one pick is wide: ONE WARP walks the sorted list 32 entries at a time -- every lane
-  // holds one entry, a ballot over "still unpicked" finds the next pick (the reference's `continue` over picked entries),
-  // lanes 1..5 / 6..10 test the five forward / backward gap bytes of the pick at once and mark the suppressed neighbours
-  // (the reference's two `break`-on-gap loops = first set bit of the ballot).  Same picks in the same order as the
-  // single-thread walk, at a few shared-memory round trips per pick instead of ~25.
+  // :291-390 greedy picking, one warp.  The sectors of a ring are order dependent (suppression crosses the sector border)
+  // and so are the picks inside a sector; see d_pick_one.  Same picks in the same order as the reference's walk.
   if (wid == 0) {
     for (int j = 0; j < 6; ++j) {
-      const int sp = S + (E - S) * j / 6, ep = S + (E - S) * (j + 1) / 6 - 1;
+      const int sp = S + n * j / 6, ep = S + n * (j + 1) / 6 - 1;
       const int len = ep - sp + 1;
       const unsigned long long* sk = sec + (sp - S);             // the sectors lie one behind the other in the sorted array
       int* out = pick_idx + (r * 6 + j) * SC_PICK_STRIDE;
@@ -378,69 +431,64 @@ __global__ void __launch_bounds__(SCR_THREADS, 1) k_scan_ring(const float4* __re
       int largest = 0;
       bool done = false;
       for (int k_hi = len - 1; k_hi >= 0 && !done; k_hi -= 32) {          // descending curvature
+        __syncwarp();
         const int k = k_hi - lane;
         const unsigned long long c = k >= 0 ? sk[k] : 0ull;
         const bool qual = k >= 0 && (double)__uint_as_float((uint32_t)(c >> 12)) > 0.1;
         const int li = (int)(c & 0xfffull);
         const unsigned qm = __ballot_sync(0xffffffffu, qual);
         const int nvalid = qm == 0xffffffffu ? 32 : __ffs(~qm) - 1;      // sorted: nothing behind the first non-qualifying entry qualifies
-        unsigned live = nvalid == 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
-        while (live) {
-          const bool cand = lane < nvalid && !picked[li];
-          const unsigned cm = __ballot_sync(0xffffffffu, cand) & live;
-          if (!cm) break;
-          const int src = __ffs(cm) - 1;
-          live &= src == 31 ? 0u : ~((2u << src) - 1u);
-          const int pli = __shfl_sync(0xffffffffu, li, src);
+        bool alive = lane < nvalid && !picked[li];
+        uint32_t gbits = 0;
+        if (lane < nvalid) {
+#pragma unroll
+          for (int l = 1; l <= 5; ++l) gbits |= (uint32_t)(gap[li + l] != 0) << (l - 1);            // :319-330
+#pragma unroll
+          for (int l = 1; l <= 5; ++l) gbits |= (uint32_t)(gap[li - l + 1] != 0) << (4 + l);        // :331-342
+        }
+        for (;;) {
+          const unsigned m = __ballot_sync(0xffffffffu, alive);
+          if (!m) break;
           largest++;
           if (largest > 20) { done = true; break; }
+          const int pli = d_pick_one(m, li, gbits, alive, picked, lane, true);
           if (lane == 0) {
             const int ind = pli + rs;
             if (largest <= 2) { label[pli] = 2; out[n_sharp] = ind; out[2 + n_ls] = ind; }
             else { label[pli] = 1; out[2 + n_ls] = ind; }
-            picked[pli] = 1;
           }
           if (largest <= 2) n_sharp++;
           n_ls++;
-          const bool gf = lane >= 1 && lane <= 5 && gap[pli + lane];                // :319-330
-          const bool gb = lane >= 6 && lane <= 10 && gap[pli - (lane - 5) + 1];     // :331-342
-          const unsigned fm = (__ballot_sync(0xffffffffu, gf) >> 1) & 31u, bm = (__ballot_sync(0xffffffffu, gb) >> 6) & 31u;
-          const int nf = fm ? __ffs(fm) - 1 : 5, nb = bm ? __ffs(bm) - 1 : 5;
-          if (lane >= 1 && lane <= nf) picked[pli + lane] = 1;
-          if (lane >= 6 && lane - 5 <= nb) picked[pli - (lane - 5)] = 1;
-          __syncwarp();
         }
         if (nvalid < 32) break;
       }
       int smallest = 0;
       done = false;
       for (int k_lo = 0; k_lo < len && !done; k_lo += 32) {               // ascending curvature
+        __syncwarp();
         const int k = k_lo + lane;
         const unsigned long long c = k < len ? sk[k] : 0ull;
         const bool qual = k < len && (double)__uint_as_float((uint32_t)(c >> 12)) < 0.1;
         const int li = (int)(c & 0xfffull);
         const unsigned qm = __ballot_sync(0xffffffffu, qual);
         const int nvalid = qm == 0xffffffffu ? 32 : __ffs(~qm) - 1;
-        unsigned live = nvalid == 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
-        while (live) {
-          const bool cand = lane < nvalid && !picked[li];
-          const unsigned cm = __ballot_sync(0xffffffffu, cand) & live;
-          if (!cm) break;
-          const int src = __ffs(cm) - 1;
-          live &= src == 31 ? 0u : ~((2u << src) - 1u);
-          const int pli = __shfl_sync(0xffffffffu, li, src);
+        bool alive = lane < nvalid && !picked[li];
+        uint32_t gbits = 0;
+        if (lane < nvalid) {
+#pragma unroll
+          for (int l = 1; l <= 5; ++l) gbits |= (uint32_t)(gap[li + l] != 0) << (l - 1);
+#pragma unroll
+          for (int l = 1; l <= 5; ++l) gbits |= (uint32_t)(gap[li - l + 1] != 0) << (4 + l);
+        }
+        for (;;) {
+          const unsigned m = __ballot_sync(0xffffffffu, alive);
+          if (!m) break;
+          smallest++;
+          const bool last = smallest >= 4;                                // :359-362: the 4th flat point is neither marked nor suppressing
+          const int pli = d_pick_one(m, li, gbits, alive, picked, lane, !last);
           if (lane == 0) { label[pli] = -1; out[22 + n_flat] = pli + rs; }
           n_flat++;
-          smallest++;
-          if (smallest >= 4) { done = true; break; }                      // :359-362: the 4th flat point is neither marked nor suppressing
-          if (lane == 0) picked[pli] = 1;
-          const bool gf = lane >= 1 && lane <= 5 && gap[pli + lane];
-          const bool gb = lane >= 6 && lane <= 10 && gap[pli - (lane - 5) + 1];
-          const unsigned fm = (__ballot_sync(0xffffffffu, gf) >> 1) & 31u, bm = (__ballot_sync(0xffffffffu, gb) >> 6) & 31u;
-          const int nf = fm ? __ffs(fm) - 1 : 5, nb = bm ? __ffs(bm) - 1 : 5;
-          if (lane >= 1 && lane <= nf) picked[pli + lane] = 1;
-          if (lane >= 6 && lane - 5 <= nb) picked[pli - (lane - 5)] = 1;
-          __syncwarp();
+          if (last) { done = true; break; }
         }
         if (nvalid < 32) break;
       }
@@ -452,29 +500,28 @@ __global__ void __launch_bounds__(SCR_THREADS, 1) k_scan_ring(const float4* __re
   SCR_STAMP(3);
   for (int i = threadIdx.x; i < L; i += blockDim.x) label_out[rs + i] = (int)label[i];
 
-  // :392-398 less-flat = every k in [sp_0, ep_5] with label <= 0, in index order
-  const int k0 = S - rs, k1 = (S + (E - S) * 6 / 6 - 1) - rs;      // local, inclusive
+  // :392-398 less-flat = every point of [S, E) with label <= 0; :401-405 VoxelGrid(0.2) of them (PCL arithmetic, see
+  // voxel.cu).  The voxel-sorted sequence of all n points exists already: drop the picked ones (stable compaction).
+  unsigned long long* lfs = sec;                            // the sector-sorted keys are no longer needed
   int n_lf = 0;
-  for (int base = k0; base <= k1; base += blockDim.x) {
-    const int i = base + threadIdx.x;
-    const int flag = (i <= k1 && label[i] <= 0) ? 1 : 0;
+  float mn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, mx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int e = base + threadIdx.x;
+    unsigned long long c = 0; int flag = 0;
+    if (e < n) { c = vox[e]; flag = label[(int)(c & 0xfffull)] <= 0 ? 1 : 0; }
     int total;
     const int ex = d_block_exscan(flag, ws, &total);
-    if (flag) lf[n_lf + ex] = (uint16_t)i;
+    if (flag) {
+      lfs[n_lf + ex] = c;
+      const int li = (int)(c & 0xfffull);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { mn[d] = fminf(mn[d], xyz[li * 3 + d]); mx[d] = fmaxf(mx[d], xyz[li * 3 + d]); }
+    }
     n_lf += total;
   }
   __syncthreads();
   SCR_STAMP(4);
   if (n_lf == 0) return;
-
-  // :401-405 VoxelGrid(0.2) of the ring's less-flat points (PCL arithmetic, see voxel.cu)
-  const float inv = 1.0f / 0.2f;
-  float mn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, mx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
-  for (int e = threadIdx.x; e < n_lf; e += blockDim.x) {
-    const int li = lf[e];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) { mn[d] = fminf(mn[d], xyz[li * 3 + d]); mx[d] = fmaxf(mx[d], xyz[li * 3 + d]); }
-  }
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
 #pragma unroll
@@ -482,44 +529,46 @@ __global__ void __launch_bounds__(SCR_THREADS, 1) k_scan_ring(const float4* __re
     if (lane == 0) { s_mn[d][wid] = mn[d]; s_mx[d][wid] = mx[d]; }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    long long dd[3]; int minb[3], divb[3];
+  if (threadIdx.x == 0) {                          // PCL's guard: (dx + 1)(dy + 1)(dz + 1) of the bounding box must fit an int
+    long long dd[3];
     for (int d = 0; d < 3; ++d) {
       float a = s_mn[d][0], b = s_mx[d][0];
       for (int w = 1; w < SCR_THREADS / 32; ++w) { a = fminf(a, s_mn[d][w]); b = fmaxf(b, s_mx[d][w]); }
       dd[d] = (long long)(__fmul_rn(__fsub_rn(b, a), inv)) + 1;
-      minb[d] = (int)floorf(__fmul_rn(a, inv));
-      divb[d] = (int)floorf(__fmul_rn(b, inv)) - minb[d] + 1;
     }
-    s_vg[0] = minb[0]; s_vg[1] = minb[1]; s_vg[2] = minb[2];
-    s_vg[3] = divb[0]; s_vg[4] = divb[0] * divb[1];
     s_vg[5] = (dd[0] * dd[1] * dd[2] > (long long)INT32_MAX) ? 1 : 0;
   }
   __syncthreads();
   SCR_STAMP(5);
   float4* outp = lf_tmp + rs;
-  if (s_vg[5]) {                                   // PCL: leaf too small -> cloud returned unchanged
-    for (int e = threadIdx.x; e < n_lf; e += blockDim.x) { const int li = lf[e]; outp[e] = make_float4(xyz[li * 3], xyz[li * 3 + 1], xyz[li * 3 + 2], inten[li]); }
-    if (threadIdx.x == 0) lf_cnt[r] = n_lf;
+  if (s_vg[5]) {                                   // PCL: leaf too small -> cloud returned unchanged (index order)
+    int n_out = 0;
+    for (int base = S - rs; base < E - rs; base += blockDim.x) {
+      const int i = base + threadIdx.x;
+      const int flag = (i < E - rs && label[i] <= 0) ? 1 : 0;
+      int total;
+      const int ex = d_block_exscan(flag, ws, &total);
+      if (flag) outp[n_out + ex] = make_float4(xyz[i * 3], xyz[i * 3 + 1], xyz[i * 3 + 2], inten[i]);
+      n_out += total;
+    }
+    if (threadIdx.x == 0) lf_cnt[r] = n_out;
     return;
   }
-  if (n_lf <= SCR_THREADS * 2) d_block_sort_lf<2>(sec, n_lf, xyz, lf, s_vg, inv);
-  else d_block_sort_lf<4>(sec, n_lf, xyz, lf, s_vg, inv);
   SCR_STAMP(6);
   int n_out = 0;
   for (int base = 0; base < n_lf; base += blockDim.x) {
     const int e = base + threadIdx.x;
     int head = 0; unsigned long long me = 0;
-    if (e < n_lf) { me = sec[e]; head = (e == 0) || ((me >> 32) != (sec[e - 1] >> 32)); }
+    if (e < n_lf) { me = lfs[e]; head = (e == 0) || ((me >> 12) != (lfs[e - 1] >> 12)); }
     int total;
     const int ex = d_block_exscan(head, ws, &total);
     if (head) {
-      const uint32_t key = (uint32_t)(me >> 32);
+      const unsigned long long key = me >> 12;
       float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f; int cnt = 0;
       for (int m = e; m < n_lf; ++m) {
-        const unsigned long long c = sec[m];
-        if ((uint32_t)(c >> 32) != key) break;
-        const int li = lf[(uint32_t)c];
+        const unsigned long long c = lfs[m];
+        if ((c >> 12) != key) break;
+        const int li = (int)(c & 0xfffull);
         sx = __fadd_rn(sx, xyz[li * 3]); sy = __fadd_rn(sy, xyz[li * 3 + 1]); sz = __fadd_rn(sz, xyz[li * 3 + 2]); si = __fadd_rn(si, inten[li]);
         ++cnt;
       }
