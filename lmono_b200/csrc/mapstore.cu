@@ -719,8 +719,10 @@ __global__ void __launch_bounds__(256) k_rf_merge(LmMapState* __restrict__ st, L
 }
 
 constexpr int RF_SCAN_THREADS = 512;
-__global__ void __launch_bounds__(RF_SCAN_THREADS) k_rf_scan(LmMapType M0, LmMapType M1, const int32_t* __restrict__ plan, RfMeta* __restrict__ meta_all) {
+__global__ void __launch_bounds__(RF_SCAN_THREADS) k_rf_scan(LmMapType M0, LmMapType M1, const int32_t* __restrict__ plan, RfMeta* __restrict__ meta_all,
+                                                             const int32_t* __restrict__ work_n) {
   lm_pdl_enter();
+  if (*work_n == 0) return;                          // every cube was updated in place: nothing was merged
   constexpr int NW = RF_SCAN_THREADS / 32;
   __shared__ int wtot[NW], wbase[NW];
   const int na = plan[LM_PLAN_ACTIVE_N];
@@ -948,7 +950,7 @@ int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf,
   LM_LAUNCH_CHECK();
   LM_LAUNCH_PDL(k_rf_merge, RF_GRID, 256, 0, ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_rf_nvx, ctx->d_rf_tlb, meta, cap_max, work_n, work);
   LM_LAUNCH_CHECK();
-  LM_LAUNCH_PDL(k_rf_scan, RF_ACT_GRID, RF_SCAN_THREADS, 0, ctx->map[0], ctx->map[1], ctx->d_rf_plan, meta);
+  LM_LAUNCH_PDL(k_rf_scan, RF_ACT_GRID, RF_SCAN_THREADS, 0, ctx->map[0], ctx->map[1], ctx->d_rf_plan, meta, work_n);
   LM_LAUNCH_CHECK();
   LM_LAUNCH_PDL(k_rf_scatter, RF_GRID, 256, 0, ctx->map[0], ctx->map[1], meta, work_n, work);
   LM_LAUNCH_CHECK();

@@ -161,16 +161,26 @@ __device__ __forceinline__ unsigned long long d_warp_min_u64(unsigned long long 
 
 constexpr int NB_LIST = 64;       // tiles a warp collects before it scans them (eight coalesced loads in flight per step)
 constexpr int NB_CHUNK = 1024;    // tiles (32 768 points) whose boxes a CTA stages in shared memory per outer trip
-__device__ __forceinline__ unsigned long long d_nn_scan_list(const float4* __restrict__ last, int nl, float4 sel, const unsigned short* list, int cnt,
-                                                             int tile0, int lane, unsigned long long bestk) {
-  for (int i = 0; i < cnt; i += 8) {
+// scan the collected tiles, eight coalesced loads in flight per round; the bound tightens after every round (warp-min) and
+// list entries whose box bound has fallen behind it are skipped
+__device__ __forceinline__ unsigned long long d_nn_scan_list(const float4* __restrict__ last, int nl, float4 sel, const unsigned short* list,
+                                                             const uint32_t* list_lb, int cnt, int tile0, int lane, unsigned long long bestk) {
+  int i = 0;
+  while (i < cnt) {
     int j[8]; float4 p[8];
+    const uint32_t thr = (uint32_t)(bestk >> 32);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { j[u] = i + u < cnt ? (tile0 + (int)list[i + u]) * 32 + lane : nl; if (j[u] < nl) p[u] = last[j[u]]; }
+    for (int u = 0; u < 8; ++u) {
+      while (i < cnt && list_lb[i] > thr) ++i;              // warp-uniform
+      j[u] = i < cnt ? (tile0 + (int)list[i]) * 32 + lane : nl;
+      if (i < cnt) ++i;
+      if (j[u] < nl) p[u] = last[j[u]];
+    }
 #pragma unroll
     for (int u = 0; u < 8; ++u) if (j[u] < nl) { const unsigned long long k = d_nn_point_key(sel, p[u], j[u]); bestk = k < bestk ? k : bestk; }
+    bestk = d_warp_min_u64(bestk);
   }
-  return d_warp_min_u64(bestk);
+  return bestk;
 }
 
 // flat features against surf_last (the corner cloud is sparse along its rings -- its tiles are long arcs with useless
@@ -180,6 +190,7 @@ __global__ void __launch_bounds__(256, 2) k_odom_nn_box(const OdomDev* __restric
   lm_pdl_enter();
   __shared__ float4 s_b0[NB_CHUNK], s_b1[NB_CHUNK];
   __shared__ unsigned short s_list[8][NB_LIST];
+  __shared__ uint32_t s_list_lb[8][NB_LIST];
   if (!o->do_solve) return;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -192,6 +203,7 @@ __global__ void __launch_bounds__(256, 2) k_odom_nn_box(const OdomDev* __restric
   const float4 sel = d_to_start(o, flat[qi]);
   const int ntile = (nl + 31) >> 5;
   unsigned short* list = s_list[threadIdx.x >> 5];
+  uint32_t* list_lb = s_list_lb[threadIdx.x >> 5];
   unsigned long long bestk = ~0ULL;
   for (int tile0 = 0; tile0 < ntile; tile0 += NB_CHUNK) {
     __syncthreads();
@@ -201,10 +213,20 @@ __global__ void __launch_bounds__(256, 2) k_odom_nn_box(const OdomDev* __restric
     uint32_t lbs[32];                                 // lane l keeps the bounds of tiles l, l + 32, ... of this chunk
 #pragma unroll
     for (int k = 0; k < 32; ++k) { const int t = k * 32 + lane; lbs[k] = tile0 + t < ntile ? __float_as_uint(d_box_lb(s_b0[t], s_b1[t], sel)) : 0xffffffffu; }
-    if (tile0 == 0) {                                 // seed: the tile with the smallest bound
+    if (tile0 == 0) {
+      // seed: the tile whose box CENTRE is nearest (many boxes contain the feature -- bound 0 -- and most of those are long
+      // arcs far away; the nearest centre is a small box close by, so the first bound is already about the true distance)
       unsigned long long seedk = ~0ULL;
 #pragma unroll
-      for (int k = 0; k < 32; ++k) { const unsigned long long v = ((unsigned long long)lbs[k] << 32) | (uint32_t)(k * 32 + lane); seedk = v < seedk ? v : seedk; }
+      for (int k = 0; k < 32; ++k) {
+        const int t = k * 32 + lane;
+        if (t < ntile) {
+          const float4 b0 = s_b0[t], b1 = s_b1[t];
+          const float cx = sel.x - 0.5f * (b0.x + b0.w), cy = sel.y - 0.5f * (b0.y + b1.x), cz = sel.z - 0.5f * (b0.z + b1.y);
+          const unsigned long long v = ((unsigned long long)__float_as_uint(cx * cx + cy * cy + cz * cz) << 32) | (uint32_t)t;
+          seedk = v < seedk ? v : seedk;
+        }
+      }
       const int seed = (int)(uint32_t)d_warp_min_u64(seedk);
       const int j = seed * 32 + lane;
       if (j < nl) bestk = d_nn_point_key(sel, last[j], j);
@@ -218,15 +240,15 @@ __global__ void __launch_bounds__(256, 2) k_odom_nn_box(const OdomDev* __restric
       if (!m) continue;
       if (cnt + __popc(m) > NB_LIST) {                // list full: scan what is collected, the tighter bound prunes the rest
         __syncwarp();
-        bestk = d_nn_scan_list(last, nl, sel, list, cnt, tile0, lane, bestk);
+        bestk = d_nn_scan_list(last, nl, sel, list, list_lb, cnt, tile0, lane, bestk);
         cnt = 0;
         m = __ballot_sync(0xffffffffu, lbs[k] <= (uint32_t)(bestk >> 32));
       }
-      if ((m >> lane) & 1u) list[cnt + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(k * 32 + lane);
+      if ((m >> lane) & 1u) { const int pos = cnt + __popc(m & ((1u << lane) - 1u)); list[pos] = (unsigned short)(k * 32 + lane); list_lb[pos] = lbs[k]; }
       cnt += __popc(m);
     }
     __syncwarp();
-    bestk = d_nn_scan_list(last, nl, sel, list, cnt, tile0, lane, bestk);
+    bestk = d_nn_scan_list(last, nl, sel, list, list_lb, cnt, tile0, lane, bestk);
     __syncwarp();
   }
   if (active && lane == 0) best[qi] = bestk;

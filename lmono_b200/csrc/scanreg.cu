@@ -352,8 +352,10 @@ constexpr int SCR_TOTAL = SCR_SEC_BYTES + SCR_VOX_BYTES + SCR_XYZ_BYTES + SCR_IN
 // sorted sector: its local index li, whether it is still pickable (`alive`, a register) and the ten gap bits around it.
 // The pick is the first alive lane; its index and gap bits are broadcast, every lane clears `alive` if it falls in the
 // suppressed span (the reference's two break-on-gap walks = first set gap bit), lanes 1..10 mark the span in shared
-// memory for the windows / sectors that follow.  No shared-memory round trip sits between two picks of a window.
-__device__ __forceinline__ int d_pick_one(unsigned m, int li, uint32_t gbits, bool& alive, unsigned char* picked, int lane, bool suppress) {
+// memory for the windows that follow.  Marks are only written inside the sector [lo, hi]: what falls behind it is
+// returned as a bit mask (bit b = local index hi + 1 + b), what falls before it cannot matter any more.
+__device__ __forceinline__ int d_pick_one(unsigned m, int li, uint32_t gbits, bool& alive, unsigned char* picked, int lane, bool suppress,
+                                          int lo, int hi, uint32_t& spill) {
   const int src = __ffs(m) - 1;
   const uint32_t pk = __shfl_sync(0xffffffffu, (uint32_t)li | (gbits << 12), src);
   const int pli = (int)(pk & 0xfffu);
@@ -362,9 +364,97 @@ __device__ __forceinline__ int d_pick_one(unsigned m, int li, uint32_t gbits, bo
   const int nf = fm ? __ffs(fm) - 1 : 5, nb = bm ? __ffs(bm) - 1 : 5;
   if (li >= pli - nb && li <= pli + nf) alive = false;
   if (lane == 0) picked[pli] = 1;
-  if (lane >= 1 && lane <= nf) picked[pli + lane] = 1;
-  if (lane >= 6 && lane - 5 <= nb) picked[pli - (lane - 5)] = 1;
+  if (lane >= 1 && lane <= nf && pli + lane <= hi) picked[pli + lane] = 1;
+  if (lane >= 6 && lane - 5 <= nb && pli - (lane - 5) >= lo) picked[pli - (lane - 5)] = 1;
+  const int over = pli + nf - hi;
+  if (over > 0) spill |= (1u << over) - 1u;
   return pli;
+}
+
+// :291-390 the greedy pick of ONE sector by one warp; `incoming` = marks the previous sector left on this sector's first
+// five points.  Returns the marks this sector leaves on the next one.  Same picks in the same order as the reference's walk.
+__device__ __noinline__ uint32_t d_pick_sector(int j, uint32_t incoming, bool redo, const unsigned long long* sec, int S, int n, int rs, int r,
+                                               unsigned char* picked, const unsigned char* gap, signed char* label,
+                                               int32_t* __restrict__ pick_idx, int32_t* __restrict__ pick_cnt, int lane) {
+  const int sp = S + n * j / 6, ep = S + n * (j + 1) / 6 - 1;
+  const int len = ep - sp + 1;
+  const int lo = sp - rs, hi = ep - rs;
+  const unsigned long long* sk = sec + (sp - S);             // the sectors lie one behind the other in the sorted array
+  int* out = pick_idx + (r * 6 + j) * SC_PICK_STRIDE;
+  if (redo) {
+    for (int i = lo + lane; i <= hi; i += 32) { picked[i] = 0; label[i] = 0; }
+    __syncwarp();
+  }
+  if (lane < 5 && ((incoming >> lane) & 1u) && lo + lane <= hi) picked[lo + lane] = 1;
+  uint32_t spill = 0;
+  int n_sharp = 0, n_ls = 0, n_flat = 0;
+  int largest = 0;
+  bool done = false;
+  for (int k_hi = len - 1; k_hi >= 0 && !done; k_hi -= 32) {          // descending curvature
+    __syncwarp();
+    const int k = k_hi - lane;
+    const unsigned long long c = k >= 0 ? sk[k] : 0ull;
+    const bool qual = k >= 0 && (double)__uint_as_float((uint32_t)(c >> 12)) > 0.1;
+    const int li = (int)(c & 0xfffull);
+    const unsigned qm = __ballot_sync(0xffffffffu, qual);
+    const int nvalid = qm == 0xffffffffu ? 32 : __ffs(~qm) - 1;      // sorted: nothing behind the first non-qualifying entry qualifies
+    bool alive = lane < nvalid && !picked[li];
+    uint32_t gbits = 0;
+    if (lane < nvalid) {
+#pragma unroll
+      for (int l = 1; l <= 5; ++l) gbits |= (uint32_t)(gap[li + l] != 0) << (l - 1);            // :319-330
+#pragma unroll
+      for (int l = 1; l <= 5; ++l) gbits |= (uint32_t)(gap[li - l + 1] != 0) << (4 + l);        // :331-342
+    }
+    for (;;) {
+      const unsigned m = __ballot_sync(0xffffffffu, alive);
+      if (!m) break;
+      largest++;
+      if (largest > 20) { done = true; break; }
+      const int pli = d_pick_one(m, li, gbits, alive, picked, lane, true, lo, hi, spill);
+      if (lane == 0) {
+        const int ind = pli + rs;
+        if (largest <= 2) { label[pli] = 2; out[n_sharp] = ind; out[2 + n_ls] = ind; }
+        else { label[pli] = 1; out[2 + n_ls] = ind; }
+      }
+      if (largest <= 2) n_sharp++;
+      n_ls++;
+    }
+    if (nvalid < 32) break;
+  }
+  int smallest = 0;
+  done = false;
+  for (int k_lo = 0; k_lo < len && !done; k_lo += 32) {               // ascending curvature
+    __syncwarp();
+    const int k = k_lo + lane;
+    const unsigned long long c = k < len ? sk[k] : 0ull;
+    const bool qual = k < len && (double)__uint_as_float((uint32_t)(c >> 12)) < 0.1;
+    const int li = (int)(c & 0xfffull);
+    const unsigned qm = __ballot_sync(0xffffffffu, qual);
+    const int nvalid = qm == 0xffffffffu ? 32 : __ffs(~qm) - 1;
+    bool alive = lane < nvalid && !picked[li];
+    uint32_t gbits = 0;
+    if (lane < nvalid) {
+#pragma unroll
+      for (int l = 1; l <= 5; ++l) gbits |= (uint32_t)(gap[li + l] != 0) << (l - 1);
+#pragma unroll
+      for (int l = 1; l <= 5; ++l) gbits |= (uint32_t)(gap[li - l + 1] != 0) << (4 + l);
+    }
+    for (;;) {
+      const unsigned m = __ballot_sync(0xffffffffu, alive);
+      if (!m) break;
+      smallest++;
+      const bool last = smallest >= 4;                                // :359-362: the 4th flat point is neither marked nor suppressing
+      const int pli = d_pick_one(m, li, gbits, alive, picked, lane, !last, lo, hi, spill);
+      if (lane == 0) { label[pli] = -1; out[22 + n_flat] = pli + rs; }
+      n_flat++;
+      if (last) { done = true; break; }
+    }
+    if (nvalid < 32) break;
+  }
+  __syncwarp();
+  if (lane == 0) { pick_cnt[r * 18 + j * 3 + 0] = n_sharp; pick_cnt[r * 18 + j * 3 + 1] = n_ls; pick_cnt[r * 18 + j * 3 + 2] = n_flat; }
+  return spill;
 }
 
 __global__ void __launch_bounds__(SCR_THREADS, 1) k_scan_ring(const float4* __restrict__ full, const float* __restrict__ curv,
@@ -419,82 +509,29 @@ __global__ void __launch_bounds__(SCR_THREADS, 1) k_scan_ring(const float4* __re
   else d_block_sort_ring<4>(sec, vox, curv, xyz, rs, S, E, inv);
   SCR_STAMP(2);
 
-  // :291-390 greedy picking, one warp.  The sectors of a ring are order dependent (suppression crosses the sector border)
-  // and so are the picks inside a sector; see d_pick_one.  Same picks in the same order as the reference's walk.
-  if (wid == 0) {
-    for (int j = 0; j < 6; ++j) {
-      const int sp = S + n * j / 6, ep = S + n * (j + 1) / 6 - 1;
-      const int len = ep - sp + 1;
-      const unsigned long long* sk = sec + (sp - S);             // the sectors lie one behind the other in the sorted array
-      int* out = pick_idx + (r * 6 + j) * SC_PICK_STRIDE;
-      int n_sharp = 0, n_ls = 0, n_flat = 0;
-      int largest = 0;
-      bool done = false;
-      for (int k_hi = len - 1; k_hi >= 0 && !done; k_hi -= 32) {          // descending curvature
-        __syncwarp();
-        const int k = k_hi - lane;
-        const unsigned long long c = k >= 0 ? sk[k] : 0ull;
-        const bool qual = k >= 0 && (double)__uint_as_float((uint32_t)(c >> 12)) > 0.1;
-        const int li = (int)(c & 0xfffull);
-        const unsigned qm = __ballot_sync(0xffffffffu, qual);
-        const int nvalid = qm == 0xffffffffu ? 32 : __ffs(~qm) - 1;      // sorted: nothing behind the first non-qualifying entry qualifies
-        bool alive = lane < nvalid && !picked[li];
-        uint32_t gbits = 0;
-        if (lane < nvalid) {
-#pragma unroll
-          for (int l = 1; l <= 5; ++l) gbits |= (uint32_t)(gap[li + l] != 0) << (l - 1);            // :319-330
-#pragma unroll
-          for (int l = 1; l <= 5; ++l) gbits |= (uint32_t)(gap[li - l + 1] != 0) << (4 + l);        // :331-342
-        }
-        for (;;) {
-          const unsigned m = __ballot_sync(0xffffffffu, alive);
-          if (!m) break;
-          largest++;
-          if (largest > 20) { done = true; break; }
-          const int pli = d_pick_one(m, li, gbits, alive, picked, lane, true);
-          if (lane == 0) {
-            const int ind = pli + rs;
-            if (largest <= 2) { label[pli] = 2; out[n_sharp] = ind; out[2 + n_ls] = ind; }
-            else { label[pli] = 1; out[2 + n_ls] = ind; }
-          }
-          if (largest <= 2) n_sharp++;
-          n_ls++;
-        }
-        if (nvalid < 32) break;
+  // :291-390 greedy picking.  The reference walks the six sectors one after the other, and a pick suppresses up to five
+  // neighbours on either side -- possibly across the sector border.  Marks reaching BACK into a finished sector change
+  // nothing; marks reaching FORWARD change the next sector only if they hit a point that sector would have picked.
+  // So six warps pick their sectors at once, each assuming no incoming marks, and a short ordered check follows: if the
+  // (final) forward marks of sector j - 1 hit a point that sector j picked, sector j is picked again with those marks (about
+  // one border in ten), which may in turn change what it passes on.  Same picks as the sequential walk.
+  __shared__ uint32_t s_spill[6];
+  if (wid < 6) {
+    const uint32_t sp_ = d_pick_sector(wid, 0u, false, sec, S, n, rs, r, picked, gap, label, pick_idx, pick_cnt, lane);
+    if (lane == 0) s_spill[wid] = sp_;
+  }
+  __syncthreads();
+  for (int j = 1; j < 6; ++j) {
+    if (wid == j) {
+      const uint32_t inc = s_spill[j - 1];
+      const int lo = S + n * j / 6 - rs, hi = S + n * (j + 1) / 6 - 1 - rs;
+      const bool hit = lane < 5 && ((inc >> lane) & 1u) && lo + lane <= hi && label[lo + lane] != 0;
+      if (__any_sync(0xffffffffu, hit)) {
+        const uint32_t sp_ = d_pick_sector(j, inc, true, sec, S, n, rs, r, picked, gap, label, pick_idx, pick_cnt, lane);
+        if (lane == 0) s_spill[j] = sp_;
       }
-      int smallest = 0;
-      done = false;
-      for (int k_lo = 0; k_lo < len && !done; k_lo += 32) {               // ascending curvature
-        __syncwarp();
-        const int k = k_lo + lane;
-        const unsigned long long c = k < len ? sk[k] : 0ull;
-        const bool qual = k < len && (double)__uint_as_float((uint32_t)(c >> 12)) < 0.1;
-        const int li = (int)(c & 0xfffull);
-        const unsigned qm = __ballot_sync(0xffffffffu, qual);
-        const int nvalid = qm == 0xffffffffu ? 32 : __ffs(~qm) - 1;
-        bool alive = lane < nvalid && !picked[li];
-        uint32_t gbits = 0;
-        if (lane < nvalid) {
-#pragma unroll
-          for (int l = 1; l <= 5; ++l) gbits |= (uint32_t)(gap[li + l] != 0) << (l - 1);
-#pragma unroll
-          for (int l = 1; l <= 5; ++l) gbits |= (uint32_t)(gap[li - l + 1] != 0) << (4 + l);
-        }
-        for (;;) {
-          const unsigned m = __ballot_sync(0xffffffffu, alive);
-          if (!m) break;
-          smallest++;
-          const bool last = smallest >= 4;                                // :359-362: the 4th flat point is neither marked nor suppressing
-          const int pli = d_pick_one(m, li, gbits, alive, picked, lane, !last);
-          if (lane == 0) { label[pli] = -1; out[22 + n_flat] = pli + rs; }
-          n_flat++;
-          if (last) { done = true; break; }
-        }
-        if (nvalid < 32) break;
-      }
-      __syncwarp();
-      if (lane == 0) { pick_cnt[r * 18 + j * 3 + 0] = n_sharp; pick_cnt[r * 18 + j * 3 + 1] = n_ls; pick_cnt[r * 18 + j * 3 + 2] = n_flat; }
     }
+    __syncthreads();
   }
   __syncthreads();
   SCR_STAMP(3);
