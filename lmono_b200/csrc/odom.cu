@@ -12,6 +12,12 @@
 //   LM solve     :494-499   lm.cu (shared with laserMapping)
 //   k_odom_finish:504-505   t_w_curr += q_w_curr * t_last_curr ; q_w_curr *= q_last_curr
 // The "last" clouds (:554-563) stay resident on the device between sweeps.
+//
+// Measured and rejected (round 2, profiles/odom_nn_box_r02.txt): an exact 1-NN that prunes 32-point tiles of the last cloud
+// by their bounding boxes.  The clouds come ring by ring, so a tile is an arc of one ring; near the sensor those arcs
+// span tens of degrees and their boxes contain most features of the neighbouring rings (bound 0), so few tiles are pruned
+// and the search becomes a chain of dependent L2 round trips: 48 us per pass (131 us with per-round re-pruning) against
+// 32 us for the tiled brute force, which streams the targets through shared memory at 82 % issue utilisation.
 #include "common.cuh"
 #include <string.h>
 #include <stdlib.h>
@@ -36,8 +42,6 @@ struct OdomState {
   int32_t* d_corr;                  // test hook: [n_sharp*2] + [n_flat*3]
   float* d_frac[2];                 // DISTORTION 1: fractional intensity of every sharp / flat feature (factor ratio s = frac / 0.1)
   int32_t* d_ringtab;               // [2][RT_STRIDE]: per last cloud, first index with ring >= r (r = 0..65) and a "sorted by ring" flag at [66]
-  float4* d_box;                    // [2][box_stride][2]: bounding box of every 32-point tile of the two last clouds (k_odom_ring_table)
-  int box_stride;
   int cap;
 };
 
@@ -136,124 +140,6 @@ __global__ void __launch_bounds__(NN_QB * NN_SUB) k_odom_nn1(const OdomDev* __re
   if (sub == 0 && qi < nq && bestk != ~0ULL) atomicMin(&best[qi], bestk);
 }
 
-// ---- exact 1-NN by bounding-box pruning (replaces the tiled brute force above; LMONO_ODOM_NN=brute keeps it for A/B runs)
-// The last clouds come ring by ring in firing order, so 32 consecutive points are a short arc of one ring: a compact
-// box.  One warp per feature: lane l computes the lower bound of the fp32 squared distance to the boxes of tiles l, l + 32,
-// ...; the tile with the smallest bound seeds the best (d2, index) key; afterwards only tiles whose bound does not exceed
-// the best d2 so far are scanned (one coalesced 512-byte load each).  The bound is evaluated with the same rounded
-// operations as the distance itself (fl(a - b), fl(x * x), fl(x + y) are monotonic), so bound <= d2 holds bit for bit and
-// the result -- including the (d2, index) tie rule -- equals the brute-force scan.  ~400 of the ~25 000 candidates of an
-// HDL-64 less-flat cloud are touched per feature.
-__device__ __forceinline__ float d_box_lb(float4 b0, float4 b1, float4 q) {
-  const float ex = fmaxf(fmaxf(__fsub_rn(b0.x, q.x), __fsub_rn(q.x, b0.w)), 0.f);
-  const float ey = fmaxf(fmaxf(__fsub_rn(b0.y, q.y), __fsub_rn(q.y, b1.x)), 0.f);
-  const float ez = fmaxf(fmaxf(__fsub_rn(b0.z, q.z), __fsub_rn(q.z, b1.y)), 0.f);
-  return __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
-}
-__device__ __forceinline__ unsigned long long d_nn_point_key(float4 sel, float4 p, int j) {
-  const float dx = __fsub_rn(sel.x, p.x), dy = __fsub_rn(sel.y, p.y), dz = __fsub_rn(sel.z, p.z);
-  float d = __fmul_rn(dx, dx);
-  d = __fadd_rn(d, __fmul_rn(dy, dy));
-  d = __fadd_rn(d, __fmul_rn(dz, dz));
-  return ((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)j;
-}
-__device__ __forceinline__ unsigned long long d_warp_min_u64(unsigned long long v);
-
-constexpr int NB_LIST = 64;       // tiles a warp collects before it scans them (eight coalesced loads in flight per step)
-constexpr int NB_CHUNK = 1024;    // tiles (32 768 points) whose boxes a CTA stages in shared memory per outer trip
-// scan the collected tiles, eight coalesced loads in flight per round; the bound tightens after every round (warp-min) and
-// list entries whose box bound has fallen behind it are skipped
-__device__ __forceinline__ unsigned long long d_nn_scan_list(const float4* __restrict__ last, int nl, float4 sel, const unsigned short* list,
-                                                             const uint32_t* list_lb, int cnt, int tile0, int lane, unsigned long long bestk) {
-  int i = 0;
-  while (i < cnt) {
-    int j[8]; float4 p[8];
-    const uint32_t thr = (uint32_t)(bestk >> 32);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      while (i < cnt && list_lb[i] > thr) ++i;              // warp-uniform
-      j[u] = i < cnt ? (tile0 + (int)list[i]) * 32 + lane : nl;
-      if (i < cnt) ++i;
-      if (j[u] < nl) p[u] = last[j[u]];
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) if (j[u] < nl) { const unsigned long long k = d_nn_point_key(sel, p[u], j[u]); bestk = k < bestk ? k : bestk; }
-    bestk = d_warp_min_u64(bestk);
-  }
-  return bestk;
-}
-
-// flat features against surf_last (the corner cloud is sparse along its rings -- its tiles are long arcs with useless
-// boxes -- and small: it keeps the brute-force kernel)
-__global__ void __launch_bounds__(256, 2) k_odom_nn_box(const OdomDev* __restrict__ o, const float4* __restrict__ flat, const float4* __restrict__ surf_last,
-                                                        const float4* __restrict__ box, unsigned long long* __restrict__ best) {
-  lm_pdl_enter();
-  __shared__ float4 s_b0[NB_CHUNK], s_b1[NB_CHUNK];
-  __shared__ unsigned short s_list[8][NB_LIST];
-  __shared__ uint32_t s_list_lb[8][NB_LIST];
-  if (!o->do_solve) return;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const int nf = o->n_flat, nl = o->n_surf_last;
-  if ((int)(blockIdx.x * blockDim.x) >> 5 >= nf) return;          // CTA-uniform
-  const bool active = warp < nf;
-  const int qi = active ? warp : 0;
-  if (nl <= 0) { if (active && lane == 0) best[qi] = ~0ULL; return; }
-  const float4* __restrict__ last = surf_last;
-  const float4 sel = d_to_start(o, flat[qi]);
-  const int ntile = (nl + 31) >> 5;
-  unsigned short* list = s_list[threadIdx.x >> 5];
-  uint32_t* list_lb = s_list_lb[threadIdx.x >> 5];
-  unsigned long long bestk = ~0ULL;
-  for (int tile0 = 0; tile0 < ntile; tile0 += NB_CHUNK) {
-    __syncthreads();
-    for (int t = threadIdx.x; t < NB_CHUNK && tile0 + t < ntile; t += blockDim.x) { s_b0[t] = box[2 * (tile0 + t)]; s_b1[t] = box[2 * (tile0 + t) + 1]; }
-    __syncthreads();
-    if (!active) continue;
-    uint32_t lbs[32];                                 // lane l keeps the bounds of tiles l, l + 32, ... of this chunk
-#pragma unroll
-    for (int k = 0; k < 32; ++k) { const int t = k * 32 + lane; lbs[k] = tile0 + t < ntile ? __float_as_uint(d_box_lb(s_b0[t], s_b1[t], sel)) : 0xffffffffu; }
-    if (tile0 == 0) {
-      // seed: the tile whose box CENTRE is nearest (many boxes contain the feature -- bound 0 -- and most of those are long
-      // arcs far away; the nearest centre is a small box close by, so the first bound is already about the true distance)
-      unsigned long long seedk = ~0ULL;
-#pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const int t = k * 32 + lane;
-        if (t < ntile) {
-          const float4 b0 = s_b0[t], b1 = s_b1[t];
-          const float cx = sel.x - 0.5f * (b0.x + b0.w), cy = sel.y - 0.5f * (b0.y + b1.x), cz = sel.z - 0.5f * (b0.z + b1.y);
-          const unsigned long long v = ((unsigned long long)__float_as_uint(cx * cx + cy * cy + cz * cz) << 32) | (uint32_t)t;
-          seedk = v < seedk ? v : seedk;
-        }
-      }
-      const int seed = (int)(uint32_t)d_warp_min_u64(seedk);
-      const int j = seed * 32 + lane;
-      if (j < nl) bestk = d_nn_point_key(sel, last[j], j);
-      bestk = d_warp_min_u64(bestk);
-    }
-    int cnt = 0;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      if (tile0 + k * 32 >= ntile) break;             // warp-uniform
-      unsigned m = __ballot_sync(0xffffffffu, lbs[k] <= (uint32_t)(bestk >> 32));
-      if (!m) continue;
-      if (cnt + __popc(m) > NB_LIST) {                // list full: scan what is collected, the tighter bound prunes the rest
-        __syncwarp();
-        bestk = d_nn_scan_list(last, nl, sel, list, list_lb, cnt, tile0, lane, bestk);
-        cnt = 0;
-        m = __ballot_sync(0xffffffffu, lbs[k] <= (uint32_t)(bestk >> 32));
-      }
-      if ((m >> lane) & 1u) { const int pos = cnt + __popc(m & ((1u << lane) - 1u)); list[pos] = (unsigned short)(k * 32 + lane); list_lb[pos] = lbs[k]; }
-      cnt += __popc(m);
-    }
-    __syncwarp();
-    bestk = d_nn_scan_list(last, nl, sel, list, list_lb, cnt, tile0, lane, bestk);
-    __syncwarp();
-  }
-  if (active && lane == 0) best[qi] = bestk;
-}
-
 __device__ __forceinline__ float d_sqdis(float4 a, float4 sel) {
   // (a.x - sel.x)*(a.x - sel.x) + (a.y - sel.y)*(a.y - sel.y) + (a.z - sel.z)*(a.z - sel.z), fp32 (:322-327)
   const float dx = __fsub_rn(a.x, sel.x), dy = __fsub_rn(a.y, sel.y), dz = __fsub_rn(a.z, sel.z);
@@ -274,28 +160,12 @@ __device__ __forceinline__ unsigned long long d_warp_min_u64(unsigned long long 
 // scan with the reference's break rule.  blockIdx.x: 0 corner_last, 1 surf_last.
 constexpr int RT_CTAS = 16;       // CTAs per cloud for the monotonicity check (k_odom_begin arms the flags)
 __global__ void __launch_bounds__(256) k_odom_ring_table(const OdomDev* __restrict__ o, const float4* __restrict__ corner_last,
-                                                         const float4* __restrict__ surf_last, int32_t* __restrict__ tab_all,
-                                                         float4* __restrict__ box_all, int box_stride) {
+                                                         const float4* __restrict__ surf_last, int32_t* __restrict__ tab_all) {
   lm_pdl_enter();
   const int c = blockIdx.y;
   const float4* __restrict__ pts = c == 0 ? corner_last : surf_last;
   const int n = c == 0 ? o->n_corner_last : o->n_surf_last;
   int32_t* tab = tab_all + c * RT_STRIDE;
-  {   // bounding boxes of the 32-point tiles (k_odom_nn_box): one warp per tile
-    float4* __restrict__ box = box_all + (size_t)c * box_stride * 2;
-    const int lane = threadIdx.x & 31, ntile = (n + 31) >> 5;
-    for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < ntile; t += (gridDim.x * blockDim.x) >> 5) {
-      const int j = t * 32 + lane;
-      float mn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, mx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
-      if (j < n) { const float4 p = pts[j]; mn[0] = mx[0] = p.x; mn[1] = mx[1] = p.y; mn[2] = mx[2] = p.z; }
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-#pragma unroll
-        for (int ofs = 16; ofs > 0; ofs >>= 1) { mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], ofs)); mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], ofs)); }
-      }
-      if (lane == 0) { box[2 * t] = make_float4(mn[0], mn[1], mn[2], mx[0]); box[2 * t + 1] = make_float4(mx[1], mx[2], 0.f, 0.f); }
-    }
-  }
   int bad = 0;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {   // ring ids outside [0, 64] (never produced by scanRegistration) also take the step-wise scan
     const int r = (int)pts[j].w;
@@ -491,8 +361,6 @@ static int odom_state(lmono_ctx* ctx, OdomState** out) {
   for (int k = 0; k < 2; ++k) { LM_CUDA(cudaMalloc((void**)&s->d_last[k], n * sizeof(float4))); LM_CUDA(cudaMalloc((void**)&s->d_best[k], n * sizeof(unsigned long long))); }
   LM_CUDA(cudaMalloc((void**)&s->d_corr, n * 10 * sizeof(int32_t)));
   LM_CUDA(cudaMalloc((void**)&s->d_ringtab, 2 * RT_STRIDE * sizeof(int32_t)));
-  s->box_stride = (int)(n / 32 + 2);
-  LM_CUDA(cudaMalloc((void**)&s->d_box, (size_t)2 * s->box_stride * 2 * sizeof(float4)));
   for (int k = 0; k < 2; ++k) LM_CUDA(cudaMalloc((void**)&s->d_frac[k], n * sizeof(float)));
   k_odom_reset<<<1, 32, 0, ctx->stream>>>(s->d, ctx->prm.distortion ? 1 : 0);
   LM_LAUNCH_CHECK();
@@ -510,7 +378,7 @@ void lm_odom_free(lmono_ctx* ctx) {
   cudaFree(s->d); cudaFreeHost(s->h);
   for (int k = 0; k < 4; ++k) cudaFree(s->d_feat[k]);
   for (int k = 0; k < 2; ++k) { cudaFree(s->d_last[k]); cudaFree(s->d_best[k]); }
-  cudaFree(s->d_corr); cudaFree(s->d_ringtab); cudaFree(s->d_box); cudaFree(s->d_frac[0]); cudaFree(s->d_frac[1]);
+  cudaFree(s->d_corr); cudaFree(s->d_ringtab); cudaFree(s->d_frac[0]); cudaFree(s->d_frac[1]);
   free(s); ctx->odom_state = nullptr;
 }
 
@@ -518,20 +386,13 @@ void lm_odom_free(lmono_ctx* ctx) {
 static int odom_associate(lmono_ctx* ctx, OdomState* s, const float4* sharp, int n_sharp, const float4* flat, int n_flat, int nl_max0, int nl_max1, int pass) {
   const int nq = n_sharp > n_flat ? n_sharp : n_flat;
   if (nq <= 0) return LMONO_OK;
-  static const bool brute = getenv("LMONO_ODOM_NN") && !strcmp(getenv("LMONO_ODOM_NN"), "brute");
-  // corner features: tiled brute force (blockIdx.z = 0 only); flat features: box-pruned search unless LMONO_ODOM_NN=brute
-  LM_LAUNCH_PDL(k_odom_best_init, lm_div_up(nq, 256), 256, 0, s->d_best[0], n_sharp, s->d_best[1], brute ? n_flat : 0);
+  LM_LAUNCH_PDL(k_odom_best_init, lm_div_up(nq, 256), 256, 0, s->d_best[0], n_sharp, s->d_best[1], n_flat);
   LM_LAUNCH_CHECK();
-  const int nlm = brute ? (nl_max0 > nl_max1 ? nl_max0 : nl_max1) : nl_max0;
-  const int nqb = brute ? nq : n_sharp;
-  if (nlm > 0 && nqb > 0) {
+  const int nlm = nl_max0 > nl_max1 ? nl_max0 : nl_max1;
+  if (nlm > 0) {
     const int gy = lm_div_up(nlm, NN_CHUNK);
-    dim3 grid(lm_div_up(nqb, NN_QB), gy < 48 ? gy : 48, brute ? 2 : 1);
+    dim3 grid(lm_div_up(nq, NN_QB), gy < 48 ? gy : 48, 2);
     LM_LAUNCH_PDL(k_odom_nn1, grid, NN_QB * NN_SUB, 0, s->d, sharp, flat, s->d_last[0], s->d_last[1], s->d_best[0], s->d_best[1]);
-    LM_LAUNCH_CHECK();
-  }
-  if (!brute && n_flat > 0) {
-    LM_LAUNCH_PDL(k_odom_nn_box, lm_div_up(n_flat * 32, 256), 256, 0, s->d, flat, s->d_last[1], s->d_box + (size_t)s->box_stride * 2, s->d_best[1]);
     LM_LAUNCH_CHECK();
   }
   const int warps = n_sharp + n_flat;
@@ -549,7 +410,7 @@ int lm_odom_enqueue(lmono_ctx* ctx, const float4* sharp, int n_sharp, const floa
   OdomState* s; int rc = odom_state(ctx, &s); if (rc) return rc;
   LM_LAUNCH_PDL(k_odom_begin, 1, 32, 0, s->d, n_sharp, n_ls, n_flat, n_lf, d_counts, s->cap, s->d_ringtab);
   LM_LAUNCH_CHECK();
-  LM_LAUNCH_PDL(k_odom_ring_table, dim3(RT_CTAS, 2), 256, 0, s->d, s->d_last[0], s->d_last[1], s->d_ringtab, s->d_box, s->box_stride);
+  LM_LAUNCH_PDL(k_odom_ring_table, dim3(RT_CTAS, 2), 256, 0, s->d, s->d_last[0], s->d_last[1], s->d_ringtab);
   LM_LAUNCH_CHECK();
   for (int opti = 0; opti < 2; ++opti) {                       // :278
     if ((rc = odom_associate(ctx, s, sharp, n_sharp, flat, n_flat, prev_ls_max, prev_lf_max, opti))) return rc;

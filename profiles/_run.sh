@@ -1,4 +1,4 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_scanreg.py tests/test_gpu_pipeline.py tests/test_golden.py tests/test_gpu_odom.py -m gpu -x -q 2>&1 | tail -5
-timeout 400 python profiles/quick.py s sweep 2>&1 | grep -v "^\[lmono" | grep "fused sweep\|k_scan_ring\|k_odom_nn\|mapping ms"
+timeout 600 python -m pytest tests/test_gpu_odom.py tests/test_gpu_pipeline.py tests/test_gpu_consumer.py -m gpu -x -q 2>&1 | tail -5
+timeout 400 python profiles/quick.py t sweep 2>&1 | grep -v "^\[lmono" | grep "fused sweep\|k_scan_ring\|k_odom_nn\|mapping ms"
