@@ -478,34 +478,43 @@ def run_ours(args):
         return r
 
     nraw = RAW_CORNER + RAW_SURF
-    others = [roof("k_lm_solve_cluster", 64.0 * nfac * max(evals, 1) / 2.0, "one LM solve: E evaluations x F factors x 64 B (SURVEY 8d); fp64-latency bound, factors stay in shared memory after the first pass"),
-              roof("k_assoc_fit", 160.0 * nq, "line / plane fit: 5 neighbours + query + factor record per query"),
-              roof("k_sort_tiles", 16.0 * nraw, "register bitonic tile sort: 8 B key read + write"),
-              roof("k_merge_ranks_smem", 16.0 * nraw, "rank merge of the sorted tiles in shared memory"),
-              roof("k_vg_write", 8.0 * nraw + 16.0 * nraw + 16.0 * nq, "VoxelGrid centroids of both feature clouds")]
-    knn8 = roof("k_assoc_knn", 116.0 * nq, "latency form of the exact 5-NN (8 lanes per query), used when a sequence runs alone on the GPU")
-    if knn8:
-        others.insert(0, knn8)
-    knn = roof("k_assoc_knn1", 116.0 * nq, "exact 5-NN: 16 B query + 5 x 16 B neighbours + 5 x 4 B indices per query (SURVEY 8d)") or {}
+    cand = [roof("k_assoc_knn1", 116.0 * nq, "exact 5-NN, throughput form (one thread per query; the form the batched step runs): 16 B query + 5 x 16 B neighbours + 5 x 4 B indices per query (SURVEY 8d)"),
+            roof("k_assoc_knn", 116.0 * nq, "exact 5-NN, latency form (8 lanes per query), used when a sequence runs alone on the GPU"),
+            roof("k_lm_solve_cluster", 64.0 * nfac * max(evals, 1) / 2.0, "one LM solve: E evaluations x F factors x 64 B (SURVEY 8d); fp64-latency bound, factors stay in shared memory after the first pass"),
+            roof("k_assoc_fit", 160.0 * nq, "line / plane fit: 5 neighbours + query + factor record per query"),
+            roof("k_sort_tiles", 16.0 * nraw, "register bitonic tile sort: 8 B key read + write"),
+            roof("k_merge_ranks_smem", 16.0 * nraw, "rank merge of the sorted tiles in shared memory"),
+            roof("k_vg_write", 8.0 * nraw + 16.0 * nraw + 16.0 * nq, "VoxelGrid centroids of both feature clouds"),
+            roof("k_rf_tailscan", 24.0 * nq + 32.0 * nq, "refilter: new points searched in their cube's voxel keys, hit centroids updated in place (16 B point + 4 B key + 4 B bound per new point, 32 B per touched centroid)")]
+    cand = [r for r in cand if r]
+    # the dominant kernel = the one with the largest share of the step in the forms the headline `value` runs (throughput forms)
+    dom_name = max((r["kernel"] for r in cand), key=lambda k: kern_us_tp.get(k, kern_us.get(k, 0.0)))
+    dom = next(r for r in cand if r["kernel"] == dom_name)
+    others = [r for r in cand if r is not dom]
+    knn = next((r for r in cand if r["kernel"] == "k_assoc_knn1"), {})
+    SURVEY_BYTES_PER_REGISTRATION = 29e6          # whole laserMapping pass of config C-3
+    whole = SURVEY_BYTES_PER_REGISTRATION * value / 1e9              # all GPUs
     roofline = {
-        "bound": "hbm", "kernel": "k_assoc_knn1 (exact 5-NN of every feature against the cube map, throughput form = the one the batched step runs; one launch per outer iteration)",
-        "achieved": knn.get("achieved"), "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
-        "frac": knn.get("frac"), "traffic": knn.get("traffic"),
+        "bound": "hbm", "kernel": dom["kernel"] + " -- " + dom["what"] + " (largest share of the step among the kernels of the batched step)",
+        "achieved": dom.get("achieved"), "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
+        "frac": dom.get("frac"), "traffic": dom.get("traffic"),
         "traffic_source": "STATIC: dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture committed as profiles/" + ncu_file + " (cold caches per ncu replay; not re-measured in this run)",
-        "algorithmic_bytes_per_launch": knn.get("algorithmic_bytes_per_launch"), "avg_launch_ms": knn.get("avg_launch_ms"),
+        "algorithmic_bytes_per_launch": dom.get("algorithmic_bytes_per_launch"), "avg_launch_ms": dom.get("avg_launch_ms"),
+        "whole_step": {"algorithmic_bytes_per_registration": SURVEY_BYTES_PER_REGISTRATION, "achieved": whole / world, "frac": whole / world / hbm_peak, "unit": "GB/s per GPU",
+                       "what": "SURVEY 8(d) bytes of one registration x registrations per step / ms_per_step (the headline leg)"},
         "timing": "one sequence alone on the GPU, un-graphed step, CUDA event after every launch",
         "queries_per_launch": int(nq), "knn_queries_per_s": nq / (knn["avg_launch_ms"] * 1e-3) if knn.get("avg_launch_ms") else None,
         "knn_queries_per_s_batched": 2.0 * nq * value,
-        "l2_hit_pct_ncu": knn.get("l2_hit_pct_ncu"),
+        "l2_hit_pct_ncu": dom.get("l2_hit_pct_ncu"),
         "kernel_us_per_step": {k: round(v, 2) for k, v in sorted(kern_us.items(), key=lambda kv: -kv[1])},
         "kernel_us_per_step_throughput_forms": {k: round(v, 2) for k, v in sorted(kern_us_tp.items(), key=lambda kv: -kv[1])},
         "kernel_us_note": "CUDA-event deltas between consecutive launches of the un-graphed step of ONE sequence: each includes ~3 us of event + launch gap, "
                           "so the sum exceeds ms_per_step (graph replay); profiles/ holds the ncu launch list of the same command and the "
-                          "timeline of the batched step (profiles/batch_timeline_r01.txt)",
+                          "timeline of the batched step (profiles/batch_timeline_r02_s8.txt)",
         "other_kernels": [r for r in others if r],
         "note": "the map (~16 MB + 16 MB index) fits the 126 MB L2 and one registration moves ~30-60 MB algorithmically (5-10 us of HBM time): "
                 "the step is bound by dependent L2 / HBM round trips, fp64 latency and ~27 launches, not by HBM bandwidth (DESIGN.md section 4); "
-                "whole-GPU counters of the batched step: profiles/batch_range_r01.csv",
+                "whole-GPU counters of the batched step: profiles/batch_range_r02.csv",
     }
 
     line = {

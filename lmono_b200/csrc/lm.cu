@@ -241,6 +241,8 @@ __device__ double d_gradient_max_norm(const double* x, const double* g) {
 // software sequence on the single controller thread).  The step differs from a divide-based Cholesky in the
 // last ulps only; north_star compares poses at 1e-4 and normal equations at 1e-5.
 __device__ __forceinline__ int d_chol6(const double* A /*21*/, const double* b, double* y) {
+  // explicit fp64 FMAs (the TU is built with -fmad=false): every s -= a * b of the three dependent chains below is one
+  // instruction instead of two
   double L[21];       // lower factor, L(i,j), j <= i, at d_tri(j, i)
   double inv[6];      // 1 / L(i,i)
   int bad = 0;
@@ -250,7 +252,7 @@ __device__ __forceinline__ int d_chol6(const double* A /*21*/, const double* b, 
     for (int j = 0; j <= i; ++j) {
       double s = A[d_tri(j, i)];
 #pragma unroll
-      for (int k = 0; k < j; ++k) s -= L[d_tri(k, i)] * L[d_tri(k, j)];
+      for (int k = 0; k < j; ++k) s = fma(-L[d_tri(k, i)], L[d_tri(k, j)], s);
       if (i == j) { if (!(s > 0.0)) bad = 1; inv[i] = rsqrt(s); L[d_tri(i, i)] = s * inv[i]; }
       else L[d_tri(j, i)] = s * inv[j];
     }
@@ -261,14 +263,14 @@ __device__ __forceinline__ int d_chol6(const double* A /*21*/, const double* b, 
   for (int i = 0; i < 6; ++i) {
     double s = b[i];
 #pragma unroll
-    for (int k = 0; k < i; ++k) s -= L[d_tri(k, i)] * z[k];
+    for (int k = 0; k < i; ++k) s = fma(-L[d_tri(k, i)], z[k], s);
     z[i] = s * inv[i];
   }
 #pragma unroll
   for (int i = 5; i >= 0; --i) {
     double s = z[i];
 #pragma unroll
-    for (int k = i + 1; k < 6; ++k) s -= L[d_tri(i, k)] * y[k];
+    for (int k = i + 1; k < 6; ++k) s = fma(-L[d_tri(i, k)], y[k], s);
     y[i] = s * inv[i];
   }
   return 0;
@@ -314,11 +316,11 @@ __device__ int d_compute_step(LmLmState* lm) {
       double sg = 0.0, sHs = 0.0;
 #pragma unroll
       for (int a = 0; a < 6; ++a) {
-        sg += step[a] * gs[a];
+        sg = fma(step[a], gs[a], sg);
         double row = 0.0;
 #pragma unroll
-        for (int b = 0; b < 6; ++b) row += Hs[d_tri(a, b)] * step[b];
-        sHs += step[a] * row;
+        for (int b = 0; b < 6; ++b) row = fma(Hs[d_tri(a, b)], step[b], row);
+        sHs = fma(step[a], row, sHs);
       }
       lm->model_cost_change = -(sg + 0.5 * sHs);
       lm->inv_model_cost_change = 1.0 / lm->model_cost_change;      // off the chain: overlaps the candidate's Plus below
