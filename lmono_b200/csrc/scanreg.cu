@@ -301,6 +301,92 @@ __device__ __forceinline__ void d_bitonic_regs2(unsigned long long (&va)[ITEMS],
   }
 }
 
+__device__ __forceinline__ void d_named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
+
+// d_bitonic_regs for a GROUP of NTHREADS threads of the CTA (t = index inside the group): the cross-warp stages meet at the
+// group's own named barrier, so several groups sort different arrays at the same time and the rest of the CTA does not wait
+template <int ITEMS, int NTHREADS>
+__device__ __forceinline__ void d_bitonic_regs_group(unsigned long long (&v)[ITEMS], int t, unsigned long long* xch, int bar_id) {
+  constexpr int N = ITEMS * NTHREADS;
+  constexpr int LOGN = (N <= 1) ? 0 : (31 - __builtin_clz((unsigned)N));
+  static_assert((1 << LOGN) == N, "ITEMS * NTHREADS must be a power of two");
+#pragma unroll
+  for (int lk = 1; lk <= LOGN; ++lk) {
+    const int k = 1 << lk;
+#pragma unroll
+    for (int lj = lk - 1; lj >= 0; --lj) {
+      const int j = 1 << lj;
+      if (j >= 32 * ITEMS) {
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) xch[t * ITEMS + r] = v[r];
+        d_named_bar(bar_id, NTHREADS);
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) {
+          const int i = t * ITEMS + r;
+          const unsigned long long o = xch[i ^ j];
+          const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+          v[r] = keep_min ? (v[r] < o ? v[r] : o) : (v[r] < o ? o : v[r]);
+        }
+        d_named_bar(bar_id, NTHREADS);
+      } else if (j >= ITEMS) {
+        const int lane_x = j / ITEMS;
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) {
+          const int i = t * ITEMS + r;
+          const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[r], lane_x);
+          const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+          v[r] = keep_min ? (v[r] < o ? v[r] : o) : (v[r] < o ? o : v[r]);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) {
+          if ((r & j) == 0 && (r | j) < ITEMS) {
+            const int i = t * ITEMS + r;
+            d_cmpx(v[r], v[r | j], (i & k) == 0);
+          }
+        }
+      }
+    }
+  }
+}
+
+// :284-288 one sector (<= 512 points) sorted by ONE group of 128 threads, 4 keys each: a 512-key network has 45 stages, the
+// 2048-key network over all six sectors 66.  Key = curvature bits (32) | local index (12), ascending.
+__device__ __forceinline__ void d_group_sort_sector(unsigned long long* out, unsigned long long* xch, const float* __restrict__ curv,
+                                                    int rs, int sp, int len, int t, int bar_id) {
+  unsigned long long v[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int e = t * 4 + r;
+    v[r] = e < len ? (((unsigned long long)__float_as_uint(curv[sp + e]) << 12) | (unsigned long long)(sp + e - rs)) : ~0ULL;
+  }
+  d_bitonic_regs_group<4, 128>(v, t, xch, bar_id);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) { const int e = t * 4 + r; if (e < len) out[e] = v[r]; }
+}
+
+// :401-405 the voxel order of the ring's points (see d_block_sort_ring) by a group of 512 threads, 4 keys each, while the
+// six picking warps work
+__device__ __forceinline__ void d_group_sort_voxels(unsigned long long* out, const float* xyz, int rs, int S, int n, float inv, int t, int bar_id) {
+  unsigned long long v[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int e = t * 4 + r;
+    unsigned long long c = ~0ULL;
+    if (e < n) {
+      const int li = S + e - rs;
+      const int vx = min(max((int)floorf(__fmul_rn(xyz[li * 3], inv)), -32768), 32767) + 32768;
+      const int vy = min(max((int)floorf(__fmul_rn(xyz[li * 3 + 1], inv)), -32768), 32767) + 32768;
+      const int vz = min(max((int)floorf(__fmul_rn(xyz[li * 3 + 2], inv)), -32768), 32767) + 32768;
+      c = ((unsigned long long)vz << 44) | ((unsigned long long)vy << 28) | ((unsigned long long)vx << 12) | (unsigned long long)li;
+    }
+    v[r] = c;
+  }
+  d_bitonic_regs_group<4, 512>(v, t, out, bar_id);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) out[t * 4 + r] = v[r];
+}
+
 // The two sorts of a ring, over the same n = E - S points, as one pass:
 //  A  :284-288 the six sector sorts as ONE network over sector (3 bits) | curvature bits (32) | local index (12):
 //     ascending (curvature, index) inside each sector, the sectors one behind the other;
@@ -505,8 +591,23 @@ __global__ void __launch_bounds__(SCR_THREADS, 1) k_scan_ring(const float4* __re
   // function of two neighbours, so every thread evaluates its share once here ((a - b)^2 == (b - a)^2 exactly, one array
   // serves both walking directions)
   for (int i = threadIdx.x; i < L; i += blockDim.x) gap[i] = (i > 0 && d_gap_exceeds(xyz, i, i - 1)) ? 1 : 0;
-  if (n <= 2 * SCR_THREADS) d_block_sort_ring<2>(sec, vox, curv, xyz, rs, S, E, inv);
-  else d_block_sort_ring<4>(sec, vox, curv, xyz, rs, S, E, inv);
+  // Usual ring (<= 2048 points, sectors <= 512): each sector is sorted by its own group of four warps, then the six picking
+  // warps and a 512-thread group that sorts the voxel keys run side by side.  Larger rings: both sorts as two block-wide
+  // networks first (d_block_sort_ring), then the pick.
+  const bool fast = n <= 2048 && (n + 5) / 6 <= 512;
+  __shared__ uint32_t s_spill[6];
+  if (fast) {
+    __syncthreads();                                   // gap[] and xyz[] complete
+    if (wid < 24) {
+      const int g = wid >> 2;
+      const int sp = S + n * g / 6, ep = S + n * (g + 1) / 6 - 1;
+      d_group_sort_sector(sec + (sp - S), vox + g * 512, curv, rs, sp, ep - sp + 1, threadIdx.x - g * 128, 1 + g);
+    }
+    __syncthreads();
+  } else {
+    if (n <= 2 * SCR_THREADS) d_block_sort_ring<2>(sec, vox, curv, xyz, rs, S, E, inv);
+    else d_block_sort_ring<4>(sec, vox, curv, xyz, rs, S, E, inv);
+  }
   SCR_STAMP(2);
 
   // :291-390 greedy picking.  The reference walks the six sectors one after the other, and a pick suppresses up to five
@@ -515,23 +616,24 @@ __global__ void __launch_bounds__(SCR_THREADS, 1) k_scan_ring(const float4* __re
   // So six warps pick their sectors at once, each assuming no incoming marks, and a short ordered check follows: if the
   // (final) forward marks of sector j - 1 hit a point that sector j picked, sector j is picked again with those marks (about
   // one border in ten), which may in turn change what it passes on.  Same picks as the sequential walk.
-  __shared__ uint32_t s_spill[6];
   if (wid < 6) {
     const uint32_t sp_ = d_pick_sector(wid, 0u, false, sec, S, n, rs, r, picked, gap, label, pick_idx, pick_cnt, lane);
     if (lane == 0) s_spill[wid] = sp_;
-  }
-  __syncthreads();
-  for (int j = 1; j < 6; ++j) {
-    if (wid == j) {
-      const uint32_t inc = s_spill[j - 1];
-      const int lo = S + n * j / 6 - rs, hi = S + n * (j + 1) / 6 - 1 - rs;
-      const bool hit = lane < 5 && ((inc >> lane) & 1u) && lo + lane <= hi && label[lo + lane] != 0;
-      if (__any_sync(0xffffffffu, hit)) {
-        const uint32_t sp_ = d_pick_sector(j, inc, true, sec, S, n, rs, r, picked, gap, label, pick_idx, pick_cnt, lane);
-        if (lane == 0) s_spill[j] = sp_;
+    d_named_bar(8, 192);
+    for (int j = 1; j < 6; ++j) {
+      if (wid == j) {
+        const uint32_t inc = s_spill[j - 1];
+        const int lo = S + n * j / 6 - rs, hi = S + n * (j + 1) / 6 - 1 - rs;
+        const bool hit = lane < 5 && ((inc >> lane) & 1u) && lo + lane <= hi && label[lo + lane] != 0;
+        if (__any_sync(0xffffffffu, hit)) {
+          const uint32_t sp2 = d_pick_sector(j, inc, true, sec, S, n, rs, r, picked, gap, label, pick_idx, pick_cnt, lane);
+          if (lane == 0) s_spill[j] = sp2;
+        }
       }
+      d_named_bar(8, 192);
     }
-    __syncthreads();
+  } else if (fast && wid >= 8 && wid < 24) {
+    d_group_sort_voxels(vox, xyz, rs, S, n, inv, threadIdx.x - 256, 7);
   }
   __syncthreads();
   SCR_STAMP(3);
