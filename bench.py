@@ -458,7 +458,7 @@ def run_ours(args):
     nfac = rep.corner_num[1] + rep.surf_num[1]
     evals = sum(s_.iterations + 1 for s_ in rep.solve)
     ncu = {}
-    ncu_file = "ncu_r02_full_metrics.json"
+    ncu_file = "ncu_r02_final_full_metrics.json"
     try:
         for l in json.load(open(os.path.join(ROOT, "profiles", ncu_file)))["launches"]:
             ncu.setdefault(l["kernel"], []).append(l)
@@ -514,7 +514,7 @@ def run_ours(args):
         "other_kernels": [r for r in others if r],
         "note": "the map (~16 MB + 16 MB index) fits the 126 MB L2 and one registration moves ~30-60 MB algorithmically (5-10 us of HBM time): "
                 "the step is bound by dependent L2 / HBM round trips, fp64 latency and ~27 launches, not by HBM bandwidth (DESIGN.md section 4); "
-                "whole-GPU counters of the batched step: profiles/batch_range_r02.csv",
+                "whole-GPU counters of the batched step: profiles/batch_range_r02_s8.csv",
     }
 
     line = {

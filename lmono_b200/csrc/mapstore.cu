@@ -534,31 +534,45 @@ __global__ void __launch_bounds__(RF_TS_THREADS) k_rf_tailscan(LmMapState* __res
       const float il = M.inv_leaf;
       if (threadIdx.x == 0) { s_mover = 0; s_badkey = 0; }
       __syncthreads();
-      for (int phase = 0; phase < 2; ++phase) {
-        const bool patch = phase == 1 && !s_mover;
+      // pass 1: every hit centroid is recomputed and written to the canonical buffer (that update is unconditional); a
+      // centroid that left its 2 m cell or its voxel is noted.  pass 2 (only if no centroid changed cell): the entries of
+      // the cell-sorted copy are patched.  A tail of up to blockDim points (the usual case) keeps its centroids in
+      // registers between the passes; a longer one recomputes them from the tail (the old prefix point is gone).
+      float4* cp = M.cellpts + (size_t)sid * M.cap;
+      const bool one_trip = nt <= (int)blockDim.x;
+      float4 pn_keep = make_float4(0.f, 0.f, 0.f, 0.f); int cell_keep = -1, lb_keep = -1;
+      for (int j = threadIdx.x; j < nt; j += blockDim.x) {
+        const uint32_t key = tkey[j];
+        if (j > 0 && tkey[j - 1] == key) continue;           // not a run head
+        const int lb = tlb[j];
+        const float4 po = pts[lb];
+        float sx = po.x, sy = po.y, sz = po.z, si = po.w;
+        int cnt = 1;
+        for (int m = j; m < nt && tkey[m] == key; ++m) {
+          const float4 t = pts[ns + m];
+          sx = __fadd_rn(sx, t.x); sy = __fadd_rn(sy, t.y); sz = __fadd_rn(sz, t.z); si = __fadd_rn(si, t.w);
+          ++cnt;
+        }
+        const float c = (float)cnt;
+        const float4 pn = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), __fdiv_rn(si, c));
+        const int cell = d_cube_cell(po, g3);
+        if (cell < 0 || d_cube_cell(pn, g3) != cell) s_mover = 1;
+        if (d_cube_voxel_key(pn, il, g3) != key) s_badkey = 1;          // the centroid left its voxel: re-voxelise the cube as a whole next time
+        pts[lb] = pn;
+        pn_keep = pn; cell_keep = cell; lb_keep = lb;
+      }
+      __syncthreads();
+      if (!s_mover) {
         for (int j = threadIdx.x; j < nt; j += blockDim.x) {
-          const uint32_t key = tkey[j];
-          if (j > 0 && tkey[j - 1] == key) continue;           // not a run head
-          const int lb = tlb[j];
-          const float4 po = pts[lb];
-          float sx = po.x, sy = po.y, sz = po.z, si = po.w;
-          int cnt = 1;
-          for (int m = j; m < nt && tkey[m] == key; ++m) {
-            const float4 t = pts[ns + m];
-            sx = __fadd_rn(sx, t.x); sy = __fadd_rn(sy, t.y); sz = __fadd_rn(sz, t.z); si = __fadd_rn(si, t.w);
-            ++cnt;
+          float4 pn; int cell, lb;
+          if (one_trip) { if (lb_keep < 0) continue; pn = pn_keep; cell = cell_keep; lb = lb_keep; }
+          else {
+            const uint32_t key = tkey[j];
+            if (j > 0 && tkey[j - 1] == key) continue;
+            lb = tlb[j];
+            pn = pts[lb];                                      // written by this thread in pass 1
+            cell = d_cube_cell(pn, g3);                        // no centroid changed cell
           }
-          const float c = (float)cnt;
-          const float4 pn = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), __fdiv_rn(si, c));
-          const int cell = d_cube_cell(po, g3);
-          if (phase == 0) {
-            if (cell < 0 || d_cube_cell(pn, g3) != cell) s_mover = 1;
-            if (d_cube_voxel_key(pn, il, g3) != key) s_badkey = 1;          // the centroid left its voxel: re-voxelise the cube as a whole next time
-            continue;
-          }
-          pts[lb] = pn;
-          if (!patch) continue;
-          float4* cp = M.cellpts + (size_t)sid * M.cap;
           const uint32_t* cs = M.cellstart + (size_t)sid * (LM_NCELL + 1) + cell;
           const int cb = (int)cs[0], ce = (int)cs[1];
           bool found = false;
@@ -571,8 +585,8 @@ __global__ void __launch_bounds__(RF_TS_THREADS) k_rf_tailscan(LmMapState* __res
           }
           if (!found) atomicOr(&st->fault, LM_FAULT_CELL_RANGE);      // the search index did not cover the prefix (internal error)
         }
-        __syncthreads();
       }
+      __syncthreads();
       if (threadIdx.x == 0) {
         M.slab_n[sid] = ns;
         M.slab_nsorted[sid] = s_badkey ? 0 : ns;
