@@ -296,6 +296,11 @@ def run_ours(args):
         return worst
 
     W = max(args.warmup, 3)
+    # nvidia-smi needs a few hundred ms to deliver its first row (longer on an 8-GPU box), the timed region below lasts a few
+    # tens of ms: the sampler runs from before the warm-up, and the same step keeps running (untimed) after the timed region
+    # until at least three rows have been taken under this load
+    sampler = ClockSampler(local)
+    sampler.start()
     for i in range(W):
         batch.step_device(join_stream=main.cuda_stream, args=bargs[i % nsw])
     batch.collect()
@@ -303,9 +308,7 @@ def run_ours(args):
     # ---- value leg: S sequences per GPU, device-resident inputs.  Per batch step: L2 flush on the main stream, event,
     # fork -> one registration per sequence, overlapping on the device -> join, event.  value = registrations / sum of the
     # event-bracketed times (the flush is outside the brackets).
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     n_launch0 = sum(c_.launch_count() for c_ in ctxs)
@@ -318,8 +321,14 @@ def run_ours(args):
     host_enqueue_s = time.perf_counter() - t_host0
     barrier()
     n_launch = sum(c_.launch_count() for c_ in ctxs) - n_launch0
-    clocks = sampler.stop()
     res = batch.collect()
+    t_hold = time.perf_counter()
+    while sampler.proc and len(sampler.rows) < 3 and time.perf_counter() - t_hold < 2.0:      # untimed: hold the load for the sampler
+        for i in range(8):
+            batch.step_device(join_stream=main.cuda_stream, args=bargs[(W + i) % nsw])
+        res_hold = batch.collect()
+    clocks = sampler.stop()
+    clocks["window"] = "warm-up + timed region + the same step held (untimed) until nvidia-smi had delivered three rows"
     step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
     total_ms_max = allmax(float(sum(step_ms)))
     value = world * S * args.steps / (total_ms_max * 1e-3)

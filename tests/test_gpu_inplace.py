@@ -3,7 +3,7 @@ voxel there (mapstore.cu: k_rf_tailscan) instead of rewriting the cube through m
 leave the same map and the same search index: the same drive is run in two processes, LMONO_RF_INPLACE=1 and =0 (the
 switch is read once per process), and every pose, report, map export and 5-NN answer is compared bit for bit; the
 in-place process must actually have taken the in-place path.  The drive revisits its sweeps, so later passes see cubes
-without a new voxel (in place) next to cubes that still grow (merge) and centroids that change their 2 m cell (index of
+without a new voxel (in place) next to cubes that still grow (merge) and centroids that change their search cell (index of
 that cube rebuilt at the start of the next step)."""
 import hashlib
 import json
