@@ -69,7 +69,8 @@ typedef struct {
   float   minimum_range;             /* scanRegistration.cpp:468 */
   float   mapping_line_resolution;   /* laserMapping.cpp:902 */
   float   mapping_plane_resolution;  /* laserMapping.cpp:903 */
-  int32_t mapping_skip_frame;        /* laserOdometry.cpp:191 */
+  int32_t mapping_skip_frame;        /* laserOdometry.cpp:191: cadence at which the ODOMETRY NODE forwards sweeps to laserMapping
+                                      * (nodes/laserOdometry_b200.cpp applies it); lmono_sweep_step* map every sweep they are given */
   /* capacities (0 = default) */
   int32_t max_sweep_points;          /* raw points per sweep            (default 262144) */
   int32_t max_feature_points;        /* points per feature cloud        (default 131072) */
