@@ -81,8 +81,15 @@ typedef struct {
   int32_t image_width, image_height; /* colour projection raster (default 1241 x 376) */
   int32_t distortion;                /* #define DISTORTION of laserOdometry.cpp:59 (default 0, as compiled in the reference): 1 = per-point
                                         interpolation ratio s = (intensity - int(intensity)) / 0.1 in TransformToStart and the factors */
-  int32_t reserved[7];
+  int32_t stages;                    /* what this ctx will be asked to run: 0 = everything (default); else a mask of LMONO_STAGE_*.  Only a ctx
+                                        with LMONO_STAGE_MAPPING allocates the cube map's slab pools (GBs); its map / sweep / shard calls
+                                        return LMONO_E_STATE otherwise.  A scanRegistration- or laserOdometry-only node passes its own bit. */
+  int32_t reserved[6];
 } lmono_params;
+#define LMONO_STAGE_SCAN     1
+#define LMONO_STAGE_ODOMETRY 2
+#define LMONO_STAGE_MAPPING  4
+#define LMONO_STAGE_COLOUR   8
 
 void lmono_default_params(lmono_params* p);
 

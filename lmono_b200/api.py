@@ -65,7 +65,7 @@ class Params(C.Structure):
                 ("cube_capacity_corner", C.c_int32), ("cube_capacity_surf", C.c_int32),
                 ("max_cubes_corner", C.c_int32), ("max_cubes_surf", C.c_int32),
                 ("image_width", C.c_int32), ("image_height", C.c_int32), ("distortion", C.c_int32),
-                ("reserved", C.c_int32 * 7)]
+                ("stages", C.c_int32), ("reserved", C.c_int32 * 6)]
 
 
 class SolveSummary(C.Structure):

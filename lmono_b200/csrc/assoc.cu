@@ -721,6 +721,7 @@ __global__ void __launch_bounds__(KNN1_THREADS) k_knn5_hook1(const LmMapState* _
 }
 
 int lm_knn5_device(lmono_ctx* ctx, int which, const float4* d_q, int n, int32_t* d_idx, float* d_d2) {
+  LM_NEED_MAP();
   if (n <= 0) return LMONO_OK;
   // same choice of form as lm_map_associate: LMONO_KNN_GROUP=0, or a ctx that runs the throughput forms
   const char* ge = getenv("LMONO_KNN_GROUP");

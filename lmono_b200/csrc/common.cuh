@@ -211,6 +211,7 @@ struct lmono_ctx {
                                 // throughput forms of the kernels (one-thread-per-query kNN, 8-CTA LM clusters) over the latency forms
 
   LmMapType map[2];
+  bool map_ready;               // the slab pools exist (lmono_params::stages includes LMONO_STAGE_MAPPING)
   LmMapState* d_state;
   LmMapState* h_state;          // pinned mirror
   // pipelined host API (lmono_map_submit_batch / _wait_batch): up to two steps of a ctx may be in flight; the step
@@ -317,6 +318,7 @@ static inline void lm_kmark(lmono_ctx* ctx, const char* file, int line) {
   fprintf(stderr, "[lmono_b200] launch error %s at %s:%d\n", cudaGetErrorName(_e), __FILE__, __LINE__); return LMONO_E_CUDA; } } while (0)
 
 static inline int lm_div_up(int a, int b) { return (a + b - 1) / b; }
+#define LM_NEED_MAP() do { if (!ctx->map_ready) return LMONO_E_STATE; } while (0)
 
 // ---------------------------------------------------------------- programmatic dependent launch
 // A registration is a chain of ~20 small dependent kernels.  Kernels on the step path are launched with

@@ -150,10 +150,14 @@ static int create_impl(lmono_ctx* ctx, void* stream) {
   LM_CUDA(cudaMalloc((void**)&ctx->d_export, ctx->export_cap * sizeof(float4)));
   k_state_init<<<1, 32, 0, ctx->stream>>>(ctx->d_state);
   LM_LAUNCH_CHECK();
-  int rc = lm_map_alloc(ctx);
-  if (rc) return rc;
-  rc = lm_map_configure_kernels(ctx);
-  if (rc) return rc;
+  int rc = LMONO_OK;
+  if (ctx->prm.stages == 0 || (ctx->prm.stages & LMONO_STAGE_MAPPING)) {     // a scan / odometry / colour-only ctx does not pay for the cube map
+    rc = lm_map_alloc(ctx);
+    if (rc) return rc;
+    rc = lm_map_configure_kernels(ctx);
+    if (rc) return rc;
+    ctx->map_ready = true;
+  }
   if ((rc = lm_sort_configure(ctx))) return rc;
   LM_CUDA(cudaStreamSynchronize(ctx->stream));
   return LMONO_OK;

@@ -797,6 +797,7 @@ int lm_solve_enqueue(lmono_ctx* ctx, int solve_index, int n_max_corner, int n_ma
 }
 
 int lm_normal_eq_enqueue(lmono_ctx* ctx, int n_max_corner, int n_max_surf) {
+  LM_NEED_MAP();
   // max_iter = 0: IterationZero fills H, g, cost and the controller stops immediately
   int rc = lm_solve_problem(ctx, map_problem(ctx, 0), n_max_corner + n_max_surf, 0, 0);
   if (rc) return rc;

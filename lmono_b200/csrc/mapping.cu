@@ -207,6 +207,7 @@ static void fill_step_args(StepArgs* a, const LmStepIn& in, const lmono_pose* wo
 
 // enqueue the whole step
 static int enqueue_step(lmono_ctx* ctx, const LmStepIn& in, const lmono_pose* wodom_curr, const lmono_pose* wmap_in = nullptr, int slot = 0) {
+  LM_NEED_MAP();
   const int nc = in.n[0], ns = in.n[1];
   if (nc < 0 || ns < 0 || nc > ctx->max_feat || ns > ctx->max_feat) return LMONO_E_CAPACITY;
   int rc;
@@ -280,6 +281,7 @@ __global__ void k_shard_gate(LmMapState* __restrict__ st, const double* __restri
 
 extern "C" int lmono_shard_configure(lmono_ctx* ctx, int32_t rank, int32_t nranks, void* d_workspace) {
   if (!ctx || nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !d_workspace)) return LMONO_E_ARG;
+  LM_NEED_MAP();
   ctx->d_shard_ws = (double*)d_workspace;
   k_shard_config<<<1, 32, 0, ctx->stream>>>(ctx->d_state, rank, nranks);
   LM_LAUNCH_CHECK();
@@ -405,6 +407,7 @@ extern "C" int lmono_sweep_step(lmono_ctx* ctx, lmono_cloud_view raw, lmono_pose
                                 lmono_pose* map_w_curr, lmono_pose* wmap_wodom,
                                 lmono_scan_report* scan_report, lmono_odom_report* odom_report, lmono_map_report* map_report) {
   if (!ctx) return LMONO_E_ARG;
+  LM_NEED_MAP();
   if (raw.n > ctx->max_sweep) return LMONO_E_CAPACITY;
   int rc;
   const float4* d_in = nullptr;
@@ -495,6 +498,7 @@ static int sweep_graph_launch(lmono_ctx* ctx, const float4* d_in, int n) {
 
 extern "C" int lmono_sweep_submit(lmono_ctx* ctx, lmono_cloud_view raw, int own_stream) {
   if (!ctx) return LMONO_E_ARG;
+  LM_NEED_MAP();
   if (raw.n > ctx->max_sweep) return LMONO_E_CAPACITY;
   if (ctx->sweep_outstanding) return LMONO_E_STATE;
   if (!ctx->ev_sweep) LM_CUDA(cudaEventCreateWithFlags(&ctx->ev_sweep, cudaEventDisableTiming));

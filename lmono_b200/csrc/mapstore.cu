@@ -69,6 +69,7 @@ void lm_map_free(lmono_ctx* ctx) {
 }
 
 int lm_map_clear_device(lmono_ctx* ctx) {
+  LM_NEED_MAP();
   for (int ty = 0; ty < 2; ++ty) { k_map_reset<<<32, 256, 0, ctx->stream>>>(ctx->map[ty]); LM_LAUNCH_CHECK(); }
   return LMONO_OK;
 }
@@ -221,6 +222,7 @@ __global__ void __launch_bounds__(256) k_begin_step(LmMapState* __restrict__ st,
 }
 
 int lm_map_begin_step(lmono_ctx* ctx, const lmono_pose* wodom_curr, const double* t_override) {
+  LM_NEED_MAP();
   PoseArg pa;
   if (wodom_curr) { for (int k = 0; k < 4; ++k) pa.q[k] = wodom_curr->q[k]; for (int k = 0; k < 3; ++k) pa.t[k] = wodom_curr->t[k]; }
   else { pa.q[0] = pa.q[1] = pa.q[2] = 0; pa.q[3] = 1; pa.t[0] = pa.t[1] = pa.t[2] = 0; }
@@ -975,6 +977,7 @@ int lm_map_insert_and_refilter(lmono_ctx* ctx, int n_max_corner, int n_max_surf,
 
 // study hook: the refilter records of the last step, [2][LM_WIN_MAX] x {active, new size, prefix size, tail size, flag, cur, slab, -}
 extern "C" int lmono_debug_rf_meta(lmono_ctx* ctx, int32_t* out, int32_t n_ints) {
+  if (ctx && !ctx->map_ready) return LMONO_E_STATE;
   if (!ctx || !out || n_ints < 0 || n_ints > (int)(sizeof(RfMeta) / 4) * 2 * LM_WIN_MAX) return LMONO_E_ARG;
   LM_CUDA(cudaMemcpyAsync(out, ctx->d_rf_meta, sizeof(int32_t) * (size_t)n_ints, cudaMemcpyDeviceToHost, ctx->stream));
   LM_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1092,6 +1095,7 @@ static int export_interleaved(lmono_ctx* ctx, int scope, int* n_total) {
 }
 
 int lm_map_export_device(lmono_ctx* ctx, int which, int scope, int* n_total) {
+  LM_NEED_MAP();
   if (which == 2) return export_interleaved(ctx, scope, n_total);
   LmMapType& M = ctx->map[which];
   int32_t* order = ctx->d_export_off + LM_NSLOT + 8;
@@ -1246,6 +1250,7 @@ __global__ void __launch_bounds__(256) k_import_verify(LmMapType M) {
 int lm_map_import_device(lmono_ctx* ctx, int which, const float4* d_pts, int n,
                          unsigned long long* d_a, unsigned long long* d_b, unsigned long long* d_c,
                          int32_t* d_n, int32_t* d_blockcnt, int32_t* d_head_rank) {
+  LM_NEED_MAP();
   LmMapType& M = ctx->map[which];
   const int blocks = lm_div_up(n, 256);
   LM_CUDA(cudaMemcpyAsync(d_n, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));

@@ -25,7 +25,7 @@ int main(int argc, char** argv) {
   int skip_frame_num = 2;
   nh.param<int>("mapping_skip_frame", skip_frame_num, 2);
   printf("Mapping %d Hz \n", 10 / skip_frame_num);
-  lmono_params prm; lmono_default_params(&prm); prm.mapping_skip_frame = skip_frame_num;
+  lmono_params prm; lmono_default_params(&prm); prm.mapping_skip_frame = skip_frame_num; prm.stages = LMONO_STAGE_ODOMETRY;
   lmono_ctx* ctx = nullptr;
   prm.max_cubes_corner = prm.max_cubes_surf = 1;      // this node never touches the cube map: no slab pool
   lmono_glue::check(lmono_create(0, &prm, nullptr, &ctx), "lmono_create");

@@ -49,6 +49,7 @@ int main(int argc, char** argv) {
   ros::NodeHandle nh;
   lmono_params prm;
   lmono_default_params(&prm);
+  prm.stages = LMONO_STAGE_SCAN;       // this node never touches the cube map: no slab pools
   int scan_line = 16; double minimum_range = 0.1;
   nh.param<int>("scan_line", scan_line, 16);
   nh.param<double>("minimum_range", minimum_range, 0.1);

@@ -134,3 +134,31 @@ def test_cpp_replay_harness_matches_python_binding(gpu_ctx_factory, tmp_path):
         vals = np.array([float(x) for x in lines[k][1:15]])
         assert np.allclose(vals[4:7], ot, atol=2e-6) and np.allclose(vals[11:14], mt, atol=2e-6)
         assert np.allclose(vals[0:4], oq, atol=2e-9) and np.allclose(vals[7:11], mq, atol=2e-9)
+
+
+@pytest.mark.gpu
+def test_stage_only_context_allocates_no_map():
+    """lmono_params::stages: a scanRegistration / laserOdometry-only ctx (what those two nodes create) does not allocate the cube
+    map's slab pools and refuses the mapping calls; its own stage gives the same results as a full ctx."""
+    import torch
+    from lmono_b200 import api, synth
+    wld = synth.make_world()
+    rng = np.random.default_rng(5)
+    raw = np.ascontiguousarray(synth.raycast_sweep_torch(wld, *synth.loop_pose(wld, 3.0), 64, 900, rng, device=torch.device("cuda", 0)), np.float32)
+    free0 = torch.cuda.mem_get_info(0)[0]
+    small = api.Context(device=0, stages=1 | 2)
+    used_small = free0 - torch.cuda.mem_get_info(0)[0]
+    full = api.Context(device=0)
+    used_full = free0 - torch.cuda.mem_get_info(0)[0] - used_small
+    try:
+        assert used_small < 0.5e9 < 2e9 < used_full, (used_small, used_full)
+        a, b = small.scan_register(raw), full.scan_register(raw)
+        for k in ("full", "sharp", "less_sharp", "flat", "less_flat"):
+            assert a[k].shape == b[k].shape and (a[k].view(np.uint32) == b[k].view(np.uint32)).all(), k
+        c, s = a["less_sharp"], a["less_flat"]
+        with pytest.raises(api.LmonoError):
+            small.map_step(c, s, [0, 0, 0, 1], [0, 0, 0])
+        with pytest.raises(api.LmonoError):
+            small.map_import(0, c)
+    finally:
+        small.close(); full.close()
