@@ -139,6 +139,13 @@ int  lmono_create(int device, const lmono_params* params, void* stream, lmono_ct
 void lmono_destroy(lmono_ctx* ctx);
 const char* lmono_strerror(int code);
 /* device-side fault bits raised since the last call (0 = none); clears them. */
+#define LMONO_FAULT_CUBE_OVERFLOW    (1u << 0)  /* a cube's slab is full: new points of that cube were dropped */
+#define LMONO_FAULT_POOL_EXHAUSTED   (1u << 1)  /* no free slab for a newly touched cube (lmono_map_evict frees far ones) */
+#define LMONO_FAULT_TAIL_OVERFLOW    (1u << 2)  /* a cube to re-voxelise as a whole exceeds 65 536 points */
+#define LMONO_FAULT_CELL_RANGE       (1u << 3)  /* internal: a point outside its cube's search table */
+#define LMONO_FAULT_FEATURE_OVERFLOW (1u << 4)  /* a feature cloud exceeded max_feature_points */
+#define LMONO_FAULT_IMPORT_NONEMPTY  (1u << 5)  /* lmono_map_import into a cube that already holds points */
+#define LMONO_FAULT_SHARD_TIMEOUT    (1u << 6)  /* cube-sharded map, peer-memory mode: a rank did not answer */
 int  lmono_last_fault(lmono_ctx* ctx, uint32_t* bits);
 int  lmono_sync(lmono_ctx* ctx);
 /* Device time (CUDA events on the ctx stream) of the most recent lmono_scan_register / lmono_odom_step /
@@ -221,6 +228,12 @@ int lmono_map_export(lmono_ctx* ctx, int which, int scope, lmono_cloud_out* out)
  * (laserMapping.cpp:741-758 arithmetic) and every cube is VoxelGrid-filtered (:788-801). */
 int lmono_map_import(lmono_ctx* ctx, int which, lmono_cloud_view pts_world);
 int lmono_map_clear(lmono_ctx* ctx);
+/* Capacity valve for long drives: the reference's cube clouds (laserMapping.cpp:104) grow without bound, the slab pools do
+ * not.  Frees the slabs of every cube more than keep_cubes (>= 3) cubes away from the window's centre cube in any axis --
+ * cubes the 5x5x3 window cannot reach without the sensor travelling (keep_cubes - 2) x 50 m first; their points leave the
+ * map.  Call it between steps, e.g. when a step returned LMONO_E_DEVICE with LMONO_FAULT_POOL_EXHAUSTED in
+ * lmono_last_fault (nodes/laserMapping_b200.cpp does).  n_freed (may be NULL): slabs returned to the pools. */
+int lmono_map_evict(lmono_ctx* ctx, int32_t keep_cubes, int32_t* n_freed);
 
 /* ------------------------------------------------------------------ cube-sharded global map (multi-GPU)
  * Extension beyond the reference (its map is one process's 21x21x11 cube array, laserMapping.cpp:74-104):

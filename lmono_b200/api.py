@@ -316,6 +316,11 @@ class Context:
             self._chk(rc, "map_export")
             return buf[: out.n_out].copy()
 
+    def map_evict(self, keep_cubes):
+        n = C.c_int32(0)
+        self._chk(self.L.lmono_map_evict(self._h, int(keep_cubes), C.byref(n)), "map_evict")
+        return n.value
+
     def map_clear(self):
         self._chk(self.L.lmono_map_clear(self._h), "map_clear")
 

@@ -6,6 +6,7 @@
 #include <stdlib.h>
 
 int lm_map_clear_device(lmono_ctx* ctx);
+int lm_map_evict_device(lmono_ctx* ctx, int keep, int* n_freed);
 int lm_map_export_device(lmono_ctx* ctx, int which, int scope, int* n_total);
 int lm_map_import_device(lmono_ctx* ctx, int which, const float4* d_pts, int n,
                          unsigned long long* d_a, unsigned long long* d_b, unsigned long long* d_c,
@@ -890,6 +891,15 @@ extern "C" int lmono_map_set_state(lmono_ctx* ctx, const lmono_pose* p) {
 }
 
 extern "C" int32_t lmono_map_result_bytes(void) { return (int32_t)sizeof(LmMapState); }
+
+extern "C" int lmono_map_evict(lmono_ctx* ctx, int32_t keep_cubes, int32_t* n_freed) {
+  if (!ctx) return LMONO_E_ARG;
+  if (ctx->step_pending) return LMONO_E_STATE;
+  int n = 0;
+  const int rc = lm_map_evict_device(ctx, keep_cubes, &n);
+  if (n_freed) *n_freed = n;
+  return rc;
+}
 
 extern "C" int lmono_map_clear(lmono_ctx* ctx) {
   if (!ctx) return LMONO_E_ARG;

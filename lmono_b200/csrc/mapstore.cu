@@ -87,6 +87,36 @@ __device__ __forceinline__ void d_free_slot(const LmMapType& M, int ps) {
   }
 }
 
+// Capacity valve for long drives (the reference's cube clouds are unbounded, the slab pools are not): give back the slabs of
+// every cube farther than `keep` cubes (Chebyshev distance) from the window's centre cube.  Those cubes lie outside the
+// 5x5x3 window, so the next registrations are unaffected; their points are gone from the map.
+__global__ void __launch_bounds__(256) k_map_evict(const LmMapState* __restrict__ st, LmMapType M0, LmMapType M1, int keep, int32_t* __restrict__ n_freed) {
+  const int keep_c = keep < 3 ? 3 : keep;            // never inside the window (+-2 cubes) or its rim
+  for (int ps = blockIdx.x * blockDim.x + threadIdx.x; ps < LM_NSLOT; ps += gridDim.x * blockDim.x) {
+    for (int ty = 0; ty < 2; ++ty) {
+      const LmMapType& M = ty == 0 ? M0 : M1;
+      const int sid = M.slot_slab[ps];
+      if (sid < 0) continue;
+      const int di = abs(M.slab_g[sid * 4 + 0] + st->cen[0] - st->center[0]);
+      const int dj = abs(M.slab_g[sid * 4 + 1] + st->cen[1] - st->center[1]);
+      const int dk = abs(M.slab_g[sid * 4 + 2] + st->cen[2] - st->center[2]);
+      if (max(di, max(dj, dk)) > keep_c) { d_free_slot(M, ps); atomicAdd(n_freed, 1); }
+    }
+  }
+}
+int lm_map_evict_device(lmono_ctx* ctx, int keep, int* n_freed) {
+  LM_NEED_MAP();
+  int32_t* d_n = ctx->d_tmp_i32;
+  LM_CUDA(cudaMemsetAsync(d_n, 0, sizeof(int32_t), ctx->stream));
+  k_map_evict<<<lm_div_up(LM_NSLOT, 256), 256, 0, ctx->stream>>>(ctx->d_state, ctx->map[0], ctx->map[1], keep, d_n);
+  LM_LAUNCH_CHECK();
+  int n = 0;
+  LM_CUDA(cudaMemcpyAsync(&n, d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  LM_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (n_freed) *n_freed = n;
+  return LMONO_OK;
+}
+
 // transformAssociateToMap (:142-146), centre cube (:312-321), the six shift loops
 // (:323-507), the valid list (:512-529) and the per-type offsets of the concatenation
 // (:533-539), all on device so consecutive sweeps need no host round trip.

@@ -104,7 +104,9 @@ void process() {
                                          lmono_glue::view(full), &o_reg);
       if (rc_step == LMONO_E_DEVICE) {      // a map capacity limit was hit (slab pool / cube slab): the pose is valid, some new points were dropped
         uint32_t bits = 0; lmono_last_fault(g_ctx, &bits);
-        ROS_WARN("lmono_map_step: map capacity reached (fault bits 0x%x): raise max_cubes_* / cube_capacity_* (INTEGRATION.md)", bits);
+        int32_t freed = 0;
+        if (bits & LMONO_FAULT_POOL_EXHAUSTED) lmono_map_evict(g_ctx, 4, &freed);      // slab pool exhausted: drop the cubes more than 4 cubes (200 m) from the window centre
+        ROS_WARN("lmono_map_step: map capacity reached (fault bits 0x%x), %d far cubes evicted: raise max_cubes_* / cube_capacity_* (INTEGRATION.md)", bits, freed);
       } else if (rc_step != LMONO_OK) {
         ROS_ERROR("lmono_map_step: %s -- sweep skipped", lmono_strerror(rc_step));
         continue;

@@ -359,3 +359,37 @@ def test_export_interleaved_like_the_reference_publishers(gpu_ctx_factory):
         key = cube * 4 + both[:, 3].astype(np.int64)
         assert np.all(np.diff(key) >= 0), scope                      # grouped by cube, corner before surf inside a cube
         assert len(np.unique(cube)) > 5
+
+
+@pytest.mark.gpu
+def test_pool_exhaustion_is_reported_and_eviction_recovers(gpu_ctx_factory):
+    """The reference's cube clouds are unbounded, the slab pools are not: with a pool of 12 slabs per map a drive that
+    touches more cubes raises LMONO_FAULT_POOL_EXHAUSTED (pose still valid, new points of unplaced cubes dropped);
+    lmono_map_evict gives the far cubes' slabs back and the next registrations place their points again."""
+    from lmono_b200 import api
+    ctx = gpu_ctx_factory(max_cubes_corner=12, max_cubes_surf=12)
+    rng = np.random.default_rng(3)
+
+    def blob(n=4000):                            # sensor-frame features around the sensor
+        p = np.zeros((n, 4), np.float32)
+        p[:, 0] = rng.uniform(-20, 20, n); p[:, 1] = rng.uniform(-20, 20, n); p[:, 2] = rng.uniform(-2, 2, n)
+        return p
+
+    # walk along x in 50 m steps: each step touches new cubes; nothing is ever optimised (empty map), points are inserted
+    faulted = False
+    for k in range(40):
+        x = 50.0 * k
+        try:
+            ctx.map_step(blob(500), blob(), [0, 0, 0, 1], [x, 0, 0])
+        except api.LmonoError as e:
+            assert e.code == -5, e
+            faulted = True
+            break
+    assert faulted
+    freed = ctx.map_evict(4)
+    assert freed > 0
+    for k2 in range(k + 1, k + 6):              # after the eviction new cubes can be placed again
+        x = 50.0 * k2
+        ctx.map_step(blob(500), blob(), [0, 0, 0, 1], [x, 0, 0])
+    n_near = len(ctx.map_export(1, 0))
+    assert n_near > 0
