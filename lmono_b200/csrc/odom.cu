@@ -112,7 +112,10 @@ __global__ void __launch_bounds__(NN_QB * NN_SUB) k_odom_nn1(const OdomDev* __re
   const int sub = threadIdx.x % NN_SUB;
   float4 sel = make_float4(0.f, 0.f, 0.f, 0.f);
   if (qi < nq) sel = d_to_start(o, qs[qi]);
-  unsigned long long bestk = ~0ULL;
+  // a lane visits its targets in ascending index order, so "strictly smaller d2 wins" keeps the lowest index among equal
+  // distances: one float compare and two selects per pair instead of a 64-bit key build and compare; the lanes' results are
+  // then combined on the packed (d2, index) key
+  float bd = INFINITY; int bi = -1;
   // target chunks are dealt round-robin over gridDim.y: the grid does not depend on the (device-side) target count
   for (int c0 = blockIdx.y * NN_CHUNK; c0 < nt; c0 += gridDim.y * NN_CHUNK) {
   const int c1 = min(c0 + NN_CHUNK, nt);
@@ -127,11 +130,11 @@ __global__ void __launch_bounds__(NN_QB * NN_SUB) k_odom_nn1(const OdomDev* __re
       float d = __fmul_rn(dx, dx);
       d = __fadd_rn(d, __fmul_rn(dy, dy));
       d = __fadd_rn(d, __fmul_rn(dz, dz));
-      const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)(tb + k);
-      bestk = key < bestk ? key : bestk;
+      if (d < bd) { bd = d; bi = tb + k; }
     }
   }
   }
+  unsigned long long bestk = bi >= 0 ? (((unsigned long long)__float_as_uint(bd) << 32) | (uint32_t)bi) : ~0ULL;
 #pragma unroll
   for (int ofs = NN_SUB / 2; ofs > 0; ofs >>= 1) {
     const unsigned long long other = __shfl_xor_sync(0xffffffffu, bestk, ofs);
