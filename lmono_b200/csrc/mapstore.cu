@@ -271,10 +271,21 @@ __device__ void d_build_cell_index(const LmMapType& M, int sid, const float4* __
   const int g3[3] = { g[0], g[1], g[2] };
   for (int i = threadIdx.x; i < LM_NCELL; i += blockDim.x) s_cnt[i] = 0;
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    int c = d_cube_cell(src[i], g3);
-    if (c < 0) { atomicOr(&st->fault, LM_FAULT_CELL_RANGE); c = 0; }
-    atomicAdd(&s_cnt[c], 1u);
+  // four independent loads in flight per trip (a plain loop waits for each load before it issues the next: one L2 / HBM round
+  // trip per 1024 points, twice over the cube)
+  for (int i0 = threadIdx.x; i0 < n; i0 += 4 * blockDim.x) {
+    float4 p[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int i = i0 + u * blockDim.x; if (i < n) p[u] = src[i]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < n) {
+        int c = d_cube_cell(p[u], g3);
+        if (c < 0) { atomicOr(&st->fault, LM_FAULT_CELL_RANGE); c = 0; }
+        atomicAdd(&s_cnt[c], 1u);
+      }
+    }
   }
   __syncthreads();
   const int per = (LM_NCELL + blockDim.x - 1) / blockDim.x;
@@ -290,13 +301,21 @@ __device__ void d_build_cell_index(const LmMapType& M, int sid, const float4* __
   if (threadIdx.x == 0) cs[LM_NCELL] = (uint32_t)n;
   __syncthreads();
   float4* cp = M.cellpts + (size_t)sid * M.cap;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    float4 p = src[i];
-    int c = d_cube_cell(p, g3);
-    if (c < 0) c = 0;
-    uint32_t pos = atomicAdd(&s_cnt[c], 1u);
-    p.w = __int_as_float(i);
-    cp[pos] = p;
+  for (int i0 = threadIdx.x; i0 < n; i0 += 4 * blockDim.x) {
+    float4 p[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int i = i0 + u * blockDim.x; if (i < n) p[u] = src[i]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < n) {
+        int c = d_cube_cell(p[u], g3);
+        if (c < 0) c = 0;
+        const uint32_t pos = atomicAdd(&s_cnt[c], 1u);
+        p[u].w = __int_as_float(i);
+        cp[pos] = p[u];
+      }
+    }
   }
   __syncthreads();
 }

@@ -28,6 +28,7 @@ d = [(torch.from_numpy(c).to(dev), torch.from_numpy(s).to(dev)) for (c, s, *_r) 
 nsw = len(sweeps)
 ident = ([0, 0, 0, 1], [0, 0, 0])
 SRC = {}
+WARM = int(os.environ.get("LMONO_TIMELINE_WARM", "64"))
 
 
 def site_name(site):
@@ -59,13 +60,16 @@ def run(n):
         a.set_device_inputs([d[k][0].data_ptr() for k in ks], [d[k][0].shape[0] for k in ks],
                             [d[k][1].data_ptr() for k in ks], [d[k][1].shape[0] for k in ks])
         bargs.append(a)
-    for i in range(4):
+    # warm-up long enough for the maps to stop gaining voxels (the same sweeps are registered again and again): the timeline
+    # then shows the steady state the bench measures (refilter in place); LMONO_TIMELINE_WARM=4 shows the first steps after
+    # an import instead, with the merge path of the refilter at work
+    for i in range(WARM):
         batch.step_device(join_stream=st.cuda_stream, args=bargs[i % nsw])
     batch.collect()
     dur = defaultdict(list)       # (ordinal, kernel) -> [us]
     spans = []
     for i in range(steps):
-        batch.step_device(join_stream=st.cuda_stream, args=bargs[(4 + i) % nsw])
+        batch.step_device(join_stream=st.cuda_stream, args=bargs[(WARM + i) % nsw])
         torch.cuda.synchronize()
         t0s, t1s = [], []
         for c_ in ctxs:
