@@ -309,6 +309,7 @@ def run_ours(args):
     # fork -> one registration per sequence, overlapping on the device -> join, event.  value = registrations / sum of the
     # event-bracketed times (the flush is outside the brackets).
     barrier()
+    torch.cuda.profiler.start()          # no-op unless a profiler is attached: `ncu --profile-from-start off ... python bench.py` lists the timed region's launches
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     n_launch0 = sum(c_.launch_count() for c_ in ctxs)
@@ -320,6 +321,7 @@ def run_ours(args):
         ev1[i].record(main)
     host_enqueue_s = time.perf_counter() - t_host0
     barrier()
+    torch.cuda.profiler.stop()
     n_launch = sum(c_.launch_count() for c_ in ctxs) - n_launch0
     res = batch.collect()
     t_hold = time.perf_counter()
