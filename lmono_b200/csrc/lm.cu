@@ -566,6 +566,10 @@ template <bool RATIO>
 __global__ void __launch_bounds__(LMC_THREADS, 1)
 k_lm_solve_cluster(LmLmState* __restrict__ lm_g, LmProblem P, int max_iter, int write_back, unsigned long long* __restrict__ stamps,
                    const LmShardPeers* __restrict__ peers /*NULL: map not sharded over GPUs*/, uint32_t* __restrict__ fault) {
+  // Distributed shared memory may only be written once the target CTA is known to be running: every CTA arrives on the
+  // cluster barrier first thing and waits for the phase behind the state set-up below, so the round trip is hidden by the
+  // predecessor wait and the set-up
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
   lm_pdl_enter();
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank();
@@ -604,6 +608,7 @@ k_lm_solve_cluster(LmLmState* __restrict__ lm_g, LmProblem P, int max_iter, int 
     }
   }
   __syncthreads();
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
   const int wb = (write_back && crank == 0) ? 1 : 0;
   LM_STAMP(stamps, 1);
   for (int it = 0; it <= max_iter; ++it) {

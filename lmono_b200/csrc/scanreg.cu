@@ -492,6 +492,7 @@ __device__ __noinline__ uint32_t d_pick_sector(int j, uint32_t incoming, bool re
 #pragma unroll
       for (int l = 1; l <= 5; ++l) gbits |= (uint32_t)(gap[li - l + 1] != 0) << (4 + l);        // :331-342
     }
+    __syncwarp();                                                     // the picks below write flags other lanes have just read
     for (;;) {
       const unsigned m = __ballot_sync(0xffffffffu, alive);
       if (!m) break;
@@ -526,6 +527,7 @@ __device__ __noinline__ uint32_t d_pick_sector(int j, uint32_t incoming, bool re
 #pragma unroll
       for (int l = 1; l <= 5; ++l) gbits |= (uint32_t)(gap[li - l + 1] != 0) << (4 + l);
     }
+    __syncwarp();
     for (;;) {
       const unsigned m = __ballot_sync(0xffffffffu, alive);
       if (!m) break;
