@@ -80,6 +80,49 @@ def build(force: bool = False) -> str:
     return _SO
 
 
+REF_ROOT = "/root/reference"          # exists in the build container only, never on the GPU box
+
+
+def build_ref() -> str:
+    """oracle/_ref: the reference's own translation units compiled against oracle/refstubs (only where the reference
+    tree exists; elsewhere the prebuilt files that travelled with the snapshot are used as they are)."""
+    d = os.path.join(_ROOT, "oracle")
+    if os.path.isdir(os.path.join(REF_ROOT, "Aloam", "src")):
+        subprocess.run(["make", "-s", "-C", d, "ref", f"REF={REF_ROOT}"], check=True)
+    return os.path.join(d, "_ref")
+
+
+_ref_libs = {}
+
+
+def ref_lib(name):
+    """ctypes handle of oracle/_ref/libref_<name>.so, or None when it was never built (no reference tree, no prebuilt file)."""
+    if name not in _ref_libs:
+        path = os.path.join(build_ref(), f"libref_{name}.so")
+        _ref_libs[name] = C.CDLL(path) if os.path.exists(path) else None
+    return _ref_libs[name]
+
+
+def ref_scan_register(raw, n_scans=64, minimum_range=5.0):
+    """laserCloudHandler of the reference (Aloam/src/scanRegistration.cpp:113-459) as compiled from /root/reference:
+    what the node published on its five topics, plus its cloudLabel / cloudCurvature arrays."""
+    R = ref_lib("scanreg")
+    raw = np.ascontiguousarray(raw, np.float32)
+    n = len(raw)
+    names = ("full", "sharp", "less_sharp", "flat", "less_flat")
+    bufs = [np.zeros((max(n, 1), 4), np.float32) for _ in names]
+    counts = np.zeros(5, np.int32)
+    labels = np.zeros(max(n, 1), np.int32)
+    curv = np.zeros(max(n, 1), np.float32)
+    R.ref_scan_register.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double] + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 3
+    rc = R.ref_scan_register(_p(raw), n, raw.shape[1], n_scans, float(minimum_range), *[_p(b) for b in bufs], n, _p(counts), _p(labels), _p(curv))
+    assert rc == 0, rc
+    out = {k: bufs[i][: counts[i]] for i, k in enumerate(names)}
+    out["labels"] = labels[: counts[0]]
+    out["curvature"] = curv[: counts[0]]
+    return out
+
+
 _lib = None
 
 
