@@ -154,6 +154,13 @@ static int count_residuals(const o_factor* f, int nf) {
   return n;
 }
 
+/* Test hook (oracle/_ref builds): when set, block i of a problem is evaluated by the callback instead of eval_block --
+ * the reference's own cost functors on dual numbers (refstubs/ceres/ceres.h) -- and only f[i].type (the residual
+ * count) is read from the factor records.  Process-wide, not thread-safe. */
+static o_block_hook g_block_hook = NULL;
+static void* g_block_hook_user = NULL;
+void lmono_cpu_lm_set_block_hook(o_block_hook fn, void* user) { g_block_hook = fn; g_block_hook_user = user; }
+
 /* ProgramEvaluator::Evaluate: cost, corrected residuals r[nres], corrected local Jacobian
  * J[nres][6] (row-major), gradient g[6] = J^T r. r, J, g may be NULL. */
 static void evaluate(const o_factor* f, int nf, const double x[7], double* cost, double* r, double* J, double* g) {
@@ -165,7 +172,7 @@ static void evaluate(const o_factor* f, int nf, const double x[7], double* cost,
   const int want_jac = (J != NULL) || (g != NULL);
   for (int i = 0; i < nf; ++i) {
     double rb[3], Jq[3][4], Jt[3][3];
-    int nr = eval_block(&f[i], q, t, rb, Jq, Jt, want_jac);
+    int nr = g_block_hook ? g_block_hook(g_block_hook_user, i, q, t, rb, Jq, Jt, want_jac) : eval_block(&f[i], q, t, rb, Jq, Jt, want_jac);
     double s = 0.0; for (int k = 0; k < nr; ++k) s += rb[k] * rb[k];
     double rho[3]; huber(s, rho);
     c += 0.5 * rho[0];

@@ -96,6 +96,11 @@ typedef struct {
 int lmono_cpu_lm_solve(const o_factor* f, int nf, o_pose* x, int max_iter,
                        o_solve_summary* sum);
 
+/* test hook for the oracle/_ref builds: residuals r[<=3] and the Jacobians d r / d q (x,y,z,w) and d r / d t of block i
+ * at (q, t) come from the callback (returns the residual count) instead of the factor record */
+typedef int (*o_block_hook)(void* user, int i, const double q[4], const double t[3], double r[3], double Jq[3][4], double Jt[3][3], int want_jac);
+void lmono_cpu_lm_set_block_hook(o_block_hook fn, void* user);
+
 /* ---- laserMapping (Aloam/src/laserMapping.cpp) --------------------------- */
 typedef struct o_mapper o_mapper;
 typedef struct {

@@ -21,9 +21,9 @@
 #undef printf
 
 static int copy_out(const char* topic, float* dst, int cap) {
-  auto it = refstub::published().find(topic);
-  if (it == refstub::published().end()) return -1;
-  const sensor_msgs::PointCloud2& m = it->second;
+  auto it = refstub::state().clouds.find(topic);
+  if (it == refstub::state().clouds.end() || it->second.empty()) return -1;
+  const sensor_msgs::PointCloud2& m = it->second.back();
   const int n = (int)m.width;
   if (n > cap) return -2;
   for (int i = 0; i < n; ++i) {
@@ -37,13 +37,13 @@ static int copy_out(const char* topic, float* dst, int cap) {
 extern "C" int ref_scan_register(const float* xyz, int n, int stride_floats, int n_scans, double minimum_range,
                                  float* full, float* sharp, float* less_sharp, float* flat, float* less_flat, int cap,
                                  int32_t* counts /*5*/, int32_t* labels, float* curvature) {
-  refstub::params()["scan_line"] = n_scans;
-  refstub::params()["minimum_range"] = minimum_range;
-  refstub::published().clear();
+  refstub::state().params["scan_line"] = n_scans;
+  refstub::state().params["minimum_range"] = minimum_range;
+  refstub::state().clouds.clear();
   int argc = 1; char arg0[] = "ascanRegistration"; char* argv[] = { arg0, nullptr };
   ref_scanreg_main(argc, argv);                                   // parameters, advertise, subscribe; the stand-in spin() returns
-  auto sub = refstub::cloud_subs().find("/velodyne_points");
-  if (sub == refstub::cloud_subs().end()) return -1;
+  auto sub = refstub::state().cloud_subs.find("/velodyne_points");
+  if (sub == refstub::state().cloud_subs.end()) return -1;
   std::memset(cloudLabel, 0, sizeof(cloudLabel));                 // a fresh process starts from zeroed globals
   std::memset(cloudCurvature, 0, sizeof(cloudCurvature));
   std::memset(cloudNeighborPicked, 0, sizeof(cloudNeighborPicked));

@@ -123,6 +123,87 @@ def ref_scan_register(raw, n_scans=64, minimum_range=5.0):
     return out
 
 
+class RefOdometry:
+    """The reference's laserOdometry node (Aloam/src/laserOdometry.cpp) compiled from /root/reference: one step() per
+    sweep through the node's own main loop.  Process-wide state, like the node's globals."""
+
+    def __init__(self):
+        self.R = ref_lib("odom")
+        lib()                                      # the stand-ins call the oracle's kd-tree and minimiser
+        self.R.ref_odom_reset()
+        self.k = 0
+
+    def step(self, sharp, less_sharp, flat, less_flat, full=None):
+        a = [_f32(x).reshape(-1, 4) for x in (sharp, less_sharp, flat, less_flat, full if full is not None else np.zeros((0, 4), np.float32))]
+        out = np.zeros(14)
+        cnt = np.zeros(2, np.int32)
+        args = []
+        for x in a:
+            args += [_p(x), len(x)]
+        rc = self.R.ref_odom_step(*args, C.c_double(0.1 * self.k), _p(out), _p(cnt))
+        assert rc == 0, rc
+        self.k += 1
+        return (out[7:11].copy(), out[11:14].copy()), (out[0:4].copy(), out[4:7].copy()), cnt
+
+
+def ref_lm_solve(factors, q, t, max_iter=4):
+    """ceres::Solve on a problem built like the reference builds it, with the cost functors of lidarFactor.hpp as compiled
+    from /root/reference evaluated on dual numbers; the minimiser loop is oracle/lm.c (factor types 0 and 2)."""
+    R = ref_lib("odom")
+    lib()
+    f = np.ascontiguousarray(factors, FACTOR_DTYPE)
+    pose = Pose.make(q, t)
+    s = SolveSummary()
+    rc = R.ref_lm_solve(_p(f), len(f), C.byref(pose), max_iter, C.byref(s))
+    assert rc == 0, rc
+    qo, to = pose.as_np()
+    return qo, to, s
+
+
+def ref_normal_eq(factors, q, t):
+    R = ref_lib("odom")
+    lib()
+    f = np.ascontiguousarray(factors, FACTOR_DTYPE)
+    H = np.zeros(36)
+    g = np.zeros(6)
+    cost = C.c_double(0)
+    pose = Pose.make(q, t)
+    rc = R.ref_normal_eq(_p(f), len(f), C.byref(pose), _p(H), _p(g), C.byref(cost))
+    assert rc == 0, rc
+    return H.reshape(6, 6), g, cost.value
+
+
+class RefMapper:
+    """The reference's laserMapping node (Aloam/src/laserMapping.cpp) compiled from /root/reference: one step() per sweep
+    through the node's callbacks and process().  Process-wide state, like the node's globals."""
+
+    def __init__(self, line_res=0.4, plane_res=0.8):
+        self.R = ref_lib("mapping")
+        lib()
+        assert self.R.ref_mapping_reset(C.c_double(line_res), C.c_double(plane_res)) == 0
+        self.k = 0
+
+    def step(self, corner_last, surf_last, q_odom, t_odom, full_res=None):
+        c = _f32(corner_last).reshape(-1, 4)
+        s = _f32(surf_last).reshape(-1, 4)
+        fr = None if full_res is None else _f32(full_res).reshape(-1, 4).copy()
+        out = np.zeros(14)
+        info = np.zeros(4, np.int32)
+        q = np.ascontiguousarray(q_odom, np.float64)
+        t = np.ascontiguousarray(t_odom, np.float64)
+        rc = self.R.ref_mapping_step(_p(c), len(c), _p(s), len(s), _p(fr) if fr is not None else None, 0 if fr is None else len(fr),
+                                     _p(q), _p(t), C.c_double(0.1 * self.k), _p(out), _p(info))
+        assert rc == 0, rc
+        self.k += 1
+        return out[0:4].copy(), out[4:7].copy(), (out[7:11].copy(), out[11:14].copy()), [int(v) for v in info[:3]], fr
+
+    def export(self, which):
+        n = self.R.ref_mapping_export(which, None, 0)
+        o = np.zeros((max(n, 1), 4), np.float32)
+        self.R.ref_mapping_export(which, _p(o), n)
+        return o[:n]
+
+
 _lib = None
 
 

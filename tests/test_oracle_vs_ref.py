@@ -46,3 +46,122 @@ def test_scan_registration_oracle_equals_reference_source(oracle, n_scans, min_r
         assert np.array_equal(_bits(ref[k]), _bits(can[k])), k
     assert ref["less_flat"].shape == can["less_flat"].shape
     assert np.abs(ref["less_flat"] - can["less_flat"]).max() <= 3e-5              # a few fp32 ulps at 50-100 m (summation order of the voxel members)
+
+
+# lidarFactor.hpp: LidarEdgeFactor / LidarPlaneNormFactor evaluated on dual numbers (the autodiff stand-in) inside a problem
+# built the way the reference builds it, against the oracle's analytic residual blocks: normal equations, iteration
+# trace, termination and final pose.  (LidarPlaneFactor takes three points, not a stored normal: it is covered by the
+# odometry sequence below.)
+def test_factors_and_solve_oracle_equals_reference_functors(oracle):
+    _need("odom")
+    from test_oracle_primitives import _random_factors
+    rng = np.random.default_rng(17)
+    for trial in range(4):
+        f = _random_factors(oracle, rng, 200)
+        f = f[f["type"] != 1]
+        q0 = np.array([0.01, -0.006, 0.008, 1.0]) * np.r_[rng.uniform(0.5, 1.5, 3), 1.0]
+        q0 /= np.linalg.norm(q0)
+        t0 = rng.uniform(-0.08, 0.08, 3)
+        H, g, c = oracle.normal_eq(f, q0, t0)
+        rH, rg, rc = oracle_lib.ref_normal_eq(f, q0, t0)
+        assert np.abs(H - rH).max() <= 1e-13 * np.abs(H).max() and np.abs(g - rg).max() <= 1e-13 * np.abs(g).max() and abs(c - rc) <= 1e-13 * c
+        q, t, s = oracle.lm_solve(f, q0, t0, 4)
+        rq, rt, rs = oracle_lib.ref_lm_solve(f, q0, t0, 4)
+        assert (s.iterations, s.num_successful, s.termination) == (rs.iterations, rs.num_successful, rs.termination), trial
+        assert np.abs(q - rq).max() <= 1e-14 and np.abs(t - rt).max() <= 1e-14
+        assert abs(s.final_cost - rs.final_cost) <= 1e-12 * s.final_cost
+
+
+# laserOdometry.cpp:220-598, the node's own loop over consecutive HDL-32 sweeps: TransformToStart, the two
+# correspondence searches with their ring-window scans, factor construction (LidarEdgeFactor / LidarPlaneFactor), two
+# solves per sweep, pose accumulation, buffer swap
+def test_odometry_sequence_oracle_equals_reference_source(oracle):
+    _need("odom")
+    w = synth.make_world()
+    rng = np.random.default_rng(5)
+    ref = oracle_lib.RefOdometry()
+    od = oracle.Odometry()
+    moved = 0.0
+    for k in range(8):
+        q, t = synth.loop_pose(w, 1.0 * k)
+        raw = synth.raycast_sweep(w, q, t, 32, 900, rng)
+        f = oracle.scan_register(raw, 32, 0.3)
+        (lq, lt), (wq, wt), rep = od.step(f["sharp"], f["less_sharp"], f["flat"], f["less_flat"])
+        (rlq, rlt), (rwq, rwt), cnt = ref.step(f["sharp"], f["less_sharp"], f["flat"], f["less_flat"], f["full"])
+        assert [int(cnt[0]), int(cnt[1])] == [rep.corner_corr[1], rep.plane_corr[1]], k         # correspondences of the last pass
+        if k:
+            assert cnt[0] > 100 and cnt[1] > 300
+        assert np.abs(lq - rlq).max() <= 1e-14 and np.abs(lt - rlt).max() <= 1e-13, k
+        assert np.abs(wq - rwq).max() <= 1e-14 and np.abs(wt - rwt).max() <= 1e-13, k
+        moved = float(np.linalg.norm(wt))
+    assert moved > 5.0
+    od.close()
+
+
+# laserMapping.cpp:232-903, the node's own process() over consecutive sweeps from an empty map: transformAssociateToMap,
+# window bookkeeping, the 5-NN association with the eigenvalue / plane-distance gates, LidarEdgeFactor /
+# LidarPlaneNormFactor construction, two solves, transformUpdate, insertion, per-cube VoxelGrid refilter, the registered cloud
+def test_mapping_sequence_oracle_equals_reference_source(oracle):
+    _need("mapping")
+    import scenario
+    ref = oracle_lib.RefMapper()
+    om = oracle.Mapper(order_mode=1, use_kdtree=1)          # the stand-in VoxelGrid sorts with this toolchain's std::sort, like PCL would
+    n_opt = 0
+    for k, (c, s, qg, tg, qo, to) in enumerate(scenario.sweeps(10, n_corner=1500, n_surf=9000)):
+        full = np.concatenate([c, s])[:6000]
+        rq, rt, (rwq, rwt), rcen, rfull = ref.step(c, s, qo, to, full)
+        q, t, rep, ofull = om.step(c, s, qo, to, full)
+        wq, wt, cen = om.get_state()
+        assert rcen == cen, k
+        assert np.abs(q - rq).max() <= 1e-13 and np.abs(t - rt).max() <= 1e-12, (k, q - rq, t - rt)
+        assert np.abs(wq - rwq).max() <= 1e-13 and np.abs(wt - rwt).max() <= 1e-11, k
+        assert np.array_equal(rfull.view(np.uint32), ofull.view(np.uint32)), k                    # /velodyne_cloud_registered
+        for which in (0, 1):
+            a, b = ref.export(which), om.export(which, 1)
+            assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), (k, which)   # every cube, bit for bit
+        n_opt += int(rep.solve[0].iterations > 0)
+    assert n_opt >= 8
+    om.close()
+
+
+def _sparse(seed, n, lo, hi):
+    rng = np.random.default_rng(seed)
+    p = np.zeros((n, 4), np.float32)
+    p[:, :3] = rng.uniform(lo, hi, (n, 3))
+    return p
+
+
+# laserMapping.cpp:323-507: the six window-shift loops.  The sensor hops out to +-600 m and back along x and y, down to
+# -360 m and up to +360 m along z, then along a diagonal; every hop inserts a sparse sweep.  cen, both maps and the pose
+# are compared after every hop.
+def test_mapping_window_shifts_oracle_equals_reference_source(oracle):
+    _need("mapping")
+    ref = oracle_lib.RefMapper()
+    om = oracle.Mapper(order_mode=1, use_kdtree=1)
+    legs = []
+    for axis, reach in ((0, 600.0), (1, 600.0), (2, 360.0)):
+        for sgn in (1, -1):
+            out = [sgn * 40.0 * k for k in range(1, int(reach / 40) + 1)]
+            for v in out + out[-2::-1] + [0.0]:
+                t = np.zeros(3)
+                t[axis] = v
+                legs.append(t)
+    legs += [np.array([55.0 * k, -47.0 * k, 31.0 * k]) for k in list(range(1, 10)) + list(range(8, -1, -1))]
+    q = np.array([0.0, 0.0, 0.0, 1.0])
+    cens = set()
+    for h, t in enumerate(legs):
+        c = _sparse(1000 + h, 300, [-70, -70, -30], [70, 70, 30])
+        s = _sparse(2000 + h, 900, [-70, -70, -30], [70, 70, 30])
+        rq, rt, _, rcen, _ = ref.step(c, s, q, t)
+        oq, ot, rep, _ = om.step(c, s, q, t)
+        _, _, cen = om.get_state()
+        assert rcen == cen, h
+        cens.add(tuple(cen))
+        assert np.array_equal(rq, oq) and np.array_equal(rt, ot), h
+        for which in (0, 1):
+            a, b = ref.export(which), om.export(which, 1)
+            assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), (h, which)
+    lo = np.min(np.array(list(cens)), axis=0)
+    hi = np.max(np.array(list(cens)), axis=0)
+    assert (lo < [10, 10, 5]).all() and (hi > [10, 10, 5]).all()       # the window moved in both directions on every axis
+    om.close()
