@@ -112,3 +112,27 @@ extern "C" int ref_mapping_export(int which, float* out, int cap) {
   }
   return n;
 }
+
+// harness conveniences for the timed arm (bench.py --impl reference), not node code: a prior map is dealt into the node's
+// cube clouds by the node's cube rule (:741-757) and passed once through the node's own per-cube filters (:788-801);
+// q/t_wmap_wodom can be put back to a given value between registrations.
+extern "C" int ref_mapping_import(int which, const float* xyzi, int n) {
+  pcl::PointCloud<PointType>::Ptr* arr = which == 0 ? laserCloudCornerArray : laserCloudSurfArray;
+  for (int i = 0; i < n; ++i) {
+    PointType p; p.x = xyzi[4 * i]; p.y = xyzi[4 * i + 1]; p.z = xyzi[4 * i + 2]; p.intensity = xyzi[4 * i + 3];
+    int c[3]; const float v[3] = { p.x, p.y, p.z }; const int cen[3] = { laserCloudCenWidth, laserCloudCenHeight, laserCloudCenDepth };
+    for (int a = 0; a < 3; ++a) { c[a] = int((v[a] + 25.0) / 50.0) + cen[a]; if (v[a] + 25.0 < 0) c[a]--; }
+    if (c[0] < 0 || c[0] >= laserCloudWidth || c[1] < 0 || c[1] >= laserCloudHeight || c[2] < 0 || c[2] >= laserCloudDepth) continue;
+    arr[c[0] + laserCloudWidth * c[1] + laserCloudWidth * laserCloudHeight * c[2]]->push_back(p);
+  }
+  for (int i = 0; i < laserCloudNum; ++i) {
+    if (arr[i]->points.empty()) continue;
+    pcl::PointCloud<PointType>::Ptr tmp(new pcl::PointCloud<PointType>());
+    pcl::VoxelGrid<PointType>& f = which == 0 ? downSizeFilterCorner : downSizeFilterSurf;
+    f.setInputCloud(arr[i]); f.filter(*tmp); arr[i] = tmp;
+  }
+  return 0;
+}
+extern "C" void ref_mapping_set_state(const double q[4], const double t[3]) {
+  q_wmap_wodom = Eigen::Quaterniond(q[3], q[0], q[1], q[2]); t_wmap_wodom = Eigen::Vector3d(t[0], t[1], t[2]);
+}

@@ -197,6 +197,15 @@ class RefMapper:
         self.k += 1
         return out[0:4].copy(), out[4:7].copy(), (out[7:11].copy(), out[11:14].copy()), [int(v) for v in info[:3]], fr
 
+    def import_points(self, which, pts):
+        pts = _f32(pts).reshape(-1, 4)
+        self.R.ref_mapping_import(which, _p(pts), len(pts))
+
+    def set_state(self, q, t):
+        q = np.ascontiguousarray(q, np.float64)
+        t = np.ascontiguousarray(t, np.float64)
+        self.R.ref_mapping_set_state(_p(q), _p(t))
+
     def export(self, which):
         n = self.R.ref_mapping_export(which, None, 0)
         o = np.zeros((max(n, 1), 4), np.float32)
