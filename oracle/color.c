@@ -170,6 +170,14 @@ static void gaussian5(const uint8_t* src, uint8_t* dst, int W, int H) {
     }
 }
 
+/* test hooks for the oracle/_ref builds: the OpenCV restatements one by one, so that the stand-in cv:: functions the
+ * reference's depthFill calls (refstubs/opencv2/opencv.hpp) are these very routines */
+void lmono_cpu_cv_kernel(int type, int ks, uint8_t* k) { make_kernel(type, ks, k); }
+void lmono_cpu_cv_morph(const uint8_t* src, uint8_t* dst, int W, int H, const uint8_t* k, int ks, int is_erode) { morph(src, dst, W, H, k, ks, is_erode); }
+void lmono_cpu_cv_median5(const uint8_t* src, uint8_t* dst, int W, int H) { median5(src, dst, W, H); }
+void lmono_cpu_cv_bilateral5(const uint8_t* src, uint8_t* dst, int W, int H, double sigma_color, double sigma_space) { bilateral5(src, dst, W, H, sigma_color, sigma_space); }
+void lmono_cpu_cv_gaussian5(const uint8_t* src, uint8_t* dst, int W, int H) { gaussian5(src, dst, W, H); }
+
 /* D3 */
 int lmono_cpu_depth_fill(const uint8_t* depth_raw, const o_camera* cam, uint8_t* out) {
   const int W = cam->width, H = cam->height; const size_t N = (size_t)W * H;

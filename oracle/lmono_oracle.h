@@ -12,15 +12,17 @@
  * (SURVEY.md section 4), and its third-party dependencies (ROS, PCL, FLANN,
  * Ceres, Eigen, OpenCV) are not installable here.  What pins this oracle:
  * (1) THE REFERENCE'S OWN SOURCES RUN HERE: `make ref` compiles the translation
- * units Aloam/src/scanRegistration.cpp, laserOdometry.cpp, laserMapping.cpp and
- * lidarFactor.hpp where they lie under /root/reference (a driver #includes
+ * units Aloam/src/scanRegistration.cpp, laserOdometry.cpp, laserMapping.cpp,
+ * lidarFactor.hpp and mono_lidar_mapping/src/map_builder/Map_Builder.cc where
+ * they lie under /root/reference (a driver #includes
  * them, nothing is copied) against functional stand-ins for those libraries
  * (refstubs/), into oracle/_ref/; tests/test_oracle_vs_ref.py runs the nodes'
  * own callbacks / main loops beside this oracle: full cloud, curvature, labels
  * and feature clouds bit for bit; odometry correspondences and poses; mapping
  * poses, registered clouds and every cube of the map bit for bit through all
  * six window shifts; solver traces with the reference cost functors on dual
- * numbers.  Everything between the library calls is therefore pinned against
+ * numbers; the colour mapper's raster, filled depth image and lifted clouds
+ * bit for bit.  Everything between the library calls is therefore pinned against
  * reference code compiled by this toolchain.
  * (2) THE LIBRARY ALGORITHMS remain restatements of the published code of the
  * un-vendored dependencies (PCL 1.8 VoxelGrid / KdTreeFLANN, FLANN 1.8/1.9
@@ -28,8 +30,8 @@
  * SelfAdjointEigenSolver / ColPivHouseholderQR, OpenCV 3.2 morphology / blur),
  * unpinned against those libraries' binaries; they are cross-checked against
  * scipy / numpy / cv2 and independent Python restatements in tests/
- * (test_oracle_primitives.py, test_oracle_*_python.py).  The colour mapper
- * (Map_Builder.cc, PinholeCamera.cc) is pinned only this second way.
+ * (test_oracle_primitives.py, test_oracle_*_python.py).  camodocal's
+ * PinholeCamera.cc is pinned only this second way.
  *
  * Every function cites the reference file:line it follows (paths relative to
  * /root/reference).
@@ -208,6 +210,13 @@ int lmono_cpu_depth_fill(const uint8_t* depth_raw, const o_camera* cam, uint8_t*
 int lmono_cpu_lift_cloud(const uint8_t* depth, const uint8_t* bgr, const o_camera* cam,
                          const o_pose* QT, float* cloud_cam_xyz, float* cloud_world_xyz,
                          uint8_t* cloud_rgb, int cap, int* n_out);
+
+/* test hooks for the oracle/_ref builds: the OpenCV 8UC1 restatements of color.c one by one (kernel type 0 RECT 1 CROSS 2 ELLIPSE) */
+void lmono_cpu_cv_kernel(int type, int ks, uint8_t* k);
+void lmono_cpu_cv_morph(const uint8_t* src, uint8_t* dst, int W, int H, const uint8_t* k, int ks, int is_erode);
+void lmono_cpu_cv_median5(const uint8_t* src, uint8_t* dst, int W, int H);
+void lmono_cpu_cv_bilateral5(const uint8_t* src, uint8_t* dst, int W, int H, double sigma_color, double sigma_space);
+void lmono_cpu_cv_gaussian5(const uint8_t* src, uint8_t* dst, int W, int H);
 
 /* libstdc++ std::sort shims (stdsort_shim.cpp): reproduce the reference's unstable sorts */
 void lmono_cpu_stdsort_voxel_pairs(uint32_t* idx, uint32_t* pt, int n);          /* PCL cloud_point_index_idx operator< */

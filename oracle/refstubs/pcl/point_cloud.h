@@ -8,6 +8,7 @@ namespace pcl {
 struct PCLHeader { std::uint32_t seq = 0; std::uint64_t stamp = 0; std::string frame_id; };
 template <class P> struct PointCloud {
   typedef boost::shared_ptr<PointCloud<P>> Ptr; typedef boost::shared_ptr<const PointCloud<P>> ConstPtr;
+  typedef typename std::vector<P>::iterator iterator; typedef typename std::vector<P>::const_iterator const_iterator;
   PCLHeader header; std::vector<P> points; std::uint32_t width = 0, height = 0; bool is_dense = true;
   PointCloud& operator+=(const PointCloud& o) {          // point_cloud.h: append, width = size, height = 1
     points.insert(points.end(), o.points.begin(), o.points.end()); width = (std::uint32_t)points.size(); height = 1;

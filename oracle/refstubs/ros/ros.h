@@ -53,4 +53,5 @@ inline void spin() {}
 #define ROS_INFO(...) ((void)0)
 #define ROS_WARN(...) ((void)0)
 #define ROS_ERROR(...) ((void)0)
+#define ROS_INFO_STREAM(x) ((void)0)
 #define ROS_BREAK() std::abort()

@@ -213,6 +213,26 @@ class RefMapper:
         return o[:n]
 
 
+def ref_color_frame(pts_cam, bgr, cam, q, t):
+    """MapBuilder::associateToMap of the reference (mono_lidar_mapping/src/map_builder/Map_Builder.cc:213-334) as compiled
+    from /root/reference: raster before depthFill, depth image after it, lifted cloud (camera frame, world frame, r g b)."""
+    R = ref_lib("color")
+    lib()
+    pts = _f32(pts_cam)
+    img = np.ascontiguousarray(bgr, np.uint8)
+    npix = cam.width * cam.height
+    raw = np.zeros((cam.height, cam.width), np.uint8)
+    filled = np.zeros((cam.height, cam.width), np.uint8)
+    cc = np.zeros((npix, 3), np.float32)
+    cw = np.zeros((npix, 3), np.float32)
+    rgb = np.zeros((npix, 3), np.uint8)
+    n = C.c_int(0)
+    pose = Pose.make(q, t)
+    rc = R.ref_color_frame(_p(pts), len(pts), pts.shape[1], _p(img), C.byref(cam), C.byref(pose), _p(raw), _p(filled), _p(cc), _p(cw), _p(rgb), npix, C.byref(n))
+    assert rc == 0, rc
+    return raw, filled, cc[: n.value], cw[: n.value], rgb[: n.value]
+
+
 _lib = None
 
 

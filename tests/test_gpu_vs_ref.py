@@ -87,3 +87,31 @@ def test_mapping_equals_reference_node(gpu_ctx_factory):
         n_opt += int(grep.optimized)
     assert n_opt >= 8 and ctx.last_fault() == 0
     print(f"mapping vs reference node: worst pose difference {worst:.2e}")
+
+
+@pytest.mark.parametrize("kernel_type,blur_type,dist", [(0, 0, False), (2, 1, True)])
+def test_colour_frame_equals_reference_mapper(gpu_ctx_factory, kernel_type, blur_type, dist):
+    """lmono_project_color beside MapBuilder::associateToMap compiled from the reference (Map_Builder.cc:213-416)"""
+    _need("color")
+    from lmono_b200 import api
+    ctx = gpu_ctx_factory()
+    rng = np.random.default_rng(21)
+    n = 120_000
+    pts = np.zeros((n, 3), np.float32)
+    pts[:, 2] = rng.uniform(-5, 110, n)
+    pts[:, 0] = rng.uniform(-1, 1, n) * pts[:, 2] * 0.95
+    pts[:, 1] = rng.uniform(-0.3, 0.3, n) * pts[:, 2]
+    img = rng.integers(0, 256, (376, 1241, 3), dtype=np.uint8)
+    kw = dict(k1=-0.05, k2=0.01, p1=0.001, p2=-0.002) if dist else {}
+    ocam = oracle_lib.make_camera(kernel_type=kernel_type, blur_type=blur_type, **kw)
+    gcam = api.Pinhole(ocam.fx, ocam.fy, ocam.cx, ocam.cy, ocam.k1, ocam.k2, ocam.p1, ocam.p2, ocam.width, ocam.height, kernel_type, 5, blur_type)
+    q = np.array([0.01, -0.02, 0.3, 0.95])
+    q /= np.linalg.norm(q)
+    t = np.array([10.0, -3.0, 1.5])
+    got = ctx.project_color(pts, img, gcam, q, t)
+    raw, filled, cc, cw, rgb = oracle_lib.ref_color_frame(pts, img, ocam, q, t)
+    assert np.array_equal(got["depth_raw"], raw) and np.array_equal(got["depth"], filled)
+    assert got["cloud_cam"].shape == cc.shape and len(cc) > 10000
+    assert np.array_equal(got["cloud_cam"].view(np.uint32), cc.view(np.uint32))
+    assert np.array_equal(got["cloud_world"].view(np.uint32), cw.view(np.uint32))
+    assert np.array_equal(got["rgb"], rgb)

@@ -165,3 +165,33 @@ def test_mapping_window_shifts_oracle_equals_reference_source(oracle):
     hi = np.max(np.array(list(cens)), axis=0)
     assert (lo < [10, 10, 5]).all() and (hi > [10, 10, 5]).all()       # the window moved in both directions on every axis
     om.close()
+
+
+# Map_Builder.cc:213-334 MapBuilder::associateToMap (with depthFill :336-403 and Point3DTo2D :405-416): the projection raster
+# with its implicit conversions and last-writer rule, depthFill's own sequence of morphology / blur calls for the three
+# kernel types and both blur types, the per-pixel lift (depth window, |x| > 20 && y > 1.8 rule), the world transform --
+# with and without lens distortion
+@pytest.mark.parametrize("kernel_type,kernel_size,blur_type,dist", [(0, 5, 0, False), (1, 5, 1, False), (2, 7, 0, False), (0, 5, 1, True)])
+def test_colour_mapper_oracle_equals_reference_source(oracle, kernel_type, kernel_size, blur_type, dist):
+    _need("color")
+    kw = dict(k1=-0.05, k2=0.01, p1=0.001, p2=-0.0005) if dist else {}
+    cam = oracle.make_camera(kernel_type=kernel_type, kernel_size=kernel_size, blur_type=blur_type, **kw)
+    rng = np.random.default_rng(12 + kernel_type)
+    n = 120_000
+    pts = np.zeros((n, 3), np.float32)
+    pts[:, 2] = rng.uniform(-5, 130, n)                                       # behind the camera, and beyond 100 m (the uchar wraps)
+    pts[:, 0] = rng.uniform(-1, 1, n) * pts[:, 2]
+    pts[:, 1] = rng.uniform(-0.35, 0.35, n) * pts[:, 2]
+    pts[:5, 2] = 0.0
+    img = rng.integers(0, 255, (cam.height, cam.width, 3)).astype(np.uint8)
+    q = np.array([0.1, -0.2, 0.05, 0.97])
+    q /= np.linalg.norm(q)
+    t = np.array([3.0, -1.0, 0.5])
+    raw, filled, cc, cw, rgb = oracle_lib.ref_color_frame(pts, img, cam, q, t)
+    oraw = oracle.project_raster(pts, cam)
+    assert (raw > 0).sum() > 50000 and np.array_equal(raw, oraw)
+    ofill = oracle.depth_fill(oraw, cam)
+    assert np.array_equal(filled, ofill)
+    occ, ocw, orgb = oracle.lift_cloud(ofill, img, cam, q, t)
+    assert cc.shape == occ.shape and len(cc) > 10000
+    assert np.array_equal(cc.view(np.uint32), occ.view(np.uint32)) and np.array_equal(cw.view(np.uint32), ocw.view(np.uint32)) and np.array_equal(rgb, orgb)
