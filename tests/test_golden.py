@@ -184,3 +184,128 @@ def test_gpu_color_golden(gpu_ctx_factory):
     assert np.array_equal(r["depth_raw"], g["depth_raw"]) and np.array_equal(r["depth"], g["depth_filled"])
     assert np.array_equal(bits(r["cloud_cam"]), bits(g["cloud_cam"])) and np.array_equal(bits(r["cloud_world"]), bits(g["cloud_world"]))
     assert np.array_equal(r["rgb"], g["rgb"])
+
+
+# ============================================================================= vectors generated by the REFERENCE's own code
+# tests/golden/ref_nodes.npz (tests/golden/make_golden_ref.py): outputs of the reference's scanRegistration / laserOdometry /
+# laserMapping nodes and colour mapper as compiled from /root/reference into oracle/_ref.  Committed, so these checks need
+# neither the reference tree nor the prebuilt libraries.
+def _ang(q0, q1):
+    return 2 * np.arccos(min(1.0, abs(float(np.dot(q0, q1)))))
+
+
+def _check_scan_ref(got, g, tag, exact_intensity):
+    assert got["full"].shape == g[f"{tag}_full"].shape
+    assert np.array_equal(bits(got["full"][:, :3]), bits(g[f"{tag}_full"][:, :3]))
+    assert np.array_equal(np.floor(got["full"][:, 3]), np.floor(g[f"{tag}_full"][:, 3]))
+    assert np.abs(got["full"][:, 3] - g[f"{tag}_full"][:, 3]).max() <= (0.0 if exact_intensity else 4e-6)
+    assert np.array_equal(bits(got["curvature"][5:-5]), bits(g[f"{tag}_curvature"][5:-5]))
+    assert np.array_equal(np.asarray(got["labels"], np.int8), g[f"{tag}_labels"])
+    for k in ("sharp", "less_sharp", "flat"):
+        assert got[k].shape == g[f"{tag}_{k}"].shape and len(got[k]) > 0, k
+        assert np.array_equal(bits(got[k][:, :3]), bits(g[f"{tag}_{k}"][:, :3])), k
+    assert got["less_flat"].shape == g[f"{tag}_less_flat"].shape
+    assert np.abs(got["less_flat"] - g[f"{tag}_less_flat"]).max() <= 3e-5          # voxel members summed in another order (introsort vs input order)
+
+
+@pytest.mark.parametrize("tag", ["s64", "s16"])
+def test_oracle_scan_reference_golden(oracle, tag):
+    g = load("ref_nodes")
+    n_scans, min_range = int(g[f"{tag}_cfg"][0]), float(g[f"{tag}_cfg"][1])
+    _check_scan_ref(oracle.scan_register(g[f"{tag}_raw"], n_scans, min_range), g, tag, exact_intensity=True)
+    r = oracle.scan_register(g[f"{tag}_raw"], n_scans, min_range, voxel_order_mode=1, sort_mode=1)        # the toolchain's own sorts: everything bit for bit
+    assert np.array_equal(bits(r["less_flat"]), bits(g[f"{tag}_less_flat"]))
+
+
+def test_oracle_odometry_reference_golden(oracle):
+    g = load("ref_nodes")
+    od = oracle.Odometry()
+    for k in range(6):
+        (lq, lt), (wq, wt), rep = od.step(*(g[f"od{k}_{n}"] for n in ("sharp", "less_sharp", "flat", "less_flat")))
+        p = g["od_poses"][k]
+        assert [rep.corner_corr[1], rep.plane_corr[1]] == [int(p[14]), int(p[15])], k
+        assert np.abs(np.concatenate([lq, lt, wq, wt]) - p[:14]).max() <= 1e-12, k
+    assert np.linalg.norm(g["od_poses"][5][11:14]) > 3.0
+    od.close()
+
+
+def test_oracle_mapping_reference_golden(oracle):
+    g = load("ref_nodes")
+    om = oracle.Mapper(order_mode=1, use_kdtree=1)
+    for k in range(6):
+        p = g["mp_poses"][k]
+        q, t, rep, reg = om.step(g[f"mp{k}_corner"], g[f"mp{k}_surf"], p[:4], p[4:7], g[f"mp{k}_full"])
+        wq, wt, cen = om.get_state()
+        assert np.abs(np.concatenate([q, t]) - p[7:14]).max() <= 1e-11 and np.abs(np.concatenate([wq, wt]) - p[14:21]).max() <= 1e-10, k
+        assert cen == [int(v) for v in p[21:24]]
+        assert np.array_equal(bits(reg), bits(g[f"mp{k}_registered"])), k
+    for which, key in ((0, "mp_map_corner"), (1, "mp_map_surf")):
+        got = om.export(which, 1)
+        assert got.shape == g[key].shape and np.array_equal(bits(got), bits(g[key])), key
+    om.close()
+
+
+def _ref_cam(g):
+    c = g["col_cam"]
+    return c, dict(fx=c[0], fy=c[1], cx=c[2], cy=c[3], k1=c[4], k2=c[5], p1=c[6], p2=c[7], width=int(c[8]), height=int(c[9]),
+                   kernel_type=int(c[10]), kernel_size=int(c[11]), blur_type=int(c[12]))
+
+
+def test_oracle_color_reference_golden(oracle):
+    g = load("ref_nodes")
+    _, kw = _ref_cam(g)
+    cam = oracle.make_camera(**kw)
+    raw = oracle.project_raster(g["col_pts"], cam)
+    assert np.array_equal(raw, g["col_raw"])
+    fill = oracle.depth_fill(raw, cam)
+    assert np.array_equal(fill, g["col_filled"])
+    cc, cw, rgb = oracle.lift_cloud(fill, g["col_img"], cam, g["col_pose"][:4], g["col_pose"][4:])
+    assert len(cc) > 1000 and np.array_equal(bits(cc), bits(g["col_cloud_cam"])) and np.array_equal(bits(cw), bits(g["col_cloud_world"]))
+    assert np.array_equal(rgb, g["col_rgb"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["s64", "s16"])
+def test_gpu_scan_reference_golden(gpu_ctx_factory, tag):
+    g = load("ref_nodes")
+    ctx = gpu_ctx_factory(scan_line=int(g[f"{tag}_cfg"][0]), minimum_range=float(g[f"{tag}_cfg"][1]))
+    _check_scan_ref(ctx.scan_register(g[f"{tag}_raw"], want_debug=True), g, tag, exact_intensity=False)
+
+
+@pytest.mark.gpu
+def test_gpu_odometry_reference_golden(gpu_ctx_factory):
+    g = load("ref_nodes")
+    ctx = gpu_ctx_factory(scan_line=16, minimum_range=0.3, max_cubes_corner=8, max_cubes_surf=8, cube_capacity_corner=1024, cube_capacity_surf=1024)
+    for k in range(6):
+        (lq, lt), (wq, wt), rep = ctx.odom_step(*(g[f"od{k}_{n}"] for n in ("sharp", "less_sharp", "flat", "less_flat")))
+        p = g["od_poses"][k]
+        assert [rep.corner_corr[1], rep.plane_corr[1]] == [int(p[14]), int(p[15])], k
+        assert np.linalg.norm(lt - p[4:7]) <= 1e-4 and np.linalg.norm(wt - p[11:14]) <= 1e-4 and _ang(lq, p[0:4]) <= 1e-4 and _ang(wq, p[7:11]) <= 1e-4, k
+
+
+@pytest.mark.gpu
+def test_gpu_mapping_reference_golden(gpu_ctx_factory):
+    g = load("ref_nodes")
+    ctx = gpu_ctx_factory()
+    for k in range(6):
+        p = g["mp_poses"][k]
+        q, t, rep, reg = ctx.map_step(g[f"mp{k}_corner"], g[f"mp{k}_surf"], p[:4], p[4:7], full_res=g[f"mp{k}_full"])
+        assert np.linalg.norm(t - p[11:14]) <= 1e-4 and _ang(q, p[7:11]) <= 1e-4, k
+        assert list(rep.cen) == [int(v) for v in p[21:24]]
+        assert np.abs(reg - g[f"mp{k}_registered"]).max() <= 1e-4, k
+    for which, key in ((0, "mp_map_corner"), (1, "mp_map_surf")):
+        got = ctx.map_export(which, 1)
+        assert got.shape == g[key].shape and np.abs(got - g[key]).max() <= 1e-4, key
+
+
+@pytest.mark.gpu
+def test_gpu_color_reference_golden(gpu_ctx_factory):
+    from lmono_b200 import api
+    g = load("ref_nodes")
+    c, kw = _ref_cam(g)
+    ctx = gpu_ctx_factory(image_width=kw["width"], image_height=kw["height"])
+    cam = api.Pinhole(c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], kw["width"], kw["height"], kw["kernel_type"], kw["kernel_size"], kw["blur_type"])
+    r = ctx.project_color(g["col_pts"], g["col_img"], cam, g["col_pose"][:4], g["col_pose"][4:])
+    assert np.array_equal(r["depth_raw"], g["col_raw"]) and np.array_equal(r["depth"], g["col_filled"])
+    assert np.array_equal(bits(r["cloud_cam"]), bits(g["col_cloud_cam"])) and np.array_equal(bits(r["cloud_world"]), bits(g["col_cloud_world"]))
+    assert np.array_equal(r["rgb"], g["col_rgb"])
