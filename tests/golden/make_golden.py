@@ -2,8 +2,9 @@
 """Generates tests/golden/*.npz: small seeded inputs together with the outputs of the CPU oracle
 (oracle/*.c, the restatement of the reference's A-LOAM / map-builder arithmetic).
 
-The reference ships no tests or fixtures for this path and cannot be built here,
-so these vectors are what pins the oracle AND the CUDA path against silent drift:
+The reference ships no tests or fixtures for this path; the oracle itself is pinned against the
+reference's own sources compiled into oracle/_ref (tests/test_oracle_vs_ref.py, make_golden_ref.py).  These
+vectors guard the oracle AND the CUDA path against silent drift:
 `tests/test_golden.py` re-runs the oracle (-m "not gpu") and the C-ABI CUDA library (-m gpu) on
 the stored inputs and compares with the stored outputs.  Regenerate only when the oracle is
 deliberately changed:  python tests/golden/make_golden.py

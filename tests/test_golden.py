@@ -1,9 +1,10 @@
 """Committed golden vectors (tests/golden/*.npz, made by tests/golden/make_golden.py).
 
-The reference has no tests / fixtures for this path, so the pin is: seeded inputs +
-oracle outputs stored in the repo.  The CPU half (-m "not gpu") checks that the oracle still
-reproduces them bit for bit; the GPU half (-m gpu) checks the CUDA library through the C ABI
-against the same stored outputs -- no oracle involved on that side."""
+The reference has no tests / fixtures for this path.  Two kinds of stored vectors: seeded inputs +
+ORACLE outputs (make_golden.py: every stage and primitive), and seeded inputs + outputs of the REFERENCE'S OWN CODE
+compiled from /root/reference (ref_nodes.npz, make_golden_ref.py; second half of this file).  The CPU half
+(-m "not gpu") checks that the oracle still reproduces them; the GPU half (-m gpu) checks the CUDA library through
+the C ABI against the same stored outputs -- no oracle involved on that side."""
 import os
 
 import numpy as np
