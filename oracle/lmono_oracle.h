@@ -13,8 +13,8 @@
  * Ceres, Eigen, OpenCV) are not installable here.  What pins this oracle:
  * (1) THE REFERENCE'S OWN SOURCES RUN HERE: `make ref` compiles the translation
  * units Aloam/src/scanRegistration.cpp, laserOdometry.cpp, laserMapping.cpp,
- * lidarFactor.hpp and mono_lidar_mapping/src/map_builder/Map_Builder.cc where
- * they lie under /root/reference (a driver #includes
+ * lidarFactor.hpp and mono_lidar_mapping/src/map_build_node.cc +
+ * map_builder/Map_Builder.cc where they lie under /root/reference (a driver #includes
  * them, nothing is copied) against functional stand-ins for those libraries
  * (refstubs/), into oracle/_ref/; tests/test_oracle_vs_ref.py runs the nodes'
  * own callbacks / main loops beside this oracle: full cloud, curvature, labels

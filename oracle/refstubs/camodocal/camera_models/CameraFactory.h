@@ -4,6 +4,7 @@
 // PinholeCamera.cc pulls in the whole calibration tool chain (OpenCV calib3d, FileStorage) and was not compiled.
 // Library stand-in, not reference source.
 #include <memory>
+#include <string>
 #include <eigen3/Eigen/Dense>
 #include <pcl/point_cloud.h>     // boost::shared_ptr alias
 namespace camodocal {
@@ -11,6 +12,8 @@ class Camera { public: virtual ~Camera() {}
   virtual void spaceToPlane(const Eigen::Vector3d& P, Eigen::Vector2d& p) const = 0;
   virtual void liftProjective(const Eigen::Vector2d& p, Eigen::Vector3d& P) const = 0; };
 typedef boost::shared_ptr<Camera> CameraPtr;
+class CameraFactory { public: static CameraFactory* instance() { static CameraFactory f; return &f; }   // declaration-level (main() only)
+  CameraPtr generateCameraFromYamlFile(const std::string&) { return CameraPtr(); } };
 class PinholeCamera : public Camera {
  public:
   PinholeCamera(double fx, double fy, double cx, double cy, double k1, double k2, double p1, double p2)

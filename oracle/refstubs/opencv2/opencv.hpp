@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <string>
 #include <vector>
 #include "lmono_oracle.h"
 #define CV_8UC1 0
@@ -37,6 +38,9 @@ class Mat {
   template <class T> const T& at(int r, int c) const { return *reinterpret_cast<const T*>(buf->data() + ((std::size_t)r * cols + c) * sizeof(T)); }
 };
 enum { COLOR_BGR2HSV = 40, COLOR_HSV2BGR = 54, COLORMAP_JET = 2 };
+// declaration-level: the node reads its yaml configuration through these in main(), which the tests do not run
+struct FileNode { template <class T> void operator>>(T&) const {} };
+struct FileStorage { enum { READ = 0 }; FileStorage(const std::string&, int) {} bool isOpened() const { return false; } FileNode operator[](const char*) const { return FileNode(); } };
 enum { MORPH_RECT = 0, MORPH_CROSS = 1, MORPH_ELLIPSE = 2 };
 enum { MORPH_ERODE = 0, MORPH_DILATE = 1, MORPH_OPEN = 2, MORPH_CLOSE = 3 };
 namespace refstub_cv { struct Log { std::vector<Mat> dilate_inputs; Mat colormap_input; }; inline Log& log() { static Log l; return l; } }

@@ -12,6 +12,8 @@
 #include <ros/time.h>
 #include <sensor_msgs/PointCloud2.h>
 #include <nav_msgs/Odometry.h>
+#include <sensor_msgs/Image.h>
+#define ROSCONSOLE_DEFAULT_NAME "ros"
 namespace refstub {
 typedef std::function<void(const sensor_msgs::PointCloud2ConstPtr&)> CloudCb;
 typedef std::function<void(const nav_msgs::Odometry::ConstPtr&)> OdomCb;
@@ -37,6 +39,7 @@ struct Publisher { std::string topic;
 struct Subscriber {};
 struct NodeHandle {
   NodeHandle() {} explicit NodeHandle(const std::string&) {}
+  bool getParam(const std::string&, std::string& v) const { v.clear(); return false; }
   template <class T> bool param(const std::string& k, T& v, const T& dflt) const {
     auto& p = refstub::state().params; auto it = p.find(k); v = it == p.end() ? dflt : (T)it->second; return it != p.end(); }
   template <class M> Publisher advertise(const std::string& topic, unsigned) { Publisher p; p.topic = topic; return p; }
@@ -44,8 +47,10 @@ struct NodeHandle {
  private:
   static void reg(const std::string& topic, void (*cb)(const sensor_msgs::PointCloud2ConstPtr&)) { refstub::state().cloud_subs[topic] = cb; }
   static void reg(const std::string& topic, void (*cb)(const nav_msgs::Odometry::ConstPtr&)) { refstub::state().odom_subs[topic] = cb; }
+  static void reg(const std::string&, void (*)(const sensor_msgs::ImageConstPtr&)) {}
 };
 inline void init(int&, char**, const std::string&) {}
+namespace console { namespace levels { enum Level { Debug, Info, Warn, Error }; } inline bool set_logger_level(const char*, levels::Level) { return true; } }
 inline bool ok() { return refstub::state().next < refstub::state().deliveries.size(); }
 inline void spinOnce() { auto& s = refstub::state(); if (s.next < s.deliveries.size()) refstub::deliver(s.deliveries[s.next++]); }
 inline void spin() {}

@@ -233,6 +233,29 @@ def ref_color_frame(pts_cam, bgr, cam, q, t):
     return raw, filled, cc[: n.value], cw[: n.value], rgb[: n.value]
 
 
+def ref_mapnode_frame(pts_lidar, bgr, cam, q_lc, t_lc, q, t, stamp=1.0):
+    """The reference's colour-map NODE (mono_lidar_mapping/src/map_build_node.cc) as compiled from /root/reference: the
+    lidar-to-camera extrinsic, the lidar-frame cloud, the image and the camera pose go through the node's own handlers and
+    process() (:73-238), which transforms the cloud and calls MapBuilder::associateToMap.  Same outputs as ref_color_frame."""
+    R = ref_lib("color")
+    lib()
+    pts = _f32(pts_lidar)
+    img = np.ascontiguousarray(bgr, np.uint8)
+    npix = cam.width * cam.height
+    raw = np.zeros((cam.height, cam.width), np.uint8)
+    filled = np.zeros((cam.height, cam.width), np.uint8)
+    cc = np.zeros((npix, 3), np.float32)
+    cw = np.zeros((npix, 3), np.float32)
+    rgb = np.zeros((npix, 3), np.uint8)
+    n = C.c_int(0)
+    ext = Pose.make(q_lc, t_lc)
+    pose = Pose.make(q, t)
+    rc = R.ref_mapnode_frame(_p(pts), len(pts), pts.shape[1], _p(img), C.byref(cam), C.byref(ext), C.byref(pose), C.c_double(stamp),
+                             _p(raw), _p(filled), _p(cc), _p(cw), _p(rgb), npix, C.byref(n))
+    assert rc == 0, rc
+    return raw, filled, cc[: n.value], cw[: n.value], rgb[: n.value]
+
+
 _lib = None
 
 

@@ -115,3 +115,22 @@ def test_colour_frame_equals_reference_mapper(gpu_ctx_factory, kernel_type, blur
     assert np.array_equal(got["cloud_cam"].view(np.uint32), cc.view(np.uint32))
     assert np.array_equal(got["cloud_world"].view(np.uint32), cw.view(np.uint32))
     assert np.array_equal(got["rgb"], rgb)
+
+
+def test_colour_frame_equals_reference_node(gpu_ctx_factory):
+    """lmono_project_color with the lidar-to-camera transform beside the reference's colour-map node run through its own
+    handlers and process() (map_build_node.cc:73-238 + Map_Builder.cc:213-416): rows D1-D4 in one pass"""
+    _need("color")
+    from lmono_b200 import api
+    from test_oracle_vs_ref import colour_node_case
+    ctx = gpu_ctx_factory()
+    ocam = oracle_lib.make_camera()
+    gcam = api.Pinhole(ocam.fx, ocam.fy, ocam.cx, ocam.cy, 0, 0, 0, 0, ocam.width, ocam.height, 0, 5, 0)
+    pl, img, q_lc, t_lc, q, t, T = colour_node_case()
+    got = ctx.project_color(pl, img, gcam, q, t, T_cam_lidar=T)
+    raw, filled, cc, cw, rgb = oracle_lib.ref_mapnode_frame(pl, img, ocam, q_lc, t_lc, q, t)
+    assert np.array_equal(got["depth_raw"], raw) and np.array_equal(got["depth"], filled)
+    assert got["cloud_cam"].shape == cc.shape and len(cc) > 100000
+    assert np.array_equal(got["cloud_cam"].view(np.uint32), cc.view(np.uint32))
+    assert np.array_equal(got["cloud_world"].view(np.uint32), cw.view(np.uint32))
+    assert np.array_equal(got["rgb"], rgb)

@@ -195,3 +195,46 @@ def test_colour_mapper_oracle_equals_reference_source(oracle, kernel_type, kerne
     occ, ocw, orgb = oracle.lift_cloud(ofill, img, cam, q, t)
     assert cc.shape == occ.shape and len(cc) > 10000
     assert np.array_equal(cc.view(np.uint32), occ.view(np.uint32)) and np.array_equal(cw.view(np.uint32), ocw.view(np.uint32)) and np.array_equal(rgb, orgb)
+
+
+def _rot(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def colour_node_case(seed=3, n=120_000):
+    """lidar-frame cloud, KITTI-like lidar-to-camera extrinsic, image, camera pose; T = [rlc^T | -rlc^T tlc] (map_build_node.cc:216-221)"""
+    rng = np.random.default_rng(seed)
+    pc = np.zeros((n, 3), np.float32)
+    pc[:, 2] = rng.uniform(-5, 110, n)
+    pc[:, 0] = rng.uniform(-1, 1, n) * pc[:, 2] * 0.95
+    pc[:, 1] = rng.uniform(-0.3, 0.3, n) * pc[:, 2]
+    q_lc = np.array([0.5, -0.5, 0.5, 0.5]) + np.array([0.01, -0.02, 0.015, 0.0])
+    q_lc /= np.linalg.norm(q_lc)
+    t_lc = np.array([0.27, -0.08, -0.05])
+    rlc = _rot(q_lc)
+    pl = ((rlc @ pc.astype(np.float64).T).T + t_lc).astype(np.float32)
+    img = rng.integers(0, 255, (376, 1241, 3)).astype(np.uint8)
+    q = np.array([0.01, -0.02, 0.3, 0.95])
+    q /= np.linalg.norm(q)
+    t = np.array([10.0, -3.0, 1.5])
+    T = np.concatenate([rlc.T, (-rlc.T @ t_lc)[:, None]], axis=1)
+    return pl, img, q_lc, t_lc, q, t, T
+
+
+# map_build_node.cc:73-238: the colour-map NODE -- extrinsicHandler, the three buffers and their synchronisation in
+# process(), T = [rlc^T | -rlc^T tlc], the cloud transform, then MapBuilder::associateToMap (rows D1-D4 in one pass)
+def test_colour_node_oracle_equals_reference_source(oracle):
+    _need("color")
+    cam = oracle.make_camera()
+    pl, img, q_lc, t_lc, q, t, T = colour_node_case()
+    raw, filled, cc, cw, rgb = oracle_lib.ref_mapnode_frame(pl, img, cam, q_lc, t_lc, q, t)
+    oraw = oracle.project_raster(oracle.transform_cloud(pl, T), cam)
+    assert (raw > 0).sum() > 50000 and np.array_equal(raw, oraw)
+    ofill = oracle.depth_fill(oraw, cam)
+    assert np.array_equal(filled, ofill)
+    occ, ocw, orgb = oracle.lift_cloud(ofill, img, cam, q, t)
+    assert cc.shape == occ.shape and len(cc) > 100000
+    assert np.array_equal(cc.view(np.uint32), occ.view(np.uint32)) and np.array_equal(cw.view(np.uint32), ocw.view(np.uint32)) and np.array_equal(rgb, orgb)
