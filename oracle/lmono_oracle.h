@@ -13,8 +13,9 @@
  * Ceres, Eigen, OpenCV) are not installable here.  What pins this oracle:
  * (1) THE REFERENCE'S OWN SOURCES RUN HERE: `make ref` compiles the translation
  * units Aloam/src/scanRegistration.cpp, laserOdometry.cpp, laserMapping.cpp,
- * lidarFactor.hpp and mono_lidar_mapping/src/map_build_node.cc +
- * map_builder/Map_Builder.cc where they lie under /root/reference (a driver #includes
+ * lidarFactor.hpp, mono_lidar_mapping/src/map_build_node.cc +
+ * map_builder/Map_Builder.cc and camera_models/src/camera_models/Camera.cc +
+ * PinholeCamera.cc where they lie under /root/reference (a driver #includes
  * them, nothing is copied) against functional stand-ins for those libraries
  * (refstubs/), into oracle/_ref/; tests/test_oracle_vs_ref.py runs the nodes'
  * own callbacks / main loops beside this oracle: full cloud, curvature, labels
@@ -30,8 +31,7 @@
  * SelfAdjointEigenSolver / ColPivHouseholderQR, OpenCV 3.2 morphology / blur),
  * unpinned against those libraries' binaries; they are cross-checked against
  * scipy / numpy / cv2 and independent Python restatements in tests/
- * (test_oracle_primitives.py, test_oracle_*_python.py).  camodocal's
- * PinholeCamera.cc is pinned only this second way.
+ * (test_oracle_primitives.py, test_oracle_*_python.py).
  *
  * Every function cites the reference file:line it follows (paths relative to
  * /root/reference).

@@ -4,10 +4,12 @@
 // process() (map_build_node.cc:73-238: extrinsic handling, buffer synchronisation, T = [rlc^T | -rlc^T tlc], the cloud
 // transform call) and MapBuilder::associateToMap (Map_Builder.cc:213-334: projection raster with its implicit float ->
 // int and double -> uchar conversions, depthFill's sequence of morphology / blur calls with the configured kernels, the
-// per-pixel lift with its depth window and the |x| > 20 && y > 1.8 rule, the transform to the world frame).  OpenCV's
-// image operators, camodocal's pinhole model, cv_bridge and pcl::transformPointCloud underneath are stand-ins (the image
-// operators being the oracle's restatements of OpenCV).  main() is compiled but not run (it reads a yaml file through
-// cv::FileStorage); the driver sets the node's globals itself.
+// per-pixel lift with its depth window and the |x| > 20 && y > 1.8 rule, the transform to the world frame) and camodocal's
+// pinhole model, which lives in the reference tree too (camera_models/src/camera_models/Camera.cc + PinholeCamera.cc:
+// constructor, spaceToPlane, liftProjective with its 8-step undistortion, distortion).  OpenCV's image operators, cv_bridge
+// and pcl::transformPointCloud underneath are stand-ins (the image operators being the oracle's restatements of OpenCV).
+// main() and the calibration half of the camera model are compiled but not run (they go through cv::FileStorage /
+// calib3d, declaration-level stand-ins); the driver sets the node's globals itself.
 // Built by `make -C oracle ref` into oracle/_ref/libref_color.so only where /root/reference exists.
 #include <cmath>
 #include <math.h>
@@ -37,14 +39,24 @@ namespace this_thread { template <class D> void refstub_sleep_for(const D&) { th
 #include "map_build_node.cc"                  /* -I/root/reference/mono_lidar_mapping/src */
 #undef main
 #include "map_builder/Map_Builder.cc"
+#include "camera_models/Camera.cc"            /* -I/root/reference/camera_models/src */
+#include "camera_models/PinholeCamera.cc"
 #undef sleep_for
 #undef thread
 #undef fflush
 #undef fprintf
 #undef printf
 
+// CameraFactory.cc drags in every camera model of camodocal; only main() names the factory, and main() is not run
+namespace camodocal {
+boost::shared_ptr<CameraFactory> CameraFactory::m_instance;
+CameraFactory::CameraFactory() {}
+boost::shared_ptr<CameraFactory> CameraFactory::instance(void) { if (!m_instance) m_instance.reset(new CameraFactory()); return m_instance; }
+CameraPtr CameraFactory::generateCameraFromYamlFile(const std::string&) { return CameraPtr(); }
+}
+
 static void configure(const o_camera* cam) {
-  m_camera.reset(new camodocal::PinholeCamera(cam->fx, cam->fy, cam->cx, cam->cy, cam->k1, cam->k2, cam->p1, cam->p2));
+  m_camera.reset(new camodocal::PinholeCamera("cam0", cam->width, cam->height, cam->k1, cam->k2, cam->p1, cam->p2, cam->fx, cam->fy, cam->cx, cam->cy));
   KERNEL_SIZE = cam->kernel_size;
   KERNEL_TYPE = cam->kernel_type == 0 ? "FULL" : cam->kernel_type == 1 ? "CROSS" : "ELLIPSE";
   BLUR_TYPE = cam->blur_type == 0 ? "bilateral" : "gaussian";

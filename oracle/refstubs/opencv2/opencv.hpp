@@ -5,6 +5,7 @@
 // The colour-space conversions, cv::circle and applyColorMap only feed the two debug images: they keep sizes and types
 // and record their input (the first dilate of a frame sees the raw depth raster, applyColorMap the filled one).
 // Library stand-in, not reference source.
+#include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -14,11 +15,20 @@
 #include "lmono_oracle.h"
 #define CV_8UC1 0
 #define CV_8UC3 16
+#define CV_32F 5
+#define CV_64F 6
+#define CV_32FC1 5
+#define CV_32FC2 13
 typedef unsigned char uchar;                     /* OpenCV's cvdef.h declares it globally */
 namespace cv {
 using ::uchar;
-struct Size { int width, height; Size(int w = 0, int h = 0) : width(w), height(h) {} };
-struct Point2f { float x, y; Point2f(float x_ = 0, float y_ = 0) : x(x_), y(y_) {} };
+struct Size { int width, height; Size(int w = 0, int h = 0) : width(w), height(h) {} bool operator==(const Size& o) const { return width == o.width && height == o.height; } };
+template <class T> struct Point_ { T x, y; Point_(T x_ = 0, T y_ = 0) : x(x_), y(y_) {} template <class U> Point_(const Point_<U>& o) : x((T)o.x), y((T)o.y) {}
+  Point_ operator-(const Point_& o) const { return Point_(x - o.x, y - o.y); } Point_ operator+(const Point_& o) const { return Point_(x + o.x, y + o.y); } };
+typedef Point_<float> Point2f; typedef Point_<double> Point2d; typedef Point_<int> Point2i;
+template <class T> struct Point3_ { T x, y, z; Point3_(T x_ = 0, T y_ = 0, T z_ = 0) : x(x_), y(y_), z(z_) {} };
+typedef Point3_<float> Point3f; typedef Point3_<double> Point3d;
+template <class T> inline double norm(const Point_<T>& p) { return std::sqrt((double)p.x * p.x + (double)p.y * p.y); }
 struct Scalar { double v[4]; Scalar(double a = 0, double b = 0, double c = 0, double d = 0) { v[0] = a; v[1] = b; v[2] = c; v[3] = d; } };
 struct Vec3b { uchar v[3]; uchar& operator[](int i) { return v[i]; } const uchar& operator[](int i) const { return v[i]; } };
 class Mat {
@@ -27,6 +37,10 @@ class Mat {
   std::shared_ptr<std::vector<uchar>> buf;                           // header copies share the pixels, clone() does not
   Mat() {}
   Mat(int r, int c, int type) : rows(r), cols(c), type_(type), buf(std::make_shared<std::vector<uchar>>((std::size_t)r * c * (type == CV_8UC3 ? 3 : 1), 0)) {}
+  Mat(Size s, int type) : Mat(s.height, s.width, type) {}
+  static Mat eye(int r, int c, int type) { return Mat(r, c, type); }          // declaration-level (calibration code only)
+  template <class T> T& at(int i) { return *reinterpret_cast<T*>(buf->data() + (std::size_t)i * sizeof(T)); }
+  template <class T> const T& at(int i) const { return *reinterpret_cast<const T*>(buf->data() + (std::size_t)i * sizeof(T)); }
   static Mat zeros(Size s, int type) { return Mat(s.height, s.width, type); }
   static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }
   int channels() const { return type_ == CV_8UC3 ? 3 : 1; }
@@ -38,9 +52,24 @@ class Mat {
   template <class T> const T& at(int r, int c) const { return *reinterpret_cast<const T*>(buf->data() + ((std::size_t)r * cols + c) * sizeof(T)); }
 };
 enum { COLOR_BGR2HSV = 40, COLOR_HSV2BGR = 54, COLORMAP_JET = 2 };
-// declaration-level: the node reads its yaml configuration through these in main(), which the tests do not run
-struct FileNode { template <class T> void operator>>(T&) const {} };
-struct FileStorage { enum { READ = 0 }; FileStorage(const std::string&, int) {} bool isOpened() const { return false; } FileNode operator[](const char*) const { return FileNode(); } };
+// declaration-level: yaml configuration and the calibration tool chain (camodocal's estimateIntrinsics / undistortion maps,
+// the nodes' main()), none of which the tests run
+struct FileNode { template <class T> void operator>>(T&) const {} FileNode operator[](const char*) const { return FileNode(); } bool isNone() const { return true; }
+  operator int() const { return 0; } operator double() const { return 0.0; } operator std::string() const { return std::string(); } };
+struct FileStorage { enum { READ = 0, WRITE = 1 }; FileStorage(const std::string&, int) {} bool isOpened() const { return false; } void release() {}
+  FileNode operator[](const char*) const { return FileNode(); } FileNode operator[](const std::string&) const { return FileNode(); } };
+template <class T> inline FileStorage& operator<<(FileStorage& f, const T&) { return f; }
+struct _OutputArray { bool needed() const { return false; } void create(int, int, int) const {} Mat getMat() const { return Mat(); } };
+typedef const _OutputArray& OutputArray; typedef const _OutputArray& InputArray;
+inline _OutputArray noArray() { return _OutputArray(); }
+enum { DECOMP_LU = 0, DECOMP_NORMAL = 16 };
+template <class A, class B, class C, class D> inline bool solvePnP(const A&, const B&, const C&, const D&, Mat&, Mat&) { return false; }
+inline bool solve(const Mat&, const Mat&, Mat&, int) { return false; }
+template <class A, class B> inline Mat findHomography(const A&, const B&) { return Mat(3, 3, CV_64F); }
+inline void Rodrigues(const Mat&, Mat&) {}
+inline void convertMaps(const Mat&, const Mat&, Mat&, Mat&, int, bool) {}
+template <class E> inline void cv2eigen(const Mat&, E&) {}
+template <class E> inline void eigen2cv(const E&, Mat&) {}
 enum { MORPH_RECT = 0, MORPH_CROSS = 1, MORPH_ELLIPSE = 2 };
 enum { MORPH_ERODE = 0, MORPH_DILATE = 1, MORPH_OPEN = 2, MORPH_CLOSE = 3 };
 namespace refstub_cv { struct Log { std::vector<Mat> dilate_inputs; Mat colormap_input; }; inline Log& log() { static Log l; return l; } }
