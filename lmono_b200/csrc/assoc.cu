@@ -470,7 +470,10 @@ __device__ __forceinline__ void d_knn5_group(const float4* __restrict__ cellpts,
 // only.  Same candidate set, same 64-bit (d2, canonical index) ranking, hence the same neighbours bit for bit.
 // Per axis: c0 = (floor(q) - 1) >> 1, cube q0 = floor((c0 + 12) / 25), r0 = c0 + 12 - 25 q0 in [0, 24]; cell c0 is local
 // r0 + 1 of cube q0 (and ALSO local 0 of cube q0 + 1 when r0 == 24), c1 = c0 + 1 likewise.
-constexpr int KNN1_THREADS = 128;
+#ifndef LM_KNN1_THREADS
+#define LM_KNN1_THREADS 128
+#endif
+constexpr int KNN1_THREADS = LM_KNN1_THREADS;
 constexpr int KNN1_SLOTS = 12;
 
 __device__ __forceinline__ void d_axis_split(float q, int* q0, int* r0) {
@@ -629,7 +632,10 @@ __global__ void __launch_bounds__(256, 4) k_assoc_knn(LmMapState* __restrict__ s
   d_assoc_knn<GROUP>(st, M0, M1, slot_valid_rank, stack0, stack1, nnref);
 }
 
-__global__ void __launch_bounds__(128) k_assoc_fit(const LmMapState* __restrict__ st, LmMapType M0, LmMapType M1,
+#ifndef LM_FIT_THREADS
+#define LM_FIT_THREADS 128
+#endif
+__global__ void __launch_bounds__(LM_FIT_THREADS) k_assoc_fit(const LmMapState* __restrict__ st, LmMapType M0, LmMapType M1,
                                                    const float4* __restrict__ stack0, const float4* __restrict__ stack1,
                                                    const int32_t* __restrict__ nnref,
                                                    LmFactor* __restrict__ fac0, LmFactor* __restrict__ fac1) {
@@ -672,7 +678,7 @@ int lm_map_associate(lmono_ctx* ctx, int n_max_corner, int n_max_surf) {
   else LM_LAUNCH_PDL(k_assoc_knn<8>, lm_div_up(nq * 8, 256), 256, 0, KNN_ARGS);
   LM_LAUNCH_CHECK();
   }
-  LM_LAUNCH_PDL(k_assoc_fit, lm_div_up(nq, 128), 128, 0, ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_stack[0], ctx->d_stack[1],
+  LM_LAUNCH_PDL(k_assoc_fit, lm_div_up(nq, LM_FIT_THREADS), LM_FIT_THREADS, 0, ctx->d_state, ctx->map[0], ctx->map[1], ctx->d_stack[0], ctx->d_stack[1],
                                                           ctx->d_nnref, ctx->d_fac[0], ctx->d_fac[1]);
   LM_LAUNCH_CHECK();
   return LMONO_OK;
