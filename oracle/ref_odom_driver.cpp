@@ -71,6 +71,7 @@ extern "C" void ref_odom_reset(void) {
   para_q[0] = para_q[1] = para_q[2] = 0; para_q[3] = 1; para_t[0] = para_t[1] = para_t[2] = 0;
   laserCloudCornerLast.reset(new pcl::PointCloud<PointType>()); laserCloudSurfLast.reset(new pcl::PointCloud<PointType>());
   laserCloudCornerLastNum = laserCloudSurfLastNum = 0;
+  corner_correspondence = plane_correspondence = 0;
   while (!cornerSharpBuf.empty()) cornerSharpBuf.pop();
   while (!cornerLessSharpBuf.empty()) cornerLessSharpBuf.pop();
   while (!surfFlatBuf.empty()) surfFlatBuf.pop();

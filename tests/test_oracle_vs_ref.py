@@ -238,3 +238,84 @@ def test_colour_node_oracle_equals_reference_source(oracle):
     occ, ocw, orgb = oracle.lift_cloud(ofill, img, cam, q, t)
     assert cc.shape == occ.shape and len(cc) > 100000
     assert np.array_equal(cc.view(np.uint32), occ.view(np.uint32)) and np.array_equal(cw.view(np.uint32), ocw.view(np.uint32)) and np.array_equal(rgb, orgb)
+
+
+# ---------------------------------------------------------------------------------------------------- edge cases
+def _edge_sweeps():
+    w = synth.make_world()
+    rng = np.random.default_rng(1)
+    q, t = synth.loop_pose(w, 4.0)
+    raw = synth.raycast_sweep(w, q, t, 64, 1875, rng)
+    az = np.arctan2(raw[:, 1], raw[:, 0])
+    el = np.degrees(np.arctan2(raw[:, 2], np.hypot(raw[:, 0], raw[:, 1])))
+    keep = np.ones(len(raw), bool)
+    keep[np.where((el > -3) & (el < -1))[0][5:]] = False
+    raw16 = synth.raycast_sweep(w, q, t, 16, 1800, rng)
+    lifted = raw16.copy()
+    lifted[::50, 2] += 30.0
+    raw32 = synth.raycast_sweep(w, q, t, 32, 1875, rng)
+    return {
+        "partial azimuth (start / end orientation fix-ups)": (raw[(az > -1.0) & (az < 1.2)], 64, 5.0),
+        "every 7th point (wide gaps)": (raw[::7], 64, 5.0),
+        "rings with fewer than six points (:279)": (raw[keep], 64, 5.0),
+        "reversed point order": (raw[::-1].copy(), 64, 5.0),
+        "elevations outside the ring rule (:169-200)": (lifted, 16, 0.3),
+        "sweep starting mid-revolution (halfPassed)": (np.roll(raw32, 20000, axis=0), 32, 0.3),
+        "duplicated points (zero gaps, curvature ties)": (np.concatenate([raw16[:3000], raw16[:3000]]), 16, 0.3),
+    }
+
+
+@pytest.mark.parametrize("case", list(_edge_sweeps().keys()) if oracle_lib.ref_lib("scanreg") is not None else [])
+def test_scan_registration_edge_cases_oracle_equals_reference_source(oracle, case):
+    raw, n_scans, min_range = _edge_sweeps()[case]
+    ref = oracle_lib.ref_scan_register(raw, n_scans, min_range)
+    ora = oracle.scan_register(raw, n_scans, min_range, voxel_order_mode=1, sort_mode=1)
+    assert len(ref["full"]) > 1000
+    for k in ("full", "labels", "sharp", "less_sharp", "flat", "less_flat"):
+        assert ref[k].shape == ora[k].shape and np.array_equal(_bits(ref[k]), _bits(ora[k])), (case, k)
+    assert np.array_equal(_bits(ref["curvature"][5:-5]), _bits(ora["curvature"][5:-5]))
+
+
+def test_odometry_few_and_no_features_oracle_equals_reference_source(oracle):
+    _need("odom")
+    w = synth.make_world()
+    rng = np.random.default_rng(2)
+    ref = oracle_lib.RefOdometry()
+    od = oracle.Odometry()
+    for k in range(5):
+        q, t = synth.loop_pose(w, 1.0 * k)
+        f = oracle.scan_register(synth.raycast_sweep(w, q, t, 16, 900, rng), 16, 0.3)
+        ns, nf = (len(f["sharp"]), len(f["flat"])) if k < 2 else ((6, 9) if k < 4 else (0, 0))       # "less correspondence!" (:487-490), then an empty problem
+        a = (f["sharp"][:ns], f["less_sharp"], f["flat"][:nf], f["less_flat"])
+        (lq, lt), (wq, wt), rep = od.step(*a)
+        (rlq, rlt), (rwq, rwt), cnt = ref.step(*a, f["full"])
+        assert [int(cnt[0]), int(cnt[1])] == [rep.corner_corr[1], rep.plane_corr[1]], k
+        assert np.abs(np.r_[lq, lt, wq, wt] - np.r_[rlq, rlt, rwq, rwt]).max() <= 1e-12, k
+    od.close()
+
+
+def test_mapping_sparse_map_and_outside_grid_oracle_equals_reference_source(oracle):
+    """:554 gate (fewer than 10 corner / 50 surf map points: no optimisation), then a pose 3 km away and 400 m down: every
+    point of the sweep falls outside the 21 x 21 x 11 grid (:752-757) and the centre index runs far out of [3, dim - 4]"""
+    _need("mapping")
+    import scenario
+    rm = oracle_lib.RefMapper()
+    om = oracle.Mapper(order_mode=1, use_kdtree=1)
+    opt = []
+    for k, (c, s, qg, tg, qo, to) in enumerate(scenario.sweeps(6, n_corner=1500, n_surf=9000)):
+        if k < 2:
+            c, s = c[:8], s[:40]
+        if k == 4:
+            to = to + np.array([3000.0, 0.0, 0.0])
+        if k == 5:
+            to = to + np.array([0.0, 0.0, -400.0])
+        rq, rt, _, rcen, _ = rm.step(c, s, qo, to)
+        q, t, rep, _ = om.step(c, s, qo, to)
+        assert rcen == om.get_state()[2], k
+        assert np.abs(np.r_[q, t] - np.r_[rq, rt]).max() <= 1e-11, k
+        for which in (0, 1):
+            a, b = rm.export(which), om.export(which, 1)
+            assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), (k, which)
+        opt.append(int(rep.optimized))
+    assert opt == [0, 0, 1, 1, 0, 0]
+    om.close()
