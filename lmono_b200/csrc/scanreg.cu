@@ -70,10 +70,73 @@ __device__ __forceinline__ int d_ring_of(float x, float y, float z, int n_scans)
   return scanID;
 }
 
-__device__ __forceinline__ float d_neg_atan2f(float y, float x) {
-  // std::atan2(float, float): evaluated in double and rounded once (CUDA's atan2f is 3 ulp)
-  return -(float)atan2((double)y, (double)x);
+// std::atan2(float, float) of the reference's platform: glibc's atan2f / atanf up to 2.40 are the fdlibm float routines
+// (argument reduction against atan(0.5), atan(1), atan(1.5), atan(inf) split in hi + lo parts, an 11-term odd
+// polynomial), under 1 ulp but NOT correctly rounded.  The azimuth feeds discrete decisions (:211-233: which side of
+// startOri - pi/2, endOri + pi/2 ... a point falls on), where one ulp flips relTime by a whole revolution, so the device
+// evaluates the same float operations in the same order and returns the same bits (checked against glibc 2.39 on 6e8
+// arguments on the host; -fmad=false and the explicit _rn intrinsics keep every product and sum separately rounded).
+__device__ __forceinline__ float d_atanf_fdlibm(float x) {
+  const uint32_t hx = __float_as_uint(x), ix = hx & 0x7fffffffu;
+  const float hi3 = 1.5707962513e+00f, lo3 = 7.5497894159e-08f;
+  int id;
+  if (ix >= 0x4c000000u) { if (ix > 0x7f800000u) return __fadd_rn(x, x); return (hx >> 31) ? __fsub_rn(-hi3, lo3) : __fadd_rn(hi3, lo3); }
+  if (ix < 0x3ee00000u) { if (ix < 0x31000000u) return x; id = -1; }
+  else {
+    x = fabsf(x);
+    if (ix < 0x3f980000u) {
+      if (ix < 0x3f300000u) { id = 0; x = __fdiv_rn(__fsub_rn(__fmul_rn(2.0f, x), 1.0f), __fadd_rn(2.0f, x)); }
+      else { id = 1; x = __fdiv_rn(__fsub_rn(x, 1.0f), __fadd_rn(x, 1.0f)); }
+    } else {
+      if (ix < 0x401c0000u) { id = 2; x = __fdiv_rn(__fsub_rn(x, 1.5f), __fadd_rn(1.0f, __fmul_rn(1.5f, x))); }
+      else { id = 3; x = __fdiv_rn(-1.0f, x); }
+    }
+  }
+  const float z = __fmul_rn(x, x), w = __fmul_rn(z, z);
+  float a = 1.6285819933e-02f;                        // odd terms: aT[10], [8], [6], [4], [2], [0]
+  a = __fadd_rn(4.9768779427e-02f, __fmul_rn(w, a));
+  a = __fadd_rn(6.6610731184e-02f, __fmul_rn(w, a));
+  a = __fadd_rn(9.0908870101e-02f, __fmul_rn(w, a));
+  a = __fadd_rn(1.4285714924e-01f, __fmul_rn(w, a));
+  a = __fadd_rn(3.3333334327e-01f, __fmul_rn(w, a));
+  const float s1 = __fmul_rn(z, a);
+  float b = -3.6531571299e-02f;                       // even terms: aT[9], [7], [5], [3], [1]
+  b = __fadd_rn(-5.8335702866e-02f, __fmul_rn(w, b));
+  b = __fadd_rn(-7.6918758452e-02f, __fmul_rn(w, b));
+  b = __fadd_rn(-1.1111110449e-01f, __fmul_rn(w, b));
+  b = __fadd_rn(-2.0000000298e-01f, __fmul_rn(w, b));
+  const float s2 = __fmul_rn(w, b);
+  const float xs = __fmul_rn(x, __fadd_rn(s1, s2));
+  if (id < 0) return __fsub_rn(x, xs);
+  const float hi = id == 0 ? 4.6364760399e-01f : id == 1 ? 7.8539812565e-01f : id == 2 ? 9.8279368877e-01f : hi3;
+  const float lo = id == 0 ? 5.0121582440e-09f : id == 1 ? 3.7748947079e-08f : id == 2 ? 3.4473217170e-08f : lo3;
+  const float r = __fsub_rn(hi, __fsub_rn(__fsub_rn(xs, lo), x));
+  return (hx >> 31) ? -r : r;
 }
+__device__ __forceinline__ float d_atan2f_fdlibm(float y, float x) {
+  const float tiny = 1.0e-30f, pi_o_4 = 7.8539818525e-01f, pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f, pi_lo = -8.7422776573e-08f;
+  const uint32_t hx = __float_as_uint(x), hy = __float_as_uint(y), ix = hx & 0x7fffffffu, iy = hy & 0x7fffffffu;
+  if (ix > 0x7f800000u || iy > 0x7f800000u) return __fadd_rn(x, y);
+  if (hx == 0x3f800000u) return d_atanf_fdlibm(y);
+  const int m = (int)((hy >> 31) & 1u) | (int)((hx >> 30) & 2u);          // 2 sign(x) + sign(y)
+  if (iy == 0) return m < 2 ? y : (m == 2 ? __fadd_rn(pi, tiny) : __fsub_rn(-pi, tiny));
+  if (ix == 0) return (hy >> 31) ? __fsub_rn(-pi_o_2, tiny) : __fadd_rn(pi_o_2, tiny);
+  if (ix == 0x7f800000u) {
+    if (iy == 0x7f800000u) return m == 0 ? __fadd_rn(pi_o_4, tiny) : m == 1 ? __fsub_rn(-pi_o_4, tiny) : m == 2 ? __fadd_rn(__fmul_rn(3.0f, pi_o_4), tiny) : __fsub_rn(__fmul_rn(-3.0f, pi_o_4), tiny);
+    return m == 0 ? 0.0f : m == 1 ? -0.0f : m == 2 ? __fadd_rn(pi, tiny) : __fsub_rn(-pi, tiny);
+  }
+  if (iy == 0x7f800000u) return (hy >> 31) ? __fsub_rn(-pi_o_2, tiny) : __fadd_rn(pi_o_2, tiny);
+  const int k = ((int)iy - (int)ix) >> 23;
+  float z;
+  if (k > 60) z = __fadd_rn(pi_o_2, __fmul_rn(0.5f, pi_lo));
+  else if ((hx >> 31) && k < -60) z = 0.0f;
+  else z = d_atanf_fdlibm(fabsf(__fdiv_rn(y, x)));
+  if (m == 0) return z;
+  if (m == 1) return __uint_as_float(__float_as_uint(z) ^ 0x80000000u);
+  if (m == 2) return __fsub_rn(pi, __fsub_rn(z, pi_lo));
+  return __fsub_rn(__fsub_rn(z, pi_lo), pi);
+}
+__device__ __forceinline__ float d_neg_atan2f(float y, float x) { return -d_atan2f_fdlibm(y, x); }
 
 __global__ void __launch_bounds__(SC_THREADS) k_scan_classify(const float4* __restrict__ in, int n, int n_scans, float thres,
                                                               int32_t* __restrict__ key, int32_t* __restrict__ block_hist, int nb,

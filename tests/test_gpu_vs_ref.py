@@ -34,7 +34,9 @@ def test_scan_register_equals_reference_node(gpu_ctx_factory, n_scans, min_range
         assert got["full"].shape == ref["full"].shape and len(ref["full"]) > 10000
         assert np.array_equal(got["full"][:, :3].view(np.uint32), ref["full"][:, :3].view(np.uint32))
         assert np.array_equal(np.floor(got["full"][:, 3]), np.floor(ref["full"][:, 3]))                 # ring ids
-        assert np.abs(got["full"][:, 3] - ref["full"][:, 3]).max() <= 4e-6                              # 0.1 relTime: atan2f of libm vs the device's
+        dI = float(np.abs(got["full"][:, 3] - ref["full"][:, 3]).max())
+        print(f"{n_scans} rings: max |d intensity| vs the reference node {dI:.2e}")
+        assert dI <= 4e-6                                                                                # 0.1 relTime
         assert np.array_equal(got["curvature"][5:-5].view(np.uint32), ref["curvature"][5:-5].view(np.uint32))
         assert np.array_equal(got["labels"], ref["labels"])
         for k in ("sharp", "less_sharp", "flat"):
@@ -134,3 +136,31 @@ def test_colour_frame_equals_reference_node(gpu_ctx_factory):
     assert np.array_equal(got["cloud_cam"].view(np.uint32), cc.view(np.uint32))
     assert np.array_equal(got["cloud_world"].view(np.uint32), cw.view(np.uint32))
     assert np.array_equal(got["rgb"], rgb)
+
+
+def test_scan_register_edge_cases_equal_reference_node(gpu_ctx_factory):
+    """partial / sparse / reversed sweeps, rings under six points, out-of-range elevations, a sweep starting mid-revolution:
+    the CUDA path beside the reference's laserCloudHandler (the duplicated-point case of the CPU test is left out: exact
+    curvature ties are where the reference's unstable std::sort is not well defined, DESIGN.md section 2)"""
+    _need("scanreg")
+    from test_oracle_vs_ref import _edge_sweeps
+    ctxs = {}
+    for case, (raw, n_scans, min_range) in _edge_sweeps().items():
+        if case.startswith("duplicated"):
+            continue
+        if n_scans not in ctxs:
+            ctxs[n_scans] = gpu_ctx_factory(scan_line=n_scans, minimum_range=min_range, max_cubes_corner=8, max_cubes_surf=8,
+                                            cube_capacity_corner=1024, cube_capacity_surf=1024)
+        got = ctxs[n_scans].scan_register(raw, want_debug=True)
+        ref = oracle_lib.ref_scan_register(raw, n_scans, min_range)
+        assert got["full"].shape == ref["full"].shape, case
+        assert np.array_equal(got["full"][:, :3].view(np.uint32), ref["full"][:, :3].view(np.uint32)), case
+        assert np.array_equal(np.floor(got["full"][:, 3]), np.floor(ref["full"][:, 3])), case
+        # ring + 0.1 relTime bit for bit: the device evaluates atan2f the way the reference's libm does (scanreg.cu d_atan2f_fdlibm);
+        # a correctly rounded atan2 differs in the last bit often enough to flip a whole-revolution wrap at :211-233 now and then
+        assert np.array_equal(got["full"][:, 3].view(np.uint32), ref["full"][:, 3].view(np.uint32)), (case, np.abs(got["full"][:, 3] - ref["full"][:, 3]).max())
+        assert np.array_equal(got["curvature"][5:-5].view(np.uint32), ref["curvature"][5:-5].view(np.uint32)), case
+        assert np.array_equal(got["labels"], ref["labels"]), case
+        for k in ("sharp", "less_sharp", "flat"):
+            assert got[k].shape == ref[k].shape and np.array_equal(got[k][:, :3].view(np.uint32), ref[k][:, :3].view(np.uint32)), (case, k)
+        assert got["less_flat"].shape == ref["less_flat"].shape and np.abs(got["less_flat"] - ref["less_flat"]).max() <= 3e-5, case
