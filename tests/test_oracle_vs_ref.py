@@ -72,6 +72,28 @@ def test_factors_and_solve_oracle_equals_reference_functors(oracle):
         assert abs(s.final_cost - rs.final_cost) <= 1e-12 * s.final_cost
 
 
+# the same with interpolation ratios s in (0, 1] on the edge factors: lidarFactor.hpp:27-34, q_last_curr = Identity.slerp(s, q),
+# t_last_curr = s t -- the factor arithmetic of `#define DISTORTION 1`, evaluated by the reference functor on dual numbers
+def test_interpolated_edge_factors_oracle_equals_reference_functors(oracle):
+    _need("odom")
+    from test_oracle_primitives import _random_factors
+    rng = np.random.default_rng(23)
+    for trial in range(3):
+        f = _random_factors(oracle, rng, 200)
+        f = f[f["type"] == 0]
+        f["s"] = rng.uniform(0.05, 1.0, len(f))
+        q0 = np.array([0.03, -0.02, 0.025, 1.0]) * np.r_[rng.uniform(0.5, 1.5, 3), 1.0]
+        q0 /= np.linalg.norm(q0)
+        t0 = rng.uniform(-0.2, 0.2, 3)
+        H, g, c = oracle.normal_eq(f, q0, t0)
+        rH, rg, rc = oracle_lib.ref_normal_eq(f, q0, t0)
+        assert np.abs(H - rH).max() <= 1e-13 * np.abs(H).max() and np.abs(g - rg).max() <= 1e-13 * np.abs(g).max() and abs(c - rc) <= 1e-13 * c
+        q, t, s_ = oracle.lm_solve(f, q0, t0, 4)
+        rq, rt, rs = oracle_lib.ref_lm_solve(f, q0, t0, 4)
+        assert (s_.iterations, s_.num_successful, s_.termination) == (rs.iterations, rs.num_successful, rs.termination), trial
+        assert np.abs(q - rq).max() <= 1e-14 and np.abs(t - rt).max() <= 1e-14
+
+
 # laserOdometry.cpp:220-598, the node's own loop over consecutive HDL-32 sweeps: TransformToStart, the two
 # correspondence searches with their ring-window scans, factor construction (LidarEdgeFactor / LidarPlaneFactor), two
 # solves per sweep, pose accumulation, buffer swap
